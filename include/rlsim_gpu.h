@@ -1,0 +1,171 @@
+/* include/rlsim_gpu.h - C ABI of librlsim_gpu.so, the B200 implementation of rlsim's
+ * library-construction hot path.
+ *
+ * The reference (sbotond/rlsim, Go) has no FFI boundary; its seams are the Go interfaces wired in
+ * main() (/root/reference/src/main.go:88-152).  The GPU path plugs in at the two *batch* methods
+ *     Pooler.InitTranscripts    (/root/reference/src/pool.go:83-135)
+ *     Sampler.SampleFragments   (/root/reference/src/sampler.go:108-154)
+ * and this header declares exactly what a cgo shim implementing those two methods binds
+ * (INTEGRATION.md shows the Go side).  Plain pointers and sizes only; every input buffer is
+ * caller-owned and only read during the call (cgo pointer rules); outputs are copied into
+ * caller-provided buffers.  All functions return 0 on success or an RLSIM_E_* code; the text of
+ * the last error is available from rlsim_last_error() - the Go shim turns any non-zero code into
+ * L.Fatalf, the reference's only error policy (/root/reference/src/logging.go:67-73).
+ *
+ * Threading: one handle = one GPU = one host thread at a time.  No callbacks.
+ */
+#ifndef RLSIM_GPU_H
+#define RLSIM_GPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLSIM_MAX_COMPS 8
+
+/* error codes; the overflow ones carry the reference's own messages */
+enum {
+    RLSIM_OK = 0,
+    RLSIM_E_CUDA = 1,         /* CUDA runtime failure */
+    RLSIM_E_ARG = 2,          /* invalid argument / call order */
+    RLSIM_E_PRIMING = 3,      /* "Error when simulating priming!"                          nnthermo.go:213 */
+    RLSIM_E_PCR_OVERFLOW = 4, /* "Integer overflow detected when amplifying fragments!"    thermocycler.go:142-144 */
+    RLSIM_E_POOL_OVERFLOW = 5,/* "Integer overflow when updating total fragment count!"    fragstats.go:88-94 */
+    RLSIM_E_UNSUPPORTED = 6,  /* outside the GPU path's limits (documented in DESIGN.md) */
+    RLSIM_E_NOMEM = 7
+};
+
+/* fragmentation methods, /root/reference/src/fragmentor.go:39-60 */
+enum { RLSIM_AFTER_PRIM = 0, RLSIM_AFTER_PRIM_DOUBLE = 1, RLSIM_AFTER_NOPRIM = 2, RLSIM_AFTER_NOPRIM_DOUBLE = 3,
+       RLSIM_PRE_PRIM = 4, RLSIM_PRIM_JUMP = 5 };
+/* mixture component types, /root/reference/src/target_mix.go:61-67 */
+enum { RLSIM_COMP_N = 0, RLSIM_COMP_SN = 1, RLSIM_COMP_G = 2 };
+
+/* one "w:type:(loc, scale[, shape], low, high)" component, target_mix.go:37-44 */
+typedef struct {
+    int32_t type;
+    int32_t reserved;
+    double weight, location, scale, shape;
+    uint64_t low, high;
+} rlsim_mixcomp;
+
+/* Everything NewFragmentor / NewTechne / NewTarget / NewLenSampler receive in main.go:98-127. */
+typedef struct {
+    int32_t kmer_len;        /* -k   args.go:107 */
+    int32_t frag_method;     /* -f   args.go:277-307 */
+    int32_t frag_param;      /*      method:param */
+    int32_t nr_cycles;       /* -c */
+    double priming_temp;     /* -p */
+    double frag_loss_prob;   /* -flg fragfilter.go:45 */
+    double fixed_eff;        /* -e   thermocycler.go:134-137 */
+    double strand_bias;      /* -b   sampler.go:219-227 (probability of "-") */
+    int32_t gc_mode;         /* 0 = parametric -eg (thermocycler.go:173-177), 1 = raw table (:169-171) */
+    int32_t n_target;        /* components of -d; 0 = raw target (-j), see rlsim_set_raw_target */
+    int32_t n_polya;         /* components of -a */
+    int32_t reserved;
+    double gc_shape, gc_min, gc_max;
+    double gc_raw[101];      /* after ProcessRawGcEffs, thermocycler.go:94-104 */
+    double len_shape, len_min, len_max; /* -el; used only when no length-efficiency table is supplied */
+    rlsim_mixcomp target[RLSIM_MAX_COMPS];
+    rlsim_mixcomp polya[RLSIM_MAX_COMPS];
+    int64_t seed_init, seed_pcr, seed_sampling; /* -si -sp -ss; 0 = not given (main.go:72-81,129-149) */
+} rlsim_params;
+
+/* per-run scalar results (fragstats.go:45-56 totals + bookkeeping) */
+typedef struct {
+    uint64_t n_transcripts;     /* records added (expression 0 included) */
+    uint64_t n_molecules;       /* sum of expression levels */
+    uint64_t n_fragments;       /* fragments kept by fragmentation (sum of "after fragmentation") */
+    uint64_t n_species;         /* distinct (transcript,start,end) */
+    uint64_t pool_total;        /* FragStats.TotalFrags */
+    uint64_t n_requested;       /* Targeter.GetReqFrags */
+    uint64_t n_sampled;         /* fragments in the result of rlsim_sample */
+    uint64_t low, high;         /* Targeter.GetLow / GetHigh */
+    uint32_t polya_max;         /* pool.go:84 */
+    uint32_t reserved;
+} rlsim_stats;
+
+/* histogram kinds (fragstats.go:45-56); every histogram is indexed by length */
+enum { RLSIM_H_TARGET = 0, RLSIM_H_POLYA = 1, RLSIM_H_AFTER_FRAG = 2, RLSIM_H_AFTER_PCR = 3, RLSIM_H_SAMPLED = 4,
+       RLSIM_H_MISSING = 5, RLSIM_H_AFTER_SAMPLING = 6 };
+
+typedef struct rlsim_handle rlsim_handle;
+
+/* ---- lifecycle: NewPool (pool.go:66-81) / Pool.Cleanup (pool.go:210-221) ---- */
+int rlsim_create(int device, rlsim_handle **out);
+void rlsim_destroy(rlsim_handle *h);
+const char *rlsim_last_error(const rlsim_handle *h);   /* h may be NULL: error of a failed rlsim_create */
+
+/* ---- model: NewFragmentor + NewTechne + NewLenSampler (main.go:98-123) ----
+ * len_eff: Techne.CalcLengthEff(l) for l = low..high (thermocycler.go:149-156), filled by the host with
+ * the same code that fills the report so both agree bit for bit; NULL = computed on the device from
+ * len_shape/min/max with the library's restatement of Go's math.Pow. */
+int rlsim_set_model(rlsim_handle *h, const rlsim_params *p);
+int rlsim_set_len_eff(rlsim_handle *h, const double *len_eff, uint64_t low, uint64_t high);
+/* raw (-j) target, parse_raw.go:83-104: lengths and normalised probabilities */
+int rlsim_set_raw_target(rlsim_handle *h, const uint32_t *lengths, const double *probs, uint32_t n);
+
+/* ---- Targeter (target.go:102-132 / raw_target.go:104-138) ----
+ * Either draw the req_frags target lengths on the device ... */
+int rlsim_sample_target(rlsim_handle *h, int64_t req_frags);
+/* ... or impose the histogram the host's own Targeter sampled (NextLenCount pairs). */
+int rlsim_set_target_hist(rlsim_handle *h, const uint32_t *lengths, const uint64_t *counts, uint32_t n);
+
+/* ---- Pooler.InitTranscripts (pool.go:83-135) ----
+ * add_transcripts replaces the `chan *Transcript` loop (input.go:103-124): `bases` = concatenated
+ * upper-cased sequences (no poly-A), offsets[n+1] into it, expr[n] = expression levels with -m applied.
+ * May be called repeatedly (batches).  first_index = global index of the first record of this process's
+ * shard (0 on a single GPU); it keys the per-transcript random streams so any sharding reproduces the
+ * same fragments. */
+int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t *offsets, const uint64_t *expr,
+                          uint32_t n);
+int rlsim_set_first_index(rlsim_handle *h, uint32_t first_index);
+/* fragment every molecule (transcript.go:139-150 + fragmentor.go), collapse identical fragments into species
+ * (transcript.go:156-215), amplify (thermocycler.go:106-147) and build the per-length pool (pool.go:156-189). */
+int rlsim_build_library(rlsim_handle *h);
+/* the two halves of build_library, for tests and profiling */
+int rlsim_fragment(rlsim_handle *h);
+int rlsim_pcr(rlsim_handle *h);
+
+/* ---- Sampler.SampleFragments (sampler.go:108-154) ----
+ * class_totals: this GPU's pooled copies per length, T_r[l], l = 0..n_len-1 (n_len = high+1).
+ * sample: global totals and this rank's base offset per length (single GPU: totals = class_totals, base = NULL).
+ * Multi-GPU: the caller all-gathers class_totals (the only data that crosses NVLink) and passes
+ * totals[l] = sum_r T_r[l], base[l] = sum_{r' < rank} T_r'[l]. */
+int rlsim_class_totals(rlsim_handle *h, uint64_t *totals, uint32_t n_len);
+int rlsim_sample(rlsim_handle *h, const uint64_t *global_totals, const uint64_t *rank_base, uint32_t n_len);
+
+/* ---- results ---- */
+int rlsim_get_stats(rlsim_handle *h, rlsim_stats *out);
+/* histogram `kind` into out[0..n) (n = number of bins wanted; bins beyond the data are 0) */
+int rlsim_get_hist(rlsim_handle *h, int kind, uint64_t *out, uint32_t n);
+/* species table sorted by (transcript, start, end); any pointer may be NULL */
+int rlsim_get_species(rlsim_handle *h, uint32_t *tr, uint32_t *start, uint32_t *end, uint32_t *count_frag,
+                      uint64_t *count_pcr, double *eff, uint32_t *gc);
+/* sampled fragments (Frag records, frag.go:46-52) in output order; any pointer may be NULL */
+int rlsim_get_sampled(rlsim_handle *h, uint32_t *tr, uint32_t *start, uint32_t *end, uint8_t *minus_strand,
+                      uint64_t *id);
+/* Frag.String for every sampled fragment (frag.go:71-126, sampler.go:206), formatted on the device:
+ * ">Fg_<id>_<name> (Strand <s> Offset <start> -- <end>)\n<seq>\n".  names/name_off: transcript names of
+ * this shard.  Call with buf = NULL to get the size. */
+int rlsim_format_fasta(rlsim_handle *h, const uint8_t *names, const uint64_t *name_off, uint8_t *buf,
+                       uint64_t cap, uint64_t *size_out);
+
+/* ---- probes used by the parity tests (deterministic building blocks on the device) ---- */
+int rlsim_probe_kmer_lut(rlsim_handle *h, double *K_out, uint32_t *w_out, uint32_t n);       /* nnthermo.go:126-175 */
+int rlsim_probe_prefix(rlsim_handle *h, uint32_t tr, int reverse, uint64_t *out, uint32_t n); /* nnthermo.go:177-201 */
+int rlsim_probe_gc_prefix(rlsim_handle *h, uint32_t tr, uint32_t *out, uint32_t n);
+int rlsim_probe_math(rlsim_handle *h, int fn, const double *x, const double *y, double *out, uint32_t n);
+int rlsim_probe_philox(rlsim_handle *h, const uint32_t *ctr_key6, uint32_t *out4, uint32_t n);
+int rlsim_probe_amplify(rlsim_handle *h, int64_t seed_pcr, const uint32_t *tse, const uint64_t *n0, const double *p,
+                        int cycles, uint64_t *out, uint32_t n);
+/* device time of the kernels of the last build_library / sample call, milliseconds, by stage */
+enum { RLSIM_T_LAYOUT = 0, RLSIM_T_PREFIX = 1, RLSIM_T_FRAGMENT = 2, RLSIM_T_DEDUP = 3, RLSIM_T_PCR = 4,
+       RLSIM_T_SELECT = 5, RLSIM_T_EXPAND = 6, RLSIM_T_FORMAT = 7, RLSIM_T_TARGET = 8, RLSIM_T_COUNT = 9 };
+int rlsim_get_timings(rlsim_handle *h, float *ms_out, uint64_t *launches_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -60,7 +60,7 @@ void orc_binding_profile(const char *plus, uint32_t len, int k, double T, int re
 }
 
 /* spec 4.3: fixed-point priming weights.  scale = 2^32 / Kmax, Kmax = max K over the 4^k ACGT k-mers
- * (det_exp), w = floor(K * scale + 0.5) saturated to 2^32. */
+ * (det_exp), w = floor(K * scale + 0.5) saturated to 2^32-1 (fits a u32). */
 static double px_kmax(int k, double T) {
     char buf[32];
     double mx = 0.0;
@@ -74,7 +74,7 @@ static double px_kmax(int k, double T) {
 }
 static uint64_t px_quant(double K, double scale) {
     double x = K * scale + 0.5;
-    if (!(x < 4294967296.0)) return 4294967296ULL;
+    if (!(x < 4294967295.0)) return 4294967295ULL;
     return (uint64_t)x;
 }
 void orc_quantized_weights(const char *plus, uint32_t len, int k, double T, int reverse, uint64_t *w) {
@@ -92,7 +92,38 @@ uint32_t orc_gc_count(const char *plus, uint32_t start, uint32_t end) {
     for (uint32_t i = start; i < end; i++) gc += (plus[i] == 'G' || plus[i] == 'C');
     return gc;
 }
-static double pw(double x, double y, int detmath) { return detmath ? det_go_pow(x, y) : pow(x, y); }
+/* Go's math.Pow (pow.go) with the platform libm standing in for Go's Exp/Log: exact for integer exponents
+ * (square-and-multiply), within a few ulp of the release binary for fractional ones. */
+static double ref_go_pow(double x, double y) {
+    if (y == 0.0 || x == 1.0) return 1.0;
+    if (y == 1.0) return x;
+    if (y == 0.5) return sqrt(x);
+    if (y == -0.5) return 1.0 / sqrt(x);
+    if (x != x || y != y) return NAN;
+    if (x == 0.0) return y < 0.0 ? INFINITY : 0.0;
+    double absy = fabs(y);
+    int flip = y < 0.0;
+    double yi = floor(absy), yf = absy - yi;
+    if (yf != 0.0 && x < 0.0) return NAN;
+    if (yi >= 9.223372036854775808e18) return exp(y * log(x));
+    double a1 = 1.0;
+    int ae = 0;
+    if (yf != 0.0) {
+        if (yf > 0.5) { yf -= 1.0; yi += 1.0; }
+        a1 = exp(yf * log(x));
+    }
+    int xe;
+    double x1 = frexp(x, &xe);
+    for (int64_t i = (int64_t)yi; i != 0; i >>= 1) {
+        if (i & 1) { a1 *= x1; ae += xe; }
+        x1 *= x1;
+        xe <<= 1;
+        if (x1 < 0.5) { x1 += x1; xe--; }
+    }
+    if (flip) { a1 = 1.0 / a1; ae = -ae; }
+    return ldexp(a1, ae);
+}
+static double pw(double x, double y, int detmath) { return detmath ? det_go_pow(x, y) : ref_go_pow(x, y); }
 /* thermocycler.go:167-180 with gc = count/len */
 double orc_gc_eff(const orc_params *p, uint32_t gc_count, uint32_t len, int detmath) {
     double gc = (double)gc_count / (double)len;

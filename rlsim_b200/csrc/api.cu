@@ -1,0 +1,929 @@
+// C ABI of librlsim_gpu.so (include/rlsim_gpu.h): handle, HBM layout, stage orchestration.
+//
+// Host glue only - every per-molecule / per-species / per-fragment computation is in the k_*.cu kernels.
+// Library plumbing used here: cub::DeviceRadixSort / DeviceRunLengthEncode / DeviceScan for the species
+// dedup (transcript.go:156-215), the per-length class view (pool.go:156-189) and the selection sort.
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "kernels.cuh"
+
+using namespace rl;
+
+namespace {
+
+template <typename T>
+struct DBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~DBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t ensure(size_t want) {  // contents are NOT preserved
+        if (want <= n) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(want, 1) * sizeof(T));
+        if (e == cudaSuccess) n = want;
+        return e;
+    }
+};
+
+struct Batch {
+    uint8_t *d_bases = nullptr;
+    uint64_t *d_src_off = nullptr;
+    uint32_t n = 0;
+    uint32_t first = 0;
+};
+
+uint32_t bits_for(uint64_t v) {
+    uint32_t b = 1;
+    while (b < 64 && (v >> b)) b++;
+    return b;
+}
+
+__global__ void k_iota(uint32_t *p, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint32_t)i;
+}
+__global__ void k_class_totals(const uint64_t *cls_pre, const uint64_t *bounds, uint32_t n_len, uint64_t *totals) {
+    uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < n_len) totals[l] = cls_pre[bounds[l + 1]] - cls_pre[bounds[l]];
+}
+
+}  // namespace
+
+struct rlsim_handle {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    std::string err;
+    rlsim_params p{};
+    bool have_model = false;
+    // target
+    std::vector<uint32_t> raw_len;
+    std::vector<double> raw_prob;
+    std::vector<uint64_t> h_target;  // histogram by length
+    bool have_target = false;
+    uint64_t req_frags = 0;
+    uint64_t low = 0, high = 0;
+    double raw_location = 0.0;
+    uint32_t polya_max = 0;
+    std::vector<double> h_len_eff;  // host-supplied table
+    uint64_t len_eff_low = 0, len_eff_high = 0;
+    // transcripts
+    uint32_t first_index = 0;
+    std::vector<Batch> batches;
+    std::vector<uint64_t> h_srclen;  // unpadded lengths as added
+    std::vector<uint64_t> h_expr;
+    std::vector<uint64_t> h_off;     // padded offsets [n+1]
+    std::vector<uint32_t> h_len;     // with polyA
+    bool ingested = false;
+    uint64_t n_mol = 0, total_padded = 0;
+    DBuf<uint8_t> d_bases;
+    DBuf<uint32_t> d_packed, d_nmask, d_gc, d_len;
+    DBuf<uint64_t> d_off, d_expr, d_mol_off, d_Pf, d_Pr;
+    bool have_prefix = false;
+    // model tables
+    DBuf<double> d_gc_raw, d_len_eff, d_raw_prob, d_K;
+    DBuf<uint32_t> d_raw_len, d_wq_f, d_wq_r;
+    DBuf<unsigned long long> d_kmax;
+    // fragmentation
+    DBuf<uint64_t> d_keys, d_keys_sorted, d_uniq;
+    DBuf<unsigned long long> d_counters;  // [0] fragment count, [1] run count
+    DBuf<unsigned long long> d_hist_frag, d_hist_polya, d_hist_target;
+    DBuf<uint2> d_long_list;
+    DBuf<uint32_t> d_long_hi;
+    DBuf<unsigned int> d_long_count;
+    DBuf<int> d_error;
+    DBuf<unsigned char> d_cub;
+    uint64_t n_frag = 0;
+    bool fragmented = false, amplified = false, sampled = false;
+    std::vector<uint64_t> h_hist_frag, h_hist_polya;
+    // species
+    uint64_t n_sp = 0;
+    DBuf<uint32_t> d_sp_tr, d_sp_start, d_sp_len, d_sp_count0, d_sp_gc;
+    DBuf<uint64_t> d_sp_count;
+    DBuf<double> d_sp_eff;
+    bool keep_debug = true;  // keep per-species eff / gc for rlsim_get_species
+    // classes
+    DBuf<uint32_t> d_iota, d_sorted_len, d_order;
+    DBuf<uint64_t> d_cls_cnt, d_cls_pre, d_bounds, d_totals;
+    uint32_t n_len = 0;
+    std::vector<uint64_t> h_totals;  // local per-length totals
+    uint64_t pool_total = 0;
+    // selection
+    std::vector<uint64_t> h_sampled, h_missing, h_after_sampling, h_after_pcr;
+    DBuf<uint64_t> d_cand_keys, d_cand_keys_sorted, d_fscan, d_taken, d_out_off, d_plan_u64;
+    DBuf<uint32_t> d_cand_idx, d_cand_idx_sorted, d_flags, d_plan_len;
+    DBuf<unsigned long long> d_hits;
+    DBuf<uint8_t> d_mode;
+    DBuf<int> d_short;
+    uint64_t n_out = 0;
+    DBuf<uint32_t> d_o_tr, d_o_start, d_o_end;
+    DBuf<uint8_t> d_o_minus;
+    DBuf<uint64_t> d_o_id;
+    // fasta
+    DBuf<uint8_t> d_names, d_fasta;
+    DBuf<uint64_t> d_name_off, d_rec_sizes, d_rec_off;
+    // timings
+    float ms[RLSIM_T_COUNT] = {0};
+    uint64_t launches[RLSIM_T_COUNT] = {0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+static std::string g_create_error;
+
+#define FAIL(h, code, msg) do { (h)->err = (msg); return (code); } while (0)
+#define CK(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__); return RLSIM_E_CUDA; } } while (0)
+
+namespace {
+
+struct StageTimer {
+    rlsim_handle *h;
+    int stage;
+    StageTimer(rlsim_handle *h_, int s, uint64_t nl) : h(h_), stage(s) { cudaEventRecord(h->ev0, h->st); h->launches[s] += nl; }
+    void stop() {
+        cudaEventRecord(h->ev1, h->st);
+        cudaEventSynchronize(h->ev1);
+        float t = 0;
+        cudaEventElapsedTime(&t, h->ev0, h->ev1);
+        h->ms[stage] += t;
+    }
+};
+
+int check_device_error(rlsim_handle *h) {
+    int e = 0;
+    CK(h, cudaMemcpyAsync(&e, h->d_error.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    switch (e) {
+    case 0: return 0;
+    case RLSIM_E_PRIMING: FAIL(h, e, "Error when simulating priming!");
+    case RLSIM_E_PCR_OVERFLOW: FAIL(h, e, "Integer overflow detected when amplifying fragments!");
+    case RLSIM_E_UNSUPPORTED: FAIL(h, e, "a molecule needs more breakpoints than the shared-memory sorter holds (32766)");
+    default: FAIL(h, e, "device-side error");
+    }
+}
+
+void mix_minmax(const rlsim_mixcomp *c, int n, uint64_t *mn, uint64_t *mx) {  // target.go:72-87
+    uint64_t lo = 0, hi = 0;
+    for (int i = 0; i < n; i++) {
+        if (i == 0) lo = c[i].low;
+        if (hi < c[i].high) hi = c[i].high;
+        if (lo > c[i].low) lo = c[i].low;
+    }
+    *mn = lo; *mx = hi;
+}
+
+bool needs_fwd(int m) { return m == RLSIM_AFTER_PRIM || m == RLSIM_AFTER_PRIM_DOUBLE || m == RLSIM_PRIM_JUMP; }
+bool needs_rev(int m) { return m == RLSIM_AFTER_PRIM_DOUBLE; }
+
+DevModel make_model(rlsim_handle *h) {
+    DevModel m{};
+    const rlsim_params &p = h->p;
+    m.k = p.kmer_len; m.method = p.frag_method; m.frag_param = p.frag_param; m.cycles = p.nr_cycles;
+    m.T = p.priming_temp; m.loss = p.frag_loss_prob; m.fixed_eff = p.fixed_eff; m.strand_bias = p.strand_bias;
+    m.gc_mode = p.gc_mode; m.n_target = p.n_target; m.n_polya = p.n_polya; m.n_raw = (int32_t)h->raw_len.size();
+    m.gc_shape = p.gc_shape; m.gc_min = p.gc_min; m.gc_max = p.gc_max;
+    m.len_shape = p.len_shape; m.len_min = p.len_min; m.len_max = p.len_max;
+    memcpy(m.target, p.target, sizeof m.target);
+    memcpy(m.polya, p.polya, sizeof m.polya);
+    m.raw_location = h->raw_location;
+    m.low = (uint32_t)h->low; m.high = (uint32_t)h->high; m.polya_max = h->polya_max; m.first_index = h->first_index;
+    // seed policy of main.go:72-81,129-149
+    int64_t si = p.seed_init, sp = p.seed_pcr ? p.seed_pcr : si, ss = p.seed_sampling ? p.seed_sampling : sp;
+    m.key_target = px_derive_key(si, TAG_TARGET);
+    m.key_frag = px_derive_key(si, TAG_FRAG);
+    m.key_pcr = px_derive_key(sp, TAG_PCR);
+    m.key_select = px_derive_key(ss, TAG_SELECT);
+    m.key_strand = px_derive_key(ss, TAG_STRAND);
+    m.gc_raw = h->d_gc_raw.p; m.len_eff = h->d_len_eff.p; m.raw_len = h->d_raw_len.p; m.raw_prob = h->d_raw_prob.p;
+    return m;
+}
+
+DevTranscripts make_tr(rlsim_handle *h) {
+    DevTranscripts t{};
+    t.n = (uint32_t)h->h_len.size();
+    t.bases = h->d_bases.p; t.packed = h->d_packed.p; t.nmask = h->d_nmask.p; t.off = h->d_off.p; t.len = h->d_len.p;
+    t.expr = h->d_expr.p; t.mol_off = h->d_mol_off.p;
+    t.Pf = h->have_prefix && needs_fwd(h->p.frag_method) ? h->d_Pf.p : nullptr;
+    t.Pr = h->have_prefix && needs_rev(h->p.frag_method) ? h->d_Pr.p : nullptr;
+    t.gc = h->d_gc.p;
+    return t;
+}
+
+DevSpecies make_sp(rlsim_handle *h) {
+    DevSpecies s{};
+    s.n = h->n_sp; s.tr = h->d_sp_tr.p; s.start = h->d_sp_start.p; s.len = h->d_sp_len.p; s.count0 = h->d_sp_count0.p;
+    s.count = h->d_sp_count.p; s.eff = h->keep_debug ? h->d_sp_eff.p : nullptr; s.gc = h->keep_debug ? h->d_sp_gc.p : nullptr;
+    return s;
+}
+
+int raw_target_finish(rlsim_handle *h) {  // raw_target.go:54,59-90
+    bool first = true;
+    uint64_t mn = 0, mx = 0;
+    double mean = 0.0, t = (double)h->req_frags;
+    for (size_t l = 0; l < h->h_target.size(); l++) {
+        uint64_t c = h->h_target[l];
+        if (!c) continue;
+        if (first) { mn = mx = l; first = false; }
+        mn = std::min<uint64_t>(mn, l); mx = std::max<uint64_t>(mx, l);
+        mean += ((double)c / t) * (double)l;
+    }
+    h->low = mn; h->high = mx; h->raw_location = mean;
+    return 0;
+}
+
+int ingest(rlsim_handle *h) {
+    if (h->ingested) return 0;
+    if (!h->have_model) FAIL(h, RLSIM_E_ARG, "rlsim_set_model must precede transcript ingest");
+    uint32_t n = (uint32_t)h->h_srclen.size();
+    h->h_off.assign(n + 1, 0);
+    h->h_len.assign(n, 0);
+    std::vector<uint64_t> mol_off(n + 1, 0);
+    for (uint32_t t = 0; t < n; t++) {
+        uint64_t L = h->h_srclen[t] + h->polya_max;
+        if (L >= (1ull << 32)) FAIL(h, RLSIM_E_UNSUPPORTED, "transcript longer than 2^32-1 bases");
+        h->h_len[t] = (uint32_t)L;
+        h->h_off[t + 1] = h->h_off[t] + ((L + 31) & ~31ull);
+        mol_off[t + 1] = mol_off[t] + h->h_expr[t];
+    }
+    h->total_padded = h->h_off[n];
+    h->n_mol = mol_off[n];
+    if (h->total_padded >= (1ull << 40)) FAIL(h, RLSIM_E_UNSUPPORTED, "more than 2^40 bases on one GPU");
+    size_t tot = h->total_padded;
+    CK(h, h->d_bases.ensure(tot + 64));
+    CK(h, h->d_packed.ensure(tot / 16 + 8));
+    CK(h, h->d_nmask.ensure(tot / 32 + 8));
+    CK(h, h->d_gc.ensure(tot + n + 8));
+    CK(h, h->d_off.ensure(n + 1)); CK(h, h->d_len.ensure(n)); CK(h, h->d_expr.ensure(n)); CK(h, h->d_mol_off.ensure(n + 1));
+    CK(h, cudaMemsetAsync(h->d_packed.p + tot / 16, 0, 8 * 4, h->st));
+    CK(h, cudaMemsetAsync(h->d_nmask.p + tot / 32, 0, 8 * 4, h->st));
+    CK(h, cudaMemcpyAsync(h->d_off.p, h->h_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemcpyAsync(h->d_len.p, h->h_len.data(), n * 4, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemcpyAsync(h->d_expr.p, h->h_expr.data(), n * 8, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemcpyAsync(h->d_mol_off.p, mol_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, h->st));
+    StageTimer tm(h, RLSIM_T_LAYOUT, h->batches.size());
+    for (auto &b : h->batches) {
+        launch_ingest(h->st, b.d_bases, b.d_src_off, b.n, h->polya_max, h->d_off.p + b.first, h->d_bases.p, h->d_packed.p,
+                      h->d_nmask.p, h->d_gc.p + b.first);
+    }
+    tm.stop();
+    CK(h, cudaGetLastError());
+    for (auto &b : h->batches) { cudaFree(b.d_bases); cudaFree(b.d_src_off); b.d_bases = nullptr; b.d_src_off = nullptr; }
+    h->batches.clear();
+    h->ingested = true;
+    return 0;
+}
+
+int upload_tables(rlsim_handle *h) {
+    CK(h, h->d_gc_raw.ensure(101));
+    CK(h, cudaMemcpyAsync(h->d_gc_raw.p, h->p.gc_raw, 101 * 8, cudaMemcpyHostToDevice, h->st));
+    if (!h->raw_len.empty()) {
+        CK(h, h->d_raw_len.ensure(h->raw_len.size()));
+        CK(h, h->d_raw_prob.ensure(h->raw_prob.size()));
+        CK(h, cudaMemcpyAsync(h->d_raw_len.p, h->raw_len.data(), h->raw_len.size() * 4, cudaMemcpyHostToDevice, h->st));
+        CK(h, cudaMemcpyAsync(h->d_raw_prob.p, h->raw_prob.data(), h->raw_prob.size() * 8, cudaMemcpyHostToDevice, h->st));
+    }
+    return 0;
+}
+
+int cub_temp(rlsim_handle *h, size_t bytes) { CK(h, h->d_cub.ensure(bytes + 16)); return 0; }
+
+}  // namespace
+
+extern "C" {
+
+int rlsim_create(int device, rlsim_handle **out) {
+    *out = nullptr;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return RLSIM_E_CUDA; }
+    rlsim_handle *h = new rlsim_handle();
+    h->device = device;
+    if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
+        (e = h->d_error.ensure(1)) != cudaSuccess || (e = h->d_counters.ensure(4)) != cudaSuccess ||
+        (e = h->d_long_count.ensure(1)) != cudaSuccess || (e = h->d_kmax.ensure(1)) != cudaSuccess) {
+        g_create_error = std::string("rlsim_create: ") + cudaGetErrorString(e);
+        delete h;
+        return RLSIM_E_CUDA;
+    }
+    cudaMemsetAsync(h->d_error.p, 0, sizeof(int), h->st);
+    *out = h;
+    return 0;
+}
+
+void rlsim_destroy(rlsim_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto &b : h->batches) { cudaFree(b.d_bases); cudaFree(b.d_src_off); }
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+const char *rlsim_last_error(const rlsim_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int rlsim_set_model(rlsim_handle *h, const rlsim_params *p) {
+    if (p->kmer_len < 1 || p->kmer_len > 12) FAIL(h, RLSIM_E_UNSUPPORTED, "primer length outside 1..12 is not supported by the GPU path");
+    if (p->n_polya < 1 || p->n_polya > RLSIM_MAX_COMPS || p->n_target < 0 || p->n_target > RLSIM_MAX_COMPS)
+        FAIL(h, RLSIM_E_ARG, "invalid number of mixture components");
+    if (p->frag_method < 0 || p->frag_method > RLSIM_PRIM_JUMP) FAIL(h, RLSIM_E_ARG, "Invalid fragmentation method.");
+    if (p->frag_method == RLSIM_PRE_PRIM && p->frag_param <= 0) FAIL(h, RLSIM_E_ARG, "pre_prim needs a positive parameter");
+    if (p->nr_cycles < 0) FAIL(h, RLSIM_E_ARG, "negative number of PCR cycles");
+    cudaSetDevice(h->device);
+    h->p = *p;
+    h->have_model = true;
+    uint64_t mn, mx;
+    mix_minmax(p->polya, p->n_polya, &mn, &mx);  // pool.go:84
+    if (mx >= (1u << 24)) FAIL(h, RLSIM_E_UNSUPPORTED, "poly(A) maximum >= 2^24");
+    if (h->ingested && h->polya_max != (uint32_t)mx) FAIL(h, RLSIM_E_ARG, "poly(A) maximum cannot change after transcripts were ingested");
+    h->polya_max = (uint32_t)mx;
+    h->have_prefix = false;
+    if (p->n_target > 0) {
+        mix_minmax(p->target, p->n_target, &h->low, &h->high);  // target.go:67
+        if (h->high >= (1u << 24)) FAIL(h, RLSIM_E_UNSUPPORTED, "maximum fragment length >= 2^24");
+    }
+    h->fragmented = h->amplified = h->sampled = false;
+    return upload_tables(h);
+}
+
+int rlsim_set_len_eff(rlsim_handle *h, const double *len_eff, uint64_t low, uint64_t high) {
+    if (high < low) FAIL(h, RLSIM_E_ARG, "len_eff: high < low");
+    h->h_len_eff.assign(len_eff, len_eff + (high - low + 1));
+    h->len_eff_low = low; h->len_eff_high = high;
+    return 0;
+}
+
+int rlsim_set_raw_target(rlsim_handle *h, const uint32_t *lengths, const double *probs, uint32_t n) {
+    if (n == 0) FAIL(h, RLSIM_E_ARG, "empty raw target");
+    cudaSetDevice(h->device);
+    h->raw_len.assign(lengths, lengths + n);
+    h->raw_prob.assign(probs, probs + n);
+    for (uint32_t i = 0; i < n; i++)
+        if (lengths[i] >= (1u << 24)) FAIL(h, RLSIM_E_UNSUPPORTED, "maximum fragment length >= 2^24");
+    return upload_tables(h);
+}
+
+int rlsim_sample_target(rlsim_handle *h, int64_t req_frags) {
+    if (!h->have_model) FAIL(h, RLSIM_E_ARG, "rlsim_set_model first");
+    if (req_frags < 0) FAIL(h, RLSIM_E_ARG, "Illegal fragment number!");
+    bool raw = h->p.n_target == 0;
+    if (raw && h->raw_len.empty()) FAIL(h, RLSIM_E_ARG, "raw target requested but rlsim_set_raw_target was not called");
+    cudaSetDevice(h->device);
+    uint32_t hist_n;
+    if (raw) hist_n = *std::max_element(h->raw_len.begin(), h->raw_len.end()) + 1;
+    else { uint64_t mn, mx; mix_minmax(h->p.target, h->p.n_target, &mn, &mx); hist_n = (uint32_t)mx + 1; }
+    CK(h, h->d_hist_target.ensure(hist_n));
+    CK(h, cudaMemsetAsync(h->d_hist_target.p, 0, (size_t)hist_n * 8, h->st));
+    DevModel m = make_model(h);
+    StageTimer tm(h, RLSIM_T_TARGET, 1);
+    launch_target(h->st, m, (uint64_t)req_frags, h->d_hist_target.p, hist_n);
+    tm.stop();
+    CK(h, cudaGetLastError());
+    h->h_target.assign(hist_n, 0);
+    CK(h, cudaMemcpyAsync(h->h_target.data(), h->d_hist_target.p, (size_t)hist_n * 8, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    h->req_frags = (uint64_t)req_frags;
+    h->have_target = true;
+    if (raw) raw_target_finish(h);
+    return 0;
+}
+
+int rlsim_set_target_hist(rlsim_handle *h, const uint32_t *lengths, const uint64_t *counts, uint32_t n) {
+    if (!h->have_model) FAIL(h, RLSIM_E_ARG, "rlsim_set_model first");
+    uint32_t mx = 0;
+    for (uint32_t i = 0; i < n; i++) mx = std::max(mx, lengths[i]);
+    if (mx >= (1u << 24)) FAIL(h, RLSIM_E_UNSUPPORTED, "maximum fragment length >= 2^24");
+    h->h_target.assign((size_t)mx + 1, 0);
+    h->req_frags = 0;
+    for (uint32_t i = 0; i < n; i++) { h->h_target[lengths[i]] += counts[i]; h->req_frags += counts[i]; }
+    h->have_target = true;
+    if (h->p.n_target == 0) raw_target_finish(h);
+    return 0;
+}
+
+int rlsim_set_first_index(rlsim_handle *h, uint32_t first_index) { h->first_index = first_index; return 0; }
+
+int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t *offsets, const uint64_t *expr, uint32_t n) {
+    if (h->ingested) FAIL(h, RLSIM_E_ARG, "transcripts cannot be added after the library was built");
+    if (n == 0) return 0;
+    cudaSetDevice(h->device);
+    Batch b;
+    b.n = n;
+    b.first = (uint32_t)h->h_srclen.size();
+    uint64_t nbytes = offsets[n] - offsets[0];
+    std::vector<uint64_t> rel(n + 1);
+    for (uint32_t i = 0; i <= n; i++) rel[i] = offsets[i] - offsets[0];
+    CK(h, cudaMalloc(&b.d_bases, std::max<uint64_t>(nbytes, 1)));
+    CK(h, cudaMalloc(&b.d_src_off, (n + 1) * 8));
+    CK(h, cudaMemcpyAsync(b.d_bases, bases + offsets[0], nbytes, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemcpyAsync(b.d_src_off, rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaStreamSynchronize(h->st));  // caller-owned buffers are only read during the call
+    for (uint32_t i = 0; i < n; i++) { h->h_srclen.push_back(rel[i + 1] - rel[i]); h->h_expr.push_back(expr[i]); }
+    h->batches.push_back(b);
+    return 0;
+}
+
+int rlsim_fragment(rlsim_handle *h) {
+    if (!h->have_model) FAIL(h, RLSIM_E_ARG, "rlsim_set_model first");
+    if (h->p.n_target == 0 && !h->have_target) FAIL(h, RLSIM_E_ARG, "a raw target needs its sampled histogram before fragmentation");
+    cudaSetDevice(h->device);
+    int rc = ingest(h);
+    if (rc) return rc;
+    if (h->low == 0) FAIL(h, RLSIM_E_ARG, "Serious trouble: fragment length is zero!");  // transcript.go:194-196
+    uint32_t n = (uint32_t)h->h_len.size();
+    int method = h->p.frag_method;
+    // ---- priming affinities -> prefix sums (nnthermo.go:177-201)
+    if (needs_fwd(method) && !h->have_prefix) {
+        uint32_t nk = 1u << (2 * h->p.kmer_len);
+        CK(h, h->d_K.ensure(nk)); CK(h, h->d_wq_f.ensure(nk)); CK(h, h->d_wq_r.ensure(nk));
+        CK(h, h->d_Pf.ensure(h->total_padded + n + 8));
+        if (needs_rev(method)) CK(h, h->d_Pr.ensure(h->total_padded + n + 8));
+        h->have_prefix = true;
+        DevTranscripts tr = make_tr(h);
+        StageTimer tm(h, RLSIM_T_PREFIX, 3);
+        launch_kmer_lut(h->st, h->p.kmer_len, h->p.priming_temp, h->d_K.p, h->d_kmax.p, h->d_wq_f.p, h->d_wq_r.p);
+        launch_prefix(h->st, tr, h->p.kmer_len, h->p.priming_temp, h->d_wq_f.p, h->d_wq_r.p, h->d_kmax.p, h->d_Pf.p, h->d_Pr.p,
+                      needs_rev(method) ? 2 : 1);
+        tm.stop();
+        CK(h, cudaGetLastError());
+    }
+    // ---- capacity estimate for the fragment keys
+    double loc = h->raw_location;
+    if (h->p.n_target > 0) {
+        double wsum = 0, lsum = 0, lmin = 1e300;
+        for (int i = 0; i < h->p.n_target; i++) { wsum += h->p.target[i].weight; lsum += h->p.target[i].weight * h->p.target[i].location; lmin = std::min(lmin, h->p.target[i].location); }
+        loc = lmin > 0 ? lmin : (wsum > 0 ? lsum / wsum : 1.0);
+    }
+    if (!(loc > 0)) loc = 1.0;
+    double est = 0;
+    for (uint32_t t = 0; t < n; t++) {
+        double L = h->h_len[t], per;
+        if (method == RLSIM_PRIM_JUMP) per = L / (double)std::max<uint64_t>(h->low, 1) + 1.0;
+        else if (method == RLSIM_PRE_PRIM) per = L / loc + 1.0;
+        else per = (h->p.frag_param == 0 ? L / loc / 2.0 : L / (double)h->p.frag_param) + 1.0;
+        est += per * (double)h->h_expr[t];
+    }
+    uint64_t cap = (uint64_t)(est * 1.15) + 65536;
+    uint32_t hist_frag_n = (uint32_t)h->high + 1, hist_pa_n = h->polya_max + 1;
+    CK(h, h->d_hist_frag.ensure(hist_frag_n)); CK(h, h->d_hist_polya.ensure(hist_pa_n));
+    uint32_t long_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(h->n_mol / 64, 4096), 1u << 24);
+    DevModel m = make_model(h);
+    DevTranscripts tr = make_tr(h);
+    for (int attempt = 0;; attempt++) {
+        if (attempt > 8) FAIL(h, RLSIM_E_NOMEM, "fragment buffer kept overflowing");
+        CK(h, h->d_keys.ensure(cap));
+        CK(h, h->d_long_list.ensure(long_cap)); CK(h, h->d_long_hi.ensure(long_cap));
+        CK(h, cudaMemsetAsync(h->d_counters.p, 0, 4 * 8, h->st));
+        CK(h, cudaMemsetAsync(h->d_long_count.p, 0, 4, h->st));
+        CK(h, cudaMemsetAsync(h->d_hist_frag.p, 0, (size_t)hist_frag_n * 8, h->st));
+        CK(h, cudaMemsetAsync(h->d_hist_polya.p, 0, (size_t)hist_pa_n * 8, h->st));
+        CK(h, cudaMemsetAsync(h->d_error.p, 0, 4, h->st));
+        StageTimer tm(h, RLSIM_T_FRAGMENT, 1);
+        rc = launch_fragment(h->st, m, tr, h->n_mol, h->d_keys.p, cap, h->d_counters.p, h->d_hist_frag.p, h->d_hist_polya.p,
+                             h->d_long_list.p, h->d_long_hi.p, long_cap, h->d_long_count.p, h->d_error.p);
+        if (rc) FAIL(h, rc, "fragmentation launch configuration unsupported (poly(A) maximum too large)");
+        unsigned int n_long = 0;
+        CK(h, cudaMemcpyAsync(&n_long, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaStreamSynchronize(h->st));
+        if (n_long > long_cap) { tm.stop(); long_cap = n_long + 1024; continue; }
+        if (n_long) {
+            h->launches[RLSIM_T_FRAGMENT]++;
+            launch_fragment_long(h->st, m, tr, h->d_keys.p, cap, h->d_counters.p, h->d_hist_frag.p, h->d_hist_polya.p,
+                                 h->d_long_list.p, h->d_long_hi.p, n_long, h->d_error.p);
+        }
+        tm.stop();
+        CK(h, cudaGetLastError());
+        unsigned long long cnt = 0;
+        CK(h, cudaMemcpyAsync(&cnt, h->d_counters.p, 8, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaStreamSynchronize(h->st));
+        if (cnt > cap) { cap = cnt + cnt / 8 + 65536; continue; }
+        h->n_frag = cnt;
+        break;
+    }
+    if ((rc = check_device_error(h))) return rc;
+    h->h_hist_frag.assign(hist_frag_n, 0);
+    h->h_hist_polya.assign(hist_pa_n, 0);
+    CK(h, cudaMemcpyAsync(h->h_hist_frag.data(), h->d_hist_frag.p, (size_t)hist_frag_n * 8, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaMemcpyAsync(h->h_hist_polya.data(), h->d_hist_polya.p, (size_t)hist_pa_n * 8, cudaMemcpyDeviceToHost, h->st));
+    // ---- species: sort + run-length encode (transcript.go:156-215)
+    uint64_t nf = h->n_frag;
+    CK(h, h->d_keys_sorted.ensure(nf)); CK(h, h->d_uniq.ensure(nf)); CK(h, h->d_sp_count0.ensure(nf));
+    {
+        StageTimer tm(h, RLSIM_T_DEDUP, 3);
+        h->n_sp = 0;
+        if (nf) {
+            if (nf >= (1ull << 31)) FAIL(h, RLSIM_E_UNSUPPORTED, "more than 2^31 fragments on one GPU");
+            int end_bit = (int)std::min<uint32_t>(64, 24 + bits_for(h->total_padded));
+            size_t tb = 0;
+            CK(h, cub::DeviceRadixSort::SortKeys(nullptr, tb, h->d_keys.p, h->d_keys_sorted.p, (int)nf, 0, end_bit, h->st));
+            if ((rc = cub_temp(h, tb))) return rc;
+            CK(h, cub::DeviceRadixSort::SortKeys(h->d_cub.p, tb, h->d_keys.p, h->d_keys_sorted.p, (int)nf, 0, end_bit, h->st));
+            tb = 0;
+            CK(h, cub::DeviceRunLengthEncode::Encode(nullptr, tb, h->d_keys_sorted.p, h->d_uniq.p, h->d_sp_count0.p,
+                                                     h->d_counters.p + 1, (int)nf, h->st));
+            if ((rc = cub_temp(h, tb))) return rc;
+            CK(h, cub::DeviceRunLengthEncode::Encode(h->d_cub.p, tb, h->d_keys_sorted.p, h->d_uniq.p, h->d_sp_count0.p,
+                                                     h->d_counters.p + 1, (int)nf, h->st));
+            unsigned long long runs = 0;
+            CK(h, cudaMemcpyAsync(&runs, h->d_counters.p + 1, 8, cudaMemcpyDeviceToHost, h->st));
+            CK(h, cudaStreamSynchronize(h->st));
+            h->n_sp = runs;
+        }
+        CK(h, h->d_sp_tr.ensure(h->n_sp)); CK(h, h->d_sp_start.ensure(h->n_sp)); CK(h, h->d_sp_len.ensure(h->n_sp));
+        CK(h, h->d_sp_count.ensure(h->n_sp)); CK(h, h->d_sp_eff.ensure(h->n_sp)); CK(h, h->d_sp_gc.ensure(h->n_sp));
+        launch_decode_species(h->st, tr, h->d_uniq.p, make_sp(h));
+        tm.stop();
+        CK(h, cudaGetLastError());
+    }
+    CK(h, cudaStreamSynchronize(h->st));
+    h->fragmented = true; h->amplified = false; h->sampled = false;
+    return 0;
+}
+
+int rlsim_pcr(rlsim_handle *h) {
+    if (!h->fragmented) FAIL(h, RLSIM_E_ARG, "rlsim_fragment first");
+    cudaSetDevice(h->device);
+    int rc;
+    uint32_t nle = (uint32_t)(h->high - h->low + 1);
+    CK(h, h->d_len_eff.ensure(nle));
+    DevModel m = make_model(h);
+    if (!h->h_len_eff.empty()) {
+        if (h->len_eff_low != h->low || h->len_eff_high != h->high) FAIL(h, RLSIM_E_ARG, "length-efficiency table does not span [low, high]");
+        CK(h, cudaMemcpyAsync(h->d_len_eff.p, h->h_len_eff.data(), (size_t)nle * 8, cudaMemcpyHostToDevice, h->st));
+    } else {
+        launch_len_eff(h->st, m, h->d_len_eff.p);
+    }
+    CK(h, cudaMemsetAsync(h->d_error.p, 0, 4, h->st));
+    DevTranscripts tr = make_tr(h);
+    {
+        StageTimer tm(h, RLSIM_T_PCR, 1);
+        launch_pcr(h->st, m, tr, make_sp(h), h->d_error.p);
+        tm.stop();
+        CK(h, cudaGetLastError());
+    }
+    if ((rc = check_device_error(h))) return rc;
+    // ---- per-length classes (pool.go:156-189): species view sorted by length, prefix sums of the amplified counts
+    uint64_t ns = h->n_sp;
+    h->n_len = (uint32_t)h->high + 1;
+    CK(h, h->d_iota.ensure(ns)); CK(h, h->d_sorted_len.ensure(ns)); CK(h, h->d_order.ensure(ns));
+    CK(h, h->d_cls_cnt.ensure(ns)); CK(h, h->d_cls_pre.ensure(ns + 1)); CK(h, h->d_bounds.ensure(h->n_len + 2));
+    CK(h, h->d_totals.ensure(h->n_len + 1));
+    {
+        StageTimer tm(h, RLSIM_T_SELECT, 6);
+        CK(h, cudaMemsetAsync(h->d_cls_pre.p, 0, 8, h->st));
+        if (ns) {
+            k_iota<<<(unsigned)((ns + 255) / 256), 256, 0, h->st>>>(h->d_iota.p, ns);
+            size_t tb = 0;
+            int eb = (int)bits_for(h->high);
+            CK(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, h->d_sp_len.p, h->d_sorted_len.p, h->d_iota.p, h->d_order.p, (int)ns, 0, eb, h->st));
+            if ((rc = cub_temp(h, tb))) return rc;
+            CK(h, cub::DeviceRadixSort::SortPairs(h->d_cub.p, tb, h->d_sp_len.p, h->d_sorted_len.p, h->d_iota.p, h->d_order.p, (int)ns, 0, eb, h->st));
+            launch_gather_counts(h->st, h->d_order.p, h->d_sp_count.p, h->d_cls_cnt.p, ns);
+            tb = 0;
+            CK(h, cub::DeviceScan::InclusiveSum(nullptr, tb, h->d_cls_cnt.p, h->d_cls_pre.p + 1, (int)ns, h->st));
+            if ((rc = cub_temp(h, tb))) return rc;
+            CK(h, cub::DeviceScan::InclusiveSum(h->d_cub.p, tb, h->d_cls_cnt.p, h->d_cls_pre.p + 1, (int)ns, h->st));
+        }
+        launch_class_bounds(h->st, h->d_sorted_len.p, ns, h->n_len, h->d_bounds.p);
+        k_class_totals<<<(h->n_len + 127) / 128, 128, 0, h->st>>>(h->d_cls_pre.p, h->d_bounds.p, h->n_len, h->d_totals.p);
+        tm.stop();
+        CK(h, cudaGetLastError());
+    }
+    h->h_totals.assign(h->n_len, 0);
+    CK(h, cudaMemcpyAsync(h->h_totals.data(), h->d_totals.p, (size_t)h->n_len * 8, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    // fragstats.go:84-95
+    h->pool_total = 0;
+    for (uint64_t c : h->h_totals) {
+        uint64_t nt = h->pool_total + c;
+        if (nt < h->pool_total) FAIL(h, RLSIM_E_POOL_OVERFLOW, "Integer overflow when updating total fragment count!");
+        h->pool_total = nt;
+    }
+    h->h_after_pcr = h->h_totals;
+    h->amplified = true; h->sampled = false;
+    return 0;
+}
+
+int rlsim_build_library(rlsim_handle *h) {
+    int rc = rlsim_fragment(h);
+    if (rc) return rc;
+    return rlsim_pcr(h);
+}
+
+int rlsim_class_totals(rlsim_handle *h, uint64_t *totals, uint32_t n_len) {
+    if (!h->amplified) FAIL(h, RLSIM_E_ARG, "rlsim_pcr first");
+    for (uint32_t l = 0; l < n_len; l++) totals[l] = l < h->h_totals.size() ? h->h_totals[l] : 0;
+    return 0;
+}
+
+int rlsim_sample(rlsim_handle *h, const uint64_t *global_totals, const uint64_t *rank_base, uint32_t n_len_in) {
+    if (!h->amplified) FAIL(h, RLSIM_E_ARG, "rlsim_pcr first");
+    if (!h->have_target) FAIL(h, RLSIM_E_ARG, "no target histogram");
+    cudaSetDevice(h->device);
+    int rc;
+    uint32_t n_len = h->n_len;
+    std::vector<uint64_t> T(n_len, 0), base(n_len, 0);
+    for (uint32_t l = 0; l < n_len; l++) {
+        T[l] = global_totals ? (l < n_len_in ? global_totals[l] : 0) : h->h_totals[l];
+        base[l] = rank_base ? (l < n_len_in ? rank_base[l] : 0) : 0;
+    }
+    // ---- sampler.go:65-106 bookkeeping per requested length
+    size_t nt = std::max<size_t>(h->h_target.size(), n_len);
+    h->h_sampled.assign(nt, 0); h->h_missing.assign(nt, 0);
+    h->h_after_sampling.assign(nt, 0);
+    std::vector<uint8_t> mode(n_len + 1, 0);
+    std::vector<uint32_t> c_len;
+    std::vector<uint64_t> c_T, c_base, c_G, c_pick, c_cand;
+    uint64_t G = 0, n_cand = 0;
+    double slack = 1.06;
+    for (size_t l = 0; l < nt; l++) {
+        uint64_t req = l < h->h_target.size() ? h->h_target[l] : 0;
+        uint64_t tot = l < n_len ? T[l] : 0;
+        uint64_t take = std::min(req, tot);
+        h->h_sampled[l] = take;
+        h->h_missing[l] = req - take;
+        h->h_after_sampling[l] = tot - take;
+        if (!take || l >= n_len) continue;
+        if (take == tot) { mode[l] = 1; continue; }
+        bool include = take <= tot - take;
+        uint64_t pick = include ? take : tot - take;
+        mode[l] = include ? 2 : 3;
+        c_len.push_back((uint32_t)l); c_T.push_back(tot); c_base.push_back(base[l]); c_G.push_back(G); c_pick.push_back(pick);
+        G += tot;
+        // expected draws until `pick` distinct values out of tot: tot * ln(tot / (tot - pick))
+        double e = (double)tot * std::log((double)tot / (double)(tot - pick));
+        c_cand.push_back((uint64_t)(e * slack + 6.0 * std::sqrt((double)pick) + 64.0));
+    }
+    uint64_t ns = h->n_sp;
+    DevModel m = make_model(h);
+    CK(h, h->d_hits.ensure(ns)); CK(h, h->d_taken.ensure(ns)); CK(h, h->d_out_off.ensure(ns + 1)); CK(h, h->d_mode.ensure(n_len + 1));
+    CK(h, cudaMemcpyAsync(h->d_mode.p, mode.data(), n_len + 1, cudaMemcpyHostToDevice, h->st));
+    uint32_t nc = (uint32_t)c_len.size();
+    for (int attempt = 0;; attempt++) {
+        if (attempt > 6) FAIL(h, RLSIM_E_NOMEM, "selection kept running out of candidates");
+        CK(h, cudaMemsetAsync(h->d_hits.p, 0, std::max<uint64_t>(ns, 1) * 8, h->st));
+        if (!nc) break;
+        std::vector<uint64_t> cand_off(nc + 1, 0);
+        for (uint32_t c = 0; c < nc; c++) cand_off[c + 1] = cand_off[c] + c_cand[c];
+        n_cand = cand_off[nc];
+        if (n_cand >= (1ull << 31)) FAIL(h, RLSIM_E_UNSUPPORTED, "more than 2^31 selection candidates on one GPU");
+        // plan arrays packed into one u64 buffer: T | base | G | cand_off | pick
+        std::vector<uint64_t> plan;
+        plan.insert(plan.end(), c_T.begin(), c_T.end());
+        plan.insert(plan.end(), c_base.begin(), c_base.end());
+        plan.insert(plan.end(), c_G.begin(), c_G.end());
+        plan.insert(plan.end(), cand_off.begin(), cand_off.end());
+        plan.insert(plan.end(), c_pick.begin(), c_pick.end());
+        CK(h, h->d_plan_u64.ensure(plan.size())); CK(h, h->d_plan_len.ensure(nc)); CK(h, h->d_short.ensure(nc));
+        CK(h, cudaMemcpyAsync(h->d_plan_u64.p, plan.data(), plan.size() * 8, cudaMemcpyHostToDevice, h->st));
+        CK(h, cudaMemcpyAsync(h->d_plan_len.p, c_len.data(), nc * 4, cudaMemcpyHostToDevice, h->st));
+        CK(h, cudaMemsetAsync(h->d_short.p, 0, nc * 4, h->st));
+        DevClassPlan plan_d{nc, h->d_plan_len.p, h->d_plan_u64.p, h->d_plan_u64.p + nc, h->d_plan_u64.p + 2 * nc,
+                            h->d_plan_u64.p + 3 * nc, h->d_plan_u64.p + 4 * nc + 1};
+        CK(h, h->d_cand_keys.ensure(n_cand)); CK(h, h->d_cand_keys_sorted.ensure(n_cand));
+        CK(h, h->d_cand_idx.ensure(n_cand)); CK(h, h->d_cand_idx_sorted.ensure(n_cand));
+        CK(h, h->d_flags.ensure(n_cand)); CK(h, h->d_fscan.ensure(n_cand + 1));
+        StageTimer tm(h, RLSIM_T_SELECT, 5);
+        launch_candidates(h->st, m, plan_d, n_cand, h->d_cand_keys.p, h->d_cand_idx.p);
+        size_t tb = 0;
+        int eb = (int)bits_for(G);
+        CK(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, h->d_cand_keys.p, h->d_cand_keys_sorted.p, h->d_cand_idx.p, h->d_cand_idx_sorted.p, (int)n_cand, 0, eb, h->st));
+        if ((rc = cub_temp(h, tb))) return rc;
+        CK(h, cub::DeviceRadixSort::SortPairs(h->d_cub.p, tb, h->d_cand_keys.p, h->d_cand_keys_sorted.p, h->d_cand_idx.p, h->d_cand_idx_sorted.p, (int)n_cand, 0, eb, h->st));
+        launch_first_flags(h->st, h->d_cand_keys_sorted.p, h->d_cand_idx_sorted.p, n_cand, h->d_flags.p);
+        CK(h, cudaMemsetAsync(h->d_fscan.p, 0, 8, h->st));
+        tb = 0;
+        CK(h, cub::DeviceScan::InclusiveSum(nullptr, tb, h->d_flags.p, h->d_fscan.p + 1, (int)n_cand, h->st));
+        if ((rc = cub_temp(h, tb))) return rc;
+        CK(h, cub::DeviceScan::InclusiveSum(h->d_cub.p, tb, h->d_flags.p, h->d_fscan.p + 1, (int)n_cand, h->st));
+        launch_apply_picks(h->st, plan_d, n_cand, h->d_cand_keys.p, h->d_flags.p, h->d_fscan.p, h->d_cls_pre.p, h->d_bounds.p,
+                           h->d_order.p, h->d_hits.p, h->d_short.p);
+        tm.stop();
+        CK(h, cudaGetLastError());
+        std::vector<int> shortf(nc, 0);
+        CK(h, cudaMemcpyAsync(shortf.data(), h->d_short.p, nc * 4, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaStreamSynchronize(h->st));
+        bool again = false;
+        for (uint32_t c = 0; c < nc; c++)
+            if (shortf[c]) { c_cand[c] = c_cand[c] * 2 + 1024; again = true; }
+        if (!again) break;
+    }
+    // ---- copies drawn per species -> output records
+    {
+        StageTimer tm(h, RLSIM_T_EXPAND, 3);
+        launch_taken(h->st, make_sp(h), h->d_mode.p, n_len, h->d_hits.p, h->d_taken.p);
+        CK(h, cudaMemsetAsync(h->d_out_off.p, 0, 8, h->st));
+        h->n_out = 0;
+        if (ns) {
+            size_t tb = 0;
+            CK(h, cub::DeviceScan::InclusiveSum(nullptr, tb, h->d_taken.p, h->d_out_off.p + 1, (int)ns, h->st));
+            if ((rc = cub_temp(h, tb))) return rc;
+            CK(h, cub::DeviceScan::InclusiveSum(h->d_cub.p, tb, h->d_taken.p, h->d_out_off.p + 1, (int)ns, h->st));
+            CK(h, cudaMemcpyAsync(&h->n_out, h->d_out_off.p + ns, 8, cudaMemcpyDeviceToHost, h->st));
+            CK(h, cudaStreamSynchronize(h->st));
+        }
+        CK(h, h->d_o_tr.ensure(h->n_out)); CK(h, h->d_o_start.ensure(h->n_out)); CK(h, h->d_o_end.ensure(h->n_out));
+        CK(h, h->d_o_minus.ensure(h->n_out)); CK(h, h->d_o_id.ensure(h->n_out));
+        DevSampled out{h->d_o_tr.p, h->d_o_start.p, h->d_o_end.p, h->d_o_minus.p, h->d_o_id.p};
+        launch_expand(h->st, m, make_sp(h), h->d_out_off.p, h->n_out, out);
+        tm.stop();
+        CK(h, cudaGetLastError());
+    }
+    CK(h, cudaStreamSynchronize(h->st));
+    h->sampled = true;
+    return 0;
+}
+
+int rlsim_get_stats(rlsim_handle *h, rlsim_stats *out) {
+    memset(out, 0, sizeof *out);
+    out->n_transcripts = h->h_srclen.size();
+    uint64_t nm = 0;
+    for (uint64_t e : h->h_expr) nm += e;
+    out->n_molecules = nm;
+    out->n_fragments = h->n_frag;
+    out->n_species = h->n_sp;
+    out->pool_total = h->pool_total;
+    out->n_requested = h->req_frags;
+    out->n_sampled = h->sampled ? h->n_out : 0;
+    out->low = h->low; out->high = h->high; out->polya_max = h->polya_max;
+    return 0;
+}
+
+int rlsim_get_hist(rlsim_handle *h, int kind, uint64_t *out, uint32_t n) {
+    const std::vector<uint64_t> *src = nullptr;
+    switch (kind) {
+    case RLSIM_H_TARGET: src = &h->h_target; break;
+    case RLSIM_H_POLYA: src = &h->h_hist_polya; break;
+    case RLSIM_H_AFTER_FRAG: src = &h->h_hist_frag; break;
+    case RLSIM_H_AFTER_PCR: src = &h->h_after_pcr; break;
+    case RLSIM_H_SAMPLED: src = &h->h_sampled; break;
+    case RLSIM_H_MISSING: src = &h->h_missing; break;
+    case RLSIM_H_AFTER_SAMPLING: src = &h->h_after_sampling; break;
+    default: FAIL(h, RLSIM_E_ARG, "unknown histogram kind");
+    }
+    for (uint32_t i = 0; i < n; i++) out[i] = i < src->size() ? (*src)[i] : 0;
+    return 0;
+}
+
+#define D2H(dst, src, bytes) do { if (dst) CK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->st)); } while (0)
+
+int rlsim_get_species(rlsim_handle *h, uint32_t *tr, uint32_t *start, uint32_t *end, uint32_t *count_frag, uint64_t *count_pcr,
+                      double *eff, uint32_t *gc) {
+    if (!h->fragmented) FAIL(h, RLSIM_E_ARG, "rlsim_fragment first");
+    cudaSetDevice(h->device);
+    uint64_t n = h->n_sp;
+    if (!n) return 0;
+    std::vector<uint32_t> len;
+    D2H(tr, h->d_sp_tr.p, n * 4);
+    D2H(start, h->d_sp_start.p, n * 4);
+    D2H(count_frag, h->d_sp_count0.p, n * 4);
+    if (end) { len.resize(n); CK(h, cudaMemcpyAsync(len.data(), h->d_sp_len.p, n * 4, cudaMemcpyDeviceToHost, h->st));
+               if (!start) FAIL(h, RLSIM_E_ARG, "end needs start"); }
+    if (h->amplified) { D2H(count_pcr, h->d_sp_count.p, n * 8); D2H(eff, h->d_sp_eff.p, n * 8); D2H(gc, h->d_sp_gc.p, n * 4); }
+    CK(h, cudaStreamSynchronize(h->st));
+    if (end) for (uint64_t i = 0; i < n; i++) end[i] = start[i] + len[i];
+    if (tr) for (uint64_t i = 0; i < n; i++) tr[i] += h->first_index;
+    return 0;
+}
+
+int rlsim_get_sampled(rlsim_handle *h, uint32_t *tr, uint32_t *start, uint32_t *end, uint8_t *minus_strand, uint64_t *id) {
+    if (!h->sampled) FAIL(h, RLSIM_E_ARG, "rlsim_sample first");
+    cudaSetDevice(h->device);
+    uint64_t n = h->n_out;
+    if (!n) return 0;
+    D2H(tr, h->d_o_tr.p, n * 4); D2H(start, h->d_o_start.p, n * 4); D2H(end, h->d_o_end.p, n * 4);
+    D2H(minus_strand, h->d_o_minus.p, n); D2H(id, h->d_o_id.p, n * 8);
+    CK(h, cudaStreamSynchronize(h->st));
+    if (tr) for (uint64_t i = 0; i < n; i++) tr[i] += h->first_index;
+    return 0;
+}
+
+int rlsim_format_fasta(rlsim_handle *h, const uint8_t *names, const uint64_t *name_off, uint8_t *buf, uint64_t cap,
+                       uint64_t *size_out) {
+    if (!h->sampled) FAIL(h, RLSIM_E_ARG, "rlsim_sample first");
+    cudaSetDevice(h->device);
+    int rc;
+    uint64_t n = h->n_out;
+    uint32_t ntr = (uint32_t)h->h_len.size();
+    *size_out = 0;
+    if (!n) return 0;
+    CK(h, h->d_name_off.ensure(ntr + 1)); CK(h, h->d_names.ensure(name_off[ntr] + 1));
+    CK(h, cudaMemcpyAsync(h->d_name_off.p, name_off, (ntr + 1) * 8, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemcpyAsync(h->d_names.p, names, name_off[ntr], cudaMemcpyHostToDevice, h->st));
+    CK(h, h->d_rec_sizes.ensure(n)); CK(h, h->d_rec_off.ensure(n + 1));
+    DevSampled s{h->d_o_tr.p, h->d_o_start.p, h->d_o_end.p, h->d_o_minus.p, h->d_o_id.p};
+    StageTimer tm(h, RLSIM_T_FORMAT, 3);
+    launch_fasta_sizes(h->st, s, n, h->d_name_off.p, h->first_index, h->d_rec_sizes.p);
+    CK(h, cudaMemsetAsync(h->d_rec_off.p, 0, 8, h->st));
+    size_t tb = 0;
+    CK(h, cub::DeviceScan::InclusiveSum(nullptr, tb, h->d_rec_sizes.p, h->d_rec_off.p + 1, (int)n, h->st));
+    if ((rc = cub_temp(h, tb))) return rc;
+    CK(h, cub::DeviceScan::InclusiveSum(h->d_cub.p, tb, h->d_rec_sizes.p, h->d_rec_off.p + 1, (int)n, h->st));
+    uint64_t total = 0;
+    CK(h, cudaMemcpyAsync(&total, h->d_rec_off.p + n, 8, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    *size_out = total;
+    if (!buf) { tm.stop(); return 0; }
+    if (cap < total) { tm.stop(); FAIL(h, RLSIM_E_ARG, "FASTA buffer too small"); }
+    CK(h, h->d_fasta.ensure(total));
+    launch_fasta_write(h->st, make_tr(h), s, n, h->d_names.p, h->d_name_off.p, h->d_rec_off.p, h->d_fasta.p);
+    tm.stop();
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(buf, h->d_fasta.p, total, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+// ---- probes ----
+int rlsim_probe_kmer_lut(rlsim_handle *h, double *K_out, uint32_t *w_out, uint32_t n) {
+    if (!h->have_model) FAIL(h, RLSIM_E_ARG, "rlsim_set_model first");
+    cudaSetDevice(h->device);
+    uint32_t nk = 1u << (2 * h->p.kmer_len);
+    if (n != nk) FAIL(h, RLSIM_E_ARG, "k-mer table size mismatch");
+    CK(h, h->d_K.ensure(nk)); CK(h, h->d_wq_f.ensure(nk)); CK(h, h->d_wq_r.ensure(nk));
+    launch_kmer_lut(h->st, h->p.kmer_len, h->p.priming_temp, h->d_K.p, h->d_kmax.p, h->d_wq_f.p, h->d_wq_r.p);
+    CK(h, cudaGetLastError());
+    D2H(K_out, h->d_K.p, (size_t)nk * 8);
+    D2H(w_out, h->d_wq_f.p, (size_t)nk * 4);
+    CK(h, cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int rlsim_probe_prefix(rlsim_handle *h, uint32_t tr, int reverse, uint64_t *out, uint32_t n) {
+    if (!h->have_prefix) FAIL(h, RLSIM_E_ARG, "no priming prefix sums (run rlsim_fragment with a priming method)");
+    if (tr >= h->h_len.size()) FAIL(h, RLSIM_E_ARG, "transcript index out of range");
+    if (reverse && !needs_rev(h->p.frag_method)) FAIL(h, RLSIM_E_ARG, "no reverse profile for this method");
+    cudaSetDevice(h->device);
+    uint32_t have = h->h_len[tr] > (uint32_t)h->p.kmer_len ? h->h_len[tr] - h->p.kmer_len + 1 : 1;
+    uint32_t m = std::min(n, have);
+    CK(h, cudaMemcpyAsync(out, (reverse ? h->d_Pr.p : h->d_Pf.p) + h->h_off[tr] + tr, (size_t)m * 8, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int rlsim_probe_gc_prefix(rlsim_handle *h, uint32_t tr, uint32_t *out, uint32_t n) {
+    if (!h->ingested) FAIL(h, RLSIM_E_ARG, "transcripts not ingested yet");
+    if (tr >= h->h_len.size()) FAIL(h, RLSIM_E_ARG, "transcript index out of range");
+    cudaSetDevice(h->device);
+    uint32_t m = std::min(n, h->h_len[tr] + 1);
+    CK(h, cudaMemcpyAsync(out, h->d_gc.p + h->h_off[tr] + tr, (size_t)m * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int rlsim_probe_math(rlsim_handle *h, int fn, const double *x, const double *y, double *out, uint32_t n) {
+    cudaSetDevice(h->device);
+    DBuf<double> dx, dy, dout;
+    CK(h, dx.ensure(n)); CK(h, dy.ensure(n)); CK(h, dout.ensure(n));
+    CK(h, cudaMemcpyAsync(dx.p, x, (size_t)n * 8, cudaMemcpyHostToDevice, h->st));
+    if (y) CK(h, cudaMemcpyAsync(dy.p, y, (size_t)n * 8, cudaMemcpyHostToDevice, h->st));
+    else CK(h, cudaMemsetAsync(dy.p, 0, (size_t)n * 8, h->st));
+    launch_math_probe(h->st, fn, dx.p, dy.p, dout.p, n);
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int rlsim_probe_philox(rlsim_handle *h, const uint32_t *ctr_key6, uint32_t *out4, uint32_t n) {
+    cudaSetDevice(h->device);
+    DBuf<uint32_t> din, dout;
+    CK(h, din.ensure((size_t)n * 6)); CK(h, dout.ensure((size_t)n * 4));
+    CK(h, cudaMemcpyAsync(din.p, ctr_key6, (size_t)n * 24, cudaMemcpyHostToDevice, h->st));
+    launch_philox_probe(h->st, din.p, dout.p, n);
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(out4, dout.p, (size_t)n * 16, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int rlsim_probe_amplify(rlsim_handle *h, int64_t seed_pcr, const uint32_t *tse, const uint64_t *n0, const double *p, int cycles,
+                        uint64_t *out, uint32_t n) {
+    cudaSetDevice(h->device);
+    DBuf<uint32_t> dt;
+    DBuf<uint64_t> dn, dout;
+    DBuf<double> dp;
+    CK(h, dt.ensure((size_t)n * 3)); CK(h, dn.ensure(n)); CK(h, dout.ensure(n)); CK(h, dp.ensure(n));
+    CK(h, cudaMemcpyAsync(dt.p, tse, (size_t)n * 12, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemcpyAsync(dn.p, n0, (size_t)n * 8, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemcpyAsync(dp.p, p, (size_t)n * 8, cudaMemcpyHostToDevice, h->st));
+    launch_amplify_probe(h->st, px_derive_key(seed_pcr, TAG_PCR), dt.p, dn.p, dp.p, cycles, dout.p, n);
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int rlsim_get_timings(rlsim_handle *h, float *ms_out, uint64_t *launches_out) {
+    for (int i = 0; i < RLSIM_T_COUNT; i++) {
+        if (ms_out) ms_out[i] = h->ms[i];
+        if (launches_out) launches_out[i] = h->launches[i];
+    }
+    return 0;
+}
+
+}  // extern "C"

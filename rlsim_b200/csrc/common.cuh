@@ -1,0 +1,63 @@
+// Shared device-side types of librlsim_gpu.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/rlsim_gpu.h"
+#include "philox.cuh"
+
+namespace rl {
+
+// Model parameters as the kernels see them (passed by value as a kernel argument).
+struct DevModel {
+    int32_t k;             // primer length
+    int32_t method;        // RLSIM_AFTER_PRIM ...
+    int32_t frag_param;
+    int32_t cycles;
+    double T;              // priming temperature
+    double loss;           // fragment loss probability
+    double fixed_eff;
+    double strand_bias;
+    int32_t gc_mode;
+    int32_t n_target;      // 0 => raw target
+    int32_t n_polya;
+    int32_t n_raw;
+    double gc_shape, gc_min, gc_max;
+    double len_shape, len_min, len_max;
+    rlsim_mixcomp target[RLSIM_MAX_COMPS];
+    rlsim_mixcomp polya[RLSIM_MAX_COMPS];
+    double raw_location;   // RawTarget pseudo component mean (raw_target.go:76-90)
+    uint32_t low, high;    // Targeter.GetLow/GetHigh
+    uint32_t polya_max;
+    uint32_t first_index;  // global index of this shard's first transcript
+    PxKey key_target, key_frag, key_pcr, key_select, key_strand;
+    // device tables
+    const double *gc_raw;      // [101]
+    const double *len_eff;     // [high-low+1]
+    const uint32_t *raw_len;   // raw target lengths
+    const double *raw_prob;    // raw target probabilities (file order)
+};
+
+// Transcript store, SoA in HBM.
+struct DevTranscripts {
+    uint32_t n;
+    const uint8_t *bases;     // plus strands with polyAmax 'A's appended, each starting at off[t] (multiple of 32)
+    const uint32_t *packed;   // 2-bit codes, 16 bases per word, word index = (off[t] + p) >> 4
+    const uint32_t *nmask;    // 1 bit per base (non-ACGT), 32 bases per word
+    const uint64_t *off;      // [n+1] padded base offsets
+    const uint32_t *len;      // [n] length including the maximal poly-A tail
+    const uint64_t *expr;     // [n]
+    const uint64_t *mol_off;  // [n+1] exclusive scan of expr
+    const uint64_t *Pf, *Pr;  // priming prefix sums, (len+1) entries per transcript at off[t] + t
+    const uint32_t *gc;       // GC prefix counts, (len+1) entries per transcript at off[t] + t
+};
+
+__device__ __forceinline__ uint32_t upper_bound_u64(const uint64_t *a, uint32_t n, uint64_t x) {
+    uint32_t lo = 0, hi = n;  // first i with a[i] > x
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (!(a[mid] > x)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+}  // namespace rl

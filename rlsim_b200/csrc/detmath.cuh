@@ -1,69 +1,55 @@
-/* oracle/detmath.h - deterministic FP64 math kernels of the "--rng=philox" spec.
- *
- * TEST INFRASTRUCTURE ONLY: CPU oracle (see oracle/README.md).  The product has
- * its own implementation of the same spec in rlsim_b200/csrc/detmath.cuh.
- *
- * Every function here is defined purely in terms of IEEE-754 binary64
- * + - * / sqrt floor and integer bit manipulation, evaluated in the written
- * order with NO fused multiply-add (build with -ffp-contract=off; the CUDA side
- * builds with -fmad=false).  Two conforming implementations therefore agree
- * bit for bit, which is what lets a counter-based stream reproduce the exact
- * same fragment set on CPU and GPU (SURVEY.md section 7 hard part 1).
- *
- *   det_log / det_exp : the classic fdlibm argument-reduction + minimax
- *                       polynomial algorithms (e_log.c / e_exp.c), < 1 ulp.
- *   det_ndtri         : Wichura's AS241 PPND16 inverse normal CDF.
- *   det_logfact_tail  : Stirling tail fc(k) = log k! - [(k+1/2)log(k+1) - (k+1) + log(2pi)/2]
- *   det_logfact       : log k!
- *   det_go_pow        : restatement of the *structure* of Go's math.Pow
- *                       (frexp / square-and-multiply / Exp(yf*Log(x))) used by
- *                       the reference at thermocycler.go:85-86,155,177.
- */
-#ifndef ORACLE_DETMATH_H
-#define ORACLE_DETMATH_H
-#include <math.h>
+// Deterministic FP64 math kernels of the "--rng=philox" spec.
+//
+// Defined purely by IEEE-754 binary64 + - * / sqrt floor and integer bit manipulation, evaluated in the
+// written order with NO fused multiply-add: this file must be compiled with -fmad=false.  The CPU oracle
+// restates the same definitions independently; the parity tests require bit equality on random inputs.
+//   det_log / det_exp : fdlibm-style argument reduction + minimax polynomial (< 1 ulp)
+//   det_ndtri         : Wichura AS241 PPND16 inverse normal CDF
+//   det_logfact[_tail]: log k! via Stirling with tail correction
+//   det_go_pow        : the structure of Go's math.Pow, which the reference's efficiency functions use
+//                       (/root/reference/src/thermocycler.go:85-86,155,177)
+#pragma once
 #include <stdint.h>
-#include <string.h>
 
-static inline uint64_t det_bits(double x) { uint64_t u; memcpy(&u, &x, 8); return u; }
-static inline double det_from_bits(uint64_t u) { double x; memcpy(&x, &u, 8); return x; }
+namespace rl {
 
-/* x = m * 2^e with m in [0.5, 1), for finite positive normal or subnormal x. */
-static inline double det_frexp(double x, int *e) {
-    uint64_t u = det_bits(x);
+__device__ __forceinline__ uint64_t d_bits(double x) { return (uint64_t)__double_as_longlong(x); }
+__device__ __forceinline__ double d_from_bits(uint64_t u) { return __longlong_as_double((long long)u); }
+
+__device__ __forceinline__ double det_frexp(double x, int *e) {
+    uint64_t u = d_bits(x);
     int ex = (int)((u >> 52) & 0x7ff);
     int adj = 0;
-    if (ex == 0) { /* subnormal: scale by 2^54 */
+    if (ex == 0) {
         x = x * 18014398509481984.0;
-        u = det_bits(x);
+        u = d_bits(x);
         ex = (int)((u >> 52) & 0x7ff);
         adj = -54;
     }
     *e = ex - 1022 + adj;
     u = (u & 0x800fffffffffffffULL) | 0x3fe0000000000000ULL;
-    return det_from_bits(u);
+    return d_from_bits(u);
 }
 
-/* y * 2^k, y in [0.25, 4]; handles overflow / gradual underflow. */
-static inline double det_ldexp(double y, int k) {
-    const double two_p1023 = det_from_bits((uint64_t)2046 << 52);  /* 2^1023 */
-    const double two_m969 = det_from_bits((uint64_t)54 << 52);     /* 2^-969 */
+__device__ __forceinline__ double det_ldexp(double y, int k) {
+    const double two_p1023 = d_from_bits((uint64_t)2046 << 52);
+    const double two_m969 = d_from_bits((uint64_t)54 << 52);
     if (k > 3000) k = 3000;
     if (k < -3000) k = -3000;
     while (k > 1023) { y = y * two_p1023; k -= 1023; }
     while (k < -1022) { y = y * two_m969; k += 969; }
-    return y * det_from_bits((uint64_t)(k + 1023) << 52);
+    return y * d_from_bits((uint64_t)(k + 1023) << 52);
 }
 
-static inline double det_log(double x) {
+static __device__ __noinline__ double det_log(double x) {
     const double Ln2Hi = 6.93147180369123816490e-01, Ln2Lo = 1.90821492927058770002e-10;
     const double L1 = 6.666666666666735130e-01, L2 = 3.999999999940941908e-01, L3 = 2.857142874366239149e-01,
                  L4 = 2.222219843214978396e-01, L5 = 1.818357216161805012e-01, L6 = 1.531383769920937332e-01,
                  L7 = 1.479819860511658591e-01;
     if (x != x) return x;
-    if (x < 0.0) return det_from_bits(0x7ff8000000000000ULL);
-    if (x == 0.0) return det_from_bits(0xfff0000000000000ULL);
-    if (det_bits(x) == 0x7ff0000000000000ULL) return x;
+    if (x < 0.0) return d_from_bits(0x7ff8000000000000ULL);
+    if (x == 0.0) return d_from_bits(0xfff0000000000000ULL);
+    if (d_bits(x) == 0x7ff0000000000000ULL) return x;
     int ki;
     double f1 = det_frexp(x, &ki);
     if (f1 < 0.70710678118654752440) { f1 = f1 * 2.0; ki--; }
@@ -79,13 +65,13 @@ static inline double det_log(double x) {
     return k * Ln2Hi - ((hfsq - (s * (hfsq + R) + k * Ln2Lo)) - f);
 }
 
-static inline double det_exp(double x) {
+static __device__ __noinline__ double det_exp(double x) {
     const double Ln2Hi = 6.93147180369123816490e-01, Ln2Lo = 1.90821492927058770002e-10,
                  Log2e = 1.44269504088896338700e+00;
     const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05,
                  P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08;
     if (x != x) return x;
-    if (x > 7.09782712893383973096e+02) return det_from_bits(0x7ff0000000000000ULL);
+    if (x > 7.09782712893383973096e+02) return d_from_bits(0x7ff0000000000000ULL);
     if (x < -7.45133219101941108420e+02) return 0.0;
     if (-3.725290298461914e-09 < x && x < 3.725290298461914e-09) return 1.0 + x;
     int k = 0;
@@ -100,8 +86,7 @@ static inline double det_exp(double x) {
     return det_ldexp(y, k);
 }
 
-/* Inverse standard normal CDF, Wichura (1988) algorithm AS241 PPND16, 0<p<1. */
-static inline double det_ndtri(double p) {
+static __device__ __noinline__ double det_ndtri(double p) {
     double q = p - 0.5, r, val;
     if (fabs(q) <= 0.425) {
         r = 0.180625 - q * q;
@@ -134,38 +119,43 @@ static inline double det_ndtri(double p) {
     return q < 0.0 ? -val : val;
 }
 
-/* Stirling tail correction fc(k), k >= 0 integer-valued. */
-static inline double det_logfact_tail(double k) {
-    static const double t[10] = {0.08106146679532726, 0.04134069595540929, 0.02767792568499834,
-                                 0.02079067210376509, 0.01664469118982119, 0.01387612882307075,
-                                 0.01189670994589177, 0.01041126526197209, 0.009255462182712733,
-                                 0.008330563433362871};
-    if (k <= 9.0) return t[(int)k];
+__device__ __forceinline__ double det_logfact_tail(double k) {
+    if (k <= 9.0) {
+        switch ((int)k) {
+        case 0: return 0.08106146679532726;
+        case 1: return 0.04134069595540929;
+        case 2: return 0.02767792568499834;
+        case 3: return 0.02079067210376509;
+        case 4: return 0.01664469118982119;
+        case 5: return 0.01387612882307075;
+        case 6: return 0.01189670994589177;
+        case 7: return 0.01041126526197209;
+        case 8: return 0.009255462182712733;
+        default: return 0.008330563433362871;
+        }
+    }
     double kp1 = k + 1.0;
     double kp1sq = kp1 * kp1;
     return (1.0 / 12.0 - (1.0 / 360.0 - 1.0 / 1260.0 / kp1sq) / kp1sq) / kp1;
 }
 
-/* log k!, k >= 0 integer-valued. */
-static inline double det_logfact(double k) {
+__device__ __forceinline__ double det_logfact(double k) {
     double kp1 = k + 1.0;
     return (k + 0.5) * det_log(kp1) - kp1 + 0.91893853320467274178 + det_logfact_tail(k);
 }
 
-/* Go math.Pow structure (special cases restricted to what the reference can
- * produce: x >= 0 finite, y finite). */
-static inline double det_go_pow(double x, double y) {
+static __device__ __noinline__ double det_go_pow(double x, double y) {
     if (y == 0.0 || x == 1.0) return 1.0;
     if (y == 1.0) return x;
     if (y == 0.5) return sqrt(x);
     if (y == -0.5) return 1.0 / sqrt(x);
-    if (x != x || y != y) return det_from_bits(0x7ff8000000000000ULL);
-    if (x == 0.0) return y < 0.0 ? det_from_bits(0x7ff0000000000000ULL) : 0.0;
+    if (x != x || y != y) return d_from_bits(0x7ff8000000000000ULL);
+    if (x == 0.0) return y < 0.0 ? d_from_bits(0x7ff0000000000000ULL) : 0.0;
     double absy = y;
     int flip = 0;
     if (absy < 0.0) { absy = -absy; flip = 1; }
     double yi = floor(absy), yf = absy - yi;
-    if (yf != 0.0 && x < 0.0) return det_from_bits(0x7ff8000000000000ULL);
+    if (yf != 0.0 && x < 0.0) return d_from_bits(0x7ff8000000000000ULL);
     if (yi >= 9.223372036854775808e18) return det_exp(y * det_log(x));
     double a1 = 1.0;
     int ae = 0;
@@ -175,17 +165,17 @@ static inline double det_go_pow(double x, double y) {
     }
     int xe;
     double x1 = det_frexp(x, &xe);
-    for (int64_t i = (int64_t)yi; i != 0; i >>= 1) {
+    for (long long i = (long long)yi; i != 0; i >>= 1) {
         if (i & 1) { a1 = a1 * x1; ae += xe; }
         x1 = x1 * x1;
         xe <<= 1;
         if (x1 < 0.5) { x1 = x1 + x1; xe--; }
     }
     if (flip) { a1 = 1.0 / a1; ae = -ae; }
-    if (a1 == 0.0 || a1 == det_from_bits(0x7ff0000000000000ULL) || a1 != a1) return a1;
-    /* a1 may be outside [0.25,4] after the loop; renormalise before scaling */
+    if (a1 == 0.0 || a1 == d_from_bits(0x7ff0000000000000ULL) || a1 != a1) return a1;
     int e2;
     double m = det_frexp(a1, &e2);
     return det_ldexp(m, ae + e2);
 }
-#endif
+
+}  // namespace rl

@@ -1,0 +1,333 @@
+// Fragmentation kernels (kernel group 1b): one thread per molecule.
+//
+// Restates, per molecule, transcript.go:139-150 (poly-A tail + Fragment call), transcript.go:279-284
+// (SimulatePolyA), fragmentor.go:95-176 (after_prim / after_prim_double / after_noprim / after_noprim_double),
+// fragmentor.go:205-270 (pre_prim), fragmentor.go:303-351 (prim_jump), nnthermo.go:203-217 (SimulatePriming, as a
+// binary search in the fixed-point prefix sums), fragfilter.go:45-50 (loss filter) and the AfterFrag / PolyALen
+// histogram updates of fragstats.go:80,116.  Kept fragments are emitted as 64-bit keys
+//     key = (global start position << 24) | length          (global start = off[t] + start)
+// so that a radix sort of the keys orders them by (transcript, start, end) and run-length encoding yields the
+// species table (transcript.go:156-215).
+//
+// Molecules whose Poisson draw asks for more than FRAG_LOCAL_BREAKS breakpoints are deferred to k_fragment_long
+// (one CTA per molecule, breakpoints sorted in shared memory).  Every draw is addressed by
+// (transcript, molecule, sub-stream, index), so both kernels produce the same fragments.
+#include "kernels.cuh"
+#include "variates.cuh"
+
+namespace rl {
+
+constexpr int FRAG_THREADS = 128;
+constexpr int FRAG_LOCAL_BREAKS = 48;
+
+struct FragOut {
+    uint64_t *keys;             // fragment keys
+    uint64_t cap;
+    unsigned long long *count;  // number of keys written (may exceed cap: overflow => caller retries)
+    unsigned long long *hist_frag;   // [high+1]
+    unsigned long long *hist_polya;  // [polya_max+1]
+    uint2 *long_list;           // deferred molecules (t, m_lo) + m_hi in long_hi
+    uint32_t *long_hi;
+    uint32_t long_cap;
+    unsigned int *long_count;
+    int *error;                 // RLSIM_E_* raised on the device
+};
+
+__device__ __forceinline__ PxStream mol_stream(const DevModel &m, uint32_t tg, uint64_t mol, uint32_t sub) {
+    return PxStream{m.key_frag, tg, (uint32_t)(mol & 0xffffffffu), (sub << 24) | (uint32_t)((mol >> 32) & 0xffffffu)};
+}
+
+// SimulatePriming, nnthermo.go:203-217, over prefix sums P[0..proflen]
+__device__ __forceinline__ bool priming(const PxStream &iv, uint32_t block, const uint64_t *__restrict__ P,
+                                        uint32_t proflen, uint32_t start, uint32_t end, uint32_t &res) {
+    if (end > proflen) end = proflen;
+    if (start >= end) { res = 0; return true; }
+    uint64_t ps = P[start];
+    uint64_t total = P[end] - ps;
+    if (total == 0) return false;
+    uint64_t tgt = ps + iv.below(block, total);
+    uint32_t lo = start, hi = end;  // smallest i in [start,end) with P[i+1] > tgt
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (!(P[mid + 1] > tgt)) lo = mid + 1; else hi = mid;
+    }
+    res = lo;
+    return true;
+}
+
+__device__ __forceinline__ bool keep_fragment(const DevModel &m, const PxStream &iv, uint32_t i) {  // fragfilter.go:45-50
+    if (m.loss <= 0.0) return true;  // u >= 0 always: the draw cannot change the outcome
+    PxBlock b = iv.block(4 * i + 2);
+    return !(px_u01(px_lo64(b)) < m.loss);
+}
+
+// Emit one fragment: warp-aggregated append + histogram
+__device__ __forceinline__ void emit(const FragOut &o, uint64_t gstart, uint32_t size, unsigned int *hist_s,
+                                     uint32_t hist_s_n, uint32_t low) {
+    unsigned mask = __activemask();
+    int leader = __ffs(mask) - 1;
+    int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(o.count, (unsigned long long)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    unsigned long long pos = base + __popc(mask & ((1u << lane) - 1u));
+    if (pos < o.cap) o.keys[pos] = (gstart << 24) | (uint64_t)size;
+    uint32_t bin = size - low;
+    if (bin < hist_s_n) atomicAdd(&hist_s[bin], 1u);
+    else atomicAdd(&o.hist_frag[size], 1ull);
+}
+
+struct MolCtx {
+    uint32_t t, tg, L, proflen;
+    uint64_t off;
+    const uint64_t *Pf, *Pr;
+};
+
+// One interval of the after_* methods, fragmentor.go:132-175
+__device__ __forceinline__ void after_interval(const DevModel &m, const MolCtx &c, const PxStream &iv, uint32_t i,
+                                               uint32_t start, uint32_t end, const FragOut &o, unsigned int *hist_s,
+                                               uint32_t hist_s_n) {
+    if (end - start < m.low) return;
+    const bool simPriming = (m.method == RLSIM_AFTER_PRIM || m.method == RLSIM_AFTER_PRIM_DOUBLE);
+    const bool doublePrime = (m.method == RLSIM_AFTER_PRIM_DOUBLE || m.method == RLSIM_AFTER_NOPRIM_DOUBLE);
+    uint32_t new_start;
+    if (simPriming) {
+        if (!priming(iv, 4 * i, c.Pf, c.proflen, start, end, new_start)) { atomicExch(o.error, RLSIM_E_PRIMING); return; }
+        if (doublePrime) {
+            uint32_t final = c.L - 1;
+            uint32_t ss = final - end + 1, ee = final - new_start + 1, ns;
+            if (!priming(iv, 4 * i + 1, c.Pr, c.proflen, ss, ee, ns)) { atomicExch(o.error, RLSIM_E_PRIMING); return; }
+            end = final - ns + 1;
+        }
+    } else {
+        new_start = start + (uint32_t)iv.below(4 * i, end - start);
+        if (doublePrime) end = new_start + (uint32_t)iv.below(4 * i + 1, end - new_start);
+    }
+    uint32_t size = end - new_start;
+    if (size < m.low || size > m.high) return;
+    if (!keep_fragment(m, iv, i)) return;
+    emit(o, c.off + new_start, size, hist_s, hist_s_n, m.low);
+}
+
+__device__ __forceinline__ void plain_interval(const DevModel &m, const MolCtx &c, const PxStream &iv, uint32_t i,
+                                               uint32_t start, uint32_t end, const FragOut &o, unsigned int *hist_s,
+                                               uint32_t hist_s_n) {  // fragmentor.go:252-269
+    uint32_t size = end - start;
+    if (size < m.low || size > m.high) return;
+    if (!keep_fragment(m, iv, i)) return;
+    emit(o, c.off + start, size, hist_s, hist_s_n, m.low);
+}
+
+// Header draws shared by both kernels: poly-A tail, mixture component, (pre_prim: elongation), Poisson.
+struct Header {
+    int polyAend;
+    uint32_t tail;
+    int32_t nb;       // number of random breakpoints (>= 1), 0 => molecule yields nothing
+    uint32_t elong;   // pre_prim: first breakpoint
+};
+
+__device__ __forceinline__ double target_location(const DevModel &m, PxCursor &hdr) {
+    if (m.n_target == 0) return m.raw_location;
+    return m.target[px_mix_comp(hdr, m.target, m.n_target)].location;
+}
+
+__device__ __forceinline__ Header mol_header(const DevModel &m, const MolCtx &c, uint64_t mol) {
+    Header h;
+    PxCursor hdr(mol_stream(m, c.tg, mol, SUB_HEADER));
+    h.tail = px_comp_len(hdr, m.polya[px_mix_comp(hdr, m.polya, m.n_polya)]);
+    h.polyAend = (int)c.L - (int)m.polya_max + (int)h.tail;  // transcript.go:283
+    h.nb = 0;
+    h.elong = 0;
+    if (m.method == RLSIM_PRIM_JUMP) return h;
+    int length = h.polyAend;
+    if (length < 1) return h;
+    double loc = target_location(m, hdr);
+    double rate;
+    if (m.method == RLSIM_PRE_PRIM) {
+        double fp = 1.0 / (double)(uint32_t)m.frag_param;
+        double ex = px_expo(hdr) / fp;
+        int el = ex >= (double)length ? length : (int)ex;
+        h.elong = (uint32_t)(length - el);
+        rate = (double)length / loc;
+    } else {
+        rate = m.frag_param == 0 ? ((double)length / loc) / 2.0 : (double)length / (double)(uint32_t)m.frag_param;
+    }
+    int32_t nb = px_poisson(hdr, rate) - 1;  // fragmentor.go:113-117
+    if (nb <= 0) nb = 1;
+    h.nb = nb;
+    if (m.method == RLSIM_PRE_PRIM && (int64_t)length - (int64_t)h.elong < 1) h.nb = 0;  // fragmentor.go:240-243
+    return h;
+}
+
+__device__ void prim_jump(const DevModel &m, const MolCtx &c, uint64_t mol, int polyAend, const FragOut &o,
+                          unsigned int *hist_s, uint32_t hist_s_n) {  // fragmentor.go:303-351
+    int ltmp = (int)c.L - (int)c.proflen;
+    if (polyAend < ltmp) return;
+    uint32_t final = (uint32_t)(polyAend - ltmp);
+    double fp = m.frag_param != 0 ? 1.0 / (double)(uint32_t)m.frag_param : 0.0;
+    PxStream iv = mol_stream(m, c.tg, mol, SUB_INTERVAL);
+    PxCursor jl(mol_stream(m, c.tg, mol, SUB_JUMPLEN));
+    uint32_t start = 0, end = 0, j = 0;
+    while (end < final) {
+        if (!priming(iv, 4 * j, c.Pf, c.proflen, end, final, start)) { atomicExch(o.error, RLSIM_E_PRIMING); return; }
+        uint64_t new_end;
+        if (fp != 0.0) {
+            double ex = px_expo(jl) / fp;
+            new_end = (uint64_t)start + (ex >= 4294967296.0 ? 4294967295ull : (uint64_t)ex);
+        } else {
+            uint32_t l = m.n_target == 0 ? px_raw_len(jl, m) : px_comp_len(jl, m.target[px_mix_comp(jl, m.target, m.n_target)]);
+            new_end = (uint64_t)start + l;
+        }
+        if (new_end > final) new_end = final;
+        end = (uint32_t)new_end;
+        uint32_t size = end - start;
+        uint32_t jj = j++;
+        if (size < m.low || size > m.high) continue;
+        if (!keep_fragment(m, iv, jj)) continue;
+        emit(o, c.off + start, size, hist_s, hist_s_n, m.low);
+    }
+}
+
+__device__ __forceinline__ MolCtx make_ctx(const DevModel &m, const DevTranscripts &tr, uint32_t t) {
+    MolCtx c;
+    c.t = t;
+    c.tg = m.first_index + t;
+    c.L = tr.len[t];
+    c.proflen = c.L > (uint32_t)m.k ? c.L - (uint32_t)m.k : 0;
+    c.off = tr.off[t];
+    c.Pf = tr.Pf ? tr.Pf + c.off + t : nullptr;
+    c.Pr = tr.Pr ? tr.Pr + c.off + t : nullptr;
+    return c;
+}
+
+__global__ void __launch_bounds__(FRAG_THREADS)
+k_fragment(const __grid_constant__ DevModel m, DevTranscripts tr, uint64_t n_mol, FragOut o, uint32_t hist_s_n) {
+    extern __shared__ unsigned int hist_s[];  // [hist_s_n] after-frag bins from `low`, then [polya_max+1]
+    unsigned int *hist_pa = hist_s + hist_s_n;
+    for (uint32_t i = threadIdx.x; i < hist_s_n + m.polya_max + 1; i += FRAG_THREADS) hist_s[i] = 0;
+    __syncthreads();
+    uint64_t g = (uint64_t)blockIdx.x * FRAG_THREADS + threadIdx.x;
+    if (g < n_mol) {
+        uint32_t t = upper_bound_u64(tr.mol_off, tr.n + 1, g) - 1;
+        uint64_t mol = g - tr.mol_off[t];
+        MolCtx c = make_ctx(m, tr, t);
+        Header h = mol_header(m, c, mol);
+        atomicAdd(&hist_pa[h.tail], 1u);
+        if (m.method == RLSIM_PRIM_JUMP) {
+            prim_jump(m, c, mol, h.polyAend, o, hist_s, hist_s_n);
+        } else if (h.nb > FRAG_LOCAL_BREAKS) {
+            unsigned int slot = atomicAdd(o.long_count, 1u);
+            if (slot < o.long_cap) { o.long_list[slot] = make_uint2(t, (uint32_t)(mol & 0xffffffffu)); o.long_hi[slot] = (uint32_t)(mol >> 32); }
+        } else if (h.nb > 0) {
+            uint32_t length = (uint32_t)h.polyAend;
+            uint32_t br[FRAG_LOCAL_BREAKS + 2];
+            PxStream bs = mol_stream(m, c.tg, mol, SUB_BREAKS);
+            uint32_t first = m.method == RLSIM_PRE_PRIM ? h.elong : 0u;
+            uint64_t span = (uint64_t)length - first;
+            br[0] = first;
+            // insertion sort while drawing (fragmentor.go:125-129)
+            int cnt = 1;
+            for (int32_t j = 0; j < h.nb; j++) {
+                uint32_t v = first + (uint32_t)bs.below((uint32_t)j, span);
+                int q = cnt++;
+                while (q > 0 && br[q - 1] > v) { br[q] = br[q - 1]; q--; }
+                br[q] = v;
+            }
+            br[cnt] = length;  // length is >= every draw, so it sorts last
+            PxStream iv = mol_stream(m, c.tg, mol, SUB_INTERVAL);
+            for (int32_t i = 0; i < h.nb; i++) {  // the last interval is never visited (fragmentor.go:132)
+                if (m.method == RLSIM_PRE_PRIM) plain_interval(m, c, iv, (uint32_t)i, br[i], br[i + 1], o, hist_s, hist_s_n);
+                else after_interval(m, c, iv, (uint32_t)i, br[i], br[i + 1], o, hist_s, hist_s_n);
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < hist_s_n; i += FRAG_THREADS)
+        if (hist_s[i]) atomicAdd(&o.hist_frag[m.low + i], (unsigned long long)hist_s[i]);
+    for (uint32_t i = threadIdx.x; i <= m.polya_max; i += FRAG_THREADS)
+        if (hist_pa[i]) atomicAdd(&o.hist_polya[i], (unsigned long long)hist_pa[i]);
+}
+
+// One CTA per deferred molecule: breakpoints drawn in parallel, bitonic-sorted in shared memory, intervals in parallel.
+constexpr int LONG_THREADS = 256;
+__global__ void __launch_bounds__(LONG_THREADS)
+k_fragment_long(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, uint32_t n_long, uint32_t smem_cap) {
+    extern __shared__ uint32_t brs[];  // smem_cap entries (power of two)
+    __shared__ Header hs;
+    uint32_t slot = blockIdx.x;
+    if (slot >= n_long) return;
+    uint32_t t = o.long_list[slot].x;
+    uint64_t mol = (uint64_t)o.long_list[slot].y | ((uint64_t)o.long_hi[slot] << 32);
+    MolCtx c = make_ctx(m, tr, t);
+    if (threadIdx.x == 0) hs = mol_header(m, c, mol);
+    __syncthreads();
+    Header h = hs;
+    uint32_t n = (uint32_t)h.nb + 2;
+    uint32_t npow = 1;
+    while (npow < n) npow <<= 1;
+    if (npow > smem_cap) { if (threadIdx.x == 0) atomicExch(o.error, RLSIM_E_UNSUPPORTED); return; }
+    uint32_t length = (uint32_t)h.polyAend;
+    uint32_t first = m.method == RLSIM_PRE_PRIM ? h.elong : 0u;
+    uint64_t span = (uint64_t)length - first;
+    PxStream bs = mol_stream(m, c.tg, mol, SUB_BREAKS);
+    for (uint32_t j = threadIdx.x; j < npow; j += LONG_THREADS) {
+        uint32_t v;
+        if (j < (uint32_t)h.nb) v = first + (uint32_t)bs.below(j, span);
+        else if (j == (uint32_t)h.nb) v = first;
+        else if (j == (uint32_t)h.nb + 1) v = length;
+        else v = 0xffffffffu;
+        brs[j] = v;
+    }
+    __syncthreads();
+    for (uint32_t k2 = 2; k2 <= npow; k2 <<= 1) {
+        for (uint32_t j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+            for (uint32_t i = threadIdx.x; i < npow; i += LONG_THREADS) {
+                uint32_t ixj = i ^ j2;
+                if (ixj > i) {
+                    uint32_t a = brs[i], b = brs[ixj];
+                    bool up = ((i & k2) == 0);
+                    if ((a > b) == up) { brs[i] = b; brs[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    PxStream iv = mol_stream(m, c.tg, mol, SUB_INTERVAL);
+    for (uint32_t i = threadIdx.x; i < (uint32_t)h.nb; i += LONG_THREADS) {
+        if (m.method == RLSIM_PRE_PRIM) plain_interval(m, c, iv, i, brs[i], brs[i + 1], o, nullptr, 0);
+        else after_interval(m, c, iv, i, brs[i], brs[i + 1], o, nullptr, 0);
+    }
+}
+
+struct FragLaunch {
+    FragOut out;
+};
+
+int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint64_t n_mol, uint64_t *keys,
+                    uint64_t cap, unsigned long long *count, unsigned long long *hist_frag, unsigned long long *hist_polya,
+                    uint2 *long_list, uint32_t *long_hi, uint32_t long_cap, unsigned int *long_count, int *error) {
+    if (n_mol == 0) return 0;
+    FragOut o{keys, cap, count, hist_frag, hist_polya, long_list, long_hi, long_cap, long_count, error};
+    uint32_t hist_s_n = m.high - m.low + 1;
+    if (hist_s_n > 8192) hist_s_n = 0;
+    size_t smem = ((size_t)hist_s_n + m.polya_max + 1) * 4;
+    if (smem > 48 * 1024) { hist_s_n = 0; smem = ((size_t)m.polya_max + 1) * 4; }
+    if (smem > 48 * 1024) return RLSIM_E_UNSUPPORTED;
+    uint64_t blocks = (n_mol + FRAG_THREADS - 1) / FRAG_THREADS;
+    if (blocks > 0x7fffffffull) return RLSIM_E_UNSUPPORTED;
+    k_fragment<<<(unsigned)blocks, FRAG_THREADS, smem, st>>>(m, tr, n_mol, o, hist_s_n);
+    return 0;
+}
+
+int launch_fragment_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint64_t *keys, uint64_t cap,
+                         unsigned long long *count, unsigned long long *hist_frag, unsigned long long *hist_polya,
+                         uint2 *long_list, uint32_t *long_hi, uint32_t n_long, int *error) {
+    if (n_long == 0) return 0;
+    FragOut o{keys, cap, count, hist_frag, hist_polya, long_list, long_hi, n_long, nullptr, error};
+    const uint32_t smem_cap = 32768;  // breakpoints per molecule (128 KB of shared memory)
+    cudaFuncSetAttribute(k_fragment_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_cap * 4));
+    k_fragment_long<<<n_long, LONG_THREADS, smem_cap * 4, st>>>(m, tr, o, n_long, smem_cap);
+    return 0;
+}
+
+}  // namespace rl

@@ -1,0 +1,126 @@
+// PCR kernel (kernel 2): one thread per fragment species.
+//
+// Restates thermocycler.go:106-147 (Techne.Pcr / AmplifyFragment), :149-156 (CalcLengthEff, via a per-length table),
+// :158-180 (CalcGcEff: the byte scan becomes two reads of the GC prefix counts) and the exact per-cycle draw
+// c <- c + Binomial(c, e) of random.go:168-233, from the species' own Philox stream (key_pcr; t, start, end).
+// Algorithmic traffic: 12 B coordinates + 4 B initial count + 2 x 4 B GC prefix + 8 B amplified count = 32 B/species.
+#include "kernels.cuh"
+#include "variates.cuh"
+
+namespace rl {
+
+__global__ void k_decode_species(DevTranscripts tr, const uint64_t *__restrict__ keys, DevSpecies sp) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sp.n) return;
+    uint64_t key = keys[i];
+    uint64_t gstart = key >> 24;
+    uint32_t t = upper_bound_u64(tr.off, tr.n + 1, gstart) - 1;
+    sp.tr[i] = t;
+    sp.start[i] = (uint32_t)(gstart - tr.off[t]);
+    sp.len[i] = (uint32_t)(key & 0xffffffu);
+}
+void launch_decode_species(cudaStream_t st, const DevTranscripts &tr, const uint64_t *keys, DevSpecies sp) {
+    if (sp.n) k_decode_species<<<(unsigned)((sp.n + 255) / 256), 256, 0, st>>>(tr, keys, sp);
+}
+
+// CalcLenScalers + CalcLengthEff, thermocycler.go:83-92,149-156, with the library's restatement of Go's math.Pow
+__global__ void k_len_eff(const __grid_constant__ DevModel m, double *__restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > m.high - m.low) return;
+    if (m.len_shape == 0.0) { out[i] = 1.0; return; }
+    double alpha = det_go_pow((double)m.low, -m.len_shape);
+    double beta = det_go_pow((double)m.high, -m.len_shape);
+    double A = (m.len_max - m.len_min) / (alpha - beta);
+    double B = m.len_min - A * beta;
+    out[i] = A * det_go_pow((double)(m.low + i), -m.len_shape) + B;
+}
+void launch_len_eff(cudaStream_t st, const DevModel &m, double *len_eff) {
+    uint32_t n = m.high - m.low + 1;
+    k_len_eff<<<(n + 127) / 128, 128, 0, st>>>(m, len_eff);
+}
+
+// CalcGcEff, thermocycler.go:158-180
+__device__ __forceinline__ double gc_eff(const DevModel &m, uint32_t gc_count, uint32_t len) {
+    double gc = (double)gc_count / (double)len;
+    if (m.gc_mode == 1) return m.gc_raw[(int)(gc * 100.0)];
+    return m.gc_min + (m.gc_max - m.gc_min) * det_go_pow(1 - det_go_pow(gc, m.gc_shape), m.gc_shape);
+}
+
+// AmplifyFragment, thermocycler.go:133-147
+__device__ __forceinline__ uint64_t amplify(PxCursor &cur, uint64_t c, double e, int cycles, bool &overflow) {
+    for (int cyc = 0; cyc < cycles; cyc++) {
+        uint64_t old = c;
+        c += px_binomial(cur, c, e);
+        if (c < old) { overflow = true; break; }
+    }
+    return c;
+}
+
+constexpr int PCR_THREADS = 128;
+__global__ void __launch_bounds__(PCR_THREADS)
+k_pcr(const __grid_constant__ DevModel m, DevTranscripts tr, DevSpecies sp, int *error) {
+    uint64_t i = (uint64_t)blockIdx.x * PCR_THREADS + threadIdx.x;
+    if (i >= sp.n) return;
+    uint32_t t = sp.tr[i], start = sp.start[i], len = sp.len[i];
+    uint32_t end = start + len;
+    double e = m.fixed_eff;
+    uint32_t gcc = 0;
+    if (e == 0.0 || sp.gc) {
+        const uint32_t *gcp = tr.gc + tr.off[t] + t;
+        gcc = gcp[end] - gcp[start];
+    }
+    if (e == 0.0) e = m.len_eff[len - m.low] * gc_eff(m, gcc, len);
+    PxCursor cur(PxStream{m.key_pcr, m.first_index + t, start, end});
+    bool ovf = false;
+    uint64_t c = amplify(cur, (uint64_t)sp.count0[i], e, m.cycles, ovf);
+    if (ovf) atomicExch(error, RLSIM_E_PCR_OVERFLOW);
+    sp.count[i] = c;
+    if (sp.eff) sp.eff[i] = e;
+    if (sp.gc) sp.gc[i] = gcc;
+}
+void launch_pcr(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, DevSpecies sp, int *error) {
+    if (sp.n) k_pcr<<<(unsigned)((sp.n + PCR_THREADS - 1) / PCR_THREADS), PCR_THREADS, 0, st>>>(m, tr, sp, error);
+}
+
+// ---- probes (parity tests of the building blocks) ----
+__global__ void k_amplify_probe(PxKey key, const uint32_t *tse, const uint64_t *n0, const double *p, int cycles,
+                                uint64_t *out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PxCursor cur(PxStream{key, tse[3 * i], tse[3 * i + 1], tse[3 * i + 2]});
+    bool ovf = false;
+    out[i] = amplify(cur, n0[i], p[i], cycles, ovf);
+}
+void launch_amplify_probe(cudaStream_t st, PxKey key, const uint32_t *tse, const uint64_t *n0, const double *p, int cycles,
+                          uint64_t *out, uint32_t n) {
+    if (n) k_amplify_probe<<<(n + 127) / 128, 128, 0, st>>>(key, tse, n0, p, cycles, out, n);
+}
+
+__global__ void k_math_probe(int fn, const double *x, const double *y, double *out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r;
+    switch (fn) {
+    case 0: r = det_log(x[i]); break;
+    case 1: r = det_exp(x[i]); break;
+    case 2: r = det_ndtri(x[i]); break;
+    case 3: r = det_logfact(x[i]); break;
+    default: r = det_go_pow(x[i], y[i]); break;
+    }
+    out[i] = r;
+}
+void launch_math_probe(cudaStream_t st, int fn, const double *x, const double *y, double *out, uint32_t n) {
+    if (n) k_math_probe<<<(n + 127) / 128, 128, 0, st>>>(fn, x, y, out, n);
+}
+
+__global__ void k_philox_probe(const uint32_t *ck, uint32_t *out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PxBlock b = philox4x32_10(ck[6 * i], ck[6 * i + 1], ck[6 * i + 2], ck[6 * i + 3], ck[6 * i + 4], ck[6 * i + 5]);
+    out[4 * i] = b.v0; out[4 * i + 1] = b.v1; out[4 * i + 2] = b.v2; out[4 * i + 3] = b.v3;
+}
+void launch_philox_probe(cudaStream_t st, const uint32_t *ck, uint32_t *out, uint32_t n) {
+    if (n) k_philox_probe<<<(n + 127) / 128, 128, 0, st>>>(ck, out, n);
+}
+
+}  // namespace rl

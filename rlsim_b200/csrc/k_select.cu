@@ -1,0 +1,180 @@
+// Target sampling, size selection and final draw (kernels 3 + 4, DESIGN.md sections 5.4-5.5).
+//
+//   k_target        : target.go:102-123 / raw_target.go:104-129 - req_frags iid target lengths -> histogram
+//   k_candidates .. : sampler.go:65-106 + pool.go:191-204 + transcript.go:172-187 - for each requested length l,
+//                     draw min(req_l, T_l) of the T_l pooled copies uniformly WITHOUT replacement.  The reference does
+//                     it by sequential weighted draws with decrement (transcript, then fragment); that two-stage
+//                     scheme is a multivariate hypergeometric draw over species, realised here in parallel as
+//                     "the first `pick` distinct values of below(block j, T_l), j = 0,1,..." (spec 4.6):
+//                     candidates -> stable radix sort -> first-occurrence flags -> scan in draw order -> cut at `pick`
+//                     -> rank-to-species binary search in the per-class prefix sums of the amplified counts.
+//   k_expand        : sampler.go:187-227 + frag.go - one record per drawn copy, strand ~ Bernoulli(bias),
+//                     per-transcript ids, output ordered by (transcript, start, end).
+#include "kernels.cuh"
+#include "variates.cuh"
+
+namespace rl {
+
+// ---------------------------------------------------------------- target lengths
+constexpr int TGT_THREADS = 256;
+__global__ void __launch_bounds__(TGT_THREADS)
+k_target(const __grid_constant__ DevModel m, uint64_t n, unsigned long long *__restrict__ hist, uint32_t hist_n, uint32_t smem_bins) {
+    extern __shared__ unsigned int hs[];
+    for (uint32_t i = threadIdx.x; i < smem_bins; i += TGT_THREADS) hs[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * TGT_THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * TGT_THREADS) {
+        PxCursor cur(PxStream{m.key_target, (uint32_t)(i & 0xffffffffu), (uint32_t)(i >> 32), 0u});
+        uint32_t l = m.n_target == 0 ? px_raw_len(cur, m) : px_comp_len(cur, m.target[px_mix_comp(cur, m.target, m.n_target)]);
+        if (l < smem_bins) atomicAdd(&hs[l], 1u);
+        else if (l < hist_n) atomicAdd(&hist[l], 1ull);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < smem_bins; i += TGT_THREADS)
+        if (hs[i]) atomicAdd(&hist[i], (unsigned long long)hs[i]);
+}
+void launch_target(cudaStream_t st, const DevModel &m, uint64_t n, unsigned long long *hist, uint32_t hist_n) {
+    if (!n) return;
+    uint32_t smem_bins = hist_n <= 12000 ? hist_n : 12000;
+    uint64_t blocks = (n + TGT_THREADS - 1) / TGT_THREADS;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_target<<<(unsigned)blocks, TGT_THREADS, smem_bins * 4, st>>>(m, n, hist, hist_n, smem_bins);
+}
+
+// ---------------------------------------------------------------- per-length classes
+__global__ void k_gather_counts(const uint32_t *__restrict__ order, const uint64_t *__restrict__ count,
+                                uint64_t *__restrict__ out, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = count[order[i]];
+}
+void launch_gather_counts(cudaStream_t st, const uint32_t *order, const uint64_t *count, uint64_t *out, uint64_t n) {
+    if (n) k_gather_counts<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(order, count, out, n);
+}
+
+// bounds[l] = first position in the length-sorted species view with length >= l, l = 0..n_len
+__global__ void k_class_bounds(const uint32_t *__restrict__ sorted_len, uint64_t n, uint32_t n_len, uint64_t *__restrict__ bounds) {
+    uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > n_len) return;
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint64_t mid = lo + ((hi - lo) >> 1);
+        if (sorted_len[mid] < l) lo = mid + 1; else hi = mid;
+    }
+    bounds[l] = lo;
+}
+void launch_class_bounds(cudaStream_t st, const uint32_t *sorted_len, uint64_t n, uint32_t n_len, uint64_t *bounds) {
+    k_class_bounds<<<(n_len + 1 + 127) / 128, 128, 0, st>>>(sorted_len, n, n_len, bounds);
+}
+
+// ---------------------------------------------------------------- without-replacement draw
+__device__ __forceinline__ uint32_t class_of(const DevClassPlan &p, uint64_t g) {
+    return upper_bound_u64(p.cand_off, p.n_classes + 1, g) - 1;
+}
+
+__global__ void k_candidates(const __grid_constant__ DevModel m, DevClassPlan plan, uint64_t n_cand, uint64_t *__restrict__ keys,
+                             uint32_t *__restrict__ idx) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_cand) return;
+    uint32_t c = class_of(plan, g);
+    uint32_t j = (uint32_t)(g - plan.cand_off[c]);
+    PxStream s{m.key_select, plan.len[c], 0u, 0u};
+    keys[g] = plan.G[c] + s.below(j, plan.T[c]);
+    idx[g] = (uint32_t)g;
+}
+void launch_candidates(cudaStream_t st, const DevModel &m, DevClassPlan plan, uint64_t n_cand, uint64_t *keys, uint32_t *idx) {
+    if (n_cand) k_candidates<<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(m, plan, n_cand, keys, idx);
+}
+
+// after the stable sort by key: the first entry of each run of equal keys is the earliest draw of that rank
+__global__ void k_first_flags(const uint64_t *__restrict__ sk, const uint32_t *__restrict__ si, uint64_t n,
+                              uint32_t *__restrict__ flags) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    flags[si[p]] = (p == 0 || sk[p] != sk[p - 1]) ? 1u : 0u;
+}
+void launch_first_flags(cudaStream_t st, const uint64_t *sk, const uint32_t *si, uint64_t n, uint32_t *flags) {
+    if (n) k_first_flags<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sk, si, n, flags);
+}
+
+__global__ void k_apply_picks(DevClassPlan plan, uint64_t n_cand, const uint64_t *__restrict__ keys,
+                              const uint32_t *__restrict__ flags, const uint64_t *__restrict__ fscan,
+                              const uint64_t *__restrict__ cls_pre, const uint64_t *__restrict__ bounds,
+                              const uint32_t *__restrict__ order, unsigned long long *__restrict__ hits, int *short_flag) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_cand) return;
+    uint32_t c = class_of(plan, g);
+    uint64_t c0 = plan.cand_off[c];
+    if (g == c0) {  // enough distinct candidates in this class?
+        uint64_t distinct = fscan[plan.cand_off[c + 1]] - fscan[c0];
+        if (distinct < plan.pick[c]) short_flag[c] = 1;
+    }
+    if (!flags[g]) return;
+    if (fscan[g] - fscan[c0] >= plan.pick[c]) return;  // beyond the first `pick` distinct values
+    uint64_t x = keys[g] - plan.G[c];                 // global rank within the class
+    uint32_t l = plan.len[c];
+    uint64_t b = bounds[l], e = bounds[l + 1];
+    uint64_t t_local = cls_pre[e] - cls_pre[b];
+    if (x < plan.base[c] || x - plan.base[c] >= t_local) return;  // another rank's copy
+    uint64_t tgt = cls_pre[b] + (x - plan.base[c]);
+    uint64_t lo = b, hi = e;  // species position with cls_pre[pos] <= tgt < cls_pre[pos+1]
+    while (lo < hi) {
+        uint64_t mid = lo + ((hi - lo) >> 1);
+        if (!(cls_pre[mid + 1] > tgt)) lo = mid + 1; else hi = mid;
+    }
+    atomicAdd(&hits[order[lo]], 1ull);
+}
+void launch_apply_picks(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, const uint64_t *keys, const uint32_t *flags,
+                        const uint64_t *fscan, const uint64_t *cls_pre, const uint64_t *bounds, const uint32_t *order,
+                        unsigned long long *hits, int *short_flag) {
+    if (n_cand)
+        k_apply_picks<<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(plan, n_cand, keys, flags, fscan, cls_pre, bounds,
+                                                                        order, hits, short_flag);
+}
+
+// mode per length: 0 = nothing drawn, 1 = whole class drawn, 2 = hits are the drawn copies, 3 = hits are the excluded copies
+__global__ void k_taken(DevSpecies sp, const uint8_t *__restrict__ mode_by_len, uint32_t n_len,
+                        const unsigned long long *__restrict__ hits, uint64_t *__restrict__ taken) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sp.n) return;
+    uint32_t l = sp.len[i];
+    uint8_t mode = l < n_len ? mode_by_len[l] : 0;
+    uint64_t c = sp.count[i], h = hits[i];
+    taken[i] = mode == 1 ? c : mode == 2 ? h : mode == 3 ? c - h : 0;
+}
+void launch_taken(cudaStream_t st, const DevSpecies &sp, const uint8_t *mode_by_len, uint32_t n_len,
+                  const unsigned long long *hits, uint64_t *taken) {
+    if (sp.n) k_taken<<<(unsigned)((sp.n + 255) / 256), 256, 0, st>>>(sp, mode_by_len, n_len, hits, taken);
+}
+
+// ---------------------------------------------------------------- final records
+__global__ void k_expand(const __grid_constant__ DevModel m, DevSpecies sp, const uint64_t *__restrict__ out_off, uint64_t n_out, DevSampled out) {
+    uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_out) return;
+    // species s with out_off[s] <= o < out_off[s+1]
+    uint64_t lo = 0, hi = sp.n;
+    while (lo < hi) {
+        uint64_t mid = lo + ((hi - lo) >> 1);
+        if (!(out_off[mid + 1] > o)) lo = mid + 1; else hi = mid;
+    }
+    uint64_t s = lo;
+    uint64_t j = o - out_off[s];
+    uint32_t t = sp.tr[s], start = sp.start[s], end = start + sp.len[s];
+    // first species of this transcript -> per-transcript fragment id (sampler.go:189,204)
+    uint64_t a = 0, b = s;
+    while (a < b) {
+        uint64_t mid = a + ((b - a) >> 1);
+        if (sp.tr[mid] < t) a = mid + 1; else b = mid;
+    }
+    PxStream str{m.key_strand, m.first_index + t, start, end};
+    bool minus = px_u01(px_draw64(str, j)) < m.strand_bias;  // sampler.go:219-227
+    out.tr[o] = t;
+    out.start[o] = start;
+    out.end[o] = end;
+    out.minus[o] = minus ? 1 : 0;
+    out.id[o] = o - out_off[a];
+}
+void launch_expand(cudaStream_t st, const DevModel &m, const DevSpecies &sp, const uint64_t *out_off, uint64_t n_out,
+                   DevSampled out) {
+    if (n_out) k_expand<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(m, sp, out_off, n_out, out);
+}
+
+}  // namespace rl

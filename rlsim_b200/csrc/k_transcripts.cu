@@ -1,0 +1,293 @@
+// Transcript ingest and priming-affinity kernels (kernel group 1a).
+//
+//   k_ingest       : transcript.go:98-117 (append polyAmax 'A's) + 2-bit packing + non-ACGT mask + GC prefix counts
+//                    (replaces the per-fragment byte scan of thermocycler.go:161-166)
+//   k_kmer_lut     : nnthermo.go:126-175 KmerAffinity for all 4^k ACGT k-mers (replaces the string-keyed memo map)
+//   k_prefix       : nnthermo.go:177-201 binding profiles, materialised as fixed-point prefix sums so that
+//                    SimulatePriming (nnthermo.go:203-217) becomes a binary search instead of an O(L) cumsum
+#include "kernels.cuh"
+#include "detmath.cuh"
+
+namespace rl {
+
+__device__ __forceinline__ int base_code(uint8_t c) {
+    switch (c) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; default: return -1; }
+}
+
+// ---------------------------------------------------------------- ingest
+// One CTA per transcript; each thread handles 32 consecutive bases per tile.
+constexpr int INGEST_THREADS = 128;
+
+__global__ void __launch_bounds__(INGEST_THREADS)
+k_ingest(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, uint32_t n, uint32_t polya_max,
+         const uint64_t *__restrict__ off, uint8_t *__restrict__ bases, uint32_t *__restrict__ packed,
+         uint32_t *__restrict__ nmask, uint32_t *__restrict__ gc) {
+    __shared__ uint32_t warp_tot[INGEST_THREADS / 32];
+    __shared__ uint32_t carry_s;
+    uint32_t t = blockIdx.x;
+    if (t >= n) return;
+    const uint64_t so = src_off[t];
+    const uint32_t l = (uint32_t)(src_off[t + 1] - so);
+    const uint32_t L = l + polya_max;
+    const uint64_t o = off[t];
+    const uint32_t Lpad = (L + 31u) & ~31u;
+    uint32_t *gcp = gc + o + t;  // (L+1) entries
+    if (threadIdx.x == 0) { carry_s = 0; gcp[0] = 0; }
+    __syncthreads();
+    for (uint32_t tile = 0; tile < Lpad; tile += INGEST_THREADS * 32) {
+        uint32_t p0 = tile + threadIdx.x * 32;
+        uint32_t pk0 = 0, pk1 = 0, mk = 0, cnt = 0;
+        uint32_t bytes[8];
+        if (p0 < Lpad) {
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    uint32_t p = p0 + w * 4 + b;
+                    uint8_t c = p < l ? src[so + p] : (p < L ? (uint8_t)'A' : (uint8_t)0);
+                    word |= (uint32_t)c << (8 * b);
+                    int code = base_code(c);
+                    int i = w * 4 + b;
+                    if (code < 0) { mk |= 1u << i; code = 0; }
+                    if (i < 16) pk0 |= (uint32_t)code << (2 * i); else pk1 |= (uint32_t)code << (2 * (i - 16));
+                    cnt += (c == 'G' || c == 'C');
+                }
+                bytes[w] = word;
+            }
+            uint4 *dst = reinterpret_cast<uint4 *>(bases + o + p0);
+            dst[0] = make_uint4(bytes[0], bytes[1], bytes[2], bytes[3]);
+            dst[1] = make_uint4(bytes[4], bytes[5], bytes[6], bytes[7]);
+            packed[((o + p0) >> 4)] = pk0;
+            packed[((o + p0) >> 4) + 1] = pk1;
+            nmask[(o + p0) >> 5] = mk;
+        }
+        // block exclusive scan of cnt
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((threadIdx.x & 31) >= d) incl += v;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint32_t base = carry_s;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) base += warp_tot[w];
+        uint32_t run = base + incl - cnt;
+        if (p0 < L) {
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    uint32_t p = p0 + w * 4 + b;
+                    uint8_t c = (uint8_t)(bytes[w] >> (8 * b));
+                    run += (c == 'G' || c == 'C');
+                    if (p < L) gcp[p + 1] = run;
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == INGEST_THREADS - 1) carry_s = base + incl;
+        __syncthreads();
+    }
+}
+
+void launch_ingest(cudaStream_t st, const uint8_t *src, const uint64_t *src_off, uint32_t n, uint32_t polya_max,
+                   const uint64_t *off, uint8_t *bases, uint32_t *packed, uint32_t *nmask, uint32_t *gc) {
+    if (n) k_ingest<<<n, INGEST_THREADS, 0, st>>>(src, src_off, n, polya_max, off, bases, packed, nmask, gc);
+}
+
+// ---------------------------------------------------------------- k-mer affinities
+// nnthermo.go:68-104 doublet tables, index 4*a+b with A C G T = 0 1 2 3
+__constant__ double NN_DH[16] = {-7.6, -8.4, -7.8, -7.2, -8.5, -8.0, -10.6, -7.8, -8.2, -9.8, -8.0, -8.4, -7.2, -8.2, -8.5, -7.6};
+__constant__ double NN_DS[16] = {-21.3, -22.4, -21.0, -20.4, -22.7, -19.9, -27.2, -21.0, -22.2, -24.4, -19.9, -22.4, -21.3, -22.2, -22.7, -21.3};
+
+// KmerAffinity over k bytes (any alphabet), nnthermo.go:126-175
+__device__ double kmer_affinity_bytes(const uint8_t *kmer, int kl, double T) {
+    double dH = +0.2, dS = -5.7;
+    for (int i = 0; i <= kl - 2; i++) {
+        int a = base_code(kmer[i]), b = base_code(kmer[i + 1]);
+        if (a >= 0 && b >= 0) { dH += NN_DH[4 * a + b]; dS += NN_DS[4 * a + b]; }
+    }
+    if (kmer[0] == 'A' || kmer[0] == 'T') { dH += 2.2; dS += 6.9; }
+    if (kmer[kl - 1] == 'A' || kmer[kl - 1] == 'T') { dH += 2.2; dS += 6.9; }
+    bool sym = true;
+    for (int j = 0; j <= kl / 2; j++)
+        if (kmer[j] != kmer[kl - j - 1]) { sym = false; break; }
+    if (sym) dS += -1.4;
+    double e = dH - (T * dS) / 1000.0;
+    return det_exp(-e / (1.9872 * T));
+}
+
+// code: base i of the k-mer in bits [2i, 2i+2)
+__global__ void k_kmer_lut(int k, double T, double *__restrict__ K, unsigned long long *__restrict__ kmax_bits) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = 1u << (2 * k);
+    if (c >= n) return;
+    uint8_t kmer[16];
+    for (int i = 0; i < k; i++) kmer[i] = (uint8_t)("ACGT"[(c >> (2 * i)) & 3]);
+    double v = kmer_affinity_bytes(kmer, k, T);
+    K[c] = v;
+    atomicMax(kmax_bits, (unsigned long long)__double_as_longlong(v));  // positive doubles order like their bit patterns
+}
+
+__device__ __forceinline__ uint32_t quantize(double K, double scale) {
+    double x = K * scale + 0.5;
+    if (!(x < 4294967295.0)) return 4294967295u;
+    return (uint32_t)x;
+}
+
+__device__ __forceinline__ uint32_t rc_code(uint32_t c, int k) {
+    uint32_t r = 0;
+    for (int i = 0; i < k; i++) r |= (3u - ((c >> (2 * i)) & 3u)) << (2 * (k - 1 - i));
+    return r;
+}
+
+// wq_f[c] = weight of the k-mer c;  wq_r[c] = weight of its reverse complement
+__global__ void k_kmer_quant(int k, const double *__restrict__ K, const unsigned long long *__restrict__ kmax_bits,
+                             uint32_t *__restrict__ wq_f, uint32_t *__restrict__ wq_r) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = 1u << (2 * k);
+    if (c >= n) return;
+    double scale = 4294967296.0 / __longlong_as_double((long long)*kmax_bits);
+    wq_f[c] = quantize(K[c], scale);
+    wq_r[c] = quantize(K[rc_code(c, k)], scale);
+}
+
+void launch_kmer_lut(cudaStream_t st, int k, double T, double *K, unsigned long long *kmax_bits, uint32_t *wq_f,
+                     uint32_t *wq_r) {
+    uint32_t n = 1u << (2 * k);
+    cudaMemsetAsync(kmax_bits, 0, 8, st);
+    k_kmer_lut<<<(n + 127) / 128, 128, 0, st>>>(k, T, K, kmax_bits);
+    k_kmer_quant<<<(n + 127) / 128, 128, 0, st>>>(k, K, kmax_bits, wq_f, wq_r);
+}
+
+// ---------------------------------------------------------------- priming prefix sums
+constexpr int PFX_THREADS = 256;
+constexpr int PFX_ITEMS = 8;
+constexpr int PFX_TILE = PFX_THREADS * PFX_ITEMS;
+constexpr int PFX_STAGE_WORDS = PFX_TILE / 16 + 4;
+constexpr int PFX_STAGE_MASK = PFX_TILE / 32 + 4;
+
+// grid = (transcripts, strands).  Forward profile entry i is the k-mer at plus[i, i+k); reverse entry i is the
+// reverse complement of plus[j, j+k), j = L-k-i (= minus[i, i+k), transcript.go:110 + nnthermo.go:184-199).
+// Both have L-k entries (nnthermo.go:193).  Output P[0..L-k]: exclusive prefix sums of the fixed-point weights.
+__global__ void __launch_bounds__(PFX_THREADS)
+k_prefix(DevTranscripts tr, int k, double T, const uint32_t *__restrict__ wq_f, const uint32_t *__restrict__ wq_r,
+         const unsigned long long *__restrict__ kmax_bits, uint64_t *__restrict__ Pf, uint64_t *__restrict__ Pr,
+         int lut_in_smem) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *stage_out = reinterpret_cast<uint64_t *>(smem_raw);                    // PFX_TILE u64
+    uint32_t *stage_pk = reinterpret_cast<uint32_t *>(stage_out + PFX_TILE);         // PFX_STAGE_WORDS
+    uint32_t *stage_mk = stage_pk + PFX_STAGE_WORDS;                                 // PFX_STAGE_MASK
+    uint64_t *warp_tot = reinterpret_cast<uint64_t *>(stage_mk + PFX_STAGE_MASK + ((PFX_STAGE_WORDS + PFX_STAGE_MASK) & 1));
+    uint32_t *lut_s = reinterpret_cast<uint32_t *>(warp_tot + PFX_THREADS / 32 + 1);
+
+    const uint32_t t = blockIdx.x;
+    const int reverse = blockIdx.y;
+    if (tr.expr[t] == 0) return;  // pool.go:104: never fragmented
+    const uint32_t L = tr.len[t];
+    const uint64_t o = tr.off[t];
+    uint64_t *P = (reverse ? Pr : Pf) + o + t;
+    const uint32_t *lut = reverse ? wq_r : wq_f;
+    if (lut_in_smem) {
+        uint32_t n = 1u << (2 * k);
+        for (uint32_t i = threadIdx.x; i < n; i += PFX_THREADS) lut_s[i] = lut[i];
+        lut = lut_s;
+    }
+    if (threadIdx.x == 0) P[0] = 0;
+    if (L <= (uint32_t)k) return;
+    const uint32_t proflen = L - (uint32_t)k;
+    const double scale = 4294967296.0 / __longlong_as_double((long long)*kmax_bits);
+    const uint32_t kmask = (k == 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
+    const uint32_t mmask = (1u << k) - 1u;
+    const uint64_t pk_base = o >> 4, mk_base = o >> 5;
+    uint64_t carry = 0;
+
+    for (uint32_t i0 = 0; i0 < proflen; i0 += PFX_TILE) {
+        uint32_t ntile = min((uint32_t)PFX_TILE, proflen - i0);
+        // plus-strand window range covered by this tile
+        uint32_t jlo, jhi;  // inclusive window starts
+        if (!reverse) { jlo = i0; jhi = i0 + ntile - 1; }
+        else { jhi = L - k - i0; jlo = L - k - (i0 + ntile - 1); }
+        uint32_t w_lo = jlo >> 4, w_hi = (jhi + k - 1) >> 4;
+        uint32_t m_lo = jlo >> 5, m_hi = (jhi + k - 1) >> 5;
+        __syncthreads();
+        for (uint32_t w = threadIdx.x; w <= w_hi - w_lo + 1; w += PFX_THREADS) stage_pk[w] = tr.packed[pk_base + w_lo + w];
+        for (uint32_t w = threadIdx.x; w <= m_hi - m_lo + 1; w += PFX_THREADS) stage_mk[w] = tr.nmask[mk_base + m_lo + w];
+        __syncthreads();
+
+        uint64_t x[PFX_ITEMS];
+        uint64_t run = 0;
+#pragma unroll
+        for (int r = 0; r < PFX_ITEMS; r++) {
+            uint32_t i = i0 + threadIdx.x * PFX_ITEMS + r;
+            uint64_t w = 0;
+            if (i < proflen) {
+                uint32_t j = reverse ? (L - k - i) : i;
+                uint32_t wi = (j >> 4) - w_lo;
+                uint64_t two = (uint64_t)stage_pk[wi] | ((uint64_t)stage_pk[wi + 1] << 32);
+                uint32_t code = (uint32_t)(two >> (2 * (j & 15))) & kmask;
+                uint32_t mi = (j >> 5) - m_lo;
+                uint64_t mtwo = (uint64_t)stage_mk[mi] | ((uint64_t)stage_mk[mi + 1] << 32);
+                uint32_t mbits = (uint32_t)(mtwo >> (j & 31)) & mmask;
+                if (mbits == 0) {
+                    w = lut[code];
+                } else {
+                    // non-ACGT letters in the window: evaluate KmerAffinity on the raw bytes
+                    uint8_t kmer[16];
+                    const uint8_t *b = tr.bases + o + j;
+                    if (!reverse) {
+                        for (int q = 0; q < k; q++) kmer[q] = b[q];
+                    } else {
+                        for (int q = 0; q < k; q++) {  // utils.go:37-59
+                            uint8_t c = b[k - 1 - q], oc;
+                            switch (c) { case 'A': oc = 'T'; break; case 'T': oc = 'A'; break; case 'G': oc = 'C'; break; case 'C': oc = 'G'; break; default: oc = 'N'; }
+                            kmer[q] = oc;
+                        }
+                    }
+                    w = quantize(kmer_affinity_bytes(kmer, k, T), scale);
+                }
+            }
+            run += w;
+            x[r] = run;
+        }
+        // block-wide exclusive scan of the per-thread totals
+        uint64_t incl = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((threadIdx.x & 31) >= d) incl += v;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint64_t base = carry;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) base += warp_tot[w];
+        uint64_t excl = base + incl - run;
+#pragma unroll
+        for (int r = 0; r < PFX_ITEMS; r++) stage_out[threadIdx.x * PFX_ITEMS + r] = excl + x[r];
+        uint64_t tile_total = 0;
+        for (int w = 0; w < PFX_THREADS / 32; w++) tile_total += warp_tot[w];
+        carry += tile_total;
+        __syncthreads();
+        for (uint32_t q = threadIdx.x; q < ntile; q += PFX_THREADS) P[i0 + 1 + q] = stage_out[q];
+    }
+}
+
+size_t prefix_smem_bytes(int k, int *lut_in_smem) {
+    size_t base = (size_t)PFX_TILE * 8 + (PFX_STAGE_WORDS + PFX_STAGE_MASK + 1) * 4 + (PFX_THREADS / 32 + 1) * 8;
+    *lut_in_smem = (k <= 6);
+    return base + (*lut_in_smem ? ((size_t)4 << (2 * k)) : 0);
+}
+
+void launch_prefix(cudaStream_t st, const DevTranscripts &tr, int k, double T, const uint32_t *wq_f, const uint32_t *wq_r,
+                   const unsigned long long *kmax_bits, uint64_t *Pf, uint64_t *Pr, int strands) {
+    if (!tr.n) return;
+    int lut_in_smem;
+    size_t smem = prefix_smem_bytes(k, &lut_in_smem);
+    cudaFuncSetAttribute(k_prefix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(tr.n, strands);
+    k_prefix<<<grid, PFX_THREADS, smem, st>>>(tr, k, T, wq_f, wq_r, kmax_bits, Pf, Pr, lut_in_smem);
+}
+
+}  // namespace rl

@@ -1,0 +1,71 @@
+// Launch prototypes of the kernel translation units (host side glue in api.cu).
+#pragma once
+#include "common.cuh"
+
+namespace rl {
+
+// k_transcripts.cu
+void launch_ingest(cudaStream_t st, const uint8_t *src, const uint64_t *src_off, uint32_t n, uint32_t polya_max,
+                   const uint64_t *off, uint8_t *bases, uint32_t *packed, uint32_t *nmask, uint32_t *gc);
+void launch_kmer_lut(cudaStream_t st, int k, double T, double *K, unsigned long long *kmax_bits, uint32_t *wq_f,
+                     uint32_t *wq_r);
+void launch_prefix(cudaStream_t st, const DevTranscripts &tr, int k, double T, const uint32_t *wq_f, const uint32_t *wq_r,
+                   const unsigned long long *kmax_bits, uint64_t *Pf, uint64_t *Pr, int strands);
+
+// k_fragment.cu
+int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint64_t n_mol, uint64_t *keys,
+                    uint64_t cap, unsigned long long *count, unsigned long long *hist_frag, unsigned long long *hist_polya,
+                    uint2 *long_list, uint32_t *long_hi, uint32_t long_cap, unsigned int *long_count, int *error);
+int launch_fragment_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint64_t *keys, uint64_t cap,
+                         unsigned long long *count, unsigned long long *hist_frag, unsigned long long *hist_polya,
+                         uint2 *long_list, uint32_t *long_hi, uint32_t n_long, int *error);
+
+// k_pcr.cu
+struct DevSpecies {
+    uint64_t n;
+    uint32_t *tr, *start, *len;   // sorted by (tr, start, len)
+    uint32_t *count0;             // copies after fragmentation
+    uint64_t *count;              // copies after PCR
+    double *eff;                  // optional (tests): per-species efficiency
+    uint32_t *gc;                 // optional (tests): GC count
+};
+void launch_decode_species(cudaStream_t st, const DevTranscripts &tr, const uint64_t *keys, DevSpecies sp);
+void launch_len_eff(cudaStream_t st, const DevModel &m, double *len_eff);
+void launch_pcr(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, DevSpecies sp, int *error);
+void launch_amplify_probe(cudaStream_t st, PxKey key, const uint32_t *tse, const uint64_t *n0, const double *p, int cycles,
+                          uint64_t *out, uint32_t n);
+void launch_math_probe(cudaStream_t st, int fn, const double *x, const double *y, double *out, uint32_t n);
+void launch_philox_probe(cudaStream_t st, const uint32_t *ck, uint32_t *out, uint32_t n);
+
+// k_select.cu
+void launch_target(cudaStream_t st, const DevModel &m, uint64_t n, unsigned long long *hist, uint32_t hist_n);
+void launch_gather_counts(cudaStream_t st, const uint32_t *order, const uint64_t *count, uint64_t *out, uint64_t n);
+void launch_class_bounds(cudaStream_t st, const uint32_t *sorted_len, uint64_t n, uint32_t n_len, uint64_t *bounds);
+struct DevClassPlan {          // per requested length class (host-built, device-resident)
+    uint32_t n_classes;
+    const uint32_t *len;       // class length
+    const uint64_t *T;         // global total of the class
+    const uint64_t *base;      // this rank's first global rank within the class
+    const uint64_t *G;         // exclusive prefix of T over the classes (sort-key offset)
+    const uint64_t *cand_off;  // [n_classes+1] candidate index range of the class
+    const uint64_t *pick;      // number of distinct ranks to keep
+};
+void launch_candidates(cudaStream_t st, const DevModel &m, DevClassPlan plan, uint64_t n_cand, uint64_t *keys,
+                       uint32_t *idx);
+void launch_first_flags(cudaStream_t st, const uint64_t *sorted_keys, const uint32_t *sorted_idx, uint64_t n, uint32_t *flags);
+void launch_apply_picks(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, const uint64_t *keys_by_idx,
+                        const uint32_t *flags, const uint64_t *flag_scan, const uint64_t *cls_pre,
+                        const uint64_t *bounds, const uint32_t *order, unsigned long long *hits, int *short_flag);
+void launch_taken(cudaStream_t st, const DevSpecies &sp, const uint8_t *mode_by_len, uint32_t n_len,
+                  const unsigned long long *hits, uint64_t *taken);
+struct DevSampled { uint32_t *tr, *start, *end; uint8_t *minus; uint64_t *id; };
+void launch_expand(cudaStream_t st, const DevModel &m, const DevSpecies &sp, const uint64_t *out_off, uint64_t n_out,
+                   DevSampled out);
+
+// k_fasta.cu
+void launch_fasta_sizes(cudaStream_t st, const DevSampled &s, uint64_t n, const uint64_t *name_off, uint32_t first_index,
+                        uint64_t *sizes);
+void launch_fasta_write(cudaStream_t st, const DevTranscripts &tr, const DevSampled &s, uint64_t n, const uint8_t *names,
+                        const uint64_t *name_off, const uint64_t *rec_off, uint8_t *out);
+
+}  // namespace rl

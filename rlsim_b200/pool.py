@@ -1,0 +1,100 @@
+"""GpuPool / GpuSampler: the two batch seams of the reference, backed by librlsim_gpu.so.
+
+    GpuPool.init_transcripts   = Pooler.InitTranscripts   (/root/reference/src/pool.go:83-135)
+    GpuSampler.sample_fragments = Sampler.SampleFragments (/root/reference/src/sampler.go:108-154)
+
+Everything between them (per-molecule fragmentation, per-species PCR, per-length pools, without-replacement
+draws) runs on the device; this file only moves buffers and, with more than one rank, performs the single
+all-gather of per-length pool totals.
+"""
+import numpy as np
+
+from . import _native, shard
+from .args import CmdArgs
+
+
+class FragStats:
+    """fragstats.go:45-56: the histograms the report needs, filled from the library's counters."""
+
+    def __init__(self):
+        self.expr_levels, self.tr_lengths = {}, {}
+        self.after_frag = self.after_pcr = self.after_sampling = self.sampled = self.missing = self.polya_len = None
+        self.total_frags = 0
+        self.nr_sampled = 0
+
+    def update_input(self, seq_len, level):  # input.go:114-117
+        self.tr_lengths[seq_len] = self.tr_lengths.get(seq_len, 0) + level
+        self.expr_levels[level & 0xffffffff] = self.expr_levels.get(level & 0xffffffff, 0) + 1
+
+
+def _nz(h):
+    return {int(i): int(h[i]) for i in np.nonzero(h)[0]}
+
+
+class GpuPool:
+    def __init__(self, device=0, rank=0, world=1, dist_device=None):
+        self.handle = _native.Handle(device)
+        self.rank, self.world, self.dist_device = rank, world, dist_device
+        self.names = []
+        self.first = 0
+
+    def configure(self, args: CmdArgs):
+        """NewFragmentor + NewTechne + NewTarget + NewLenSampler, main.go:88-127."""
+        self.args = args
+        self.params = args.to_params()
+        h = self.handle
+        h.set_model(self.params)
+        if args.raw_len_probs is not None:
+            h.set_raw_target(args.raw_len_probs.lengths, args.raw_len_probs.probs)
+        h.sample_target(args.req_frags)  # same histogram on every rank (stream keyed by the draw index)
+        return self
+
+    def init_transcripts(self, names, seqs, levels, stats: FragStats = None):
+        """pool.go:83-135 for this rank's contiguous shard of the input."""
+        h = self.handle
+        n = len(seqs)
+        if stats is not None:
+            for s, lv in zip(seqs, levels):
+                stats.update_input(len(s), lv)
+        bounds = shard.contiguous_partition(shard.work_estimate([len(s) for s in seqs], levels), self.world)
+        a, b = bounds[self.rank], bounds[self.rank + 1]
+        self.first, self.names = a, names[a:b]
+        h.set_first_index(a)
+        h.add_transcripts(seqs[a:b], levels[a:b])
+        h.build_library()
+        if stats is not None:
+            st = h.stats()
+            red = lambda x: shard.allreduce_hist(x, device=self.dist_device)
+            stats.after_frag = _nz(red(h.hist(_native.H_AFTER_FRAG, int(st.high) + 1)))
+            stats.polya_len = _nz(red(h.hist(_native.H_POLYA, int(st.polya_max) + 1)))
+        return self
+
+
+class GpuSampler:
+    def __init__(self, strand_bias=0.5):
+        self.strand_bias = strand_bias  # already part of the model block; kept for interface parity (sampler.go:59)
+
+    def sample_fragments(self, pool: GpuPool, stats: FragStats = None):
+        """sampler.go:108-154.  -> dict of arrays (tr, start, end, minus, id) for this rank's shard."""
+        h = pool.handle
+        local = h.class_totals()
+        total, base = shard.allgather_totals(local, device=pool.dist_device)
+        h.sample(total, base)
+        if stats is not None:
+            n = len(total)
+            stats.after_pcr = _nz(total)
+            stats.total_frags = int(total.sum(dtype=np.uint64)) if float(total.sum(dtype=np.float64)) < 1.8e19 else None
+            if stats.total_frags is None:
+                raise OverflowError("Integer overflow when updating total fragment count!")
+            tn = max(n, int(h.stats().high) + 2)
+            stats.sampled = {k: v for k, v in _nz(h.hist(_native.H_SAMPLED, tn)).items()}
+            tgt = h.hist(_native.H_TARGET, tn)
+            smp = h.hist(_native.H_SAMPLED, tn)
+            mis = h.hist(_native.H_MISSING, tn)
+            asm = h.hist(_native.H_AFTER_SAMPLING, tn)
+            req = np.nonzero(tgt)[0]
+            stats.sampled = {int(l): int(smp[l]) for l in req}    # sampler.go:95
+            stats.missing = {int(l): int(mis[l]) for l in req}    # sampler.go:101
+            stats.after_sampling = {int(l): int(asm[l]) for l in np.nonzero(total)[0]}  # fragstats.go:86,97-102
+            stats.nr_sampled = int(smp.sum())
+        return h.sampled()

@@ -1,0 +1,179 @@
+"""GPU parity: the CUDA path (through the C ABI) must reproduce the oracle's philox mode bit for bit."""
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def h0(gpu):
+    return gpu.Handle(0)
+
+
+def test_philox_blocks(gpu, oracle, h0):
+    rng = np.random.default_rng(0)
+    ck = rng.integers(0, 2**32, size=(4096, 6), dtype=np.uint64).astype(np.uint32)
+    ck[0] = 0
+    ck[1] = 0xFFFFFFFF
+    ck[2] = [0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344, 0xA4093822, 0x299F31D0]
+    got = h0.probe_philox(ck)
+    assert list(got[0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]  # Random123 known answers
+    assert list(got[1]) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert list(got[2]) == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+    L = oracle.lib()
+    out = np.zeros(4, dtype=np.uint32)
+    for i in range(0, 4096, 37):
+        c, k = np.ascontiguousarray(ck[i, :4]), np.ascontiguousarray(ck[i, 4:])
+        L.orc_philox(c.ctypes.data, k.ctypes.data, out.ctypes.data)
+        assert list(out) == list(got[i])
+
+
+@pytest.mark.parametrize("fn,name", [(0, "orc_det_log"), (1, "orc_det_exp"), (2, "orc_det_ndtri"), (3, "orc_det_logfact")])
+def test_detmath_bit_exact(oracle, h0, fn, name):
+    rng = np.random.default_rng(fn)
+    if fn == 0:
+        x = np.concatenate([np.exp(rng.uniform(-700, 700, 20000)), rng.uniform(0, 2, 20000), [1.0, 5e-324, 1e308]])
+    elif fn == 1:
+        x = np.concatenate([rng.uniform(-745, 709, 20000), rng.uniform(-1, 1, 20000), [0.0, -1e-10, 800.0, -800.0]])
+    elif fn == 2:
+        x = np.concatenate([rng.uniform(0, 1, 30000), 10.0 ** rng.uniform(-300, -1, 5000), 1 - 10.0 ** rng.uniform(-15, -1, 5000)])
+        x = x[(x > 0) & (x < 1)]
+    else:
+        x = np.concatenate([np.arange(0, 300, dtype=np.float64), np.floor(10.0 ** rng.uniform(2, 18, 5000))])
+    got = h0.probe_math(fn, x)
+    f = getattr(oracle.lib(), name)
+    want = np.array([f(float(v)) for v in x])
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+
+
+def test_go_pow_bit_exact(oracle, h0):
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(0, 1, 5000), rng.uniform(1, 5000, 5000)])
+    y = rng.choice([-0.1, 0.1, 0.4, 1.0, 2.0, 3.5, -2.3, 8.0, 0.5, -0.5, 0.0], size=len(x))
+    got = h0.probe_math(4, x, y)
+    want = np.array([oracle.lib().orc_det_go_pow(float(a), float(b)) for a, b in zip(x, y)])
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+
+
+def test_amplify_bit_exact(oracle, h0):
+    """thermocycler.go:133-147 on arbitrary (species, count, efficiency): covers the inversion and BTRS branches,
+    p in {0, 1}, p > 0.5 and counts up to 1e12."""
+    rng = np.random.default_rng(11)
+    n = 3000
+    tse = rng.integers(0, 2**31, size=(n, 3)).astype(np.uint32)
+    n0 = np.concatenate([rng.integers(1, 30, 1000), rng.integers(30, 10**6, 1000), rng.integers(10**6, 10**12, 1000)]).astype(np.uint64)
+    p = rng.uniform(0, 1, n)
+    p[:10] = 0.0
+    p[10:20] = 1.0
+    p[20:40] = 1e-9
+    for cycles in (1, 11):
+        got = h0.probe_amplify(77, tse, n0, p, cycles)
+        L = oracle.lib()
+        want = np.array([L.orc_px_binomial(77, int(a), int(b), int(c), int(m), float(q), cycles)
+                         for (a, b, c), m, q in zip(tse, n0, p)], dtype=np.uint64)
+        assert np.array_equal(got, want)
+
+
+def _compare(oracle, native, argv, seqs_override=None, seed=("-si", "42"), check_fasta=True):
+    args = util.parse(list(argv) + list(seed))
+    names, seqs, levels = util.transcripts(args) if seqs_override is None else seqs_override
+    o = util.run_oracle(oracle, args, names, seqs, levels, oracle.MODE_PHILOX, stages="pcr")
+    so = o.species()  # amplified counts, before the draw decrements them
+    o.sample()
+    h = util.run_gpu(native, args, names, seqs, levels)
+    st = h.stats()
+    assert (st.low, st.high, st.polya_max) == (o.low, o.high, o.polya_max)
+    for kind in (oracle.H_TARGET, oracle.H_POLYA, oracle.H_AFTER_FRAG, oracle.H_AFTER_PCR, oracle.H_SAMPLED,
+                 oracle.H_MISSING, oracle.H_AFTER_SAMPLING):
+        assert h.hist_dict(kind, 1 << 16) == o.hist_dict(kind), "histogram %d" % kind
+    sg = h.species()
+    assert st.n_species == len(so["tr"])
+    for k in ("tr", "start", "end", "gc"):
+        assert np.array_equal(so[k], sg[k]), k
+    assert np.array_equal(so["count0"], sg["count0"].astype(np.uint64))
+    assert np.array_equal(so["count"], sg["count"]), "amplified copy numbers"
+    assert np.array_equal(so["eff"].view(np.uint64), sg["eff"].view(np.uint64)), "per-species efficiency"
+    assert st.pool_total == o.pool_total
+    fo, fg = o.sampled(), h.sampled()
+    for k in ("tr", "start", "end", "minus", "id"):
+        assert np.array_equal(fo[k], fg[k]), k
+    if check_fasta:
+        assert h.fasta(names) == o.fasta(names)
+    return o, h
+
+
+@pytest.mark.parametrize("name", sorted(util.PIN_CONFIGS))
+def test_full_path_bit_exact(oracle, gpu, name):
+    _compare(oracle, gpu, util.PIN_CONFIGS[name], seed=("-si", str(util.pin_seed(name))))
+
+
+def test_seed_policy(oracle, gpu):
+    """main.go:129-149: -sp / -ss re-key PCR and sampling only."""
+    _compare(oracle, gpu, util.C1 + ["-sp", "5", "-ss", "9"])
+    _compare(oracle, gpu, util.C1 + ["-sp", "5"])
+
+
+def test_raw_params(oracle, gpu):
+    """-j raw_params.json: raw target + raw GC table, 12 cycles (src/Makefile `t` target)."""
+    _compare(oracle, gpu, ["-j", util.RAW_PARAMS, "-n", "20000"])
+    _compare(oracle, gpu, ["-j", util.RAW_PARAMS, "-n", "5000", "-jm", "0.5", "-f", "prim_jump"])
+
+
+def test_fixed_efficiency_doubling(gpu):
+    """-e 1.0 -c 11: Binomial(n, 1) = n on every branch => after-PCR histogram = 2048 x after-fragmentation
+    (the release binary shows the same identity)."""
+    args = util.parse(util.C1 + ["-e", "1.0", "-si", "3"])
+    names, seqs, levels = util.transcripts(args)
+    h = util.run_gpu(gpu, args, names, seqs, levels, stages="pcr")
+    af, ap = h.hist_dict(gpu.H_AFTER_FRAG, 400), h.hist_dict(gpu.H_AFTER_PCR, 400)
+    assert ap == {k: v * 2048 for k, v in af.items()}
+
+
+def test_non_acgt_and_edge_transcripts(oracle, gpu):
+    """IUPAC letters (Go map misses / 'N' in RevComp), a transcript shorter than k, zero expression, one molecule."""
+    names, seqs, levels = util.synth_transcriptome(40, seed=3, mean_len=900, hi=4000, total_molecules=20000, non_acgt=0.01)
+    seqs[0] = b"ACG"
+    seqs[1] = b""
+    levels[2] = 0
+    levels[3] = 1
+    _compare(oracle, gpu, ["-n", "30000", "-c", "8"], seqs_override=(names, seqs, levels))
+    _compare(oracle, gpu, ["-n", "3000", "-f", "prim_jump:200"], seqs_override=(names, seqs, levels))
+
+
+def test_long_molecule_path(oracle, gpu):
+    """A 60 kb transcript with the default -d asks for ~150 breakpoints: exercises k_fragment_long."""
+    names, seqs, levels = util.synth_transcriptome(6, seed=8, mean_len=60000, sigma=0.05, lo=50000, hi=70000, total_molecules=600)
+    _compare(oracle, gpu, ["-n", "20000", "-c", "5"], seqs_override=(names, seqs, levels))
+    _compare(oracle, gpu, ["-n", "2000", "-f", "pre_prim:20000", "-d", "1:n:(150,20,50,400)"], seqs_override=(names, seqs, levels))
+
+
+def test_pool_exhaustion_and_complement(oracle, gpu):
+    """C2-like: classes that are drained entirely (missing fragments) and classes where more than half is drawn
+    (complement rule of spec 4.6)."""
+    o, h = _compare(oracle, gpu, ["-n", "60000", "-c", "2", "-d", "1:n:(150,3,140,160)"], seed=("-si", "5"))
+    assert sum(o.hist_dict(oracle.H_MISSING).values()) > 0
+    st = h.stats()
+    assert st.n_sampled + sum(h.hist_dict(gpu.H_MISSING, 400).values()) == 60000
+
+
+def test_sharding_invariance(oracle, gpu):
+    """Two contiguous shards on two handles with the all-gathered totals reproduce the single-handle result
+    (what N GPUs do)."""
+    from rlsim_b200 import shard
+    args = util.parse(["-n", "40000", "-c", "6", "-si", "13"])
+    names, seqs, levels = util.synth_transcriptome(60, seed=4, mean_len=1200, hi=5000, total_molecules=30000)
+    whole = util.run_gpu(gpu, args, names, seqs, levels)
+    ref = whole.sampled()
+    b = shard.contiguous_partition(shard.work_estimate([len(s) for s in seqs], levels), 2)
+    parts = [util.run_gpu(gpu, args, names[b[r]:b[r + 1]], seqs[b[r]:b[r + 1]], levels[b[r]:b[r + 1]], stages="pcr", first=b[r])
+             for r in range(2)]
+    tot = [p.class_totals() for p in parts]
+    glob = tot[0] + tot[1]
+    outs = []
+    for r, p in enumerate(parts):
+        p.sample(glob, np.zeros_like(glob) if r == 0 else tot[0])
+        outs.append(p.sampled())
+    for k in ("tr", "start", "end", "minus", "id"):
+        assert np.array_equal(np.concatenate([outs[0][k], outs[1][k]]), ref[k]), k
