@@ -1,0 +1,325 @@
+#!/usr/bin/env python3
+"""bench.py - fragments/sec through the library-construction hot path (frag + PCR + size-select).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scale S]
+
+Workload (config C3 of BASELINE.json / SURVEY.md 8d): synthetic human-transcriptome-scale set - 200 000 transcripts
+(lognormal lengths, ~4.5e8 nt), ~1e7 molecules (sel gamma-mixture expression), 1e7 requested fragments, 15 PCR cycles,
+-d '0.9:sn:(600,50,4,300,2000) + 0.1:n:(700,1,600,2000)' -f after_prim_double -eg '(1.0,0.5,0.8)' -el '(0.1,0.7,1.0)'.
+One STEP = one pass of the whole path over that library: target lengths -> priming prefix sums -> fragmentation ->
+species dedup -> PCR -> per-length pools -> without-replacement draw -> fragment records.
+
+    value : whole-job fragments/s with the transcripts already resident in HBM when the timed region starts
+    e2e   : the same through the public API (GpuPool / GpuSampler over the C ABI) with HOST buffers: pinned-host ->
+            device copy of the transcripts and device -> pinned-host read of the sampled fragment records inside
+            the timed region, every step
+    N > 1 : weak scaling - every rank owns its own C3-shaped shard (rank r: transcripts [r*200k, (r+1)*200k)),
+            N x 1e7 fragments are requested from the global pool; the only collective is the all-gather of
+            per-length pool totals.
+
+--impl reference times the reference's own release binary (oracle/_ref) on the box's host cores on a bounded
+sample of the same workload.  The oracle / reference binary are used here only as the CPU baseline legs.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C3_FLAGS = ["-d", "0.9:sn:(600,50,4,300,2000) + 0.1:n:(700,1,600,2000)", "-f", "after_prim_double", "-c", "15",
+            "-eg", "(1.0,0.5,0.8)", "-el", "(0.1,0.7,1.0)"]
+C3_TRANSCRIPTS, C3_MOLECULES, C3_FRAGS = 200_000, 10_000_000, 10_000_000
+REF_SAMPLE_TRANSCRIPTS = 4000  # bounded sample for the CPU reference: 1/50 of C3
+SEED = 20261019
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip() == "Active":
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_args(n_frags, seed):
+    from rlsim_b200.args import CmdArgs
+    return CmdArgs.parse(["-n", str(n_frags), "-si", str(seed)] + C3_FLAGS + ["-"])
+
+
+def reference_arm(opts, rank):
+    """The reference's own CPU implementation (release binary) on a bounded sample of the workload."""
+    from oracle import refbin
+    from rlsim_b200 import synth
+    if rank != 0:
+        return
+    n_tr = max(50, int(REF_SAMPLE_TRANSCRIPTS * opts.scale))
+    frac = n_tr / C3_TRANSCRIPTS
+    bases, off, levels = synth.transcriptome(n_tr, seed=SEED, total_molecules=C3_MOLECULES * frac)
+    n_frags = int(C3_FRAGS * frac)
+    cores = os.cpu_count() or 1
+    have_bin = refbin.available()
+    sample = ("first %d of the %d C3 transcripts' distribution (%d molecules), -n %d, same flags; %s -t %d"
+              % (n_tr, C3_TRANSCRIPTS, int(levels.sum()), n_frags, "release binary rlsim 1.4" if have_bin else "oracle port (ref mode)", cores))
+    with tempfile.TemporaryDirectory() as td:
+        fa = os.path.join(td, "sample.fas")
+        synth.write_fasta(fa, bases, off, levels)
+        times, sampled = [], 0
+        for step in range(opts.warmup + opts.steps):
+            t0 = time.perf_counter()
+            if have_bin:
+                r = refbin.run(["-n", str(n_frags), "-si", str(step + 1)] + C3_FLAGS, fa, threads=cores, keep_fasta=False)
+                sampled = sum(r["report"]["Sampled fragments"]["Data"].values())
+            else:
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                import util
+                from oracle import pyoracle
+                a = make_args(n_frags, step + 1)
+                seqs = [bases[int(off[i]):int(off[i + 1])].tobytes() for i in range(n_tr)]
+                s = util.run_oracle(pyoracle, a, None, seqs, [int(x) for x in levels], pyoracle.MODE_REF)
+                sampled = len(s.sampled()["tr"])
+            dt = time.perf_counter() - t0
+            if step >= opts.warmup:
+                times.append(dt)
+    ms = 1000.0 * float(np.mean(times))
+    value = sampled / (ms / 1000.0)
+    line = {"impl": "reference", "metric": "fragments/sec (frag+PCR+size-select)", "value": value, "unit": "fragments/s",
+            "n_gpus": opts.gpus, "steps": opts.steps, "warmup": opts.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64+u64", "data": "synthetic",
+            "config": {"workload": "C3 sample: " + sample},
+            "cpu_baseline": {"value": value, "unit": "fragments/s", "cores": cores,
+                             "kind": "reference" if have_bin else "port", "sample": sample},
+            "e2e": {"value": value, "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the C3 workload per GPU (1.0 = the named config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    opts = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if opts.impl == "reference":
+        reference_arm(opts, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from rlsim_b200 import _native, shard, synth
+    from rlsim_b200.pool import GpuPool, GpuSampler
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- synthetic library of this rank (weak scaling: every rank owns a C3-shaped shard)
+    n_tr = max(50, int(C3_TRANSCRIPTS * opts.scale))
+    n_mol = C3_MOLECULES * opts.scale
+    n_frags_global = int(C3_FRAGS * opts.scale) * world
+    bases_np, off_np, levels_np = synth.transcriptome(n_tr, seed=SEED + rank, total_molecules=n_mol)
+    bases = torch.from_numpy(bases_np).pin_memory()
+    off = torch.from_numpy(off_np.view(np.int64)).pin_memory()
+    levels = torch.from_numpy(levels_np.view(np.int64)).pin_memory()
+    first = rank * n_tr
+    h2d_bytes = bases.numel() + off.numel() * 8 + levels.numel() * 8
+
+    pool = GpuPool(local_rank, rank, world, dev if world > 1 else None)
+    sampler = GpuSampler()
+    h = pool.handle
+    out_cap = int(C3_FRAGS * opts.scale * 1.5) + 1024
+    out = dict(tr=torch.empty(out_cap, dtype=torch.int32).pin_memory(), start=torch.empty(out_cap, dtype=torch.int32).pin_memory(),
+               end=torch.empty(out_cap, dtype=torch.int32).pin_memory(), minus=torch.empty(out_cap, dtype=torch.uint8).pin_memory(),
+               id=torch.empty(out_cap, dtype=torch.int64).pin_memory())
+
+    def select(step):
+        local = h.class_totals()
+        total, base = shard.allgather_totals(local, device=dev if world > 1 else None)
+        h.sample(total, base)
+
+    def step_e2e(step):
+        """public API, host buffers in, host records out"""
+        args = make_args(n_frags_global, step + 1)
+        pool.reset().configure(args)
+        pool.init_transcripts_arrays(bases, off, levels, n_tr, first)
+        local = h.class_totals()
+        total, base = shard.allgather_totals(local, device=dev if world > 1 else None)
+        h.sample(total, base)
+        n = int(h.stats().n_sampled)
+        if n > out_cap:
+            raise SystemExit("output buffer too small")
+        h.sampled(into=out)
+        return n
+
+    def step_resident(step):
+        """transcripts stay in HBM; everything derived from them is recomputed"""
+        args = make_args(n_frags_global, step + 1)
+        pool.configure(args)  # new seeds; invalidates prefix sums / species / pools
+        h.build_library()
+        select(step)
+        return int(h.stats().n_sampled)
+
+    # ---- warm-up (also allocates every device buffer)
+    for s in range(opts.warmup):
+        step_e2e(s)
+    clocks = ClockSampler(local_rank)
+    clocks.start()  # sampled across both timed regions
+    time.sleep(0.3)
+    # ---- e2e
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = 0
+    for s in range(opts.steps):
+        n_e2e += step_e2e(100 + s)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    d2h_bytes = (n_e2e // max(opts.steps, 1)) * 21 + 7 * 8 * (int(h.stats().high) + 2)
+    # ---- device-resident
+    for s in range(min(opts.warmup, 2)):
+        step_resident(50 + s)
+    ms0, nl0 = h.timings()
+    barrier()
+    t0 = time.perf_counter()
+    n_res = 0
+    for s in range(opts.steps):
+        n_res += step_resident(200 + s)
+    barrier()
+    t_res = time.perf_counter() - t0
+    clk = clocks.stop()
+    ms1, nl1 = h.timings()
+    st = h.stats()
+
+    if world > 1:
+        t = torch.tensor([t_res, t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_res, t_e2e = float(t[0]), float(t[1])
+        c = torch.tensor([n_res, n_e2e], dtype=torch.int64, device=dev)
+        dist.all_reduce(c)
+        n_res, n_e2e = int(c[0]), int(c[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    K = max(opts.steps, 1)
+    stage_ms = {k: (ms1[k] - ms0[k]) / K for k in ms1}
+    launches = sum(nl1[k] - nl0[k] for k in nl1) // K
+    nt_total = int(bases.numel()) + n_tr * int(st.polya_max)
+    # algorithmic bytes per step of each own kernel group
+    alg = {
+        "prefix": 16.25 * nt_total,                       # 0.25 B/nt read + 2 x 8 B/nt prefix sums written
+        "fragment": 120.0 * float(st.n_molecules),        # ~120 B/molecule (draws are register-resident; searches + keys)
+        "pcr": 32.0 * float(st.n_species),                # 32 B/species
+        "expand": 150.0 * float(st.n_sampled),            # ~150 B/sampled fragment
+    }
+    peak, peak_src = peaks()
+    kernels = {}
+    for k, b in alg.items():
+        if stage_ms[k] > 0:
+            kernels[k] = {"ms": stage_ms[k], "alg_bytes": b, "gbs": b / (stage_ms[k] * 1e6)}
+    for k in ("dedup", "select", "target", "layout"):
+        kernels[k] = {"ms": stage_ms[k]}
+    own = {k: v for k, v in kernels.items() if "gbs" in v}
+    dom = max(own, key=lambda k: own[k]["ms"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": own[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": own[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "pcr": {"achieved": own["pcr"]["gbs"], "frac": own["pcr"]["gbs"] / peak, "ms": own["pcr"]["ms"],
+                        "species": int(st.n_species), "note": "issue-bound: 15 exact binomial draws per 32 B species"}}
+    ms_per_step = 1000.0 * t_res / K
+    line = {
+        "metric": "fragments/sec (frag+PCR+size-select)", "value": n_res / t_res, "unit": "fragments/s", "n_gpus": world,
+        "steps": opts.steps, "warmup": opts.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64+u64", "data": "synthetic",
+        "config": {"workload": "C3 synthetic human-transcriptome-scale: %d transcripts / %d nt / %d molecules per GPU, %d requested "
+                               "fragments in total, 15 cycles, after_prim_double" % (n_tr, int(bases.numel()), int(st.n_molecules), n_frags_global),
+                   "flags": " ".join(C3_FLAGS), "scale": opts.scale, "sharding": "contiguous transcripts per rank; allgather of per-length totals",
+                   "l2": "inputs (0.45 GB bases + 7 GB prefix sums per GPU) exceed the 126 MB L2; no explicit flush",
+                   "species_per_gpu": int(st.n_species), "fragments_after_fragmentation_per_gpu": int(st.n_fragments),
+                   "pool_total_rank0": int(st.pool_total)},
+        "e2e": {"value": n_e2e / t_e2e, "unit": "fragments/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                "ms_per_step": 1000.0 * t_e2e / K},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": roofline,
+        "kernels_ms_per_step": {k: round(v["ms"], 4) for k, v in kernels.items()},
+        "kernels_gbs": {k: round(v["gbs"], 2) for k, v in own.items()},
+    }
+    if world == 1 and not opts.no_cpu_baseline:
+        # the reference's release binary on this box's host cores, bounded sample (reported baseline, not the target)
+        try:
+            import io
+            from contextlib import redirect_stdout
+            buf = io.StringIO()
+            ref_opts = argparse.Namespace(gpus=1, steps=1, warmup=0, scale=opts.scale)
+            with redirect_stdout(buf):
+                reference_arm(ref_opts, 0)
+            line["cpu_baseline"] = json.loads(buf.getvalue())["cpu_baseline"]
+        except Exception as e:  # the baseline must never break the GPU line
+            line["cpu_baseline"] = {"value": None, "unit": "fragments/s", "cores": os.cpu_count(), "kind": "reference",
+                                    "sample": "failed: %s" % e}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -121,6 +121,8 @@ int rlsim_set_target_hist(rlsim_handle *h, const uint32_t *lengths, const uint64
 int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t *offsets, const uint64_t *expr,
                           uint32_t n);
 int rlsim_set_first_index(rlsim_handle *h, uint32_t first_index);
+/* forget the transcripts and everything derived from them; device buffers are kept for the next library */
+int rlsim_clear_transcripts(rlsim_handle *h);
 /* fragment every molecule (transcript.go:139-150 + fragmentor.go), collapse identical fragments into species
  * (transcript.go:156-215), amplify (thermocycler.go:106-147) and build the per-length pool (pool.go:156-189). */
 int rlsim_build_library(rlsim_handle *h);

@@ -18,7 +18,7 @@ T_NAMES = ["layout", "prefix", "fragment", "dedup", "pcr", "select", "expand", "
 
 EXPORTS = [
     "rlsim_create", "rlsim_destroy", "rlsim_last_error", "rlsim_set_model", "rlsim_set_len_eff", "rlsim_set_raw_target",
-    "rlsim_sample_target", "rlsim_set_target_hist", "rlsim_add_transcripts", "rlsim_set_first_index",
+    "rlsim_sample_target", "rlsim_set_target_hist", "rlsim_add_transcripts", "rlsim_set_first_index", "rlsim_clear_transcripts",
     "rlsim_build_library", "rlsim_fragment", "rlsim_pcr", "rlsim_class_totals", "rlsim_sample", "rlsim_get_stats",
     "rlsim_get_hist", "rlsim_get_species", "rlsim_get_sampled", "rlsim_format_fasta", "rlsim_probe_kmer_lut",
     "rlsim_probe_prefix", "rlsim_probe_gc_prefix", "rlsim_probe_math", "rlsim_probe_philox", "rlsim_probe_amplify",
@@ -64,6 +64,7 @@ def load():
         "rlsim_set_target_hist": (i32, [vp, vp, vp, u32]),
         "rlsim_add_transcripts": (i32, [vp, vp, vp, vp, u32]),
         "rlsim_set_first_index": (i32, [vp, u32]),
+        "rlsim_clear_transcripts": (i32, [vp]),
         "rlsim_build_library": (i32, [vp]),
         "rlsim_fragment": (i32, [vp]),
         "rlsim_pcr": (i32, [vp]),
@@ -153,6 +154,9 @@ class Handle:
     # ---- transcripts
     def set_first_index(self, i):
         self._chk(self.L.rlsim_set_first_index(self.h, int(i)))
+
+    def clear_transcripts(self):
+        self._chk(self.L.rlsim_clear_transcripts(self.h))
 
     def add_transcripts_raw(self, bases, offsets, expr, n):
         """bases/offsets/expr: host numpy arrays or (pinned) torch tensors."""

@@ -407,6 +407,18 @@ int rlsim_set_target_hist(rlsim_handle *h, const uint32_t *lengths, const uint64
 
 int rlsim_set_first_index(rlsim_handle *h, uint32_t first_index) { h->first_index = first_index; return 0; }
 
+int rlsim_clear_transcripts(rlsim_handle *h) {
+    cudaSetDevice(h->device);
+    for (auto &b : h->batches) { cudaFree(b.d_bases); cudaFree(b.d_src_off); }
+    h->batches.clear();
+    h->h_srclen.clear(); h->h_expr.clear(); h->h_off.clear(); h->h_len.clear();
+    h->ingested = false; h->have_prefix = false; h->fragmented = h->amplified = h->sampled = false;
+    h->n_mol = h->total_padded = h->n_frag = h->n_sp = h->n_out = h->pool_total = 0;
+    memset(h->ms, 0, sizeof h->ms);
+    memset(h->launches, 0, sizeof h->launches);
+    return 0;
+}
+
 int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t *offsets, const uint64_t *expr, uint32_t n) {
     if (h->ingested) FAIL(h, RLSIM_E_ARG, "transcripts cannot be added after the library was built");
     if (n == 0) return 0;

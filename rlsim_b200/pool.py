@@ -49,6 +49,21 @@ class GpuPool:
         h.sample_target(args.req_frags)  # same histogram on every rank (stream keyed by the draw index)
         return self
 
+    def reset(self):
+        """Start another library on the same GPU, keeping the device buffers."""
+        self.handle.clear_transcripts()
+        return self
+
+    def init_transcripts_arrays(self, bases, offsets, levels, n, first=0):
+        """pool.go:83-135 for a shard that is already one concatenated buffer (numpy arrays or pinned torch
+        tensors): `bases` u8, `offsets` u64[n+1], `levels` u64[n]; `first` = global index of its first record."""
+        h = self.handle
+        self.first = first
+        h.set_first_index(first)
+        h.add_transcripts_raw(bases, offsets, levels, n)
+        h.build_library()
+        return self
+
     def init_transcripts(self, names, seqs, levels, stats: FragStats = None):
         """pool.go:83-135 for this rank's contiguous shard of the input."""
         h = self.handle

@@ -1,0 +1,190 @@
+"""Host-side logic (no GPU): flags, mixture language, FASTA reader, report schema, C-ABI surface, sharding."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+import util
+from rlsim_b200 import args as A
+from rlsim_b200 import fasta, mixture, report, shard
+
+ROOT = os.path.dirname(util.HERE)
+
+
+def test_default_flags_match_reference():
+    a = util.parse(["-n", "10"])
+    assert (a.nr_cycles, a.strand_bias, a.priming_temp, a.kmer_length, a.fixed_eff) == (11, 0.5, 5.0, 6, 0.0)
+    assert a.frag_method.name == "after_prim_double" and a.frag_method.param == 0
+    assert len(a.raw_gc_effs) == 101 and a.raw_gc_effs[17] == 0.6214855142919264  # args.go:194
+    assert str(a.target_mix[0]) == "sn:(189, 24, -1.09975, 76, 294)"
+    assert str(a.polya_param[0]) == "g:(150, 1, 0, 220)"
+    assert a.len_eff_param.shape == 0.0 and a.gob_dir.startswith("rlsim_gob_")
+    p = a.to_params()
+    assert p.gc_mode == 1 and p.n_target == 1 and p.n_polya == 1 and p.kmer_len == 6
+
+
+def test_go_flag_syntax():
+    a = A.CmdArgs.parse(["--n=5", "-c", "3", "-g", "-v", "-f=pre_prim", "x.fa", "-n", "7"])
+    assert a.req_frags == 5 and a.nr_cycles == 3 and a.verbose and a.gob_dir == ""
+    assert a.frag_method.param == 2000  # args.go:301-304
+    assert a.input_files == ["x.fa", "-n", "7"]  # parsing stops at the first non-flag argument
+    with pytest.raises(A.ArgError):
+        A.CmdArgs.parse(["-nope", "1"])
+    with pytest.raises(A.ExitRequest):
+        A.CmdArgs.parse(["-V"])
+    with pytest.raises(A.ExitRequest):
+        A.CmdArgs.parse(["x.fa"])  # no fragments requested
+
+
+@pytest.mark.parametrize("bad", ["1.0:sn:(189,24,76,294)", "1.0:x:(1,2,3,4)", "1.0:n:(1,2,9,3)", "", "1.0:n:1,2,3,4",
+                                 "1.0:n:(-1,2,3,4)"])
+def test_mixture_errors(bad):
+    with pytest.raises(mixture.ArgError):
+        mixture.parse_mixture(bad)
+
+
+def test_mixture_parse():
+    m = mixture.parse_mixture("0.9:sn:(600,50,4,300,2000) + 0.1:n:(700, 1, 600, 2000)")
+    assert [c.type for c in m] == ["sn", "n"] and m[0].shape == 4 and m[1].weight == 0.1
+    assert mixture.global_min_max(m) == (300, 2000)
+
+
+def test_eff_param_and_method_errors():
+    assert A.parse_eff_param(" (1.0,0.5,0.8) ").min == 0.5
+    for bad in ["1,2,3", "(1,2)", "(-1,0.5,0.8)", "(1,1.5,0.8)"]:
+        with pytest.raises(A.ArgError):
+            A.parse_eff_param(bad)
+    with pytest.raises(A.ArgError):
+        A.parse_frag_method("bogus")
+    assert A.parse_frag_method("prim_jump:300").param == 300
+
+
+def test_raw_params_file():
+    a = util.parse(["-j", util.RAW_PARAMS])
+    assert a.req_frags == 964058 and a.nr_cycles == 12 and len(a.raw_gc_effs) == 101
+    assert abs(sum(a.raw_len_probs.probs) - 1.0) < 1e-12
+    p = a.to_params()
+    assert p.n_target == 0 and p.gc_mode == 1
+    a2 = util.parse(["-j", util.RAW_PARAMS, "-jm", "0.5", "-n", "5"])
+    assert min(a2.processed_raw_gc_effs()) == 0.5 and a2.req_frags == 5
+
+
+def test_fasta_reader_quirks():
+    data = b">a$5 \nacgt\nNN tt\r\n>b$x\nAC\n>c\nAC\n>d$7\nA>C\n"
+    recs = fasta.read_records(data)
+    assert recs[0] == (b"a$5 ", b"ACGTNNTT")
+    # fasta.go:138: any '>' opens a record once the buffer holds more than one byte
+    assert [r[0] for r in recs] == [b"a$5 ", b"b$x", b"c", b"d$7", b"C"]
+    assert fasta.parse_seq_name(b"a$5 ") == (b"a", 5)
+    assert fasta.parse_seq_name(b"b$x") is None and fasta.parse_seq_name(b"c") is None and fasta.parse_seq_name(b"$3") is None
+    names, seqs, levels = fasta.load_transcripts([util.BASIC_FASTA], 1.0)
+    assert [len(s) for s in seqs] == [1075, 3477, 4002, 2729, 1690] and levels == [10200, 8900, 2300, 2160, 0]
+    assert fasta.load_transcripts([util.BASIC_FASTA], 0.1)[2] == [1020, 890, 230, 216, 0]  # input.go:113
+
+
+def test_report_schema():
+    with tempfile.TemporaryDirectory() as td:
+        r = report.Report(os.path.join(td, "r.json"))
+        r.report_map({100: 3, 7: 1}, "Length", "Count", "Target lenghts", "bar")
+        r.report_float([0.0, 0.5], [0.1, 0.2], "GC content (%)", "Efficiency", "GC efficiency function", "line")
+        r.write_json()
+        d = json.load(open(r.path))
+    assert d["Target lenghts"] == {"Xl": "Length", "Yl": "Count", "Vis": "bar", "Pos": 0, "Data": {"100": 3, "7": 1}}
+    assert d["GC efficiency function"]["Pos"] == 1 and d["GC efficiency function"]["Data"] == {"0": 0.1, "0.5": 0.2}
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads without a GPU and exports exactly what include/rlsim_gpu.h declares."""
+    from rlsim_b200 import _native
+    lib = _native.load()
+    hdr = open(os.path.join(ROOT, "include", "rlsim_gpu.h")).read()
+    declared = sorted(set(re.findall(r"\b(rlsim_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(declared) >= 25
+    for name in declared:
+        getattr(lib, name)
+    assert sorted(declared) == sorted(_native.EXPORTS)
+
+
+def test_struct_layout_matches_header():
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "rlsim_gpu.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu",' \
+          "sizeof(rlsim_params),sizeof(rlsim_mixcomp),sizeof(rlsim_stats),offsetof(rlsim_params,gc_raw)," \
+          "offsetof(rlsim_params,target),offsetof(rlsim_params,seed_init));return 0;}"
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "t")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    from rlsim_b200._native import Stats
+    assert sizes == [ctypes.sizeof(A.CParams), ctypes.sizeof(A.CMixComp), ctypes.sizeof(Stats), A.CParams.gc_raw.offset,
+                     A.CParams.target.offset, A.CParams.seed_init.offset]
+    from oracle import pyoracle
+    assert ctypes.sizeof(pyoracle.Params) == ctypes.sizeof(A.CParams)
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without a CUDA device the product fails loudly instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from rlsim_b200 import _native
+    with pytest.raises(_native.RlsimError):
+        _native.Handle(0)
+
+
+def test_product_never_touches_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "rlsim_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "pyoracle" not in txt and "liboracle" not in txt and "oracle/" not in txt.replace("the oracle", ""), f
+
+
+def test_contiguous_partition():
+    rng = np.random.default_rng(0)
+    w = rng.gamma(0.5, 10.0, 1000)
+    for n in (1, 2, 3, 8):
+        b = shard.contiguous_partition(w, n)
+        assert b[0] == 0 and b[-1] == 1000 and all(x <= y for x, y in zip(b, b[1:])) and len(b) == n + 1
+        loads = [w[b[i]:b[i + 1]].sum() for i in range(n)]
+        assert max(loads) <= w.sum() / n + w.max() + 1e-9
+    assert shard.contiguous_partition([0, 0, 0], 2) == [0, 0, 3]
+
+
+_GLOO = r"""
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch.distributed as dist
+from rlsim_b200 import shard
+dist.init_process_group("gloo")
+r = dist.get_rank()
+local = np.array([10 * (r + 1), 0, 7, 2**40 + r], dtype=np.uint64)
+tot, base = shard.allgather_totals(local)
+assert list(tot) == [30, 0, 14, 2**41 + 1], tot
+assert list(base) == ([0, 0, 0, 0] if r == 0 else [10, 0, 7, 2**40]), base
+h = shard.allreduce_hist(np.array([r + 1, 5], dtype=np.uint64))
+assert list(h) == [3, 10]
+big = np.array([2**63 + 5], dtype=np.uint64)
+try:
+    shard.allgather_totals(big)
+    raise SystemExit("overflow not detected")
+except OverflowError:
+    pass
+dist.destroy_process_group()
+"""
+
+
+def test_allgather_world_size_2_gloo():
+    """The N>1 host path: per-length totals all-gathered, rank bases derived, overflow detected (fragstats.go:88-94)."""
+    with tempfile.TemporaryDirectory() as td:
+        script = os.path.join(td, "w.py")
+        open(script, "w").write(_GLOO % ROOT)
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+        subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                               "--master-addr", "127.0.0.1", "--master-port", "29731", script], env=env, timeout=300)
