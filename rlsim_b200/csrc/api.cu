@@ -44,6 +44,9 @@ uint32_t bits_for(uint64_t v) {
     return b;
 }
 
+// kernels launched by one cub::DeviceRadixSort call over `bits` key bits (histogram + exclusive sum + onesweep passes)
+uint64_t radix_launches(int bits) { return 2 + (uint64_t)((bits + 7) / 8); }
+
 __global__ void k_iota(uint32_t *p, uint64_t n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = (uint32_t)i;
@@ -93,7 +96,8 @@ struct rlsim_handle {
     DBuf<uint64_t> d_keys, d_keys_sorted, d_uniq;
     DBuf<unsigned long long> d_counters;  // [0] fragment count, [1] run count
     DBuf<unsigned long long> d_hist_frag, d_hist_polya, d_hist_target;
-    DBuf<uint2> d_long_list;
+    DBuf<uint2> d_long_list, d_q_b;
+    DBuf<uint4> d_q_a;
     DBuf<uint32_t> d_long_hi;
     DBuf<unsigned int> d_long_count;
     DBuf<int> d_error;
@@ -452,8 +456,8 @@ int rlsim_fragment(rlsim_handle *h) {
     if (needs_fwd(method) && !h->have_prefix) {
         uint32_t nk = 1u << (2 * h->p.kmer_len);
         CK(h, h->d_K.ensure(nk)); CK(h, h->d_wq_f.ensure(nk)); CK(h, h->d_wq_r.ensure(nk));
-        CK(h, h->d_Pf.ensure(h->total_padded + n + 8));
-        if (needs_rev(method)) CK(h, h->d_Pr.ensure(h->total_padded + n + 8));
+        CK(h, h->d_Pf.ensure(h->total_padded + 2ull * n + 8));
+        if (needs_rev(method)) CK(h, h->d_Pr.ensure(h->total_padded + 2ull * n + 8));
         h->have_prefix = true;
         DevTranscripts tr = make_tr(h);
         StageTimer tm(h, RLSIM_T_PREFIX, 3);
@@ -485,28 +489,32 @@ int rlsim_fragment(rlsim_handle *h) {
     uint32_t long_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(h->n_mol / 64, 4096), 1u << 24);
     DevModel m = make_model(h);
     DevTranscripts tr = make_tr(h);
+    bool queued = (method <= RLSIM_AFTER_NOPRIM_DOUBLE);  // after_* methods go through the interval queue
+    uint64_t q_cap = queued ? cap : 1;
     for (int attempt = 0;; attempt++) {
         if (attempt > 8) FAIL(h, RLSIM_E_NOMEM, "fragment buffer kept overflowing");
         CK(h, h->d_keys.ensure(cap));
+        CK(h, h->d_q_a.ensure(q_cap)); CK(h, h->d_q_b.ensure(q_cap));
         CK(h, h->d_long_list.ensure(long_cap)); CK(h, h->d_long_hi.ensure(long_cap));
         CK(h, cudaMemsetAsync(h->d_counters.p, 0, 4 * 8, h->st));
         CK(h, cudaMemsetAsync(h->d_long_count.p, 0, 4, h->st));
         CK(h, cudaMemsetAsync(h->d_hist_frag.p, 0, (size_t)hist_frag_n * 8, h->st));
         CK(h, cudaMemsetAsync(h->d_hist_polya.p, 0, (size_t)hist_pa_n * 8, h->st));
         CK(h, cudaMemsetAsync(h->d_error.p, 0, 4, h->st));
+        FragBuffers fb{h->d_keys.p, cap, h->d_counters.p, h->d_hist_frag.p, h->d_hist_polya.p, h->d_long_list.p, h->d_long_hi.p,
+                       long_cap, h->d_long_count.p, h->d_error.p, h->d_q_a.p, h->d_q_b.p, q_cap, h->d_counters.p + 2};
         StageTimer tm(h, RLSIM_T_FRAGMENT, 1);
-        rc = launch_fragment(h->st, m, tr, h->n_mol, h->d_keys.p, cap, h->d_counters.p, h->d_hist_frag.p, h->d_hist_polya.p,
-                             h->d_long_list.p, h->d_long_hi.p, long_cap, h->d_long_count.p, h->d_error.p);
+        rc = launch_fragment(h->st, m, tr, h->n_mol, fb);
         if (rc) FAIL(h, rc, "fragmentation launch configuration unsupported (poly(A) maximum too large)");
         unsigned int n_long = 0;
+        unsigned long long n_q = 0;
         CK(h, cudaMemcpyAsync(&n_long, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaMemcpyAsync(&n_q, h->d_counters.p + 2, 8, cudaMemcpyDeviceToHost, h->st));
         CK(h, cudaStreamSynchronize(h->st));
         if (n_long > long_cap) { tm.stop(); long_cap = n_long + 1024; continue; }
-        if (n_long) {
-            h->launches[RLSIM_T_FRAGMENT]++;
-            launch_fragment_long(h->st, m, tr, h->d_keys.p, cap, h->d_counters.p, h->d_hist_frag.p, h->d_hist_polya.p,
-                                 h->d_long_list.p, h->d_long_hi.p, n_long, h->d_error.p);
-        }
+        if (n_q > q_cap) { tm.stop(); q_cap = n_q + n_q / 8 + 65536; continue; }
+        if (n_q) { h->launches[RLSIM_T_FRAGMENT]++; launch_intervals(h->st, m, tr, fb, n_q); }
+        if (n_long) { h->launches[RLSIM_T_FRAGMENT]++; launch_fragment_long(h->st, m, tr, fb, n_long); }
         tm.stop();
         CK(h, cudaGetLastError());
         unsigned long long cnt = 0;
@@ -525,7 +533,7 @@ int rlsim_fragment(rlsim_handle *h) {
     uint64_t nf = h->n_frag;
     CK(h, h->d_keys_sorted.ensure(nf)); CK(h, h->d_uniq.ensure(nf)); CK(h, h->d_sp_count0.ensure(nf));
     {
-        StageTimer tm(h, RLSIM_T_DEDUP, 3);
+        StageTimer tm(h, RLSIM_T_DEDUP, 3 + radix_launches((int)std::min<uint32_t>(64, 24 + bits_for(h->total_padded))));
         h->n_sp = 0;
         if (nf) {
             if (nf >= (1ull << 31)) FAIL(h, RLSIM_E_UNSUPPORTED, "more than 2^31 fragments on one GPU");
@@ -572,7 +580,7 @@ int rlsim_pcr(rlsim_handle *h) {
     CK(h, cudaMemsetAsync(h->d_error.p, 0, 4, h->st));
     DevTranscripts tr = make_tr(h);
     {
-        StageTimer tm(h, RLSIM_T_PCR, 1);
+        StageTimer tm(h, RLSIM_T_PCR, h->h_len_eff.empty() ? 2 : 1);
         launch_pcr(h->st, m, tr, make_sp(h), h->d_error.p);
         tm.stop();
         CK(h, cudaGetLastError());
@@ -585,7 +593,7 @@ int rlsim_pcr(rlsim_handle *h) {
     CK(h, h->d_cls_cnt.ensure(ns)); CK(h, h->d_cls_pre.ensure(ns + 1)); CK(h, h->d_bounds.ensure(h->n_len + 2));
     CK(h, h->d_totals.ensure(h->n_len + 1));
     {
-        StageTimer tm(h, RLSIM_T_SELECT, 6);
+        StageTimer tm(h, RLSIM_T_SELECT, 6 + radix_launches((int)bits_for(h->high)));
         CK(h, cudaMemsetAsync(h->d_cls_pre.p, 0, 8, h->st));
         if (ns) {
             k_iota<<<(unsigned)((ns + 255) / 256), 256, 0, h->st>>>(h->d_iota.p, ns);
@@ -699,7 +707,7 @@ int rlsim_sample(rlsim_handle *h, const uint64_t *global_totals, const uint64_t 
         CK(h, h->d_cand_keys.ensure(n_cand)); CK(h, h->d_cand_keys_sorted.ensure(n_cand));
         CK(h, h->d_cand_idx.ensure(n_cand)); CK(h, h->d_cand_idx_sorted.ensure(n_cand));
         CK(h, h->d_flags.ensure(n_cand)); CK(h, h->d_fscan.ensure(n_cand + 1));
-        StageTimer tm(h, RLSIM_T_SELECT, 5);
+        StageTimer tm(h, RLSIM_T_SELECT, 5 + radix_launches((int)bits_for(G)));
         launch_candidates(h->st, m, plan_d, n_cand, h->d_cand_keys.p, h->d_cand_idx.p);
         size_t tb = 0;
         int eb = (int)bits_for(G);
@@ -726,7 +734,7 @@ int rlsim_sample(rlsim_handle *h, const uint64_t *global_totals, const uint64_t 
     }
     // ---- copies drawn per species -> output records
     {
-        StageTimer tm(h, RLSIM_T_EXPAND, 3);
+        StageTimer tm(h, RLSIM_T_EXPAND, 4);
         launch_taken(h->st, make_sp(h), h->d_mode.p, n_len, h->d_hits.p, h->d_taken.p);
         CK(h, cudaMemsetAsync(h->d_out_off.p, 0, 8, h->st));
         h->n_out = 0;
@@ -872,7 +880,7 @@ int rlsim_probe_prefix(rlsim_handle *h, uint32_t tr, int reverse, uint64_t *out,
     cudaSetDevice(h->device);
     uint32_t have = h->h_len[tr] > (uint32_t)h->p.kmer_len ? h->h_len[tr] - h->p.kmer_len + 1 : 1;
     uint32_t m = std::min(n, have);
-    CK(h, cudaMemcpyAsync(out, (reverse ? h->d_Pr.p : h->d_Pf.p) + h->h_off[tr] + tr, (size_t)m * 8, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaMemcpyAsync(out, (reverse ? h->d_Pr.p : h->d_Pf.p) + prefix_base(h->h_off[tr], tr), (size_t)m * 8, cudaMemcpyDeviceToHost, h->st));
     CK(h, cudaStreamSynchronize(h->st));
     return 0;
 }

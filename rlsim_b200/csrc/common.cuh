@@ -47,9 +47,13 @@ struct DevTranscripts {
     const uint32_t *len;      // [n] length including the maximal poly-A tail
     const uint64_t *expr;     // [n]
     const uint64_t *mol_off;  // [n+1] exclusive scan of expr
-    const uint64_t *Pf, *Pr;  // priming prefix sums, (len+1) entries per transcript at off[t] + t
+    const uint64_t *Pf, *Pr;  // priming prefix sums, (len-k+1) entries per transcript at prefix_base(off[t], t)
     const uint32_t *gc;       // GC prefix counts, (len+1) entries per transcript at off[t] + t
 };
+
+// First entry of transcript t's prefix-sum array: odd index, so that P[1] (the first computed sum) is 16-byte
+// aligned for vector stores.  Region of transcript t: [off[t]+2t+1, off[t+1]+2t+2].
+__host__ __device__ __forceinline__ uint64_t prefix_base(uint64_t off, uint32_t t) { return off + 2ull * t + 1ull; }
 
 __device__ __forceinline__ uint32_t upper_bound_u64(const uint64_t *a, uint32_t n, uint64_t x) {
     uint32_t lo = 0, hi = n;  // first i with a[i] > x

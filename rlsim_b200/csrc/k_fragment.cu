@@ -31,6 +31,11 @@ struct FragOut {
     uint32_t long_cap;
     unsigned int *long_count;
     int *error;                 // RLSIM_E_* raised on the device
+    // interval work queue (after_* methods): filled by k_fragment, drained by k_intervals
+    uint4 *q_a;                 // (t, m_lo, interval index, start)
+    uint2 *q_b;                 // (end, m_hi)
+    uint64_t q_cap;
+    unsigned long long *q_count;
 };
 
 __device__ __forceinline__ PxStream mol_stream(const DevModel &m, uint32_t tg, uint64_t mol, uint32_t sub) {
@@ -75,6 +80,21 @@ __device__ __forceinline__ void emit(const FragOut &o, uint64_t gstart, uint32_t
     uint32_t bin = size - low;
     if (bin < hist_s_n) atomicAdd(&hist_s[bin], 1u);
     else atomicAdd(&o.hist_frag[size], 1ull);
+}
+
+// Queue one interval that passed the `end - start >= low` pre-filter (fragmentor.go:136-138) for k_intervals.
+__device__ __forceinline__ void enqueue(const FragOut &o, uint32_t t, uint64_t mol, uint32_t i, uint32_t start, uint32_t end) {
+    unsigned mask = __activemask();
+    int leader = __ffs(mask) - 1;
+    int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(o.q_count, (unsigned long long)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    unsigned long long pos = base + __popc(mask & ((1u << lane) - 1u));
+    if (pos < o.q_cap) {
+        o.q_a[pos] = make_uint4(t, (uint32_t)(mol & 0xffffffffu), i, start);
+        o.q_b[pos] = make_uint2(end, (uint32_t)(mol >> 32));
+    }
 }
 
 struct MolCtx {
@@ -195,8 +215,8 @@ __device__ __forceinline__ MolCtx make_ctx(const DevModel &m, const DevTranscrip
     c.L = tr.len[t];
     c.proflen = c.L > (uint32_t)m.k ? c.L - (uint32_t)m.k : 0;
     c.off = tr.off[t];
-    c.Pf = tr.Pf ? tr.Pf + c.off + t : nullptr;
-    c.Pr = tr.Pr ? tr.Pr + c.off + t : nullptr;
+    c.Pf = tr.Pf ? tr.Pf + prefix_base(c.off, t) : nullptr;
+    c.Pr = tr.Pr ? tr.Pr + prefix_base(c.off, t) : nullptr;
     return c;
 }
 
@@ -237,7 +257,7 @@ k_fragment(const __grid_constant__ DevModel m, DevTranscripts tr, uint64_t n_mol
             PxStream iv = mol_stream(m, c.tg, mol, SUB_INTERVAL);
             for (int32_t i = 0; i < h.nb; i++) {  // the last interval is never visited (fragmentor.go:132)
                 if (m.method == RLSIM_PRE_PRIM) plain_interval(m, c, iv, (uint32_t)i, br[i], br[i + 1], o, hist_s, hist_s_n);
-                else after_interval(m, c, iv, (uint32_t)i, br[i], br[i + 1], o, hist_s, hist_s_n);
+                else if (br[i + 1] - br[i] >= m.low) enqueue(o, t, mol, (uint32_t)i, br[i], br[i + 1]);
             }
         }
     }
@@ -246,6 +266,28 @@ k_fragment(const __grid_constant__ DevModel m, DevTranscripts tr, uint64_t n_mol
         if (hist_s[i]) atomicAdd(&o.hist_frag[m.low + i], (unsigned long long)hist_s[i]);
     for (uint32_t i = threadIdx.x; i <= m.polya_max; i += FRAG_THREADS)
         if (hist_pa[i]) atomicAdd(&o.hist_polya[i], (unsigned long long)hist_pa[i]);
+}
+
+// One thread per queued interval: the two dependent priming searches (nnthermo.go:203-217) + filters + emit.
+// Kept separate from k_fragment so that this latency-bound part runs lean (few registers, full occupancy).
+constexpr int IV_THREADS = 256;
+__global__ void __launch_bounds__(IV_THREADS)
+k_intervals(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, uint64_t n_q, uint32_t hist_s_n) {
+    extern __shared__ unsigned int hist_s[];
+    for (uint32_t i = threadIdx.x; i < hist_s_n; i += IV_THREADS) hist_s[i] = 0;
+    __syncthreads();
+    uint64_t g = (uint64_t)blockIdx.x * IV_THREADS + threadIdx.x;
+    if (g < n_q) {
+        uint4 a = o.q_a[g];
+        uint2 b = o.q_b[g];
+        uint64_t mol = (uint64_t)a.y | ((uint64_t)b.y << 32);
+        MolCtx c = make_ctx(m, tr, a.x);
+        PxStream iv = mol_stream(m, c.tg, mol, SUB_INTERVAL);
+        after_interval(m, c, iv, a.z, a.w, b.x, o, hist_s, hist_s_n);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < hist_s_n; i += IV_THREADS)
+        if (hist_s[i]) atomicAdd(&o.hist_frag[m.low + i], (unsigned long long)hist_s[i]);
 }
 
 // One CTA per deferred molecule: breakpoints drawn in parallel, bitonic-sorted in shared memory, intervals in parallel.
@@ -299,17 +341,16 @@ k_fragment_long(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o
     }
 }
 
-struct FragLaunch {
-    FragOut out;
-};
+static uint32_t frag_hist_bins(const DevModel &m) {
+    uint32_t n = m.high - m.low + 1;
+    return n > 8192 ? 0 : n;
+}
 
-int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint64_t n_mol, uint64_t *keys,
-                    uint64_t cap, unsigned long long *count, unsigned long long *hist_frag, unsigned long long *hist_polya,
-                    uint2 *long_list, uint32_t *long_hi, uint32_t long_cap, unsigned int *long_count, int *error) {
+int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint64_t n_mol, const FragBuffers &fb) {
     if (n_mol == 0) return 0;
-    FragOut o{keys, cap, count, hist_frag, hist_polya, long_list, long_hi, long_cap, long_count, error};
-    uint32_t hist_s_n = m.high - m.low + 1;
-    if (hist_s_n > 8192) hist_s_n = 0;
+    FragOut o{fb.keys, fb.cap, fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, fb.long_cap, fb.long_count,
+              fb.error, fb.q_a, fb.q_b, fb.q_cap, fb.q_count};
+    uint32_t hist_s_n = frag_hist_bins(m);
     size_t smem = ((size_t)hist_s_n + m.polya_max + 1) * 4;
     if (smem > 48 * 1024) { hist_s_n = 0; smem = ((size_t)m.polya_max + 1) * 4; }
     if (smem > 48 * 1024) return RLSIM_E_UNSUPPORTED;
@@ -319,11 +360,21 @@ int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr
     return 0;
 }
 
-int launch_fragment_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint64_t *keys, uint64_t cap,
-                         unsigned long long *count, unsigned long long *hist_frag, unsigned long long *hist_polya,
-                         uint2 *long_list, uint32_t *long_hi, uint32_t n_long, int *error) {
+int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint64_t n_q) {
+    if (n_q == 0) return 0;
+    FragOut o{fb.keys, fb.cap, fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, fb.long_cap, fb.long_count,
+              fb.error, fb.q_a, fb.q_b, fb.q_cap, fb.q_count};
+    uint32_t hist_s_n = frag_hist_bins(m);
+    uint64_t blocks = (n_q + IV_THREADS - 1) / IV_THREADS;
+    if (blocks > 0x7fffffffull) return RLSIM_E_UNSUPPORTED;
+    k_intervals<<<(unsigned)blocks, IV_THREADS, (size_t)hist_s_n * 4, st>>>(m, tr, o, n_q, hist_s_n);
+    return 0;
+}
+
+int launch_fragment_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t n_long) {
     if (n_long == 0) return 0;
-    FragOut o{keys, cap, count, hist_frag, hist_polya, long_list, long_hi, n_long, nullptr, error};
+    FragOut o{fb.keys, fb.cap, fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, n_long, nullptr,
+              fb.error, fb.q_a, fb.q_b, fb.q_cap, fb.q_count};
     const uint32_t smem_cap = 32768;  // breakpoints per molecule (128 KB of shared memory)
     cudaFuncSetAttribute(k_fragment_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_cap * 4));
     k_fragment_long<<<n_long, LONG_THREADS, smem_cap * 4, st>>>(m, tr, o, n_long, smem_cap);

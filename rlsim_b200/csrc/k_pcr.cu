@@ -46,12 +46,103 @@ __device__ __forceinline__ double gc_eff(const DevModel &m, uint32_t gc_count, u
     return m.gc_min + (m.gc_max - m.gc_min) * det_go_pow(1 - det_go_pow(gc, m.gc_shape), m.gc_shape);
 }
 
-// AmplifyFragment, thermocycler.go:133-147
-__device__ __forceinline__ uint64_t amplify(PxCursor &cur, uint64_t c, double e, int cycles, bool &overflow) {
-    for (int cyc = 0; cyc < cycles; cyc++) {
-        uint64_t old = c;
-        c += px_binomial(cur, c, e);
-        if (c < old) { overflow = true; break; }
+// AmplifyFragment, thermocycler.go:133-147: `cycles` times c <- c + Binomial(c, pp), from the species' own cursor.
+//
+// Same draws, in the same per-species order, as px_binomial() called once per cycle (variates.cuh; the oracle restates
+// that form) - but scheduled for a warp: the BTRS acceptance test that needs four logarithms ("slow path", ~14% of the
+// attempts) is not evaluated inside the cycle loop, where it would run for a handful of lanes in almost every
+// iteration.  A lane that needs it PARKS; lanes keep running fast-path work (inversion, squeeze accepts) until each
+// one is parked or done, then the slow test runs once for all parked lanes together.  Per-species constants
+// (p, q, p/q, log q) are hoisted out of the cycle loop.
+__device__ __forceinline__ uint64_t amplify(PxCursor &cur, uint64_t c, double pp, int cycles, bool &overflow) {
+    if (!(pp > 0.0) || c == 0) return c;  // Binomial(c, 0) = 0, Binomial(0, .) = 0
+    if (pp >= 1.0) {                      // Binomial(c, 1) = c
+        for (int cyc = 0; cyc < cycles; cyc++) {
+            uint64_t nc = c + c;
+            if (nc < c) { overflow = true; break; }
+            c = nc;
+        }
+        return c;
+    }
+    const bool flip = !(pp <= 0.5);
+    const double p = flip ? 1.0 - pp : pp;
+    const double q = 1.0 - p;
+    const double r = p / q;
+    const double lq = det_log(q);
+    int cyc = 0;
+    bool have_setup = false;
+    double nd = 0, b = 0, a = 0, cc = 0, vr = 0, alpha = 0, mm = 0;  // BTRS constants of the current cycle
+    double us = 0, v = 0, k = 0;                                    // the parked attempt
+    while (cyc < cycles) {
+        bool parked = false;
+        // ---- fast phase: run until this lane needs the slow test or has finished all cycles
+        while (cyc < cycles) {
+            uint64_t res;
+            if (!have_setup) {
+                nd = (double)c;
+                if (nd * p < 10.0) {  // BINV inversion
+                    double qn = det_exp(nd * lq);
+                    double bound = nd * p + 10.0 * sqrt(nd * p * q + 1.0);
+                    if (bound > nd) bound = nd;
+                    for (;;) {
+                        double x = 0.0, px = qn, u = cur.u01();
+                        bool restart = false;
+                        while (u > px) {
+                            x = x + 1.0;
+                            if (x > bound) { restart = true; break; }
+                            u = u - px;
+                            px = ((nd - x + 1.0) * r) * px / x;
+                        }
+                        if (!restart) { res = (uint64_t)x; break; }
+                    }
+                    uint64_t nc = c + (flip ? c - res : res);
+                    if (nc < c) { overflow = true; return c; }
+                    c = nc;
+                    cyc++;
+                    continue;
+                }
+                double spq = sqrt(nd * p * q);
+                b = 1.15 + 2.53 * spq;
+                a = -0.0873 + 0.0248 * b + 0.01 * p;
+                cc = nd * p + 0.5;
+                vr = 0.92 - 4.2 / b;
+                alpha = (2.83 + 5.1 / b) * spq;
+                mm = floor((nd + 1.0) * p);
+                have_setup = true;
+            }
+            double u = cur.u01() - 0.5;
+            v = cur.u01_open();
+            us = 0.5 - fabs(u);
+            k = floor((2.0 * a / us + b) * u + cc);
+            if (us >= 0.07 && v <= vr) {  // squeeze accept
+                res = (uint64_t)k;
+                uint64_t nc = c + (flip ? c - res : res);
+                if (nc < c) { overflow = true; return c; }
+                c = nc;
+                cyc++;
+                have_setup = false;
+                continue;
+            }
+            if (k < 0.0 || k > nd) continue;
+            parked = true;
+            break;
+        }
+        // ---- slow phase (lanes reconverge here): exact acceptance test of the parked attempt
+        if (parked) {
+            double lv = det_log(v * alpha / (a / (us * us) + b));
+            double ub = (mm + 0.5) * det_log((mm + 1.0) / (r * (nd - mm + 1.0))) +
+                        (nd + 1.0) * det_log((nd - mm + 1.0) / (nd - k + 1.0)) +
+                        (k + 0.5) * det_log(r * (nd - k + 1.0) / (k + 1.0)) + det_logfact_tail(mm) +
+                        det_logfact_tail(nd - mm) - det_logfact_tail(k) - det_logfact_tail(nd - k);
+            if (lv <= ub) {
+                uint64_t res = (uint64_t)k;
+                uint64_t nc = c + (flip ? c - res : res);
+                if (nc < c) { overflow = true; return c; }
+                c = nc;
+                cyc++;
+                have_setup = false;
+            }
+        }
     }
     return c;
 }

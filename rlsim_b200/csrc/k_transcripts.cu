@@ -166,29 +166,33 @@ void launch_kmer_lut(cudaStream_t st, int k, double T, double *K, unsigned long 
 constexpr int PFX_THREADS = 256;
 constexpr int PFX_ITEMS = 8;
 constexpr int PFX_TILE = PFX_THREADS * PFX_ITEMS;
-constexpr int PFX_STAGE_WORDS = PFX_TILE / 16 + 4;
-constexpr int PFX_STAGE_MASK = PFX_TILE / 32 + 4;
+constexpr int PFX_STAGE_WORDS = PFX_TILE / 16 + 6;
+constexpr int PFX_STAGE_MASK = PFX_TILE / 32 + 6;
 
 // grid = (transcripts, strands).  Forward profile entry i is the k-mer at plus[i, i+k); reverse entry i is the
 // reverse complement of plus[j, j+k), j = L-k-i (= minus[i, i+k), transcript.go:110 + nnthermo.go:184-199).
-// Both have L-k entries (nnthermo.go:193).  Output P[0..L-k]: exclusive prefix sums of the fixed-point weights.
+// Both have L-k entries (nnthermo.go:193).  Output P[0..L-k]: exclusive prefix sums of the fixed-point weights,
+// stored at prefix_base(off[t], t) so that P[1] is 16-byte aligned.
+//
+// Each thread owns 8 consecutive profile entries: it pulls the <= 3 packed words and 2 mask words covering its
+// 8 windows from the staged tile once, extracts the 8 k-mer codes by shifts, gathers the weights from the
+// shared-memory LUT, and writes its 8 running sums with four 16-byte stores.
 __global__ void __launch_bounds__(PFX_THREADS)
 k_prefix(DevTranscripts tr, int k, double T, const uint32_t *__restrict__ wq_f, const uint32_t *__restrict__ wq_r,
          const unsigned long long *__restrict__ kmax_bits, uint64_t *__restrict__ Pf, uint64_t *__restrict__ Pr,
          int lut_in_smem) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *stage_out = reinterpret_cast<uint64_t *>(smem_raw);                    // PFX_TILE u64
-    uint32_t *stage_pk = reinterpret_cast<uint32_t *>(stage_out + PFX_TILE);         // PFX_STAGE_WORDS
-    uint32_t *stage_mk = stage_pk + PFX_STAGE_WORDS;                                 // PFX_STAGE_MASK
-    uint64_t *warp_tot = reinterpret_cast<uint64_t *>(stage_mk + PFX_STAGE_MASK + ((PFX_STAGE_WORDS + PFX_STAGE_MASK) & 1));
-    uint32_t *lut_s = reinterpret_cast<uint32_t *>(warp_tot + PFX_THREADS / 32 + 1);
+    uint64_t *warp_tot = reinterpret_cast<uint64_t *>(smem_raw);              // PFX_THREADS/32
+    uint32_t *stage_pk = reinterpret_cast<uint32_t *>(warp_tot + PFX_THREADS / 32);  // PFX_STAGE_WORDS
+    uint32_t *stage_mk = stage_pk + PFX_STAGE_WORDS;                          // PFX_STAGE_MASK
+    uint32_t *lut_s = stage_mk + PFX_STAGE_MASK;
 
     const uint32_t t = blockIdx.x;
     const int reverse = blockIdx.y;
     if (tr.expr[t] == 0) return;  // pool.go:104: never fragmented
     const uint32_t L = tr.len[t];
     const uint64_t o = tr.off[t];
-    uint64_t *P = (reverse ? Pr : Pf) + o + t;
+    uint64_t *P = (reverse ? Pr : Pf) + prefix_base(o, t);
     const uint32_t *lut = reverse ? wq_r : wq_f;
     if (lut_in_smem) {
         uint32_t n = 1u << (2 * k);
@@ -199,83 +203,102 @@ k_prefix(DevTranscripts tr, int k, double T, const uint32_t *__restrict__ wq_f, 
     if (L <= (uint32_t)k) return;
     const uint32_t proflen = L - (uint32_t)k;
     const double scale = 4294967296.0 / __longlong_as_double((long long)*kmax_bits);
-    const uint32_t kmask = (k == 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
+    const uint32_t kmask = (1u << (2 * k)) - 1u;
     const uint32_t mmask = (1u << k) - 1u;
     const uint64_t pk_base = o >> 4, mk_base = o >> 5;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t carry = 0;
 
     for (uint32_t i0 = 0; i0 < proflen; i0 += PFX_TILE) {
-        uint32_t ntile = min((uint32_t)PFX_TILE, proflen - i0);
-        // plus-strand window range covered by this tile
-        uint32_t jlo, jhi;  // inclusive window starts
+        const uint32_t ntile = min((uint32_t)PFX_TILE, proflen - i0);
+        uint32_t jlo, jhi;  // plus-strand window starts covered by this tile (inclusive)
         if (!reverse) { jlo = i0; jhi = i0 + ntile - 1; }
         else { jhi = L - k - i0; jlo = L - k - (i0 + ntile - 1); }
-        uint32_t w_lo = jlo >> 4, w_hi = (jhi + k - 1) >> 4;
-        uint32_t m_lo = jlo >> 5, m_hi = (jhi + k - 1) >> 5;
-        __syncthreads();
-        for (uint32_t w = threadIdx.x; w <= w_hi - w_lo + 1; w += PFX_THREADS) stage_pk[w] = tr.packed[pk_base + w_lo + w];
-        for (uint32_t w = threadIdx.x; w <= m_hi - m_lo + 1; w += PFX_THREADS) stage_mk[w] = tr.nmask[mk_base + m_lo + w];
+        const uint32_t w_lo = jlo >> 4, w_n = ((jhi + k - 1) >> 4) - w_lo + 3;
+        const uint32_t m_lo = jlo >> 5, m_n = ((jhi + k - 1) >> 5) - m_lo + 2;
+        __syncthreads();  // previous tile's readers of stage_* / warp_tot are done
+        for (uint32_t w = threadIdx.x; w < w_n; w += PFX_THREADS) stage_pk[w] = tr.packed[pk_base + w_lo + w];
+        for (uint32_t w = threadIdx.x; w < m_n; w += PFX_THREADS) stage_mk[w] = tr.nmask[mk_base + m_lo + w];
         __syncthreads();
 
+        const uint32_t ib = i0 + threadIdx.x * PFX_ITEMS;  // first profile entry of this thread
         uint64_t x[PFX_ITEMS];
         uint64_t run = 0;
+        if (ib < proflen) {
+            // lowest plus-strand window start among this thread's entries
+            const uint32_t nvalid = min((uint32_t)PFX_ITEMS, proflen - ib);
+            const uint32_t jb = reverse ? (L - k - (ib + nvalid - 1)) : ib;
+            const uint32_t wi = (jb >> 4) - w_lo, mi = (jb >> 5) - m_lo;
+            const uint32_t p0 = stage_pk[wi], p1 = stage_pk[wi + 1], p2 = stage_pk[wi + 2];
+            const uint64_t lo64 = (uint64_t)p0 | ((uint64_t)p1 << 32), hi64 = (uint64_t)p1 | ((uint64_t)p2 << 32);
+            const uint64_t m64 = (uint64_t)stage_mk[mi] | ((uint64_t)stage_mk[mi + 1] << 32);
+            const uint32_t ob = jb & 15, omb = jb & 31;
 #pragma unroll
-        for (int r = 0; r < PFX_ITEMS; r++) {
-            uint32_t i = i0 + threadIdx.x * PFX_ITEMS + r;
-            uint64_t w = 0;
-            if (i < proflen) {
-                uint32_t j = reverse ? (L - k - i) : i;
-                uint32_t wi = (j >> 4) - w_lo;
-                uint64_t two = (uint64_t)stage_pk[wi] | ((uint64_t)stage_pk[wi + 1] << 32);
-                uint32_t code = (uint32_t)(two >> (2 * (j & 15))) & kmask;
-                uint32_t mi = (j >> 5) - m_lo;
-                uint64_t mtwo = (uint64_t)stage_mk[mi] | ((uint64_t)stage_mk[mi + 1] << 32);
-                uint32_t mbits = (uint32_t)(mtwo >> (j & 31)) & mmask;
-                if (mbits == 0) {
-                    w = lut[code];
-                } else {
-                    // non-ACGT letters in the window: evaluate KmerAffinity on the raw bytes
-                    uint8_t kmer[16];
-                    const uint8_t *b = tr.bases + o + j;
-                    if (!reverse) {
-                        for (int q = 0; q < k; q++) kmer[q] = b[q];
+            for (int r = 0; r < PFX_ITEMS; r++) {
+                uint64_t w = 0;
+                if ((uint32_t)r < nvalid) {
+                    const uint32_t d = reverse ? (nvalid - 1 - r) : (uint32_t)r;  // window start = jb + d
+                    const uint32_t ofs = ob + d;
+                    const uint32_t code = (ofs < 16 ? (uint32_t)(lo64 >> (2 * ofs)) : (uint32_t)(hi64 >> (2 * (ofs - 16)))) & kmask;
+                    const uint32_t mbits = (uint32_t)(m64 >> (omb + d)) & mmask;
+                    if (mbits == 0) {
+                        w = lut[code];
                     } else {
-                        for (int q = 0; q < k; q++) {  // utils.go:37-59
-                            uint8_t c = b[k - 1 - q], oc;
-                            switch (c) { case 'A': oc = 'T'; break; case 'T': oc = 'A'; break; case 'G': oc = 'C'; break; case 'C': oc = 'G'; break; default: oc = 'N'; }
-                            kmer[q] = oc;
+                        // non-ACGT letters in the window: evaluate KmerAffinity on the raw bytes
+                        uint8_t kmer[16];
+                        const uint8_t *bp = tr.bases + o + jb + d;
+                        if (!reverse) {
+                            for (int q = 0; q < k; q++) kmer[q] = bp[q];
+                        } else {
+                            for (int q = 0; q < k; q++) {  // utils.go:37-59
+                                uint8_t c = bp[k - 1 - q], oc;
+                                switch (c) { case 'A': oc = 'T'; break; case 'T': oc = 'A'; break; case 'G': oc = 'C'; break; case 'C': oc = 'G'; break; default: oc = 'N'; }
+                                kmer[q] = oc;
+                            }
                         }
+                        w = quantize(kmer_affinity_bytes(kmer, k, T), scale);
                     }
-                    w = quantize(kmer_affinity_bytes(kmer, k, T), scale);
                 }
+                run += w;
+                x[r] = run;
             }
-            run += w;
-            x[r] = run;
+        } else {
+#pragma unroll
+            for (int r = 0; r < PFX_ITEMS; r++) x[r] = 0;
         }
         // block-wide exclusive scan of the per-thread totals
         uint64_t incl = run;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             uint64_t v = __shfl_up_sync(0xffffffffu, incl, d);
-            if ((threadIdx.x & 31) >= d) incl += v;
+            if (lane >= (uint32_t)d) incl += v;
         }
-        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+        if (lane == 31) warp_tot[warp] = incl;
         __syncthreads();
-        uint64_t base = carry;
-        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) base += warp_tot[w];
-        uint64_t excl = base + incl - run;
+        uint64_t base = carry, tile_total = 0;
 #pragma unroll
-        for (int r = 0; r < PFX_ITEMS; r++) stage_out[threadIdx.x * PFX_ITEMS + r] = excl + x[r];
-        uint64_t tile_total = 0;
-        for (int w = 0; w < PFX_THREADS / 32; w++) tile_total += warp_tot[w];
+        for (int w = 0; w < PFX_THREADS / 32; w++) {
+            uint64_t v = warp_tot[w];
+            if ((uint32_t)w < warp) base += v;
+            tile_total += v;
+        }
         carry += tile_total;
-        __syncthreads();
-        for (uint32_t q = threadIdx.x; q < ntile; q += PFX_THREADS) P[i0 + 1 + q] = stage_out[q];
+        const uint64_t excl = base + incl - run;
+        if (ib < proflen) {
+            uint64_t *dst = P + 1 + ib;
+            if (ib + PFX_ITEMS <= proflen) {
+                ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dst);
+#pragma unroll
+                for (int r = 0; r < PFX_ITEMS; r += 2) d2[r >> 1] = make_ulonglong2(excl + x[r], excl + x[r + 1]);
+            } else {
+                for (uint32_t r = 0; r < proflen - ib; r++) dst[r] = excl + x[r];
+            }
+        }
     }
 }
 
 size_t prefix_smem_bytes(int k, int *lut_in_smem) {
-    size_t base = (size_t)PFX_TILE * 8 + (PFX_STAGE_WORDS + PFX_STAGE_MASK + 1) * 4 + (PFX_THREADS / 32 + 1) * 8;
+    size_t base = (PFX_THREADS / 32) * 8 + (size_t)(PFX_STAGE_WORDS + PFX_STAGE_MASK) * 4;
     *lut_in_smem = (k <= 6);
     return base + (*lut_in_smem ? ((size_t)4 << (2 * k)) : 0);
 }
@@ -285,7 +308,6 @@ void launch_prefix(cudaStream_t st, const DevTranscripts &tr, int k, double T, c
     if (!tr.n) return;
     int lut_in_smem;
     size_t smem = prefix_smem_bytes(k, &lut_in_smem);
-    cudaFuncSetAttribute(k_prefix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(tr.n, strands);
     k_prefix<<<grid, PFX_THREADS, smem, st>>>(tr, k, T, wq_f, wq_r, kmax_bits, Pf, Pr, lut_in_smem);
 }

@@ -13,12 +13,16 @@ void launch_prefix(cudaStream_t st, const DevTranscripts &tr, int k, double T, c
                    const unsigned long long *kmax_bits, uint64_t *Pf, uint64_t *Pr, int strands);
 
 // k_fragment.cu
-int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint64_t n_mol, uint64_t *keys,
-                    uint64_t cap, unsigned long long *count, unsigned long long *hist_frag, unsigned long long *hist_polya,
-                    uint2 *long_list, uint32_t *long_hi, uint32_t long_cap, unsigned int *long_count, int *error);
-int launch_fragment_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint64_t *keys, uint64_t cap,
-                         unsigned long long *count, unsigned long long *hist_frag, unsigned long long *hist_polya,
-                         uint2 *long_list, uint32_t *long_hi, uint32_t n_long, int *error);
+struct FragBuffers {
+    uint64_t *keys; uint64_t cap; unsigned long long *count;       // fragment keys out
+    unsigned long long *hist_frag, *hist_polya;                    // histograms by length
+    uint2 *long_list; uint32_t *long_hi; uint32_t long_cap; unsigned int *long_count;  // deferred long molecules
+    int *error;
+    uint4 *q_a; uint2 *q_b; uint64_t q_cap; unsigned long long *q_count;               // interval work queue
+};
+int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint64_t n_mol, const FragBuffers &fb);
+int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint64_t n_q);
+int launch_fragment_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t n_long);
 
 // k_pcr.cu
 struct DevSpecies {
