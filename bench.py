@@ -154,6 +154,10 @@ def main():
     if opts.impl == "reference":
         reference_arm(opts, rank)
         return
+    # libraries (NCCL) print banners on stdout: keep fd 1 clean for the single JSON line
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -196,18 +200,31 @@ def main():
         total, base = shard.allgather_totals(local, device=dev if world > 1 else None)
         h.sample(total, base)
 
-    def step_e2e(step):
+    e2e_phase = {"configure+target": 0.0, "h2d (add_transcripts)": 0.0, "build_library": 0.0, "select": 0.0, "d2h (records)": 0.0}
+
+    def step_e2e(step, timed=False):
         """public API, host buffers in, host records out"""
+        t = [time.perf_counter()]
         args = make_args(n_frags_global, step + 1)
         pool.reset().configure(args)
-        pool.init_transcripts_arrays(bases, off, levels, n_tr, first)
+        t.append(time.perf_counter())
+        h.set_first_index(first)
+        h.add_transcripts_raw(bases, off, levels, n_tr)
+        t.append(time.perf_counter())
+        h.build_library()
+        t.append(time.perf_counter())
         local = h.class_totals()
         total, base = shard.allgather_totals(local, device=dev if world > 1 else None)
         h.sample(total, base)
+        t.append(time.perf_counter())
         n = int(h.stats().n_sampled)
         if n > out_cap:
             raise SystemExit("output buffer too small")
         h.sampled(into=out)
+        t.append(time.perf_counter())
+        if timed:
+            for k, a, b in zip(e2e_phase, t[:-1], t[1:]):
+                e2e_phase[k] += 1000.0 * (b - a)
         return n
 
     def step_resident(step):
@@ -229,7 +246,7 @@ def main():
     t0 = time.perf_counter()
     n_e2e = 0
     for s in range(opts.steps):
-        n_e2e += step_e2e(100 + s)
+        n_e2e += step_e2e(100 + s, timed=True)
     barrier()
     t_e2e = time.perf_counter() - t0
     d2h_bytes = (n_e2e // max(opts.steps, 1)) * 21 + 7 * 8 * (int(h.stats().high) + 2)
@@ -296,7 +313,7 @@ def main():
                    "species_per_gpu": int(st.n_species), "fragments_after_fragmentation_per_gpu": int(st.n_fragments),
                    "pool_total_rank0": int(st.pool_total)},
         "e2e": {"value": n_e2e / t_e2e, "unit": "fragments/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
-                "ms_per_step": 1000.0 * t_e2e / K},
+                "ms_per_step": 1000.0 * t_e2e / K, "phases_ms_rank0": {k: round(v / K, 3) for k, v in e2e_phase.items()}},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline,
@@ -316,7 +333,8 @@ def main():
         except Exception as e:  # the baseline must never break the GPU line
             line["cpu_baseline"] = {"value": None, "unit": "fragments/s", "cores": os.cpu_count(), "kind": "reference",
                                     "sample": "failed: %s" % e}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -22,20 +22,36 @@ struct DBuf {
     size_t n = 0;
     ~DBuf() { release(); }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-    cudaError_t ensure(size_t want) {  // contents are NOT preserved
-        if (want <= n) return cudaSuccess;
+    cudaError_t ensure(size_t want) {  // contents are NOT preserved; grows with 1/8 slack so sizes that
+        if (want <= n) return cudaSuccess;  // fluctuate from run to run do not reallocate every time
         release();
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(want, 1) * sizeof(T));
-        if (e == cudaSuccess) n = want;
+        size_t cap = want + want / 8 + 16;
+        cudaError_t e = cudaMalloc(&p, cap * sizeof(T));
+        if (e != cudaSuccess) { cap = std::max<size_t>(want, 1); e = cudaMalloc(&p, cap * sizeof(T)); }
+        if (e == cudaSuccess) n = cap;
+        return e;
+    }
+    // grow to at least `want` elements keeping the first `used` (device-to-device copy on `st`)
+    cudaError_t grow_preserve(size_t want, size_t used, cudaStream_t st) {
+        if (want <= n) return cudaSuccess;
+        size_t cap = want + want / 2 + 16;
+        T *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, cap * sizeof(T));
+        if (e != cudaSuccess) { cap = want; e = cudaMalloc(&q, cap * sizeof(T)); }
+        if (e != cudaSuccess) return e;
+        if (p && used) {
+            e = cudaMemcpyAsync(q, p, std::min(used, n) * sizeof(T), cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+        if (p) cudaFree(p);
+        p = q; n = cap;
         return e;
     }
 };
 
-struct Batch {
-    uint8_t *d_bases = nullptr;
-    uint64_t *d_src_off = nullptr;
-    uint32_t n = 0;
-    uint32_t first = 0;
+struct Staging {  // reusable device staging of the batch being ingested (kept across rlsim_clear_transcripts)
+    DBuf<uint8_t> bases;
+    DBuf<uint64_t> off;
 };
 
 uint32_t bits_for(uint64_t v) {
@@ -77,17 +93,19 @@ struct rlsim_handle {
     uint64_t len_eff_low = 0, len_eff_high = 0;
     // transcripts
     uint32_t first_index = 0;
-    std::vector<Batch> batches;
+    Staging staging;
+    cudaStream_t st_copy = nullptr;  // H2D of the next chunk overlaps ingest/prefix of the previous one
+    std::vector<cudaEvent_t> ev_chunk;
     std::vector<uint64_t> h_srclen;  // unpadded lengths as added
     std::vector<uint64_t> h_expr;
     std::vector<uint64_t> h_off;     // padded offsets [n+1]
     std::vector<uint32_t> h_len;     // with polyA
-    bool ingested = false;
     uint64_t n_mol = 0, total_padded = 0;
     DBuf<uint8_t> d_bases;
     DBuf<uint32_t> d_packed, d_nmask, d_gc, d_len;
     DBuf<uint64_t> d_off, d_expr, d_mol_off, d_Pf, d_Pr;
-    bool have_prefix = false;
+    uint32_t prefix_upto = 0;  // transcripts [0, prefix_upto) have valid priming prefix sums for the current model
+    bool lut_valid = false;
     // model tables
     DBuf<double> d_gc_raw, d_len_eff, d_raw_prob, d_K;
     DBuf<uint32_t> d_raw_len, d_wq_f, d_wq_r;
@@ -211,8 +229,8 @@ DevTranscripts make_tr(rlsim_handle *h) {
     t.n = (uint32_t)h->h_len.size();
     t.bases = h->d_bases.p; t.packed = h->d_packed.p; t.nmask = h->d_nmask.p; t.off = h->d_off.p; t.len = h->d_len.p;
     t.expr = h->d_expr.p; t.mol_off = h->d_mol_off.p;
-    t.Pf = h->have_prefix && needs_fwd(h->p.frag_method) ? h->d_Pf.p : nullptr;
-    t.Pr = h->have_prefix && needs_rev(h->p.frag_method) ? h->d_Pr.p : nullptr;
+    t.Pf = needs_fwd(h->p.frag_method) ? h->d_Pf.p : nullptr;
+    t.Pr = needs_rev(h->p.frag_method) ? h->d_Pr.p : nullptr;
     t.gc = h->d_gc.p;
     return t;
 }
@@ -239,45 +257,41 @@ int raw_target_finish(rlsim_handle *h) {  // raw_target.go:54,59-90
     return 0;
 }
 
-int ingest(rlsim_handle *h) {
-    if (h->ingested) return 0;
-    if (!h->have_model) FAIL(h, RLSIM_E_ARG, "rlsim_set_model must precede transcript ingest");
-    uint32_t n = (uint32_t)h->h_srclen.size();
-    h->h_off.assign(n + 1, 0);
-    h->h_len.assign(n, 0);
+// priming affinities -> prefix sums for transcripts [t0, t1) (nnthermo.go:177-201); launches only
+int launch_prefix_range(rlsim_handle *h, uint32_t t0, uint32_t t1) {
+    int method = h->p.frag_method;
+    if (!h->lut_valid) {
+        uint32_t nk = 1u << (2 * h->p.kmer_len);
+        CK(h, h->d_K.ensure(nk)); CK(h, h->d_wq_f.ensure(nk)); CK(h, h->d_wq_r.ensure(nk));
+        launch_kmer_lut(h->st, h->p.kmer_len, h->p.priming_temp, h->d_K.p, h->d_kmax.p, h->d_wq_f.p, h->d_wq_r.p);
+        h->lut_valid = true;
+        h->launches[RLSIM_T_PREFIX] += 2;
+    }
+    launch_prefix(h->st, make_tr(h), t0, t1, h->p.kmer_len, h->p.priming_temp, h->d_wq_f.p, h->d_wq_r.p, h->d_kmax.p,
+                  h->d_Pf.p, h->d_Pr.p, needs_rev(method) ? 2 : 1);
+    h->launches[RLSIM_T_PREFIX] += 1;
+    return 0;
+}
+
+// everything that needs the complete transcript set: molecule offsets, remaining prefix sums
+int finalize(rlsim_handle *h) {
+    uint32_t n = (uint32_t)h->h_len.size();
     std::vector<uint64_t> mol_off(n + 1, 0);
-    for (uint32_t t = 0; t < n; t++) {
-        uint64_t L = h->h_srclen[t] + h->polya_max;
-        if (L >= (1ull << 32)) FAIL(h, RLSIM_E_UNSUPPORTED, "transcript longer than 2^32-1 bases");
-        h->h_len[t] = (uint32_t)L;
-        h->h_off[t + 1] = h->h_off[t] + ((L + 31) & ~31ull);
-        mol_off[t + 1] = mol_off[t] + h->h_expr[t];
-    }
-    h->total_padded = h->h_off[n];
+    for (uint32_t t = 0; t < n; t++) mol_off[t + 1] = mol_off[t] + h->h_expr[t];
     h->n_mol = mol_off[n];
-    if (h->total_padded >= (1ull << 40)) FAIL(h, RLSIM_E_UNSUPPORTED, "more than 2^40 bases on one GPU");
-    size_t tot = h->total_padded;
-    CK(h, h->d_bases.ensure(tot + 64));
-    CK(h, h->d_packed.ensure(tot / 16 + 8));
-    CK(h, h->d_nmask.ensure(tot / 32 + 8));
-    CK(h, h->d_gc.ensure(tot + n + 8));
-    CK(h, h->d_off.ensure(n + 1)); CK(h, h->d_len.ensure(n)); CK(h, h->d_expr.ensure(n)); CK(h, h->d_mol_off.ensure(n + 1));
-    CK(h, cudaMemsetAsync(h->d_packed.p + tot / 16, 0, 8 * 4, h->st));
-    CK(h, cudaMemsetAsync(h->d_nmask.p + tot / 32, 0, 8 * 4, h->st));
-    CK(h, cudaMemcpyAsync(h->d_off.p, h->h_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, h->st));
-    CK(h, cudaMemcpyAsync(h->d_len.p, h->h_len.data(), n * 4, cudaMemcpyHostToDevice, h->st));
-    CK(h, cudaMemcpyAsync(h->d_expr.p, h->h_expr.data(), n * 8, cudaMemcpyHostToDevice, h->st));
+    CK(h, h->d_mol_off.ensure(n + 1));
     CK(h, cudaMemcpyAsync(h->d_mol_off.p, mol_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, h->st));
-    StageTimer tm(h, RLSIM_T_LAYOUT, h->batches.size());
-    for (auto &b : h->batches) {
-        launch_ingest(h->st, b.d_bases, b.d_src_off, b.n, h->polya_max, h->d_off.p + b.first, h->d_bases.p, h->d_packed.p,
-                      h->d_nmask.p, h->d_gc.p + b.first);
+    CK(h, cudaStreamSynchronize(h->st));
+    if (needs_fwd(h->p.frag_method) && h->prefix_upto < n) {
+        CK(h, h->d_Pf.grow_preserve(h->total_padded + 2ull * n + 8, h->prefix_upto ? h->d_Pf.n : 0, h->st));
+        if (needs_rev(h->p.frag_method)) CK(h, h->d_Pr.grow_preserve(h->total_padded + 2ull * n + 8, h->prefix_upto ? h->d_Pr.n : 0, h->st));
+        StageTimer tm(h, RLSIM_T_PREFIX, 0);
+        int rc = launch_prefix_range(h, h->prefix_upto, n);
+        if (rc) return rc;
+        tm.stop();
+        CK(h, cudaGetLastError());
+        h->prefix_upto = n;
     }
-    tm.stop();
-    CK(h, cudaGetLastError());
-    for (auto &b : h->batches) { cudaFree(b.d_bases); cudaFree(b.d_src_off); b.d_bases = nullptr; b.d_src_off = nullptr; }
-    h->batches.clear();
-    h->ingested = true;
     return 0;
 }
 
@@ -306,6 +320,7 @@ int rlsim_create(int device, rlsim_handle **out) {
     rlsim_handle *h = new rlsim_handle();
     h->device = device;
     if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
         (e = h->d_error.ensure(1)) != cudaSuccess || (e = h->d_counters.ensure(4)) != cudaSuccess ||
         (e = h->d_long_count.ensure(1)) != cudaSuccess || (e = h->d_kmax.ensure(1)) != cudaSuccess) {
@@ -321,7 +336,8 @@ int rlsim_create(int device, rlsim_handle **out) {
 void rlsim_destroy(rlsim_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    for (auto &b : h->batches) { cudaFree(b.d_bases); cudaFree(b.d_src_off); }
+    for (auto e : h->ev_chunk) cudaEventDestroy(e);
+    if (h->st_copy) cudaStreamDestroy(h->st_copy);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->st) cudaStreamDestroy(h->st);
@@ -343,9 +359,10 @@ int rlsim_set_model(rlsim_handle *h, const rlsim_params *p) {
     uint64_t mn, mx;
     mix_minmax(p->polya, p->n_polya, &mn, &mx);  // pool.go:84
     if (mx >= (1u << 24)) FAIL(h, RLSIM_E_UNSUPPORTED, "poly(A) maximum >= 2^24");
-    if (h->ingested && h->polya_max != (uint32_t)mx) FAIL(h, RLSIM_E_ARG, "poly(A) maximum cannot change after transcripts were ingested");
+    if (!h->h_len.empty() && h->polya_max != (uint32_t)mx) FAIL(h, RLSIM_E_ARG, "poly(A) maximum cannot change after transcripts were added");
     h->polya_max = (uint32_t)mx;
-    h->have_prefix = false;
+    h->prefix_upto = 0;
+    h->lut_valid = false;
     if (p->n_target > 0) {
         mix_minmax(p->target, p->n_target, &h->low, &h->high);  // target.go:67
         if (h->high >= (1u << 24)) FAIL(h, RLSIM_E_UNSUPPORTED, "maximum fragment length >= 2^24");
@@ -413,10 +430,9 @@ int rlsim_set_first_index(rlsim_handle *h, uint32_t first_index) { h->first_inde
 
 int rlsim_clear_transcripts(rlsim_handle *h) {
     cudaSetDevice(h->device);
-    for (auto &b : h->batches) { cudaFree(b.d_bases); cudaFree(b.d_src_off); }
-    h->batches.clear();
+    cudaStreamSynchronize(h->st);
     h->h_srclen.clear(); h->h_expr.clear(); h->h_off.clear(); h->h_len.clear();
-    h->ingested = false; h->have_prefix = false; h->fragmented = h->amplified = h->sampled = false;
+    h->prefix_upto = 0; h->fragmented = h->amplified = h->sampled = false;
     h->n_mol = h->total_padded = h->n_frag = h->n_sp = h->n_out = h->pool_total = 0;
     memset(h->ms, 0, sizeof h->ms);
     memset(h->launches, 0, sizeof h->launches);
@@ -424,22 +440,69 @@ int rlsim_clear_transcripts(rlsim_handle *h) {
 }
 
 int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t *offsets, const uint64_t *expr, uint32_t n) {
-    if (h->ingested) FAIL(h, RLSIM_E_ARG, "transcripts cannot be added after the library was built");
+    if (!h->have_model) FAIL(h, RLSIM_E_ARG, "rlsim_set_model must precede rlsim_add_transcripts (the poly(A) maximum shapes the layout)");
     if (n == 0) return 0;
     cudaSetDevice(h->device);
-    Batch b;
-    b.n = n;
-    b.first = (uint32_t)h->h_srclen.size();
-    uint64_t nbytes = offsets[n] - offsets[0];
+    CK(h, cudaStreamSynchronize(h->st));  // earlier kernels may still read the staging buffer / offset arrays
+    const uint32_t n0 = (uint32_t)h->h_len.size();
+    const uint64_t nbytes = offsets[n] - offsets[0];
+    if (h->h_off.empty()) h->h_off.push_back(0);
     std::vector<uint64_t> rel(n + 1);
     for (uint32_t i = 0; i <= n; i++) rel[i] = offsets[i] - offsets[0];
-    CK(h, cudaMalloc(&b.d_bases, std::max<uint64_t>(nbytes, 1)));
-    CK(h, cudaMalloc(&b.d_src_off, (n + 1) * 8));
-    CK(h, cudaMemcpyAsync(b.d_bases, bases + offsets[0], nbytes, cudaMemcpyHostToDevice, h->st));
-    CK(h, cudaMemcpyAsync(b.d_src_off, rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, h->st));
-    CK(h, cudaStreamSynchronize(h->st));  // caller-owned buffers are only read during the call
-    for (uint32_t i = 0; i < n; i++) { h->h_srclen.push_back(rel[i + 1] - rel[i]); h->h_expr.push_back(expr[i]); }
-    h->batches.push_back(b);
+    for (uint32_t i = 0; i < n; i++) {
+        uint64_t L = rel[i + 1] - rel[i] + h->polya_max;
+        if (L >= (1ull << 32)) FAIL(h, RLSIM_E_UNSUPPORTED, "transcript longer than 2^32-1 bases");
+        h->h_srclen.push_back(rel[i + 1] - rel[i]);
+        h->h_expr.push_back(expr[i]);
+        h->h_len.push_back((uint32_t)L);
+        h->h_off.push_back(h->h_off.back() + ((L + 31) & ~31ull));
+    }
+    const uint32_t nn = n0 + n;
+    const uint64_t old_total = h->total_padded, tot = h->h_off[nn];
+    if (tot >= (1ull << 40)) FAIL(h, RLSIM_E_UNSUPPORTED, "more than 2^40 bases on one GPU");
+    h->total_padded = tot;
+    h->fragmented = h->amplified = h->sampled = false;
+    // ---- device arrays: grow keeping what earlier batches wrote
+    CK(h, h->d_bases.grow_preserve(tot + 64, old_total, h->st));
+    CK(h, h->d_packed.grow_preserve(tot / 16 + 8, old_total / 16, h->st));
+    CK(h, h->d_nmask.grow_preserve(tot / 32 + 8, old_total / 32, h->st));
+    CK(h, h->d_gc.grow_preserve(tot + nn + 8, old_total + n0 + 1, h->st));
+    const bool want_prefix = needs_fwd(h->p.frag_method) && h->prefix_upto == n0;
+    if (want_prefix) {
+        CK(h, h->d_Pf.grow_preserve(tot + 2ull * nn + 8, n0 ? old_total + 2ull * n0 + 2 : 0, h->st));
+        if (needs_rev(h->p.frag_method)) CK(h, h->d_Pr.grow_preserve(tot + 2ull * nn + 8, n0 ? old_total + 2ull * n0 + 2 : 0, h->st));
+    }
+    CK(h, h->d_off.ensure(nn + 1)); CK(h, h->d_len.ensure(nn)); CK(h, h->d_expr.ensure(nn));
+    CK(h, cudaMemcpyAsync(h->d_off.p, h->h_off.data(), (size_t)(nn + 1) * 8, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemcpyAsync(h->d_len.p, h->h_len.data(), (size_t)nn * 4, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemcpyAsync(h->d_expr.p, h->h_expr.data(), (size_t)nn * 8, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemsetAsync(h->d_packed.p + tot / 16, 0, 8 * 4, h->st));
+    CK(h, cudaMemsetAsync(h->d_nmask.p + tot / 32, 0, 8 * 4, h->st));
+    CK(h, h->staging.bases.ensure(nbytes));
+    CK(h, h->staging.off.ensure(n + 1));
+    CK(h, cudaMemcpyAsync(h->staging.off.p, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, h->st));
+    // ---- pipeline: H2D of chunk c+1 on the copy stream overlaps ingest (+ prefix sums) of chunk c
+    const uint64_t chunk_bytes = 32ull << 20;
+    StageTimer tm(h, RLSIM_T_LAYOUT, 0);
+    uint32_t t0 = 0, c = 0;
+    while (t0 < n) {
+        uint32_t t1 = t0;
+        while (t1 < n && rel[t1] - rel[t0] < chunk_bytes) t1++;
+        if (h->ev_chunk.size() <= c) { cudaEvent_t e; CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_chunk.push_back(e); }
+        if (rel[t1] > rel[t0])
+            CK(h, cudaMemcpyAsync(h->staging.bases.p + rel[t0], bases + offsets[0] + rel[t0], rel[t1] - rel[t0], cudaMemcpyHostToDevice, h->st_copy));
+        CK(h, cudaEventRecord(h->ev_chunk[c], h->st_copy));
+        CK(h, cudaStreamWaitEvent(h->st, h->ev_chunk[c], 0));
+        launch_ingest(h->st, h->staging.bases.p, h->staging.off.p + t0, t1 - t0, h->polya_max, h->d_off.p + n0 + t0, h->d_bases.p,
+                      h->d_packed.p, h->d_nmask.p, h->d_gc.p + n0 + t0);
+        h->launches[RLSIM_T_LAYOUT]++;
+        if (want_prefix) { int rc = launch_prefix_range(h, n0 + t0, n0 + t1); if (rc) return rc; }
+        t0 = t1; c++;
+    }
+    CK(h, cudaStreamSynchronize(h->st_copy));  // caller-owned buffers are only read during the call
+    tm.stop();
+    CK(h, cudaGetLastError());
+    if (want_prefix) h->prefix_upto = nn;
     return 0;
 }
 
@@ -447,26 +510,11 @@ int rlsim_fragment(rlsim_handle *h) {
     if (!h->have_model) FAIL(h, RLSIM_E_ARG, "rlsim_set_model first");
     if (h->p.n_target == 0 && !h->have_target) FAIL(h, RLSIM_E_ARG, "a raw target needs its sampled histogram before fragmentation");
     cudaSetDevice(h->device);
-    int rc = ingest(h);
+    int rc = finalize(h);
     if (rc) return rc;
     if (h->low == 0) FAIL(h, RLSIM_E_ARG, "Serious trouble: fragment length is zero!");  // transcript.go:194-196
     uint32_t n = (uint32_t)h->h_len.size();
     int method = h->p.frag_method;
-    // ---- priming affinities -> prefix sums (nnthermo.go:177-201)
-    if (needs_fwd(method) && !h->have_prefix) {
-        uint32_t nk = 1u << (2 * h->p.kmer_len);
-        CK(h, h->d_K.ensure(nk)); CK(h, h->d_wq_f.ensure(nk)); CK(h, h->d_wq_r.ensure(nk));
-        CK(h, h->d_Pf.ensure(h->total_padded + 2ull * n + 8));
-        if (needs_rev(method)) CK(h, h->d_Pr.ensure(h->total_padded + 2ull * n + 8));
-        h->have_prefix = true;
-        DevTranscripts tr = make_tr(h);
-        StageTimer tm(h, RLSIM_T_PREFIX, 3);
-        launch_kmer_lut(h->st, h->p.kmer_len, h->p.priming_temp, h->d_K.p, h->d_kmax.p, h->d_wq_f.p, h->d_wq_r.p);
-        launch_prefix(h->st, tr, h->p.kmer_len, h->p.priming_temp, h->d_wq_f.p, h->d_wq_r.p, h->d_kmax.p, h->d_Pf.p, h->d_Pr.p,
-                      needs_rev(method) ? 2 : 1);
-        tm.stop();
-        CK(h, cudaGetLastError());
-    }
     // ---- capacity estimate for the fragment keys
     double loc = h->raw_location;
     if (h->p.n_target > 0) {
@@ -818,7 +866,6 @@ int rlsim_get_sampled(rlsim_handle *h, uint32_t *tr, uint32_t *start, uint32_t *
     D2H(tr, h->d_o_tr.p, n * 4); D2H(start, h->d_o_start.p, n * 4); D2H(end, h->d_o_end.p, n * 4);
     D2H(minus_strand, h->d_o_minus.p, n); D2H(id, h->d_o_id.p, n * 8);
     CK(h, cudaStreamSynchronize(h->st));
-    if (tr) for (uint64_t i = 0; i < n; i++) tr[i] += h->first_index;
     return 0;
 }
 
@@ -850,7 +897,7 @@ int rlsim_format_fasta(rlsim_handle *h, const uint8_t *names, const uint64_t *na
     if (!buf) { tm.stop(); return 0; }
     if (cap < total) { tm.stop(); FAIL(h, RLSIM_E_ARG, "FASTA buffer too small"); }
     CK(h, h->d_fasta.ensure(total));
-    launch_fasta_write(h->st, make_tr(h), s, n, h->d_names.p, h->d_name_off.p, h->d_rec_off.p, h->d_fasta.p);
+    launch_fasta_write(h->st, make_tr(h), s, n, h->d_names.p, h->d_name_off.p, h->d_rec_off.p, h->first_index, h->d_fasta.p);
     tm.stop();
     CK(h, cudaGetLastError());
     CK(h, cudaMemcpyAsync(buf, h->d_fasta.p, total, cudaMemcpyDeviceToHost, h->st));
@@ -874,7 +921,7 @@ int rlsim_probe_kmer_lut(rlsim_handle *h, double *K_out, uint32_t *w_out, uint32
 }
 
 int rlsim_probe_prefix(rlsim_handle *h, uint32_t tr, int reverse, uint64_t *out, uint32_t n) {
-    if (!h->have_prefix) FAIL(h, RLSIM_E_ARG, "no priming prefix sums (run rlsim_fragment with a priming method)");
+    if (h->prefix_upto <= tr) FAIL(h, RLSIM_E_ARG, "no priming prefix sums (run rlsim_fragment with a priming method)");
     if (tr >= h->h_len.size()) FAIL(h, RLSIM_E_ARG, "transcript index out of range");
     if (reverse && !needs_rev(h->p.frag_method)) FAIL(h, RLSIM_E_ARG, "no reverse profile for this method");
     cudaSetDevice(h->device);
@@ -886,7 +933,6 @@ int rlsim_probe_prefix(rlsim_handle *h, uint32_t tr, int reverse, uint64_t *out,
 }
 
 int rlsim_probe_gc_prefix(rlsim_handle *h, uint32_t tr, uint32_t *out, uint32_t n) {
-    if (!h->ingested) FAIL(h, RLSIM_E_ARG, "transcripts not ingested yet");
     if (tr >= h->h_len.size()) FAIL(h, RLSIM_E_ARG, "transcript index out of range");
     cudaSetDevice(h->device);
     uint32_t m = std::min(n, h->h_len[tr] + 1);

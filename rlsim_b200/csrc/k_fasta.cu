@@ -24,27 +24,28 @@ __device__ __forceinline__ uint8_t *put_str(uint8_t *p, const char *s) {
     return p;
 }
 
-__global__ void k_fasta_sizes(DevSampled s, uint64_t n, const uint64_t *__restrict__ name_off, uint64_t *__restrict__ sizes) {
+__global__ void k_fasta_sizes(DevSampled s, uint64_t n, const uint64_t *__restrict__ name_off, uint32_t first_index,
+                              uint64_t *__restrict__ sizes) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t t = s.tr[i];
+    uint32_t t = s.tr[i] - first_index;
     uint64_t nl = name_off[t + 1] - name_off[t];
     // ">Fg_" id "_" name " (Strand " c " Offset " start " -- " end ")\n" seq "\n"
     sizes[i] = 4 + dec_digits(s.id[i]) + 1 + nl + 9 + 1 + 8 + dec_digits(s.start[i]) + 4 + dec_digits(s.end[i]) + 2 +
                (uint64_t)(s.end[i] - s.start[i]) + 1;
 }
-void launch_fasta_sizes(cudaStream_t st, const DevSampled &s, uint64_t n, const uint64_t *name_off, uint32_t,
+void launch_fasta_sizes(cudaStream_t st, const DevSampled &s, uint64_t n, const uint64_t *name_off, uint32_t first_index,
                         uint64_t *sizes) {
-    if (n) k_fasta_sizes<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, n, name_off, sizes);
+    if (n) k_fasta_sizes<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, n, name_off, first_index, sizes);
 }
 
 __global__ void k_fasta_write(DevTranscripts tr, DevSampled s, uint64_t n, const uint8_t *__restrict__ names,
                               const uint64_t *__restrict__ name_off, const uint64_t *__restrict__ rec_off,
-                              uint8_t *__restrict__ out) {
+                              uint32_t first_index, uint8_t *__restrict__ out) {
     uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint32_t lane = threadIdx.x & 31;
     if (i >= n) return;
-    uint32_t t = s.tr[i], start = s.start[i], end = s.end[i];
+    uint32_t t = s.tr[i] - first_index, start = s.start[i], end = s.end[i];
     bool minus = s.minus[i] != 0;
     uint64_t nl = name_off[t + 1] - name_off[t];
     uint8_t *p = out + rec_off[i];
@@ -81,8 +82,8 @@ __global__ void k_fasta_write(DevTranscripts tr, DevSampled s, uint64_t n, const
     if (lane == 0) sp[len] = '\n';
 }
 void launch_fasta_write(cudaStream_t st, const DevTranscripts &tr, const DevSampled &s, uint64_t n, const uint8_t *names,
-                        const uint64_t *name_off, const uint64_t *rec_off, uint8_t *out) {
-    if (n) k_fasta_write<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(tr, s, n, names, name_off, rec_off, out);
+                        const uint64_t *name_off, const uint64_t *rec_off, uint32_t first_index, uint8_t *out) {
+    if (n) k_fasta_write<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(tr, s, n, names, name_off, rec_off, first_index, out);
 }
 
 }  // namespace rl

@@ -54,26 +54,28 @@ __device__ __forceinline__ double gc_eff(const DevModel &m, uint32_t gc_count, u
 // iteration.  A lane that needs it PARKS; lanes keep running fast-path work (inversion, squeeze accepts) until each
 // one is parked or done, then the slow test runs once for all parked lanes together.  Per-species constants
 // (p, q, p/q, log q) are hoisted out of the cycle loop.
-__device__ __forceinline__ uint64_t amplify(PxCursor &cur, uint64_t c, double pp, int cycles, bool &overflow) {
-    if (!(pp > 0.0) || c == 0) return c;  // Binomial(c, 0) = 0, Binomial(0, .) = 0
-    if (pp >= 1.0) {                      // Binomial(c, 1) = c
+// Must be called by ALL 32 lanes of a warp (lanes without a species pass live = false): the fast and slow phases
+// are separated by __syncwarp() so the slow test really runs once per round for all parked lanes together.
+__device__ __forceinline__ uint64_t amplify(PxCursor &cur, uint64_t c, double pp, int cycles, bool live, bool &overflow) {
+    if (!(pp > 0.0) || c == 0) live = false;  // Binomial(c, 0) = 0, Binomial(0, .) = 0: nothing to draw
+    if (live && pp >= 1.0) {                  // Binomial(c, 1) = c
         for (int cyc = 0; cyc < cycles; cyc++) {
             uint64_t nc = c + c;
             if (nc < c) { overflow = true; break; }
             c = nc;
         }
-        return c;
+        live = false;
     }
     const bool flip = !(pp <= 0.5);
     const double p = flip ? 1.0 - pp : pp;
     const double q = 1.0 - p;
     const double r = p / q;
     const double lq = det_log(q);
-    int cyc = 0;
+    int cyc = live ? 0 : cycles;
     bool have_setup = false;
     double nd = 0, b = 0, a = 0, cc = 0, vr = 0, alpha = 0, mm = 0;  // BTRS constants of the current cycle
     double us = 0, v = 0, k = 0;                                    // the parked attempt
-    while (cyc < cycles) {
+    while (__any_sync(0xffffffffu, cyc < cycles)) {
         bool parked = false;
         // ---- fast phase: run until this lane needs the slow test or has finished all cycles
         while (cyc < cycles) {
@@ -96,7 +98,7 @@ __device__ __forceinline__ uint64_t amplify(PxCursor &cur, uint64_t c, double pp
                         if (!restart) { res = (uint64_t)x; break; }
                     }
                     uint64_t nc = c + (flip ? c - res : res);
-                    if (nc < c) { overflow = true; return c; }
+                    if (nc < c) { overflow = true; cyc = cycles; break; }
                     c = nc;
                     cyc++;
                     continue;
@@ -117,7 +119,7 @@ __device__ __forceinline__ uint64_t amplify(PxCursor &cur, uint64_t c, double pp
             if (us >= 0.07 && v <= vr) {  // squeeze accept
                 res = (uint64_t)k;
                 uint64_t nc = c + (flip ? c - res : res);
-                if (nc < c) { overflow = true; return c; }
+                if (nc < c) { overflow = true; cyc = cycles; break; }
                 c = nc;
                 cyc++;
                 have_setup = false;
@@ -127,7 +129,8 @@ __device__ __forceinline__ uint64_t amplify(PxCursor &cur, uint64_t c, double pp
             parked = true;
             break;
         }
-        // ---- slow phase (lanes reconverge here): exact acceptance test of the parked attempt
+        __syncwarp();
+        // ---- slow phase: exact acceptance test of the parked attempts, all parked lanes together
         if (parked) {
             double lv = det_log(v * alpha / (a / (us * us) + b));
             double ub = (mm + 0.5) * det_log((mm + 1.0) / (r * (nd - mm + 1.0))) +
@@ -137,33 +140,37 @@ __device__ __forceinline__ uint64_t amplify(PxCursor &cur, uint64_t c, double pp
             if (lv <= ub) {
                 uint64_t res = (uint64_t)k;
                 uint64_t nc = c + (flip ? c - res : res);
-                if (nc < c) { overflow = true; return c; }
-                c = nc;
-                cyc++;
-                have_setup = false;
+                if (nc < c) { overflow = true; cyc = cycles; }
+                else { c = nc; cyc++; have_setup = false; }
             }
         }
+        __syncwarp();
     }
     return c;
 }
 
 constexpr int PCR_THREADS = 128;
-__global__ void __launch_bounds__(PCR_THREADS)
+__global__ void __launch_bounds__(PCR_THREADS, 5)
 k_pcr(const __grid_constant__ DevModel m, DevTranscripts tr, DevSpecies sp, int *error) {
     uint64_t i = (uint64_t)blockIdx.x * PCR_THREADS + threadIdx.x;
-    if (i >= sp.n) return;
-    uint32_t t = sp.tr[i], start = sp.start[i], len = sp.len[i];
-    uint32_t end = start + len;
+    const bool live = i < sp.n;
+    uint32_t t = 0, start = 0, len = 1, gcc = 0;
+    uint64_t c0 = 0;
     double e = m.fixed_eff;
-    uint32_t gcc = 0;
-    if (e == 0.0 || sp.gc) {
-        const uint32_t *gcp = tr.gc + tr.off[t] + t;
-        gcc = gcp[end] - gcp[start];
+    if (live) {
+        t = sp.tr[i]; start = sp.start[i]; len = sp.len[i];
+        c0 = sp.count0[i];
+        if (e == 0.0 || sp.gc) {
+            const uint32_t *gcp = tr.gc + tr.off[t] + t;
+            gcc = gcp[start + len] - gcp[start];
+        }
+        if (e == 0.0) e = m.len_eff[len - m.low] * gc_eff(m, gcc, len);
     }
-    if (e == 0.0) e = m.len_eff[len - m.low] * gc_eff(m, gcc, len);
+    const uint32_t end = start + len;
     PxCursor cur(PxStream{m.key_pcr, m.first_index + t, start, end});
     bool ovf = false;
-    uint64_t c = amplify(cur, (uint64_t)sp.count0[i], e, m.cycles, ovf);
+    uint64_t c = amplify(cur, c0, e, m.cycles, live, ovf);
+    if (!live) return;
     if (ovf) atomicExch(error, RLSIM_E_PCR_OVERFLOW);
     sp.count[i] = c;
     if (sp.eff) sp.eff[i] = e;
@@ -177,10 +184,12 @@ void launch_pcr(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, De
 __global__ void k_amplify_probe(PxKey key, const uint32_t *tse, const uint64_t *n0, const double *p, int cycles,
                                 uint64_t *out, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    PxCursor cur(PxStream{key, tse[3 * i], tse[3 * i + 1], tse[3 * i + 2]});
+    const bool live = i < n;
+    uint32_t j = live ? i : 0;
+    PxCursor cur(PxStream{key, tse[3 * j], tse[3 * j + 1], tse[3 * j + 2]});
     bool ovf = false;
-    out[i] = amplify(cur, n0[i], p[i], cycles, ovf);
+    uint64_t r = amplify(cur, n0[j], p[j], cycles, live, ovf);
+    if (live) out[i] = r;
 }
 void launch_amplify_probe(cudaStream_t st, PxKey key, const uint32_t *tse, const uint64_t *n0, const double *p, int cycles,
                           uint64_t *out, uint32_t n) {

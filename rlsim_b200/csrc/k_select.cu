@@ -166,7 +166,7 @@ __global__ void k_expand(const __grid_constant__ DevModel m, DevSpecies sp, cons
     }
     PxStream str{m.key_strand, m.first_index + t, start, end};
     bool minus = px_u01(px_draw64(str, j)) < m.strand_bias;  // sampler.go:219-227
-    out.tr[o] = t;
+    out.tr[o] = m.first_index + t;  // global transcript index
     out.start[o] = start;
     out.end[o] = end;
     out.minus[o] = minus ? 1 : 0;

@@ -5,6 +5,7 @@
 //   k_kmer_lut     : nnthermo.go:126-175 KmerAffinity for all 4^k ACGT k-mers (replaces the string-keyed memo map)
 //   k_prefix       : nnthermo.go:177-201 binding profiles, materialised as fixed-point prefix sums so that
 //                    SimulatePriming (nnthermo.go:203-217) becomes a binary search instead of an O(L) cumsum
+#include <algorithm>
 #include "kernels.cuh"
 #include "detmath.cuh"
 
@@ -178,7 +179,7 @@ constexpr int PFX_STAGE_MASK = PFX_TILE / 32 + 6;
 // 8 windows from the staged tile once, extracts the 8 k-mer codes by shifts, gathers the weights from the
 // shared-memory LUT, and writes its 8 running sums with four 16-byte stores.
 __global__ void __launch_bounds__(PFX_THREADS)
-k_prefix(DevTranscripts tr, int k, double T, const uint32_t *__restrict__ wq_f, const uint32_t *__restrict__ wq_r,
+k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, const uint32_t *__restrict__ wq_f, const uint32_t *__restrict__ wq_r,
          const unsigned long long *__restrict__ kmax_bits, uint64_t *__restrict__ Pf, uint64_t *__restrict__ Pr,
          int lut_in_smem) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -187,26 +188,27 @@ k_prefix(DevTranscripts tr, int k, double T, const uint32_t *__restrict__ wq_f, 
     uint32_t *stage_mk = stage_pk + PFX_STAGE_WORDS;                          // PFX_STAGE_MASK
     uint32_t *lut_s = stage_mk + PFX_STAGE_MASK;
 
-    const uint32_t t = blockIdx.x;
     const int reverse = blockIdx.y;
-    if (tr.expr[t] == 0) return;  // pool.go:104: never fragmented
-    const uint32_t L = tr.len[t];
-    const uint64_t o = tr.off[t];
-    uint64_t *P = (reverse ? Pr : Pf) + prefix_base(o, t);
     const uint32_t *lut = reverse ? wq_r : wq_f;
-    if (lut_in_smem) {
+    if (lut_in_smem) {  // once per (persistent) CTA, not once per transcript
         uint32_t n = 1u << (2 * k);
         for (uint32_t i = threadIdx.x; i < n; i += PFX_THREADS) lut_s[i] = lut[i];
         lut = lut_s;
     }
-    if (threadIdx.x == 0) P[0] = 0;
-    if (L <= (uint32_t)k) return;
-    const uint32_t proflen = L - (uint32_t)k;
     const double scale = 4294967296.0 / __longlong_as_double((long long)*kmax_bits);
     const uint32_t kmask = (1u << (2 * k)) - 1u;
     const uint32_t mmask = (1u << k) - 1u;
-    const uint64_t pk_base = o >> 4, mk_base = o >> 5;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (uint32_t t = t_begin + blockIdx.x; t < t_end; t += gridDim.x) {
+    if (tr.expr[t] == 0) continue;  // pool.go:104: never fragmented
+    const uint32_t L = tr.len[t];
+    const uint64_t o = tr.off[t];
+    uint64_t *P = (reverse ? Pr : Pf) + prefix_base(o, t);
+    if (threadIdx.x == 0) P[0] = 0;
+    if (L <= (uint32_t)k) continue;
+    const uint32_t proflen = L - (uint32_t)k;
+    const uint64_t pk_base = o >> 4, mk_base = o >> 5;
     uint64_t carry = 0;
 
     for (uint32_t i0 = 0; i0 < proflen; i0 += PFX_TILE) {
@@ -295,6 +297,7 @@ k_prefix(DevTranscripts tr, int k, double T, const uint32_t *__restrict__ wq_f, 
             }
         }
     }
+    }  // transcripts of this CTA
 }
 
 size_t prefix_smem_bytes(int k, int *lut_in_smem) {
@@ -303,13 +306,13 @@ size_t prefix_smem_bytes(int k, int *lut_in_smem) {
     return base + (*lut_in_smem ? ((size_t)4 << (2 * k)) : 0);
 }
 
-void launch_prefix(cudaStream_t st, const DevTranscripts &tr, int k, double T, const uint32_t *wq_f, const uint32_t *wq_r,
+void launch_prefix(cudaStream_t st, const DevTranscripts &tr, uint32_t t_begin, uint32_t t_end, int k, double T, const uint32_t *wq_f, const uint32_t *wq_r,
                    const unsigned long long *kmax_bits, uint64_t *Pf, uint64_t *Pr, int strands) {
-    if (!tr.n) return;
+    if (t_end <= t_begin) return;
     int lut_in_smem;
     size_t smem = prefix_smem_bytes(k, &lut_in_smem);
-    dim3 grid(tr.n, strands);
-    k_prefix<<<grid, PFX_THREADS, smem, st>>>(tr, k, T, wq_f, wq_r, kmax_bits, Pf, Pr, lut_in_smem);
+    dim3 grid(std::min<uint32_t>(t_end - t_begin, 148u * 8u), strands);  // persistent CTAs: the 16 KB LUT is loaded once per CTA
+    k_prefix<<<grid, PFX_THREADS, smem, st>>>(tr, t_begin, t_end, k, T, wq_f, wq_r, kmax_bits, Pf, Pr, lut_in_smem);
 }
 
 }  // namespace rl

@@ -9,7 +9,7 @@ void launch_ingest(cudaStream_t st, const uint8_t *src, const uint64_t *src_off,
                    const uint64_t *off, uint8_t *bases, uint32_t *packed, uint32_t *nmask, uint32_t *gc);
 void launch_kmer_lut(cudaStream_t st, int k, double T, double *K, unsigned long long *kmax_bits, uint32_t *wq_f,
                      uint32_t *wq_r);
-void launch_prefix(cudaStream_t st, const DevTranscripts &tr, int k, double T, const uint32_t *wq_f, const uint32_t *wq_r,
+void launch_prefix(cudaStream_t st, const DevTranscripts &tr, uint32_t t_begin, uint32_t t_end, int k, double T, const uint32_t *wq_f, const uint32_t *wq_r,
                    const unsigned long long *kmax_bits, uint64_t *Pf, uint64_t *Pr, int strands);
 
 // k_fragment.cu
@@ -70,6 +70,6 @@ void launch_expand(cudaStream_t st, const DevModel &m, const DevSpecies &sp, con
 void launch_fasta_sizes(cudaStream_t st, const DevSampled &s, uint64_t n, const uint64_t *name_off, uint32_t first_index,
                         uint64_t *sizes);
 void launch_fasta_write(cudaStream_t st, const DevTranscripts &tr, const DevSampled &s, uint64_t n, const uint8_t *names,
-                        const uint64_t *name_off, const uint64_t *rec_off, uint8_t *out);
+                        const uint64_t *name_off, const uint64_t *rec_off, uint32_t first_index, uint8_t *out);
 
 }  // namespace rl
