@@ -117,7 +117,7 @@ struct rlsim_handle {
     DBuf<uint2> d_long_list, d_q_b;
     DBuf<uint4> d_q_a;
     DBuf<uint32_t> d_long_hi;
-    DBuf<unsigned int> d_long_count;
+    DBuf<unsigned int> d_long_count, d_work;
     DBuf<int> d_error;
     DBuf<unsigned char> d_cub;
     uint64_t n_frag = 0;
@@ -268,7 +268,7 @@ int launch_prefix_range(rlsim_handle *h, uint32_t t0, uint32_t t1) {
         h->launches[RLSIM_T_PREFIX] += 2;
     }
     launch_prefix(h->st, make_tr(h), t0, t1, h->p.kmer_len, h->p.priming_temp, h->d_wq_f.p, h->d_wq_r.p, h->d_kmax.p,
-                  h->d_Pf.p, h->d_Pr.p, needs_rev(method) ? 2 : 1);
+                  h->d_Pf.p, h->d_Pr.p, needs_rev(method) ? 2 : 1, h->d_work.p);
     h->launches[RLSIM_T_PREFIX] += 1;
     return 0;
 }
@@ -323,7 +323,7 @@ int rlsim_create(int device, rlsim_handle **out) {
         (e = cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
         (e = h->d_error.ensure(1)) != cudaSuccess || (e = h->d_counters.ensure(4)) != cudaSuccess ||
-        (e = h->d_long_count.ensure(1)) != cudaSuccess || (e = h->d_kmax.ensure(1)) != cudaSuccess) {
+        (e = h->d_long_count.ensure(1)) != cudaSuccess || (e = h->d_work.ensure(4)) != cudaSuccess || (e = h->d_kmax.ensure(1)) != cudaSuccess) {
         g_create_error = std::string("rlsim_create: ") + cudaGetErrorString(e);
         delete h;
         return RLSIM_E_CUDA;

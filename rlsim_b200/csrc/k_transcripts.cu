@@ -164,155 +164,162 @@ void launch_kmer_lut(cudaStream_t st, int k, double T, double *K, unsigned long 
 }
 
 // ---------------------------------------------------------------- priming prefix sums
-constexpr int PFX_THREADS = 256;
-constexpr int PFX_ITEMS = 8;
-constexpr int PFX_TILE = PFX_THREADS * PFX_ITEMS;
-constexpr int PFX_STAGE_WORDS = PFX_TILE / 16 + 6;
-constexpr int PFX_STAGE_MASK = PFX_TILE / 32 + 6;
+constexpr int PFX_THREADS = 256;                 // 8 independent warps per CTA
+constexpr int PFX_ITEMS = 8;                     // profile entries per lane and sub-tile
+constexpr int PFX_SUB = 32 * PFX_ITEMS;          // 256 entries per warp sub-tile
+constexpr int PFX_ROW_U64 = PFX_ITEMS + 2;       // padded row of one lane in the transpose tile (80 B: conflict-free 16 B accesses)
+constexpr int PFX_TILE_U64 = 32 * PFX_ROW_U64;
 
-// grid = (transcripts, strands).  Forward profile entry i is the k-mer at plus[i, i+k); reverse entry i is the
-// reverse complement of plus[j, j+k), j = L-k-i (= minus[i, i+k), transcript.go:110 + nnthermo.go:184-199).
-// Both have L-k entries (nnthermo.go:193).  Output P[0..L-k]: exclusive prefix sums of the fixed-point weights,
-// stored at prefix_base(off[t], t) so that P[1] is 16-byte aligned.
+// One WARP per (transcript, strand); persistent CTAs fetch work from a global counter, so the 16 KB LUT is loaded
+// once per CTA and there is no block-level barrier in the loop.  Forward profile entry i is the k-mer at
+// plus[i, i+k); reverse entry i is the reverse complement of plus[j, j+k), j = L-k-i (= minus[i, i+k),
+// transcript.go:110 + nnthermo.go:184-199).  Both have L-k entries (nnthermo.go:193).  Output P[0..L-k]: exclusive
+// prefix sums of the fixed-point weights, stored at prefix_base(off[t], t) so that P[1] is 16-byte aligned.
 //
-// Each thread owns 8 consecutive profile entries: it pulls the <= 3 packed words and 2 mask words covering its
-// 8 windows from the staged tile once, extracts the 8 k-mer codes by shifts, gathers the weights from the
-// shared-memory LUT, and writes its 8 running sums with four 16-byte stores.
-__global__ void __launch_bounds__(PFX_THREADS)
-k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, const uint32_t *__restrict__ wq_f, const uint32_t *__restrict__ wq_r,
-         const unsigned long long *__restrict__ kmax_bits, uint64_t *__restrict__ Pf, uint64_t *__restrict__ Pr,
-         int lut_in_smem) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *warp_tot = reinterpret_cast<uint64_t *>(smem_raw);              // PFX_THREADS/32
-    uint32_t *stage_pk = reinterpret_cast<uint32_t *>(warp_tot + PFX_THREADS / 32);  // PFX_STAGE_WORDS
-    uint32_t *stage_mk = stage_pk + PFX_STAGE_WORDS;                          // PFX_STAGE_MASK
-    uint32_t *lut_s = stage_mk + PFX_STAGE_MASK;
+// Each lane owns 8 consecutive entries of a 256-entry sub-tile: it loads the 3 packed words and 2 mask words covering
+// its 8 windows (read-only path; neighbouring lanes share the words), extracts the 8 k-mer codes by shifts, gathers
+// the weights from the shared-memory LUT, and the warp scans the lane totals with shuffles.  The words of the next
+// sub-tile are requested before the current one is processed.
+struct PfxWords { uint32_t p0, p1, p2, m0, m1; };
 
+__device__ __forceinline__ uint32_t pfx_jb(int reverse, uint32_t L, int k, uint32_t proflen, uint32_t ib) {
+    // lowest plus-strand window start among the (valid) entries [ib, ib+8) of this lane
+    if (!reverse) return ib;
+    uint32_t nvalid = min((uint32_t)PFX_ITEMS, proflen - ib);
+    return L - k - (ib + nvalid - 1);
+}
+__device__ __forceinline__ PfxWords pfx_load(const DevTranscripts &tr, uint64_t o, uint32_t jb) {
+    const uint32_t *pk = tr.packed + (o >> 4) + (jb >> 4);
+    const uint32_t *mk = tr.nmask + (o >> 5) + (jb >> 5);
+    return PfxWords{__ldg(pk), __ldg(pk + 1), __ldg(pk + 2), __ldg(mk), __ldg(mk + 1)};
+}
+
+__global__ void __launch_bounds__(PFX_THREADS)
+k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, const uint32_t *__restrict__ wq_f,
+         const uint32_t *__restrict__ wq_r, const unsigned long long *__restrict__ kmax_bits, uint64_t *__restrict__ Pf,
+         uint64_t *__restrict__ Pr, int lut_in_smem, unsigned int *__restrict__ work) {
+    extern __shared__ __align__(16) unsigned char pfx_smem[];
+    uint64_t *tile_s = reinterpret_cast<uint64_t *>(pfx_smem);                            // 8 warps x PFX_TILE_U64
+    uint32_t *lut_s = reinterpret_cast<uint32_t *>(tile_s + (PFX_THREADS / 32) * PFX_TILE_U64);
     const int reverse = blockIdx.y;
     const uint32_t *lut = reverse ? wq_r : wq_f;
-    if (lut_in_smem) {  // once per (persistent) CTA, not once per transcript
+    if (lut_in_smem) {
         uint32_t n = 1u << (2 * k);
         for (uint32_t i = threadIdx.x; i < n; i += PFX_THREADS) lut_s[i] = lut[i];
         lut = lut_s;
     }
+    __syncthreads();
     const double scale = 4294967296.0 / __longlong_as_double((long long)*kmax_bits);
     const uint32_t kmask = (1u << (2 * k)) - 1u;
     const uint32_t mmask = (1u << k) - 1u;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t *Pout = reverse ? Pr : Pf;
 
-    for (uint32_t t = t_begin + blockIdx.x; t < t_end; t += gridDim.x) {
-    if (tr.expr[t] == 0) continue;  // pool.go:104: never fragmented
-    const uint32_t L = tr.len[t];
-    const uint64_t o = tr.off[t];
-    uint64_t *P = (reverse ? Pr : Pf) + prefix_base(o, t);
-    if (threadIdx.x == 0) P[0] = 0;
-    if (L <= (uint32_t)k) continue;
-    const uint32_t proflen = L - (uint32_t)k;
-    const uint64_t pk_base = o >> 4, mk_base = o >> 5;
-    uint64_t carry = 0;
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = t_begin + atomicAdd(&work[reverse], 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= t_end) break;
+        if (tr.expr[t] == 0) continue;  // pool.go:104: never fragmented
+        const uint32_t L = tr.len[t];
+        const uint64_t o = tr.off[t];
+        uint64_t *P = Pout + prefix_base(o, t);
+        if (lane == 0) P[0] = 0;
+        if (L <= (uint32_t)k) continue;
+        const uint32_t proflen = L - (uint32_t)k;
+        uint64_t carry = 0;
 
-    for (uint32_t i0 = 0; i0 < proflen; i0 += PFX_TILE) {
-        const uint32_t ntile = min((uint32_t)PFX_TILE, proflen - i0);
-        uint32_t jlo, jhi;  // plus-strand window starts covered by this tile (inclusive)
-        if (!reverse) { jlo = i0; jhi = i0 + ntile - 1; }
-        else { jhi = L - k - i0; jlo = L - k - (i0 + ntile - 1); }
-        const uint32_t w_lo = jlo >> 4, w_n = ((jhi + k - 1) >> 4) - w_lo + 3;
-        const uint32_t m_lo = jlo >> 5, m_n = ((jhi + k - 1) >> 5) - m_lo + 2;
-        __syncthreads();  // previous tile's readers of stage_* / warp_tot are done
-        for (uint32_t w = threadIdx.x; w < w_n; w += PFX_THREADS) stage_pk[w] = tr.packed[pk_base + w_lo + w];
-        for (uint32_t w = threadIdx.x; w < m_n; w += PFX_THREADS) stage_mk[w] = tr.nmask[mk_base + m_lo + w];
-        __syncthreads();
-
-        const uint32_t ib = i0 + threadIdx.x * PFX_ITEMS;  // first profile entry of this thread
-        uint64_t x[PFX_ITEMS];
-        uint64_t run = 0;
-        if (ib < proflen) {
-            // lowest plus-strand window start among this thread's entries
-            const uint32_t nvalid = min((uint32_t)PFX_ITEMS, proflen - ib);
-            const uint32_t jb = reverse ? (L - k - (ib + nvalid - 1)) : ib;
-            const uint32_t wi = (jb >> 4) - w_lo, mi = (jb >> 5) - m_lo;
-            const uint32_t p0 = stage_pk[wi], p1 = stage_pk[wi + 1], p2 = stage_pk[wi + 2];
-            const uint64_t lo64 = (uint64_t)p0 | ((uint64_t)p1 << 32), hi64 = (uint64_t)p1 | ((uint64_t)p2 << 32);
-            const uint64_t m64 = (uint64_t)stage_mk[mi] | ((uint64_t)stage_mk[mi + 1] << 32);
-            const uint32_t ob = jb & 15, omb = jb & 31;
+        uint32_t ib = lane * PFX_ITEMS;
+        PfxWords nxt{0, 0, 0, 0, 0};
+        if (ib < proflen) nxt = pfx_load(tr, o, pfx_jb(reverse, L, k, proflen, ib));
+        for (uint32_t i0 = 0; i0 < proflen; i0 += PFX_SUB) {
+            ib = i0 + lane * PFX_ITEMS;
+            const PfxWords w5 = nxt;
+            const uint32_t ibn = ib + PFX_SUB;
+            if (ibn < proflen) nxt = pfx_load(tr, o, pfx_jb(reverse, L, k, proflen, ibn));  // prefetch the next sub-tile
+            uint64_t x[PFX_ITEMS];
+            uint64_t run = 0;
+            if (ib < proflen) {
+                const uint32_t nvalid = min((uint32_t)PFX_ITEMS, proflen - ib);
+                const uint32_t jb = pfx_jb(reverse, L, k, proflen, ib);
+                const uint64_t lo64 = (uint64_t)w5.p0 | ((uint64_t)w5.p1 << 32), hi64 = (uint64_t)w5.p1 | ((uint64_t)w5.p2 << 32);
+                const uint64_t m64 = (uint64_t)w5.m0 | ((uint64_t)w5.m1 << 32);
+                const uint32_t ob = jb & 15, omb = jb & 31;
 #pragma unroll
-            for (int r = 0; r < PFX_ITEMS; r++) {
-                uint64_t w = 0;
-                if ((uint32_t)r < nvalid) {
-                    const uint32_t d = reverse ? (nvalid - 1 - r) : (uint32_t)r;  // window start = jb + d
-                    const uint32_t ofs = ob + d;
-                    const uint32_t code = (ofs < 16 ? (uint32_t)(lo64 >> (2 * ofs)) : (uint32_t)(hi64 >> (2 * (ofs - 16)))) & kmask;
-                    const uint32_t mbits = (uint32_t)(m64 >> (omb + d)) & mmask;
-                    if (mbits == 0) {
-                        w = lut[code];
-                    } else {
-                        // non-ACGT letters in the window: evaluate KmerAffinity on the raw bytes
-                        uint8_t kmer[16];
-                        const uint8_t *bp = tr.bases + o + jb + d;
-                        if (!reverse) {
-                            for (int q = 0; q < k; q++) kmer[q] = bp[q];
+                for (int r = 0; r < PFX_ITEMS; r++) {
+                    uint64_t w = 0;
+                    if ((uint32_t)r < nvalid) {
+                        const uint32_t d = reverse ? (nvalid - 1 - r) : (uint32_t)r;  // window start = jb + d
+                        const uint32_t ofs = ob + d;
+                        const uint32_t code = (ofs < 16 ? (uint32_t)(lo64 >> (2 * ofs)) : (uint32_t)(hi64 >> (2 * (ofs - 16)))) & kmask;
+                        const uint32_t mbits = (uint32_t)(m64 >> (omb + d)) & mmask;
+                        if (mbits == 0) {
+                            w = lut[code];
                         } else {
-                            for (int q = 0; q < k; q++) {  // utils.go:37-59
-                                uint8_t c = bp[k - 1 - q], oc;
-                                switch (c) { case 'A': oc = 'T'; break; case 'T': oc = 'A'; break; case 'G': oc = 'C'; break; case 'C': oc = 'G'; break; default: oc = 'N'; }
-                                kmer[q] = oc;
+                            // non-ACGT letters in the window: evaluate KmerAffinity on the raw bytes
+                            uint8_t kmer[16];
+                            const uint8_t *bp = tr.bases + o + jb + d;
+                            if (!reverse) {
+                                for (int q = 0; q < k; q++) kmer[q] = bp[q];
+                            } else {
+                                for (int q = 0; q < k; q++) {  // utils.go:37-59
+                                    uint8_t c = bp[k - 1 - q], oc;
+                                    switch (c) { case 'A': oc = 'T'; break; case 'T': oc = 'A'; break; case 'G': oc = 'C'; break; case 'C': oc = 'G'; break; default: oc = 'N'; }
+                                    kmer[q] = oc;
+                                }
                             }
+                            w = quantize(kmer_affinity_bytes(kmer, k, T), scale);
                         }
-                        w = quantize(kmer_affinity_bytes(kmer, k, T), scale);
                     }
+                    run += w;
+                    x[r] = run;
                 }
-                run += w;
-                x[r] = run;
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < PFX_ITEMS; r++) x[r] = 0;
-        }
-        // block-wide exclusive scan of the per-thread totals
-        uint64_t incl = run;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint64_t v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= (uint32_t)d) incl += v;
-        }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        uint64_t base = carry, tile_total = 0;
-#pragma unroll
-        for (int w = 0; w < PFX_THREADS / 32; w++) {
-            uint64_t v = warp_tot[w];
-            if ((uint32_t)w < warp) base += v;
-            tile_total += v;
-        }
-        carry += tile_total;
-        const uint64_t excl = base + incl - run;
-        if (ib < proflen) {
-            uint64_t *dst = P + 1 + ib;
-            if (ib + PFX_ITEMS <= proflen) {
-                ulonglong2 *d2 = reinterpret_cast<ulonglong2 *>(dst);
-#pragma unroll
-                for (int r = 0; r < PFX_ITEMS; r += 2) d2[r >> 1] = make_ulonglong2(excl + x[r], excl + x[r + 1]);
             } else {
-                for (uint32_t r = 0; r < proflen - ib; r++) dst[r] = excl + x[r];
+#pragma unroll
+                for (int r = 0; r < PFX_ITEMS; r++) x[r] = 0;
             }
+            // warp-wide inclusive scan of the lane totals
+            uint64_t incl = run;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint64_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += v;
+            }
+            const uint64_t excl = carry + incl - run;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+            // transpose through this warp's shared-memory tile so that every store instruction covers 512 contiguous bytes
+            uint64_t *tile = tile_s + (threadIdx.x >> 5) * PFX_TILE_U64;
+            {
+                ulonglong2 *row = reinterpret_cast<ulonglong2 *>(tile + lane * PFX_ROW_U64);
+#pragma unroll
+                for (int r = 0; r < PFX_ITEMS; r += 2) row[r >> 1] = make_ulonglong2(excl + x[r], excl + x[r + 1]);
+            }
+            __syncwarp();
+            const uint32_t nsub = min((uint32_t)PFX_SUB, proflen - i0);
+            uint64_t *dst = P + 1 + i0;
+#pragma unroll
+            for (int q = 0; q < PFX_ITEMS / 2; q++) {
+                const uint32_t e = 2 * (q * 32 + lane);  // first of the two entries this lane stores
+                const uint64_t *src = tile + (e >> 3) * PFX_ROW_U64 + (e & 7);
+                if (e + 1 < nsub) *reinterpret_cast<ulonglong2 *>(dst + e) = *reinterpret_cast<const ulonglong2 *>(src);
+                else if (e < nsub) dst[e] = src[0];
+            }
+            __syncwarp();
         }
     }
-    }  // transcripts of this CTA
 }
 
-size_t prefix_smem_bytes(int k, int *lut_in_smem) {
-    size_t base = (PFX_THREADS / 32) * 8 + (size_t)(PFX_STAGE_WORDS + PFX_STAGE_MASK) * 4;
-    *lut_in_smem = (k <= 6);
-    return base + (*lut_in_smem ? ((size_t)4 << (2 * k)) : 0);
-}
-
-void launch_prefix(cudaStream_t st, const DevTranscripts &tr, uint32_t t_begin, uint32_t t_end, int k, double T, const uint32_t *wq_f, const uint32_t *wq_r,
-                   const unsigned long long *kmax_bits, uint64_t *Pf, uint64_t *Pr, int strands) {
+void launch_prefix(cudaStream_t st, const DevTranscripts &tr, uint32_t t_begin, uint32_t t_end, int k, double T,
+                   const uint32_t *wq_f, const uint32_t *wq_r, const unsigned long long *kmax_bits, uint64_t *Pf, uint64_t *Pr,
+                   int strands, unsigned int *work) {
     if (t_end <= t_begin) return;
-    int lut_in_smem;
-    size_t smem = prefix_smem_bytes(k, &lut_in_smem);
-    dim3 grid(std::min<uint32_t>(t_end - t_begin, 148u * 8u), strands);  // persistent CTAs: the 16 KB LUT is loaded once per CTA
-    k_prefix<<<grid, PFX_THREADS, smem, st>>>(tr, t_begin, t_end, k, T, wq_f, wq_r, kmax_bits, Pf, Pr, lut_in_smem);
+    int lut_in_smem = (k <= 6);
+    size_t smem = (size_t)(PFX_THREADS / 32) * PFX_TILE_U64 * 8 + (lut_in_smem ? ((size_t)4 << (2 * k)) : 16);
+    uint32_t warps_needed = t_end - t_begin;
+    uint32_t blocks = std::min<uint32_t>((warps_needed + 7) / 8, 148u * 6u);
+    cudaMemsetAsync(work, 0, 2 * sizeof(unsigned int), st);
+    dim3 grid(blocks, strands);
+    k_prefix<<<grid, PFX_THREADS, smem, st>>>(tr, t_begin, t_end, k, T, wq_f, wq_r, kmax_bits, Pf, Pr, lut_in_smem, work);
 }
 
 }  // namespace rl
