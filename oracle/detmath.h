@@ -141,9 +141,9 @@ static inline double det_logfact_tail(double k) {
                                  0.01189670994589177, 0.01041126526197209, 0.009255462182712733,
                                  0.008330563433362871};
     if (k <= 9.0) return t[(int)k];
-    double kp1 = k + 1.0;
-    double kp1sq = kp1 * kp1;
-    return (1.0 / 12.0 - (1.0 / 360.0 - 1.0 / 1260.0 / kp1sq) / kp1sq) / kp1;
+    double inv = 1.0 / (k + 1.0);
+    double inv2 = inv * inv;
+    return inv * (1.0 / 12.0 - inv2 * (1.0 / 360.0 - inv2 * (1.0 / 1260.0)));
 }
 
 /* log k!, k >= 0 integer-valued. */

@@ -118,43 +118,46 @@ static int32_t px_poisson(px_stream *st, double mean) {
     }
 }
 
-/* Binomial(n, pp): inversion below n*min(p,q) = 10, BTRS (Hoermann 1993) above; exact in distribution,
- * same law as random.go:168-233. */
+/* Binomial(n, pp): BINV inversion below n*min(p,q) = 10, BTRS (Hoermann 1993) above; exact in distribution, same law as
+ * random.go:168-233.  Every attempt (inversion or BTRS) consumes ONE whole Philox block of the species' PCR stream:
+ * inversion uses its low half, BTRS the low half for u and the high half for v.  1/x in the inversion recurrence is the
+ * correctly rounded reciprocal (a table on the GPU), 1/b is shared by the two BTRS constants that need it. */
 static uint64_t px_binomial(px_stream *st, uint64_t n, double pp) {
     if (n == 0 || !(pp > 0.0)) return 0;
     if (pp >= 1.0) return n;
     double p = pp <= 0.5 ? pp : 1.0 - pp;
     double q = 1.0 - p;
     double nd = (double)n;
+    double r = p / q;
     uint64_t res;
     if (nd * p < 10.0) {
-        double s = p / q;
         double qn = det_exp(nd * det_log(q));
         double bound = nd * p + 10.0 * sqrt(nd * p * q + 1.0);
         if (bound > nd) bound = nd;
         for (;;) {
-            double x = 0.0, px = qn, u = px_u01(px_next64(st));
+            double x = 0.0, px = qn, u = px_u01(px_blk_lo(px_next_block(st)));
             int restart = 0;
             while (u > px) {
                 x = x + 1.0;
                 if (x > bound) { restart = 1; break; }
                 u = u - px;
-                px = ((nd - x + 1.0) * s) * px / x;
+                px = (((nd - x + 1.0) * r) * px) * (1.0 / x);
             }
             if (!restart) { res = (uint64_t)x; break; }
         }
     } else {
         double spq = sqrt(nd * p * q);
-        double r = p / q;
         double b = 1.15 + 2.53 * spq;
+        double invb = 1.0 / b;
         double a = -0.0873 + 0.0248 * b + 0.01 * p;
         double c = nd * p + 0.5;
-        double vr = 0.92 - 4.2 / b;
-        double alpha = (2.83 + 5.1 / b) * spq;
+        double vr = 0.92 - 4.2 * invb;
+        double alpha = (2.83 + 5.1 * invb) * spq;
         double m = floor((nd + 1.0) * p);
         for (;;) {
-            double u = px_u01(px_next64(st)) - 0.5;
-            double v = px_u01_open(px_next64(st));
+            px_block blk = px_next_block(st);
+            double u = px_u01(px_blk_lo(blk)) - 0.5;
+            double v = px_u01_open(px_blk_hi(blk));
             double us = 0.5 - fabs(u);
             double k = floor((2.0 * a / us + b) * u + c);
             if (us >= 0.07 && v <= vr) { res = (uint64_t)k; break; }

@@ -50,13 +50,14 @@ typedef struct {
     uint32_t c1, c2, c3;
     /* sequential cursor (in 64-bit halves) and one-block cache */
     uint64_t cur;
+    uint32_t curb; /* sequential cursor in whole blocks (PCR stream) */
     uint32_t cached_block;
     int have;
     px_block blk;
 } px_stream;
 
 static inline void px_stream_init(px_stream *s, px_key key, uint32_t c1, uint32_t c2, uint32_t c3) {
-    s->key = key; s->c1 = c1; s->c2 = c2; s->c3 = c3; s->cur = 0; s->have = 0; s->cached_block = 0;
+    s->key = key; s->c1 = c1; s->c2 = c2; s->c3 = c3; s->cur = 0; s->curb = 0; s->have = 0; s->cached_block = 0;
 }
 
 static inline px_block px_stream_block(const px_stream *s, uint32_t b) {
@@ -71,6 +72,9 @@ static inline uint64_t px_draw64(px_stream *s, uint64_t d) {
                    : ((uint64_t)s->blk.v[0] | ((uint64_t)s->blk.v[1] << 32));
 }
 static inline uint64_t px_next64(px_stream *s) { return px_draw64(s, s->cur++); }
+static inline px_block px_next_block(px_stream *s) { return px_stream_block(s, s->curb++); }
+static inline uint64_t px_blk_lo(px_block b) { return (uint64_t)b.v[0] | ((uint64_t)b.v[1] << 32); }
+static inline uint64_t px_blk_hi(px_block b) { return (uint64_t)b.v[2] | ((uint64_t)b.v[3] << 32); }
 
 /* U in [0,1): top 53 bits. */
 static inline double px_u01(uint64_t x) { return (double)(x >> 11) * 1.1102230246251565404e-16; }

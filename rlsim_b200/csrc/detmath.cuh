@@ -134,9 +134,9 @@ __device__ __forceinline__ double det_logfact_tail(double k) {
         default: return 0.008330563433362871;
         }
     }
-    double kp1 = k + 1.0;
-    double kp1sq = kp1 * kp1;
-    return (1.0 / 12.0 - (1.0 / 360.0 - 1.0 / 1260.0 / kp1sq) / kp1sq) / kp1;
+    double inv = 1.0 / (k + 1.0);
+    double inv2 = inv * inv;
+    return inv * (1.0 / 12.0 - inv2 * (1.0 / 360.0 - inv2 * (1.0 / 1260.0)));
 }
 
 __device__ __forceinline__ double det_logfact(double k) {

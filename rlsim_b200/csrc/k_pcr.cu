@@ -46,17 +46,26 @@ __device__ __forceinline__ double gc_eff(const DevModel &m, uint32_t gc_count, u
     return m.gc_min + (m.gc_max - m.gc_min) * det_go_pow(1 - det_go_pow(gc, m.gc_shape), m.gc_shape);
 }
 
-// AmplifyFragment, thermocycler.go:133-147: `cycles` times c <- c + Binomial(c, pp), from the species' own cursor.
+// 1/x for the inversion recurrence (x <= 44 while n*min(p,q) < 10): correctly rounded reciprocals, spec 4.4
+__constant__ double RCP_TABLE[64] = {
+    0.0,       1.0 / 1,  1.0 / 2,  1.0 / 3,  1.0 / 4,  1.0 / 5,  1.0 / 6,  1.0 / 7,  1.0 / 8,  1.0 / 9,  1.0 / 10, 1.0 / 11, 1.0 / 12,
+    1.0 / 13,  1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25,
+    1.0 / 26,  1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32, 1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37, 1.0 / 38,
+    1.0 / 39,  1.0 / 40, 1.0 / 41, 1.0 / 42, 1.0 / 43, 1.0 / 44, 1.0 / 45, 1.0 / 46, 1.0 / 47, 1.0 / 48, 1.0 / 49, 1.0 / 50, 1.0 / 51,
+    1.0 / 52,  1.0 / 53, 1.0 / 54, 1.0 / 55, 1.0 / 56, 1.0 / 57, 1.0 / 58, 1.0 / 59, 1.0 / 60, 1.0 / 61, 1.0 / 62, 1.0 / 63};
+
+// AmplifyFragment, thermocycler.go:133-147: `cycles` times c <- c + Binomial(c, pp), every attempt from one whole
+// Philox block of the species' own stream (spec 4.4: BINV inversion below c*min(p,q) = 10, BTRS above).
 //
-// Same draws, in the same per-species order, as px_binomial() called once per cycle (variates.cuh; the oracle restates
-// that form) - but scheduled for a warp: the BTRS acceptance test that needs four logarithms ("slow path", ~14% of the
-// attempts) is not evaluated inside the cycle loop, where it would run for a handful of lanes in almost every
-// iteration.  A lane that needs it PARKS; lanes keep running fast-path work (inversion, squeeze accepts) until each
-// one is parked or done, then the slow test runs once for all parked lanes together.  Per-species constants
-// (p, q, p/q, log q) are hoisted out of the cycle loop.
-// Must be called by ALL 32 lanes of a warp (lanes without a species pass live = false): the fast and slow phases
-// are separated by __syncwarp() so the slow test really runs once per round for all parked lanes together.
-__device__ __forceinline__ uint64_t amplify(PxCursor &cur, uint64_t c, double pp, int cycles, bool live, bool &overflow) {
+// Scheduled per WARP, in rounds.  In a round every runnable lane makes exactly one attempt of its current cycle -
+// Philox block, (setup), inversion walk or BTRS squeeze test - so that code runs with (nearly) all lanes.  An attempt
+// that needs the exact BTRS acceptance test (four logarithms, ~14% of the attempts) only marks its lane PENDING; the
+// test runs when at least PCR_SLOW_BATCH lanes are pending (or nothing else can run), for all of them together.
+// Per-species constants (p, q, p/q, log q) are hoisted out of the cycle loop.  Must be called by all 32 lanes
+// (lanes without a species pass live = false).  The draws of a species depend only on its own block counter, so the
+// schedule does not change the result: it is the sequence the oracle produces cycle by cycle.
+constexpr int PCR_SLOW_BATCH = 10;
+__device__ __forceinline__ uint64_t amplify(const PxStream &stream, uint64_t c, double pp, int cycles, bool live, bool &overflow) {
     if (!(pp > 0.0) || c == 0) live = false;  // Binomial(c, 0) = 0, Binomial(0, .) = 0: nothing to draw
     if (live && pp >= 1.0) {                  // Binomial(c, 1) = c
         for (int cyc = 0; cyc < cycles; cyc++) {
@@ -70,81 +79,80 @@ __device__ __forceinline__ uint64_t amplify(PxCursor &cur, uint64_t c, double pp
     const double p = flip ? 1.0 - pp : pp;
     const double q = 1.0 - p;
     const double r = p / q;
-    const double lq = det_log(q);
+    const double lq = live ? det_log(q) : 0.0;
     int cyc = live ? 0 : cycles;
-    bool have_setup = false;
-    double nd = 0, b = 0, a = 0, cc = 0, vr = 0, alpha = 0, mm = 0;  // BTRS constants of the current cycle
-    double us = 0, v = 0, k = 0;                                    // the parked attempt
-    while (__any_sync(0xffffffffu, cyc < cycles)) {
-        bool parked = false;
-        // ---- fast phase: run until this lane needs the slow test or has finished all cycles
-        while (cyc < cycles) {
-            uint64_t res;
+    uint32_t blk = 0;
+    bool pending = false, have_setup = false, inv_mode = false;
+    double nd = 0, b = 0, a = 0, cc = 0, vr = 0, alpha = 0, mm = 0, qn = 0, bound = 0;
+    double us = 0, v = 0, k = 0;
+    for (;;) {
+        const bool runnable = cyc < cycles && !pending;
+        if (!__any_sync(0xffffffffu, cyc < cycles)) break;
+        if (runnable) {
             if (!have_setup) {
                 nd = (double)c;
-                if (nd * p < 10.0) {  // BINV inversion
-                    double qn = det_exp(nd * lq);
-                    double bound = nd * p + 10.0 * sqrt(nd * p * q + 1.0);
+                inv_mode = nd * p < 10.0;
+                if (inv_mode) {
+                    qn = det_exp(nd * lq);
+                    bound = nd * p + 10.0 * sqrt(nd * p * q + 1.0);
                     if (bound > nd) bound = nd;
-                    for (;;) {
-                        double x = 0.0, px = qn, u = cur.u01();
-                        bool restart = false;
-                        while (u > px) {
-                            x = x + 1.0;
-                            if (x > bound) { restart = true; break; }
-                            u = u - px;
-                            px = ((nd - x + 1.0) * r) * px / x;
-                        }
-                        if (!restart) { res = (uint64_t)x; break; }
-                    }
-                    uint64_t nc = c + (flip ? c - res : res);
-                    if (nc < c) { overflow = true; cyc = cycles; break; }
-                    c = nc;
-                    cyc++;
-                    continue;
+                } else {
+                    double spq = sqrt(nd * p * q);
+                    b = 1.15 + 2.53 * spq;
+                    double invb = 1.0 / b;
+                    a = -0.0873 + 0.0248 * b + 0.01 * p;
+                    cc = nd * p + 0.5;
+                    vr = 0.92 - 4.2 * invb;
+                    alpha = (2.83 + 5.1 * invb) * spq;
+                    mm = floor((nd + 1.0) * p);
                 }
-                double spq = sqrt(nd * p * q);
-                b = 1.15 + 2.53 * spq;
-                a = -0.0873 + 0.0248 * b + 0.01 * p;
-                cc = nd * p + 0.5;
-                vr = 0.92 - 4.2 / b;
-                alpha = (2.83 + 5.1 / b) * spq;
-                mm = floor((nd + 1.0) * p);
                 have_setup = true;
             }
-            double u = cur.u01() - 0.5;
-            v = cur.u01_open();
-            us = 0.5 - fabs(u);
-            k = floor((2.0 * a / us + b) * u + cc);
-            if (us >= 0.07 && v <= vr) {  // squeeze accept
-                res = (uint64_t)k;
-                uint64_t nc = c + (flip ? c - res : res);
-                if (nc < c) { overflow = true; cyc = cycles; break; }
-                c = nc;
-                cyc++;
-                have_setup = false;
-                continue;
+            const PxBlock B = stream.block(blk++);
+            bool done = false;
+            uint64_t res = 0;
+            if (inv_mode) {  // BINV: walk the pmf from 0
+                double x = 0.0, px = qn, u = px_u01(px_lo64(B));
+                bool restart = false;
+                while (u > px) {
+                    x = x + 1.0;
+                    if (x > bound) { restart = true; break; }
+                    u = u - px;
+                    px = (((nd - x + 1.0) * r) * px) * RCP_TABLE[(int)x];
+                }
+                if (!restart) { res = (uint64_t)x; done = true; }
+            } else {         // BTRS: squeeze
+                double u = px_u01(px_lo64(B)) - 0.5;
+                v = px_u01_open(px_hi64(B));
+                us = 0.5 - fabs(u);
+                k = floor((2.0 * a / us + b) * u + cc);
+                if (us >= 0.07 && v <= vr) { res = (uint64_t)k; done = true; }
+                else if (!(k < 0.0 || k > nd)) pending = true;
             }
-            if (k < 0.0 || k > nd) continue;
-            parked = true;
-            break;
-        }
-        __syncwarp();
-        // ---- slow phase: exact acceptance test of the parked attempts, all parked lanes together
-        if (parked) {
-            double lv = det_log(v * alpha / (a / (us * us) + b));
-            double ub = (mm + 0.5) * det_log((mm + 1.0) / (r * (nd - mm + 1.0))) +
-                        (nd + 1.0) * det_log((nd - mm + 1.0) / (nd - k + 1.0)) +
-                        (k + 0.5) * det_log(r * (nd - k + 1.0) / (k + 1.0)) + det_logfact_tail(mm) +
-                        det_logfact_tail(nd - mm) - det_logfact_tail(k) - det_logfact_tail(nd - k);
-            if (lv <= ub) {
-                uint64_t res = (uint64_t)k;
+            if (done) {
                 uint64_t nc = c + (flip ? c - res : res);
                 if (nc < c) { overflow = true; cyc = cycles; }
                 else { c = nc; cyc++; have_setup = false; }
             }
         }
-        __syncwarp();
+        const unsigned pend = __ballot_sync(0xffffffffu, pending);
+        const unsigned run = __ballot_sync(0xffffffffu, cyc < cycles && !pending);
+        if (pend != 0u && (__popc(pend) >= PCR_SLOW_BATCH || run == 0u)) {
+            if (pending) {  // exact acceptance test
+                double lv = det_log(v * alpha / (a / (us * us) + b));
+                double ub = (mm + 0.5) * det_log((mm + 1.0) / (r * (nd - mm + 1.0))) +
+                            (nd + 1.0) * det_log((nd - mm + 1.0) / (nd - k + 1.0)) +
+                            (k + 0.5) * det_log(r * (nd - k + 1.0) / (k + 1.0)) + det_logfact_tail(mm) +
+                            det_logfact_tail(nd - mm) - det_logfact_tail(k) - det_logfact_tail(nd - k);
+                if (lv <= ub) {
+                    uint64_t res = (uint64_t)k;
+                    uint64_t nc = c + (flip ? c - res : res);
+                    if (nc < c) { overflow = true; cyc = cycles; }
+                    else { c = nc; cyc++; have_setup = false; }
+                }
+                pending = false;
+            }
+        }
     }
     return c;
 }
@@ -167,9 +175,9 @@ k_pcr(const __grid_constant__ DevModel m, DevTranscripts tr, DevSpecies sp, int 
         if (e == 0.0) e = m.len_eff[len - m.low] * gc_eff(m, gcc, len);
     }
     const uint32_t end = start + len;
-    PxCursor cur(PxStream{m.key_pcr, m.first_index + t, start, end});
+    const PxStream stream{m.key_pcr, m.first_index + t, start, end};
     bool ovf = false;
-    uint64_t c = amplify(cur, c0, e, m.cycles, live, ovf);
+    uint64_t c = amplify(stream, c0, e, m.cycles, live, ovf);
     if (!live) return;
     if (ovf) atomicExch(error, RLSIM_E_PCR_OVERFLOW);
     sp.count[i] = c;
@@ -186,9 +194,9 @@ __global__ void k_amplify_probe(PxKey key, const uint32_t *tse, const uint64_t *
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;
     uint32_t j = live ? i : 0;
-    PxCursor cur(PxStream{key, tse[3 * j], tse[3 * j + 1], tse[3 * j + 2]});
+    const PxStream stream{key, tse[3 * j], tse[3 * j + 1], tse[3 * j + 2]};
     bool ovf = false;
-    uint64_t r = amplify(cur, n0[j], p[j], cycles, live, ovf);
+    uint64_t r = amplify(stream, n0[j], p[j], cycles, live, ovf);
     if (live) out[i] = r;
 }
 void launch_amplify_probe(cudaStream_t st, PxKey key, const uint32_t *tse, const uint64_t *n0, const double *p, int cycles,

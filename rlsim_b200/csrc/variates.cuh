@@ -1,7 +1,7 @@
 // Random variates of the "--rng=philox" spec, device side.
 // Same laws as /root/reference/src/random.go:120-367; algorithms chosen for the GPU:
 //   Poisson  : multiplication method below 12 (random.go:127-139), PTRS (Hoermann 1993) above
-//   Binomial : BINV inversion below n*min(p,q)=10, BTRS (Hoermann 1993) above  (random.go:168-233: NR rejection)
+//   Binomial : BINV inversion below n*min(p,q)=10, BTRS (Hoermann 1993) above  (random.go:168-233: NR rejection); k_pcr.cu
 //   normal   : inverse CDF (AS241) of one open uniform          (Go: ziggurat)
 //   gamma    : Marsaglia-Tsang (random.go:282-367: Knuth / Kundu-Gupta)
 // Compiled with -fmad=false; the oracle restates them in plain C and must agree bit for bit.
@@ -113,54 +113,6 @@ static __device__ __noinline__ int32_t px_poisson(PxCursor &cur, double mean) {
     }
 }
 
-__device__ __forceinline__ uint64_t px_binomial(PxCursor &cur, uint64_t n, double pp) {
-    if (n == 0 || !(pp > 0.0)) return 0;
-    if (pp >= 1.0) return n;
-    double p = pp <= 0.5 ? pp : 1.0 - pp;
-    double q = 1.0 - p;
-    double nd = (double)n;
-    uint64_t res;
-    if (nd * p < 10.0) {
-        double s = p / q;
-        double qn = det_exp(nd * det_log(q));
-        double bound = nd * p + 10.0 * sqrt(nd * p * q + 1.0);
-        if (bound > nd) bound = nd;
-        for (;;) {
-            double x = 0.0, px = qn, u = cur.u01();
-            bool restart = false;
-            while (u > px) {
-                x = x + 1.0;
-                if (x > bound) { restart = true; break; }
-                u = u - px;
-                px = ((nd - x + 1.0) * s) * px / x;
-            }
-            if (!restart) { res = (uint64_t)x; break; }
-        }
-    } else {
-        double spq = sqrt(nd * p * q);
-        double r = p / q;
-        double b = 1.15 + 2.53 * spq;
-        double a = -0.0873 + 0.0248 * b + 0.01 * p;
-        double c = nd * p + 0.5;
-        double vr = 0.92 - 4.2 / b;
-        double alpha = (2.83 + 5.1 / b) * spq;
-        double m = floor((nd + 1.0) * p);
-        for (;;) {
-            double u = cur.u01() - 0.5;
-            double v = cur.u01_open();
-            double us = 0.5 - fabs(u);
-            double k = floor((2.0 * a / us + b) * u + c);
-            if (us >= 0.07 && v <= vr) { res = (uint64_t)k; break; }
-            if (k < 0.0 || k > nd) continue;
-            v = det_log(v * alpha / (a / (us * us) + b));
-            double ub = (m + 0.5) * det_log((m + 1.0) / (r * (nd - m + 1.0))) +
-                        (nd + 1.0) * det_log((nd - m + 1.0) / (nd - k + 1.0)) +
-                        (k + 0.5) * det_log(r * (nd - k + 1.0) / (k + 1.0)) + det_logfact_tail(m) +
-                        det_logfact_tail(nd - m) - det_logfact_tail(k) - det_logfact_tail(nd - k);
-            if (v <= ub) { res = (uint64_t)k; break; }
-        }
-    }
-    return pp <= 0.5 ? res : n - res;
-}
+// Binomial draws live in k_pcr.cu (amplify): they are scheduled per warp, see there.
 
 }  // namespace rl
