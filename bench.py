@@ -195,10 +195,13 @@ def main():
                end=torch.empty(out_cap, dtype=torch.int32).pin_memory(), minus=torch.empty(out_cap, dtype=torch.uint8).pin_memory(),
                id=torch.empty(out_cap, dtype=torch.int64).pin_memory())
 
+    exchange = shard.RecordExchange(dev) if world > 1 else None
+
     def select(step):
-        local = h.class_totals()
-        total, base = shard.allgather_totals(local, device=dev if world > 1 else None)
-        h.sample(total, base)
+        if world > 1:  # classes partitioned over ranks + one all-to-all of the drawn copy ranks
+            exchange.run(h, rank, world, n_frags_global // world + 4096)
+        else:
+            h.sample()
 
     e2e_phase = {"configure+target": 0.0, "h2d (add_transcripts)": 0.0, "build_library": 0.0, "select": 0.0, "d2h (records)": 0.0}
 
@@ -213,9 +216,7 @@ def main():
         t.append(time.perf_counter())
         h.build_library()
         t.append(time.perf_counter())
-        local = h.class_totals()
-        total, base = shard.allgather_totals(local, device=dev if world > 1 else None)
-        h.sample(total, base)
+        select(step)
         t.append(time.perf_counter())
         n = int(h.stats().n_sampled)
         if n > out_cap:
@@ -280,10 +281,12 @@ def main():
     K = max(opts.steps, 1)
     stage_ms = {k: (ms1[k] - ms0[k]) / K for k in ms1}
     launches = sum(nl1[k] - nl0[k] for k in nl1) // K
-    nt_total = int(bases.numel()) + n_tr * int(st.polya_max)
+    expressed = levels_np > 0  # pool.go:104: unexpressed transcripts get no prefix sums
+    lens = (off_np[1:] - off_np[:-1]).astype(np.int64)
+    nt_total = int(lens[expressed].sum()) + int(expressed.sum()) * int(st.polya_max)
     # algorithmic bytes per step of each own kernel group
     alg = {
-        "prefix": 16.25 * nt_total,                       # 0.25 B/nt read + 2 x 8 B/nt prefix sums written
+        "prefix": 16.25 * nt_total,                       # 0.25 B/nt read + 2 x 8 B/nt prefix sums written (expressed transcripts)
         "fragment": 120.0 * float(st.n_molecules),        # ~120 B/molecule (draws are register-resident; searches + keys)
         "pcr": 32.0 * float(st.n_species),                # 32 B/species
         "expand": 150.0 * float(st.n_sampled),            # ~150 B/sampled fragment

@@ -109,6 +109,10 @@ int rlsim_set_raw_target(rlsim_handle *h, const uint32_t *lengths, const double 
 /* ---- Targeter (target.go:102-132 / raw_target.go:104-138) ----
  * Either draw the req_frags target lengths on the device ... */
 int rlsim_sample_target(rlsim_handle *h, int64_t req_frags);
+/* Multi-GPU: draw only the target lengths with draw index in [first, first+count) (the stream is addressed by the draw
+ * index); read the partial histogram with rlsim_get_hist(RLSIM_H_TARGET), sum it over the ranks and impose the sum with
+ * rlsim_set_target_hist. */
+int rlsim_sample_target_range(rlsim_handle *h, uint64_t first, uint64_t count);
 /* ... or impose the histogram the host's own Targeter sampled (NextLenCount pairs). */
 int rlsim_set_target_hist(rlsim_handle *h, const uint32_t *lengths, const uint64_t *counts, uint32_t n);
 
@@ -137,6 +141,18 @@ int rlsim_pcr(rlsim_handle *h);
  * totals[l] = sum_r T_r[l], base[l] = sum_{r' < rank} T_r'[l]. */
 int rlsim_class_totals(rlsim_handle *h, uint64_t *totals, uint32_t n_len);
 int rlsim_sample(rlsim_handle *h, const uint64_t *global_totals, const uint64_t *rank_base, uint32_t n_len);
+
+/* Multi-GPU form without redundant work: the length classes are partitioned over the ranks
+ * (class l is drawn by rank l % nparts).  all_totals = T_r[l] of every rank, row-major [nparts][n_len] (the all-gathered
+ * class_totals).  rlsim_select_classes draws this rank's classes and writes the copy ranks to take (or to leave, for
+ * classes drawn more than half) as 16-byte records {u32 len, u32 0, u64 rank_in_class} into `records_dev` - the caller's
+ * DEVICE buffer of `cap` records - grouped by owner rank; counts_out[r] = records for rank r, *needed_out = their sum
+ * (if it exceeds cap nothing is written: grow the buffer and call again).  The caller routes the groups with one
+ * all-to-all, hands what it receives to rlsim_apply_selected, and finishes with rlsim_finish_sample. */
+int rlsim_select_classes(rlsim_handle *h, const uint64_t *all_totals, uint32_t nparts, uint32_t part, uint32_t n_len,
+                         void *records_dev, uint64_t cap, uint64_t *counts_out, uint64_t *needed_out);
+int rlsim_apply_selected(rlsim_handle *h, const void *records_dev, uint64_t n);
+int rlsim_finish_sample(rlsim_handle *h);
 
 /* ---- results ---- */
 int rlsim_get_stats(rlsim_handle *h, rlsim_stats *out);

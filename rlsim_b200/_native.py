@@ -18,8 +18,8 @@ T_NAMES = ["layout", "prefix", "fragment", "dedup", "pcr", "select", "expand", "
 
 EXPORTS = [
     "rlsim_create", "rlsim_destroy", "rlsim_last_error", "rlsim_set_model", "rlsim_set_len_eff", "rlsim_set_raw_target",
-    "rlsim_sample_target", "rlsim_set_target_hist", "rlsim_add_transcripts", "rlsim_set_first_index", "rlsim_clear_transcripts",
-    "rlsim_build_library", "rlsim_fragment", "rlsim_pcr", "rlsim_class_totals", "rlsim_sample", "rlsim_get_stats",
+    "rlsim_sample_target", "rlsim_sample_target_range", "rlsim_set_target_hist", "rlsim_add_transcripts", "rlsim_set_first_index", "rlsim_clear_transcripts",
+    "rlsim_build_library", "rlsim_fragment", "rlsim_pcr", "rlsim_class_totals", "rlsim_sample", "rlsim_select_classes", "rlsim_apply_selected", "rlsim_finish_sample", "rlsim_get_stats",
     "rlsim_get_hist", "rlsim_get_species", "rlsim_get_sampled", "rlsim_format_fasta", "rlsim_probe_kmer_lut",
     "rlsim_probe_prefix", "rlsim_probe_gc_prefix", "rlsim_probe_math", "rlsim_probe_philox", "rlsim_probe_amplify",
     "rlsim_get_timings",
@@ -61,6 +61,7 @@ def load():
         "rlsim_set_len_eff": (i32, [vp, vp, u64, u64]),
         "rlsim_set_raw_target": (i32, [vp, vp, vp, u32]),
         "rlsim_sample_target": (i32, [vp, i64]),
+        "rlsim_sample_target_range": (i32, [vp, u64, u64]),
         "rlsim_set_target_hist": (i32, [vp, vp, vp, u32]),
         "rlsim_add_transcripts": (i32, [vp, vp, vp, vp, u32]),
         "rlsim_set_first_index": (i32, [vp, u32]),
@@ -70,6 +71,9 @@ def load():
         "rlsim_pcr": (i32, [vp]),
         "rlsim_class_totals": (i32, [vp, vp, u32]),
         "rlsim_sample": (i32, [vp, vp, vp, u32]),
+        "rlsim_select_classes": (i32, [vp, vp, u32, u32, u32, vp, u64, vp, C.POINTER(u64)]),
+        "rlsim_apply_selected": (i32, [vp, vp, u64]),
+        "rlsim_finish_sample": (i32, [vp]),
         "rlsim_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "rlsim_get_hist": (i32, [vp, i32, vp, u32]),
         "rlsim_get_species": (i32, [vp] + [vp] * 7),
@@ -146,6 +150,9 @@ class Handle:
     def sample_target(self, n):
         self._chk(self.L.rlsim_sample_target(self.h, int(n)))
 
+    def sample_target_range(self, first, count):
+        self._chk(self.L.rlsim_sample_target_range(self.h, int(first), int(count)))
+
     def set_target_hist(self, lengths, counts):
         lengths = np.ascontiguousarray(lengths, dtype=np.uint32)
         counts = np.ascontiguousarray(counts, dtype=np.uint64)
@@ -193,6 +200,23 @@ class Handle:
         gt = np.ascontiguousarray(global_totals, dtype=np.uint64)
         rb = np.ascontiguousarray(rank_base, dtype=np.uint64)
         self._chk(self.L.rlsim_sample(self.h, _p(gt), _p(rb), len(gt)))
+
+    def select_classes(self, all_totals, part, records_ptr=None, cap=0):
+        """Multi-GPU selection: draw the classes l % nparts == part.  all_totals: [nparts, n_len] u64 (all-gathered
+        class_totals); records_ptr: device pointer to cap 16-byte records.  -> (counts per owner rank, records needed)"""
+        at = np.ascontiguousarray(all_totals, dtype=np.uint64)
+        nparts, n_len = at.shape
+        counts = np.zeros(nparts, dtype=np.uint64)
+        needed = C.c_uint64()
+        self._chk(self.L.rlsim_select_classes(self.h, _p(at), nparts, int(part), n_len,
+                                              C.c_void_p(records_ptr) if records_ptr else None, int(cap), _p(counts), C.byref(needed)))
+        return counts, int(needed.value)
+
+    def apply_selected(self, records_ptr, n):
+        self._chk(self.L.rlsim_apply_selected(self.h, C.c_void_p(records_ptr) if records_ptr else None, int(n)))
+
+    def finish_sample(self):
+        self._chk(self.L.rlsim_finish_sample(self.h))
 
     # ---- results
     def stats(self):

@@ -141,6 +141,8 @@ struct rlsim_handle {
     DBuf<uint32_t> d_cand_idx, d_cand_idx_sorted, d_flags, d_plan_len;
     DBuf<unsigned long long> d_hits;
     DBuf<uint8_t> d_mode;
+    DBuf<unsigned long long> d_emit;  // [0..64) counts, [64..128) segment offsets, [128..192) cursors
+    DBuf<uint64_t> d_all_base, d_my_base;
     DBuf<int> d_short;
     uint64_t n_out = 0;
     DBuf<uint32_t> d_o_tr, d_o_start, d_o_end;
@@ -388,9 +390,8 @@ int rlsim_set_raw_target(rlsim_handle *h, const uint32_t *lengths, const double 
     return upload_tables(h);
 }
 
-int rlsim_sample_target(rlsim_handle *h, int64_t req_frags) {
+static int sample_target_range(rlsim_handle *h, uint64_t first, uint64_t count, bool whole) {
     if (!h->have_model) FAIL(h, RLSIM_E_ARG, "rlsim_set_model first");
-    if (req_frags < 0) FAIL(h, RLSIM_E_ARG, "Illegal fragment number!");
     bool raw = h->p.n_target == 0;
     if (raw && h->raw_len.empty()) FAIL(h, RLSIM_E_ARG, "raw target requested but rlsim_set_raw_target was not called");
     cudaSetDevice(h->device);
@@ -401,16 +402,25 @@ int rlsim_sample_target(rlsim_handle *h, int64_t req_frags) {
     CK(h, cudaMemsetAsync(h->d_hist_target.p, 0, (size_t)hist_n * 8, h->st));
     DevModel m = make_model(h);
     StageTimer tm(h, RLSIM_T_TARGET, 1);
-    launch_target(h->st, m, (uint64_t)req_frags, h->d_hist_target.p, hist_n);
+    launch_target(h->st, m, first, count, h->d_hist_target.p, hist_n);
     tm.stop();
     CK(h, cudaGetLastError());
     h->h_target.assign(hist_n, 0);
     CK(h, cudaMemcpyAsync(h->h_target.data(), h->d_hist_target.p, (size_t)hist_n * 8, cudaMemcpyDeviceToHost, h->st));
     CK(h, cudaStreamSynchronize(h->st));
-    h->req_frags = (uint64_t)req_frags;
-    h->have_target = true;
-    if (raw) raw_target_finish(h);
+    h->req_frags = count;
+    h->have_target = whole;  // a partial histogram must be completed with rlsim_set_target_hist
+    if (raw && whole) raw_target_finish(h);
     return 0;
+}
+
+int rlsim_sample_target(rlsim_handle *h, int64_t req_frags) {
+    if (req_frags < 0) FAIL(h, RLSIM_E_ARG, "Illegal fragment number!");
+    return sample_target_range(h, 0, (uint64_t)req_frags, true);
+}
+
+int rlsim_sample_target_range(rlsim_handle *h, uint64_t first, uint64_t count) {
+    return sample_target_range(h, first, count, false);
 }
 
 int rlsim_set_target_hist(rlsim_handle *h, const uint32_t *lengths, const uint64_t *counts, uint32_t n) {
@@ -688,18 +698,19 @@ int rlsim_class_totals(rlsim_handle *h, uint64_t *totals, uint32_t n_len) {
     return 0;
 }
 
-int rlsim_sample(rlsim_handle *h, const uint64_t *global_totals, const uint64_t *rank_base, uint32_t n_len_in) {
-    if (!h->amplified) FAIL(h, RLSIM_E_ARG, "rlsim_pcr first");
-    if (!h->have_target) FAIL(h, RLSIM_E_ARG, "no target histogram");
-    cudaSetDevice(h->device);
+}  // extern "C" (selection helpers follow)
+
+namespace {
+
+// Size selection core (sampler.go:65-106 + spec 4.6) for the length classes l with l % nparts == part.
+//   records == nullptr : single-rank form - drawn ranks are applied to this rank's species directly (rank_base form)
+//   records != nullptr : drawn / excluded ranks are written as records grouped by owner rank (multi-GPU form)
+int select_core(rlsim_handle *h, const std::vector<uint64_t> &T, const std::vector<uint64_t> &base, uint32_t nparts,
+                uint32_t part, const uint64_t *d_all_base, uint4 *records, uint64_t cap, uint64_t *counts_out,
+                uint64_t *needed_out) {
     int rc;
     uint32_t n_len = h->n_len;
-    std::vector<uint64_t> T(n_len, 0), base(n_len, 0);
-    for (uint32_t l = 0; l < n_len; l++) {
-        T[l] = global_totals ? (l < n_len_in ? global_totals[l] : 0) : h->h_totals[l];
-        base[l] = rank_base ? (l < n_len_in ? rank_base[l] : 0) : 0;
-    }
-    // ---- sampler.go:65-106 bookkeeping per requested length
+    // ---- sampler.go:65-106 bookkeeping per requested length (global view, identical on every rank)
     size_t nt = std::max<size_t>(h->h_target.size(), n_len);
     h->h_sampled.assign(nt, 0); h->h_missing.assign(nt, 0);
     h->h_after_sampling.assign(nt, 0);
@@ -720,6 +731,7 @@ int rlsim_sample(rlsim_handle *h, const uint64_t *global_totals, const uint64_t 
         bool include = take <= tot - take;
         uint64_t pick = include ? take : tot - take;
         mode[l] = include ? 2 : 3;
+        if (l % nparts != part) continue;  // another rank draws this class
         c_len.push_back((uint32_t)l); c_T.push_back(tot); c_base.push_back(base[l]); c_G.push_back(G); c_pick.push_back(pick);
         G += tot;
         // expected draws until `pick` distinct values out of tot: tot * ln(tot / (tot - pick))
@@ -730,7 +742,10 @@ int rlsim_sample(rlsim_handle *h, const uint64_t *global_totals, const uint64_t 
     DevModel m = make_model(h);
     CK(h, h->d_hits.ensure(ns)); CK(h, h->d_taken.ensure(ns)); CK(h, h->d_out_off.ensure(ns + 1)); CK(h, h->d_mode.ensure(n_len + 1));
     CK(h, cudaMemcpyAsync(h->d_mode.p, mode.data(), n_len + 1, cudaMemcpyHostToDevice, h->st));
+    CK(h, h->d_emit.ensure(3 * 64));
     uint32_t nc = (uint32_t)c_len.size();
+    if (counts_out) for (uint32_t r = 0; r < nparts; r++) counts_out[r] = 0;
+    if (needed_out) *needed_out = 0;
     for (int attempt = 0;; attempt++) {
         if (attempt > 6) FAIL(h, RLSIM_E_NOMEM, "selection kept running out of candidates");
         CK(h, cudaMemsetAsync(h->d_hits.p, 0, std::max<uint64_t>(ns, 1) * 8, h->st));
@@ -768,8 +783,16 @@ int rlsim_sample(rlsim_handle *h, const uint64_t *global_totals, const uint64_t 
         CK(h, cub::DeviceScan::InclusiveSum(nullptr, tb, h->d_flags.p, h->d_fscan.p + 1, (int)n_cand, h->st));
         if ((rc = cub_temp(h, tb))) return rc;
         CK(h, cub::DeviceScan::InclusiveSum(h->d_cub.p, tb, h->d_flags.p, h->d_fscan.p + 1, (int)n_cand, h->st));
-        launch_apply_picks(h->st, plan_d, n_cand, h->d_cand_keys.p, h->d_flags.p, h->d_fscan.p, h->d_cls_pre.p, h->d_bounds.p,
-                           h->d_order.p, h->d_hits.p, h->d_short.p);
+        unsigned long long h_counts[64] = {0};
+        if (!records) {
+            launch_apply_picks(h->st, plan_d, n_cand, h->d_cand_keys.p, h->d_flags.p, h->d_fscan.p, h->d_cls_pre.p, h->d_bounds.p,
+                               h->d_order.p, h->d_hits.p, h->d_short.p);
+        } else {  // count per owner, then scatter into the owner groups
+            CK(h, cudaMemsetAsync(h->d_emit.p, 0, 3 * 64 * 8, h->st));
+            launch_emit_selected(h->st, plan_d, n_cand, h->d_cand_keys.p, h->d_flags.p, h->d_fscan.p, d_all_base, nparts, n_len, 0,
+                                 h->d_emit.p, nullptr, nullptr, nullptr, h->d_short.p);
+            CK(h, cudaMemcpyAsync(h_counts, h->d_emit.p, nparts * 8, cudaMemcpyDeviceToHost, h->st));
+        }
         tm.stop();
         CK(h, cudaGetLastError());
         std::vector<int> shortf(nc, 0);
@@ -778,32 +801,121 @@ int rlsim_sample(rlsim_handle *h, const uint64_t *global_totals, const uint64_t 
         bool again = false;
         for (uint32_t c = 0; c < nc; c++)
             if (shortf[c]) { c_cand[c] = c_cand[c] * 2 + 1024; again = true; }
-        if (!again) break;
-    }
-    // ---- copies drawn per species -> output records
-    {
-        StageTimer tm(h, RLSIM_T_EXPAND, 4);
-        launch_taken(h->st, make_sp(h), h->d_mode.p, n_len, h->d_hits.p, h->d_taken.p);
-        CK(h, cudaMemsetAsync(h->d_out_off.p, 0, 8, h->st));
-        h->n_out = 0;
-        if (ns) {
-            size_t tb = 0;
-            CK(h, cub::DeviceScan::InclusiveSum(nullptr, tb, h->d_taken.p, h->d_out_off.p + 1, (int)ns, h->st));
-            if ((rc = cub_temp(h, tb))) return rc;
-            CK(h, cub::DeviceScan::InclusiveSum(h->d_cub.p, tb, h->d_taken.p, h->d_out_off.p + 1, (int)ns, h->st));
-            CK(h, cudaMemcpyAsync(&h->n_out, h->d_out_off.p + ns, 8, cudaMemcpyDeviceToHost, h->st));
-            CK(h, cudaStreamSynchronize(h->st));
+        if (again) continue;
+        if (records) {
+            unsigned long long seg[64] = {0}, total = 0;
+            for (uint32_t r = 0; r < nparts; r++) { seg[r] = total; total += h_counts[r]; counts_out[r] = h_counts[r]; }
+            *needed_out = total;
+            if (total > cap) return 0;  // caller grows its buffer and calls again
+            CK(h, cudaMemcpyAsync(h->d_emit.p + 64, seg, nparts * 8, cudaMemcpyHostToDevice, h->st));
+            StageTimer tm2(h, RLSIM_T_SELECT, 1);
+            launch_emit_selected(h->st, plan_d, n_cand, h->d_cand_keys.p, h->d_flags.p, h->d_fscan.p, d_all_base, nparts, n_len, 1,
+                                 h->d_emit.p, h->d_emit.p + 64, h->d_emit.p + 128, records, h->d_short.p);
+            tm2.stop();
+            CK(h, cudaGetLastError());
         }
-        CK(h, h->d_o_tr.ensure(h->n_out)); CK(h, h->d_o_start.ensure(h->n_out)); CK(h, h->d_o_end.ensure(h->n_out));
-        CK(h, h->d_o_minus.ensure(h->n_out)); CK(h, h->d_o_id.ensure(h->n_out));
-        DevSampled out{h->d_o_tr.p, h->d_o_start.p, h->d_o_end.p, h->d_o_minus.p, h->d_o_id.p};
-        launch_expand(h->st, m, make_sp(h), h->d_out_off.p, h->n_out, out);
-        tm.stop();
-        CK(h, cudaGetLastError());
+        break;
     }
+    return 0;
+}
+
+// copies drawn per species -> output records (sampler.go:187-227)
+int finish_sample(rlsim_handle *h) {
+    int rc;
+    uint64_t ns = h->n_sp;
+    DevModel m = make_model(h);
+    StageTimer tm(h, RLSIM_T_EXPAND, 4);
+    launch_taken(h->st, make_sp(h), h->d_mode.p, h->n_len, h->d_hits.p, h->d_taken.p);
+    CK(h, cudaMemsetAsync(h->d_out_off.p, 0, 8, h->st));
+    h->n_out = 0;
+    if (ns) {
+        size_t tb = 0;
+        CK(h, cub::DeviceScan::InclusiveSum(nullptr, tb, h->d_taken.p, h->d_out_off.p + 1, (int)ns, h->st));
+        if ((rc = cub_temp(h, tb))) return rc;
+        CK(h, cub::DeviceScan::InclusiveSum(h->d_cub.p, tb, h->d_taken.p, h->d_out_off.p + 1, (int)ns, h->st));
+        CK(h, cudaMemcpyAsync(&h->n_out, h->d_out_off.p + ns, 8, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaStreamSynchronize(h->st));
+    }
+    CK(h, h->d_o_tr.ensure(h->n_out)); CK(h, h->d_o_start.ensure(h->n_out)); CK(h, h->d_o_end.ensure(h->n_out));
+    CK(h, h->d_o_minus.ensure(h->n_out)); CK(h, h->d_o_id.ensure(h->n_out));
+    DevSampled out{h->d_o_tr.p, h->d_o_start.p, h->d_o_end.p, h->d_o_minus.p, h->d_o_id.p};
+    launch_expand(h->st, m, make_sp(h), h->d_out_off.p, h->n_out, out);
+    tm.stop();
+    CK(h, cudaGetLastError());
     CK(h, cudaStreamSynchronize(h->st));
     h->sampled = true;
     return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rlsim_sample(rlsim_handle *h, const uint64_t *global_totals, const uint64_t *rank_base, uint32_t n_len_in) {
+    if (!h->amplified) FAIL(h, RLSIM_E_ARG, "rlsim_pcr first");
+    if (!h->have_target) FAIL(h, RLSIM_E_ARG, "no target histogram");
+    cudaSetDevice(h->device);
+    uint32_t n_len = h->n_len;
+    std::vector<uint64_t> T(n_len, 0), base(n_len, 0);
+    for (uint32_t l = 0; l < n_len; l++) {
+        T[l] = global_totals ? (l < n_len_in ? global_totals[l] : 0) : h->h_totals[l];
+        base[l] = rank_base ? (l < n_len_in ? rank_base[l] : 0) : 0;
+    }
+    int rc = select_core(h, T, base, 1, 0, nullptr, nullptr, 0, nullptr, nullptr);
+    if (rc) return rc;
+    return finish_sample(h);
+}
+
+int rlsim_select_classes(rlsim_handle *h, const uint64_t *all_totals, uint32_t nparts, uint32_t part, uint32_t n_len_in,
+                         void *records_dev, uint64_t cap, uint64_t *counts_out, uint64_t *needed_out) {
+    if (!h->amplified) FAIL(h, RLSIM_E_ARG, "rlsim_pcr first");
+    if (!h->have_target) FAIL(h, RLSIM_E_ARG, "no target histogram");
+    if (nparts < 1 || nparts > 64 || part >= nparts) FAIL(h, RLSIM_E_ARG, "invalid rank partition");
+    if (!records_dev && cap) FAIL(h, RLSIM_E_ARG, "record buffer missing");
+    cudaSetDevice(h->device);
+    uint32_t n_len = h->n_len;
+    // global totals and every rank's first copy rank per class
+    std::vector<uint64_t> T(n_len, 0), all_base((size_t)nparts * n_len, 0), mine(n_len, 0);
+    for (uint32_t l = 0; l < n_len; l++) {
+        uint64_t acc = 0;
+        for (uint32_t r = 0; r < nparts; r++) {
+            all_base[(size_t)r * n_len + l] = acc;
+            uint64_t t = l < n_len_in ? all_totals[(size_t)r * n_len_in + l] : 0;
+            uint64_t na = acc + t;
+            if (na < acc) FAIL(h, RLSIM_E_POOL_OVERFLOW, "Integer overflow when updating total fragment count!");
+            acc = na;
+        }
+        T[l] = acc;
+        mine[l] = all_base[(size_t)part * n_len + l];
+    }
+    CK(h, h->d_all_base.ensure(all_base.size())); CK(h, h->d_my_base.ensure(n_len));
+    CK(h, cudaMemcpyAsync(h->d_all_base.p, all_base.data(), all_base.size() * 8, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemcpyAsync(h->d_my_base.p, mine.data(), (size_t)n_len * 8, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemsetAsync(h->d_error.p, 0, 4, h->st));
+    static uint4 dummy_sentinel;
+    uint4 *rec = records_dev ? (uint4 *)records_dev : &dummy_sentinel;  // non-null => record form; cap 0 => sizes only
+    return select_core(h, T, mine, nparts, part, h->d_all_base.p, rec, records_dev ? cap : 0, counts_out, needed_out);
+}
+
+int rlsim_apply_selected(rlsim_handle *h, const void *records_dev, uint64_t n) {
+    if (!h->amplified) FAIL(h, RLSIM_E_ARG, "rlsim_pcr first");
+    cudaSetDevice(h->device);
+    StageTimer tm(h, RLSIM_T_SELECT, 1);
+    launch_apply_records(h->st, (const uint4 *)records_dev, n, h->d_my_base.p, h->d_cls_pre.p, h->d_bounds.p, h->d_order.p,
+                         h->d_hits.p, h->d_error.p);
+    tm.stop();
+    CK(h, cudaGetLastError());
+    int e = 0;
+    CK(h, cudaMemcpyAsync(&e, h->d_error.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    if (e) FAIL(h, RLSIM_E_ARG, "a selection record was routed to a rank that does not own the copy");
+    return 0;
+}
+
+int rlsim_finish_sample(rlsim_handle *h) {
+    if (!h->amplified) FAIL(h, RLSIM_E_ARG, "rlsim_pcr first");
+    cudaSetDevice(h->device);
+    return finish_sample(h);
 }
 
 int rlsim_get_stats(rlsim_handle *h, rlsim_stats *out) {

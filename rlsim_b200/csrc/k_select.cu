@@ -18,11 +18,13 @@ namespace rl {
 // ---------------------------------------------------------------- target lengths
 constexpr int TGT_THREADS = 256;
 __global__ void __launch_bounds__(TGT_THREADS)
-k_target(const __grid_constant__ DevModel m, uint64_t n, unsigned long long *__restrict__ hist, uint32_t hist_n, uint32_t smem_bins) {
+k_target(const __grid_constant__ DevModel m, uint64_t first, uint64_t n, unsigned long long *__restrict__ hist, uint32_t hist_n,
+         uint32_t smem_bins) {
     extern __shared__ unsigned int hs[];
     for (uint32_t i = threadIdx.x; i < smem_bins; i += TGT_THREADS) hs[i] = 0;
     __syncthreads();
-    for (uint64_t i = (uint64_t)blockIdx.x * TGT_THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * TGT_THREADS) {
+    for (uint64_t q = (uint64_t)blockIdx.x * TGT_THREADS + threadIdx.x; q < n; q += (uint64_t)gridDim.x * TGT_THREADS) {
+        const uint64_t i = first + q;  // global draw index: the stream address
         PxCursor cur(PxStream{m.key_target, (uint32_t)(i & 0xffffffffu), (uint32_t)(i >> 32), 0u});
         uint32_t l = m.n_target == 0 ? px_raw_len(cur, m) : px_comp_len(cur, m.target[px_mix_comp(cur, m.target, m.n_target)]);
         if (l < smem_bins) atomicAdd(&hs[l], 1u);
@@ -32,12 +34,12 @@ k_target(const __grid_constant__ DevModel m, uint64_t n, unsigned long long *__r
     for (uint32_t i = threadIdx.x; i < smem_bins; i += TGT_THREADS)
         if (hs[i]) atomicAdd(&hist[i], (unsigned long long)hs[i]);
 }
-void launch_target(cudaStream_t st, const DevModel &m, uint64_t n, unsigned long long *hist, uint32_t hist_n) {
+void launch_target(cudaStream_t st, const DevModel &m, uint64_t first, uint64_t n, unsigned long long *hist, uint32_t hist_n) {
     if (!n) return;
     uint32_t smem_bins = hist_n <= 12000 ? hist_n : 12000;
     uint64_t blocks = (n + TGT_THREADS - 1) / TGT_THREADS;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_target<<<(unsigned)blocks, TGT_THREADS, smem_bins * 4, st>>>(m, n, hist, hist_n, smem_bins);
+    k_target<<<(unsigned)blocks, TGT_THREADS, smem_bins * 4, st>>>(m, first, n, hist, hist_n, smem_bins);
 }
 
 // ---------------------------------------------------------------- per-length classes
@@ -128,6 +130,91 @@ void launch_apply_picks(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, con
     if (n_cand)
         k_apply_picks<<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(plan, n_cand, keys, flags, fscan, cls_pre, bounds,
                                                                         order, hits, short_flag);
+}
+
+// ---- multi-GPU: length classes are partitioned over the ranks; the rank that draws a class routes every drawn
+// (or, in complement mode, excluded) copy rank to the rank that owns the copy.  Record = {len, 0, x_lo, x_hi}.
+__device__ __forceinline__ bool picked(const DevClassPlan &plan, uint64_t g, uint32_t c, const uint32_t *flags,
+                                       const uint64_t *fscan) {
+    return flags[g] && (fscan[g] - fscan[plan.cand_off[c]] < plan.pick[c]);
+}
+__device__ __forceinline__ uint32_t owner_of(const uint64_t *all_base, uint32_t nparts, uint32_t n_len, uint32_t l, uint64_t x) {
+    uint32_t o = 0;  // last rank whose first copy rank of this class is <= x (empty ranks have base == next base)
+    for (uint32_t r = 1; r < nparts; r++)
+        if (all_base[(uint64_t)r * n_len + l] <= x) o = r;
+    return o;
+}
+constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_MAX_PARTS = 64;
+// pass 0: per-owner counts (+ per-class "not enough distinct candidates" flags); pass 1: scatter into the owner groups
+__global__ void __launch_bounds__(EMIT_THREADS)
+k_emit_selected(DevClassPlan plan, uint64_t n_cand, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ flags,
+                const uint64_t *__restrict__ fscan, const uint64_t *__restrict__ all_base, uint32_t nparts, uint32_t n_len,
+                int pass, unsigned long long *__restrict__ counts, const unsigned long long *__restrict__ seg_off,
+                unsigned long long *__restrict__ cursor, uint4 *__restrict__ records, int *short_flag) {
+    __shared__ unsigned int cnt_s[EMIT_MAX_PARTS];
+    __shared__ unsigned long long base_s[EMIT_MAX_PARTS];
+    if (threadIdx.x < EMIT_MAX_PARTS) cnt_s[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t g = (uint64_t)blockIdx.x * EMIT_THREADS + threadIdx.x;
+    bool sel = false;
+    uint32_t owner = 0, l = 0, local = 0;
+    uint64_t x = 0;
+    if (g < n_cand) {
+        uint32_t c = class_of(plan, g);
+        if (pass == 0 && g == plan.cand_off[c]) {
+            uint64_t distinct = fscan[plan.cand_off[c + 1]] - fscan[plan.cand_off[c]];
+            if (distinct < plan.pick[c]) short_flag[c] = 1;
+        }
+        if (picked(plan, g, c, flags, fscan)) {
+            sel = true;
+            x = keys[g] - plan.G[c];
+            l = plan.len[c];
+            owner = owner_of(all_base, nparts, n_len, l, x);
+            local = atomicAdd(&cnt_s[owner], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < nparts && cnt_s[threadIdx.x]) {
+        if (pass == 0) atomicAdd(&counts[threadIdx.x], (unsigned long long)cnt_s[threadIdx.x]);
+        else base_s[threadIdx.x] = seg_off[threadIdx.x] + atomicAdd(&cursor[threadIdx.x], (unsigned long long)cnt_s[threadIdx.x]);
+    }
+    if (pass == 0) return;
+    __syncthreads();
+    if (sel) records[base_s[owner] + local] = make_uint4(l, 0u, (uint32_t)(x & 0xffffffffu), (uint32_t)(x >> 32));
+}
+void launch_emit_selected(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, const uint64_t *keys, const uint32_t *flags,
+                          const uint64_t *fscan, const uint64_t *all_base, uint32_t nparts, uint32_t n_len, int pass,
+                          unsigned long long *counts, const unsigned long long *seg_off, unsigned long long *cursor,
+                          uint4 *records, int *short_flag) {
+    if (n_cand)
+        k_emit_selected<<<(unsigned)((n_cand + EMIT_THREADS - 1) / EMIT_THREADS), EMIT_THREADS, 0, st>>>(
+            plan, n_cand, keys, flags, fscan, all_base, nparts, n_len, pass, counts, seg_off, cursor, records, short_flag);
+}
+
+// records received from the drawing ranks -> hits on this rank's species
+__global__ void k_apply_records(const uint4 *__restrict__ records, uint64_t n, const uint64_t *__restrict__ my_base,
+                                const uint64_t *__restrict__ cls_pre, const uint64_t *__restrict__ bounds,
+                                const uint32_t *__restrict__ order, unsigned long long *__restrict__ hits, int *error) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 r = records[i];
+    uint32_t l = r.x;
+    uint64_t x = (uint64_t)r.z | ((uint64_t)r.w << 32);
+    uint64_t b = bounds[l], e = bounds[l + 1];
+    uint64_t t_local = cls_pre[e] - cls_pre[b];
+    if (x < my_base[l] || x - my_base[l] >= t_local) { atomicExch(error, RLSIM_E_ARG); return; }  // mis-routed record
+    uint64_t tgt = cls_pre[b] + (x - my_base[l]);
+    uint64_t lo = b, hi = e;
+    while (lo < hi) {
+        uint64_t mid = lo + ((hi - lo) >> 1);
+        if (!(cls_pre[mid + 1] > tgt)) lo = mid + 1; else hi = mid;
+    }
+    atomicAdd(&hits[order[lo]], 1ull);
+}
+void launch_apply_records(cudaStream_t st, const uint4 *records, uint64_t n, const uint64_t *my_base, const uint64_t *cls_pre,
+                          const uint64_t *bounds, const uint32_t *order, unsigned long long *hits, int *error) {
+    if (n) k_apply_records<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(records, n, my_base, cls_pre, bounds, order, hits, error);
 }
 
 // mode per length: 0 = nothing drawn, 1 = whole class drawn, 2 = hits are the drawn copies, 3 = hits are the excluded copies

@@ -42,7 +42,7 @@ void launch_math_probe(cudaStream_t st, int fn, const double *x, const double *y
 void launch_philox_probe(cudaStream_t st, const uint32_t *ck, uint32_t *out, uint32_t n);
 
 // k_select.cu
-void launch_target(cudaStream_t st, const DevModel &m, uint64_t n, unsigned long long *hist, uint32_t hist_n);
+void launch_target(cudaStream_t st, const DevModel &m, uint64_t first, uint64_t n, unsigned long long *hist, uint32_t hist_n);
 void launch_gather_counts(cudaStream_t st, const uint32_t *order, const uint64_t *count, uint64_t *out, uint64_t n);
 void launch_class_bounds(cudaStream_t st, const uint32_t *sorted_len, uint64_t n, uint32_t n_len, uint64_t *bounds);
 struct DevClassPlan {          // per requested length class (host-built, device-resident)
@@ -60,6 +60,12 @@ void launch_first_flags(cudaStream_t st, const uint64_t *sorted_keys, const uint
 void launch_apply_picks(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, const uint64_t *keys_by_idx,
                         const uint32_t *flags, const uint64_t *flag_scan, const uint64_t *cls_pre,
                         const uint64_t *bounds, const uint32_t *order, unsigned long long *hits, int *short_flag);
+void launch_emit_selected(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, const uint64_t *keys, const uint32_t *flags,
+                          const uint64_t *fscan, const uint64_t *all_base, uint32_t nparts, uint32_t n_len, int pass,
+                          unsigned long long *counts, const unsigned long long *seg_off, unsigned long long *cursor,
+                          uint4 *records, int *short_flag);
+void launch_apply_records(cudaStream_t st, const uint4 *records, uint64_t n, const uint64_t *my_base, const uint64_t *cls_pre,
+                          const uint64_t *bounds, const uint32_t *order, unsigned long long *hits, int *error);
 void launch_taken(cudaStream_t st, const DevSpecies &sp, const uint8_t *mode_by_len, uint32_t n_len,
                   const unsigned long long *hits, uint64_t *taken);
 struct DevSampled { uint32_t *tr, *start, *end; uint8_t *minus; uint64_t *id; };

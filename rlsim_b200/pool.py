@@ -46,7 +46,16 @@ class GpuPool:
         h.set_model(self.params)
         if args.raw_len_probs is not None:
             h.set_raw_target(args.raw_len_probs.lengths, args.raw_len_probs.probs)
-        h.sample_target(args.req_frags)  # same histogram on every rank (stream keyed by the draw index)
+        if self.world > 1:  # every rank draws 1/world of the target lengths; the histograms are summed (same total
+            n = args.req_frags  # histogram on every rank: the stream is keyed by the global draw index)
+            a, b = n * self.rank // self.world, n * (self.rank + 1) // self.world
+            h.sample_target_range(a, b - a)
+            nb = int(max([c.high for c in args.target_mix] + (args.raw_len_probs.lengths if args.raw_len_probs else [0]))) + 1
+            tot = shard.allreduce_hist(h.hist(_native.H_TARGET, nb), device=self.dist_device)
+            nz = np.nonzero(tot)[0]
+            h.set_target_hist(nz.astype(np.uint32), tot[nz])
+        else:
+            h.sample_target(args.req_frags)
         return self
 
     def reset(self):
@@ -92,9 +101,14 @@ class GpuSampler:
     def sample_fragments(self, pool: GpuPool, stats: FragStats = None):
         """sampler.go:108-154.  -> dict of arrays (tr, start, end, minus, id) for this rank's shard."""
         h = pool.handle
-        local = h.class_totals()
-        total, base = shard.allgather_totals(local, device=pool.dist_device)
-        h.sample(total, base)
+        if pool.world > 1:  # classes partitioned over the ranks, drawn copy ranks routed to their owners (all-to-all)
+            if not hasattr(pool, "_exchange"):
+                pool._exchange = shard.RecordExchange(pool.dist_device)
+            all_tot = pool._exchange.run(h, pool.rank, pool.world, int(h.stats().n_requested) // pool.world + 4096)
+            total = all_tot.sum(axis=0, dtype=np.uint64)
+        else:
+            total = h.class_totals()
+            h.sample()
         if stats is not None:
             n = len(total)
             stats.after_pcr = _nz(total)

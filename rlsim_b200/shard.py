@@ -56,6 +56,60 @@ def allgather_totals(local_totals, group=None, device=None):
     return total, base
 
 
+def allgather_totals_matrix(local_totals, group=None, device=None):
+    """-> [world, n_len] u64 matrix of every rank's per-length totals (row r = rank r)."""
+    import torch
+    import torch.distributed as dist
+    local = np.ascontiguousarray(local_totals, dtype=np.uint64)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local[None, :].copy()
+    world = dist.get_world_size(group)
+    t = torch.from_numpy(local.view(np.int64).copy())
+    if device is not None:
+        t = t.to(device)
+    gathered = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t, group=group)
+    return np.stack([g.cpu().numpy().view(np.uint64) for g in gathered])
+
+
+class RecordExchange:
+    """Size selection on N GPUs without redundant work.
+
+    Length classes are partitioned over the ranks (class l is drawn by rank l % N); every drawn (or, for classes drawn
+    more than half, excluded) copy rank is routed to the rank that owns the copy with ONE all-to-all over NVLink
+    (16-byte records); the owner maps it to its species.  Same result as one GPU: the per-class streams do not depend on
+    who evaluates them."""
+
+    def __init__(self, device):
+        self.device = device
+        self.send = None
+
+    def _buffer(self, torch, n):
+        if self.send is None or self.send.shape[0] < n:
+            self.send = torch.empty((int(n * 1.25) + 1024, 2), dtype=torch.int64, device=self.device)
+        return self.send
+
+    def run(self, handle, rank, world, expected_records, group=None):
+        import torch
+        import torch.distributed as dist
+        all_tot = allgather_totals_matrix(handle.class_totals(), group, self.device)
+        buf = self._buffer(torch, expected_records)
+        counts, needed = handle.select_classes(all_tot, rank, buf.data_ptr(), buf.shape[0])
+        if needed > buf.shape[0]:
+            buf = self._buffer(torch, needed)
+            counts, needed = handle.select_classes(all_tot, rank, buf.data_ptr(), buf.shape[0])
+        send_counts = torch.from_numpy(counts.astype(np.int64)).to(self.device)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=group)
+        rc = [int(x) for x in recv_counts.cpu()]
+        recv = torch.empty((sum(rc), 2), dtype=torch.int64, device=self.device)
+        dist.all_to_all_single(recv, buf[:needed], output_split_sizes=rc, input_split_sizes=[int(c) for c in counts], group=group)
+        torch.cuda.synchronize(self.device)
+        handle.apply_selected(recv.data_ptr() if recv.shape[0] else None, recv.shape[0])
+        handle.finish_sample()
+        return all_tot
+
+
 def allreduce_hist(h, group=None, device=None):
     """Sum a per-rank u64 histogram over the ranks (report panels)."""
     import torch

@@ -177,3 +177,70 @@ def test_sharding_invariance(oracle, gpu):
         outs.append(p.sampled())
     for k in ("tr", "start", "end", "minus", "id"):
         assert np.array_equal(np.concatenate([outs[0][k], outs[1][k]]), ref[k]), k
+
+
+def test_class_partitioned_selection(gpu):
+    """The N-GPU form without redundant work: classes drawn by rank l % N, drawn copy ranks routed to their owners
+    (the all-to-all is emulated with device copies between two handles on one GPU).  Identical to one GPU."""
+    import torch
+    from rlsim_b200 import shard
+    args = util.parse(["-n", "40000", "-c", "6", "-si", "13"])
+    names, seqs, levels = util.synth_transcriptome(60, seed=4, mean_len=1200, hi=5000, total_molecules=30000)
+    whole = util.run_gpu(gpu, args, names, seqs, levels)
+    ref = whole.sampled()
+    for world in (2, 3):
+        b = shard.contiguous_partition(shard.work_estimate([len(s) for s in seqs], levels), world)
+        parts = [util.run_gpu(gpu, args, names[b[r]:b[r + 1]], seqs[b[r]:b[r + 1]], levels[b[r]:b[r + 1]], stages="pcr", first=b[r])
+                 for r in range(world)]
+        all_tot = np.stack([p.class_totals() for p in parts])
+        sends, counts = [], []
+        for r, p in enumerate(parts):
+            c, needed = p.select_classes(all_tot, r)  # size query
+            buf = torch.empty((max(needed, 1), 2), dtype=torch.int64, device="cuda:0")
+            c, needed2 = p.select_classes(all_tot, r, buf.data_ptr(), buf.shape[0])
+            assert needed2 == needed and int(c.sum()) == needed
+            sends.append(buf[:needed])
+            counts.append([int(x) for x in c])
+        torch.cuda.synchronize()
+        outs = []
+        for r, p in enumerate(parts):
+            segs = []
+            for s_ in range(world):
+                o = sum(counts[s_][:r])
+                segs.append(sends[s_][o:o + counts[s_][r]])
+            recv = torch.cat(segs) if segs else torch.empty((0, 2), dtype=torch.int64, device="cuda:0")
+            torch.cuda.synchronize()
+            p.apply_selected(recv.data_ptr() if recv.shape[0] else None, recv.shape[0])
+            p.finish_sample()
+            outs.append(p.sampled())
+        for k in ("tr", "start", "end", "minus", "id"):
+            assert np.array_equal(np.concatenate([o[k] for o in outs]), ref[k]), (world, k)
+        for kind in (gpu.H_SAMPLED, gpu.H_MISSING, gpu.H_AFTER_SAMPLING):
+            assert parts[0].hist_dict(kind, 4096) == whole.hist_dict(kind, 4096)
+
+
+def test_target_sampling_partition(gpu):
+    """a19 on N ranks: each draws a slice of the draw indices; the summed histogram equals the single-rank one."""
+    for argv in (["-n", "100000", "-si", "3"], ["-j", util.RAW_PARAMS, "-n", "50000", "-si", "4"]):
+        args = util.parse(argv)
+        whole = gpu.Handle(0)
+        whole.set_model(args.to_params())
+        if args.raw_len_probs is not None:
+            whole.set_raw_target(args.raw_len_probs.lengths, args.raw_len_probs.probs)
+        whole.sample_target(args.req_frags)
+        ref = whole.hist(gpu.H_TARGET, 4096)
+        acc = np.zeros_like(ref)
+        n = args.req_frags
+        for r in range(3):
+            h = gpu.Handle(0)
+            h.set_model(args.to_params())
+            if args.raw_len_probs is not None:
+                h.set_raw_target(args.raw_len_probs.lengths, args.raw_len_probs.probs)
+            a, b = n * r // 3, n * (r + 1) // 3
+            h.sample_target_range(a, b - a)
+            acc += h.hist(gpu.H_TARGET, 4096)
+        assert np.array_equal(acc, ref)
+        nz = np.nonzero(acc)[0]
+        h.set_target_hist(nz.astype(np.uint32), acc[nz])
+        st, sw = h.stats(), whole.stats()
+        assert (st.low, st.high, st.n_requested) == (sw.low, sw.high, sw.n_requested)
