@@ -285,25 +285,37 @@ def main():
     lens = (off_np[1:] - off_np[:-1]).astype(np.int64)
     nt_total = int(lens[expressed].sum()) + int(expressed.sum()) * int(st.polya_max)
     # algorithmic bytes per step of each own kernel group
+    n_intervals = float(st.n_fragments) * 1.0  # queued intervals ~ kept fragments at this -d (upper bound of what the searches touch)
     alg = {
         "prefix": 16.25 * nt_total,                       # 0.25 B/nt read + 2 x 8 B/nt prefix sums written (expressed transcripts)
-        "fragment": 120.0 * float(st.n_molecules),        # ~120 B/molecule (draws are register-resident; searches + keys)
+        "fragment": 8.0 * float(st.n_molecules) + 24.0 * n_intervals,   # k_fragment: 8 B/molecule in, 24 B per queued interval out
+        "intervals": (24.0 + 2 * 12 * 8.0 + 8.0) * n_intervals,         # k_intervals: record in, 2 searches x ~12 probes x 8 B, key out
         "pcr": 32.0 * float(st.n_species),                # 32 B/species
         "expand": 150.0 * float(st.n_sampled),            # ~150 B/sampled fragment
     }
     peak, peak_src = peaks()
     kernels = {}
     for k, b in alg.items():
-        if stage_ms[k] > 0:
+        if stage_ms.get(k, 0) > 0:
             kernels[k] = {"ms": stage_ms[k], "alg_bytes": b, "gbs": b / (stage_ms[k] * 1e6)}
     for k in ("dedup", "select", "target", "layout"):
         kernels[k] = {"ms": stage_ms[k]}
     own = {k: v for k, v in kernels.items() if "gbs" in v}
     dom = max(own, key=lambda k: own[k]["ms"])
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": own[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": own[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
-                "pcr": {"achieved": own["pcr"]["gbs"], "frac": own["pcr"]["gbs"] / peak, "ms": own["pcr"]["ms"],
-                        "species": int(st.n_species), "note": "issue-bound: 15 exact binomial draws per 32 B species"}}
+    # measured DRAM traffic per unit from the committed ncu --set full capture (profiles/ncu_traffic.json), scaled to this run
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        units = {"pcr": float(st.n_species), "prefix": float(nt_total), "intervals": n_intervals, "fragment": float(st.n_molecules),
+                 "expand": float(st.n_sampled)}
+        if dom in tj and dom in units:
+            traffic = tj[dom]["bytes_per_unit"] * units[dom]
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": own[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": own[dom]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                "note": ("k_pcr is FP64-issue bound (15 exact binomial draws per 32 B species): see profiles/r1_final_ncu_summary.md"
+                         if dom == "pcr" else ""),
+                "all": {("k_" + k): {"ms": round(v["ms"], 4), "achieved": round(v["gbs"], 2), "frac": round(v["gbs"] / peak, 4)} for k, v in own.items()}}
     ms_per_step = 1000.0 * t_res / K
     line = {
         "metric": "fragments/sec (frag+PCR+size-select)", "value": n_res / t_res, "unit": "fragments/s", "n_gpus": world,

@@ -180,7 +180,8 @@ int rlsim_probe_amplify(rlsim_handle *h, int64_t seed_pcr, const uint32_t *tse, 
                         int cycles, uint64_t *out, uint32_t n);
 /* device time of the kernels of the last build_library / sample call, milliseconds, by stage */
 enum { RLSIM_T_LAYOUT = 0, RLSIM_T_PREFIX = 1, RLSIM_T_FRAGMENT = 2, RLSIM_T_DEDUP = 3, RLSIM_T_PCR = 4,
-       RLSIM_T_SELECT = 5, RLSIM_T_EXPAND = 6, RLSIM_T_FORMAT = 7, RLSIM_T_TARGET = 8, RLSIM_T_COUNT = 9 };
+       RLSIM_T_SELECT = 5, RLSIM_T_EXPAND = 6, RLSIM_T_FORMAT = 7, RLSIM_T_TARGET = 8, RLSIM_T_INTERVALS = 9,
+       RLSIM_T_COUNT = 10 };
 int rlsim_get_timings(rlsim_handle *h, float *ms_out, uint64_t *launches_out);
 
 #ifdef __cplusplus

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librlsim_gpu.so")
 
 H_TARGET, H_POLYA, H_AFTER_FRAG, H_AFTER_PCR, H_SAMPLED, H_MISSING, H_AFTER_SAMPLING = range(7)
-T_NAMES = ["layout", "prefix", "fragment", "dedup", "pcr", "select", "expand", "format", "target"]
+T_NAMES = ["layout", "prefix", "fragment", "dedup", "pcr", "select", "expand", "format", "target", "intervals"]
 
 EXPORTS = [
     "rlsim_create", "rlsim_destroy", "rlsim_last_error", "rlsim_set_model", "rlsim_set_len_eff", "rlsim_set_raw_target",

@@ -571,9 +571,13 @@ int rlsim_fragment(rlsim_handle *h) {
         CK(h, cudaStreamSynchronize(h->st));
         if (n_long > long_cap) { tm.stop(); long_cap = n_long + 1024; continue; }
         if (n_q > q_cap) { tm.stop(); q_cap = n_q + n_q / 8 + 65536; continue; }
-        if (n_q) { h->launches[RLSIM_T_FRAGMENT]++; launch_intervals(h->st, m, tr, fb, n_q); }
         if (n_long) { h->launches[RLSIM_T_FRAGMENT]++; launch_fragment_long(h->st, m, tr, fb, n_long); }
         tm.stop();
+        if (n_q) {
+            StageTimer tq(h, RLSIM_T_INTERVALS, 1);
+            launch_intervals(h->st, m, tr, fb, n_q);
+            tq.stop();
+        }
         CK(h, cudaGetLastError());
         unsigned long long cnt = 0;
         CK(h, cudaMemcpyAsync(&cnt, h->d_counters.p, 8, cudaMemcpyDeviceToHost, h->st));
