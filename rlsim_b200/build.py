@@ -21,16 +21,40 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "rlsim_gpu.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not os.path.isdir(os.path.join(CSRC, f))] + \
+           [os.path.join(HERE, "..", "include", "rlsim_gpu.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
-        return LIB
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+HOST_DIR = os.path.join(CSRC, "host")
+HOST_BIN = os.path.join(HERE, "rlsim_gpu")
+HOST_SOURCES = ["args.cpp", "io.cpp", "main.cpp"]
+
+
+def _host_stale():
+    if not os.path.exists(HOST_BIN):
+        return True
+    t = os.path.getmtime(HOST_BIN)
+    deps = [os.path.join(HOST_DIR, f) for f in os.listdir(HOST_DIR)] + [os.path.join(HERE, "..", "include", "rlsim_gpu.h"), LIB]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_host(force=False):
+    """The C++ twin of the Go host: rlsim_b200/rlsim_gpu (same flags / FASTA / report), linked against librlsim_gpu.so."""
+    if not force and not _host_stale():
+        return HOST_BIN
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall"] + [os.path.join(HOST_DIR, s) for s in HOST_SOURCES] + \
+          ["-L" + HERE, "-lrlsim_gpu", "-Wl,-rpath,$ORIGIN", "-o", HOST_BIN]
     subprocess.check_call(cmd)
+    return HOST_BIN
+
+
+def build(force=False, verbose=False):
+    if force or _stale():
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+        subprocess.check_call(cmd)
+    build_host(force)
     return LIB
 
 

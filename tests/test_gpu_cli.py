@@ -84,3 +84,41 @@ def test_pcr_overflow_is_reported(gpu):
     with pytest.raises(gpu.RlsimError) as e:
         util.run_gpu(gpu, args, names, seqs, levels, stages="pcr")
     assert "Integer overflow detected when amplifying fragments!" in str(e.value)
+
+
+def _run_cpp(argv, tmp_path):
+    exe = os.path.join(ROOT, "rlsim_b200", "rlsim_gpu")
+    rep = str(tmp_path / "report_cpp.json")
+    p = subprocess.run([exe, "-r", rep] + argv + [util.BASIC_FASTA], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    return p.stdout, json.load(open(rep)), p.stderr.decode()
+
+
+@pytest.mark.parametrize("argv", [["-n", "10000", "-si", "42", "-v"], ["-j", util.RAW_PARAMS, "-n", "3000", "-si", "5", "-f", "after_prim"],
+                                  ["-n", "2000", "-si", "9", "-e", "0.6", "-b", "0.2", "-m", "0.3", "-f", "pre_prim:800"]])
+def test_cpp_twin_equals_python_twin(argv, tmp_path):
+    """rlsim_gpu (C++ host over the C ABI) and `python -m rlsim_b200` are the same program: identical FASTA, identical
+    report (numbers compared as numbers)."""
+    f_cpp, r_cpp, log = _run_cpp(argv, tmp_path)
+    f_py, r_py, _ = _run_cli(argv, tmp_path)
+    assert f_cpp == f_py
+    assert sorted(r_cpp) == sorted(r_py)
+    for t in r_py:
+        assert {k: r_cpp[t][k] for k in ("Xl", "Yl", "Vis", "Pos")} == {k: r_py[t][k] for k in ("Xl", "Yl", "Vis", "Pos")}, t
+        a, b = r_cpp[t]["Data"], r_py[t]["Data"]
+        assert a.keys() == b.keys(), t
+        for k in a:
+            assert a[k] == pytest.approx(b[k], rel=1e-12), (t, k)
+    if "-v" in argv:
+        assert "Sampled 10000 fragments." in log
+
+
+def test_cpp_twin_fractional_length_efficiency(tmp_path):
+    """With -el the C++ host hands its own length-efficiency table to the library (rlsim_set_len_eff), the way a Go
+    host would: the run completes and the table in the report is the one used."""
+    f_cpp, r_cpp, _ = _run_cpp(util.C2[:2] + ["-si", "4"] + util.C2[2:], tmp_path)
+    assert len(r_cpp) == 12 and len(r_cpp["Length efficiency function"]["Data"]) == 1701
+    g = util.golden("c2")["panels"]["Length efficiency function"]
+    for k, v in g.items():
+        assert r_cpp["Length efficiency function"]["Data"][k] == pytest.approx(v, rel=1e-14)
+    assert f_cpp.count(b">") == sum(r_cpp["Sampled fragments"]["Data"].values())

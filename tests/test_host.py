@@ -188,3 +188,23 @@ def test_allgather_world_size_2_gloo():
         env = dict(os.environ, MASTER_ADDR="127.0.0.1")
         subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                                "--master-addr", "127.0.0.1", "--master-port", "29731", script], env=env, timeout=300)
+
+
+def test_cpp_twin_cli_surface():
+    """rlsim_gpu: -V, fatal argument errors (exit 1, reference messages) and loud failure without a GPU."""
+    import torch
+    exe = os.path.join(ROOT, "rlsim_b200", "rlsim_gpu")
+    if not os.path.exists(exe):
+        from rlsim_b200 import build
+        build.build()
+    assert subprocess.check_output([exe, "-V"]).decode().strip() == "1.3"
+    for argv, msg in ((["-n", "10", "-f", "bogus"], b"Malformed fragmentation method string"),
+                      (["-n", "10", "-d", "1:n:(1,2,9,3)"], b"Maximum fragment size is smaller"),
+                      (["-n", "10", "-flg", "2"], b"fragment loss probability"),
+                      (["-n", "10", "-eg", "(1,2,3)"], b"outside the range"),
+                      (["-nope", "1"], b"flag provided but not defined")):
+        p = subprocess.run([exe] + argv + [util.BASIC_FASTA], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert p.returncode == 1 and msg in p.stderr, (argv, p.stderr)
+    if not torch.cuda.is_available():
+        p = subprocess.run([exe, "-n", "10", util.BASIC_FASTA], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert p.returncode == 1 and b"cuda" in p.stderr.lower()
