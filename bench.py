@@ -287,7 +287,7 @@ def main():
     # algorithmic bytes per step of each own kernel group
     n_intervals = float(st.n_fragments) * 1.0  # queued intervals ~ kept fragments at this -d (upper bound of what the searches touch)
     alg = {
-        "prefix": 16.25 * nt_total,                       # 0.25 B/nt read + 2 x 8 B/nt prefix sums written (expressed transcripts)
+        "prefix": 8.5 * nt_total,                         # 0.25 B/nt read + 2 strands x (4 B fine + 8/64 B coarse) written (expressed transcripts)
         "fragment": 8.0 * float(st.n_molecules) + 24.0 * n_intervals,   # k_fragment: 8 B/molecule in, 24 B per queued interval out
         "intervals": (24.0 + 2 * 12 * 8.0 + 8.0) * n_intervals,         # k_intervals: record in, 2 searches x ~12 probes x 8 B, key out
         "pcr": 32.0 * float(st.n_species),                # 32 B/species

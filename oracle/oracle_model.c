@@ -59,8 +59,9 @@ void orc_binding_profile(const char *plus, uint32_t len, int k, double T, int re
     free(tmp);
 }
 
-/* spec 4.3: fixed-point priming weights.  scale = 2^32 / Kmax, Kmax = max K over the 4^k ACGT k-mers
- * (det_exp), w = floor(K * scale + 0.5) saturated to 2^32-1 (fits a u32). */
+/* spec 4.3: fixed-point priming weights.  scale = 2^26 / Kmax, Kmax = max K over the 4^k ACGT k-mers
+ * (det_exp), w = floor(K * scale + 0.5) saturated to 2^26-1 (64 of them sum to less than 2^32: the GPU keeps
+ * u32 sums inside 64-entry blocks and u64 sums per block). */
 static double px_kmax(int k, double T) {
     char buf[32];
     double mx = 0.0;
@@ -74,14 +75,14 @@ static double px_kmax(int k, double T) {
 }
 static uint64_t px_quant(double K, double scale) {
     double x = K * scale + 0.5;
-    if (!(x < 4294967295.0)) return 4294967295ULL;
+    if (!(x < 67108863.0)) return 67108863ULL;
     return (uint64_t)x;
 }
 void orc_quantized_weights(const char *plus, uint32_t len, int k, double T, int reverse, uint64_t *w) {
     if (len <= (uint32_t)k) return;
     double *prof = (double *)malloc((size_t)(len - k) * 8);
     orc_binding_profile(plus, len, k, T, reverse, 1, prof);
-    double scale = 4294967296.0 / px_kmax(k, T);
+    double scale = 67108864.0 / px_kmax(k, T);
     for (uint32_t i = 0; i < len - (uint32_t)k; i++) w[i] = px_quant(prof[i], scale);
     free(prof);
 }

@@ -101,9 +101,12 @@ struct rlsim_handle {
     std::vector<uint64_t> h_off;     // padded offsets [n+1]
     std::vector<uint32_t> h_len;     // with polyA
     uint64_t n_mol = 0, total_padded = 0;
+    double sum_expr = 0, sum_expr_len = 0;  // for the fragment-capacity estimate
+    bool mol_off_valid = false;
     DBuf<uint8_t> d_bases;
     DBuf<uint32_t> d_packed, d_nmask, d_gc, d_len;
-    DBuf<uint64_t> d_off, d_expr, d_mol_off, d_Pf, d_Pr;
+    DBuf<uint64_t> d_off, d_expr, d_mol_off, d_Cf, d_Cr;  // coarse prefix sums
+    DBuf<uint32_t> d_Ff, d_Fr;                          // fine (in-block) prefix sums
     uint32_t prefix_upto = 0;  // transcripts [0, prefix_upto) have valid priming prefix sums for the current model
     bool lut_valid = false;
     // model tables
@@ -231,8 +234,10 @@ DevTranscripts make_tr(rlsim_handle *h) {
     t.n = (uint32_t)h->h_len.size();
     t.bases = h->d_bases.p; t.packed = h->d_packed.p; t.nmask = h->d_nmask.p; t.off = h->d_off.p; t.len = h->d_len.p;
     t.expr = h->d_expr.p; t.mol_off = h->d_mol_off.p;
-    t.Pf = needs_fwd(h->p.frag_method) ? h->d_Pf.p : nullptr;
-    t.Pr = needs_rev(h->p.frag_method) ? h->d_Pr.p : nullptr;
+    t.Ff = needs_fwd(h->p.frag_method) ? h->d_Ff.p : nullptr;
+    t.Cf = needs_fwd(h->p.frag_method) ? h->d_Cf.p : nullptr;
+    t.Fr = needs_rev(h->p.frag_method) ? h->d_Fr.p : nullptr;
+    t.Cr = needs_rev(h->p.frag_method) ? h->d_Cr.p : nullptr;
     t.gc = h->d_gc.p;
     return t;
 }
@@ -259,6 +264,17 @@ int raw_target_finish(rlsim_handle *h) {  // raw_target.go:54,59-90
     return 0;
 }
 
+// capacity of the two-level prefix-sum arrays for `tot` padded bases in `n` transcripts, keeping the first old_tot / old_n
+int grow_prefix(rlsim_handle *h, uint64_t tot, uint32_t n, uint64_t old_tot, uint32_t old_n) {
+    CK(h, h->d_Ff.grow_preserve(tot + 64, old_tot, h->st));
+    CK(h, h->d_Cf.grow_preserve(tot / 32 + 2ull * n + 8, old_n ? old_tot / 32 + 2ull * old_n + 2 : 0, h->st));
+    if (needs_rev(h->p.frag_method)) {
+        CK(h, h->d_Fr.grow_preserve(tot + 64, old_tot, h->st));
+        CK(h, h->d_Cr.grow_preserve(tot / 32 + 2ull * n + 8, old_n ? old_tot / 32 + 2ull * old_n + 2 : 0, h->st));
+    }
+    return 0;
+}
+
 // priming affinities -> prefix sums for transcripts [t0, t1) (nnthermo.go:177-201); launches only
 int launch_prefix_range(rlsim_handle *h, uint32_t t0, uint32_t t1) {
     int method = h->p.frag_method;
@@ -270,7 +286,7 @@ int launch_prefix_range(rlsim_handle *h, uint32_t t0, uint32_t t1) {
         h->launches[RLSIM_T_PREFIX] += 2;
     }
     launch_prefix(h->st, make_tr(h), t0, t1, h->p.kmer_len, h->p.priming_temp, h->d_wq_f.p, h->d_wq_r.p, h->d_kmax.p,
-                  h->d_Pf.p, h->d_Pr.p, needs_rev(method) ? 2 : 1, h->d_work.p);
+                  h->d_Ff.p, h->d_Fr.p, h->d_Cf.p, h->d_Cr.p, needs_rev(method) ? 2 : 1, h->d_work.p);
     h->launches[RLSIM_T_PREFIX] += 1;
     return 0;
 }
@@ -278,15 +294,18 @@ int launch_prefix_range(rlsim_handle *h, uint32_t t0, uint32_t t1) {
 // everything that needs the complete transcript set: molecule offsets, remaining prefix sums
 int finalize(rlsim_handle *h) {
     uint32_t n = (uint32_t)h->h_len.size();
-    std::vector<uint64_t> mol_off(n + 1, 0);
-    for (uint32_t t = 0; t < n; t++) mol_off[t + 1] = mol_off[t] + h->h_expr[t];
-    h->n_mol = mol_off[n];
-    CK(h, h->d_mol_off.ensure(n + 1));
-    CK(h, cudaMemcpyAsync(h->d_mol_off.p, mol_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, h->st));
-    CK(h, cudaStreamSynchronize(h->st));
+    if (!h->mol_off_valid) {
+        std::vector<uint64_t> mol_off(n + 1, 0);
+        for (uint32_t t = 0; t < n; t++) mol_off[t + 1] = mol_off[t] + h->h_expr[t];
+        h->n_mol = mol_off[n];
+        CK(h, h->d_mol_off.ensure(n + 1));
+        CK(h, cudaMemcpyAsync(h->d_mol_off.p, mol_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, h->st));
+        CK(h, cudaStreamSynchronize(h->st));
+        h->mol_off_valid = true;
+    }
     if (needs_fwd(h->p.frag_method) && h->prefix_upto < n) {
-        CK(h, h->d_Pf.grow_preserve(h->total_padded + 2ull * n + 8, h->prefix_upto ? h->d_Pf.n : 0, h->st));
-        if (needs_rev(h->p.frag_method)) CK(h, h->d_Pr.grow_preserve(h->total_padded + 2ull * n + 8, h->prefix_upto ? h->d_Pr.n : 0, h->st));
+        int rcg = grow_prefix(h, h->total_padded, n, h->prefix_upto ? h->total_padded : 0, h->prefix_upto);
+        if (rcg) return rcg;
         StageTimer tm(h, RLSIM_T_PREFIX, 0);
         int rc = launch_prefix_range(h, h->prefix_upto, n);
         if (rc) return rc;
@@ -444,6 +463,7 @@ int rlsim_clear_transcripts(rlsim_handle *h) {
     h->h_srclen.clear(); h->h_expr.clear(); h->h_off.clear(); h->h_len.clear();
     h->prefix_upto = 0; h->fragmented = h->amplified = h->sampled = false;
     h->n_mol = h->total_padded = h->n_frag = h->n_sp = h->n_out = h->pool_total = 0;
+    h->sum_expr = h->sum_expr_len = 0; h->mol_off_valid = false;
     memset(h->ms, 0, sizeof h->ms);
     memset(h->launches, 0, sizeof h->launches);
     return 0;
@@ -465,12 +485,15 @@ int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t 
         h->h_srclen.push_back(rel[i + 1] - rel[i]);
         h->h_expr.push_back(expr[i]);
         h->h_len.push_back((uint32_t)L);
+        h->sum_expr += (double)expr[i];
+        h->sum_expr_len += (double)expr[i] * (double)L;
         h->h_off.push_back(h->h_off.back() + ((L + 31) & ~31ull));
     }
     const uint32_t nn = n0 + n;
     const uint64_t old_total = h->total_padded, tot = h->h_off[nn];
     if (tot >= (1ull << 40)) FAIL(h, RLSIM_E_UNSUPPORTED, "more than 2^40 bases on one GPU");
     h->total_padded = tot;
+    h->mol_off_valid = false;
     h->fragmented = h->amplified = h->sampled = false;
     // ---- device arrays: grow keeping what earlier batches wrote
     CK(h, h->d_bases.grow_preserve(tot + 64, old_total, h->st));
@@ -479,8 +502,8 @@ int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t 
     CK(h, h->d_gc.grow_preserve(tot + nn + 8, old_total + n0 + 1, h->st));
     const bool want_prefix = needs_fwd(h->p.frag_method) && h->prefix_upto == n0;
     if (want_prefix) {
-        CK(h, h->d_Pf.grow_preserve(tot + 2ull * nn + 8, n0 ? old_total + 2ull * n0 + 2 : 0, h->st));
-        if (needs_rev(h->p.frag_method)) CK(h, h->d_Pr.grow_preserve(tot + 2ull * nn + 8, n0 ? old_total + 2ull * n0 + 2 : 0, h->st));
+        int rcg = grow_prefix(h, tot, nn, old_total, n0);
+        if (rcg) return rcg;
     }
     CK(h, h->d_off.ensure(nn + 1)); CK(h, h->d_len.ensure(nn)); CK(h, h->d_expr.ensure(nn));
     CK(h, cudaMemcpyAsync(h->d_off.p, h->h_off.data(), (size_t)(nn + 1) * 8, cudaMemcpyHostToDevice, h->st));
@@ -533,14 +556,11 @@ int rlsim_fragment(rlsim_handle *h) {
         loc = lmin > 0 ? lmin : (wsum > 0 ? lsum / wsum : 1.0);
     }
     if (!(loc > 0)) loc = 1.0;
-    double est = 0;
-    for (uint32_t t = 0; t < n; t++) {
-        double L = h->h_len[t], per;
-        if (method == RLSIM_PRIM_JUMP) per = L / (double)std::max<uint64_t>(h->low, 1) + 1.0;
-        else if (method == RLSIM_PRE_PRIM) per = L / loc + 1.0;
-        else per = (h->p.frag_param == 0 ? L / loc / 2.0 : L / (double)h->p.frag_param) + 1.0;
-        est += per * (double)h->h_expr[t];
-    }
+    // expected fragments <= sum over molecules of (Poisson rate + 1): (sum expr*L) / denominator + sum expr
+    double denom = method == RLSIM_PRIM_JUMP ? (double)std::max<uint64_t>(h->low, 1)
+                 : method == RLSIM_PRE_PRIM ? loc
+                 : (h->p.frag_param == 0 ? 2.0 * loc : (double)h->p.frag_param);
+    double est = h->sum_expr_len / denom + h->sum_expr;
     uint64_t cap = (uint64_t)(est * 1.15) + 65536;
     uint32_t hist_frag_n = (uint32_t)h->high + 1, hist_pa_n = h->polya_max + 1;
     CK(h, h->d_hist_frag.ensure(hist_frag_n)); CK(h, h->d_hist_polya.ensure(hist_pa_n));
@@ -1041,10 +1061,15 @@ int rlsim_probe_prefix(rlsim_handle *h, uint32_t tr, int reverse, uint64_t *out,
     if (tr >= h->h_len.size()) FAIL(h, RLSIM_E_ARG, "transcript index out of range");
     if (reverse && !needs_rev(h->p.frag_method)) FAIL(h, RLSIM_E_ARG, "no reverse profile for this method");
     cudaSetDevice(h->device);
-    uint32_t have = h->h_len[tr] > (uint32_t)h->p.kmer_len ? h->h_len[tr] - h->p.kmer_len + 1 : 1;
-    uint32_t m = std::min(n, have);
-    CK(h, cudaMemcpyAsync(out, (reverse ? h->d_Pr.p : h->d_Pf.p) + prefix_base(h->h_off[tr], tr), (size_t)m * 8, cudaMemcpyDeviceToHost, h->st));
+    // rebuild P(0..proflen) from the two levels: P(i) = coarse[i >> 6] + (i & 63 ? fine[i - 1] : 0)
+    uint32_t proflen = h->h_len[tr] > (uint32_t)h->p.kmer_len ? h->h_len[tr] - h->p.kmer_len : 0;
+    uint32_t have = proflen + 1, nblk = (proflen + 63) / 64;
+    std::vector<uint32_t> fine(std::max<uint32_t>(proflen, 1));
+    std::vector<uint64_t> coarse(nblk + 1);
+    if (proflen) CK(h, cudaMemcpyAsync(fine.data(), (reverse ? h->d_Fr.p : h->d_Ff.p) + h->h_off[tr], (size_t)proflen * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaMemcpyAsync(coarse.data(), (reverse ? h->d_Cr.p : h->d_Cf.p) + coarse_base(h->h_off[tr], tr), (size_t)(nblk + 1) * 8, cudaMemcpyDeviceToHost, h->st));
     CK(h, cudaStreamSynchronize(h->st));
+    for (uint32_t i = 0; i < std::min(n, have); i++) out[i] = coarse[i >> 6] + ((i & 63) ? fine[i - 1] : 0);
     return 0;
 }
 

@@ -47,13 +47,28 @@ struct DevTranscripts {
     const uint32_t *len;      // [n] length including the maximal poly-A tail
     const uint64_t *expr;     // [n]
     const uint64_t *mol_off;  // [n+1] exclusive scan of expr
-    const uint64_t *Pf, *Pr;  // priming prefix sums, (len-k+1) entries per transcript at prefix_base(off[t], t)
+    // priming prefix sums, two levels: fine = u32 inclusive sums inside 64-entry blocks at off[t],
+    // coarse = u64 sum of everything before each block at coarse_base(off[t], t)
+    const uint32_t *Ff, *Fr;
+    const uint64_t *Cf, *Cr;
     const uint32_t *gc;       // GC prefix counts, (len+1) entries per transcript at off[t] + t
 };
 
-// First entry of transcript t's prefix-sum array: odd index, so that P[1] (the first computed sum) is 16-byte
-// aligned for vector stores.  Region of transcript t: [off[t]+2t+1, off[t+1]+2t+2].
-__host__ __device__ __forceinline__ uint64_t prefix_base(uint64_t off, uint32_t t) { return off + 2ull * t + 1ull; }
+// Two-level prefix sums of the fixed-point priming weights w (< 2^26, so a 64-entry block sums to < 2^32):
+//   fine[i]   = w[64*(i/64)] + ... + w[i]            (u32, at entry off[t] + i)
+//   coarse[b] = w[0] + ... + w[64*b - 1]             (u64, at coarse_base(off[t], t) + b; coarse[nblk] = total)
+// P(i) = sum of w[j], j < i  =  coarse[i >> 6] + (i & 63 ? fine[i - 1] : 0).
+constexpr uint32_t PFX_BLOCK_SHIFT = 6, PFX_BLOCK = 64;
+__host__ __device__ __forceinline__ uint64_t coarse_base(uint64_t off, uint32_t t) { return (off >> 5) + 2ull * t; }
+
+struct Profile {  // one strand of one transcript
+    const uint32_t *F;
+    const uint64_t *C;
+    __device__ __forceinline__ uint64_t P(uint32_t i) const {
+        uint64_t c = C[i >> PFX_BLOCK_SHIFT];
+        return (i & (PFX_BLOCK - 1)) ? c + F[i - 1] : c;
+    }
+};
 
 __device__ __forceinline__ uint32_t upper_bound_u64(const uint64_t *a, uint32_t n, uint64_t x) {
     uint32_t lo = 0, hi = n;  // first i with a[i] > x

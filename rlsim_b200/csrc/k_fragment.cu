@@ -42,37 +42,55 @@ __device__ __forceinline__ PxStream mol_stream(const DevModel &m, uint32_t tg, u
     return PxStream{m.key_frag, tg, (uint32_t)(mol & 0xffffffffu), (sub << 24) | (uint32_t)((mol >> 32) & 0xffffffu)};
 }
 
-// SimulatePriming, nnthermo.go:203-217, over prefix sums P[0..proflen]: the smallest i in [start,end) with
-// P[i+1] > P[start] + u.  The answer is defined by the integers alone; HOW it is searched is free.  The weights of
-// neighbouring k-mers vary by less than one order of magnitude, so P is close to linear inside a window:
-// interpolation finds the position in ~3 dependent round trips (2 adjacent loads each) where bisection needs ~11;
-// after PRIME_INTERP_STEPS misses it falls back to bisection on the narrowed bracket.
+// SimulatePriming, nnthermo.go:203-217, over the prefix sums P(0..proflen): the smallest i in [start,end) with
+// P(i+1) > P(start) + u.  The answer is defined by the integers alone; HOW it is searched is free.  The weights of
+// neighbouring k-mers vary by less than one order of magnitude, so P is close to linear inside a window: an
+// interpolated guess in the coarse (per 64 entries) array picks the block, an interpolated guess inside the block's
+// 64 u32 sums lands within a few entries, and a short walk finishes - ~3 dependent round trips where bisection of a
+// flat u64 array needs ~11.
 constexpr int PRIME_INTERP_STEPS = 4;
-__device__ __forceinline__ bool priming(const PxStream &iv, uint32_t block, const uint64_t *__restrict__ P,
-                                        uint32_t proflen, uint32_t start, uint32_t end, uint32_t &res) {
+__device__ __forceinline__ bool priming(const PxStream &iv, uint32_t block, const Profile &pf, uint32_t proflen,
+                                        uint32_t start, uint32_t end, uint32_t &res) {
     if (end > proflen) end = proflen;
     if (start >= end) { res = 0; return true; }
-    uint64_t plo = P[start], phi = P[end];
-    uint64_t total = phi - plo;
+    const uint64_t ps = pf.P(start), pe = pf.P(end);
+    const uint64_t total = pe - ps;
     if (total == 0) return false;
-    uint64_t tgt = plo + iv.below(block, total);
-    // invariant: P[lo] <= tgt < P[hi], lo < hi; answer i satisfies P[i] <= tgt < P[i+1]
-    uint32_t lo = start, hi = end;
+    const uint64_t tgt = ps + iv.below(block, total);
+    // ---- block b in [bs, be] with C[b] <= tgt < C[b+1]   (C[bs] <= P(start) <= tgt < P(end) <= C[be+1])
+    uint32_t lo = start >> PFX_BLOCK_SHIFT, hi = ((end - 1) >> PFX_BLOCK_SHIFT) + 1;
+    uint64_t clo = 0, chi = 0;  // = C[lo], C[hi] whenever `have`
+    const bool have = hi - lo > 1;
+    if (have) {
+        clo = pf.C[lo]; chi = pf.C[hi];
 #pragma unroll 1
-    for (int it = 0; it < PRIME_INTERP_STEPS && hi - lo > 1; it++) {
-        double f = (double)(tgt - plo) / (double)(phi - plo);
-        uint32_t pos = lo + (uint32_t)(f * (double)(hi - lo));
-        if (pos >= hi) pos = hi - 1;
-        uint64_t a = P[pos], b = P[pos + 1];
-        if (tgt < a) { hi = pos; phi = a; }
-        else if (tgt >= b) { lo = pos + 1; plo = b; }
-        else { res = pos; return true; }
+        for (int it = 0; it < PRIME_INTERP_STEPS && hi - lo > 1; it++) {
+            double f = (double)(tgt - clo) / (double)(chi - clo);
+            uint32_t g = lo + (uint32_t)(f * (double)(hi - lo));
+            if (g >= hi) g = hi - 1;
+            uint64_t a = pf.C[g], b = pf.C[g + 1];
+            if (tgt < a) { hi = g; chi = a; }
+            else if (tgt >= b) { lo = g + 1; clo = b; }
+            else { lo = g; hi = g + 1; clo = a; chi = b; }
+        }
+        while (hi - lo > 1) {
+            uint32_t mid = lo + ((hi - lo) >> 1);
+            uint64_t c = pf.C[mid];
+            if (c <= tgt) { lo = mid; clo = c; } else { hi = mid; chi = c; }
+        }
     }
-    while (hi - lo > 1) {
-        uint32_t mid = lo + ((hi - lo) >> 1);
-        if (P[mid] <= tgt) lo = mid; else hi = mid;
-    }
-    res = lo;
+    const uint32_t b = lo;
+    if (!have) { clo = pf.C[b]; chi = pf.C[b + 1]; }
+    // ---- entry j of the block: smallest j with fine[64 b + j] > r
+    const uint32_t r = (uint32_t)(tgt - clo);
+    const uint32_t base = b << PFX_BLOCK_SHIFT;
+    const uint32_t nb = min(PFX_BLOCK, proflen - base);
+    const uint32_t *F = pf.F + base;
+    uint32_t j = (uint32_t)(((uint64_t)r * nb) / (chi - clo));  // chi - clo = block sum > r
+    if (j >= nb) j = nb - 1;
+    if (F[j] > r) { while (j > 0 && F[j - 1] > r) j--; }
+    else { do { j++; } while (F[j] <= r); }  // F[nb-1] = block sum > r: terminates inside the block
+    res = base + j;
     return true;
 }
 
@@ -116,7 +134,7 @@ __device__ __forceinline__ void enqueue(const FragOut &o, uint32_t t, uint64_t m
 struct MolCtx {
     uint32_t t, tg, L, proflen;
     uint64_t off;
-    const uint64_t *Pf, *Pr;
+    Profile Pf, Pr;
 };
 
 // One interval of the after_* methods, fragmentor.go:132-175
@@ -231,8 +249,8 @@ __device__ __forceinline__ MolCtx make_ctx(const DevModel &m, const DevTranscrip
     c.L = tr.len[t];
     c.proflen = c.L > (uint32_t)m.k ? c.L - (uint32_t)m.k : 0;
     c.off = tr.off[t];
-    c.Pf = tr.Pf ? tr.Pf + prefix_base(c.off, t) : nullptr;
-    c.Pr = tr.Pr ? tr.Pr + prefix_base(c.off, t) : nullptr;
+    c.Pf = Profile{tr.Ff ? tr.Ff + c.off : nullptr, tr.Cf ? tr.Cf + coarse_base(c.off, t) : nullptr};
+    c.Pr = Profile{tr.Fr ? tr.Fr + c.off : nullptr, tr.Cr ? tr.Cr + coarse_base(c.off, t) : nullptr};
     return c;
 }
 

@@ -132,9 +132,11 @@ __global__ void k_kmer_lut(int k, double T, double *__restrict__ K, unsigned lon
     atomicMax(kmax_bits, (unsigned long long)__double_as_longlong(v));  // positive doubles order like their bit patterns
 }
 
+// spec 4.3: w = min(floor(K * 2^26 / Kmax + 1/2), 2^26 - 1)
+#define PFX_SCALE 67108864.0
 __device__ __forceinline__ uint32_t quantize(double K, double scale) {
     double x = K * scale + 0.5;
-    if (!(x < 4294967295.0)) return 4294967295u;
+    if (!(x < 67108863.0)) return 67108863u;
     return (uint32_t)x;
 }
 
@@ -150,7 +152,7 @@ __global__ void k_kmer_quant(int k, const double *__restrict__ K, const unsigned
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n = 1u << (2 * k);
     if (c >= n) return;
-    double scale = 4294967296.0 / __longlong_as_double((long long)*kmax_bits);
+    double scale = PFX_SCALE / __longlong_as_double((long long)*kmax_bits);
     wq_f[c] = quantize(K[c], scale);
     wq_r[c] = quantize(K[rc_code(c, k)], scale);
 }
@@ -166,20 +168,21 @@ void launch_kmer_lut(cudaStream_t st, int k, double T, double *K, unsigned long 
 // ---------------------------------------------------------------- priming prefix sums
 constexpr int PFX_THREADS = 256;                 // 8 independent warps per CTA
 constexpr int PFX_ITEMS = 8;                     // profile entries per lane and sub-tile
-constexpr int PFX_SUB = 32 * PFX_ITEMS;          // 256 entries per warp sub-tile
-constexpr int PFX_ROW_U64 = PFX_ITEMS + 2;       // padded row of one lane in the transpose tile (80 B: conflict-free 16 B accesses)
-constexpr int PFX_TILE_U64 = 32 * PFX_ROW_U64;
+constexpr int PFX_SUB = 32 * PFX_ITEMS;          // 256 entries per warp sub-tile = 4 blocks of 64
+constexpr int PFX_ROW_U32 = PFX_ITEMS + 4;       // padded row of one lane in the transpose tile (48 B: 16 B accesses stay conflict-free)
+constexpr int PFX_TILE_U32 = 32 * PFX_ROW_U32;
 
 // One WARP per (transcript, strand); persistent CTAs fetch work from a global counter, so the 16 KB LUT is loaded
 // once per CTA and there is no block-level barrier in the loop.  Forward profile entry i is the k-mer at
 // plus[i, i+k); reverse entry i is the reverse complement of plus[j, j+k), j = L-k-i (= minus[i, i+k),
-// transcript.go:110 + nnthermo.go:184-199).  Both have L-k entries (nnthermo.go:193).  Output P[0..L-k]: exclusive
-// prefix sums of the fixed-point weights, stored at prefix_base(off[t], t) so that P[1] is 16-byte aligned.
+// transcript.go:110 + nnthermo.go:184-199).  Both have L-k entries (nnthermo.go:193).  Output: the two-level prefix
+// sums of common.cuh (4 B per entry + 8 B per 64 entries).
 //
 // Each lane owns 8 consecutive entries of a 256-entry sub-tile: it loads the 3 packed words and 2 mask words covering
 // its 8 windows (read-only path; neighbouring lanes share the words), extracts the 8 k-mer codes by shifts, gathers
-// the weights from the shared-memory LUT, and the warp scans the lane totals with shuffles.  The words of the next
-// sub-tile are requested before the current one is processed.
+// the weights from the shared-memory LUT; an 8-lane segmented shuffle scan gives the in-block sums, four shuffles the
+// block totals.  The words of the next sub-tile are requested before the current one is processed; the sums go
+// through a per-warp shared-memory tile so that every store instruction covers 512 contiguous bytes.
 struct PfxWords { uint32_t p0, p1, p2, m0, m1; };
 
 __device__ __forceinline__ uint32_t pfx_jb(int reverse, uint32_t L, int k, uint32_t proflen, uint32_t ib) {
@@ -194,13 +197,14 @@ __device__ __forceinline__ PfxWords pfx_load(const DevTranscripts &tr, uint64_t 
     return PfxWords{__ldg(pk), __ldg(pk + 1), __ldg(pk + 2), __ldg(mk), __ldg(mk + 1)};
 }
 
-__global__ void __launch_bounds__(PFX_THREADS)
+__global__ void __launch_bounds__(PFX_THREADS, 4)
 k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, const uint32_t *__restrict__ wq_f,
-         const uint32_t *__restrict__ wq_r, const unsigned long long *__restrict__ kmax_bits, uint64_t *__restrict__ Pf,
-         uint64_t *__restrict__ Pr, int lut_in_smem, unsigned int *__restrict__ work) {
+         const uint32_t *__restrict__ wq_r, const unsigned long long *__restrict__ kmax_bits, uint32_t *__restrict__ Ff,
+         uint32_t *__restrict__ Fr, uint64_t *__restrict__ Cf, uint64_t *__restrict__ Cr, int lut_in_smem,
+         unsigned int *__restrict__ work) {
     extern __shared__ __align__(16) unsigned char pfx_smem[];
-    uint64_t *tile_s = reinterpret_cast<uint64_t *>(pfx_smem);                            // 8 warps x PFX_TILE_U64
-    uint32_t *lut_s = reinterpret_cast<uint32_t *>(tile_s + (PFX_THREADS / 32) * PFX_TILE_U64);
+    uint32_t *tile_s = reinterpret_cast<uint32_t *>(pfx_smem);                 // 8 warps x PFX_TILE_U32
+    uint32_t *lut_s = tile_s + (PFX_THREADS / 32) * PFX_TILE_U32;
     const int reverse = blockIdx.y;
     const uint32_t *lut = reverse ? wq_r : wq_f;
     if (lut_in_smem) {
@@ -209,11 +213,11 @@ k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, c
         lut = lut_s;
     }
     __syncthreads();
-    const double scale = 4294967296.0 / __longlong_as_double((long long)*kmax_bits);
+    const double scale = PFX_SCALE / __longlong_as_double((long long)*kmax_bits);
     const uint32_t kmask = (1u << (2 * k)) - 1u;
     const uint32_t mmask = (1u << k) - 1u;
     const uint32_t lane = threadIdx.x & 31;
-    uint64_t *Pout = reverse ? Pr : Pf;
+    uint32_t *tile = tile_s + (threadIdx.x >> 5) * PFX_TILE_U32;
 
     for (;;) {
         uint32_t t = 0;
@@ -223,11 +227,12 @@ k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, c
         if (tr.expr[t] == 0) continue;  // pool.go:104: never fragmented
         const uint32_t L = tr.len[t];
         const uint64_t o = tr.off[t];
-        uint64_t *P = Pout + prefix_base(o, t);
-        if (lane == 0) P[0] = 0;
+        uint32_t *F = (reverse ? Fr : Ff) + o;
+        uint64_t *C = (reverse ? Cr : Cf) + coarse_base(o, t);
+        if (lane == 0) C[0] = 0;
         if (L <= (uint32_t)k) continue;
         const uint32_t proflen = L - (uint32_t)k;
-        uint64_t carry = 0;
+        uint64_t carry = 0;  // sum of all weights before this sub-tile
 
         uint32_t ib = lane * PFX_ITEMS;
         PfxWords nxt{0, 0, 0, 0, 0};
@@ -237,72 +242,96 @@ k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, c
             const PfxWords w5 = nxt;
             const uint32_t ibn = ib + PFX_SUB;
             if (ibn < proflen) nxt = pfx_load(tr, o, pfx_jb(reverse, L, k, proflen, ibn));  // prefetch the next sub-tile
-            uint64_t x[PFX_ITEMS];
-            uint64_t run = 0;
+            uint32_t x[PFX_ITEMS];
+            uint32_t run = 0;
             if (ib < proflen) {
                 const uint32_t nvalid = min((uint32_t)PFX_ITEMS, proflen - ib);
                 const uint32_t jb = pfx_jb(reverse, L, k, proflen, ib);
-                const uint64_t lo64 = (uint64_t)w5.p0 | ((uint64_t)w5.p1 << 32), hi64 = (uint64_t)w5.p1 | ((uint64_t)w5.p2 << 32);
-                const uint64_t m64 = (uint64_t)w5.m0 | ((uint64_t)w5.m1 << 32);
                 const uint32_t ob = jb & 15, omb = jb & 31;
+                // 64 bits of 2-bit codes starting at base jb (covers the 8 windows: 7 + k <= 19 bases), and their N-mask
+                const uint64_t lo64 = (uint64_t)w5.p0 | ((uint64_t)w5.p1 << 32);
+                uint64_t win = lo64 >> (2 * ob);
+                if (ob) win |= (uint64_t)w5.p2 << (64 - 2 * ob);
+                const uint32_t win_lo = (uint32_t)win, win_hi = (uint32_t)(win >> 32);
+                const uint32_t mwin = (uint32_t)((((uint64_t)w5.m0 | ((uint64_t)w5.m1 << 32)) >> omb));
+                const bool clean = (mwin & ((1u << (PFX_ITEMS - 1 + k)) - 1u)) == 0;
+                if (clean && nvalid == PFX_ITEMS) {
+                    // fast path: no non-ACGT letter near, all 8 entries valid - constant shifts, one LUT gather each
 #pragma unroll
-                for (int r = 0; r < PFX_ITEMS; r++) {
-                    uint64_t w = 0;
-                    if ((uint32_t)r < nvalid) {
-                        const uint32_t d = reverse ? (nvalid - 1 - r) : (uint32_t)r;  // window start = jb + d
-                        const uint32_t ofs = ob + d;
-                        const uint32_t code = (ofs < 16 ? (uint32_t)(lo64 >> (2 * ofs)) : (uint32_t)(hi64 >> (2 * (ofs - 16)))) & kmask;
-                        const uint32_t mbits = (uint32_t)(m64 >> (omb + d)) & mmask;
-                        if (mbits == 0) {
-                            w = lut[code];
-                        } else {
-                            // non-ACGT letters in the window: evaluate KmerAffinity on the raw bytes
-                            uint8_t kmer[16];
-                            const uint8_t *bp = tr.bases + o + jb + d;
-                            if (!reverse) {
-                                for (int q = 0; q < k; q++) kmer[q] = bp[q];
-                            } else {
-                                for (int q = 0; q < k; q++) {  // utils.go:37-59
-                                    uint8_t c = bp[k - 1 - q], oc;
-                                    switch (c) { case 'A': oc = 'T'; break; case 'T': oc = 'A'; break; case 'G': oc = 'C'; break; case 'C': oc = 'G'; break; default: oc = 'N'; }
-                                    kmer[q] = oc;
-                                }
-                            }
-                            w = quantize(kmer_affinity_bytes(kmer, k, T), scale);
-                        }
+                    for (int r = 0; r < PFX_ITEMS; r++) {
+                        const int d = reverse ? (PFX_ITEMS - 1 - r) : r;  // window start = jb + d
+                        const uint32_t code = __funnelshift_r(win_lo, win_hi, 2 * d) & kmask;
+                        run += lut[code];
+                        x[r] = run;
                     }
-                    run += w;
-                    x[r] = run;
+                } else {
+#pragma unroll
+                    for (int r = 0; r < PFX_ITEMS; r++) {
+                        uint32_t w = 0;
+                        if ((uint32_t)r < nvalid) {
+                            const uint32_t d = reverse ? (nvalid - 1 - r) : (uint32_t)r;
+                            const uint32_t code = (uint32_t)(win >> (2 * d)) & kmask;
+                            const uint32_t mbits = (mwin >> d) & mmask;
+                            if (mbits == 0) {
+                                w = lut[code];
+                            } else {
+                                // non-ACGT letters in the window: evaluate KmerAffinity on the raw bytes
+                                uint8_t kmer[16];
+                                const uint8_t *bp = tr.bases + o + jb + d;
+                                if (!reverse) {
+                                    for (int q = 0; q < k; q++) kmer[q] = bp[q];
+                                } else {
+                                    for (int q = 0; q < k; q++) {  // utils.go:37-59
+                                        uint8_t c = bp[k - 1 - q], oc;
+                                        switch (c) { case 'A': oc = 'T'; break; case 'T': oc = 'A'; break; case 'G': oc = 'C'; break; case 'C': oc = 'G'; break; default: oc = 'N'; }
+                                        kmer[q] = oc;
+                                    }
+                                }
+                                w = quantize(kmer_affinity_bytes(kmer, k, T), scale);
+                            }
+                        }
+                        run += w;
+                        x[r] = run;
+                    }
                 }
             } else {
 #pragma unroll
                 for (int r = 0; r < PFX_ITEMS; r++) x[r] = 0;
             }
-            // warp-wide inclusive scan of the lane totals
-            uint64_t incl = run;
+            // in-block sums: inclusive scan of the lane totals inside each group of 8 lanes (= one 64-entry block)
+            uint32_t incl = run;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint64_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= (uint32_t)d) incl += v;
+            for (int d = 1; d < 8; d <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, d, 8);
+                if ((lane & 7) >= (uint32_t)d) incl += v;
             }
-            const uint64_t excl = carry + incl - run;
-            carry += __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t excl = incl - run;
+            // block totals of the 4 blocks of this sub-tile -> coarse sums
+            const uint32_t g0 = __shfl_sync(0xffffffffu, incl, 7), g1 = __shfl_sync(0xffffffffu, incl, 15),
+                           g2 = __shfl_sync(0xffffffffu, incl, 23), g3 = __shfl_sync(0xffffffffu, incl, 31);
+            if (lane < 4) {  // coarse[(i0 >> 6) + lane + 1] = sum of everything before block lane+1 of this sub-tile
+                uint64_t cs = carry + g0;
+                if (lane >= 1) cs += g1;
+                if (lane >= 2) cs += g2;
+                if (lane >= 3) cs += g3;
+                if (i0 + lane * PFX_BLOCK < proflen) C[(i0 >> PFX_BLOCK_SHIFT) + lane + 1] = cs;
+            }
+            carry += (uint64_t)g0 + g1 + g2 + g3;
             // transpose through this warp's shared-memory tile so that every store instruction covers 512 contiguous bytes
-            uint64_t *tile = tile_s + (threadIdx.x >> 5) * PFX_TILE_U64;
             {
-                ulonglong2 *row = reinterpret_cast<ulonglong2 *>(tile + lane * PFX_ROW_U64);
-#pragma unroll
-                for (int r = 0; r < PFX_ITEMS; r += 2) row[r >> 1] = make_ulonglong2(excl + x[r], excl + x[r + 1]);
+                uint4 *row = reinterpret_cast<uint4 *>(tile + lane * PFX_ROW_U32);
+                row[0] = make_uint4(excl + x[0], excl + x[1], excl + x[2], excl + x[3]);
+                row[1] = make_uint4(excl + x[4], excl + x[5], excl + x[6], excl + x[7]);
             }
             __syncwarp();
             const uint32_t nsub = min((uint32_t)PFX_SUB, proflen - i0);
-            uint64_t *dst = P + 1 + i0;
+            uint32_t *dst = F + i0;
 #pragma unroll
-            for (int q = 0; q < PFX_ITEMS / 2; q++) {
-                const uint32_t e = 2 * (q * 32 + lane);  // first of the two entries this lane stores
-                const uint64_t *src = tile + (e >> 3) * PFX_ROW_U64 + (e & 7);
-                if (e + 1 < nsub) *reinterpret_cast<ulonglong2 *>(dst + e) = *reinterpret_cast<const ulonglong2 *>(src);
-                else if (e < nsub) dst[e] = src[0];
+            for (int q = 0; q < 2; q++) {
+                const uint32_t e = 4 * (q * 32 + lane);  // first of the four entries this lane stores
+                const uint32_t *src = tile + (e >> 3) * PFX_ROW_U32 + (e & 7);
+                if (e + 3 < nsub) *reinterpret_cast<uint4 *>(dst + e) = *reinterpret_cast<const uint4 *>(src);
+                else for (uint32_t z = 0; z < 4 && e + z < nsub; z++) dst[e + z] = src[z];
             }
             __syncwarp();
         }
@@ -310,16 +339,16 @@ k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, c
 }
 
 void launch_prefix(cudaStream_t st, const DevTranscripts &tr, uint32_t t_begin, uint32_t t_end, int k, double T,
-                   const uint32_t *wq_f, const uint32_t *wq_r, const unsigned long long *kmax_bits, uint64_t *Pf, uint64_t *Pr,
-                   int strands, unsigned int *work) {
+                   const uint32_t *wq_f, const uint32_t *wq_r, const unsigned long long *kmax_bits, uint32_t *Ff, uint32_t *Fr,
+                   uint64_t *Cf, uint64_t *Cr, int strands, unsigned int *work) {
     if (t_end <= t_begin) return;
     int lut_in_smem = (k <= 6);
-    size_t smem = (size_t)(PFX_THREADS / 32) * PFX_TILE_U64 * 8 + (lut_in_smem ? ((size_t)4 << (2 * k)) : 16);
+    size_t smem = (size_t)(PFX_THREADS / 32) * PFX_TILE_U32 * 4 + (lut_in_smem ? ((size_t)4 << (2 * k)) : 16);
     uint32_t warps_needed = t_end - t_begin;
     uint32_t blocks = std::min<uint32_t>((warps_needed + 7) / 8, 148u * 6u);
     cudaMemsetAsync(work, 0, 2 * sizeof(unsigned int), st);
     dim3 grid(blocks, strands);
-    k_prefix<<<grid, PFX_THREADS, smem, st>>>(tr, t_begin, t_end, k, T, wq_f, wq_r, kmax_bits, Pf, Pr, lut_in_smem, work);
+    k_prefix<<<grid, PFX_THREADS, smem, st>>>(tr, t_begin, t_end, k, T, wq_f, wq_r, kmax_bits, Ff, Fr, Cf, Cr, lut_in_smem, work);
 }
 
 }  // namespace rl

@@ -10,7 +10,8 @@ void launch_ingest(cudaStream_t st, const uint8_t *src, const uint64_t *src_off,
 void launch_kmer_lut(cudaStream_t st, int k, double T, double *K, unsigned long long *kmax_bits, uint32_t *wq_f,
                      uint32_t *wq_r);
 void launch_prefix(cudaStream_t st, const DevTranscripts &tr, uint32_t t_begin, uint32_t t_end, int k, double T, const uint32_t *wq_f, const uint32_t *wq_r,
-                   const unsigned long long *kmax_bits, uint64_t *Pf, uint64_t *Pr, int strands, unsigned int *work);
+                   const unsigned long long *kmax_bits, uint32_t *Ff, uint32_t *Fr, uint64_t *Cf, uint64_t *Cr, int strands,
+                   unsigned int *work);
 
 // k_fragment.cu
 struct FragBuffers {

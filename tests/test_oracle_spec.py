@@ -90,9 +90,9 @@ def test_quantized_weights(oracle):
     n = len(seq) - 6
     w = np.zeros(n, dtype=np.uint64)
     L.orc_quantized_weights(seq, len(seq), 6, 5.0, 0, w.ctypes.data)
-    assert w[0] == 4294967295  # CGCGCG is the strongest hexamer: saturates
+    assert w[0] == 67108863  # CGCGCG is the strongest hexamer: saturates at 2^26 - 1
     k = np.array([L.orc_kmer_affinity(seq[i:i + 6], 6, 5.0, 1) for i in range(n)])
-    assert np.all(np.abs(w / 4294967296.0 - k / k.max()) <= 2.0 ** -32)
+    assert np.all(np.abs(w / 67108864.0 - k / k.max()) <= 2.0 ** -26)
 
 
 @pytest.mark.parametrize("n,p", [(1, 0.5), (7, 0.3), (24, 0.9), (25, 0.3), (1000, 0.009), (1000, 0.0101), (1000, 0.75),
