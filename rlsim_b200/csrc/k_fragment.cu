@@ -180,14 +180,14 @@ struct Header {
     uint32_t elong;   // pre_prim: first breakpoint
 };
 
-__device__ __forceinline__ double target_location(const DevModel &m, PxCursor &hdr) {
+template <class Cur> __device__ __forceinline__ double target_location(const DevModel &m, Cur &hdr) {
     if (m.n_target == 0) return m.raw_location;
     return m.target[px_mix_comp(hdr, m.target, m.n_target)].location;
 }
 
 __device__ __forceinline__ Header mol_header(const DevModel &m, const MolCtx &c, uint64_t mol) {
     Header h;
-    PxCursor hdr(mol_stream(m, c.tg, mol, SUB_HEADER));
+    PxCursor3 hdr(mol_stream(m, c.tg, mol, SUB_HEADER));  // first six header draws generated convergently
     h.tail = px_comp_len(hdr, m.polya[px_mix_comp(hdr, m.polya, m.n_polya)]);
     h.polyAend = (int)c.L - (int)m.polya_max + (int)h.tail;  // transcript.go:283
     h.nb = 0;
@@ -254,7 +254,7 @@ __device__ __forceinline__ MolCtx make_ctx(const DevModel &m, const DevTranscrip
     return c;
 }
 
-__global__ void __launch_bounds__(FRAG_THREADS)
+__global__ void __launch_bounds__(FRAG_THREADS, 10)
 k_fragment(const __grid_constant__ DevModel m, DevTranscripts tr, uint64_t n_mol, FragOut o, uint32_t hist_s_n) {
     extern __shared__ unsigned int hist_s[];  // [hist_s_n] after-frag bins from `low`, then [polya_max+1]
     unsigned int *hist_pa = hist_s + hist_s_n;
@@ -262,7 +262,12 @@ k_fragment(const __grid_constant__ DevModel m, DevTranscripts tr, uint64_t n_mol
     __syncthreads();
     uint64_t g = (uint64_t)blockIdx.x * FRAG_THREADS + threadIdx.x;
     if (g < n_mol) {
-        uint32_t t = upper_bound_u64(tr.mol_off, tr.n + 1, g) - 1;
+        // molecule -> transcript: the warp's first lane searches; a warp rarely spans more than a few transcripts
+        const uint64_t g0 = g - (threadIdx.x & 31);
+        uint32_t t = 0;
+        if ((threadIdx.x & 31) == 0) t = upper_bound_u64(tr.mol_off, tr.n + 1, g0) - 1;
+        t = __shfl_sync(__activemask(), t, 0);
+        while (tr.mol_off[t + 1] <= g) t++;
         uint64_t mol = g - tr.mol_off[t];
         MolCtx c = make_ctx(m, tr, t);
         Header h = mol_header(m, c, mol);
@@ -384,7 +389,8 @@ int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr
     if (n_mol == 0) return 0;
     FragOut o{fb.keys, fb.cap, fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, fb.long_cap, fb.long_count,
               fb.error, fb.q_a, fb.q_b, fb.q_cap, fb.q_count};
-    uint32_t hist_s_n = frag_hist_bins(m);
+    // after_* methods only queue intervals here (k_intervals owns the after-fragmentation histogram)
+    uint32_t hist_s_n = m.method <= RLSIM_AFTER_NOPRIM_DOUBLE ? 0 : frag_hist_bins(m);
     size_t smem = ((size_t)hist_s_n + m.polya_max + 1) * 4;
     if (smem > 48 * 1024) { hist_s_n = 0; smem = ((size_t)m.polya_max + 1) * 4; }
     if (smem > 48 * 1024) return RLSIM_E_UNSUPPORTED;

@@ -158,7 +158,7 @@ __device__ __forceinline__ uint64_t amplify(const PxStream &stream, uint64_t c, 
 }
 
 constexpr int PCR_THREADS = 128;
-__global__ void __launch_bounds__(PCR_THREADS, 5)
+__global__ void __launch_bounds__(PCR_THREADS, 9)
 k_pcr(const __grid_constant__ DevModel m, DevTranscripts tr, DevSpecies sp, int *error) {
     uint64_t i = (uint64_t)blockIdx.x * PCR_THREADS + threadIdx.x;
     const bool live = i < sp.n;

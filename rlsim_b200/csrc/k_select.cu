@@ -17,7 +17,7 @@ namespace rl {
 
 // ---------------------------------------------------------------- target lengths
 constexpr int TGT_THREADS = 256;
-__global__ void __launch_bounds__(TGT_THREADS)
+__global__ void __launch_bounds__(TGT_THREADS, 4)
 k_target(const __grid_constant__ DevModel m, uint64_t first, uint64_t n, unsigned long long *__restrict__ hist, uint32_t hist_n,
          uint32_t smem_bins) {
     extern __shared__ unsigned int hs[];

@@ -85,6 +85,31 @@ struct PxCursor {
     __device__ __forceinline__ double u01_open() { return px_u01_open(next64()); }
 };
 
+// Sequential cursor whose first three blocks (six draws) are generated up front, in convergent code: the header
+// draws of a molecule (poly-A, component, Poisson) are consumed inside data-dependent loops where generating a
+// block on demand runs with a fraction of the warp.  Draws beyond the sixth fall back to on-demand blocks.
+struct PxCursor3 {
+    PxStream s;
+    uint32_t cur;
+    uint64_t d0, d1, d2, d3, d4, d5;  // scalars, selected with predicated moves (no local-memory array)
+    PxBlock blk;
+    __device__ __forceinline__ PxCursor3(const PxStream &st) : s(st), cur(0) {
+        PxBlock a = s.block(0), b = s.block(1), c = s.block(2);
+        d0 = px_lo64(a); d1 = px_hi64(a); d2 = px_lo64(b); d3 = px_hi64(b); d4 = px_lo64(c); d5 = px_hi64(c);
+    }
+    __device__ __forceinline__ uint64_t next64() {
+        uint32_t d = cur++;
+        if (d >= 6) {
+            if ((d & 1u) == 0u) blk = s.block(d >> 1);
+            return (d & 1u) ? px_hi64(blk) : px_lo64(blk);
+        }
+        uint64_t lo = d < 2 ? d0 : (d < 4 ? d2 : d4), hi = d < 2 ? d1 : (d < 4 ? d3 : d5);
+        return (d & 1u) ? hi : lo;
+    }
+    __device__ __forceinline__ double u01() { return px_u01(next64()); }
+    __device__ __forceinline__ double u01_open() { return px_u01_open(next64()); }
+};
+
 // random-access 64-bit draw d of a stream
 __device__ __forceinline__ uint64_t px_draw64(const PxStream &s, uint64_t d) {
     PxBlock b = s.block((uint32_t)(d >> 1));

@@ -11,10 +11,10 @@
 
 namespace rl {
 
-__device__ __forceinline__ double px_normal(PxCursor &c) { return det_ndtri(c.u01_open()); }
-__device__ __forceinline__ double px_expo(PxCursor &c) { return -det_log(c.u01_open()); }
+template <class Cur> __device__ __forceinline__ double px_normal(Cur &c) { return det_ndtri(c.u01_open()); }
+template <class Cur> __device__ __forceinline__ double px_expo(Cur &c) { return -det_log(c.u01_open()); }
 
-static __device__ __noinline__ double px_gamma(PxCursor &cur, double shape) {
+template <class Cur> static __device__ __noinline__ double px_gamma(Cur &cur, double shape) {
     double a = shape < 1.0 ? shape + 1.0 : shape;
     double d = a - 1.0 / 3.0;
     double c = 1.0 / sqrt(9.0 * d);
@@ -33,7 +33,7 @@ static __device__ __noinline__ double px_gamma(PxCursor &cur, double shape) {
 }
 
 // MixComp.SampleLength, target_mix.go:55-72
-static __device__ __noinline__ uint32_t px_comp_len(PxCursor &cur, const rlsim_mixcomp &c) {
+template <class Cur> static __device__ __noinline__ uint32_t px_comp_len(Cur &cur, const rlsim_mixcomp &c) {
     if (c.low == c.high) return (uint32_t)c.low;
     double l = (double)c.low, h = (double)c.high;
     for (;;) {
@@ -61,7 +61,7 @@ static __device__ __noinline__ uint32_t px_comp_len(PxCursor &cur, const rlsim_m
 }
 
 // TargetMix.SampleMixComp, target_mix.go:232-245 (declaration order)
-__device__ __forceinline__ int px_mix_comp(PxCursor &cur, const rlsim_mixcomp *c, int n) {
+template <class Cur> __device__ __forceinline__ int px_mix_comp(Cur &cur, const rlsim_mixcomp *c, int n) {
     double tot = 0.0;
     for (int i = 0; i < n; i++) tot = tot + c[i].weight;
     double u = cur.u01() * tot;
@@ -74,7 +74,7 @@ __device__ __forceinline__ int px_mix_comp(PxCursor &cur, const rlsim_mixcomp *c
 }
 
 // RawTarget.SampleMixLen, raw_target.go:148-154: cumulative probabilities in file order, first csum > u
-static __device__ __noinline__ uint32_t px_raw_len(PxCursor &cur, const DevModel &m) {
+template <class Cur> static __device__ __noinline__ uint32_t px_raw_len(Cur &cur, const DevModel &m) {
     double tot = 0.0;
     for (int i = 0; i < m.n_raw; i++) tot = tot + m.raw_prob[i];
     double u = cur.u01() * tot;
@@ -86,7 +86,7 @@ static __device__ __noinline__ uint32_t px_raw_len(PxCursor &cur, const DevModel
     return m.raw_len[m.n_raw - 1];
 }
 
-static __device__ __noinline__ int32_t px_poisson(PxCursor &cur, double mean) {
+template <class Cur> static __device__ __noinline__ int32_t px_poisson(Cur &cur, double mean) {
     if (mean < 12.0) {
         double g = det_exp(-mean), t = 1.0;
         int32_t em = -1;
