@@ -23,7 +23,7 @@ struct DBuf {
     ~DBuf() { release(); }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
     cudaError_t ensure(size_t want) {  // contents are NOT preserved; grows with 1/8 slack so sizes that
-        if (want <= n) return cudaSuccess;  // fluctuate from run to run do not reallocate every time
+        if (p && want <= n) return cudaSuccess;  // fluctuate from run to run do not reallocate every time
         release();
         size_t cap = want + want / 8 + 16;
         cudaError_t e = cudaMalloc(&p, cap * sizeof(T));
@@ -33,7 +33,7 @@ struct DBuf {
     }
     // grow to at least `want` elements keeping the first `used` (device-to-device copy on `st`)
     cudaError_t grow_preserve(size_t want, size_t used, cudaStream_t st) {
-        if (want <= n) return cudaSuccess;
+        if (p && want <= n) return cudaSuccess;
         size_t cap = want + want / 2 + 16;
         T *q = nullptr;
         cudaError_t e = cudaMalloc(&q, cap * sizeof(T));

@@ -244,3 +244,45 @@ def test_target_sampling_partition(gpu):
         h.set_target_hist(nz.astype(np.uint32), acc[nz])
         st, sw = h.stats(), whole.stats()
         assert (st.low, st.high, st.n_requested) == (sw.low, sw.high, sw.n_requested)
+
+
+def test_batched_add_transcripts_equals_single_call(gpu):
+    """The Go shim feeds rlsim_add_transcripts in batches: device arrays grow keeping earlier
+    batches, the result is that of one call."""
+    args = util.parse(["-n", "30000", "-c", "7", "-si", "21"])
+    names, seqs, levels = util.synth_transcriptome(90, seed=12, mean_len=1500, hi=6000, total_molecules=25000, non_acgt=0.002)
+    one = util.run_gpu(gpu, args, names, seqs, levels)
+    h = gpu.Handle(0)
+    h.set_model(args.to_params())
+    h.sample_target(args.req_frags)
+    for a, b in ((0, 1), (1, 37), (37, 38), (38, 90)):
+        h.add_transcripts(seqs[a:b], levels[a:b])
+    h.build_library()
+    h.sample()
+    for k in ("tr", "start", "end", "count0", "count"):
+        assert np.array_equal(one.species()[k], h.species()[k]), k
+    for k in ("tr", "start", "end", "minus", "id"):
+        assert np.array_equal(one.sampled()[k], h.sampled()[k]), k
+    assert one.fasta(names) == h.fasta(names)
+    # a second library on the same handle (buffers reused) gives the same answer again
+    h.clear_transcripts()
+    h.set_model(args.to_params())
+    h.sample_target(args.req_frags)
+    h.add_transcripts(seqs, levels)
+    h.build_library()
+    h.sample()
+    assert one.fasta(names) == h.fasta(names)
+
+
+def test_degenerate_inputs(oracle, gpu):
+    """Nothing expressed; a single molecule; primer length 1 and 12 (LUT in global memory); fixed-length tails."""
+    names, seqs, levels = util.synth_transcriptome(5, seed=2, mean_len=800, hi=2000, total_molecules=100)
+    args = util.parse(["-n", "100", "-si", "1"])
+    h = util.run_gpu(gpu, args, names, seqs, [0] * 5)
+    st = h.stats()
+    assert (st.n_molecules, st.n_fragments, st.n_species, st.n_sampled, st.pool_total) == (0, 0, 0, 0, 0)
+    assert sum(h.hist_dict(gpu.H_MISSING, 400).values()) == 100 and h.fasta(names) == b""
+    _compare(oracle, gpu, ["-n", "50"], seqs_override=(names, seqs, [1, 0, 0, 0, 0]))
+    _compare(oracle, gpu, ["-n", "2000", "-k", "1"], seqs_override=(names, seqs, levels))
+    _compare(oracle, gpu, ["-n", "2000", "-k", "12", "-p", "9.5"], seqs_override=(names, seqs, levels))
+    _compare(oracle, gpu, ["-n", "2000", "-a", "1:n:(40,5,33,33)", "-d", "1:n:(120,10,120,120)"], seqs_override=(names, seqs, levels))
