@@ -47,12 +47,18 @@ __device__ __forceinline__ double gc_eff(const DevModel &m, uint32_t gc_count, u
 }
 
 // 1/x for the inversion recurrence (x <= 44 while n*min(p,q) < 10): correctly rounded reciprocals, spec 4.4
-__constant__ double RCP_TABLE[64] = {
-    0.0,       1.0 / 1,  1.0 / 2,  1.0 / 3,  1.0 / 4,  1.0 / 5,  1.0 / 6,  1.0 / 7,  1.0 / 8,  1.0 / 9,  1.0 / 10, 1.0 / 11, 1.0 / 12,
-    1.0 / 13,  1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25,
-    1.0 / 26,  1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32, 1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37, 1.0 / 38,
-    1.0 / 39,  1.0 / 40, 1.0 / 41, 1.0 / 42, 1.0 / 43, 1.0 / 44, 1.0 / 45, 1.0 / 46, 1.0 / 47, 1.0 / 48, 1.0 / 49, 1.0 / 50, 1.0 / 51,
-    1.0 / 52,  1.0 / 53, 1.0 / 54, 1.0 / 55, 1.0 / 56, 1.0 / 57, 1.0 / 58, 1.0 / 59, 1.0 / 60, 1.0 / 61, 1.0 / 62, 1.0 / 63};
+__constant__ double RCP_TABLE[128] = {     0.0, 1.0 / 1, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 /
+    8, 1.0 / 9, 1.0 / 10, 1.0 / 11, 1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19,
+    1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0
+    / 31, 1.0 / 32, 1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37, 1.0 / 38, 1.0 / 39, 1.0 / 40, 1.0 / 41, 1.0 /
+    42, 1.0 / 43, 1.0 / 44, 1.0 / 45, 1.0 / 46, 1.0 / 47, 1.0 / 48, 1.0 / 49, 1.0 / 50, 1.0 / 51, 1.0 / 52, 1.0 / 53,
+    1.0 / 54, 1.0 / 55, 1.0 / 56, 1.0 / 57, 1.0 / 58, 1.0 / 59, 1.0 / 60, 1.0 / 61, 1.0 / 62, 1.0 / 63, 1.0 / 64, 1.0
+    / 65, 1.0 / 66, 1.0 / 67, 1.0 / 68, 1.0 / 69, 1.0 / 70, 1.0 / 71, 1.0 / 72, 1.0 / 73, 1.0 / 74, 1.0 / 75, 1.0 /
+    76, 1.0 / 77, 1.0 / 78, 1.0 / 79, 1.0 / 80, 1.0 / 81, 1.0 / 82, 1.0 / 83, 1.0 / 84, 1.0 / 85, 1.0 / 86, 1.0 / 87,
+    1.0 / 88, 1.0 / 89, 1.0 / 90, 1.0 / 91, 1.0 / 92, 1.0 / 93, 1.0 / 94, 1.0 / 95, 1.0 / 96, 1.0 / 97, 1.0 / 98, 1.0
+    / 99, 1.0 / 100, 1.0 / 101, 1.0 / 102, 1.0 / 103, 1.0 / 104, 1.0 / 105, 1.0 / 106, 1.0 / 107, 1.0 / 108, 1.0 /
+    109, 1.0 / 110, 1.0 / 111, 1.0 / 112, 1.0 / 113, 1.0 / 114, 1.0 / 115, 1.0 / 116, 1.0 / 117, 1.0 / 118, 1.0 / 119,
+    1.0 / 120, 1.0 / 121, 1.0 / 122, 1.0 / 123, 1.0 / 124, 1.0 / 125, 1.0 / 126, 1.0 / 127};
 
 // AmplifyFragment, thermocycler.go:133-147: `cycles` times c <- c + Binomial(c, pp), every attempt from one whole
 // Philox block of the species' own stream (spec 4.4: BINV inversion below c*min(p,q) = 10, BTRS above).
@@ -65,6 +71,9 @@ __constant__ double RCP_TABLE[64] = {
 // (lanes without a species pass live = false).  The draws of a species depend only on its own block counter, so the
 // schedule does not change the result: it is the sequence the oracle produces cycle by cycle.
 constexpr int PCR_SLOW_BATCH = 10;
+#ifndef PCR_BINV_MAX
+#define PCR_BINV_MAX 10.0
+#endif
 __device__ __forceinline__ uint64_t amplify(const PxStream &stream, uint64_t c, double pp, int cycles, bool live, bool &overflow) {
     if (!(pp > 0.0) || c == 0) live = false;  // Binomial(c, 0) = 0, Binomial(0, .) = 0: nothing to draw
     if (live && pp >= 1.0) {                  // Binomial(c, 1) = c
@@ -91,7 +100,7 @@ __device__ __forceinline__ uint64_t amplify(const PxStream &stream, uint64_t c, 
         if (runnable) {
             if (!have_setup) {
                 nd = (double)c;
-                inv_mode = nd * p < 10.0;
+                inv_mode = nd * p < PCR_BINV_MAX;
                 if (inv_mode) {
                     qn = det_exp(nd * lq);
                     bound = nd * p + 10.0 * sqrt(nd * p * q + 1.0);
@@ -138,13 +147,34 @@ __device__ __forceinline__ uint64_t amplify(const PxStream &stream, uint64_t c, 
         const unsigned pend = __ballot_sync(0xffffffffu, pending);
         const unsigned run = __ballot_sync(0xffffffffu, cyc < cycles && !pending);
         if (pend != 0u && (__popc(pend) >= PCR_SLOW_BATCH || run == 0u)) {
-            if (pending) {  // exact acceptance test
-                double lv = det_log(v * alpha / (a / (us * us) + b));
-                double ub = (mm + 0.5) * det_log((mm + 1.0) / (r * (nd - mm + 1.0))) +
-                            (nd + 1.0) * det_log((nd - mm + 1.0) / (nd - k + 1.0)) +
-                            (k + 0.5) * det_log(r * (nd - k + 1.0) / (k + 1.0)) + det_logfact_tail(mm) +
-                            det_logfact_tail(nd - mm) - det_logfact_tail(k) - det_logfact_tail(nd - k);
-                if (lv <= ub) {
+            if (pending) {
+                // Acceptance test  log(v * alpha / (a/us^2 + b))  <=  ub(k).  Decision first in FP32: every logarithm of ub
+                // has an argument 1 + d with small d, d is formed from an exactly cancelling FP64 numerator, so the FP32
+                // evaluation errs by less than ~5e-7 of the sum of the term magnitudes; when the gap is inside a 4x wider
+                // margin the exact FP64 test of the spec decides.  Same decisions as the spec, a fraction of the FP64 work.
+                const double t1 = r * (nd - mm + 1.0), t3 = k + 1.0, t2 = nd - k + 1.0;
+                const float d1 = (float)((mm + 1.0) - t1) / (float)t1;         // (m+1)/(r(n-m+1)) - 1
+                const float d2 = (float)(k - mm) / (float)t2;                  // (n-m+1)/(n-k+1) - 1
+                const float d3 = (float)(r * t2 - t3) / (float)t3;             // r(n-k+1)/(k+1) - 1
+                const float f1 = (float)(mm + 0.5) * log1pf(d1), f2 = (float)(nd + 1.0) * log1pf(d2), f3 = (float)(k + 0.5) * log1pf(d3);
+                const float ft = (float)(det_logfact_tail(mm) + det_logfact_tail(nd - mm)) - (float)(det_logfact_tail(k) + det_logfact_tail(nd - k));
+                const float lvf = logf((float)(v * alpha) / (float)(a / (us * us) + b));
+                const float gap = lvf - (f1 + f2 + f3 + ft);
+                // 2e-6 * magnitudes: FP32 evaluation error (<= ~5e-7 of them); 2e-15 * coefficients: the spec's own FP64 quotient
+                // rounding (1.1e-16 per argument) amplified by the coefficients, which matters once counts pass ~1e9
+                const float margin = 2e-6f * (fabsf(f1) + fabsf(f2) + fabsf(f3) + fabsf(lvf) + 1.0f) + (float)(2e-15 * (mm + nd + k));
+                bool accept;
+                if (fabsf(gap) > margin) {
+                    accept = gap < 0.0f;
+                } else {  // exact acceptance test of the spec
+                    double lv = det_log(v * alpha / (a / (us * us) + b));
+                    double ub = (mm + 0.5) * det_log((mm + 1.0) / (r * (nd - mm + 1.0))) +
+                                (nd + 1.0) * det_log((nd - mm + 1.0) / (nd - k + 1.0)) +
+                                (k + 0.5) * det_log(r * (nd - k + 1.0) / (k + 1.0)) + det_logfact_tail(mm) +
+                                det_logfact_tail(nd - mm) - det_logfact_tail(k) - det_logfact_tail(nd - k);
+                    accept = lv <= ub;
+                }
+                if (accept) {
                     uint64_t res = (uint64_t)k;
                     uint64_t nc = c + (flip ? c - res : res);
                     if (nc < c) { overflow = true; cyc = cycles; }

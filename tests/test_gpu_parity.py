@@ -286,3 +286,20 @@ def test_degenerate_inputs(oracle, gpu):
     _compare(oracle, gpu, ["-n", "2000", "-k", "1"], seqs_override=(names, seqs, levels))
     _compare(oracle, gpu, ["-n", "2000", "-k", "12", "-p", "9.5"], seqs_override=(names, seqs, levels))
     _compare(oracle, gpu, ["-n", "2000", "-a", "1:n:(40,5,33,33)", "-d", "1:n:(120,10,120,120)"], seqs_override=(names, seqs, levels))
+
+
+def test_amplify_large_sample_bit_exact(oracle, h0):
+    """400 000 species x 15 cycles across all count regimes: the FP32 pre-decision of the BTRS acceptance test must
+    never disagree with the exact FP64 test of the spec (a single wrong decision changes a copy number)."""
+    rng = np.random.default_rng(2024)
+    n = 400_000
+    tse = rng.integers(0, 2**31, size=(n, 3)).astype(np.uint32)
+    n0 = np.concatenate([rng.integers(1, 4, n // 2), rng.integers(20, 5000, n // 4),
+                         np.floor(10.0 ** rng.uniform(4, 12.5, n - n // 2 - n // 4))]).astype(np.uint64)
+    p = np.concatenate([rng.uniform(0.05, 0.95, n - 1000), rng.uniform(0.4999, 0.5001, 500), rng.uniform(0, 0.01, 500)])
+    got = h0.probe_amplify(5, tse, n0, p, 15)
+    L = oracle.lib()
+    idx = np.concatenate([np.arange(0, n, 7), np.arange(n - 1000, n)])  # oracle on a 1/7 subsample + all edge probabilities
+    want = np.array([L.orc_px_binomial(5, int(tse[i, 0]), int(tse[i, 1]), int(tse[i, 2]), int(n0[i]), float(p[i]), 15) for i in idx],
+                    dtype=np.uint64)
+    assert np.array_equal(got[idx], want)
