@@ -166,6 +166,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    cpus = shard.bind_to_gpu_numa_node(local_rank) if world > 1 else None  # before any pinned allocation
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -323,7 +324,8 @@ def main():
         "vs_baseline": None, "dtype": "f64+u64", "data": "synthetic",
         "config": {"workload": "C3 synthetic human-transcriptome-scale: %d transcripts / %d nt / %d molecules per GPU, %d requested "
                                "fragments in total, 15 cycles, after_prim_double" % (n_tr, int(bases.numel()), int(st.n_molecules), n_frags_global),
-                   "flags": " ".join(C3_FLAGS), "scale": opts.scale, "sharding": "contiguous transcripts per rank; allgather of per-length totals",
+                   "flags": " ".join(C3_FLAGS), "scale": opts.scale, "sharding": "contiguous transcripts per rank; allgather of per-length totals + all-to-all of drawn copy ranks",
+                   "cpu_binding_rank0": (sorted(cpus)[0], sorted(cpus)[-1], len(cpus)) if cpus else None,
                    "l2": "inputs (0.45 GB bases + 7 GB prefix sums per GPU) exceed the 126 MB L2; no explicit flush",
                    "species_per_gpu": int(st.n_species), "fragments_after_fragmentation_per_gpu": int(st.n_fragments),
                    "pool_total_rank0": int(st.pool_total)},

@@ -7,8 +7,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <vector>
 #include "kernels.cuh"
 
@@ -103,8 +105,17 @@ struct rlsim_handle {
     uint64_t n_mol = 0, total_padded = 0;
     double sum_expr = 0, sum_expr_len = 0;  // for the fragment-capacity estimate
     bool mol_off_valid = false;
+    std::vector<uint64_t> h_mol_off;        // exclusive scan of the expression levels [n+1]
+    // eager pipeline: while later chunks are still being copied, earlier chunks are already fragmented and amplified
+    uint32_t eager_upto = 0;                // transcripts [0, eager_upto) are done under the current model
+    bool eager_failed = false;              // a buffer estimate was too small: the monolithic path takes over
+    bool eager_started = false;             // counters / histograms zeroed for this transcript set
+    bool eager_pcr = false;                 // species counts already amplified (consumed by the next rlsim_pcr)
+    uint64_t eager_keys = 0, eager_sp = 0;  // running fragment-key / species counts
+    bool len_eff_ready = false;
     DBuf<uint8_t> d_bases;
-    DBuf<uint32_t> d_packed, d_nmask, d_gc, d_len;
+    DBuf<uint32_t> d_packed, d_nmask, d_len;
+    DBuf<uint2> d_gc;  // GC groups: {prefix count, bit mask} per 32 bases
     DBuf<uint64_t> d_off, d_expr, d_mol_off, d_Cf, d_Cr;  // coarse prefix sums
     DBuf<uint32_t> d_Ff, d_Fr;                          // fine (in-block) prefix sums
     uint32_t prefix_upto = 0;  // transcripts [0, prefix_upto) have valid priming prefix sums for the current model
@@ -291,15 +302,152 @@ int launch_prefix_range(rlsim_handle *h, uint32_t t0, uint32_t t1) {
     return 0;
 }
 
+int cub_temp(rlsim_handle *h, size_t bytes);
+int check_device_error(rlsim_handle *h);
+
+void eager_reset(rlsim_handle *h) {
+    h->eager_upto = 0; h->eager_failed = h->eager_started = h->eager_pcr = false; h->eager_keys = h->eager_sp = 0;
+}
+
+double frag_denominator(rlsim_handle *h) {  // expected fragments per molecule <= L / denominator + 1
+    int method = h->p.frag_method;
+    double loc = h->raw_location;
+    if (h->p.n_target > 0) {
+        double lmin = 1e300;
+        for (int i = 0; i < h->p.n_target; i++) lmin = std::min(lmin, h->p.target[i].location);
+        loc = lmin;
+    }
+    if (!(loc > 0)) loc = 1.0;
+    return method == RLSIM_PRIM_JUMP ? (double)std::max<uint64_t>(h->low, 1)
+         : method == RLSIM_PRE_PRIM ? loc
+         : (h->p.frag_param == 0 ? 2.0 * loc : (double)h->p.frag_param);
+}
+
+// Techne.CalcLengthEff table on the device: the host's own (rlsim_set_len_eff) or the library's
+int ensure_len_eff(rlsim_handle *h) {
+    if (h->len_eff_ready) return 0;
+    uint32_t nle = (uint32_t)(h->high - h->low + 1);
+    CK(h, h->d_len_eff.ensure(nle));
+    if (!h->h_len_eff.empty()) {
+        if (h->len_eff_low != h->low || h->len_eff_high != h->high) FAIL(h, RLSIM_E_ARG, "length-efficiency table does not span [low, high]");
+        CK(h, cudaMemcpyAsync(h->d_len_eff.p, h->h_len_eff.data(), (size_t)nle * 8, cudaMemcpyHostToDevice, h->st));
+    } else {
+        launch_len_eff(h->st, make_model(h), h->d_len_eff.p);
+    }
+    h->len_eff_ready = true;
+    return 0;
+}
+
+bool eager_possible(rlsim_handle *h, uint32_t n0) {
+    const bool disabled = getenv("RLSIM_NO_EAGER") != nullptr;  // diagnostic switch: always take the monolithic path
+    return !disabled && h->have_model && h->p.frag_method <= RLSIM_AFTER_NOPRIM_DOUBLE && (h->p.n_target > 0 || h->have_target) &&
+           h->low > 0 && h->high >= h->low && !h->eager_failed && h->eager_upto == n0;
+}
+
+// Fragment, dedup and amplify the transcripts [t0, t1) of a chunk whose ingest + prefix sums are already queued on
+// the compute stream.  The host waits on the compute stream only; the copy stream keeps feeding later chunks.
+int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
+    int rc;
+    const bool trace = getenv("RLSIM_TRACE") != nullptr;
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tt0 = now_ms();
+    double tt1 = 0, tt2 = 0, tt3 = 0;
+    const uint64_t g0 = h->h_mol_off[t0], g1 = h->h_mol_off[t1];
+    if (!h->eager_started) {  // first chunk: histograms, counters
+        h->eager_started = true;
+        uint32_t hist_frag_n = (uint32_t)h->high + 1, hist_pa_n = h->polya_max + 1;
+        CK(h, h->d_hist_frag.ensure(hist_frag_n)); CK(h, h->d_hist_polya.ensure(hist_pa_n));
+        CK(h, cudaMemsetAsync(h->d_hist_frag.p, 0, (size_t)hist_frag_n * 8, h->st));
+        CK(h, cudaMemsetAsync(h->d_hist_polya.p, 0, (size_t)hist_pa_n * 8, h->st));
+        CK(h, cudaMemsetAsync(h->d_counters.p, 0, 4 * 8, h->st));
+        CK(h, cudaMemsetAsync(h->d_error.p, 0, 4, h->st));
+    }
+    if (g1 == g0) { h->eager_upto = t1; return 0; }
+    double sel = 0, se = 0;
+    for (uint32_t t = t0; t < t1; t++) { se += (double)h->h_expr[t]; sel += (double)h->h_expr[t] * (double)h->h_len[t]; }
+    const uint64_t est = (uint64_t)((sel / frag_denominator(h) + se) * 1.25) + 8192;
+    CK(h, h->d_keys.grow_preserve(h->eager_keys + est, h->eager_keys, h->st));
+    CK(h, h->d_q_a.ensure(est)); CK(h, h->d_q_b.ensure(est));
+    const uint32_t long_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((g1 - g0) / 16, 4096), 1u << 24);
+    CK(h, h->d_long_list.ensure(long_cap)); CK(h, h->d_long_hi.ensure(long_cap));
+    CK(h, cudaMemsetAsync(h->d_counters.p + 2, 0, 8, h->st));
+    CK(h, cudaMemsetAsync(h->d_long_count.p, 0, 4, h->st));
+    DevModel m = make_model(h);
+    DevTranscripts tr = make_tr(h);
+    FragBuffers fb{h->d_keys.p, h->d_keys.n, h->d_counters.p, h->d_hist_frag.p, h->d_hist_polya.p, h->d_long_list.p, h->d_long_hi.p,
+                   long_cap, h->d_long_count.p, h->d_error.p, h->d_q_a.p, h->d_q_b.p, h->d_q_a.n, h->d_counters.p + 2};
+    if ((rc = launch_fragment(h->st, m, tr, g0, g1, fb))) { h->eager_failed = true; return 0; }
+    unsigned int n_long = 0;
+    unsigned long long n_q = 0, cnt = 0;
+    CK(h, cudaMemcpyAsync(&n_long, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaMemcpyAsync(&n_q, h->d_counters.p + 2, 8, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    tt1 = now_ms();
+    if (n_long > long_cap || n_q > h->d_q_a.n) { h->eager_failed = true; return 0; }
+    launch_intervals(h->st, m, tr, fb, n_q);
+    launch_fragment_long(h->st, m, tr, fb, n_long);
+    h->launches[RLSIM_T_FRAGMENT] += 1 + (n_long ? 1 : 0); h->launches[RLSIM_T_INTERVALS] += n_q ? 1 : 0;
+    CK(h, cudaMemcpyAsync(&cnt, h->d_counters.p, 8, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    tt2 = now_ms();
+    CK(h, cudaGetLastError());
+    if (cnt > h->d_keys.n) { h->eager_failed = true; return 0; }
+    const uint64_t nf = cnt - h->eager_keys;
+    if (nf >= (1ull << 31)) { h->eager_failed = true; return 0; }
+    uint64_t runs = 0;
+    if (nf) {
+        // species of this chunk: sort + run-length encode its keys (transcript.go:156-215), appended to the species table
+        CK(h, h->d_keys_sorted.ensure(nf)); CK(h, h->d_uniq.ensure(nf));
+        const uint64_t need = h->eager_sp + nf;
+        CK(h, h->d_sp_count0.grow_preserve(need, h->eager_sp, h->st));
+        int end_bit = (int)std::min<uint32_t>(64, 24 + bits_for(h->total_padded));
+        size_t tb = 0;
+        CK(h, cub::DeviceRadixSort::SortKeys(nullptr, tb, h->d_keys.p + h->eager_keys, h->d_keys_sorted.p, (int)nf, 0, end_bit, h->st));
+        if ((rc = cub_temp(h, tb))) return rc;
+        CK(h, cub::DeviceRadixSort::SortKeys(h->d_cub.p, tb, h->d_keys.p + h->eager_keys, h->d_keys_sorted.p, (int)nf, 0, end_bit, h->st));
+        tb = 0;
+        CK(h, cub::DeviceRunLengthEncode::Encode(nullptr, tb, h->d_keys_sorted.p, h->d_uniq.p, h->d_sp_count0.p + h->eager_sp,
+                                                 h->d_counters.p + 1, (int)nf, h->st));
+        if ((rc = cub_temp(h, tb))) return rc;
+        CK(h, cub::DeviceRunLengthEncode::Encode(h->d_cub.p, tb, h->d_keys_sorted.p, h->d_uniq.p, h->d_sp_count0.p + h->eager_sp,
+                                                 h->d_counters.p + 1, (int)nf, h->st));
+        unsigned long long r64 = 0;
+        CK(h, cudaMemcpyAsync(&r64, h->d_counters.p + 1, 8, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaStreamSynchronize(h->st));
+        tt3 = now_ms();
+        runs = r64;
+        h->launches[RLSIM_T_DEDUP] += 3 + radix_launches(end_bit);
+        const uint64_t ns = h->eager_sp + runs;
+        CK(h, h->d_sp_tr.grow_preserve(ns, h->eager_sp, h->st)); CK(h, h->d_sp_start.grow_preserve(ns, h->eager_sp, h->st));
+        CK(h, h->d_sp_len.grow_preserve(ns, h->eager_sp, h->st)); CK(h, h->d_sp_count.grow_preserve(ns, h->eager_sp, h->st));
+        CK(h, h->d_sp_eff.grow_preserve(ns, h->eager_sp, h->st)); CK(h, h->d_sp_gc.grow_preserve(ns, h->eager_sp, h->st));
+        DevSpecies sp{};
+        sp.n = runs;
+        sp.tr = h->d_sp_tr.p + h->eager_sp; sp.start = h->d_sp_start.p + h->eager_sp; sp.len = h->d_sp_len.p + h->eager_sp;
+        sp.count0 = h->d_sp_count0.p + h->eager_sp; sp.count = h->d_sp_count.p + h->eager_sp;
+        sp.eff = h->keep_debug ? h->d_sp_eff.p + h->eager_sp : nullptr; sp.gc = h->keep_debug ? h->d_sp_gc.p + h->eager_sp : nullptr;
+        launch_decode_species(h->st, tr, h->d_uniq.p, sp);
+        if ((rc = ensure_len_eff(h))) return rc;
+        m = make_model(h);  // picks up the length-efficiency table pointer
+        launch_pcr(h->st, m, tr, sp, h->d_error.p);  // thermocycler.go:106-147 for this chunk's species
+        h->launches[RLSIM_T_PCR] += 1;
+        CK(h, cudaGetLastError());
+    }
+    if (trace) fprintf(stderr, "[rlsim trace]   layout+fragment %.3f, intervals %.3f, sort+rle %.3f, enqueue pcr %.3f ms (%llu frags, %llu species)\n", tt1 - tt0, tt2 - tt1, tt3 - tt2, now_ms() - tt3, (unsigned long long)nf, (unsigned long long)runs);
+    h->eager_keys = cnt;
+    h->eager_sp += runs;
+    h->eager_upto = t1;
+    return 0;
+}
+
 // everything that needs the complete transcript set: molecule offsets, remaining prefix sums
 int finalize(rlsim_handle *h) {
     uint32_t n = (uint32_t)h->h_len.size();
     if (!h->mol_off_valid) {
-        std::vector<uint64_t> mol_off(n + 1, 0);
-        for (uint32_t t = 0; t < n; t++) mol_off[t + 1] = mol_off[t] + h->h_expr[t];
-        h->n_mol = mol_off[n];
+        if (h->h_mol_off.empty()) h->h_mol_off.push_back(0);
+        h->n_mol = h->h_mol_off[n];
         CK(h, h->d_mol_off.ensure(n + 1));
-        CK(h, cudaMemcpyAsync(h->d_mol_off.p, mol_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, h->st));
+        CK(h, cudaMemcpyAsync(h->d_mol_off.p, h->h_mol_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, h->st));
         CK(h, cudaStreamSynchronize(h->st));
         h->mol_off_valid = true;
     }
@@ -384,6 +532,8 @@ int rlsim_set_model(rlsim_handle *h, const rlsim_params *p) {
     h->polya_max = (uint32_t)mx;
     h->prefix_upto = 0;
     h->lut_valid = false;
+    h->len_eff_ready = false;
+    eager_reset(h);
     if (p->n_target > 0) {
         mix_minmax(p->target, p->n_target, &h->low, &h->high);  // target.go:67
         if (h->high >= (1u << 24)) FAIL(h, RLSIM_E_UNSUPPORTED, "maximum fragment length >= 2^24");
@@ -396,6 +546,9 @@ int rlsim_set_len_eff(rlsim_handle *h, const double *len_eff, uint64_t low, uint
     if (high < low) FAIL(h, RLSIM_E_ARG, "len_eff: high < low");
     h->h_len_eff.assign(len_eff, len_eff + (high - low + 1));
     h->len_eff_low = low; h->len_eff_high = high;
+    h->len_eff_ready = false;
+    h->eager_pcr = false;
+    if (h->eager_upto) { h->eager_upto = 0; h->eager_failed = true; }  // species already amplified with another table
     return 0;
 }
 
@@ -429,7 +582,7 @@ static int sample_target_range(rlsim_handle *h, uint64_t first, uint64_t count, 
     CK(h, cudaStreamSynchronize(h->st));
     h->req_frags = count;
     h->have_target = whole;  // a partial histogram must be completed with rlsim_set_target_hist
-    if (raw && whole) raw_target_finish(h);
+    if (raw && whole) { raw_target_finish(h); h->len_eff_ready = false; if (h->eager_upto) { h->eager_upto = 0; h->eager_failed = true; } }
     return 0;
 }
 
@@ -451,11 +604,15 @@ int rlsim_set_target_hist(rlsim_handle *h, const uint32_t *lengths, const uint64
     h->req_frags = 0;
     for (uint32_t i = 0; i < n; i++) { h->h_target[lengths[i]] += counts[i]; h->req_frags += counts[i]; }
     h->have_target = true;
-    if (h->p.n_target == 0) raw_target_finish(h);
+    if (h->p.n_target == 0) { raw_target_finish(h); h->len_eff_ready = false; if (h->eager_upto) { h->eager_upto = 0; h->eager_failed = true; } }
     return 0;
 }
 
-int rlsim_set_first_index(rlsim_handle *h, uint32_t first_index) { h->first_index = first_index; return 0; }
+int rlsim_set_first_index(rlsim_handle *h, uint32_t first_index) {
+    if (first_index != h->first_index && h->eager_upto) { h->eager_upto = 0; h->eager_failed = true; }  // streams are keyed by it
+    h->first_index = first_index;
+    return 0;
+}
 
 int rlsim_clear_transcripts(rlsim_handle *h) {
     cudaSetDevice(h->device);
@@ -464,6 +621,8 @@ int rlsim_clear_transcripts(rlsim_handle *h) {
     h->prefix_upto = 0; h->fragmented = h->amplified = h->sampled = false;
     h->n_mol = h->total_padded = h->n_frag = h->n_sp = h->n_out = h->pool_total = 0;
     h->sum_expr = h->sum_expr_len = 0; h->mol_off_valid = false;
+    h->h_mol_off.clear();
+    eager_reset(h);
     memset(h->ms, 0, sizeof h->ms);
     memset(h->launches, 0, sizeof h->launches);
     return 0;
@@ -478,64 +637,121 @@ int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t 
     const uint64_t nbytes = offsets[n] - offsets[0];
     if (h->h_off.empty()) h->h_off.push_back(0);
     std::vector<uint64_t> rel(n + 1);
-    for (uint32_t i = 0; i <= n; i++) rel[i] = offsets[i] - offsets[0];
-    for (uint32_t i = 0; i < n; i++) {
-        uint64_t L = rel[i + 1] - rel[i] + h->polya_max;
-        if (L >= (1ull << 32)) FAIL(h, RLSIM_E_UNSUPPORTED, "transcript longer than 2^32-1 bases");
-        h->h_srclen.push_back(rel[i + 1] - rel[i]);
-        h->h_expr.push_back(expr[i]);
-        h->h_len.push_back((uint32_t)L);
-        h->sum_expr += (double)expr[i];
-        h->sum_expr_len += (double)expr[i] * (double)L;
-        h->h_off.push_back(h->h_off.back() + ((L + 31) & ~31ull));
+    if (h->h_mol_off.empty()) h->h_mol_off.push_back(0);
+    h->h_srclen.resize(n0 + n); h->h_expr.resize(n0 + n); h->h_len.resize(n0 + n); h->h_off.resize(n0 + n + 1); h->h_mol_off.resize(n0 + n + 1);
+    {
+        const uint64_t o0 = offsets[0], pa = h->polya_max;
+        uint64_t *srclen = h->h_srclen.data() + n0, *ex = h->h_expr.data() + n0, *off = h->h_off.data() + n0;
+        uint32_t *len = h->h_len.data() + n0;
+        uint64_t *molo = h->h_mol_off.data() + n0;
+        double se = 0, sel = 0;
+        uint64_t too_long = 0;
+        rel[0] = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            const uint64_t r1 = offsets[i + 1] - o0, l = r1 - rel[i], L = l + pa;
+            rel[i + 1] = r1;
+            too_long |= L >> 32;
+            srclen[i] = l; ex[i] = expr[i]; len[i] = (uint32_t)L;
+            off[i + 1] = off[i] + ((L + 31) & ~31ull);
+            molo[i + 1] = molo[i] + expr[i];
+            se += (double)expr[i];
+            sel += (double)expr[i] * (double)L;
+        }
+        if (too_long) {
+            h->h_srclen.resize(n0); h->h_expr.resize(n0); h->h_len.resize(n0); h->h_off.resize(n0 + 1); h->h_mol_off.resize(n0 + 1);
+            FAIL(h, RLSIM_E_UNSUPPORTED, "transcript longer than 2^32-1 bases");
+        }
+        h->sum_expr += se; h->sum_expr_len += sel;
     }
     const uint32_t nn = n0 + n;
     const uint64_t old_total = h->total_padded, tot = h->h_off[nn];
     if (tot >= (1ull << 40)) FAIL(h, RLSIM_E_UNSUPPORTED, "more than 2^40 bases on one GPU");
     h->total_padded = tot;
     h->mol_off_valid = false;
+    h->eager_pcr = false;
     h->fragmented = h->amplified = h->sampled = false;
     // ---- device arrays: grow keeping what earlier batches wrote
     CK(h, h->d_bases.grow_preserve(tot + 64, old_total, h->st));
     CK(h, h->d_packed.grow_preserve(tot / 16 + 8, old_total / 16, h->st));
     CK(h, h->d_nmask.grow_preserve(tot / 32 + 8, old_total / 32, h->st));
-    CK(h, h->d_gc.grow_preserve(tot + nn + 8, old_total + n0 + 1, h->st));
+    CK(h, h->d_gc.grow_preserve(tot / 32 + nn + 8, old_total / 32 + n0 + 1, h->st));
     const bool want_prefix = needs_fwd(h->p.frag_method) && h->prefix_upto == n0;
     if (want_prefix) {
         int rcg = grow_prefix(h, tot, nn, old_total, n0);
         if (rcg) return rcg;
     }
+    const bool want_eager = (want_prefix || !needs_fwd(h->p.frag_method)) && eager_possible(h, n0);
     CK(h, h->d_off.ensure(nn + 1)); CK(h, h->d_len.ensure(nn)); CK(h, h->d_expr.ensure(nn));
+    if (want_eager) {
+        CK(h, h->d_mol_off.ensure(nn + 1));
+        CK(h, cudaMemcpyAsync(h->d_mol_off.p, h->h_mol_off.data(), (size_t)(nn + 1) * 8, cudaMemcpyHostToDevice, h->st));
+        h->n_mol = h->h_mol_off[nn];
+    }
     CK(h, cudaMemcpyAsync(h->d_off.p, h->h_off.data(), (size_t)(nn + 1) * 8, cudaMemcpyHostToDevice, h->st));
     CK(h, cudaMemcpyAsync(h->d_len.p, h->h_len.data(), (size_t)nn * 4, cudaMemcpyHostToDevice, h->st));
     CK(h, cudaMemcpyAsync(h->d_expr.p, h->h_expr.data(), (size_t)nn * 8, cudaMemcpyHostToDevice, h->st));
     CK(h, cudaMemsetAsync(h->d_packed.p + tot / 16, 0, 8 * 4, h->st));
     CK(h, cudaMemsetAsync(h->d_nmask.p + tot / 32, 0, 8 * 4, h->st));
-    CK(h, h->staging.bases.ensure(nbytes));
+    CK(h, h->staging.bases.ensure(nbytes + 64));  // k_ingest reads whole aligned words
     CK(h, h->staging.off.ensure(n + 1));
     CK(h, cudaMemcpyAsync(h->staging.off.p, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, h->st));
     // ---- pipeline: H2D of chunk c+1 on the copy stream overlaps ingest (+ prefix sums) of chunk c
-    const uint64_t chunk_bytes = 32ull << 20;
+    const uint64_t chunk_bytes = getenv("RLSIM_CHUNK_BYTES") ? std::max(1ll, atoll(getenv("RLSIM_CHUNK_BYTES")))  // test knob
+                               : (uint64_t)(getenv("RLSIM_CHUNK_MB") ? std::max(1, atoi(getenv("RLSIM_CHUNK_MB"))) : 32) << 20;
     StageTimer tm(h, RLSIM_T_LAYOUT, 0);
-    uint32_t t0 = 0, c = 0;
-    while (t0 < n) {
+    std::vector<uint32_t> cuts{0};
+    for (uint32_t t0 = 0; t0 < n;) {
         uint32_t t1 = t0;
         while (t1 < n && rel[t1] - rel[t0] < chunk_bytes) t1++;
-        if (h->ev_chunk.size() <= c) { cudaEvent_t e; CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_chunk.push_back(e); }
+        cuts.push_back(t1);
+        t0 = t1;
+    }
+    const uint32_t n_chunks = (uint32_t)cuts.size() - 1;
+    while (h->ev_chunk.size() < n_chunks) { cudaEvent_t e; CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_chunk.push_back(e); }
+    for (uint32_t c = 0; c < n_chunks; c++) {  // all copies are queued first: the copy engine never waits for the host
+        const uint32_t t0 = cuts[c], t1 = cuts[c + 1];
         if (rel[t1] > rel[t0])
             CK(h, cudaMemcpyAsync(h->staging.bases.p + rel[t0], bases + offsets[0] + rel[t0], rel[t1] - rel[t0], cudaMemcpyHostToDevice, h->st_copy));
         CK(h, cudaEventRecord(h->ev_chunk[c], h->st_copy));
-        CK(h, cudaStreamWaitEvent(h->st, h->ev_chunk[c], 0));
-        launch_ingest(h->st, h->staging.bases.p, h->staging.off.p + t0, t1 - t0, h->polya_max, h->d_off.p + n0 + t0, h->d_bases.p,
-                      h->d_packed.p, h->d_nmask.p, h->d_gc.p + n0 + t0);
-        h->launches[RLSIM_T_LAYOUT]++;
-        if (want_prefix) { int rc = launch_prefix_range(h, n0 + t0, n0 + t1); if (rc) return rc; }
-        t0 = t1; c++;
+    }
+    // Eager groups are self-sizing: once a group is done, every chunk that has arrived meanwhile forms the next one, so
+    // the per-group fixed cost (host round trips for counts, small sorts) never makes compute fall behind the copies.
+    // The grouping does not influence the result (streams are addressed by global molecule / species identity).
+    bool eager = want_eager;
+    const bool trace = getenv("RLSIM_TRACE") != nullptr;
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now_ms();
+    for (uint32_t c = 0; c < n_chunks;) {
+        uint32_t c_end = c + 1;
+        if (eager) {
+            CK(h, cudaEventSynchronize(h->ev_chunk[c]));
+            while (c_end < n_chunks && cudaEventQuery(h->ev_chunk[c_end]) == cudaSuccess) c_end++;
+            (void)cudaGetLastError();  // cudaErrorNotReady from the query is not an error
+        }
+        for (uint32_t cc = c; cc < c_end; cc++) {
+            const uint32_t t0 = cuts[cc], t1 = cuts[cc + 1];
+            CK(h, cudaStreamWaitEvent(h->st, h->ev_chunk[cc], 0));
+            launch_ingest(h->st, h->staging.bases.p, h->staging.off.p + t0, t1 - t0, n0 + t0, (h->h_off[n0 + t1] - h->h_off[n0 + t0]) >> 5,
+                          h->polya_max, h->d_off.p + n0 + t0, h->d_bases.p, h->d_packed.p, h->d_nmask.p, h->d_gc.p);
+            h->launches[RLSIM_T_LAYOUT] += 2;
+            if (want_prefix) { int rc = launch_prefix_range(h, n0 + t0, n0 + t1); if (rc) return rc; }
+        }
+        if (eager) {
+            if (trace) { const double t_l = now_ms(); cudaStreamSynchronize(h->st); fprintf(stderr, "[rlsim trace]   prev pcr + ingest + prefix %.3f ms\n", now_ms() - t_l); }
+            const double t_a = now_ms();
+            int rc = eager_chunk(h, n0 + cuts[c], n0 + cuts[c_end]);
+            if (rc) return rc;
+            eager = !h->eager_failed;
+            if (trace) fprintf(stderr, "[rlsim trace] chunks %u..%u arrived %.3f ms, group done %.3f ms\n", c, c_end, t_a - t_begin, now_ms() - t_begin);
+        }
+        c = c_end;
     }
     CK(h, cudaStreamSynchronize(h->st_copy));  // caller-owned buffers are only read during the call
+    if (trace) fprintf(stderr, "[rlsim trace] copies done %.3f ms\n", now_ms() - t_begin);
     tm.stop();
     CK(h, cudaGetLastError());
     if (want_prefix) h->prefix_upto = nn;
+    if (want_eager && !h->eager_failed) h->mol_off_valid = true;
     return 0;
 }
 
@@ -548,6 +764,23 @@ int rlsim_fragment(rlsim_handle *h) {
     if (h->low == 0) FAIL(h, RLSIM_E_ARG, "Serious trouble: fragment length is zero!");  // transcript.go:194-196
     uint32_t n = (uint32_t)h->h_len.size();
     int method = h->p.frag_method;
+    if (n && h->eager_upto == n && !h->eager_failed) {
+        // every chunk was fragmented, deduplicated and amplified while the transcripts were still arriving
+        if ((rc = check_device_error(h))) return rc;
+        uint32_t hist_frag_n = (uint32_t)h->high + 1, hist_pa_n = h->polya_max + 1;
+        h->h_hist_frag.assign(hist_frag_n, 0);
+        h->h_hist_polya.assign(hist_pa_n, 0);
+        CK(h, cudaMemcpyAsync(h->h_hist_frag.data(), h->d_hist_frag.p, (size_t)hist_frag_n * 8, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaMemcpyAsync(h->h_hist_polya.data(), h->d_hist_polya.p, (size_t)hist_pa_n * 8, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaStreamSynchronize(h->st));
+        h->n_frag = h->eager_keys;
+        h->n_sp = h->eager_sp;
+        h->eager_pcr = true;
+        h->eager_upto = 0; h->eager_failed = true;  // consumed: a repeated call recomputes from the resident transcripts
+        h->fragmented = true; h->amplified = false; h->sampled = false;
+        return 0;
+    }
+    h->eager_upto = 0; h->eager_failed = true; h->eager_pcr = false;
     // ---- capacity estimate for the fragment keys
     double loc = h->raw_location;
     if (h->p.n_target > 0) {
@@ -582,7 +815,7 @@ int rlsim_fragment(rlsim_handle *h) {
         FragBuffers fb{h->d_keys.p, cap, h->d_counters.p, h->d_hist_frag.p, h->d_hist_polya.p, h->d_long_list.p, h->d_long_hi.p,
                        long_cap, h->d_long_count.p, h->d_error.p, h->d_q_a.p, h->d_q_b.p, q_cap, h->d_counters.p + 2};
         StageTimer tm(h, RLSIM_T_FRAGMENT, 1);
-        rc = launch_fragment(h->st, m, tr, h->n_mol, fb);
+        rc = launch_fragment(h->st, m, tr, 0, h->n_mol, fb);
         if (rc) FAIL(h, rc, "fragmentation launch configuration unsupported (poly(A) maximum too large)");
         unsigned int n_long = 0;
         unsigned long long n_q = 0;
@@ -650,19 +883,15 @@ int rlsim_pcr(rlsim_handle *h) {
     if (!h->fragmented) FAIL(h, RLSIM_E_ARG, "rlsim_fragment first");
     cudaSetDevice(h->device);
     int rc;
-    uint32_t nle = (uint32_t)(h->high - h->low + 1);
-    CK(h, h->d_len_eff.ensure(nle));
+    const bool had_len_eff = h->len_eff_ready;
+    if ((rc = ensure_len_eff(h))) return rc;
     DevModel m = make_model(h);
-    if (!h->h_len_eff.empty()) {
-        if (h->len_eff_low != h->low || h->len_eff_high != h->high) FAIL(h, RLSIM_E_ARG, "length-efficiency table does not span [low, high]");
-        CK(h, cudaMemcpyAsync(h->d_len_eff.p, h->h_len_eff.data(), (size_t)nle * 8, cudaMemcpyHostToDevice, h->st));
-    } else {
-        launch_len_eff(h->st, m, h->d_len_eff.p);
-    }
-    CK(h, cudaMemsetAsync(h->d_error.p, 0, 4, h->st));
     DevTranscripts tr = make_tr(h);
-    {
-        StageTimer tm(h, RLSIM_T_PCR, h->h_len_eff.empty() ? 2 : 1);
+    if (h->eager_pcr) {
+        h->eager_pcr = false;  // counts were amplified chunk by chunk
+    } else {
+        CK(h, cudaMemsetAsync(h->d_error.p, 0, 4, h->st));
+        StageTimer tm(h, RLSIM_T_PCR, had_len_eff ? 1 : 2);
         launch_pcr(h->st, m, tr, make_sp(h), h->d_error.p);
         tm.stop();
         CK(h, cudaGetLastError());
@@ -1077,8 +1306,10 @@ int rlsim_probe_gc_prefix(rlsim_handle *h, uint32_t tr, uint32_t *out, uint32_t 
     if (tr >= h->h_len.size()) FAIL(h, RLSIM_E_ARG, "transcript index out of range");
     cudaSetDevice(h->device);
     uint32_t m = std::min(n, h->h_len[tr] + 1);
-    CK(h, cudaMemcpyAsync(out, h->d_gc.p + h->h_off[tr] + tr, (size_t)m * 4, cudaMemcpyDeviceToHost, h->st));
+    std::vector<uint2> g((size_t)(h->h_len[tr] >> 5) + 1);
+    CK(h, cudaMemcpyAsync(g.data(), h->d_gc.p + (h->h_off[tr] >> 5) + tr, g.size() * sizeof(uint2), cudaMemcpyDeviceToHost, h->st));
     CK(h, cudaStreamSynchronize(h->st));
+    for (uint32_t x = 0; x < m; x++) out[x] = g[x >> 5].x + (uint32_t)__builtin_popcount(g[x >> 5].y & ((1u << (x & 31)) - 1u));
     return 0;
 }
 

@@ -51,7 +51,8 @@ struct DevTranscripts {
     // coarse = u64 sum of everything before each block at coarse_base(off[t], t)
     const uint32_t *Ff, *Fr;
     const uint64_t *Cf, *Cr;
-    const uint32_t *gc;       // GC prefix counts, (len+1) entries per transcript at off[t] + t
+    const uint2 *gc;          // per 32-base group {#GC before the group, GC bit mask of the group}; transcript t has
+                              // padded_len/32 + 1 entries starting at off[t]/32 + t (see gc_before)
 };
 
 // Two-level prefix sums of the fixed-point priming weights w (< 2^26, so a 64-entry block sums to < 2^32):
@@ -69,6 +70,12 @@ struct Profile {  // one strand of one transcript
         return (i & (PFX_BLOCK - 1)) ? c + F[i - 1] : c;
     }
 };
+
+// number of G/C among the first x bases of a transcript whose GC groups start at g
+__device__ __forceinline__ uint32_t gc_before(const uint2 *g, uint32_t x) {
+    uint2 e = g[x >> 5];
+    return e.x + __popc(e.y & ((1u << (x & 31)) - 1u));
+}
 
 __device__ __forceinline__ uint32_t upper_bound_u64(const uint64_t *a, uint32_t n, uint64_t x) {
     uint32_t lo = 0, hi = n;  // first i with a[i] > x

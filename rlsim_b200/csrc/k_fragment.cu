@@ -255,13 +255,13 @@ __device__ __forceinline__ MolCtx make_ctx(const DevModel &m, const DevTranscrip
 }
 
 __global__ void __launch_bounds__(FRAG_THREADS, 10)
-k_fragment(const __grid_constant__ DevModel m, DevTranscripts tr, uint64_t n_mol, FragOut o, uint32_t hist_s_n) {
+k_fragment(const __grid_constant__ DevModel m, DevTranscripts tr, uint64_t g_begin, uint64_t g_end, FragOut o, uint32_t hist_s_n) {
     extern __shared__ unsigned int hist_s[];  // [hist_s_n] after-frag bins from `low`, then [polya_max+1]
     unsigned int *hist_pa = hist_s + hist_s_n;
     for (uint32_t i = threadIdx.x; i < hist_s_n + m.polya_max + 1; i += FRAG_THREADS) hist_s[i] = 0;
     __syncthreads();
-    uint64_t g = (uint64_t)blockIdx.x * FRAG_THREADS + threadIdx.x;
-    if (g < n_mol) {
+    uint64_t g = g_begin + (uint64_t)blockIdx.x * FRAG_THREADS + threadIdx.x;  // global molecule index
+    if (g < g_end) {
         // molecule -> transcript: the warp's first lane searches; a warp rarely spans more than a few transcripts
         const uint64_t g0 = g - (threadIdx.x & 31);
         uint32_t t = 0;
@@ -385,8 +385,10 @@ static uint32_t frag_hist_bins(const DevModel &m) {
     return n > 8192 ? 0 : n;
 }
 
-int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint64_t n_mol, const FragBuffers &fb) {
-    if (n_mol == 0) return 0;
+int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint64_t g_begin, uint64_t g_end,
+                    const FragBuffers &fb) {
+    if (g_end <= g_begin) return 0;
+    const uint64_t n_mol = g_end - g_begin;
     FragOut o{fb.keys, fb.cap, fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, fb.long_cap, fb.long_count,
               fb.error, fb.q_a, fb.q_b, fb.q_cap, fb.q_count};
     // after_* methods only queue intervals here (k_intervals owns the after-fragmentation histogram)
@@ -396,7 +398,7 @@ int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr
     if (smem > 48 * 1024) return RLSIM_E_UNSUPPORTED;
     uint64_t blocks = (n_mol + FRAG_THREADS - 1) / FRAG_THREADS;
     if (blocks > 0x7fffffffull) return RLSIM_E_UNSUPPORTED;
-    k_fragment<<<(unsigned)blocks, FRAG_THREADS, smem, st>>>(m, tr, n_mol, o, hist_s_n);
+    k_fragment<<<(unsigned)blocks, FRAG_THREADS, smem, st>>>(m, tr, g_begin, g_end, o, hist_s_n);
     return 0;
 }
 

@@ -199,8 +199,8 @@ k_pcr(const __grid_constant__ DevModel m, DevTranscripts tr, DevSpecies sp, int 
         t = sp.tr[i]; start = sp.start[i]; len = sp.len[i];
         c0 = sp.count0[i];
         if (e == 0.0 || sp.gc) {
-            const uint32_t *gcp = tr.gc + tr.off[t] + t;
-            gcc = gcp[start + len] - gcp[start];
+            const uint2 *gcp = tr.gc + (tr.off[t] >> 5) + t;
+            gcc = gc_before(gcp, start + len) - gc_before(gcp, start);
         }
         if (e == 0.0) e = m.len_eff[len - m.low] * gc_eff(m, gcc, len);
     }

@@ -16,86 +16,122 @@ __device__ __forceinline__ int base_code(uint8_t c) {
 }
 
 // ---------------------------------------------------------------- ingest
-// One CTA per transcript; each thread handles 32 consecutive bases per tile.
-constexpr int INGEST_THREADS = 128;
+// Pass 1 (k_ingest): one thread per 32-base group of the padded layout.  The source batch is the plain concatenation of
+// the transcripts, so consecutive threads read consecutive source bytes (aligned word loads + funnel shift for the
+// arbitrary source alignment) and write consecutive words of every output array.  Four bases are classified at a time
+// with byte-parallel integer operations.
+// Pass 2 (k_gc_scan): one warp per transcript turns the per-group G/C counts into exclusive prefix counts.
+constexpr int INGEST_THREADS = 256;
+
+__device__ __forceinline__ uint32_t byte_mask(int64_t k) {  // low k bytes set, k clamped to [0, 4]
+    return k <= 0 ? 0u : (k >= 4 ? 0xffffffffu : ((1u << (8 * (int)k)) - 1u));
+}
+__device__ __forceinline__ uint32_t gather_bit0(uint32_t z) {  // bit 0 of each byte -> 4 adjacent bits
+    z &= 0x01010101u;
+    return (z | (z >> 7) | (z >> 14) | (z >> 21)) & 0xfu;
+}
 
 __global__ void __launch_bounds__(INGEST_THREADS)
-k_ingest(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, uint32_t n, uint32_t polya_max,
+k_ingest(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, uint32_t n, uint32_t t_index0, uint32_t polya_max,
          const uint64_t *__restrict__ off, uint8_t *__restrict__ bases, uint32_t *__restrict__ packed,
-         uint32_t *__restrict__ nmask, uint32_t *__restrict__ gc) {
-    __shared__ uint32_t warp_tot[INGEST_THREADS / 32];
-    __shared__ uint32_t carry_s;
-    uint32_t t = blockIdx.x;
-    if (t >= n) return;
+         uint32_t *__restrict__ nmask, uint2 *__restrict__ gc) {
+    const uint64_t P0 = off[0], n_groups = (off[n] - P0) >> 5;
+    const uint64_t g = (uint64_t)blockIdx.x * INGEST_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    // transcript of the warp's first group: 32-ary search, every lane probes one split point per round
+    const uint64_t gw = min(g - lane, n_groups ? n_groups - 1 : 0);
+    const uint64_t Pw = P0 + (gw << 5);
+    uint32_t lo = 0, hi = n;  // invariant: off[lo] <= Pw < off[hi]
+    while (hi - lo > 1) {
+        uint32_t span = hi - lo;
+        uint32_t probe = lo + (uint32_t)(((uint64_t)span * (lane + 1)) / 33);  // lo <= probe < hi
+        bool le = off[probe] <= Pw;
+        uint32_t b = __ballot_sync(0xffffffffu, le);
+        // the probes are nondecreasing in the lane index; off[] is nondecreasing: ballot is a prefix of ones
+        int k = __popc(b);  // lanes 0..k-1 satisfy off[probe] <= Pw
+        uint32_t new_lo = k ? __shfl_sync(0xffffffffu, probe, k - 1) : lo;
+        uint32_t new_hi = k < 32 ? __shfl_sync(0xffffffffu, probe, k) : hi;
+        if (new_lo == lo && new_hi == hi) {  // span too small for the probes to separate: finish linearly
+            while (lo + 1 < hi && off[lo + 1] <= Pw) lo++;
+            hi = lo + 1;
+        } else { lo = new_lo; hi = new_hi; }
+    }
+    if (g >= n_groups) return;
+    const uint64_t P = P0 + (g << 5);
+    uint32_t t = lo;
+    while (off[t + 1] <= P) t++;  // later lanes may sit in later transcripts (zero-length ones are skipped)
     const uint64_t so = src_off[t];
     const uint32_t l = (uint32_t)(src_off[t + 1] - so);
     const uint32_t L = l + polya_max;
-    const uint64_t o = off[t];
-    const uint32_t Lpad = (L + 31u) & ~31u;
-    uint32_t *gcp = gc + o + t;  // (L+1) entries
-    if (threadIdx.x == 0) { carry_s = 0; gcp[0] = 0; }
-    __syncthreads();
-    for (uint32_t tile = 0; tile < Lpad; tile += INGEST_THREADS * 32) {
-        uint32_t p0 = tile + threadIdx.x * 32;
-        uint32_t pk0 = 0, pk1 = 0, mk = 0, cnt = 0;
-        uint32_t bytes[8];
-        if (p0 < Lpad) {
+    const uint32_t p0 = (uint32_t)(P - off[t]);
+    uint32_t w[9];
 #pragma unroll
-            for (int w = 0; w < 8; w++) {
-                uint32_t word = 0;
+    for (int j = 0; j < 9; j++) w[j] = 0;
+    uint32_t sh = 0;
+    if (p0 < l) {
+        const uint8_t *a = src + so + p0;
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(a) & 3u);
+        const uint32_t *aw = reinterpret_cast<const uint32_t *>(a - mis);
+        const uint32_t n_words = (min(l - p0, 32u) + mis + 3u) >> 2;
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    uint32_t p = p0 + w * 4 + b;
-                    uint8_t c = p < l ? src[so + p] : (p < L ? (uint8_t)'A' : (uint8_t)0);
-                    word |= (uint32_t)c << (8 * b);
-                    int code = base_code(c);
-                    int i = w * 4 + b;
-                    if (code < 0) { mk |= 1u << i; code = 0; }
-                    if (i < 16) pk0 |= (uint32_t)code << (2 * i); else pk1 |= (uint32_t)code << (2 * (i - 16));
-                    cnt += (c == 'G' || c == 'C');
-                }
-                bytes[w] = word;
-            }
-            uint4 *dst = reinterpret_cast<uint4 *>(bases + o + p0);
-            dst[0] = make_uint4(bytes[0], bytes[1], bytes[2], bytes[3]);
-            dst[1] = make_uint4(bytes[4], bytes[5], bytes[6], bytes[7]);
-            packed[((o + p0) >> 4)] = pk0;
-            packed[((o + p0) >> 4) + 1] = pk1;
-            nmask[(o + p0) >> 5] = mk;
-        }
-        // block exclusive scan of cnt
-        uint32_t incl = cnt;
+        for (int j = 0; j < 9; j++)
+            if ((uint32_t)j < n_words) w[j] = __ldg(aw + j);
+        sh = 8 * mis;
+    }
+    uint32_t out[8], pk0 = 0, pk1 = 0, mk = 0, gm = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        uint32_t x = __funnelshift_r(w[j], w[j + 1], sh);
+        const int64_t q = (int64_t)p0 + 4 * j;
+        const uint32_t ms = byte_mask((int64_t)l - q), ma = byte_mask((int64_t)L - q);
+        x = (x & ms) | (0x41414141u & ma & ~ms);  // transcript.go:98-117: the poly(A) tail; zero padding after it
+        out[j] = x;
+        const uint32_t v = __vcmpeq4(x, 0x41414141u) | __vcmpeq4(x, 0x43434343u) | __vcmpeq4(x, 0x47474747u) | __vcmpeq4(x, 0x54545454u);
+        const uint32_t y = ((x >> 1) ^ (x >> 2)) & 0x03030303u & v;  // A C G T -> 0 1 2 3, anything else 0 + mask bit
+        const uint32_t code8 = (y | (y >> 6) | (y >> 12) | (y >> 18)) & 0xffu;
+        if (j < 4) pk0 |= code8 << (8 * j); else pk1 |= code8 << (8 * (j - 4));
+        mk |= gather_bit0(~v) << (4 * j);
+        gm |= gather_bit0(y ^ (y >> 1)) << (4 * j);
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(bases + P);
+    dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+    dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+    *reinterpret_cast<uint2 *>(packed + (P >> 4)) = make_uint2(pk0, pk1);
+    nmask[P >> 5] = mk;
+    gc[(P >> 5) + t_index0 + t] = make_uint2(__popc(gm), gm);
+}
+
+__global__ void __launch_bounds__(INGEST_THREADS)
+k_gc_scan(uint32_t n, uint32_t t_index0, const uint64_t *__restrict__ off, uint2 *__restrict__ gc) {
+    const uint32_t t = blockIdx.x * (INGEST_THREADS / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= n) return;
+    const uint32_t J = (uint32_t)((off[t + 1] - off[t]) >> 5);
+    uint2 *g = gc + (off[t] >> 5) + t_index0 + t;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < J; base += 32) {
+        const uint32_t j = base + lane;
+        uint2 e = j < J ? g[j] : make_uint2(0, 0);
+        uint32_t incl = e.x;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-            if ((threadIdx.x & 31) >= d) incl += v;
+            if (lane >= d) incl += v;
         }
-        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        uint32_t base = carry_s;
-        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) base += warp_tot[w];
-        uint32_t run = base + incl - cnt;
-        if (p0 < L) {
-#pragma unroll
-            for (int w = 0; w < 8; w++) {
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    uint32_t p = p0 + w * 4 + b;
-                    uint8_t c = (uint8_t)(bytes[w] >> (8 * b));
-                    run += (c == 'G' || c == 'C');
-                    if (p < L) gcp[p + 1] = run;
-                }
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == INGEST_THREADS - 1) carry_s = base + incl;
-        __syncthreads();
+        if (j < J) g[j] = make_uint2(carry + incl - e.x, e.y);
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
+    if (lane == 0) g[J] = make_uint2(carry, 0);
 }
 
-void launch_ingest(cudaStream_t st, const uint8_t *src, const uint64_t *src_off, uint32_t n, uint32_t polya_max,
-                   const uint64_t *off, uint8_t *bases, uint32_t *packed, uint32_t *nmask, uint32_t *gc) {
-    if (n) k_ingest<<<n, INGEST_THREADS, 0, st>>>(src, src_off, n, polya_max, off, bases, packed, nmask, gc);
+// src_off / off point at the first transcript of the batch; t_index0 is its index on this handle
+void launch_ingest(cudaStream_t st, const uint8_t *src, const uint64_t *src_off, uint32_t n, uint32_t t_index0, uint64_t n_groups,
+                   uint32_t polya_max, const uint64_t *off, uint8_t *bases, uint32_t *packed, uint32_t *nmask, uint2 *gc) {
+    if (!n) return;
+    if (n_groups)
+        k_ingest<<<(unsigned)((n_groups + INGEST_THREADS - 1) / INGEST_THREADS), INGEST_THREADS, 0, st>>>(
+            src, src_off, n, t_index0, polya_max, off, bases, packed, nmask, gc);
+    k_gc_scan<<<(n + INGEST_THREADS / 32 - 1) / (INGEST_THREADS / 32), INGEST_THREADS, 0, st>>>(n, t_index0, off, gc);
 }
 
 // ---------------------------------------------------------------- k-mer affinities

@@ -58,6 +58,8 @@ def run(argv, out=None):
     if world > 1:
         import torch
         import torch.distributed as dist
+        from . import shard
+        shard.bind_to_gpu_numa_node(local_rank)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl")
         dist_device = torch.device("cuda", local_rank)

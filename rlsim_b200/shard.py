@@ -12,6 +12,29 @@ all-gather (NCCL on GPUs, gloo in the CPU tests).
 import numpy as np
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs NVML reports as local to its GPU, so that pinned host buffers are first-touched on
+    the NUMA node the GPU hangs off (with 8 ranks copying at once, remote-socket buffers halve the PCIe throughput).
+    Best effort: returns the CPU set or None."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[local_rank]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and 64 * w + b < n_cpu}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or None
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def contiguous_partition(work, n_ranks):
     """Boundaries b[0..n_ranks] of contiguous ranges with ~equal total work (prefix quantiles)."""
     work = np.asarray(work, dtype=np.float64)

@@ -274,6 +274,51 @@ def test_batched_add_transcripts_equals_single_call(gpu):
     assert one.fasta(names) == h.fasta(names)
 
 
+@pytest.mark.parametrize("flags", [["-f", "after_prim_double"], ["-f", "after_noprim"], ["-f", "pre_prim"], ["-f", "prim_jump"],
+                                   ["-f", "after_prim", "-b", "0.3", "-flg", "0.2"]])
+def test_eager_chunk_pipeline_equals_monolithic(gpu, monkeypatch, flags):
+    """rlsim_add_transcripts fragments / deduplicates / amplifies each copied chunk while later chunks are in flight
+    (after_* methods); the result is bit-identical to the monolithic rlsim_fragment + rlsim_pcr over resident
+    transcripts, for any chunking, for repeated build_library calls, and for batches added in several calls."""
+    args = util.parse(["-n", "40000", "-c", "9", "-si", "5", "-eg", "(1.0,0.5,0.8)"] + flags)
+    names, seqs, levels = util.synth_transcriptome(400, seed=31, mean_len=1200, hi=5000, total_molecules=60000, non_acgt=0.001)
+    levels = list(levels)
+    levels[3] = levels[4] = 0
+
+    def run(first_builds=1, batches=((0, 400),)):
+        h = gpu.Handle(0)
+        h.set_model(args.to_params())
+        h.sample_target(args.req_frags)
+        h.set_first_index(7)
+        for a, b in batches:
+            h.add_transcripts(seqs[a:b], levels[a:b])
+        for _ in range(first_builds):
+            h.build_library()
+        h.sample()
+        return h
+
+    monkeypatch.setenv("RLSIM_NO_EAGER", "1")
+    mono = run()
+    monkeypatch.delenv("RLSIM_NO_EAGER")
+    variants = []
+    for chunk in ("4096", "50000", "100000000"):
+        monkeypatch.setenv("RLSIM_CHUNK_BYTES", chunk)
+        variants.append(run())
+    monkeypatch.setenv("RLSIM_CHUNK_BYTES", "30000")
+    variants.append(run(first_builds=2))                                   # second build recomputes from resident data
+    variants.append(run(batches=((0, 1), (1, 150), (150, 151), (151, 400))))  # eager across several add calls
+    for h in variants:
+        for k in ("tr", "start", "end", "count0", "count"):
+            assert np.array_equal(mono.species()[k], h.species()[k]), k
+        for k in ("tr", "start", "end", "minus", "id"):
+            assert np.array_equal(mono.sampled()[k], h.sampled()[k]), k
+        for which in (gpu.H_AFTER_FRAG, gpu.H_POLYA, gpu.H_AFTER_PCR):
+            assert mono.hist_dict(which, 6000) == h.hist_dict(which, 6000)
+        assert mono.fasta(names) == h.fasta(names)
+        sm, sh = mono.stats(), h.stats()
+        assert (sm.n_fragments, sm.n_species, sm.pool_total, sm.n_sampled) == (sh.n_fragments, sh.n_species, sh.pool_total, sh.n_sampled)
+
+
 def test_degenerate_inputs(oracle, gpu):
     """Nothing expressed; a single molecule; primer length 1 and 12 (LUT in global memory); fixed-length tails."""
     names, seqs, levels = util.synth_transcriptome(5, seed=2, mean_len=800, hi=2000, total_molecules=100)
