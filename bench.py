@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the C3 workload per GPU (1.0 = the named config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fasta", action="store_true", help="skip the extra end-to-end measurement that includes FASTA text")
     opts = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -252,6 +253,59 @@ def main():
     barrier()
     t_e2e = time.perf_counter() - t0
     d2h_bytes = (n_e2e // max(opts.steps, 1)) * 21 + 7 * 8 * (int(h.stats().high) + 2)
+    # ---- e2e including FASTA text (reported separately; frag.go:71-126 formatted on the device)
+    e2e_fasta = None
+    if world == 1 and not opts.no_fasta:
+        names = [b"T%d$%d" % (i, int(levels_np[i])) for i in range(n_tr)]
+        names_u8 = np.frombuffer(b"".join(names), dtype=np.uint8).copy()
+        names_off = np.zeros(n_tr + 1, dtype=np.uint64)
+        names_off[1:] = np.cumsum([len(x) for x in names])
+        text_bytes = h.fasta_into(names_u8, names_off, None)  # records of the last e2e step: sizes the pinned buffer
+        text = torch.empty(int(text_bytes * 1.05) + (1 << 20), dtype=torch.uint8).pin_memory()
+        fsteps = max(1, min(3, opts.steps))
+        ms_f0 = h.timings()[0]["format"]
+        for timed in (False, True):
+            barrier()
+            t0 = time.perf_counter()
+            nf = tb = 0
+            for s in range(fsteps):
+                nf += step_e2e(300 + s)
+                tb += h.fasta_into(names_u8, names_off, text)
+            barrier()
+            t_f = time.perf_counter() - t0
+        e2e_fasta = {"value": nf / t_f, "unit": "fragments/s", "steps": fsteps, "ms_per_step": 1000.0 * t_f / fsteps,
+                     "text_bytes_per_step": tb // fsteps, "format_kernels_ms_per_step": (h.timings()[0]["format"] - ms_f0) / (2 * fsteps),
+                     "note": "the e2e step above plus rlsim_format_fasta: records formatted on the device, text copied to pinned host memory"}
+        del text
+    # ---- e2e from raw FASTA text: records split / despaced / upper-cased / parsed on the device
+    e2e_text_in = None
+    if world == 1 and not opts.no_fasta:
+        raw = torch.from_numpy(synth.fasta_text(bases_np, off_np, levels_np, width=70).copy()).pin_memory()
+        tsteps = max(1, min(5, opts.steps))
+
+        def step_text(step):
+            pool.reset().configure(make_args(n_frags_global, step + 1))
+            h.set_first_index(0)
+            idx = h.add_fasta(raw, 1.0)
+            assert idx["n_added"] == n_tr
+            h.build_library()
+            select(step)
+            n = int(h.stats().n_sampled)
+            h.sampled(into=out)
+            return n
+
+        step_text(400)
+        barrier()
+        t0 = time.perf_counter()
+        nt_in = 0
+        for s in range(tsteps):
+            nt_in += step_text(401 + s)
+        barrier()
+        t_t = time.perf_counter() - t0
+        e2e_text_in = {"value": nt_in / t_t, "unit": "fragments/s", "steps": tsteps, "ms_per_step": 1000.0 * t_t / tsteps,
+                       "text_bytes_per_step": int(raw.numel()),
+                       "note": "the e2e step fed with the raw FASTA text (70-column lines) through rlsim_add_fasta instead of parsed arrays"}
+        del raw
     # ---- device-resident
     for s in range(min(opts.warmup, 2)):
         step_resident(50 + s)
@@ -331,6 +385,14 @@ def main():
                    "pool_total_rank0": int(st.pool_total)},
         "e2e": {"value": n_e2e / t_e2e, "unit": "fragments/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                 "ms_per_step": 1000.0 * t_e2e / K, "phases_ms_rank0": {k: round(v / K, 3) for k, v in e2e_phase.items()}},
+        "e2e_fasta": e2e_fasta,
+        "e2e_text_in": e2e_text_in,
+        "stage_rates": {  # per-stage rates of the device-resident step
+            "prefix_nt_per_s": nt_total / (stage_ms["prefix"] * 1e-3) if stage_ms.get("prefix", 0) > 0 else None,
+            "fragmentation_molecules_per_s": float(st.n_molecules) / ((stage_ms["fragment"] + stage_ms.get("intervals", 0.0)) * 1e-3),
+            "pcr_species_per_s": float(st.n_species) / (stage_ms["pcr"] * 1e-3),
+            "selection_fragments_per_s": float(st.n_sampled) / ((stage_ms["select"] + stage_ms["expand"]) * 1e-3),
+        },
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline,

@@ -124,6 +124,20 @@ int rlsim_set_target_hist(rlsim_handle *h, const uint32_t *lengths, const uint64
  * same fragments. */
 int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t *offsets, const uint64_t *expr,
                           uint32_t n);
+/* Device-side FASTA reader (next row 8f-3; fasta.go:113-212 ReadFasta/FastaToSeq, input.go:82-124 ParseSeqName and the
+ * -m multiplier): `text` = the raw bytes of the input files, concatenated as io.MultiReader would (fasta.go:98-104).
+ * Record splitting, despacing, upper-casing and `name$level` parsing run on the GPU; records with malformed names are
+ * skipped as the reference does; the remaining records are added exactly as rlsim_add_transcripts would add them.
+ * *n_records = records found, *n_added = records added.  RLSIM_E_ARG with the reference's message when the text does
+ * not start with '>' ("Illegal fasta record"); RLSIM_E_UNSUPPORTED for a run of more than 64 consecutive '>'. */
+int rlsim_add_fasta(rlsim_handle *h, const uint8_t *text, uint64_t n_bytes, double expr_mul, uint32_t *n_records,
+                    uint32_t *n_added);
+/* Record table of the last rlsim_add_fasta, one entry per record found (any pointer may be NULL): name_start = offset of
+ * the name line in `text`, line_len = its length, name_len = bytes before the '$' (0 when malformed), level = expression
+ * level with the multiplier applied, seq_len = sequence length, valid = 0 for skipped records ("Skipping transcript
+ * with malformed name: <line>", input.go:83). */
+int rlsim_get_fasta_index(rlsim_handle *h, uint64_t *name_start, uint32_t *line_len, uint32_t *name_len, uint64_t *level,
+                          uint64_t *seq_len, uint8_t *valid);
 int rlsim_set_first_index(rlsim_handle *h, uint32_t first_index);
 /* forget the transcripts and everything derived from them; device buffers are kept for the next library */
 int rlsim_clear_transcripts(rlsim_handle *h);

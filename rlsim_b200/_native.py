@@ -16,9 +16,11 @@ LIB_PATH = os.path.join(HERE, "librlsim_gpu.so")
 H_TARGET, H_POLYA, H_AFTER_FRAG, H_AFTER_PCR, H_SAMPLED, H_MISSING, H_AFTER_SAMPLING = range(7)
 T_NAMES = ["layout", "prefix", "fragment", "dedup", "pcr", "select", "expand", "format", "target", "intervals"]
 
+E_CUDA, E_ARG, E_PRIMING, E_PCR_OVERFLOW, E_POOL_OVERFLOW, E_UNSUPPORTED, E_NOMEM = range(1, 8)  # include/rlsim_gpu.h
+
 EXPORTS = [
     "rlsim_create", "rlsim_destroy", "rlsim_last_error", "rlsim_set_model", "rlsim_set_len_eff", "rlsim_set_raw_target",
-    "rlsim_sample_target", "rlsim_sample_target_range", "rlsim_set_target_hist", "rlsim_add_transcripts", "rlsim_set_first_index", "rlsim_clear_transcripts",
+    "rlsim_sample_target", "rlsim_sample_target_range", "rlsim_set_target_hist", "rlsim_add_transcripts", "rlsim_add_fasta", "rlsim_get_fasta_index", "rlsim_set_first_index", "rlsim_clear_transcripts",
     "rlsim_build_library", "rlsim_fragment", "rlsim_pcr", "rlsim_class_totals", "rlsim_sample", "rlsim_select_classes", "rlsim_apply_selected", "rlsim_finish_sample", "rlsim_get_stats",
     "rlsim_get_hist", "rlsim_get_species", "rlsim_get_sampled", "rlsim_format_fasta", "rlsim_probe_kmer_lut",
     "rlsim_probe_prefix", "rlsim_probe_gc_prefix", "rlsim_probe_math", "rlsim_probe_philox", "rlsim_probe_amplify",
@@ -64,6 +66,8 @@ def load():
         "rlsim_sample_target_range": (i32, [vp, u64, u64]),
         "rlsim_set_target_hist": (i32, [vp, vp, vp, u32]),
         "rlsim_add_transcripts": (i32, [vp, vp, vp, vp, u32]),
+        "rlsim_add_fasta": (i32, [vp, vp, u64, C.c_double, C.POINTER(u32), C.POINTER(u32)]),
+        "rlsim_get_fasta_index": (i32, [vp] + [vp] * 6),
         "rlsim_set_first_index": (i32, [vp, u32]),
         "rlsim_clear_transcripts": (i32, [vp]),
         "rlsim_build_library": (i32, [vp]),
@@ -177,6 +181,21 @@ class Handle:
         expr = np.ascontiguousarray(expr, dtype=np.uint64)
         self.add_transcripts_raw(np.ascontiguousarray(bases), off, expr, len(seqs))
 
+    def add_fasta(self, text, expr_mul=1.0):
+        """Raw FASTA text (bytes / uint8 array / pinned tensor) -> parsed and added on the device.
+        Returns the record table of rlsim_get_fasta_index as a dict of numpy arrays (one entry per record found)."""
+        if isinstance(text, (bytes, bytearray, memoryview)):
+            text = np.frombuffer(text, dtype=np.uint8)
+        nbytes = text.numel() if hasattr(text, "numel") else text.size
+        n_rec, n_add = C.c_uint32(), C.c_uint32()
+        self._chk(self.L.rlsim_add_fasta(self.h, _addr(text), int(nbytes), float(expr_mul), C.byref(n_rec), C.byref(n_add)))
+        n = n_rec.value
+        idx = dict(name_start=np.zeros(n, np.uint64), line_len=np.zeros(n, np.uint32), name_len=np.zeros(n, np.uint32),
+                   level=np.zeros(n, np.uint64), seq_len=np.zeros(n, np.uint64), valid=np.zeros(n, np.uint8))
+        self._chk(self.L.rlsim_get_fasta_index(self.h, *[_p(idx[k]) for k in ("name_start", "line_len", "name_len", "level", "seq_len", "valid")]))
+        idx["n_added"] = n_add.value
+        return idx
+
     # ---- stages
     def fragment(self):
         self._chk(self.L.rlsim_fragment(self.h))
@@ -262,6 +281,17 @@ class Handle:
         buf = np.zeros(max(size.value, 1), dtype=np.uint8)
         self._chk(self.L.rlsim_format_fasta(self.h, _p(nb), _p(off), _p(buf), size.value, C.byref(size)))
         return buf[:size.value].tobytes()
+
+    def fasta_into(self, names_u8, names_off, buf):
+        """Format the sampled fragments as FASTA text into a caller-owned (ideally pinned) uint8 buffer; returns the size.
+        names_u8 / names_off: concatenated transcript names and their u64 offsets.  buf=None only sizes the text."""
+        size = C.c_uint64()
+        if buf is None:
+            self._chk(self.L.rlsim_format_fasta(self.h, _addr(names_u8), _addr(names_off), None, 0, C.byref(size)))
+        else:
+            cap = buf.numel() if hasattr(buf, "numel") else buf.size
+            self._chk(self.L.rlsim_format_fasta(self.h, _addr(names_u8), _addr(names_off), _addr(buf), cap, C.byref(size)))
+        return size.value
 
     def timings(self):
         ms = np.zeros(len(T_NAMES), dtype=np.float32)

@@ -97,6 +97,10 @@ struct rlsim_handle {
     uint32_t first_index = 0;
     Staging staging;
     cudaStream_t st_copy = nullptr;  // H2D of the next chunk overlaps ingest/prefix of the previous one
+    cudaStream_t st_pcr = nullptr;   // eager pipeline: PCR of group g (FP64 issue bound) overlaps the memory-bound stages of group g+1
+    cudaEvent_t ev_sp = nullptr, ev_pcr = nullptr;
+    bool pcr_in_flight = false;
+    unsigned long long *pin = nullptr;  // pinned scratch for the small device-to-host count reads
     std::vector<cudaEvent_t> ev_chunk;
     std::vector<uint64_t> h_srclen;  // unpadded lengths as added
     std::vector<uint64_t> h_expr;
@@ -116,6 +120,16 @@ struct rlsim_handle {
     DBuf<uint8_t> d_bases;
     DBuf<uint32_t> d_packed, d_nmask, d_len;
     DBuf<uint2> d_gc;  // GC groups: {prefix count, bit mask} per 32 bases
+    // device FASTA reader (rlsim_add_fasta)
+    DBuf<uint8_t> d_fa_text, d_fa_tiles, d_fa_seq, d_fa_seq2, d_fa_valid;
+    DBuf<uint4> d_fa_carry;
+    DBuf<unsigned long long> d_fa_tot;
+    DBuf<uint64_t> d_fa_rec_start, d_fa_hdr_end, d_fa_seq_off, d_fa_level, d_fa_seq_len;
+    DBuf<uint32_t> d_fa_hdr_len, d_fa_name_len;
+    std::vector<uint64_t> fa_start, fa_level, fa_seq_len;
+    std::vector<uint32_t> fa_hdr_len, fa_name_len;
+    std::vector<uint8_t> fa_valid;
+    uint32_t fa_n = 0;
     DBuf<uint64_t> d_off, d_expr, d_mol_off, d_Cf, d_Cr;  // coarse prefix sums
     DBuf<uint32_t> d_Ff, d_Fr;                          // fine (in-block) prefix sums
     uint32_t prefix_upto = 0;  // transcripts [0, prefix_upto) have valid priming prefix sums for the current model
@@ -302,6 +316,7 @@ int launch_prefix_range(rlsim_handle *h, uint32_t t0, uint32_t t1) {
     return 0;
 }
 
+#define D2H(dst, src, bytes) do { if (dst) CK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->st)); } while (0)
 int cub_temp(rlsim_handle *h, size_t bytes);
 int check_device_error(rlsim_handle *h);
 
@@ -344,6 +359,10 @@ bool eager_possible(rlsim_handle *h, uint32_t n0) {
            h->low > 0 && h->high >= h->low && !h->eager_failed && h->eager_upto == n0;
 }
 
+bool ns_need(rlsim_handle *h, uint64_t ns) {  // would any per-species array be reallocated for ns species?
+    return ns > h->d_sp_tr.n || ns > h->d_sp_start.n || ns > h->d_sp_len.n || ns > h->d_sp_count.n || ns > h->d_sp_eff.n || ns > h->d_sp_gc.n;
+}
+
 // Fragment, dedup and amplify the transcripts [t0, t1) of a chunk whose ingest + prefix sums are already queued on
 // the compute stream.  The host waits on the compute stream only; the copy stream keeps feeding later chunks.
 int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
@@ -377,18 +396,19 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
     FragBuffers fb{h->d_keys.p, h->d_keys.n, h->d_counters.p, h->d_hist_frag.p, h->d_hist_polya.p, h->d_long_list.p, h->d_long_hi.p,
                    long_cap, h->d_long_count.p, h->d_error.p, h->d_q_a.p, h->d_q_b.p, h->d_q_a.n, h->d_counters.p + 2};
     if ((rc = launch_fragment(h->st, m, tr, g0, g1, fb))) { h->eager_failed = true; return 0; }
-    unsigned int n_long = 0;
-    unsigned long long n_q = 0, cnt = 0;
-    CK(h, cudaMemcpyAsync(&n_long, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
-    CK(h, cudaMemcpyAsync(&n_q, h->d_counters.p + 2, 8, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaMemcpyAsync(h->pin, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaMemcpyAsync(h->pin + 1, h->d_counters.p + 2, 8, cudaMemcpyDeviceToHost, h->st));
     CK(h, cudaStreamSynchronize(h->st));
+    const unsigned int n_long = *reinterpret_cast<unsigned int *>(h->pin);
+    const unsigned long long n_q = h->pin[1];
     tt1 = now_ms();
     if (n_long > long_cap || n_q > h->d_q_a.n) { h->eager_failed = true; return 0; }
     launch_intervals(h->st, m, tr, fb, n_q);
     launch_fragment_long(h->st, m, tr, fb, n_long);
     h->launches[RLSIM_T_FRAGMENT] += 1 + (n_long ? 1 : 0); h->launches[RLSIM_T_INTERVALS] += n_q ? 1 : 0;
-    CK(h, cudaMemcpyAsync(&cnt, h->d_counters.p, 8, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaMemcpyAsync(h->pin + 2, h->d_counters.p, 8, cudaMemcpyDeviceToHost, h->st));
     CK(h, cudaStreamSynchronize(h->st));
+    const unsigned long long cnt = h->pin[2];
     tt2 = now_ms();
     CK(h, cudaGetLastError());
     if (cnt > h->d_keys.n) { h->eager_failed = true; return 0; }
@@ -399,6 +419,7 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
         // species of this chunk: sort + run-length encode its keys (transcript.go:156-215), appended to the species table
         CK(h, h->d_keys_sorted.ensure(nf)); CK(h, h->d_uniq.ensure(nf));
         const uint64_t need = h->eager_sp + nf;
+        if (h->pcr_in_flight && need > h->d_sp_count0.n) CK(h, cudaStreamWaitEvent(h->st, h->ev_pcr, 0));
         CK(h, h->d_sp_count0.grow_preserve(need, h->eager_sp, h->st));
         int end_bit = (int)std::min<uint32_t>(64, 24 + bits_for(h->total_padded));
         size_t tb = 0;
@@ -411,11 +432,13 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
         if ((rc = cub_temp(h, tb))) return rc;
         CK(h, cub::DeviceRunLengthEncode::Encode(h->d_cub.p, tb, h->d_keys_sorted.p, h->d_uniq.p, h->d_sp_count0.p + h->eager_sp,
                                                  h->d_counters.p + 1, (int)nf, h->st));
-        unsigned long long r64 = 0;
-        CK(h, cudaMemcpyAsync(&r64, h->d_counters.p + 1, 8, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaMemcpyAsync(h->pin + 3, h->d_counters.p + 1, 8, cudaMemcpyDeviceToHost, h->st));
         CK(h, cudaStreamSynchronize(h->st));
         tt3 = now_ms();
-        runs = r64;
+        runs = h->pin[3];
+        // the species arrays move when they grow: the previous group's PCR must have finished with them first
+        if (h->pcr_in_flight && (ns_need(h, h->eager_sp + runs)))
+            CK(h, cudaStreamWaitEvent(h->st, h->ev_pcr, 0));
         h->launches[RLSIM_T_DEDUP] += 3 + radix_launches(end_bit);
         const uint64_t ns = h->eager_sp + runs;
         CK(h, h->d_sp_tr.grow_preserve(ns, h->eager_sp, h->st)); CK(h, h->d_sp_start.grow_preserve(ns, h->eager_sp, h->st));
@@ -429,7 +452,11 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
         launch_decode_species(h->st, tr, h->d_uniq.p, sp);
         if ((rc = ensure_len_eff(h))) return rc;
         m = make_model(h);  // picks up the length-efficiency table pointer
-        launch_pcr(h->st, m, tr, sp, h->d_error.p);  // thermocycler.go:106-147 for this chunk's species
+        CK(h, cudaEventRecord(h->ev_sp, h->st));
+        CK(h, cudaStreamWaitEvent(h->st_pcr, h->ev_sp, 0));
+        launch_pcr(h->st_pcr, m, tr, sp, h->d_error.p);  // thermocycler.go:106-147 for this group's species
+        CK(h, cudaEventRecord(h->ev_pcr, h->st_pcr));
+        h->pcr_in_flight = true;
         h->launches[RLSIM_T_PCR] += 1;
         CK(h, cudaGetLastError());
     }
@@ -490,6 +517,10 @@ int rlsim_create(int device, rlsim_handle **out) {
     h->device = device;
     if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->st_pcr, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&h->ev_sp, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&h->ev_pcr, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaHostAlloc((void **)&h->pin, 64, cudaHostAllocDefault)) != cudaSuccess ||
         (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
         (e = h->d_error.ensure(1)) != cudaSuccess || (e = h->d_counters.ensure(4)) != cudaSuccess ||
         (e = h->d_long_count.ensure(1)) != cudaSuccess || (e = h->d_work.ensure(4)) != cudaSuccess || (e = h->d_kmax.ensure(1)) != cudaSuccess) {
@@ -507,6 +538,10 @@ void rlsim_destroy(rlsim_handle *h) {
     cudaSetDevice(h->device);
     for (auto e : h->ev_chunk) cudaEventDestroy(e);
     if (h->st_copy) cudaStreamDestroy(h->st_copy);
+    if (h->st_pcr) cudaStreamDestroy(h->st_pcr);
+    if (h->ev_sp) cudaEventDestroy(h->ev_sp);
+    if (h->ev_pcr) cudaEventDestroy(h->ev_pcr);
+    if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->st) cudaStreamDestroy(h->st);
@@ -628,7 +663,10 @@ int rlsim_clear_transcripts(rlsim_handle *h) {
     return 0;
 }
 
-int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t *offsets, const uint64_t *expr, uint32_t n) {
+}  // extern "C"
+
+// bases: host memory (copied in pipelined chunks), or -- dev_bases -- sequences already in device memory
+static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_bases, const uint64_t *offsets, const uint64_t *expr, uint32_t n) {
     if (!h->have_model) FAIL(h, RLSIM_E_ARG, "rlsim_set_model must precede rlsim_add_transcripts (the poly(A) maximum shapes the layout)");
     if (n == 0) return 0;
     cudaSetDevice(h->device);
@@ -692,7 +730,8 @@ int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t 
     CK(h, cudaMemcpyAsync(h->d_expr.p, h->h_expr.data(), (size_t)nn * 8, cudaMemcpyHostToDevice, h->st));
     CK(h, cudaMemsetAsync(h->d_packed.p + tot / 16, 0, 8 * 4, h->st));
     CK(h, cudaMemsetAsync(h->d_nmask.p + tot / 32, 0, 8 * 4, h->st));
-    CK(h, h->staging.bases.ensure(nbytes + 64));  // k_ingest reads whole aligned words
+    if (!dev_bases) CK(h, h->staging.bases.ensure(nbytes + 64));  // k_ingest reads whole aligned words
+    const uint8_t *src = dev_bases ? dev_bases + offsets[0] : h->staging.bases.p;
     CK(h, h->staging.off.ensure(n + 1));
     CK(h, cudaMemcpyAsync(h->staging.off.p, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, h->st));
     // ---- pipeline: H2D of chunk c+1 on the copy stream overlaps ingest (+ prefix sums) of chunk c
@@ -710,7 +749,7 @@ int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t 
     while (h->ev_chunk.size() < n_chunks) { cudaEvent_t e; CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_chunk.push_back(e); }
     for (uint32_t c = 0; c < n_chunks; c++) {  // all copies are queued first: the copy engine never waits for the host
         const uint32_t t0 = cuts[c], t1 = cuts[c + 1];
-        if (rel[t1] > rel[t0])
+        if (rel[t1] > rel[t0] && !dev_bases)
             CK(h, cudaMemcpyAsync(h->staging.bases.p + rel[t0], bases + offsets[0] + rel[t0], rel[t1] - rel[t0], cudaMemcpyHostToDevice, h->st_copy));
         CK(h, cudaEventRecord(h->ev_chunk[c], h->st_copy));
     }
@@ -731,7 +770,7 @@ int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t 
         for (uint32_t cc = c; cc < c_end; cc++) {
             const uint32_t t0 = cuts[cc], t1 = cuts[cc + 1];
             CK(h, cudaStreamWaitEvent(h->st, h->ev_chunk[cc], 0));
-            launch_ingest(h->st, h->staging.bases.p, h->staging.off.p + t0, t1 - t0, n0 + t0, (h->h_off[n0 + t1] - h->h_off[n0 + t0]) >> 5,
+            launch_ingest(h->st, src, h->staging.off.p + t0, t1 - t0, n0 + t0, (h->h_off[n0 + t1] - h->h_off[n0 + t0]) >> 5,
                           h->polya_max, h->d_off.p + n0 + t0, h->d_bases.p, h->d_packed.p, h->d_nmask.p, h->d_gc.p);
             h->launches[RLSIM_T_LAYOUT] += 2;
             if (want_prefix) { int rc = launch_prefix_range(h, n0 + t0, n0 + t1); if (rc) return rc; }
@@ -746,12 +785,121 @@ int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t 
         }
         c = c_end;
     }
+    if (h->pcr_in_flight) { CK(h, cudaStreamWaitEvent(h->st, h->ev_pcr, 0)); h->pcr_in_flight = false; }
     CK(h, cudaStreamSynchronize(h->st_copy));  // caller-owned buffers are only read during the call
     if (trace) fprintf(stderr, "[rlsim trace] copies done %.3f ms\n", now_ms() - t_begin);
     tm.stop();
     CK(h, cudaGetLastError());
     if (want_prefix) h->prefix_upto = nn;
     if (want_eager && !h->eager_failed) h->mol_off_valid = true;
+    return 0;
+}
+
+extern "C" {
+
+int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t *offsets, const uint64_t *expr, uint32_t n) {
+    return add_core(h, bases, nullptr, offsets, expr, n);
+}
+
+// Device-side FASTA reader (k_fasta_in.cu): fasta.go:113-212 + input.go:82-124 in four kernels, then the usual ingest
+int rlsim_add_fasta(rlsim_handle *h, const uint8_t *text, uint64_t n_bytes, double expr_mul, uint32_t *n_records, uint32_t *n_added) {
+    if (n_records) *n_records = 0;
+    if (n_added) *n_added = 0;
+    h->fa_n = 0;
+    if (!h->have_model) FAIL(h, RLSIM_E_ARG, "rlsim_set_model must precede rlsim_add_fasta (the poly(A) maximum shapes the layout)");
+    if (n_bytes == 0) return 0;
+    if (text[0] != '>') {  // fasta.go:183-185
+        std::string head((const char *)text, (size_t)std::min<uint64_t>(n_bytes, 80));
+        FAIL(h, RLSIM_E_ARG, ("Illegal fasta record:\n" + head).c_str());
+    }
+    cudaSetDevice(h->device);
+    CK(h, cudaStreamSynchronize(h->st));
+    const uint32_t nt = fasta_tiles(n_bytes);
+    CK(h, h->d_fa_text.ensure(n_bytes + 64));
+    CK(h, h->d_fa_tiles.ensure((size_t)nt * fasta_tile_bytes() + 64));
+    CK(h, h->d_fa_carry.ensure(nt + 1));
+    CK(h, h->d_fa_tot.ensure(2));
+    StageTimer tm(h, RLSIM_T_LAYOUT, 4);
+    CK(h, cudaMemcpyAsync(h->d_fa_text.p, text, n_bytes, cudaMemcpyHostToDevice, h->st));
+    CK(h, cudaMemsetAsync(h->d_error.p, 0, 4, h->st));
+    launch_fasta_parse(h->st, h->d_fa_text.p, n_bytes, h->d_fa_tiles.p, h->d_fa_carry.p, h->d_fa_tot.p, nullptr, nullptr, nullptr, nullptr,
+                       h->d_error.p, 0);
+    CK(h, cudaMemcpyAsync(h->pin + 4, h->d_fa_tot.p, 16, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaStreamSynchronize(h->st));
+    CK(h, cudaGetLastError());
+    const uint64_t n_rec64 = h->pin[4], kept = h->pin[5];
+    if (n_rec64 >= (1ull << 32)) FAIL(h, RLSIM_E_UNSUPPORTED, "more than 2^32-1 FASTA records");
+    const uint32_t n_rec = (uint32_t)n_rec64;
+    CK(h, h->d_fa_rec_start.ensure(n_rec + 1)); CK(h, h->d_fa_hdr_end.ensure(n_rec + 1)); CK(h, h->d_fa_seq_off.ensure(n_rec + 1));
+    CK(h, h->d_fa_seq.ensure(kept + 64));
+    CK(h, h->d_fa_hdr_len.ensure(n_rec + 1)); CK(h, h->d_fa_name_len.ensure(n_rec + 1)); CK(h, h->d_fa_level.ensure(n_rec + 1));
+    CK(h, h->d_fa_seq_len.ensure(n_rec + 1)); CK(h, h->d_fa_valid.ensure(n_rec + 1));
+    CK(h, cudaMemsetAsync(h->d_fa_hdr_end.p, 0xff, (size_t)(n_rec + 1) * 8, h->st));
+    launch_fasta_parse(h->st, h->d_fa_text.p, n_bytes, h->d_fa_tiles.p, h->d_fa_carry.p, h->d_fa_tot.p, h->d_fa_rec_start.p,
+                       h->d_fa_hdr_end.p, h->d_fa_seq_off.p, h->d_fa_seq.p, h->d_error.p, 1);
+    launch_fasta_headers(h->st, h->d_fa_text.p, n_bytes, n_rec, h->d_fa_rec_start.p, h->d_fa_hdr_end.p, h->d_fa_seq_off.p, kept, expr_mul,
+                         h->d_fa_hdr_len.p, h->d_fa_name_len.p, h->d_fa_level.p, h->d_fa_seq_len.p, h->d_fa_valid.p);
+    h->fa_start.resize(n_rec); h->fa_hdr_len.resize(n_rec); h->fa_name_len.resize(n_rec); h->fa_level.resize(n_rec);
+    h->fa_seq_len.resize(n_rec); h->fa_valid.resize(n_rec);
+    std::vector<uint64_t> seq_off(n_rec + 1);
+    if (n_rec) {
+        D2H(h->fa_start.data(), h->d_fa_rec_start.p, (size_t)n_rec * 8); D2H(h->fa_hdr_len.data(), h->d_fa_hdr_len.p, (size_t)n_rec * 4);
+        D2H(h->fa_name_len.data(), h->d_fa_name_len.p, (size_t)n_rec * 4); D2H(h->fa_level.data(), h->d_fa_level.p, (size_t)n_rec * 8);
+        D2H(h->fa_seq_len.data(), h->d_fa_seq_len.p, (size_t)n_rec * 8); D2H(h->fa_valid.data(), h->d_fa_valid.p, (size_t)n_rec);
+        D2H(seq_off.data(), h->d_fa_seq_off.p, (size_t)n_rec * 8);
+    }
+    CK(h, cudaStreamSynchronize(h->st));
+    tm.stop();
+    CK(h, cudaGetLastError());
+    int rc;
+    if ((rc = check_device_error(h))) {
+        if (rc == RLSIM_E_UNSUPPORTED) h->err = "FASTA text with a long run of consecutive '>' characters: use the host reader";
+        return rc;
+    }
+    seq_off[n_rec] = kept;
+    h->fa_n = n_rec;
+    for (uint32_t r = 0; r < n_rec; r++) h->fa_start[r] += 1;  // name line starts after the '>'
+    // records with malformed names are skipped (input.go:108-110)
+    std::vector<uint64_t> offsets, levels;
+    offsets.reserve(n_rec + 1); levels.reserve(n_rec);
+    uint32_t n_valid = 0;
+    for (uint32_t r = 0; r < n_rec; r++) n_valid += h->fa_valid[r];
+    const uint8_t *src = h->d_fa_seq.p;
+    if (n_valid == n_rec) {
+        offsets.assign(seq_off.begin(), seq_off.end());
+        levels.assign(h->fa_level.begin(), h->fa_level.end());
+    } else {
+        std::vector<uint64_t> from;
+        uint64_t pos = 0;
+        for (uint32_t r = 0; r < n_rec; r++)
+            if (h->fa_valid[r]) { from.push_back(seq_off[r]); offsets.push_back(pos); levels.push_back(h->fa_level[r]); pos += h->fa_seq_len[r]; }
+        offsets.push_back(pos);
+        if (n_valid) {
+            CK(h, h->d_fa_seq2.ensure(pos + 64));
+            DBuf<uint64_t> d_from, d_to;
+            CK(h, d_from.ensure(n_valid)); CK(h, d_to.ensure(n_valid + 1));
+            CK(h, cudaMemcpyAsync(d_from.p, from.data(), (size_t)n_valid * 8, cudaMemcpyHostToDevice, h->st));
+            CK(h, cudaMemcpyAsync(d_to.p, offsets.data(), (size_t)(n_valid + 1) * 8, cudaMemcpyHostToDevice, h->st));
+            launch_fasta_gather(h->st, h->d_fa_seq.p, d_from.p, d_to.p, n_valid, h->d_fa_seq2.p);
+            CK(h, cudaStreamSynchronize(h->st));
+            src = h->d_fa_seq2.p;
+        }
+    }
+    if (n_records) *n_records = n_rec;
+    if (n_added) *n_added = n_valid;
+    if (!n_valid) return 0;
+    return add_core(h, nullptr, src, offsets.data(), levels.data(), n_valid);
+}
+
+int rlsim_get_fasta_index(rlsim_handle *h, uint64_t *name_start, uint32_t *line_len, uint32_t *name_len, uint64_t *level,
+                          uint64_t *seq_len, uint8_t *valid) {
+    const size_t n = h->fa_n;
+    if (name_start) memcpy(name_start, h->fa_start.data(), n * 8);
+    if (line_len) memcpy(line_len, h->fa_hdr_len.data(), n * 4);
+    if (name_len) memcpy(name_len, h->fa_name_len.data(), n * 4);
+    if (level) memcpy(level, h->fa_level.data(), n * 8);
+    if (seq_len) memcpy(seq_len, h->fa_seq_len.data(), n * 8);
+    if (valid) memcpy(valid, h->fa_valid.data(), n);
     return 0;
 }
 
@@ -1202,7 +1350,6 @@ int rlsim_get_hist(rlsim_handle *h, int kind, uint64_t *out, uint32_t n) {
     return 0;
 }
 
-#define D2H(dst, src, bytes) do { if (dst) CK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->st)); } while (0)
 
 int rlsim_get_species(rlsim_handle *h, uint32_t *tr, uint32_t *start, uint32_t *end, uint32_t *count_frag, uint64_t *count_pcr,
                       double *eff, uint32_t *gc) {

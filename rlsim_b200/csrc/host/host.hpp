@@ -51,7 +51,9 @@ struct Transcripts {                                      // input.go:103-124 re
     std::vector<uint64_t> offsets, levels;
     std::map<uint32_t, uint64_t> tr_lengths, expr_levels; // fragstats.go TrLengths / ExprLevels
 };
-Transcripts load_transcripts(const std::vector<std::string> &files, double expr_mul);  // fasta.go:113-212 + input.go:82-124
+std::string read_input(const std::vector<std::string> &files);                          // fasta.go:98-104 (io.MultiReader) or stdin
+Transcripts load_transcripts(const std::string &data, double expr_mul);                 // fasta.go:113-212 + input.go:82-124 on the host
+bool load_transcripts_device(rlsim_handle *h, const std::string &data, double expr_mul, Transcripts *out);  // the same on the GPU (bases stay there)
 
 class Report {                                            // report.go:46-148
   public:

@@ -1,5 +1,6 @@
 // FASTA input (fasta.go:113-212, input.go:82-124), JSON report (report.go:46-148), logging (logging.go:49-122).
 #include <algorithm>
+#include <cerrno>
 #include <charconv>
 #include <cmath>
 #include <chrono>
@@ -32,14 +33,15 @@ static bool parse_seq_name(const std::string &s, std::string *name, uint64_t *le
     if (d == std::string::npos || d == 0 || s.find('$', d + 1) != std::string::npos) return false;
     *name = s.substr(0, d);
     size_t i = d + 1;
-    while (i < s.size() && (s[i] == ' ' || s[i] == '\t' || s[i] == '\r' || s[i] == '\n')) i++;
+    while (i < s.size() && (s[i] == ' ' || s[i] == '\t' || s[i] == '\r' || s[i] == '\n' || s[i] == '\v' || s[i] == '\f')) i++;
     if (i >= s.size() || !isdigit((unsigned char)s[i])) return false;
     char *end;
+    errno = 0;
     *level = strtoull(s.c_str() + i, &end, 10);
-    return true;
+    return errno != ERANGE;  // strconv.ParseUint: value out of range
 }
 
-Transcripts load_transcripts(const std::vector<std::string> &files, double expr_mul) {
+std::string read_input(const std::vector<std::string> &files) {
     std::string data;
     if (files.empty()) { std::stringstream ss; ss << std::cin.rdbuf(); data = ss.str(); }
     for (auto &f : files) {  // io.MultiReader: plain concatenation
@@ -48,6 +50,35 @@ Transcripts load_transcripts(const std::vector<std::string> &files, double expr_
         std::stringstream ss; ss << in.rdbuf();
         data += ss.str();
     }
+    return data;
+}
+
+// Device-side reader: rlsim_add_fasta splits, despaces, upper-cases and parses the records on the GPU and adds them.
+// Returns false when the text needs the host reader (RLSIM_E_UNSUPPORTED); other errors are fatal as in the reference.
+bool load_transcripts_device(rlsim_handle *h, const std::string &data, double expr_mul, Transcripts *out) {
+    uint32_t n_rec = 0, n_add = 0;
+    int rc = rlsim_add_fasta(h, (const uint8_t *)data.data(), data.size(), expr_mul, &n_rec, &n_add);
+    if (rc == RLSIM_E_UNSUPPORTED) return false;
+    if (rc) fatal(rlsim_last_error(h));
+    std::vector<uint64_t> start(n_rec), level(n_rec), seq_len(n_rec);
+    std::vector<uint32_t> line_len(n_rec), name_len(n_rec);
+    std::vector<uint8_t> valid(n_rec);
+    rlsim_get_fasta_index(h, start.data(), line_len.data(), name_len.data(), level.data(), seq_len.data(), valid.data());
+    Transcripts tr;
+    tr.offsets.push_back(0);
+    for (uint32_t r = 0; r < n_rec; r++) {
+        if (!valid[r]) { log_line("Skipping transcript with malformed name: " + data.substr(start[r], line_len[r])); continue; }
+        tr.names.push_back(data.substr(start[r], name_len[r]));
+        tr.levels.push_back(level[r]);
+        tr.offsets.push_back(tr.offsets.back() + seq_len[r]);
+        tr.tr_lengths[(uint32_t)seq_len[r]] += level[r];   // input.go:115
+        tr.expr_levels[(uint32_t)level[r]] += 1;           // input.go:117
+    }
+    *out = std::move(tr);
+    return true;
+}
+
+Transcripts load_transcripts(const std::string &data, double expr_mul) {
     Transcripts tr;
     tr.offsets.push_back(0);
     size_t n = data.size(), rec = 0;

@@ -80,10 +80,15 @@ int main(int argc, char **argv) {
     }
     logv("Poly(A) tail distribution components:");
     logv(mixture_string(args.polya));
-    Transcripts tr = load_transcripts(args.input_files, args.expr_mul);
+    const std::string data = read_input(args.input_files);
     logv("Fragmenting transcripts and amplifying fragments:");
-    if (!tr.levels.empty())
-        check(h, rlsim_add_transcripts(h, tr.bases.data(), tr.offsets.data(), tr.levels.data(), (uint32_t)tr.levels.size()));
+    Transcripts tr;
+    if (getenv("RLSIM_HOST_FASTA") || !load_transcripts_device(h, data, args.expr_mul, &tr)) {
+        check(h, rlsim_clear_transcripts(h));
+        tr = load_transcripts(data, args.expr_mul);
+        if (!tr.levels.empty())
+            check(h, rlsim_add_transcripts(h, tr.bases.data(), tr.offsets.data(), tr.levels.data(), (uint32_t)tr.levels.size()));
+    }
     check(h, rlsim_build_library(h));                   // Pool.InitTranscripts
     size_t expressed = 0;
     for (auto l : tr.levels) expressed += l > 0;

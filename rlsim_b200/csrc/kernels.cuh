@@ -74,6 +74,16 @@ struct DevSampled { uint32_t *tr, *start, *end; uint8_t *minus; uint64_t *id; };
 void launch_expand(cudaStream_t st, const DevModel &m, const DevSpecies &sp, const uint64_t *out_off, uint64_t n_out,
                    DevSampled out);
 
+// k_fasta_in.cu
+uint32_t fasta_tiles(uint64_t n);
+size_t fasta_tile_bytes();
+void launch_fasta_parse(cudaStream_t st, const uint8_t *text, uint64_t n, void *tiles, uint4 *carry, unsigned long long *totals,
+                        uint64_t *rec_start, uint64_t *hdr_end, uint64_t *seq_off, uint8_t *seq, int *err, int pass);
+void launch_fasta_headers(cudaStream_t st, const uint8_t *text, uint64_t n, uint32_t n_rec, const uint64_t *rec_start,
+                          const uint64_t *hdr_end, const uint64_t *seq_off, uint64_t total_kept, double expr_mul,
+                          uint32_t *hdr_len, uint32_t *name_len, uint64_t *level, uint64_t *seq_len, uint8_t *valid);
+void launch_fasta_gather(cudaStream_t st, const uint8_t *src, const uint64_t *from, const uint64_t *to, uint32_t n, uint8_t *dst);
+
 // k_fasta.cu
 void launch_fasta_sizes(cudaStream_t st, const DevSampled &s, uint64_t n, const uint64_t *name_off, uint32_t first_index,
                         uint64_t *sizes);

@@ -11,7 +11,7 @@ from typing import List, Tuple
 
 import numpy as np
 
-_LEVEL = re.compile(rb"^[ \t\r\n]*([+-]?\d+)")
+_LEVEL = re.compile(rb"^[ \t\r\n\v\f]*(\d+)")  # TrimSpace + Sscanf("%d") into a uint64: no sign
 _DESPACE = bytes.maketrans(b"", b"")
 
 
@@ -57,17 +57,15 @@ def parse_seq_name(s: bytes):  # input.go:82-101
     if not m:
         return None
     level = int(m.group(1))
-    if level < 0:
+    if level >= 1 << 64:  # strconv.ParseUint: value out of range
         return None
     return spl[0], level
 
 
-def load_transcripts(files: List[str], expr_mul: float = 1.0, log=None):
+def load_transcripts(files: List[str], expr_mul: float = 1.0, log=None, data: bytes = None):
     """input.go:103-124 -> (names, seqs, levels); malformed names are skipped with a log line."""
-    if files:
-        data = b"".join(open(f, "rb").read() for f in files)  # io.MultiReader: plain concatenation
-    else:
-        data = sys.stdin.buffer.read()
+    if data is None:
+        data = read_input(files)
     names, seqs, levels = [], [], []
     for name, seq in read_records(data):
         parsed = parse_seq_name(name)
@@ -81,3 +79,29 @@ def load_transcripts(files: List[str], expr_mul: float = 1.0, log=None):
         seqs.append(seq)
         levels.append(level)
     return names, seqs, levels
+
+
+def read_input(files: List[str]) -> bytes:
+    """fasta.go:98-104 / input.go:45-60: the files concatenated (io.MultiReader), or stdin."""
+    if files:
+        return b"".join(open(f, "rb").read() for f in files)
+    return sys.stdin.buffer.read()
+
+
+def load_transcripts_device(handle, data: bytes, expr_mul: float = 1.0, log=None):
+    """Device-side reader (rlsim_add_fasta): the text is split, despaced, upper-cased and its `name$level` lines
+    parsed on the GPU; the records are added to `handle`.  -> (names, seq_lens, levels) of the added transcripts.
+    Same records, same skips and same log lines as load_transcripts + add_transcripts."""
+    idx = handle.add_fasta(data, expr_mul)
+    names, lens, levels = [], [], []
+    start, line_len, name_len = idx["name_start"], idx["line_len"], idx["name_len"]
+    for r in range(len(start)):
+        s0 = int(start[r])
+        if not idx["valid"][r]:
+            if log:
+                log("Skipping transcript with malformed name: %s" % data[s0:s0 + int(line_len[r])].decode("latin1"))
+            continue
+        names.append(bytes(data[s0:s0 + int(name_len[r])]))
+        lens.append(int(idx["seq_len"][r]))
+        levels.append(int(idx["level"][r]))
+    return names, lens, levels

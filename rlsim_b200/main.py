@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _native, effs
 from .args import ArgError, CmdArgs, ExitRequest
-from .fasta import load_transcripts
+from .fasta import load_transcripts, read_input
 from .mixture import mixture_string
 from .pool import FragStats, GpuPool, GpuSampler
 from .report import Report
@@ -93,9 +93,20 @@ def run(argv, out=None):
         log.v("Poly(A) tail distribution components:")
         for line in mixture_string(args.polya_param).split("\n"):
             log.v(line)
-        names, seqs, levels = load_transcripts(args.input_files, args.expr_mul, log.println)
+        levels = None
+        data = read_input(args.input_files)
         log.v("Fragmenting transcripts and amplifying fragments:")
-        pool.init_transcripts(names, seqs, levels, stats)
+        if pool.world == 1 and not os.environ.get("RLSIM_HOST_FASTA"):
+            # device-side FASTA reader (fasta.go:113-212 on the GPU); unusual texts fall back to the host reader
+            try:
+                levels = pool.init_transcripts_fasta(data, args.expr_mul, stats, log.println)
+            except _native.RlsimError as e:
+                if e.code != _native.E_UNSUPPORTED:
+                    raise
+                pool.reset()
+        if levels is None:
+            names, seqs, levels = load_transcripts(args.input_files, args.expr_mul, log.println, data=data)
+            pool.init_transcripts(names, seqs, levels, stats)
         log.v("Initialized %d transcripts." % sum(1 for lv in levels if lv > 0))
         frags = GpuSampler(args.strand_bias).sample_fragments(pool, stats)
         fasta = h.fasta(pool.names)

@@ -85,6 +85,26 @@ class GpuPool:
         self.first, self.names = a, names[a:b]
         h.set_first_index(a)
         h.add_transcripts(seqs[a:b], levels[a:b])
+        return self._build(stats)
+
+    def init_transcripts_fasta(self, data: bytes, expr_mul: float = 1.0, stats: FragStats = None, log=None):
+        """pool.go:83-135 fed by the device-side FASTA reader (single GPU): `data` = raw text of the input files.
+        -> levels of the added transcripts."""
+        from .fasta import load_transcripts_device
+        if self.world != 1:
+            raise ValueError("the device FASTA reader serves the single-GPU path; shards are cut by the host reader")
+        h = self.handle
+        h.set_first_index(0)
+        names, lens, levels = load_transcripts_device(h, data, expr_mul, log)
+        if stats is not None:
+            for ln, lv in zip(lens, levels):
+                stats.update_input(ln, lv)
+        self.first, self.names = 0, names
+        self._build(stats)
+        return levels
+
+    def _build(self, stats):
+        h = self.handle
         h.build_library()
         if stats is not None:
             st = h.stats()

@@ -40,5 +40,19 @@ def write_fasta(path, bases, off, levels, first=0, count=None, width=0):
             f.write(b"\n")
 
 
+def fasta_text(bases, off, levels, width=70):
+    """The same records as one in-memory FASTA text (uint8 array), sequences wrapped at `width` columns."""
+    parts = []
+    for i in range(len(levels)):
+        parts.append(b">T%07d$%d\n" % (i, int(levels[i])))
+        seq = bases[int(off[i]):int(off[i + 1])].tobytes()
+        if width:
+            parts.append(b"\n".join(seq[j:j + width] for j in range(0, len(seq), width)))
+        else:
+            parts.append(seq)
+        parts.append(b"\n")
+    return np.frombuffer(b"".join(parts), dtype=np.uint8)
+
+
 def names_for(n, first=0):
     return [b"T%07d" % i for i in range(first, first + n)]
