@@ -134,6 +134,8 @@ struct rlsim_handle {
     DBuf<uint32_t> d_Ff, d_Fr;                          // fine (in-block) prefix sums
     uint32_t prefix_upto = 0;  // transcripts [0, prefix_upto) have valid priming prefix sums for the current model
     bool lut_valid = false;
+    int lut_k = 0; double lut_T = 0; bool lut_sym = false, want_mirror = true;  // cached k-mer table; reverse-complement symmetric after quantisation
+    DBuf<uint32_t> d_dirty;  // per transcript: letters outside ACGT present
     // model tables
     DBuf<double> d_gc_raw, d_len_eff, d_raw_prob, d_K;
     DBuf<uint32_t> d_raw_len, d_wq_f, d_wq_r;
@@ -264,6 +266,8 @@ DevTranscripts make_tr(rlsim_handle *h) {
     t.Fr = needs_rev(h->p.frag_method) ? h->d_Fr.p : nullptr;
     t.Cr = needs_rev(h->p.frag_method) ? h->d_Cr.p : nullptr;
     t.gc = h->d_gc.p;
+    t.dirty = h->d_dirty.p;
+    t.sym = h->lut_sym && h->want_mirror ? 1 : 0;
     return t;
 }
 
@@ -306,9 +310,12 @@ int launch_prefix_range(rlsim_handle *h, uint32_t t0, uint32_t t1) {
     if (!h->lut_valid) {
         uint32_t nk = 1u << (2 * h->p.kmer_len);
         CK(h, h->d_K.ensure(nk)); CK(h, h->d_wq_f.ensure(nk)); CK(h, h->d_wq_r.ensure(nk));
-        launch_kmer_lut(h->st, h->p.kmer_len, h->p.priming_temp, h->d_K.p, h->d_kmax.p, h->d_wq_f.p, h->d_wq_r.p);
-        h->lut_valid = true;
-        h->launches[RLSIM_T_PREFIX] += 2;
+        launch_kmer_lut(h->st, h->p.kmer_len, h->p.priming_temp, h->d_K.p, h->d_kmax.p, h->d_wq_f.p, h->d_wq_r.p, h->d_work.p + 2);
+        CK(h, cudaMemcpyAsync(h->pin + 6, h->d_work.p + 2, 4, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaStreamSynchronize(h->st));
+        h->lut_sym = *reinterpret_cast<unsigned int *>(h->pin + 6) == 0;
+        h->lut_valid = true; h->lut_k = h->p.kmer_len; h->lut_T = h->p.priming_temp;
+        h->launches[RLSIM_T_PREFIX] += 3;
     }
     launch_prefix(h->st, make_tr(h), t0, t1, h->p.kmer_len, h->p.priming_temp, h->d_wq_f.p, h->d_wq_r.p, h->d_kmax.p,
                   h->d_Ff.p, h->d_Fr.p, h->d_Cf.p, h->d_Cr.p, needs_rev(method) ? 2 : 1, h->d_work.p);
@@ -566,7 +573,8 @@ int rlsim_set_model(rlsim_handle *h, const rlsim_params *p) {
     if (!h->h_len.empty() && h->polya_max != (uint32_t)mx) FAIL(h, RLSIM_E_ARG, "poly(A) maximum cannot change after transcripts were added");
     h->polya_max = (uint32_t)mx;
     h->prefix_upto = 0;
-    h->lut_valid = false;
+    h->lut_valid = h->lut_valid && h->lut_k == p->kmer_len && h->lut_T == p->priming_temp;
+    h->want_mirror = getenv("RLSIM_NO_MIRROR") == nullptr;  // diagnostic switch: always build explicit reverse arrays
     h->len_eff_ready = false;
     eager_reset(h);
     if (p->n_target > 0) {
@@ -720,6 +728,7 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     }
     const bool want_eager = (want_prefix || !needs_fwd(h->p.frag_method)) && eager_possible(h, n0);
     CK(h, h->d_off.ensure(nn + 1)); CK(h, h->d_len.ensure(nn)); CK(h, h->d_expr.ensure(nn));
+    CK(h, h->d_dirty.grow_preserve(nn + 1, n0, h->st));
     if (want_eager) {
         CK(h, h->d_mol_off.ensure(nn + 1));
         CK(h, cudaMemcpyAsync(h->d_mol_off.p, h->h_mol_off.data(), (size_t)(nn + 1) * 8, cudaMemcpyHostToDevice, h->st));
@@ -771,7 +780,7 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
             const uint32_t t0 = cuts[cc], t1 = cuts[cc + 1];
             CK(h, cudaStreamWaitEvent(h->st, h->ev_chunk[cc], 0));
             launch_ingest(h->st, src, h->staging.off.p + t0, t1 - t0, n0 + t0, (h->h_off[n0 + t1] - h->h_off[n0 + t0]) >> 5,
-                          h->polya_max, h->d_off.p + n0 + t0, h->d_bases.p, h->d_packed.p, h->d_nmask.p, h->d_gc.p);
+                          h->polya_max, h->d_off.p + n0 + t0, h->d_bases.p, h->d_packed.p, h->d_nmask.p, h->d_gc.p, h->d_dirty.p);
             h->launches[RLSIM_T_LAYOUT] += 2;
             if (want_prefix) { int rc = launch_prefix_range(h, n0 + t0, n0 + t1); if (rc) return rc; }
         }
@@ -1424,7 +1433,7 @@ int rlsim_probe_kmer_lut(rlsim_handle *h, double *K_out, uint32_t *w_out, uint32
     uint32_t nk = 1u << (2 * h->p.kmer_len);
     if (n != nk) FAIL(h, RLSIM_E_ARG, "k-mer table size mismatch");
     CK(h, h->d_K.ensure(nk)); CK(h, h->d_wq_f.ensure(nk)); CK(h, h->d_wq_r.ensure(nk));
-    launch_kmer_lut(h->st, h->p.kmer_len, h->p.priming_temp, h->d_K.p, h->d_kmax.p, h->d_wq_f.p, h->d_wq_r.p);
+    launch_kmer_lut(h->st, h->p.kmer_len, h->p.priming_temp, h->d_K.p, h->d_kmax.p, h->d_wq_f.p, h->d_wq_r.p, h->d_work.p + 2);
     CK(h, cudaGetLastError());
     D2H(K_out, h->d_K.p, (size_t)nk * 8);
     D2H(w_out, h->d_wq_f.p, (size_t)nk * 4);
@@ -1439,13 +1448,26 @@ int rlsim_probe_prefix(rlsim_handle *h, uint32_t tr, int reverse, uint64_t *out,
     cudaSetDevice(h->device);
     // rebuild P(0..proflen) from the two levels: P(i) = coarse[i >> 6] + (i & 63 ? fine[i - 1] : 0)
     uint32_t proflen = h->h_len[tr] > (uint32_t)h->p.kmer_len ? h->h_len[tr] - h->p.kmer_len : 0;
-    uint32_t have = proflen + 1, nblk = (proflen + 63) / 64;
-    std::vector<uint32_t> fine(std::max<uint32_t>(proflen, 1));
+    const bool sym = make_tr(h).sym != 0;
+    bool mirror = false;
+    if (sym && reverse) {
+        uint32_t dirty = 0;
+        CK(h, cudaMemcpyAsync(&dirty, h->d_dirty.p + tr, 4, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaStreamSynchronize(h->st));
+        mirror = dirty == 0;
+    }
+    const bool use_rev = reverse && !mirror;
+    const uint32_t entries = proflen + ((sym && !use_rev && h->h_len[tr] >= (uint32_t)h->p.kmer_len) ? 1 : 0);  // windows held
+    const uint32_t nblk = (entries + 63) / 64;
+    std::vector<uint32_t> fine(std::max<uint32_t>(entries, 1));
     std::vector<uint64_t> coarse(nblk + 1);
-    if (proflen) CK(h, cudaMemcpyAsync(fine.data(), (reverse ? h->d_Fr.p : h->d_Ff.p) + h->h_off[tr], (size_t)proflen * 4, cudaMemcpyDeviceToHost, h->st));
-    CK(h, cudaMemcpyAsync(coarse.data(), (reverse ? h->d_Cr.p : h->d_Cf.p) + coarse_base(h->h_off[tr], tr), (size_t)(nblk + 1) * 8, cudaMemcpyDeviceToHost, h->st));
+    if (entries) CK(h, cudaMemcpyAsync(fine.data(), (use_rev ? h->d_Fr.p : h->d_Ff.p) + h->h_off[tr], (size_t)entries * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaMemcpyAsync(coarse.data(), (use_rev ? h->d_Cr.p : h->d_Cf.p) + coarse_base(h->h_off[tr], tr), (size_t)(nblk + 1) * 8, cudaMemcpyDeviceToHost, h->st));
     CK(h, cudaStreamSynchronize(h->st));
-    for (uint32_t i = 0; i < std::min(n, have); i++) out[i] = coarse[i >> 6] + ((i & 63) ? fine[i - 1] : 0);
+    auto P = [&](uint32_t i) { return coarse[i >> 6] + ((i & 63) ? fine[i - 1] : 0); };
+    const uint32_t have = proflen + 1;
+    for (uint32_t i = 0; i < std::min(n, have); i++)
+        out[i] = mirror ? P(proflen + 1) - P(proflen + 1 - i) : P(i);  // mirrored: P_rev(i) = W(n+1) - W(n+1-i)
     return 0;
 }
 

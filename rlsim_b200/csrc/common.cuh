@@ -51,6 +51,9 @@ struct DevTranscripts {
     // coarse = u64 sum of everything before each block at coarse_base(off[t], t)
     const uint32_t *Ff, *Fr;
     const uint64_t *Cf, *Cr;
+    const uint32_t *dirty;    // per transcript: non-zero when a letter outside ACGT occurs (incl. the poly(A) tail: never)
+    int sym;                  // quantised k-mer table is reverse-complement symmetric: clean transcripts carry no reverse
+                              // arrays, their forward arrays hold one more entry (window len-k) and are read mirrored
     const uint2 *gc;          // per 32-base group {#GC before the group, GC bit mask of the group}; transcript t has
                               // padded_len/32 + 1 entries starting at off[t]/32 + t (see gc_before)
 };

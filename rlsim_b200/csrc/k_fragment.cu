@@ -49,14 +49,8 @@ __device__ __forceinline__ PxStream mol_stream(const DevModel &m, uint32_t tg, u
 // 64 u32 sums lands within a few entries, and a short walk finishes - ~3 dependent round trips where bisection of a
 // flat u64 array needs ~11.
 constexpr int PRIME_INTERP_STEPS = 4;
-__device__ __forceinline__ bool priming(const PxStream &iv, uint32_t block, const Profile &pf, uint32_t proflen,
-                                        uint32_t start, uint32_t end, uint32_t &res) {
-    if (end > proflen) end = proflen;
-    if (start >= end) { res = 0; return true; }
-    const uint64_t ps = pf.P(start), pe = pf.P(end);
-    const uint64_t total = pe - ps;
-    if (total == 0) return false;
-    const uint64_t tgt = ps + iv.below(block, total);
+// smallest i in [start, end) with P(i+1) > tgt, given P(start) <= tgt < P(end); plen = number of profile entries held
+__device__ __forceinline__ uint32_t prime_search(const Profile &pf, uint32_t plen, uint32_t start, uint32_t end, uint64_t tgt) {
     // ---- block b in [bs, be] with C[b] <= tgt < C[b+1]   (C[bs] <= P(start) <= tgt < P(end) <= C[be+1])
     uint32_t lo = start >> PFX_BLOCK_SHIFT, hi = ((end - 1) >> PFX_BLOCK_SHIFT) + 1;
     uint64_t clo = 0, chi = 0;  // = C[lo], C[hi] whenever `have`
@@ -84,13 +78,44 @@ __device__ __forceinline__ bool priming(const PxStream &iv, uint32_t block, cons
     // ---- entry j of the block: smallest j with fine[64 b + j] > r
     const uint32_t r = (uint32_t)(tgt - clo);
     const uint32_t base = b << PFX_BLOCK_SHIFT;
-    const uint32_t nb = min(PFX_BLOCK, proflen - base);
+    const uint32_t nb = min(PFX_BLOCK, plen - base);
     const uint32_t *F = pf.F + base;
     uint32_t j = (uint32_t)(((uint64_t)r * nb) / (chi - clo));  // chi - clo = block sum > r
     if (j >= nb) j = nb - 1;
     if (F[j] > r) { while (j > 0 && F[j - 1] > r) j--; }
     else { do { j++; } while (F[j] <= r); }  // F[nb-1] = block sum > r: terminates inside the block
-    res = base + j;
+    return base + j;
+}
+
+__device__ __forceinline__ bool priming(const PxStream &iv, uint32_t block, const Profile &pf, uint32_t proflen,
+                                        uint32_t start, uint32_t end, uint32_t &res) {
+    if (end > proflen) end = proflen;
+    if (start >= end) { res = 0; return true; }
+    const uint64_t ps = pf.P(start), pe = pf.P(end);
+    const uint64_t total = pe - ps;
+    if (total == 0) return false;
+    res = prime_search(pf, proflen, start, end, ps + iv.below(block, total));
+    return true;
+}
+
+// The same draw on the reverse profile of a transcript without non-ACGT letters when the quantised k-mer table is
+// reverse-complement symmetric: reverse entry j is forward window n - j (n = proflen), so with W = forward prefix sums
+// over the n + 1 windows, P_rev(j) = W(n+1) - W(n+1-j).  "Smallest j in [s, e) with P_rev(j+1) > P_rev(s) + u" becomes
+// "smallest x in [n-e+1, n-s+1) with W(x+1) > W(n-s+1) - u - 1", j = n - x: no reverse arrays are needed.
+__device__ __forceinline__ bool priming_reverse(const PxStream &iv, uint32_t block, const Profile &pfwd, const Profile &prev,
+                                                bool mirror, uint32_t proflen, uint32_t start, uint32_t end, uint32_t &res) {
+    if (end > proflen) end = proflen;
+    if (start >= end) { res = 0; return true; }
+    // one search serves both representations (a single inlined copy keeps the register count of k_intervals down)
+    const Profile pf = mirror ? pfwd : prev;
+    const uint32_t plen = mirror ? proflen + 1 : proflen;
+    const uint32_t lo = mirror ? proflen - end + 1 : start, hi = mirror ? proflen - start + 1 : end;
+    const uint64_t plo = pf.P(lo), phi = pf.P(hi);
+    const uint64_t total = phi - plo;
+    if (total == 0) return false;
+    const uint64_t u = iv.below(block, total);
+    const uint32_t x = prime_search(pf, plen, lo, hi, mirror ? phi - u - 1 : plo + u);
+    res = mirror ? proflen - x : x;
     return true;
 }
 
@@ -135,6 +160,7 @@ struct MolCtx {
     uint32_t t, tg, L, proflen;
     uint64_t off;
     Profile Pf, Pr;
+    bool mirror;  // reverse profile = forward arrays read backwards (symmetric table, no non-ACGT letter)
 };
 
 // One interval of the after_* methods, fragmentor.go:132-175
@@ -150,7 +176,7 @@ __device__ __forceinline__ void after_interval(const DevModel &m, const MolCtx &
         if (doublePrime) {
             uint32_t final = c.L - 1;
             uint32_t ss = final - end + 1, ee = final - new_start + 1, ns;
-            if (!priming(iv, 4 * i + 1, c.Pr, c.proflen, ss, ee, ns)) { atomicExch(o.error, RLSIM_E_PRIMING); return; }
+            if (!priming_reverse(iv, 4 * i + 1, c.Pf, c.Pr, c.mirror, c.proflen, ss, ee, ns)) { atomicExch(o.error, RLSIM_E_PRIMING); return; }
             end = final - ns + 1;
         }
     } else {
@@ -251,6 +277,7 @@ __device__ __forceinline__ MolCtx make_ctx(const DevModel &m, const DevTranscrip
     c.off = tr.off[t];
     c.Pf = Profile{tr.Ff ? tr.Ff + c.off : nullptr, tr.Cf ? tr.Cf + coarse_base(c.off, t) : nullptr};
     c.Pr = Profile{tr.Fr ? tr.Fr + c.off : nullptr, tr.Cr ? tr.Cr + coarse_base(c.off, t) : nullptr};
+    c.mirror = tr.sym && tr.Fr && tr.dirty[t] == 0;
     return c;
 }
 
@@ -310,7 +337,7 @@ k_fragment(const __grid_constant__ DevModel m, DevTranscripts tr, uint64_t g_beg
 // One thread per queued interval: the two dependent priming searches (nnthermo.go:203-217) + filters + emit.
 // Kept separate from k_fragment so that this latency-bound part runs lean (few registers, full occupancy).
 constexpr int IV_THREADS = 256;
-__global__ void __launch_bounds__(IV_THREADS)
+__global__ void __launch_bounds__(IV_THREADS, 5)
 k_intervals(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, uint64_t n_q, uint32_t hist_s_n) {
     extern __shared__ unsigned int hist_s[];
     for (uint32_t i = threadIdx.x; i < hist_s_n; i += IV_THREADS) hist_s[i] = 0;

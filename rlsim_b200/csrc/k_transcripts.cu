@@ -34,7 +34,7 @@ __device__ __forceinline__ uint32_t gather_bit0(uint32_t z) {  // bit 0 of each 
 __global__ void __launch_bounds__(INGEST_THREADS)
 k_ingest(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, uint32_t n, uint32_t t_index0, uint32_t polya_max,
          const uint64_t *__restrict__ off, uint8_t *__restrict__ bases, uint32_t *__restrict__ packed,
-         uint32_t *__restrict__ nmask, uint2 *__restrict__ gc) {
+         uint32_t *__restrict__ nmask, uint2 *__restrict__ gc, uint32_t *__restrict__ dirty) {
     const uint64_t P0 = off[0], n_groups = (off[n] - P0) >> 5;
     const uint64_t g = (uint64_t)blockIdx.x * INGEST_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -98,6 +98,11 @@ k_ingest(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, 
     dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
     *reinterpret_cast<uint2 *>(packed + (P >> 4)) = make_uint2(pk0, pk1);
     nmask[P >> 5] = mk;
+    {   // letters outside ACGT among the real positions [p0, L) of this group
+        const uint32_t nreal = L > p0 ? min(L - p0, 32u) : 0u;
+        const uint32_t real = nreal >= 32 ? 0xffffffffu : ((1u << nreal) - 1u);
+        if (mk & real) atomicOr(&dirty[t_index0 + t], 1u);
+    }
     gc[(P >> 5) + t_index0 + t] = make_uint2(__popc(gm), gm);
 }
 
@@ -126,11 +131,13 @@ k_gc_scan(uint32_t n, uint32_t t_index0, const uint64_t *__restrict__ off, uint2
 
 // src_off / off point at the first transcript of the batch; t_index0 is its index on this handle
 void launch_ingest(cudaStream_t st, const uint8_t *src, const uint64_t *src_off, uint32_t n, uint32_t t_index0, uint64_t n_groups,
-                   uint32_t polya_max, const uint64_t *off, uint8_t *bases, uint32_t *packed, uint32_t *nmask, uint2 *gc) {
+                   uint32_t polya_max, const uint64_t *off, uint8_t *bases, uint32_t *packed, uint32_t *nmask, uint2 *gc,
+                   uint32_t *dirty) {
     if (!n) return;
+    cudaMemsetAsync(dirty + t_index0, 0, (size_t)n * 4, st);
     if (n_groups)
         k_ingest<<<(unsigned)((n_groups + INGEST_THREADS - 1) / INGEST_THREADS), INGEST_THREADS, 0, st>>>(
-            src, src_off, n, t_index0, polya_max, off, bases, packed, nmask, gc);
+            src, src_off, n, t_index0, polya_max, off, bases, packed, nmask, gc, dirty);
     k_gc_scan<<<(n + INGEST_THREADS / 32 - 1) / (INGEST_THREADS / 32), INGEST_THREADS, 0, st>>>(n, t_index0, off, gc);
 }
 
@@ -193,12 +200,20 @@ __global__ void k_kmer_quant(int k, const double *__restrict__ K, const unsigned
     wq_r[c] = quantize(K[rc_code(c, k)], scale);
 }
 
+__global__ void k_lut_asym(int k, const uint32_t *__restrict__ wq_f, const uint32_t *__restrict__ wq_r, unsigned int *asym) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < (1u << (2 * k)) && wq_f[c] != wq_r[c]) atomicOr(asym, 1u);
+}
+
+// *asym != 0 afterwards: some k-mer and its reverse complement quantise to different weights
 void launch_kmer_lut(cudaStream_t st, int k, double T, double *K, unsigned long long *kmax_bits, uint32_t *wq_f,
-                     uint32_t *wq_r) {
+                     uint32_t *wq_r, unsigned int *asym) {
     uint32_t n = 1u << (2 * k);
     cudaMemsetAsync(kmax_bits, 0, 8, st);
     k_kmer_lut<<<(n + 127) / 128, 128, 0, st>>>(k, T, K, kmax_bits);
     k_kmer_quant<<<(n + 127) / 128, 128, 0, st>>>(k, K, kmax_bits, wq_f, wq_r);
+    cudaMemsetAsync(asym, 0, 4, st);
+    k_lut_asym<<<(n + 127) / 128, 128, 0, st>>>(k, wq_f, wq_r, asym);
 }
 
 // ---------------------------------------------------------------- priming prefix sums
@@ -265,9 +280,11 @@ k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, c
         const uint64_t o = tr.off[t];
         uint32_t *F = (reverse ? Fr : Ff) + o;
         uint64_t *C = (reverse ? Cr : Cf) + coarse_base(o, t);
+        if (tr.sym && reverse && tr.dirty[t] == 0) continue;  // read mirrored from the forward arrays (priming_mirror)
         if (lane == 0) C[0] = 0;
-        if (L <= (uint32_t)k) continue;
-        const uint32_t proflen = L - (uint32_t)k;
+        if (L < (uint32_t)k + (tr.sym && !reverse ? 0u : 1u)) continue;
+        // symmetric mode: the forward arrays also hold window len-k, the first window of the reverse profile
+        const uint32_t proflen = L - (uint32_t)k + (tr.sym && !reverse ? 1u : 0u);
         uint64_t carry = 0;  // sum of all weights before this sub-tile
 
         uint32_t ib = lane * PFX_ITEMS;

@@ -319,6 +319,35 @@ def test_eager_chunk_pipeline_equals_monolithic(gpu, monkeypatch, flags):
         assert (sm.n_fragments, sm.n_species, sm.pool_total, sm.n_sampled) == (sh.n_fragments, sh.n_species, sh.pool_total, sh.n_sampled)
 
 
+def test_mirrored_reverse_profile_equals_explicit_arrays(oracle, gpu, monkeypatch):
+    """The quantised k-mer table is reverse-complement symmetric (checked on the device when it is built), so
+    transcripts without non-ACGT letters carry no reverse prefix sums: the reverse priming draw searches the forward
+    arrays mirrored.  Same fragments as with explicit reverse arrays (RLSIM_NO_MIRROR) and as the oracle."""
+    args = util.parse(["-n", "30000", "-c", "7", "-si", "77", "-f", "after_prim_double"])
+    names, seqs, levels = util.synth_transcriptome(120, seed=5, mean_len=1400, hi=6000, total_molecules=40000, non_acgt=0.0)
+    rng = np.random.default_rng(3)
+    seqs = list(seqs)
+    for t in (0, 7, 8, 50, 119):  # a few transcripts with letters outside ACGT keep their explicit reverse arrays
+        b = bytearray(seqs[t])
+        for pos in rng.integers(0, len(b), size=5):
+            b[pos] = ord("N") if pos % 2 else ord("R")
+        seqs[t] = bytes(b)
+    seqs[20] = seqs[20][:6]   # exactly k bases + tail
+    seqs[21] = seqs[21][:3]
+    mirrored = util.run_gpu(gpu, args, names, seqs, levels)
+    monkeypatch.setenv("RLSIM_NO_MIRROR", "1")
+    explicit = util.run_gpu(gpu, args, names, seqs, levels)
+    monkeypatch.delenv("RLSIM_NO_MIRROR")
+    for k in ("tr", "start", "end", "count0", "count"):
+        assert np.array_equal(mirrored.species()[k], explicit.species()[k]), k
+    assert mirrored.fasta(names) == explicit.fasta(names)
+    o = util.run_oracle(oracle, args, names, seqs, levels, oracle.MODE_PHILOX)
+    assert mirrored.fasta(names) == o.fasta(names)
+    for t in (0, 1, 7, 20, 21, 119):  # reverse prefix sums reconstructed from either representation
+        n = len(seqs[t]) + int(mirrored.stats().polya_max) + 1
+        assert np.array_equal(mirrored.probe_prefix(t, 1, n), explicit.probe_prefix(t, 1, n)), t
+
+
 def test_degenerate_inputs(oracle, gpu):
     """Nothing expressed; a single molecule; primer length 1 and 12 (LUT in global memory); fixed-length tails."""
     names, seqs, levels = util.synth_transcriptome(5, seed=2, mean_len=800, hi=2000, total_molecules=100)
