@@ -76,6 +76,7 @@ __global__ void k_class_totals(const uint64_t *cls_pre, const uint64_t *bounds, 
 
 }  // namespace
 
+struct PendingTime { int stage; cudaEvent_t a, b; };  // a stage timer whose events have not been resolved yet
 struct rlsim_handle {
     int device = 0;
     cudaStream_t st = nullptr;
@@ -98,10 +99,14 @@ struct rlsim_handle {
     Staging staging;
     cudaStream_t st_copy = nullptr;  // H2D of the next chunk overlaps ingest/prefix of the previous one
     cudaStream_t st_pcr = nullptr;   // eager pipeline: PCR of group g (FP64 issue bound) overlaps the memory-bound stages of group g+1
-    cudaEvent_t ev_sp = nullptr, ev_pcr = nullptr;
+    cudaEvent_t ev_sp = nullptr, ev_pcr = nullptr, ev_ingest = nullptr, ev_aux = nullptr;
+    cudaStream_t st_aux = nullptr;   // target-length sampling runs beside the transcript pipeline
+    bool target_pending = false;     // the sampled histogram is still on the device (target_host)
+    uint32_t target_hist_n = 0;
     bool pcr_in_flight = false;
     unsigned long long *pin = nullptr;  // pinned scratch for the small device-to-host count reads
-    std::vector<cudaEvent_t> ev_chunk;
+    std::vector<cudaEvent_t> ev_chunk, ev_free;
+    std::vector<PendingTime> pending_times;  // stage timers not yet resolved (drain_timers)
     std::vector<uint64_t> h_srclen;  // unpadded lengths as added
     std::vector<uint64_t> h_expr;
     std::vector<uint64_t> h_off;     // padded offsets [n+1]
@@ -194,18 +199,35 @@ static std::string g_create_error;
 
 namespace {
 
+// Stage timing never blocks the host: event pairs are parked and resolved when the timings are read.
+void drain_timers(rlsim_handle *h);
 struct StageTimer {
     rlsim_handle *h;
     int stage;
-    StageTimer(rlsim_handle *h_, int s, uint64_t nl) : h(h_), stage(s) { cudaEventRecord(h->ev0, h->st); h->launches[s] += nl; }
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    StageTimer(rlsim_handle *h_, int s, uint64_t nl, cudaStream_t stream = nullptr) : h(h_), stage(s), st(stream ? stream : h_->st) {
+        for (cudaEvent_t *e : {&a, &b}) {
+            if (!h->ev_free.empty()) { *e = h->ev_free.back(); h->ev_free.pop_back(); }
+            else cudaEventCreate(e);
+        }
+        cudaEventRecord(a, st);
+        h->launches[s] += nl;
+    }
     void stop() {
-        cudaEventRecord(h->ev1, h->st);
-        cudaEventSynchronize(h->ev1);
-        float t = 0;
-        cudaEventElapsedTime(&t, h->ev0, h->ev1);
-        h->ms[stage] += t;
+        cudaEventRecord(b, st);
+        h->pending_times.push_back(PendingTime{stage, a, b});
+        if (h->pending_times.size() > 512) drain_timers(h);
     }
 };
+void drain_timers(rlsim_handle *h) {
+    for (auto &p : h->pending_times) {
+        float t = 0;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) h->ms[p.stage] += t;
+        h->ev_free.push_back(p.a); h->ev_free.push_back(p.b);
+    }
+    h->pending_times.clear();
+}
 
 int check_device_error(rlsim_handle *h) {
     int e = 0;
@@ -525,8 +547,11 @@ int rlsim_create(int device, rlsim_handle **out) {
     if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&h->st_pcr, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->st_aux, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&h->ev_sp, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&h->ev_pcr, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&h->ev_ingest, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaHostAlloc((void **)&h->pin, 64, cudaHostAllocDefault)) != cudaSuccess ||
         (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
         (e = h->d_error.ensure(1)) != cudaSuccess || (e = h->d_counters.ensure(4)) != cudaSuccess ||
@@ -543,11 +568,16 @@ int rlsim_create(int device, rlsim_handle **out) {
 void rlsim_destroy(rlsim_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    drain_timers(h);
     for (auto e : h->ev_chunk) cudaEventDestroy(e);
+    for (auto e : h->ev_free) cudaEventDestroy(e);
     if (h->st_copy) cudaStreamDestroy(h->st_copy);
     if (h->st_pcr) cudaStreamDestroy(h->st_pcr);
+    if (h->st_aux) cudaStreamDestroy(h->st_aux);
+    if (h->ev_aux) cudaEventDestroy(h->ev_aux);
     if (h->ev_sp) cudaEventDestroy(h->ev_sp);
     if (h->ev_pcr) cudaEventDestroy(h->ev_pcr);
+    if (h->ev_ingest) cudaEventDestroy(h->ev_ingest);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -605,6 +635,16 @@ int rlsim_set_raw_target(rlsim_handle *h, const uint32_t *lengths, const double 
     return upload_tables(h);
 }
 
+// bring the sampled target histogram to the host (no-op when it is already there)
+static int target_host(rlsim_handle *h) {
+    if (!h->target_pending) return 0;
+    h->target_pending = false;
+    h->h_target.assign(h->target_hist_n, 0);
+    CK(h, cudaMemcpyAsync(h->h_target.data(), h->d_hist_target.p, (size_t)h->target_hist_n * 8, cudaMemcpyDeviceToHost, h->st_aux));
+    CK(h, cudaStreamSynchronize(h->st_aux));
+    return 0;
+}
+
 static int sample_target_range(rlsim_handle *h, uint64_t first, uint64_t count, bool whole) {
     if (!h->have_model) FAIL(h, RLSIM_E_ARG, "rlsim_set_model first");
     bool raw = h->p.n_target == 0;
@@ -614,18 +654,26 @@ static int sample_target_range(rlsim_handle *h, uint64_t first, uint64_t count, 
     if (raw) hist_n = *std::max_element(h->raw_len.begin(), h->raw_len.end()) + 1;
     else { uint64_t mn, mx; mix_minmax(h->p.target, h->p.n_target, &mn, &mx); hist_n = (uint32_t)mx + 1; }
     CK(h, h->d_hist_target.ensure(hist_n));
-    CK(h, cudaMemsetAsync(h->d_hist_target.p, 0, (size_t)hist_n * 8, h->st));
+    // The draws depend on nothing but the model: they run on their own stream beside the transcript pipeline, and the
+    // histogram comes to the host when it is first needed (target_host).
+    CK(h, cudaEventRecord(h->ev_aux, h->st));                 // model tables uploaded, earlier readers of the histogram done
+    CK(h, cudaStreamWaitEvent(h->st_aux, h->ev_aux, 0));
+    CK(h, cudaMemsetAsync(h->d_hist_target.p, 0, (size_t)hist_n * 8, h->st_aux));
     DevModel m = make_model(h);
-    StageTimer tm(h, RLSIM_T_TARGET, 1);
-    launch_target(h->st, m, first, count, h->d_hist_target.p, hist_n);
+    StageTimer tm(h, RLSIM_T_TARGET, 1, h->st_aux);
+    launch_target(h->st_aux, m, first, count, h->d_hist_target.p, hist_n);
     tm.stop();
     CK(h, cudaGetLastError());
-    h->h_target.assign(hist_n, 0);
-    CK(h, cudaMemcpyAsync(h->h_target.data(), h->d_hist_target.p, (size_t)hist_n * 8, cudaMemcpyDeviceToHost, h->st));
-    CK(h, cudaStreamSynchronize(h->st));
+    h->target_pending = true;
+    h->target_hist_n = hist_n;
     h->req_frags = count;
     h->have_target = whole;  // a partial histogram must be completed with rlsim_set_target_hist
-    if (raw && whole) { raw_target_finish(h); h->len_eff_ready = false; if (h->eager_upto) { h->eager_upto = 0; h->eager_failed = true; } }
+    if (getenv("RLSIM_SYNC_TARGET")) { int rc = target_host(h); if (rc) return rc; }
+    if (raw && whole) {  // the raw target's range and mean shape the library: needed now
+        int rc = target_host(h);
+        if (rc) return rc;
+        raw_target_finish(h); h->len_eff_ready = false; if (h->eager_upto) { h->eager_upto = 0; h->eager_failed = true; }
+    }
     return 0;
 }
 
@@ -643,6 +691,7 @@ int rlsim_set_target_hist(rlsim_handle *h, const uint32_t *lengths, const uint64
     uint32_t mx = 0;
     for (uint32_t i = 0; i < n; i++) mx = std::max(mx, lengths[i]);
     if (mx >= (1u << 24)) FAIL(h, RLSIM_E_UNSUPPORTED, "maximum fragment length >= 2^24");
+    if (h->target_pending) { cudaSetDevice(h->device); CK(h, cudaStreamSynchronize(h->st_aux)); h->target_pending = false; }
     h->h_target.assign((size_t)mx + 1, 0);
     h->req_frags = 0;
     for (uint32_t i = 0; i < n; i++) { h->h_target[lengths[i]] += counts[i]; h->req_frags += counts[i]; }
@@ -666,6 +715,7 @@ int rlsim_clear_transcripts(rlsim_handle *h) {
     h->sum_expr = h->sum_expr_len = 0; h->mol_off_valid = false;
     h->h_mol_off.clear();
     eager_reset(h);
+    drain_timers(h);
     memset(h->ms, 0, sizeof h->ms);
     memset(h->launches, 0, sizeof h->launches);
     return 0;
@@ -678,7 +728,6 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     if (!h->have_model) FAIL(h, RLSIM_E_ARG, "rlsim_set_model must precede rlsim_add_transcripts (the poly(A) maximum shapes the layout)");
     if (n == 0) return 0;
     cudaSetDevice(h->device);
-    CK(h, cudaStreamSynchronize(h->st));  // earlier kernels may still read the staging buffer / offset arrays
     const uint32_t n0 = (uint32_t)h->h_len.size();
     const uint64_t nbytes = offsets[n] - offsets[0];
     if (h->h_off.empty()) h->h_off.push_back(0);
@@ -739,14 +788,22 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     CK(h, cudaMemcpyAsync(h->d_expr.p, h->h_expr.data(), (size_t)nn * 8, cudaMemcpyHostToDevice, h->st));
     CK(h, cudaMemsetAsync(h->d_packed.p + tot / 16, 0, 8 * 4, h->st));
     CK(h, cudaMemsetAsync(h->d_nmask.p + tot / 32, 0, 8 * 4, h->st));
-    if (!dev_bases) CK(h, h->staging.bases.ensure(nbytes + 64));  // k_ingest reads whole aligned words
-    const uint8_t *src = dev_bases ? dev_bases + offsets[0] : h->staging.bases.p;
     CK(h, h->staging.off.ensure(n + 1));
     CK(h, cudaMemcpyAsync(h->staging.off.p, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, h->st));
+    // ---- The copy engine serves requests in the order they reach it, and requests of a stream may be held back until the
+    // stream's next operation: the chunk copies wait for an event behind the small metadata copies, or those could land
+    // behind all the chunks and stall the first ingest for the whole transfer.  The same event orders the chunk copies
+    // after the previous batch's ingest kernels, which read the staging buffer.
+    if (!dev_bases) CK(h, h->staging.bases.ensure(nbytes + 64));  // k_ingest reads whole aligned words
+    // (measured) a timing event recorded on the compute stream while the chunk copies are queued completes only after
+    // all of them, and holds back the first ingest: the stage timer starts before the copies are queued
+    StageTimer tm(h, RLSIM_T_LAYOUT, 0);
+    CK(h, cudaEventRecord(h->ev_ingest, h->st));
+    CK(h, cudaStreamWaitEvent(h->st_copy, h->ev_ingest, 0));
+    const uint8_t *src = dev_bases ? dev_bases + offsets[0] : h->staging.bases.p;
     // ---- pipeline: H2D of chunk c+1 on the copy stream overlaps ingest (+ prefix sums) of chunk c
     const uint64_t chunk_bytes = getenv("RLSIM_CHUNK_BYTES") ? std::max(1ll, atoll(getenv("RLSIM_CHUNK_BYTES")))  // test knob
                                : (uint64_t)(getenv("RLSIM_CHUNK_MB") ? std::max(1, atoi(getenv("RLSIM_CHUNK_MB"))) : 32) << 20;
-    StageTimer tm(h, RLSIM_T_LAYOUT, 0);
     std::vector<uint32_t> cuts{0};
     for (uint32_t t0 = 0; t0 < n;) {
         uint32_t t1 = t0;
@@ -1119,6 +1176,7 @@ int select_core(rlsim_handle *h, const std::vector<uint64_t> &T, const std::vect
                 uint32_t part, const uint64_t *d_all_base, uint4 *records, uint64_t cap, uint64_t *counts_out,
                 uint64_t *needed_out) {
     int rc;
+    if ((rc = target_host(h))) return rc;
     uint32_t n_len = h->n_len;
     // ---- sampler.go:65-106 bookkeeping per requested length (global view, identical on every rank)
     size_t nt = std::max<size_t>(h->h_target.size(), n_len);
@@ -1344,6 +1402,7 @@ int rlsim_get_stats(rlsim_handle *h, rlsim_stats *out) {
 }
 
 int rlsim_get_hist(rlsim_handle *h, int kind, uint64_t *out, uint32_t n) {
+    if (kind == RLSIM_H_TARGET && h->target_pending) { cudaSetDevice(h->device); int rc = target_host(h); if (rc) return rc; }
     const std::vector<uint64_t> *src = nullptr;
     switch (kind) {
     case RLSIM_H_TARGET: src = &h->h_target; break;
@@ -1526,6 +1585,8 @@ int rlsim_probe_amplify(rlsim_handle *h, int64_t seed_pcr, const uint32_t *tse, 
 }
 
 int rlsim_get_timings(rlsim_handle *h, float *ms_out, uint64_t *launches_out) {
+    cudaSetDevice(h->device);
+    drain_timers(h);
     for (int i = 0; i < RLSIM_T_COUNT; i++) {
         if (ms_out) ms_out[i] = h->ms[i];
         if (launches_out) launches_out[i] = h->launches[i];
