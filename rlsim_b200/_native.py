@@ -11,7 +11,7 @@ import numpy as np
 from .args import CParams
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librlsim_gpu.so")
+LIB_PATH = os.environ.get("RLSIM_GPU_LIB") or os.path.join(HERE, "librlsim_gpu.so")  # override: A/B runs of two builds
 
 H_TARGET, H_POLYA, H_AFTER_FRAG, H_AFTER_PCR, H_SAMPLED, H_MISSING, H_AFTER_SAMPLING = range(7)
 T_NAMES = ["layout", "prefix", "fragment", "dedup", "pcr", "select", "expand", "format", "target", "intervals"]

@@ -82,9 +82,18 @@ __device__ __forceinline__ uint32_t prime_search(const Profile &pf, uint32_t ple
     const uint32_t *F = pf.F + base;
     uint32_t j = (uint32_t)(((uint64_t)r * nb) / (chi - clo));  // chi - clo = block sum > r
     if (j >= nb) j = nb - 1;
-    if (F[j] > r) { while (j > 0 && F[j - 1] > r) j--; }
-    else { do { j++; } while (F[j] <= r); }  // F[nb-1] = block sum > r: terminates inside the block
-    return base + j;
+    // walk from the guess four entries at a time (one 16-byte load per step; F + base is 256-byte aligned): c = how
+    // many entries of the quad are <= r.  Entries at or beyond nb count as > r (F[nb-1] = block sum > r).
+    uint32_t q = j & ~3u, c;
+    auto quad = [&](uint32_t q0) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(F + q0);
+        return (uint32_t)(v.x <= r) + (uint32_t)(q0 + 1 < nb && v.y <= r) + (uint32_t)(q0 + 2 < nb && v.z <= r) +
+               (uint32_t)(q0 + 3 < nb && v.w <= r);
+    };
+    c = quad(q);
+    if (c == 4) { do { q += 4; c = quad(q); } while (c == 4); }          // the sums are increasing: all four <= r, go up
+    else if (c == 0) { while (q > 0) { q -= 4; c = quad(q); if (c) break; } }  // first entry already > r: go down
+    return base + q + c;
 }
 
 __device__ __forceinline__ bool priming(const PxStream &iv, uint32_t block, const Profile &pf, uint32_t proflen,
@@ -289,7 +298,8 @@ k_fragment(const __grid_constant__ DevModel m, DevTranscripts tr, uint64_t g_beg
     __syncthreads();
     uint64_t g = g_begin + (uint64_t)blockIdx.x * FRAG_THREADS + threadIdx.x;  // global molecule index
     if (g < g_end) {
-        // molecule -> transcript: the warp's first lane searches; a warp rarely spans more than a few transcripts
+        // molecule -> transcript: the warp's first lane searches; a warp rarely spans more than a few transcripts.
+        // (measured: a 32-ary search by the whole warp and a tile loop per CTA are both slower here)
         const uint64_t g0 = g - (threadIdx.x & 31);
         uint32_t t = 0;
         if ((threadIdx.x & 31) == 0) t = upper_bound_u64(tr.mol_off, tr.n + 1, g0) - 1;
@@ -342,8 +352,7 @@ k_intervals(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, ui
     extern __shared__ unsigned int hist_s[];
     for (uint32_t i = threadIdx.x; i < hist_s_n; i += IV_THREADS) hist_s[i] = 0;
     __syncthreads();
-    uint64_t g = (uint64_t)blockIdx.x * IV_THREADS + threadIdx.x;
-    if (g < n_q) {
+    for (uint64_t g = (uint64_t)blockIdx.x * IV_THREADS + threadIdx.x; g < n_q; g += (uint64_t)gridDim.x * IV_THREADS) {
         uint4 a = o.q_a[g];
         uint2 b = o.q_b[g];
         uint64_t mol = (uint64_t)a.y | ((uint64_t)b.y << 32);
@@ -436,7 +445,8 @@ int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &t
     uint32_t hist_s_n = frag_hist_bins(m);
     uint64_t blocks = (n_q + IV_THREADS - 1) / IV_THREADS;
     if (blocks > 0x7fffffffull) return RLSIM_E_UNSUPPORTED;
-    k_intervals<<<(unsigned)blocks, IV_THREADS, (size_t)hist_s_n * 4, st>>>(m, tr, o, n_q, hist_s_n);
+    const uint64_t max_blocks = 148ull * 5 * 6;
+    k_intervals<<<(unsigned)std::min(blocks, max_blocks), IV_THREADS, (size_t)hist_s_n * 4, st>>>(m, tr, o, n_q, hist_s_n);
     return 0;
 }
 
