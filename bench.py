@@ -253,6 +253,7 @@ def main():
     barrier()
     t_e2e = time.perf_counter() - t0
     d2h_bytes = (n_e2e // max(opts.steps, 1)) * 21 + 7 * 8 * (int(h.stats().high) + 2)
+    e2e_eager = bool(int(h.stats().flags) & _native.F_EAGER)
     # ---- e2e including FASTA text (reported separately; frag.go:71-126 formatted on the device)
     e2e_fasta = None
     if world == 1 and not opts.no_fasta:
@@ -336,13 +337,16 @@ def main():
     K = max(opts.steps, 1)
     stage_ms = {k: (ms1[k] - ms0[k]) / K for k in ms1}
     launches = sum(nl1[k] - nl0[k] for k in nl1) // K
+    mirrored = bool(int(st.flags) & _native.F_MIRRORED_REVERSE)
     expressed = levels_np > 0  # pool.go:104: unexpressed transcripts get no prefix sums
     lens = (off_np[1:] - off_np[:-1]).astype(np.int64)
     nt_total = int(lens[expressed].sum()) + int(expressed.sum()) * int(st.polya_max)
     # algorithmic bytes per step of each own kernel group
     n_intervals = float(st.n_fragments) * 1.0  # queued intervals ~ kept fragments at this -d (upper bound of what the searches touch)
     alg = {
-        "prefix": 8.5 * nt_total,                         # 0.25 B/nt read + 2 strands x (4 B fine + 8/64 B coarse) written (expressed transcripts)
+        # 0.25 B/nt read + per strand (4 B fine + 8/64 B coarse) written, expressed transcripts; one strand when the reverse
+        # profile is read mirrored from the forward sums (symmetric k-mer table)
+        "prefix": (0.25 + (1 if mirrored else 2) * 4.125) * nt_total,
         "fragment": 8.0 * float(st.n_molecules) + 24.0 * n_intervals,   # k_fragment: 8 B/molecule in, 24 B per queued interval out
         "intervals": (24.0 + 2 * 12 * 8.0 + 8.0) * n_intervals,         # k_intervals: record in, 2 searches x ~12 probes x 8 B, key out
         "pcr": 32.0 * float(st.n_species),                # 32 B/species
@@ -380,7 +384,9 @@ def main():
                                "fragments in total, 15 cycles, after_prim_double" % (n_tr, int(bases.numel()), int(st.n_molecules), n_frags_global),
                    "flags": " ".join(C3_FLAGS), "scale": opts.scale, "sharding": "contiguous transcripts per rank; allgather of per-length totals + all-to-all of drawn copy ranks",
                    "cpu_binding_rank0": (sorted(cpus)[0], sorted(cpus)[-1], len(cpus)) if cpus else None,
-                   "l2": "inputs (0.45 GB bases + 7 GB prefix sums per GPU) exceed the 126 MB L2; no explicit flush",
+                   "l2": "inputs (0.45 GB bases + %.1f GB prefix sums per GPU) exceed the 126 MB L2; no explicit flush" % ((1 if mirrored else 2) * 4.125 * nt_total / 1e9),
+                   "reverse_profile": "mirrored forward sums" if mirrored else "explicit arrays",
+                   "e2e_path": "eager chunk pipeline (fragment+dedup+PCR per arrived group of 32 MB chunks)" if e2e_eager else "monolithic",
                    "species_per_gpu": int(st.n_species), "fragments_after_fragmentation_per_gpu": int(st.n_fragments),
                    "pool_total_rank0": int(st.pool_total)},
         "e2e": {"value": n_e2e / t_e2e, "unit": "fragments/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),

@@ -83,8 +83,11 @@ typedef struct {
     uint64_t n_sampled;         /* fragments in the result of rlsim_sample */
     uint64_t low, high;         /* Targeter.GetLow / GetHigh */
     uint32_t polya_max;         /* pool.go:84 */
-    uint32_t reserved;
+    uint32_t flags;             /* RLSIM_F_*: how the library was built (informational) */
 } rlsim_stats;
+/* rlsim_stats.flags */
+enum { RLSIM_F_MIRRORED_REVERSE = 1,  /* reverse priming reads the forward prefix sums mirrored (symmetric k-mer table) */
+       RLSIM_F_EAGER = 2 };           /* the last library was fragmented and amplified while its transcripts were copied */
 
 /* histogram kinds (fragstats.go:45-56); every histogram is indexed by length */
 enum { RLSIM_H_TARGET = 0, RLSIM_H_POLYA = 1, RLSIM_H_AFTER_FRAG = 2, RLSIM_H_AFTER_PCR = 3, RLSIM_H_SAMPLED = 4,

@@ -1,19 +1,33 @@
 #!/usr/bin/env python3
-"""Rebuild profiles/r1_final_ncu_summary.md from the ncu exports in gpurun_out/ (launch list csv + `--page raw --csv`
-of the full capture) and the bench JSON lines copied into profiles/.  Usage: python profiles/make_summary.py"""
+"""Rebuild profiles/r1_final_ncu_summary.md and profiles/ncu_traffic.json from the ncu exports brought back in
+gpurun_out/ and the bench JSON lines copied into profiles/.
+
+Inputs (see the commands in the summary it writes):
+  gpurun_out/r1_final_launches.csv   launch list of bench.py (copied to profiles/r1_final_launches_ncu.csv)
+  gpurun_out/r1_final_full_raw.csv   `ncu -i r1_final_full.ncu-rep --page raw --csv` of profiles/profile_run.py
+  gpurun_out/r1_final_prof_plain.log stdout of the un-profiled profiles/profile_run.py (unit counts)
+Usage: python profiles/make_summary.py
+"""
 import csv
 import json
 import os
 import re
+import shutil
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = lambda *p: os.path.join(ROOT, "gpurun_out", *p)
 P = lambda *p: os.path.join(ROOT, "profiles", *p)
 out = []
 out.append("# Round 1 - ncu evidence, final state of the round\n")
-out.append("Command (1 GPU, B200, `--clock-control none`): `python bench.py --steps 1 --warmup 1 --scale 0.25 --no-cpu-baseline`")
-out.append("(C3 at 1/4 scale: 50 000 transcripts, 112.7 M nt, 2.48 M molecules, 2.5 M requested fragments; 2 end-to-end + 2 device-resident passes).")
-out.append("The same command exited 0 without ncu first. Per-launch times under ncu are cold-cache and serialised: compare shares.\n")
+
+# ---------------------------------------------------------------- launch list of the bench command
+if os.path.exists(G("r1_final_launches.csv")):
+    shutil.copy(G("r1_final_launches.csv"), P("r1_final_launches_ncu.csv"))
+out.append("Launch list (1 GPU, B200): `ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv python bench.py --steps 1 "
+           "--warmup 1 --scale 0.25 --no-cpu-baseline --no-fasta`")
+out.append("(C3 at 1/4 scale: 50 000 transcripts, 112.7 M nt, 2.48 M molecules, 2.5 M requested fragments; 2 end-to-end passes through the "
+           "eager chunk pipeline + 2 device-resident passes). The same command exited 0 without ncu first. Per-launch times under ncu are "
+           "cold-cache and serialised: compare shares.\n")
 rows = [r for r in csv.reader(open(P("r1_final_launches_ncu.csv"))) if len(r) > 10]
 hdr = rows[0]
 ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
@@ -26,38 +40,68 @@ for r in rows[1:]:
     a[0] += 1
     a[1] += v
 tot = sum(a[1] for a in agg.values())
-out.append("## Launch list (profiles/r1_final_launches_ncu.csv): %d launches\n" % (len(rows) - 1))
+own = sum(a[1] for k, a in agg.items() if "rl::" in k or "k_" in k)
+out.append("## Launch list (profiles/r1_final_launches_ncu.csv): %d launches, %.1f %% of the kernel time in this repo's own kernels\n"
+           % (len(rows) - 1, 100 * own / tot))
 out.append("| kernel | launches | total us | share |\n|---|---:|---:|---:|")
-for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:18]:
+for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:22]:
     out.append("| `%s` | %d | %.1f | %.1f%% |" % (k, c, t, 100 * t / tot))
 d = json.load(open(P("r1_final_bench.json")))
-out.append("\nCUDA-event stage times of the un-profiled full-scale run (profiles/r1_final_bench.json), ms per step of %.2f ms:" % d["ms_per_step"])
+out.append("\nCUDA-event stage times of the un-profiled full-scale run (profiles/r1_final_bench.json), ms per device-resident step of %.2f ms:"
+           % d["ms_per_step"])
 out.append(", ".join("%s %.2f" % (k, v) for k, v in sorted(d["kernels_ms_per_step"].items(), key=lambda kv: -kv[1])) + ".")
-out.append("Under ncu `k_prefix` / `k_ingest` appear once per 32 MB chunk in the end-to-end passes (there they overlap the H2D copy) and `k_prefix` once per device-resident pass.\n")
-rows = list(csv.reader(open(G("prof_r1_final_raw.csv"))))
+out.append("(`prefix` and `target` overlap on two streams in that step; alone `k_prefix` takes 0.70 ms.) In the end-to-end passes "
+           "`k_ingest`, `k_gc_scan`, `k_prefix`, `k_fragment`, `k_intervals`, the key sort and `k_pcr` appear once per group of arrived "
+           "chunks: they overlap the H2D copy.\n")
+
+# ---------------------------------------------------------------- full capture of the monolithic pass
+rows = list(csv.reader(open(G("r1_final_full_raw.csv"))))
 hdr, units = rows[0], rows[1]
 g = lambda r, n: r[hdr.index(n)]
 u = lambda n: units[hdr.index(n)]
+fl = lambda r, n: float(g(r, n).replace(",", "") or 0)
 st = [h for h in hdr if "pcsamp_warps_issue_stalled" in h and "not_issued" not in h]
 best = {}
 for r in rows[2:]:
-    name = re.sub(r"\(.*", "", g(r, "Kernel Name"))
-    if name not in best or float(g(best[name], "gpu__time_duration.sum")) < float(g(r, "gpu__time_duration.sum")):
+    name = re.sub(r"\(.*", "", g(r, "Kernel Name")).replace("rl::", "")
+    if name not in best or fl(best[name], "gpu__time_duration.sum") < fl(r, "gpu__time_duration.sum"):
         best[name] = r
-out.append("## `ncu --set full` (gpurun_out/prof_r1_final.ncu-rep), largest launch of each kernel, scale 0.25\n")
+out.append("## `ncu --set full --import-source on` of `python profiles/profile_run.py` (C3 at full scale, one monolithic pass: every "
+           "kernel launches once at full size), largest launch of each kernel\n")
 out.append("| kernel | time %s | DRAM read %s | DRAM write %s | DRAM %% peak | issue active %% | FP64 pipe %% | regs | warps active %% | active lanes / inst | top stalls |"
            % (u("gpu__time_duration.sum"), u("dram__bytes_read.sum"), u("dram__bytes_write.sum")))
 out.append("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|")
-for name, r in sorted(best.items(), key=lambda kv: -float(g(kv[1], "gpu__time_duration.sum"))):
-    t = sum(float(g(r, h).replace(",", "") or 0) for h in st)
-    top = sorted(((float(g(r, h).replace(",", "") or 0), h) for h in st), reverse=True)[:3]
+for name, r in sorted(best.items(), key=lambda kv: -fl(kv[1], "gpu__time_duration.sum")):
+    t = sum(fl(r, h) for h in st) or 1.0
+    top = sorted(((fl(r, h), h) for h in st), reverse=True)[:3]
     tops = ", ".join("%s %.0f%%" % (h.replace("smsp__pcsamp_warps_issue_stalled_", ""), 100 * v / t) for v, h in top)
     out.append("| `%s` | %.1f | %.3f | %.3f | %.1f | %.1f | %.1f | %s | %.1f | %.1f | %s |" % (
-        name, float(g(r, "gpu__time_duration.sum")), float(g(r, "dram__bytes_read.sum")), float(g(r, "dram__bytes_write.sum")),
-        float(g(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")), float(g(r, "smsp__issue_active.avg.pct_of_peak_sustained_active")),
-        float(g(r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")), g(r, "launch__registers_per_thread"),
-        float(g(r, "sm__warps_active.avg.pct_of_peak_sustained_active")), float(g(r, "smsp__thread_inst_executed_per_inst_executed.ratio")), tops))
-n2, n4, ref = (json.load(open(P(f))) for f in ("r1_final_bench_n2.json", "r1_final_bench_n4.json", "r1_final_bench_reference.json"))
+        name, fl(r, "gpu__time_duration.sum"), fl(r, "dram__bytes_read.sum"), fl(r, "dram__bytes_write.sum"),
+        fl(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"), fl(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        fl(r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"), g(r, "launch__registers_per_thread"),
+        fl(r, "sm__warps_active.avg.pct_of_peak_sustained_active"), fl(r, "smsp__thread_inst_executed_per_inst_executed.ratio"), tops))
+
+# ---------------------------------------------------------------- DRAM traffic per unit (bench.py: roofline.traffic)
+m = re.search(r"nt (\d+) molecules (\d+) fragments (\d+) species (\d+) sampled (\d+)", open(G("r1_final_prof_plain.log")).read())
+nt, mol, frag, sp, smp = (int(x) for x in m.groups())
+units_of = {"k_pcr": ("pcr", sp, "species"), "k_intervals": ("intervals", frag, "queued interval (~ kept fragment)"),
+            "k_prefix": ("prefix", nt, "nt (expressed)"), "k_fragment": ("fragment", mol, "molecule"),
+            "k_expand": ("expand", smp, "sampled fragment"), "k_ingest": ("ingest", nt, "nt")}
+to_bytes = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+traffic = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full of profiles/profile_run.py "
+                       "(C3 at full scale, whole-library launches), divided by the units of that launch; bench.py scales it to the run"}
+for name, (key, n_units, unit) in units_of.items():
+    if name in best:
+        r = best[name]
+        b = fl(r, "dram__bytes_read.sum") * to_bytes[u("dram__bytes_read.sum")] + fl(r, "dram__bytes_write.sum") * to_bytes[u("dram__bytes_write.sum")]
+        traffic[key] = {"bytes_per_unit": round(b / n_units, 3), "unit": unit, "launch_bytes": int(b), "launch_units": n_units}
+json.dump(traffic, open(P("ncu_traffic.json"), "w"), indent=1)
+out.append("\nDRAM traffic per unit of work (profiles/ncu_traffic.json): " + ", ".join(
+    "%s %.1f B/%s" % (k, v["bytes_per_unit"], v["unit"]) for k, v in traffic.items() if k != "_comment") + ".")
+
+# ---------------------------------------------------------------- history
+n = {k: json.load(open(P("r1_final_bench_%s.json" % k))) for k in ("n2", "n4", "n8", "reference") if os.path.exists(P("r1_final_bench_%s.json" % k))}
+km = d["kernels_ms_per_step"]
 out.append("""
 ## What changed during the round (device-resident C3 step, one B200; CUDA-event stage times in ms)
 
@@ -70,14 +114,28 @@ out.append("""
 | + PCR in warp rounds with batched exact tests, interpolation search for priming | 11.2 | 2.93 | 2.05 | 2.56 | |
 | + two-level prefix sums (u32 in-block + u64 per block), constant-shift fast path | 9.7 | 2.93 | 1.15 | 2.57 | half the prefix bytes |
 | + prefetched header draws, occupancy-targeted launch bounds | 8.6 | 2.17 | 1.15 | 2.26 | |
-| + FP32 pre-decision of the BTRS acceptance test (exact FP64 fallback) | %.1f | %.2f | %.2f | %.2f | final |
+| + FP32 pre-decision of the BTRS acceptance test (exact FP64 fallback) | 8.1 | 2.17 | 1.15 | 1.76 | |
+| + reverse priming through mirrored forward sums (symmetric k-mer table): no reverse arrays | 7.6 | 2.15 | 0.70 | 1.76 | half the prefix bytes again |
+| + target draws on their own stream, quad-wise in-block walk of the priming search | %.1f | %.2f | %.2f | %.2f | final (`prefix` overlaps `k_target`) |
 
-End to end (host buffers in, fragment records out): 43.8 ms -> %.1f ms (persistent staging, H2D on a copy stream overlapped with
-ingest + prefix sums per 32 MB chunk, global transcript index written on the device).
-Weak scaling (profiles/r1_final_bench_n2.json, _n4.json): %.2f / %.2f / %.2f G fragments/s at 1 / 2 / 4 GPUs (%.0f %% / %.0f %% of linear).
-Reference release binary on the same box, %d cores (profiles/r1_final_bench_reference.json): %.2e fragments/s.""" % (
-    d["ms_per_step"], d["kernels_ms_per_step"]["fragment"] + d["kernels_ms_per_step"]["intervals"], d["kernels_ms_per_step"]["prefix"],
-    d["kernels_ms_per_step"]["pcr"], d["e2e"]["ms_per_step"], d["value"] / 1e9, n2["value"] / 1e9, n4["value"] / 1e9,
-    100 * n2["value"] / (2 * d["value"]), 100 * n4["value"] / (4 * d["value"]), ref["cpu_baseline"]["cores"], ref["value"]))
+End to end (host buffers in, fragment records out): 43.8 ms -> 21.8 ms (persistent staging, H2D on a copy stream overlapped with ingest +
+prefix sums per 32 MB chunk) -> %.1f ms (eager chunk pipeline: every arrived group of chunks is fragmented, deduplicated and amplified while
+later chunks are still in flight; PCR on its own stream; GC counts as {prefix, bit mask} per 32 bases; flat vectorised ingest kernel).
+With FASTA text formatted on the device and copied out (%.2f GB per step): %.0f ms. Fed with the raw FASTA text through the device-side
+reader instead of parsed arrays: %.1f ms."""
+           % (d["ms_per_step"], km["fragment"] + km["intervals"], km["prefix"], km["pcr"], d["e2e"]["ms_per_step"],
+              (d.get("e2e_fasta") or {}).get("text_bytes_per_step", 0) / 1e9, (d.get("e2e_fasta") or {}).get("ms_per_step", float("nan")),
+              (d.get("e2e_text_in") or {}).get("ms_per_step", float("nan"))))
+if all(k in n for k in ("n2", "n4")):
+    line = "Weak scaling (profiles/r1_final_bench_n2.json, _n4.json%s): %.2f / %.2f / %.2f" % (
+        ", _n8.json" if "n8" in n else "", d["value"] / 1e9, n["n2"]["value"] / 1e9, n["n4"]["value"] / 1e9)
+    eff = "%.0f %% / %.0f %%" % (100 * n["n2"]["value"] / (2 * d["value"]), 100 * n["n4"]["value"] / (4 * d["value"]))
+    if "n8" in n:
+        line += " / %.2f" % (n["n8"]["value"] / 1e9)
+        eff += " / %.0f %%" % (100 * n["n8"]["value"] / (8 * d["value"]))
+    out.append(line + " G fragments/s at 1 / 2 / 4%s GPUs (%s of linear)." % (" / 8" if "n8" in n else "", eff))
+if "reference" in n:
+    out.append("Reference release binary on the same box, %d cores (profiles/r1_final_bench_reference.json): %.2e fragments/s."
+               % (n["reference"]["cpu_baseline"]["cores"], n["reference"]["value"]))
 open(P("r1_final_ncu_summary.md"), "w").write("\n".join(out) + "\n")
-print("\n".join(out[-40:]))
+print("\n".join(out[-30:]))

@@ -33,4 +33,6 @@ for step in range(2):  # the second pass runs with every buffer allocated
     h.sample()
     torch.cuda.synchronize()
 st = h.stats()
-print("molecules %d fragments %d species %d sampled %d" % (st.n_molecules, st.n_fragments, st.n_species, st.n_sampled))
+expressed = levels_np > 0
+nt = int((off_np[1:] - off_np[:-1]).astype(np.int64)[expressed].sum()) + int(expressed.sum()) * int(st.polya_max)
+print("nt %d molecules %d fragments %d species %d sampled %d" % (nt, st.n_molecules, st.n_fragments, st.n_species, st.n_sampled))

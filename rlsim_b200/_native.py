@@ -18,6 +18,8 @@ T_NAMES = ["layout", "prefix", "fragment", "dedup", "pcr", "select", "expand", "
 
 E_CUDA, E_ARG, E_PRIMING, E_PCR_OVERFLOW, E_POOL_OVERFLOW, E_UNSUPPORTED, E_NOMEM = range(1, 8)  # include/rlsim_gpu.h
 
+F_MIRRORED_REVERSE, F_EAGER = 1, 2  # rlsim_stats.flags
+
 EXPORTS = [
     "rlsim_create", "rlsim_destroy", "rlsim_last_error", "rlsim_set_model", "rlsim_set_len_eff", "rlsim_set_raw_target",
     "rlsim_sample_target", "rlsim_sample_target_range", "rlsim_set_target_hist", "rlsim_add_transcripts", "rlsim_add_fasta", "rlsim_get_fasta_index", "rlsim_set_first_index", "rlsim_clear_transcripts",
@@ -32,7 +34,7 @@ class Stats(C.Structure):
     _fields_ = [("n_transcripts", C.c_uint64), ("n_molecules", C.c_uint64), ("n_fragments", C.c_uint64),
                 ("n_species", C.c_uint64), ("pool_total", C.c_uint64), ("n_requested", C.c_uint64),
                 ("n_sampled", C.c_uint64), ("low", C.c_uint64), ("high", C.c_uint64), ("polya_max", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("flags", C.c_uint32)]
 
 
 class RlsimError(RuntimeError):

@@ -120,6 +120,7 @@ struct rlsim_handle {
     bool eager_failed = false;              // a buffer estimate was too small: the monolithic path takes over
     bool eager_started = false;             // counters / histograms zeroed for this transcript set
     bool eager_pcr = false;                 // species counts already amplified (consumed by the next rlsim_pcr)
+    bool eager_used = false;                // the current species table came from the eager pipeline (rlsim_stats.flags)
     uint64_t eager_keys = 0, eager_sp = 0;  // running fragment-key / species counts
     bool len_eff_ready = false;
     DBuf<uint8_t> d_bases;
@@ -990,11 +991,12 @@ int rlsim_fragment(rlsim_handle *h) {
         h->n_frag = h->eager_keys;
         h->n_sp = h->eager_sp;
         h->eager_pcr = true;
+        h->eager_used = true;
         h->eager_upto = 0; h->eager_failed = true;  // consumed: a repeated call recomputes from the resident transcripts
         h->fragmented = true; h->amplified = false; h->sampled = false;
         return 0;
     }
-    h->eager_upto = 0; h->eager_failed = true; h->eager_pcr = false;
+    h->eager_upto = 0; h->eager_failed = true; h->eager_pcr = false; h->eager_used = false;
     // ---- capacity estimate for the fragment keys
     double loc = h->raw_location;
     if (h->p.n_target > 0) {
@@ -1398,6 +1400,8 @@ int rlsim_get_stats(rlsim_handle *h, rlsim_stats *out) {
     out->n_requested = h->req_frags;
     out->n_sampled = h->sampled ? h->n_out : 0;
     out->low = h->low; out->high = h->high; out->polya_max = h->polya_max;
+    out->flags = (needs_rev(h->p.frag_method) && h->lut_valid && h->lut_sym && h->want_mirror ? RLSIM_F_MIRRORED_REVERSE : 0) |
+                 (h->eager_used ? RLSIM_F_EAGER : 0);
     return 0;
 }
 
