@@ -220,19 +220,23 @@ template <class Cur> __device__ __forceinline__ double target_location(const Dev
     return m.target[px_mix_comp(hdr, m.target, m.n_target)].location;
 }
 
+// KIND: 0 = after_* methods, 1 = pre_prim, 2 = prim_jump (compile-time specialisations of the molecule kernel), -1 = runtime
+template <int KIND>
 __device__ __forceinline__ Header mol_header(const DevModel &m, const MolCtx &c, uint64_t mol) {
+    const bool is_jump = KIND < 0 ? m.method == RLSIM_PRIM_JUMP : KIND == 2;
+    const bool is_pre = KIND < 0 ? m.method == RLSIM_PRE_PRIM : KIND == 1;
     Header h;
     PxCursor3 hdr(mol_stream(m, c.tg, mol, SUB_HEADER));  // first six header draws generated convergently
     h.tail = px_comp_len(hdr, m.polya[px_mix_comp(hdr, m.polya, m.n_polya)]);
     h.polyAend = (int)c.L - (int)m.polya_max + (int)h.tail;  // transcript.go:283
     h.nb = 0;
     h.elong = 0;
-    if (m.method == RLSIM_PRIM_JUMP) return h;
+    if (is_jump) return h;
     int length = h.polyAend;
     if (length < 1) return h;
     double loc = target_location(m, hdr);
     double rate;
-    if (m.method == RLSIM_PRE_PRIM) {
+    if (is_pre) {
         double fp = 1.0 / (double)(uint32_t)m.frag_param;
         double ex = px_expo(hdr) / fp;
         int el = ex >= (double)length ? length : (int)ex;
@@ -244,7 +248,7 @@ __device__ __forceinline__ Header mol_header(const DevModel &m, const MolCtx &c,
     int32_t nb = px_poisson(hdr, rate) - 1;  // fragmentor.go:113-117
     if (nb <= 0) nb = 1;
     h.nb = nb;
-    if (m.method == RLSIM_PRE_PRIM && (int64_t)length - (int64_t)h.elong < 1) h.nb = 0;  // fragmentor.go:240-243
+    if (is_pre && (int64_t)length - (int64_t)h.elong < 1) h.nb = 0;  // fragmentor.go:240-243
     return h;
 }
 
@@ -290,6 +294,7 @@ __device__ __forceinline__ MolCtx make_ctx(const DevModel &m, const DevTranscrip
     return c;
 }
 
+template <int KIND>
 __global__ void __launch_bounds__(FRAG_THREADS, 10)
 k_fragment(const __grid_constant__ DevModel m, DevTranscripts tr, uint64_t g_begin, uint64_t g_end, FragOut o, uint32_t hist_s_n) {
     extern __shared__ unsigned int hist_s[];  // [hist_s_n] after-frag bins from `low`, then [polya_max+1]
@@ -307,9 +312,9 @@ k_fragment(const __grid_constant__ DevModel m, DevTranscripts tr, uint64_t g_beg
         while (tr.mol_off[t + 1] <= g) t++;
         uint64_t mol = g - tr.mol_off[t];
         MolCtx c = make_ctx(m, tr, t);
-        Header h = mol_header(m, c, mol);
+        Header h = mol_header<KIND>(m, c, mol);
         atomicAdd(&hist_pa[h.tail], 1u);
-        if (m.method == RLSIM_PRIM_JUMP) {
+        if (KIND == 2) {
             prim_jump(m, c, mol, h.polyAend, o, hist_s, hist_s_n);
         } else if (h.nb > FRAG_LOCAL_BREAKS) {
             unsigned int slot = atomicAdd(o.long_count, 1u);
@@ -318,7 +323,7 @@ k_fragment(const __grid_constant__ DevModel m, DevTranscripts tr, uint64_t g_beg
             uint32_t length = (uint32_t)h.polyAend;
             uint32_t br[FRAG_LOCAL_BREAKS + 2];
             PxStream bs = mol_stream(m, c.tg, mol, SUB_BREAKS);
-            uint32_t first = m.method == RLSIM_PRE_PRIM ? h.elong : 0u;
+            uint32_t first = KIND == 1 ? h.elong : 0u;
             uint64_t span = (uint64_t)length - first;
             br[0] = first;
             // insertion sort while drawing (fragmentor.go:125-129)
@@ -332,7 +337,7 @@ k_fragment(const __grid_constant__ DevModel m, DevTranscripts tr, uint64_t g_beg
             br[cnt] = length;  // length is >= every draw, so it sorts last
             PxStream iv = mol_stream(m, c.tg, mol, SUB_INTERVAL);
             for (int32_t i = 0; i < h.nb; i++) {  // the last interval is never visited (fragmentor.go:132)
-                if (m.method == RLSIM_PRE_PRIM) plain_interval(m, c, iv, (uint32_t)i, br[i], br[i + 1], o, hist_s, hist_s_n);
+                if (KIND == 1) plain_interval(m, c, iv, (uint32_t)i, br[i], br[i + 1], o, hist_s, hist_s_n);
                 else if (br[i + 1] - br[i] >= m.low) enqueue(o, t, mol, (uint32_t)i, br[i], br[i + 1]);
             }
         }
@@ -376,7 +381,7 @@ k_fragment_long(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o
     uint32_t t = o.long_list[slot].x;
     uint64_t mol = (uint64_t)o.long_list[slot].y | ((uint64_t)o.long_hi[slot] << 32);
     MolCtx c = make_ctx(m, tr, t);
-    if (threadIdx.x == 0) hs = mol_header(m, c, mol);
+    if (threadIdx.x == 0) hs = mol_header<-1>(m, c, mol);
     __syncthreads();
     Header h = hs;
     uint32_t n = (uint32_t)h.nb + 2;
@@ -434,7 +439,9 @@ int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr
     if (smem > 48 * 1024) return RLSIM_E_UNSUPPORTED;
     uint64_t blocks = (n_mol + FRAG_THREADS - 1) / FRAG_THREADS;
     if (blocks > 0x7fffffffull) return RLSIM_E_UNSUPPORTED;
-    k_fragment<<<(unsigned)blocks, FRAG_THREADS, smem, st>>>(m, tr, g_begin, g_end, o, hist_s_n);
+    if (m.method == RLSIM_PRIM_JUMP) k_fragment<2><<<(unsigned)blocks, FRAG_THREADS, smem, st>>>(m, tr, g_begin, g_end, o, hist_s_n);
+    else if (m.method == RLSIM_PRE_PRIM) k_fragment<1><<<(unsigned)blocks, FRAG_THREADS, smem, st>>>(m, tr, g_begin, g_end, o, hist_s_n);
+    else k_fragment<0><<<(unsigned)blocks, FRAG_THREADS, smem, st>>>(m, tr, g_begin, g_end, o, hist_s_n);
     return 0;
 }
 
