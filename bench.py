@@ -201,7 +201,7 @@ def main():
 
     def select(step):
         if world > 1:  # classes partitioned over ranks + one all-to-all of the drawn copy ranks
-            exchange.run(h, rank, world, n_frags_global // world + 4096)
+            exchange.run(h, rank, world, n_frags_global // world + 4096, pool=pool)
         else:
             h.sample()
 

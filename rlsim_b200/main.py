@@ -73,6 +73,7 @@ def run(argv, out=None):
     stats = FragStats()
     try:
         pool = GpuPool(local_rank, rank, world, dist_device).configure(args)
+        pool.finish_target()  # the report wants the whole target histogram now (multi-GPU: summed over the ranks)
         h = pool.handle
         st = h.stats()
         log.v("Number of requested fragments: %d" % args.req_frags)

@@ -46,17 +46,29 @@ class GpuPool:
         h.set_model(self.params)
         if args.raw_len_probs is not None:
             h.set_raw_target(args.raw_len_probs.lengths, args.raw_len_probs.probs)
+        self._target_nb = 0
         if self.world > 1:  # every rank draws 1/world of the target lengths; the histograms are summed (same total
             n = args.req_frags  # histogram on every rank: the stream is keyed by the global draw index)
             a, b = n * self.rank // self.world, n * (self.rank + 1) // self.world
-            h.sample_target_range(a, b - a)
+            h.sample_target_range(a, b - a)  # asynchronous, on the library's own stream
             nb = int(max([c.high for c in args.target_mix] + (args.raw_len_probs.lengths if args.raw_len_probs else [0]))) + 1
-            tot = shard.allreduce_hist(h.hist(_native.H_TARGET, nb), device=self.dist_device)
-            nz = np.nonzero(tot)[0]
-            h.set_target_hist(nz.astype(np.uint32), tot[nz])
+            if args.raw_len_probs is not None:
+                self._sum_target(shard.allreduce_hist(h.hist(_native.H_TARGET, nb), device=self.dist_device))  # shapes the library: now
+            else:
+                self._target_nb = nb  # summed later, together with the per-length totals (finish_target / RecordExchange)
         else:
             h.sample_target(args.req_frags)
         return self
+
+    def _sum_target(self, tot):
+        nz = np.nonzero(tot)[0]
+        self.handle.set_target_hist(nz.astype(np.uint32), tot[nz])
+        self._target_nb = 0
+
+    def finish_target(self):
+        """Multi-GPU: sum the ranks' partial target histograms if that is still pending (no-op otherwise)."""
+        if getattr(self, "_target_nb", 0):
+            self._sum_target(shard.allreduce_hist(self.handle.hist(_native.H_TARGET, self._target_nb), device=self.dist_device))
 
     def reset(self):
         """Start another library on the same GPU, keeping the device buffers."""
@@ -124,7 +136,7 @@ class GpuSampler:
         if pool.world > 1:  # classes partitioned over the ranks, drawn copy ranks routed to their owners (all-to-all)
             if not hasattr(pool, "_exchange"):
                 pool._exchange = shard.RecordExchange(pool.dist_device)
-            all_tot = pool._exchange.run(h, pool.rank, pool.world, int(h.stats().n_requested) // pool.world + 4096)
+            all_tot = pool._exchange.run(h, pool.rank, pool.world, int(pool.args.req_frags) // pool.world + 4096, pool=pool)
             total = all_tot.sum(axis=0, dtype=np.uint64)
         else:
             total = h.class_totals()

@@ -112,10 +112,17 @@ class RecordExchange:
             self.send = torch.empty((int(n * 1.25) + 1024, 2), dtype=torch.int64, device=self.device)
         return self.send
 
-    def run(self, handle, rank, world, expected_records, group=None):
+    def run(self, handle, rank, world, expected_records, group=None, pool=None):
         import torch
         import torch.distributed as dist
-        all_tot = allgather_totals_matrix(handle.class_totals(), group, self.device)
+        nb = getattr(pool, "_target_nb", 0) if pool is not None else 0
+        if nb:  # the partial target histograms ride along with the per-length totals: one collective instead of two
+            totals = handle.class_totals()
+            both = allgather_totals_matrix(np.concatenate([totals, handle.hist(0, nb)]), group, self.device)
+            all_tot = np.ascontiguousarray(both[:, :len(totals)])
+            pool._sum_target(both[:, len(totals):].sum(axis=0, dtype=np.uint64))
+        else:
+            all_tot = allgather_totals_matrix(handle.class_totals(), group, self.device)
         buf = self._buffer(torch, expected_records)
         counts, needed = handle.select_classes(all_tot, rank, buf.data_ptr(), buf.shape[0])
         if needed > buf.shape[0]:
