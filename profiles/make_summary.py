@@ -35,7 +35,7 @@ agg = {}
 for r in rows[1:]:
     v = float(r[vi].replace(",", ""))
     v = v / 1e3 if r[ui] == "ns" else (v * 1e3 if r[ui] == "ms" else v)
-    short = re.sub(r"<.*", "", re.sub(r"\(.*", "", r[ki])) or "(memset/memcpy)"
+    short = re.sub(r"<.*", "", re.sub(r"\(.*", "", r[ki]).replace("<unnamed>::", "").replace("void rl::", "rl::")) or "(memset/memcpy)"
     a = agg.setdefault(short, [0, 0.0])
     a[0] += 1
     a[1] += v
@@ -63,7 +63,7 @@ fl = lambda r, n: float(g(r, n).replace(",", "") or 0)
 st = [h for h in hdr if "pcsamp_warps_issue_stalled" in h and "not_issued" not in h]
 best = {}
 for r in rows[2:]:
-    name = re.sub(r"\(.*", "", g(r, "Kernel Name")).replace("rl::", "")
+    name = re.sub(r"<.*", "", re.sub(r"\(.*", "", g(r, "Kernel Name")).replace("<unnamed>::", "").replace("void ", "").replace("rl::", ""))
     if name not in best or fl(best[name], "gpu__time_duration.sum") < fl(r, "gpu__time_duration.sum"):
         best[name] = r
 out.append("## `ncu --set full --import-source on` of `python profiles/profile_run.py` (C3 at full scale, one monolithic pass: every "
@@ -116,7 +116,7 @@ out.append("""
 | + prefetched header draws, occupancy-targeted launch bounds | 8.6 | 2.17 | 1.15 | 2.26 | |
 | + FP32 pre-decision of the BTRS acceptance test (exact FP64 fallback) | 8.1 | 2.17 | 1.15 | 1.76 | |
 | + reverse priming through mirrored forward sums (symmetric k-mer table): no reverse arrays | 7.6 | 2.15 | 0.70 | 1.76 | half the prefix bytes again |
-| + target draws on their own stream, quad-wise in-block walk of the priming search | %.1f | %.2f | %.2f | %.2f | final (`prefix` overlaps `k_target`) |
+| + target draws on their own stream, quad-wise in-block walk of the priming search, molecule kernel compiled per method | %.1f | %.2f | %.2f | %.2f | final (`prefix` overlaps `k_target`; alone 0.70) |
 
 End to end (host buffers in, fragment records out): 43.8 ms -> 21.8 ms (persistent staging, H2D on a copy stream overlapped with ingest +
 prefix sums per 32 MB chunk) -> %.1f ms (eager chunk pipeline: every arrived group of chunks is fragmented, deduplicated and amplified while
