@@ -669,7 +669,6 @@ static int sample_target_range(rlsim_handle *h, uint64_t first, uint64_t count, 
     h->target_hist_n = hist_n;
     h->req_frags = count;
     h->have_target = whole;  // a partial histogram must be completed with rlsim_set_target_hist
-    if (getenv("RLSIM_SYNC_TARGET")) { int rc = target_host(h); if (rc) return rc; }
     if (raw && whole) {  // the raw target's range and mean shape the library: needed now
         int rc = target_host(h);
         if (rc) return rc;

@@ -83,6 +83,11 @@ def test_fasta_reader_quirks():
     assert [r[0] for r in recs] == [b"a$5 ", b"b$x", b"c", b"d$7", b"C"]
     assert fasta.parse_seq_name(b"a$5 ") == (b"a", 5)
     assert fasta.parse_seq_name(b"b$x") is None and fasta.parse_seq_name(b"c") is None and fasta.parse_seq_name(b"$3") is None
+    # input.go:92-93: TrimSpace + Sscanf("%d") into a uint64 - no sign, must fit 64 bits, trailing text ignored
+    assert fasta.parse_seq_name(b"a$+5") is None and fasta.parse_seq_name(b"a$-5") is None
+    assert fasta.parse_seq_name(b"a$\t\v\f 12junk\r") == (b"a", 12)
+    assert fasta.parse_seq_name(b"a$18446744073709551615") == (b"a", 2**64 - 1) and fasta.parse_seq_name(b"a$18446744073709551616") is None
+    assert fasta.parse_seq_name(b"a$1$2") is None
     names, seqs, levels = fasta.load_transcripts([util.BASIC_FASTA], 1.0)
     assert [len(s) for s in seqs] == [1075, 3477, 4002, 2729, 1690] and levels == [10200, 8900, 2300, 2160, 0]
     assert fasta.load_transcripts([util.BASIC_FASTA], 0.1)[2] == [1020, 890, 230, 216, 0]  # input.go:113
