@@ -11,12 +11,47 @@
 #include <cstring>
 #include <string>
 #include <chrono>
+#include <new>
 #include <vector>
 #include "kernels.cuh"
 
 using namespace rl;
 
 namespace {
+
+// Host array in pinned memory with the few std::vector operations the bookkeeping needs: copies from it to the device
+// are real asynchronous DMA (a pageable source would be staged by the driver, with the host waiting for the staging).
+template <typename T>
+struct PinVec {
+    T *p = nullptr;
+    size_t n = 0, cap = 0;
+    PinVec() = default;
+    PinVec(const PinVec &) = delete;
+    PinVec &operator=(const PinVec &) = delete;
+    ~PinVec() { if (p) cudaFreeHost(p); }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+    T *begin() { return p; }
+    T *end() { return p + n; }
+    const T *begin() const { return p; }
+    const T *end() const { return p + n; }
+    void clear() { n = 0; }
+    void reserve(size_t want) {
+        if (want <= cap) return;
+        size_t c = std::max<size_t>(want + want / 2, 1024);
+        T *q = nullptr;
+        if (cudaHostAlloc((void **)&q, c * sizeof(T), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); throw std::bad_alloc(); }
+        if (n) memcpy(q, p, n * sizeof(T));
+        if (p) cudaFreeHost(p);
+        p = q; cap = c;
+    }
+    void resize(size_t want) { reserve(want); if (want > n) memset(p + n, 0, (want - n) * sizeof(T)); n = want; }
+    void push_back(const T &v) { reserve(n + 1); p[n++] = v; }
+};
 
 template <typename T>
 struct DBuf {
@@ -108,13 +143,13 @@ struct rlsim_handle {
     std::vector<cudaEvent_t> ev_chunk, ev_free;
     std::vector<PendingTime> pending_times;  // stage timers not yet resolved (drain_timers)
     std::vector<uint64_t> h_srclen;  // unpadded lengths as added
-    std::vector<uint64_t> h_expr;
-    std::vector<uint64_t> h_off;     // padded offsets [n+1]
-    std::vector<uint32_t> h_len;     // with polyA
+    PinVec<uint64_t> h_expr, h_rel;   // pinned: sources of the per-batch metadata copies
+    PinVec<uint64_t> h_off;          // padded offsets [n+1]
+    PinVec<uint32_t> h_len;          // with polyA
     uint64_t n_mol = 0, total_padded = 0;
     double sum_expr = 0, sum_expr_len = 0;  // for the fragment-capacity estimate
     bool mol_off_valid = false;
-    std::vector<uint64_t> h_mol_off;        // exclusive scan of the expression levels [n+1]
+    PinVec<uint64_t> h_mol_off;             // exclusive scan of the expression levels [n+1]
     // eager pipeline: while later chunks are still being copied, earlier chunks are already fragmented and amplified
     uint32_t eager_upto = 0;                // transcripts [0, eager_upto) are done under the current model
     bool eager_failed = false;              // a buffer estimate was too small: the monolithic path takes over
@@ -451,7 +486,7 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
         const uint64_t need = h->eager_sp + nf;
         if (h->pcr_in_flight && need > h->d_sp_count0.n) CK(h, cudaStreamWaitEvent(h->st, h->ev_pcr, 0));
         CK(h, h->d_sp_count0.grow_preserve(need, h->eager_sp, h->st));
-        int end_bit = (int)std::min<uint32_t>(64, 24 + bits_for(h->total_padded));
+        int end_bit = (int)std::min<uint32_t>(64, key_len_bits((uint32_t)h->high) + bits_for(h->total_padded));
         size_t tb = 0;
         CK(h, cub::DeviceRadixSort::SortKeys(nullptr, tb, h->d_keys.p + h->eager_keys, h->d_keys_sorted.p, (int)nf, 0, end_bit, h->st));
         if ((rc = cub_temp(h, tb))) return rc;
@@ -479,7 +514,7 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
         sp.tr = h->d_sp_tr.p + h->eager_sp; sp.start = h->d_sp_start.p + h->eager_sp; sp.len = h->d_sp_len.p + h->eager_sp;
         sp.count0 = h->d_sp_count0.p + h->eager_sp; sp.count = h->d_sp_count.p + h->eager_sp;
         sp.eff = h->keep_debug ? h->d_sp_eff.p + h->eager_sp : nullptr; sp.gc = h->keep_debug ? h->d_sp_gc.p + h->eager_sp : nullptr;
-        launch_decode_species(h->st, tr, h->d_uniq.p, sp);
+        launch_decode_species(h->st, tr, h->d_uniq.p, sp, (uint32_t)h->high);
         if ((rc = ensure_len_eff(h))) return rc;
         m = make_model(h);  // picks up the length-efficiency table pointer
         CK(h, cudaEventRecord(h->ev_sp, h->st));
@@ -731,7 +766,8 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     const uint32_t n0 = (uint32_t)h->h_len.size();
     const uint64_t nbytes = offsets[n] - offsets[0];
     if (h->h_off.empty()) h->h_off.push_back(0);
-    std::vector<uint64_t> rel(n + 1);
+    PinVec<uint64_t> &rel = h->h_rel;
+    rel.resize(n + 1);
     if (h->h_mol_off.empty()) h->h_mol_off.push_back(0);
     h->h_srclen.resize(n0 + n); h->h_expr.resize(n0 + n); h->h_len.resize(n0 + n); h->h_off.resize(n0 + n + 1); h->h_mol_off.resize(n0 + n + 1);
     {
@@ -1063,11 +1099,11 @@ int rlsim_fragment(rlsim_handle *h) {
     uint64_t nf = h->n_frag;
     CK(h, h->d_keys_sorted.ensure(nf)); CK(h, h->d_uniq.ensure(nf)); CK(h, h->d_sp_count0.ensure(nf));
     {
-        StageTimer tm(h, RLSIM_T_DEDUP, 3 + radix_launches((int)std::min<uint32_t>(64, 24 + bits_for(h->total_padded))));
+        StageTimer tm(h, RLSIM_T_DEDUP, 3 + radix_launches((int)std::min<uint32_t>(64, key_len_bits((uint32_t)h->high) + bits_for(h->total_padded))));
         h->n_sp = 0;
         if (nf) {
             if (nf >= (1ull << 31)) FAIL(h, RLSIM_E_UNSUPPORTED, "more than 2^31 fragments on one GPU");
-            int end_bit = (int)std::min<uint32_t>(64, 24 + bits_for(h->total_padded));
+            int end_bit = (int)std::min<uint32_t>(64, key_len_bits((uint32_t)h->high) + bits_for(h->total_padded));
             size_t tb = 0;
             CK(h, cub::DeviceRadixSort::SortKeys(nullptr, tb, h->d_keys.p, h->d_keys_sorted.p, (int)nf, 0, end_bit, h->st));
             if ((rc = cub_temp(h, tb))) return rc;
@@ -1085,7 +1121,7 @@ int rlsim_fragment(rlsim_handle *h) {
         }
         CK(h, h->d_sp_tr.ensure(h->n_sp)); CK(h, h->d_sp_start.ensure(h->n_sp)); CK(h, h->d_sp_len.ensure(h->n_sp));
         CK(h, h->d_sp_count.ensure(h->n_sp)); CK(h, h->d_sp_eff.ensure(h->n_sp)); CK(h, h->d_sp_gc.ensure(h->n_sp));
-        launch_decode_species(h->st, tr, h->d_uniq.p, make_sp(h));
+        launch_decode_species(h->st, tr, h->d_uniq.p, make_sp(h), (uint32_t)h->high);
         tm.stop();
         CK(h, cudaGetLastError());
     }

@@ -80,6 +80,13 @@ __device__ __forceinline__ uint32_t gc_before(const uint2 *g, uint32_t x) {
     return e.x + __popc(e.y & ((1u << (x & 31)) - 1u));
 }
 
+// bits of the length field of a fragment key (lengths are <= high < 2^24)
+__host__ __device__ __forceinline__ uint32_t key_len_bits(uint32_t high) {
+    uint32_t b = 1;
+    while (b < 24 && (high >> b)) b++;
+    return b;
+}
+
 __device__ __forceinline__ uint32_t upper_bound_u64(const uint64_t *a, uint32_t n, uint64_t x) {
     uint32_t lo = 0, hi = n;  // first i with a[i] > x
     while (lo < hi) {

@@ -5,7 +5,7 @@
 // fragmentor.go:205-270 (pre_prim), fragmentor.go:303-351 (prim_jump), nnthermo.go:203-217 (SimulatePriming, as a
 // binary search in the fixed-point prefix sums), fragfilter.go:45-50 (loss filter) and the AfterFrag / PolyALen
 // histogram updates of fragstats.go:80,116.  Kept fragments are emitted as 64-bit keys
-//     key = (global start position << 24) | length          (global start = off[t] + start)
+//     key = (global start position << len_bits) | length    (global start = off[t] + start; len_bits = bits of `high`)
 // so that a radix sort of the keys orders them by (transcript, start, end) and run-length encoding yields the
 // species table (transcript.go:156-215).
 //
@@ -23,6 +23,7 @@ constexpr int FRAG_LOCAL_BREAKS = 48;
 struct FragOut {
     uint64_t *keys;             // fragment keys
     uint64_t cap;
+    uint32_t len_bits;          // key = (off[t] + start) << len_bits | length: as few sort passes as the model allows
     unsigned long long *count;  // number of keys written (may exceed cap: overflow => caller retries)
     unsigned long long *hist_frag;   // [high+1]
     unsigned long long *hist_polya;  // [polya_max+1]
@@ -144,7 +145,7 @@ __device__ __forceinline__ void emit(const FragOut &o, uint64_t gstart, uint32_t
     if (lane == leader) base = atomicAdd(o.count, (unsigned long long)__popc(mask));
     base = __shfl_sync(mask, base, leader);
     unsigned long long pos = base + __popc(mask & ((1u << lane) - 1u));
-    if (pos < o.cap) o.keys[pos] = (gstart << 24) | (uint64_t)size;
+    if (pos < o.cap) o.keys[pos] = (gstart << o.len_bits) | (uint64_t)size;
     uint32_t bin = size - low;
     if (bin < hist_s_n) atomicAdd(&hist_s[bin], 1u);
     else atomicAdd(&o.hist_frag[size], 1ull);
@@ -430,7 +431,7 @@ int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr
                     const FragBuffers &fb) {
     if (g_end <= g_begin) return 0;
     const uint64_t n_mol = g_end - g_begin;
-    FragOut o{fb.keys, fb.cap, fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, fb.long_cap, fb.long_count,
+    FragOut o{fb.keys, fb.cap, key_len_bits(m.high), fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, fb.long_cap, fb.long_count,
               fb.error, fb.q_a, fb.q_b, fb.q_cap, fb.q_count};
     // after_* methods only queue intervals here (k_intervals owns the after-fragmentation histogram)
     uint32_t hist_s_n = m.method <= RLSIM_AFTER_NOPRIM_DOUBLE ? 0 : frag_hist_bins(m);
@@ -447,7 +448,7 @@ int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr
 
 int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint64_t n_q) {
     if (n_q == 0) return 0;
-    FragOut o{fb.keys, fb.cap, fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, fb.long_cap, fb.long_count,
+    FragOut o{fb.keys, fb.cap, key_len_bits(m.high), fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, fb.long_cap, fb.long_count,
               fb.error, fb.q_a, fb.q_b, fb.q_cap, fb.q_count};
     uint32_t hist_s_n = frag_hist_bins(m);
     uint64_t blocks = (n_q + IV_THREADS - 1) / IV_THREADS;
@@ -459,7 +460,7 @@ int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &t
 
 int launch_fragment_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t n_long) {
     if (n_long == 0) return 0;
-    FragOut o{fb.keys, fb.cap, fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, n_long, nullptr,
+    FragOut o{fb.keys, fb.cap, key_len_bits(m.high), fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, n_long, nullptr,
               fb.error, fb.q_a, fb.q_b, fb.q_cap, fb.q_count};
     const uint32_t smem_cap = 32768;  // breakpoints per molecule (128 KB of shared memory)
     cudaFuncSetAttribute(k_fragment_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_cap * 4));

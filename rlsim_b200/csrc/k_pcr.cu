@@ -9,18 +9,18 @@
 
 namespace rl {
 
-__global__ void k_decode_species(DevTranscripts tr, const uint64_t *__restrict__ keys, DevSpecies sp) {
+__global__ void k_decode_species(DevTranscripts tr, const uint64_t *__restrict__ keys, DevSpecies sp, uint32_t len_bits) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= sp.n) return;
     uint64_t key = keys[i];
-    uint64_t gstart = key >> 24;
+    uint64_t gstart = key >> len_bits;
     uint32_t t = upper_bound_u64(tr.off, tr.n + 1, gstart) - 1;
     sp.tr[i] = t;
     sp.start[i] = (uint32_t)(gstart - tr.off[t]);
-    sp.len[i] = (uint32_t)(key & 0xffffffu);
+    sp.len[i] = (uint32_t)(key & ((1ull << len_bits) - 1ull));
 }
-void launch_decode_species(cudaStream_t st, const DevTranscripts &tr, const uint64_t *keys, DevSpecies sp) {
-    if (sp.n) k_decode_species<<<(unsigned)((sp.n + 255) / 256), 256, 0, st>>>(tr, keys, sp);
+void launch_decode_species(cudaStream_t st, const DevTranscripts &tr, const uint64_t *keys, DevSpecies sp, uint32_t high) {
+    if (sp.n) k_decode_species<<<(unsigned)((sp.n + 255) / 256), 256, 0, st>>>(tr, keys, sp, key_len_bits(high));
 }
 
 // CalcLenScalers + CalcLengthEff, thermocycler.go:83-92,149-156, with the library's restatement of Go's math.Pow

@@ -36,7 +36,7 @@ struct DevSpecies {
     double *eff;                  // optional (tests): per-species efficiency
     uint32_t *gc;                 // optional (tests): GC count
 };
-void launch_decode_species(cudaStream_t st, const DevTranscripts &tr, const uint64_t *keys, DevSpecies sp);
+void launch_decode_species(cudaStream_t st, const DevTranscripts &tr, const uint64_t *keys, DevSpecies sp, uint32_t high);
 void launch_len_eff(cudaStream_t st, const DevModel &m, double *len_eff);
 void launch_pcr(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, DevSpecies sp, int *error);
 void launch_amplify_probe(cudaStream_t st, PxKey key, const uint32_t *tse, const uint64_t *n0, const double *p, int cycles,
