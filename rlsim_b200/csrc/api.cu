@@ -218,7 +218,7 @@ struct rlsim_handle {
     uint64_t n_out = 0;
     DBuf<uint32_t> d_o_tr, d_o_start, d_o_end;
     DBuf<uint8_t> d_o_minus;
-    DBuf<uint64_t> d_o_id;
+    DBuf<uint64_t> d_o_id, d_tr_out_base;
     // fasta
     DBuf<uint8_t> d_names, d_fasta;
     DBuf<uint64_t> d_name_off, d_rec_sizes, d_rec_off;
@@ -1329,7 +1329,7 @@ int finish_sample(rlsim_handle *h) {
     int rc;
     uint64_t ns = h->n_sp;
     DevModel m = make_model(h);
-    StageTimer tm(h, RLSIM_T_EXPAND, 4);
+    StageTimer tm(h, RLSIM_T_EXPAND, 5);
     launch_taken(h->st, make_sp(h), h->d_mode.p, h->n_len, h->d_hits.p, h->d_taken.p);
     CK(h, cudaMemsetAsync(h->d_out_off.p, 0, 8, h->st));
     h->n_out = 0;
@@ -1344,7 +1344,8 @@ int finish_sample(rlsim_handle *h) {
     CK(h, h->d_o_tr.ensure(h->n_out)); CK(h, h->d_o_start.ensure(h->n_out)); CK(h, h->d_o_end.ensure(h->n_out));
     CK(h, h->d_o_minus.ensure(h->n_out)); CK(h, h->d_o_id.ensure(h->n_out));
     DevSampled out{h->d_o_tr.p, h->d_o_start.p, h->d_o_end.p, h->d_o_minus.p, h->d_o_id.p};
-    launch_expand(h->st, m, make_sp(h), h->d_out_off.p, h->n_out, out);
+    CK(h, h->d_tr_out_base.ensure(h->h_len.size() + 1));
+    launch_expand(h->st, m, make_sp(h), h->d_out_off.p, h->d_tr_out_base.p, h->n_out, out);
     tm.stop();
     CK(h, cudaGetLastError());
     CK(h, cudaStreamSynchronize(h->st));

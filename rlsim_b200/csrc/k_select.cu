@@ -233,7 +233,16 @@ void launch_taken(cudaStream_t st, const DevSpecies &sp, const uint8_t *mode_by_
 }
 
 // ---------------------------------------------------------------- final records
-__global__ void k_expand(const __grid_constant__ DevModel m, DevSpecies sp, const uint64_t *__restrict__ out_off, uint64_t n_out, DevSampled out) {
+// first output record of every transcript that has species: the per-transcript fragment ids count from there
+__global__ void k_tr_out_base(DevSpecies sp, const uint64_t *__restrict__ out_off, uint64_t *__restrict__ tr_out_base) {
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= sp.n) return;
+    const uint32_t t = sp.tr[s];
+    if (s == 0 || sp.tr[s - 1] != t) tr_out_base[t] = out_off[s];
+}
+
+__global__ void k_expand(const __grid_constant__ DevModel m, DevSpecies sp, const uint64_t *__restrict__ out_off,
+                         const uint64_t *__restrict__ tr_out_base, uint64_t n_out, DevSampled out) {
     uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= n_out) return;
     // species s with out_off[s] <= o < out_off[s+1]
@@ -245,23 +254,19 @@ __global__ void k_expand(const __grid_constant__ DevModel m, DevSpecies sp, cons
     uint64_t s = lo;
     uint64_t j = o - out_off[s];
     uint32_t t = sp.tr[s], start = sp.start[s], end = start + sp.len[s];
-    // first species of this transcript -> per-transcript fragment id (sampler.go:189,204)
-    uint64_t a = 0, b = s;
-    while (a < b) {
-        uint64_t mid = a + ((b - a) >> 1);
-        if (sp.tr[mid] < t) a = mid + 1; else b = mid;
-    }
     PxStream str{m.key_strand, m.first_index + t, start, end};
     bool minus = px_u01(px_draw64(str, j)) < m.strand_bias;  // sampler.go:219-227
     out.tr[o] = m.first_index + t;  // global transcript index
     out.start[o] = start;
     out.end[o] = end;
     out.minus[o] = minus ? 1 : 0;
-    out.id[o] = o - out_off[a];
+    out.id[o] = o - tr_out_base[t];  // per-transcript fragment id (sampler.go:189,204)
 }
-void launch_expand(cudaStream_t st, const DevModel &m, const DevSpecies &sp, const uint64_t *out_off, uint64_t n_out,
-                   DevSampled out) {
-    if (n_out) k_expand<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(m, sp, out_off, n_out, out);
+void launch_expand(cudaStream_t st, const DevModel &m, const DevSpecies &sp, const uint64_t *out_off, uint64_t *tr_out_base,
+                   uint64_t n_out, DevSampled out) {
+    if (!n_out) return;
+    k_tr_out_base<<<(unsigned)((sp.n + 255) / 256), 256, 0, st>>>(sp, out_off, tr_out_base);
+    k_expand<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(m, sp, out_off, tr_out_base, n_out, out);
 }
 
 }  // namespace rl

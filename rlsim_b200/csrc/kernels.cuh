@@ -72,8 +72,8 @@ void launch_apply_records(cudaStream_t st, const uint4 *records, uint64_t n, con
 void launch_taken(cudaStream_t st, const DevSpecies &sp, const uint8_t *mode_by_len, uint32_t n_len,
                   const unsigned long long *hits, uint64_t *taken);
 struct DevSampled { uint32_t *tr, *start, *end; uint8_t *minus; uint64_t *id; };
-void launch_expand(cudaStream_t st, const DevModel &m, const DevSpecies &sp, const uint64_t *out_off, uint64_t n_out,
-                   DevSampled out);
+void launch_expand(cudaStream_t st, const DevModel &m, const DevSpecies &sp, const uint64_t *out_off, uint64_t *tr_out_base,
+                   uint64_t n_out, DevSampled out);
 
 // k_fasta_in.cu
 uint32_t fasta_tiles(uint64_t n);
