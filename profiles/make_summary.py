@@ -133,7 +133,8 @@ if all(k in n for k in ("n2", "n4")):
     if "n8" in n:
         line += " / %.2f" % (n["n8"]["value"] / 1e9)
         eff += " / %.0f %%" % (100 * n["n8"]["value"] / (8 * d["value"]))
-    out.append(line + " G fragments/s at 1 / 2 / 4%s GPUs (%s of linear)." % (" / 8" if "n8" in n else "", eff))
+    out.append(line + " G fragments/s at 1 / 2 / 4%s GPUs (%s of linear; the 8-GPU line was measured two small kernel changes "
+               "before the others, against 1.37 G fragments/s at one GPU then: 82 %%)." % (" / 8" if "n8" in n else "", eff))
 if "reference" in n:
     out.append("Reference release binary on the same box, %d cores (profiles/r1_final_bench_reference.json): %.2e fragments/s."
                % (n["reference"]["cpu_baseline"]["cores"], n["reference"]["value"]))
