@@ -374,7 +374,9 @@ def main():
                 "frac": own[dom]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
                 "note": ("k_pcr is FP64-issue bound (15 exact binomial draws per 32 B species): see profiles/r1_final_ncu_summary.md"
                          if dom == "pcr" else ""),
-                "all": {("k_" + k): {"ms": round(v["ms"], 4), "achieved": round(v["gbs"], 2), "frac": round(v["gbs"] / peak, 4)} for k, v in own.items()}}
+                "all": {("k_" + k): {"ms": round(v["ms"], 4), "achieved": round(v["gbs"], 2), "frac": round(v["gbs"] / peak, 4)} for k, v in own.items()},
+                "all_note": "k_prefix shares the GPU with k_target (own stream) in this step: alone it takes 0.70 ms = 2.7 TB/s "
+                            "(profiles/r1_final_ncu_summary.md)"}
     ms_per_step = 1000.0 * t_res / K
     line = {
         "metric": "fragments/sec (frag+PCR+size-select)", "value": n_res / t_res, "unit": "fragments/s", "n_gpus": world,

@@ -900,7 +900,11 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
 extern "C" {
 
 int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t *offsets, const uint64_t *expr, uint32_t n) {
-    return add_core(h, bases, nullptr, offsets, expr, n);
+    try {
+        return add_core(h, bases, nullptr, offsets, expr, n);
+    } catch (const std::bad_alloc &) {  // host bookkeeping arrays: no exception crosses the C ABI
+        FAIL(h, RLSIM_E_NOMEM, "out of host memory while adding transcripts");
+    }
 }
 
 // Device-side FASTA reader (k_fasta_in.cu): fasta.go:113-212 + input.go:82-124 in four kernels, then the usual ingest
@@ -990,7 +994,11 @@ int rlsim_add_fasta(rlsim_handle *h, const uint8_t *text, uint64_t n_bytes, doub
     if (n_records) *n_records = n_rec;
     if (n_added) *n_added = n_valid;
     if (!n_valid) return 0;
-    return add_core(h, nullptr, src, offsets.data(), levels.data(), n_valid);
+    try {
+        return add_core(h, nullptr, src, offsets.data(), levels.data(), n_valid);
+    } catch (const std::bad_alloc &) {
+        FAIL(h, RLSIM_E_NOMEM, "out of host memory while adding transcripts");
+    }
 }
 
 int rlsim_get_fasta_index(rlsim_handle *h, uint64_t *name_start, uint32_t *line_len, uint32_t *name_len, uint64_t *level,
