@@ -134,7 +134,8 @@ class RecordExchange:
         rc = [int(x) for x in recv_counts.cpu()]
         recv = torch.empty((sum(rc), 2), dtype=torch.int64, device=self.device)
         dist.all_to_all_single(recv, buf[:needed], output_split_sizes=rc, input_split_sizes=[int(c) for c in counts], group=group)
-        torch.cuda.synchronize(self.device)
+        if self.device is not None and torch.cuda.is_available():
+            torch.cuda.synchronize(self.device)
         handle.apply_selected(recv.data_ptr() if recv.shape[0] else None, recv.shape[0])
         handle.finish_sample()
         return all_tot

@@ -181,6 +181,42 @@ try:
     raise SystemExit("overflow not detected")
 except OverflowError:
     pass
+
+# the selection exchange (RecordExchange): [totals | partial target] in one all-gather, then counts + records all-to-all
+import ctypes
+class FakeHandle:
+    def class_totals(self):
+        return np.array([5 + r, 3, 0, 7], dtype=np.uint64)
+    def hist(self, kind, nb):
+        assert kind == 0
+        return (np.arange(nb) + r).astype(np.uint64)
+    def select_classes(self, all_tot, rank, ptr, cap):
+        assert all_tot.shape == (2, 4) and list(all_tot[:, 0]) == [5, 6] and rank == r
+        counts = np.array([r + 1, 2], dtype=np.uint64)      # records for rank 0, rank 1
+        needed = int(counts.sum())
+        if needed <= cap:
+            rec = (ctypes.c_int64 * (2 * needed)).from_address(ptr)
+            k = 0
+            for dest in range(2):
+                for j in range(int(counts[dest])):
+                    rec[2 * k], rec[2 * k + 1] = 100 * r + dest, j
+                    k += 1
+        return counts, needed
+    def apply_selected(self, ptr, n):
+        rec = (ctypes.c_int64 * (2 * n)).from_address(ptr) if n else []
+        self.got = sorted((rec[2 * i], rec[2 * i + 1]) for i in range(n))
+    def finish_sample(self):
+        self.finished = True
+class FakePool:
+    _target_nb = 3
+    def _sum_target(self, tot):
+        self.target, self._target_nb = list(tot), 0
+fh, fp = FakeHandle(), FakePool()
+all_tot = shard.RecordExchange(None).run(fh, r, 2, 16, pool=fp)
+assert all_tot.shape == (2, 4) and list(all_tot[1]) == [6, 3, 0, 7]
+assert fp.target == [1, 3, 5] and fp._target_nb == 0                       # (0,1,2) + (1,2,3)
+want = {0: [(0, 0), (100, 0), (100, 1)], 1: [(1, 0), (1, 1), (101, 0), (101, 1)]}[r]   # from rank 0: r+1=1 / 2; from rank 1: 2 / 2
+assert fh.got == sorted(want) and fh.finished, (r, fh.got)
 dist.destroy_process_group()
 """
 
