@@ -110,7 +110,8 @@ int rlsim_set_len_eff(rlsim_handle *h, const double *len_eff, uint64_t low, uint
 int rlsim_set_raw_target(rlsim_handle *h, const uint32_t *lengths, const double *probs, uint32_t n);
 
 /* ---- Targeter (target.go:102-132 / raw_target.go:104-138) ----
- * Either draw the req_frags target lengths on the device ... */
+ * Either draw the req_frags target lengths on the device ... (the draws run on a stream of their own beside the
+ * transcript pipeline; the histogram reaches the host when it is first needed: selection, rlsim_get_hist) */
 int rlsim_sample_target(rlsim_handle *h, int64_t req_frags);
 /* Multi-GPU: draw only the target lengths with draw index in [first, first+count) (the stream is addressed by the draw
  * index); read the partial histogram with rlsim_get_hist(RLSIM_H_TARGET), sum it over the ranks and impose the sum with
@@ -124,7 +125,11 @@ int rlsim_set_target_hist(rlsim_handle *h, const uint32_t *lengths, const uint64
  * upper-cased sequences (no poly-A), offsets[n+1] into it, expr[n] = expression levels with -m applied.
  * May be called repeatedly (batches).  first_index = global index of the first record of this process's
  * shard (0 on a single GPU); it keys the per-transcript random streams so any sharding reproduces the
- * same fragments. */
+ * same fragments.
+ * When the model, the target (and, if the host supplies it, the length-efficiency table) and first_index are already set,
+ * the library does not wait for rlsim_build_library: every group of 32 MB chunks that has reached the device is
+ * fragmented, deduplicated and amplified while the following chunks are still being copied, and rlsim_build_library only
+ * finishes the per-length view (rlsim_stats.flags & RLSIM_F_EAGER).  The result does not depend on that. */
 int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t *offsets, const uint64_t *expr,
                           uint32_t n);
 /* Device-side FASTA reader (next row 8f-3; fasta.go:113-212 ReadFasta/FastaToSeq, input.go:82-124 ParseSeqName and the
