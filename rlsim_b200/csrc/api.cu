@@ -219,6 +219,7 @@ struct rlsim_handle {
     DBuf<uint32_t> d_o_tr, d_o_start, d_o_end;
     DBuf<uint8_t> d_o_minus;
     DBuf<uint64_t> d_o_id, d_tr_out_base;
+    DBuf<uint32_t> d_cand_k32, d_cand_k32_sorted;  // narrow sort keys of the selection candidates
     // fasta
     DBuf<uint8_t> d_names, d_fasta;
     DBuf<uint64_t> d_name_off, d_rec_sizes, d_rec_off;
@@ -1284,13 +1285,23 @@ int select_core(rlsim_handle *h, const std::vector<uint64_t> &T, const std::vect
         CK(h, h->d_cand_idx.ensure(n_cand)); CK(h, h->d_cand_idx_sorted.ensure(n_cand));
         CK(h, h->d_flags.ensure(n_cand)); CK(h, h->d_fscan.ensure(n_cand + 1));
         StageTimer tm(h, RLSIM_T_SELECT, 5 + radix_launches((int)bits_for(G)));
-        launch_candidates(h->st, m, plan_d, n_cand, h->d_cand_keys.p, h->d_cand_idx.p);
+        // every key is below G: when G fits 32 bits the sort runs on a narrow copy of the keys (a third less traffic)
+        const bool narrow = G <= 0xffffffffull;
+        if (narrow) { CK(h, h->d_cand_k32.ensure(n_cand)); CK(h, h->d_cand_k32_sorted.ensure(n_cand)); }
+        launch_candidates(h->st, m, plan_d, n_cand, h->d_cand_keys.p, narrow ? h->d_cand_k32.p : nullptr, h->d_cand_idx.p);
         size_t tb = 0;
         int eb = (int)bits_for(G);
-        CK(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, h->d_cand_keys.p, h->d_cand_keys_sorted.p, h->d_cand_idx.p, h->d_cand_idx_sorted.p, (int)n_cand, 0, eb, h->st));
-        if ((rc = cub_temp(h, tb))) return rc;
-        CK(h, cub::DeviceRadixSort::SortPairs(h->d_cub.p, tb, h->d_cand_keys.p, h->d_cand_keys_sorted.p, h->d_cand_idx.p, h->d_cand_idx_sorted.p, (int)n_cand, 0, eb, h->st));
-        launch_first_flags(h->st, h->d_cand_keys_sorted.p, h->d_cand_idx_sorted.p, n_cand, h->d_flags.p);
+        if (narrow) {
+            CK(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, h->d_cand_k32.p, h->d_cand_k32_sorted.p, h->d_cand_idx.p, h->d_cand_idx_sorted.p, (int)n_cand, 0, eb, h->st));
+            if ((rc = cub_temp(h, tb))) return rc;
+            CK(h, cub::DeviceRadixSort::SortPairs(h->d_cub.p, tb, h->d_cand_k32.p, h->d_cand_k32_sorted.p, h->d_cand_idx.p, h->d_cand_idx_sorted.p, (int)n_cand, 0, eb, h->st));
+            launch_first_flags32(h->st, h->d_cand_k32_sorted.p, h->d_cand_idx_sorted.p, n_cand, h->d_flags.p);
+        } else {
+            CK(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, h->d_cand_keys.p, h->d_cand_keys_sorted.p, h->d_cand_idx.p, h->d_cand_idx_sorted.p, (int)n_cand, 0, eb, h->st));
+            if ((rc = cub_temp(h, tb))) return rc;
+            CK(h, cub::DeviceRadixSort::SortPairs(h->d_cub.p, tb, h->d_cand_keys.p, h->d_cand_keys_sorted.p, h->d_cand_idx.p, h->d_cand_idx_sorted.p, (int)n_cand, 0, eb, h->st));
+            launch_first_flags(h->st, h->d_cand_keys_sorted.p, h->d_cand_idx_sorted.p, n_cand, h->d_flags.p);
+        }
         CK(h, cudaMemsetAsync(h->d_fscan.p, 0, 8, h->st));
         tb = 0;
         CK(h, cub::DeviceScan::InclusiveSum(nullptr, tb, h->d_flags.p, h->d_fscan.p + 1, (int)n_cand, h->st));

@@ -72,29 +72,37 @@ __device__ __forceinline__ uint32_t class_of(const DevClassPlan &p, uint64_t g) 
     return upper_bound_u64(p.cand_off, p.n_classes + 1, g) - 1;
 }
 
+// keys32: optional narrow copy of the keys for the sort (all keys < 2^32: a third less sort traffic)
 __global__ void k_candidates(const __grid_constant__ DevModel m, DevClassPlan plan, uint64_t n_cand, uint64_t *__restrict__ keys,
-                             uint32_t *__restrict__ idx) {
+                             uint32_t *__restrict__ keys32, uint32_t *__restrict__ idx) {
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_cand) return;
     uint32_t c = class_of(plan, g);
     uint32_t j = (uint32_t)(g - plan.cand_off[c]);
     PxStream s{m.key_select, plan.len[c], 0u, 0u};
-    keys[g] = plan.G[c] + s.below(j, plan.T[c]);
+    const uint64_t key = plan.G[c] + s.below(j, plan.T[c]);
+    keys[g] = key;
+    if (keys32) keys32[g] = (uint32_t)key;
     idx[g] = (uint32_t)g;
 }
-void launch_candidates(cudaStream_t st, const DevModel &m, DevClassPlan plan, uint64_t n_cand, uint64_t *keys, uint32_t *idx) {
-    if (n_cand) k_candidates<<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(m, plan, n_cand, keys, idx);
+void launch_candidates(cudaStream_t st, const DevModel &m, DevClassPlan plan, uint64_t n_cand, uint64_t *keys, uint32_t *keys32,
+                       uint32_t *idx) {
+    if (n_cand) k_candidates<<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(m, plan, n_cand, keys, keys32, idx);
 }
 
 // after the stable sort by key: the first entry of each run of equal keys is the earliest draw of that rank
-__global__ void k_first_flags(const uint64_t *__restrict__ sk, const uint32_t *__restrict__ si, uint64_t n,
+template <typename K>
+__global__ void k_first_flags(const K *__restrict__ sk, const uint32_t *__restrict__ si, uint64_t n,
                               uint32_t *__restrict__ flags) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     flags[si[p]] = (p == 0 || sk[p] != sk[p - 1]) ? 1u : 0u;
 }
 void launch_first_flags(cudaStream_t st, const uint64_t *sk, const uint32_t *si, uint64_t n, uint32_t *flags) {
-    if (n) k_first_flags<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sk, si, n, flags);
+    if (n) k_first_flags<uint64_t><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sk, si, n, flags);
+}
+void launch_first_flags32(cudaStream_t st, const uint32_t *sk, const uint32_t *si, uint64_t n, uint32_t *flags) {
+    if (n) k_first_flags<uint32_t><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sk, si, n, flags);
 }
 
 __global__ void k_apply_picks(DevClassPlan plan, uint64_t n_cand, const uint64_t *__restrict__ keys,

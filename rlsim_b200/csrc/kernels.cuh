@@ -57,9 +57,10 @@ struct DevClassPlan {          // per requested length class (host-built, device
     const uint64_t *cand_off;  // [n_classes+1] candidate index range of the class
     const uint64_t *pick;      // number of distinct ranks to keep
 };
-void launch_candidates(cudaStream_t st, const DevModel &m, DevClassPlan plan, uint64_t n_cand, uint64_t *keys,
+void launch_candidates(cudaStream_t st, const DevModel &m, DevClassPlan plan, uint64_t n_cand, uint64_t *keys, uint32_t *keys32,
                        uint32_t *idx);
 void launch_first_flags(cudaStream_t st, const uint64_t *sorted_keys, const uint32_t *sorted_idx, uint64_t n, uint32_t *flags);
+void launch_first_flags32(cudaStream_t st, const uint32_t *sorted_keys, const uint32_t *sorted_idx, uint64_t n, uint32_t *flags);
 void launch_apply_picks(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, const uint64_t *keys_by_idx,
                         const uint32_t *flags, const uint64_t *flag_scan, const uint64_t *cls_pre,
                         const uint64_t *bounds, const uint32_t *order, unsigned long long *hits, int *short_flag);
