@@ -116,7 +116,8 @@ out.append("""
 | + prefetched header draws, occupancy-targeted launch bounds | 8.6 | 2.17 | 1.15 | 2.26 | |
 | + FP32 pre-decision of the BTRS acceptance test (exact FP64 fallback) | 8.1 | 2.17 | 1.15 | 1.76 | |
 | + reverse priming through mirrored forward sums (symmetric k-mer table): no reverse arrays | 7.6 | 2.15 | 0.70 | 1.76 | half the prefix bytes again |
-| + target draws on their own stream, quad-wise in-block walk of the priming search, molecule kernel compiled per method | %.1f | %.2f | %.2f | %.2f | final (`prefix` overlaps `k_target`; alone 0.70) |
+| + target draws on their own stream, quad-wise in-block walk of the priming search, molecule kernel compiled per method | 7.3 | 1.89 | 0.70 | 1.76 | |
+| + compact fragment keys, transcript output base table in `k_expand`, 32-bit selection sort keys | %.1f | %.2f | %.2f | %.2f | final (`prefix` overlaps `k_target`; alone 0.70) |
 
 End to end (host buffers in, fragment records out): 43.8 ms -> 21.8 ms (persistent staging, H2D on a copy stream overlapped with ingest +
 prefix sums per 32 MB chunk) -> %.1f ms (eager chunk pipeline: every arrived group of chunks is fragmented, deduplicated and amplified while
@@ -134,7 +135,8 @@ if all(k in n for k in ("n2", "n4")):
         line += " / %.2f" % (n["n8"]["value"] / 1e9)
         eff += " / %.0f %%" % (100 * n["n8"]["value"] / (8 * d["value"]))
     out.append(line + " G fragments/s at 1 / 2 / 4%s GPUs (%s of linear; the 8-GPU line was measured two small kernel changes "
-               "before the others, against 1.37 G fragments/s at one GPU then: 82 %%)." % (" / 8" if "n8" in n else "", eff))
+               "before the others, against 1.37 G fragments/s at one GPU then: 82 %%; the 2- and 4-GPU lines just before the last 0.1 ms "
+               "came off the selection sort: against 1.41 then, 86 %% / 86 %%)." % (" / 8" if "n8" in n else "", eff))
 if "reference" in n:
     out.append("Reference release binary on the same box, %d cores (profiles/r1_final_bench_reference.json): %.2e fragments/s."
                % (n["reference"]["cpu_baseline"]["cores"], n["reference"]["value"]))
