@@ -135,8 +135,8 @@ if all(k in n for k in ("n2", "n4")):
         line += " / %.2f" % (n["n8"]["value"] / 1e9)
         eff += " / %.0f %%" % (100 * n["n8"]["value"] / (8 * d["value"]))
     out.append(line + " G fragments/s at 1 / 2 / 4%s GPUs (%s of linear; the 8-GPU line was measured two small kernel changes "
-               "before the others, against 1.37 G fragments/s at one GPU then: 82 %%; the 2- and 4-GPU lines just before the last 0.1 ms "
-               "came off the selection sort: against 1.41 then, 86 %% / 86 %%)." % (" / 8" if "n8" in n else "", eff))
+               "before the others, against 1.37 G fragments/s at one GPU then: 82 %%; the 4-GPU line just before the last 0.1 ms "
+               "came off the selection sort: against 1.41 then, 86 %%)." % (" / 8" if "n8" in n else "", eff))
 if "reference" in n:
     out.append("Reference release binary on the same box, %d cores (profiles/r1_final_bench_reference.json): %.2e fragments/s."
                % (n["reference"]["cpu_baseline"]["cores"], n["reference"]["value"]))
