@@ -1,5 +1,6 @@
-"""Device-side FASTA reader (rlsim_add_fasta) against the host reader that mirrors
-fasta.go:113-212 / input.go:82-124: same records, same skips, same sequences, same library."""
+"""Device-side FASTA reader (rlsim_add_fasta) against oracle/fasta_reader.py, the byte-by-byte
+restatement of fasta.go:113-212 / input.go:82-124 that is pinned against the release binary (tests/test_oracle_pin.py):
+same records, same skips, same sequences, same library."""
 import os
 import subprocess
 import sys
@@ -8,22 +9,14 @@ import numpy as np
 import pytest
 
 import util
-from rlsim_b200 import fasta as hostfasta
+from oracle import fasta_reader
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(util.HERE)
 
 
 def _host_index(data, expr_mul=1.0):
-    recs = hostfasta.read_records(data)
-    rows = []
-    for name, seq in recs:
-        parsed = hostfasta.parse_seq_name(name)
-        if parsed is None:
-            rows.append((name, None, None, len(seq), seq))
-        else:
-            rows.append((name, parsed[0], int(float(parsed[1]) * expr_mul), len(seq), seq))
-    return rows
+    return [(r["line"], r["name"], r["level"], len(r["seq"]), r["seq"]) for r in fasta_reader.read(data, expr_mul)]
 
 
 def _device(gpu, data, expr_mul=1.0, argv=("-n", "300", "-si", "2")):
@@ -71,6 +64,14 @@ def _check_index(gpu, data, expr_mul=1.0):
 
 def _seq(rng, n, alphabet=b"ACGT"):
     return bytes(rng.choice(list(alphabet), size=n).astype(np.uint8))
+
+
+def test_texts_pinned_against_the_release_binary(gpu):
+    """The unusual texts of tests/golden/fasta_reader.json (what the binary made of them pins the oracle reader)."""
+    import json
+    for name, g in sorted(json.load(open(os.path.join(util.GOLDEN, "fasta_reader.json"))).items()):
+        mul = float(g["argv"][g["argv"].index("-m") + 1]) if "-m" in g["argv"] else 1.0
+        _check_index(gpu, g["text"].encode("latin1"), expr_mul=mul)
 
 
 def test_basic_fixture_and_layouts(gpu):

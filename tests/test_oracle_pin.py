@@ -96,3 +96,42 @@ def test_live_binary_matches_golden(oracle):
             L.orc_revcomp(ref, len(ref), out.ctypes.data)
             ref = out.tobytes()
         assert seq == ref
+
+
+# ---------------------------------------------------------------- the FASTA reader (fasta.go:113-212, input.go:82-124)
+def _reader_golden():
+    import json
+    import os
+    return json.load(open(os.path.join(util.GOLDEN, "fasta_reader.json")))
+
+
+@pytest.mark.parametrize("name", sorted(_reader_golden()))
+def test_fasta_reader_pinned_against_release_binary(name):
+    """oracle/fasta_reader.py against what the release binary made of the same unusual text: the two report panels the
+    reader feeds, the skipped name lines (in order) and the names that reach the FASTA output."""
+    from oracle import fasta_reader
+    g = _reader_golden()[name]
+    mul = float(g["argv"][g["argv"].index("-m") + 1]) if "-m" in g["argv"] else 1.0
+    rows = fasta_reader.read(g["text"].encode("latin1"), mul)
+    tr_len, expr = fasta_reader.panels(rows)
+    assert {str(k): v for k, v in tr_len.items()} == g["panels"]["Transcript lengths"]
+    assert {str(k): v for k, v in expr.items()} == g["panels"]["Expression levels"]
+    assert [r["line"].decode("latin1") for r in rows if r["name"] is None] == g["skipped"]
+    expressed = {r["name"].decode("latin1") for r in rows if r["name"] is not None and r["level"] > 0}
+    assert set(g["out_names"]) <= expressed and g["out_names"]
+
+
+def test_host_mirrors_match_the_reader_oracle():
+    """rlsim_b200/fasta.py (vectorised host mirror) against oracle/fasta_reader.py, also on texts the binary cannot take
+    (a record without newline makes it panic; the mirrors and the device reader treat it as a bare name line)."""
+    from oracle import fasta_reader
+    from rlsim_b200 import fasta as hostfasta
+    texts = [g["text"].encode("latin1") for g in _reader_golden().values()]
+    texts += [b">a$1\nAC\n>>>b$2\nGT\n", b">a$1\nACGT\n>tail$3", b">only", b">a$5\n\n\n", b">a$1\nAC>b$2\nG T\tA\r\n>c", b""]
+    for t in texts:
+        want = fasta_reader.read(t)
+        got = hostfasta.read_records(t)
+        assert [(r["line"], r["seq"]) for r in want] == got, t[:40]
+        for r in want:
+            p = hostfasta.parse_seq_name(r["line"])
+            assert (p is None) == (r["name"] is None) and (p is None or (p[0], p[1]) == (r["name"], r["level"])), r["line"]
