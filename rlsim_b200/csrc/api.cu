@@ -156,6 +156,7 @@ struct rlsim_handle {
     bool eager_started = false;             // counters / histograms zeroed for this transcript set
     bool eager_pcr = false;                 // species counts already amplified (consumed by the next rlsim_pcr)
     bool eager_used = false;                // the current species table came from the eager pipeline (rlsim_stats.flags)
+    uint32_t eager_groups = 0;              // groups started since the last reset (test hook)
     uint64_t eager_keys = 0, eager_sp = 0;  // running fragment-key / species counts
     bool len_eff_ready = false;
     DBuf<uint8_t> d_bases;
@@ -388,6 +389,7 @@ int check_device_error(rlsim_handle *h);
 
 void eager_reset(rlsim_handle *h) {
     h->eager_upto = 0; h->eager_failed = h->eager_started = h->eager_pcr = false; h->eager_keys = h->eager_sp = 0;
+    h->eager_groups = 0;
 }
 
 double frag_denominator(rlsim_handle *h) {  // expected fragments per molecule <= L / denominator + 1
@@ -468,7 +470,11 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
     const unsigned int n_long = *reinterpret_cast<unsigned int *>(h->pin);
     const unsigned long long n_q = h->pin[1];
     tt1 = now_ms();
-    if (n_long > long_cap || n_q > h->d_q_a.n) { h->eager_failed = true; return 0; }
+    // test hook: pretend the estimate of group number RLSIM_EAGER_TEST_FAIL (0-based) was too small
+    const char *fail_at = getenv("RLSIM_EAGER_TEST_FAIL");
+    const bool forced = fail_at && (uint32_t)atoi(fail_at) == h->eager_groups;
+    h->eager_groups++;
+    if (forced || n_long > long_cap || n_q > h->d_q_a.n) { h->eager_failed = true; return 0; }
     launch_intervals(h->st, m, tr, fb, n_q);
     launch_fragment_long(h->st, m, tr, fb, n_long);
     h->launches[RLSIM_T_FRAGMENT] += 1 + (n_long ? 1 : 0); h->launches[RLSIM_T_INTERVALS] += n_q ? 1 : 0;

@@ -307,6 +307,17 @@ def test_eager_chunk_pipeline_equals_monolithic(gpu, monkeypatch, flags):
     monkeypatch.setenv("RLSIM_CHUNK_BYTES", "30000")
     variants.append(run(first_builds=2))                                   # second build recomputes from resident data
     variants.append(run(batches=((0, 1), (1, 150), (150, 151), (151, 400))))  # eager across several add calls
+    # a buffer estimate that turns out too small in the first group, or in a later one (two add calls make at least two
+    # groups whatever the copy timing): the monolithic path takes over and recomputes from the resident transcripts
+    for fail_at, batches in (("0", ((0, 400),)), ("1", ((0, 200), (200, 400)))):
+        monkeypatch.setenv("RLSIM_EAGER_TEST_FAIL", fail_at)
+        h = run(batches=batches)
+        assert not (int(h.stats().flags) & gpu.F_EAGER), fail_at
+        variants.append(h)
+    monkeypatch.delenv("RLSIM_EAGER_TEST_FAIL")
+    # the eager pipeline serves the after_* methods (pre_prim / prim_jump always take the monolithic path)
+    assert bool(int(variants[0].stats().flags) & gpu.F_EAGER) == flags[1].startswith("after")
+    assert not (int(mono.stats().flags) & gpu.F_EAGER)
     for h in variants:
         for k in ("tr", "start", "end", "count0", "count"):
             assert np.array_equal(mono.species()[k], h.species()[k]), k
