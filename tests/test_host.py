@@ -249,3 +249,23 @@ def test_cpp_twin_cli_surface():
     if not torch.cuda.is_available():
         p = subprocess.run([exe, "-n", "10", util.BASIC_FASTA], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
         assert p.returncode == 1 and b"cuda" in p.stderr.lower()
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's own CPU implementation on a bounded sample) prints ONE JSON line with
+    the keys the driver reads; under torchrun only rank 0 prints."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--scale", "0.02"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=600)
+    assert p.returncode == 0, p.stderr.decode()[-1500:]
+    lines = [l for l in p.stdout.decode().splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "fragments/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["metric"] == "fragments/sec (frag+PCR+size-select)" and d["vs_baseline"] is None
+    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["e2e"] == {"value": d["value"], "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env["RANK"] = "1"
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--scale", "0.02"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=600)
+    assert p.returncode == 0 and p.stdout.strip() == b""
