@@ -269,3 +269,12 @@ def test_bench_reference_arm_contract():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
                         "--scale", "0.02"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=600)
     assert p.returncode == 0 and p.stdout.strip() == b""
+
+
+def test_bench_own_arm_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0", "--scale", "0.01"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert p.returncode != 0 and b"no CPU fallback" in p.stderr and p.stdout.strip() == b""
