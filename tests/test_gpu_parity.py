@@ -109,6 +109,25 @@ def test_full_path_bit_exact(oracle, gpu, name):
     _compare(oracle, gpu, util.PIN_CONFIGS[name], seed=("-si", str(util.pin_seed(name))))
 
 
+@pytest.mark.parametrize("name", sorted(util.PIN_CONFIGS))
+def test_frozen_spec_digests(gpu, name):
+    """The CUDA path against the frozen digests of the specification (tests/golden/philox_spec.json) - no oracle involved."""
+    import hashlib
+    import json
+    import os
+    g = json.load(open(os.path.join(util.GOLDEN, "philox_spec.json")))[name]
+    args = util.parse(list(g["argv"]) + ["-si", str(g["seed"])])
+    names, seqs, levels = util.transcripts(args)
+    h = util.run_gpu(gpu, args, names, seqs, levels)
+    sp, sm = h.species(), h.sampled()
+    dg = lambda *arrs: hashlib.sha256(b"".join(np.ascontiguousarray(a).astype("<u8").tobytes() for a in arrs)).hexdigest()
+    st = h.stats()
+    assert (int(st.n_species), int(st.n_sampled), int(st.pool_total)) == (g["n_species"], g["n_sampled"], g["pool_total"])
+    assert dg(sp["tr"], sp["start"], sp["end"], sp["count0"]) == g["species"] and dg(sp["count"]) == g["counts"]
+    assert dg(sm["tr"], sm["start"], sm["end"], sm["minus"], sm["id"]) == g["sampled"]
+    assert hashlib.sha256(h.fasta(names)).hexdigest() == g["fasta"]
+
+
 def test_seed_policy(oracle, gpu):
     """main.go:129-149: -sp / -ss re-key PCR and sampling only."""
     _compare(oracle, gpu, util.C1 + ["-sp", "5", "-ss", "9"])

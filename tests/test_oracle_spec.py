@@ -260,3 +260,30 @@ def test_order_free_streams(oracle):
     m = whole["tr"] >= 2
     for k in ("tr", "start", "end", "count0", "count"):
         assert np.array_equal(whole[k][m], part[k]), k
+
+
+# ---------------------------------------------------------------- the specification is frozen
+def _spec_golden():
+    import json
+    import os
+    return json.load(open(os.path.join(util.GOLDEN, "philox_spec.json")))
+
+
+@pytest.mark.parametrize("name", sorted(_spec_golden()))
+def test_philox_spec_is_frozen(oracle, name):
+    """tests/golden/philox_spec.json: digests of what the normative restatement produces for every pinned configuration.
+    The oracle and the CUDA path are compared with each other everywhere else; this tripwire catches a change that moves
+    both together (regenerate with tests/golden/make_spec_golden.py only when the specification changes on purpose)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_spec_golden", os.path.join(util.GOLDEN, "make_spec_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = _spec_golden()[name]
+    args = util.parse(list(g["argv"]) + ["-si", str(g["seed"])])
+    names, seqs, levels = util.transcripts(args)
+    o = util.run_oracle(oracle, args, names, seqs, levels, oracle.MODE_PHILOX, stages="pcr")
+    sp = o.species()
+    o.sample()
+    got = mod.digest(sp, o, names)
+    assert got == {k: g[k] for k in got}
