@@ -87,11 +87,14 @@ typedef struct {
 } rlsim_stats;
 /* rlsim_stats.flags */
 enum { RLSIM_F_MIRRORED_REVERSE = 1,  /* reverse priming reads the forward prefix sums mirrored (symmetric k-mer table) */
-       RLSIM_F_EAGER = 2 };           /* the last library was fragmented and amplified while its transcripts were copied */
+       RLSIM_F_EAGER = 2,             /* the last library was fragmented and amplified while its transcripts were copied */
+       RLSIM_F_GROUPS_SHIFT = 8,      /* bits 8..15: number of chunk groups the eager pipeline ran (saturating at 255) */
+       RLSIM_F_PAGEABLE_STAGED = 4 }; /* the last rlsim_add_transcripts staged a pageable caller buffer through pinned memory */
 
 /* histogram kinds (fragstats.go:45-56); every histogram is indexed by length */
 enum { RLSIM_H_TARGET = 0, RLSIM_H_POLYA = 1, RLSIM_H_AFTER_FRAG = 2, RLSIM_H_AFTER_PCR = 3, RLSIM_H_SAMPLED = 4,
-       RLSIM_H_MISSING = 5, RLSIM_H_AFTER_SAMPLING = 6 };
+       RLSIM_H_MISSING = 5, RLSIM_H_AFTER_SAMPLING = 6,
+       RLSIM_H_POOL_GLOBAL = 7 };  /* after PCR, summed over the ranks (rlsim_sample_distributed) */
 
 typedef struct rlsim_handle rlsim_handle;
 
@@ -169,12 +172,28 @@ int rlsim_sample(rlsim_handle *h, const uint64_t *global_totals, const uint64_t 
  * class_totals).  rlsim_select_classes draws this rank's classes and writes the copy ranks to take (or to leave, for
  * classes drawn more than half) as 16-byte records {u32 len, u32 0, u64 rank_in_class} into `records_dev` - the caller's
  * DEVICE buffer of `cap` records - grouped by owner rank; counts_out[r] = records for rank r, *needed_out = their sum
- * (if it exceeds cap nothing is written: grow the buffer and call again).  The caller routes the groups with one
+ * (if it exceeds cap nothing is written: grow the buffer and call again).  The records are complete in device memory
+ * when the call returns (the library synchronises its own stream).  The caller routes the groups with one
  * all-to-all, hands what it receives to rlsim_apply_selected, and finishes with rlsim_finish_sample. */
 int rlsim_select_classes(rlsim_handle *h, const uint64_t *all_totals, uint32_t nparts, uint32_t part, uint32_t n_len,
                          void *records_dev, uint64_t cap, uint64_t *counts_out, uint64_t *needed_out);
 int rlsim_apply_selected(rlsim_handle *h, const void *records_dev, uint64_t n);
 int rlsim_finish_sample(rlsim_handle *h);
+
+/* ---- the same exchange inside the library: one process per GPU, an NCCL communicator of the library's own, everything
+ * queued on the handle's stream (no host framework between the steps).  libnccl.so.2 is bound at run time.
+ * Rank 0 makes an id with rlsim_comm_unique_id, the host passes it to every rank by any means, every rank calls
+ * rlsim_comm_init (collective).  rlsim_sample_distributed = Sampler.SampleFragments on all ranks: all-gather of
+ * [per-length pool totals | partial target histogram], class-partitioned draw, one grouped send/recv that routes the drawn
+ * copy ranks to their owners, apply, expand.  Afterwards RLSIM_H_POOL_GLOBAL holds the pool totals summed over the ranks.
+ * rlsim_comm_sum_target sums the partial target histograms early (a raw -j target shapes the library).
+ * rlsim_exchange_plan is the host arithmetic of the routing: counts[s*n+d] = records of sender s for rank d. */
+#define RLSIM_COMM_ID_BYTES 128
+int rlsim_comm_unique_id(uint8_t *id_out);
+int rlsim_comm_init(rlsim_handle *h, const uint8_t *id, int nranks, int rank);
+int rlsim_comm_sum_target(rlsim_handle *h);
+int rlsim_sample_distributed(rlsim_handle *h);
+int rlsim_exchange_plan(const uint64_t *counts, uint32_t n, uint32_t rank, uint64_t *send_off, uint64_t *recv_off);
 
 /* ---- results ---- */
 int rlsim_get_stats(rlsim_handle *h, rlsim_stats *out);
@@ -186,6 +205,12 @@ int rlsim_get_species(rlsim_handle *h, uint32_t *tr, uint32_t *start, uint32_t *
 /* sampled fragments (Frag records, frag.go:46-52) in output order; any pointer may be NULL */
 int rlsim_get_sampled(rlsim_handle *h, uint32_t *tr, uint32_t *start, uint32_t *end, uint8_t *minus_strand,
                       uint64_t *id);
+/* The same records packed for the host link: 6 bytes per fragment instead of 21.  The records are ordered by
+ * (transcript, start, end), so tr_counts[t] (t = 0 .. n_transcripts-1, this shard's indices) = number of records of
+ * transcript t replaces the per-record transcript index AND the id (ids count 0,1,.. within a transcript's run,
+ * sampler.go:189,204).  start[i] as above; len_strand[i] = (end - start) | strand << (8*elem_bytes - 1), elem_bytes = 2
+ * (needs high < 32768) or 4.  Any pointer may be NULL.  Pageable destinations are staged through pinned memory. */
+int rlsim_get_sampled_packed(rlsim_handle *h, uint32_t *tr_counts, uint32_t *start, void *len_strand, int elem_bytes);
 /* Frag.String for every sampled fragment (frag.go:71-126, sampler.go:206), formatted on the device:
  * ">Fg_<id>_<name> (Strand <s> Offset <start> -- <end>)\n<seq>\n".  names/name_off: transcript names of
  * this shard.  Call with buf = NULL to get the size. */
@@ -203,7 +228,7 @@ int rlsim_probe_amplify(rlsim_handle *h, int64_t seed_pcr, const uint32_t *tse, 
 /* device time of the kernels of the last build_library / sample call, milliseconds, by stage */
 enum { RLSIM_T_LAYOUT = 0, RLSIM_T_PREFIX = 1, RLSIM_T_FRAGMENT = 2, RLSIM_T_DEDUP = 3, RLSIM_T_PCR = 4,
        RLSIM_T_SELECT = 5, RLSIM_T_EXPAND = 6, RLSIM_T_FORMAT = 7, RLSIM_T_TARGET = 8, RLSIM_T_INTERVALS = 9,
-       RLSIM_T_COUNT = 10 };
+       RLSIM_T_EXCHANGE = 10, RLSIM_T_COUNT = 11 };
 int rlsim_get_timings(rlsim_handle *h, float *ms_out, uint64_t *launches_out);
 
 #ifdef __cplusplus

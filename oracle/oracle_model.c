@@ -60,9 +60,12 @@ void orc_binding_profile(const char *plus, uint32_t len, int k, double T, int re
 }
 
 /* spec 4.3: fixed-point priming weights.  scale = 2^26 / Kmax, Kmax = max K over the 4^k ACGT k-mers
- * (det_exp), w = floor(K * scale + 0.5) saturated to 2^26-1 (64 of them sum to less than 2^32: the GPU keeps
+ * (det_exp), w = floor(K * scale + 0.5) clamped to [1, 2^26-1] (64 of them sum to less than 2^32: the GPU keeps
  * u32 sums inside 64-entry blocks and u64 sums per block). */
 static double px_kmax(int k, double T) {
+    static int cache_k = -1;          /* one (k, T) at a time: the table scan is 4^k evaluations */
+    static double cache_T = 0.0, cache_v = 0.0;
+    if (k == cache_k && T == cache_T) return cache_v;
     char buf[32];
     double mx = 0.0;
     uint64_t n = (uint64_t)1 << (2 * k);
@@ -71,11 +74,13 @@ static double px_kmax(int k, double T) {
         double v = orc_kmer_affinity_n(buf, k, T, 1);
         if (v > mx) mx = v;
     }
+    cache_k = k; cache_T = T; cache_v = mx;
     return mx;
 }
 static uint64_t px_quant(double K, double scale) {
     double x = K * scale + 0.5;
     if (!(x < 67108863.0)) return 67108863ULL;
+    if (x < 1.0) return 1ULL;  /* never 0: a window of weak k-mers (low -p, runs of N) keeps a positive total */
     return (uint64_t)x;
 }
 void orc_quantized_weights(const char *plus, uint32_t len, int k, double T, int reverse, uint64_t *w) {

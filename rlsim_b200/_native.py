@@ -14,19 +14,22 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RLSIM_GPU_LIB") or os.path.join(HERE, "librlsim_gpu.so")  # override: A/B runs of two builds
 
 H_TARGET, H_POLYA, H_AFTER_FRAG, H_AFTER_PCR, H_SAMPLED, H_MISSING, H_AFTER_SAMPLING = range(7)
-T_NAMES = ["layout", "prefix", "fragment", "dedup", "pcr", "select", "expand", "format", "target", "intervals"]
+T_NAMES = ["layout", "prefix", "fragment", "dedup", "pcr", "select", "expand", "format", "target", "intervals", "exchange"]
+H_POOL_GLOBAL = 7
+COMM_ID_BYTES = 128
 
 E_CUDA, E_ARG, E_PRIMING, E_PCR_OVERFLOW, E_POOL_OVERFLOW, E_UNSUPPORTED, E_NOMEM = range(1, 8)  # include/rlsim_gpu.h
 
-F_MIRRORED_REVERSE, F_EAGER = 1, 2  # rlsim_stats.flags
+F_MIRRORED_REVERSE, F_EAGER, F_PAGEABLE_STAGED, F_GROUPS_SHIFT = 1, 2, 4, 8  # rlsim_stats.flags
 
 EXPORTS = [
     "rlsim_create", "rlsim_destroy", "rlsim_last_error", "rlsim_set_model", "rlsim_set_len_eff", "rlsim_set_raw_target",
     "rlsim_sample_target", "rlsim_sample_target_range", "rlsim_set_target_hist", "rlsim_add_transcripts", "rlsim_add_fasta", "rlsim_get_fasta_index", "rlsim_set_first_index", "rlsim_clear_transcripts",
     "rlsim_build_library", "rlsim_fragment", "rlsim_pcr", "rlsim_class_totals", "rlsim_sample", "rlsim_select_classes", "rlsim_apply_selected", "rlsim_finish_sample", "rlsim_get_stats",
-    "rlsim_get_hist", "rlsim_get_species", "rlsim_get_sampled", "rlsim_format_fasta", "rlsim_probe_kmer_lut",
+    "rlsim_get_hist", "rlsim_get_species", "rlsim_get_sampled", "rlsim_get_sampled_packed", "rlsim_format_fasta", "rlsim_probe_kmer_lut",
     "rlsim_probe_prefix", "rlsim_probe_gc_prefix", "rlsim_probe_math", "rlsim_probe_philox", "rlsim_probe_amplify",
-    "rlsim_get_timings",
+    "rlsim_get_timings", "rlsim_comm_unique_id", "rlsim_comm_init", "rlsim_comm_sum_target", "rlsim_sample_distributed",
+    "rlsim_exchange_plan",
 ]
 
 
@@ -84,6 +87,7 @@ def load():
         "rlsim_get_hist": (i32, [vp, i32, vp, u32]),
         "rlsim_get_species": (i32, [vp] + [vp] * 7),
         "rlsim_get_sampled": (i32, [vp] + [vp] * 5),
+        "rlsim_get_sampled_packed": (i32, [vp, vp, vp, vp, i32]),
         "rlsim_format_fasta": (i32, [vp, vp, vp, vp, u64, C.POINTER(u64)]),
         "rlsim_probe_kmer_lut": (i32, [vp, vp, vp, u32]),
         "rlsim_probe_prefix": (i32, [vp, u32, i32, vp, u32]),
@@ -92,12 +96,37 @@ def load():
         "rlsim_probe_philox": (i32, [vp, vp, vp, u32]),
         "rlsim_probe_amplify": (i32, [vp, i64, vp, vp, vp, i32, vp, u32]),
         "rlsim_get_timings": (i32, [vp, vp, vp]),
+        "rlsim_comm_unique_id": (i32, [vp]),
+        "rlsim_comm_init": (i32, [vp, vp, i32, i32]),
+        "rlsim_comm_sum_target": (i32, [vp]),
+        "rlsim_sample_distributed": (i32, [vp]),
+        "rlsim_exchange_plan": (i32, [vp, u32, u32, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
         f.restype, f.argtypes = res, args
     _lib = L
     return L
+
+
+def comm_unique_id():
+    """ncclUniqueId made by the library (rank 0 calls this; the host broadcasts the bytes to every rank)."""
+    buf = np.zeros(COMM_ID_BYTES, dtype=np.uint8)
+    rc = load().rlsim_comm_unique_id(buf.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise RlsimError(rc, "NCCL is not available (libnccl.so.2)")
+    return buf.tobytes()
+
+
+def exchange_plan(counts, rank):
+    """Host arithmetic of the record routing: counts[s, d] = records sender s holds for rank d -> (send_off, recv_off)."""
+    c = np.ascontiguousarray(counts, dtype=np.uint64)
+    n = c.shape[0]
+    so, ro = np.zeros(n + 1, np.uint64), np.zeros(n + 1, np.uint64)
+    rc = load().rlsim_exchange_plan(c.ctypes.data_as(C.c_void_p), n, int(rank), so.ctypes.data_as(C.c_void_p), ro.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise RlsimError(rc, "invalid exchange plan arguments")
+    return so, ro
 
 
 def _p(a):
@@ -166,6 +195,7 @@ class Handle:
 
     # ---- transcripts
     def set_first_index(self, i):
+        self.first = int(i)
         self._chk(self.L.rlsim_set_first_index(self.h, int(i)))
 
     def clear_transcripts(self):
@@ -239,6 +269,19 @@ class Handle:
     def finish_sample(self):
         self._chk(self.L.rlsim_finish_sample(self.h))
 
+    # ---- the exchange inside the library (NCCL communicator of the library's own)
+    def comm_init(self, id_bytes, nranks, rank):
+        buf = np.frombuffer(bytes(id_bytes), dtype=np.uint8).copy()
+        assert buf.size == COMM_ID_BYTES
+        self._chk(self.L.rlsim_comm_init(self.h, _p(buf), int(nranks), int(rank)))
+        self.comm_ready = True
+
+    def comm_sum_target(self):
+        self._chk(self.L.rlsim_comm_sum_target(self.h))
+
+    def sample_distributed(self):
+        self._chk(self.L.rlsim_sample_distributed(self.h))
+
     # ---- results
     def stats(self):
         s = Stats()
@@ -265,12 +308,51 @@ class Handle:
         self._chk(self.L.rlsim_get_species(self.h, *[_p(out[k]) for k in ("tr", "start", "end", "count0", "count", "eff", "gc")]))
         return out
 
-    def sampled(self, into=None):
+    def sampled_unpacked(self, into=None):
+        """rlsim_get_sampled: five arrays, 21 bytes per record."""
         n = int(self.stats().n_sampled)
         out = into or dict(tr=np.zeros(n, np.uint32), start=np.zeros(n, np.uint32), end=np.zeros(n, np.uint32),
                            minus=np.zeros(n, np.uint8), id=np.zeros(n, np.uint64))
         self._chk(self.L.rlsim_get_sampled(self.h, *[_addr(out[k]) for k in ("tr", "start", "end", "minus", "id")]))
         return out
+
+    def sampled_packed(self, into=None, elem_bytes=None):
+        """rlsim_get_sampled_packed: records per transcript + (start, length|strand) per record, 6 bytes per record.
+        into: dict(tr_counts, start, len_strand) of host arrays / pinned tensors.  -> (dict, elem_bytes)"""
+        st = self.stats()
+        n, ntr = int(st.n_sampled), int(st.n_transcripts)
+        if elem_bytes is None:
+            elem_bytes = 2 if int(st.high) < 32768 else 4
+        out = into or dict(tr_counts=np.zeros(ntr, np.uint32), start=np.zeros(n, np.uint32),
+                           len_strand=np.zeros(n, np.uint16 if elem_bytes == 2 else np.uint32))
+        self._chk(self.L.rlsim_get_sampled_packed(self.h, _addr(out["tr_counts"]), _addr(out["start"]), _addr(out["len_strand"]),
+                                                  int(elem_bytes)))
+        return out, elem_bytes
+
+    @staticmethod
+    def unpack_records(packed, elem_bytes, first=0, n=None):
+        """Packed records -> the five Frag arrays (frag.go:46-52): what a host does while it prints the records."""
+        cnt = np.asarray(packed["tr_counts"]).astype(np.int64)
+        n = int(cnt.sum()) if n is None else n
+        start = np.asarray(packed["start"])[:n].astype(np.uint32)
+        ls = np.asarray(packed["len_strand"])[:n]
+        bit = 8 * elem_bytes - 1
+        length = (ls & ((1 << bit) - 1)).astype(np.uint32)
+        tr = np.repeat(np.arange(len(cnt), dtype=np.int64) + first, cnt).astype(np.uint32)
+        base = np.cumsum(cnt) - cnt
+        ids = (np.arange(n, dtype=np.int64) - np.repeat(base, cnt)).astype(np.uint64)
+        return dict(tr=tr, start=start, end=start + length, minus=(ls >> bit).astype(np.uint8), id=ids)
+
+    def sampled(self, into=None):
+        """The sampled fragments (Frag records) in output order.  Travels over the host link in the packed form and is
+        expanded here; `into` (pre-allocated five-array buffers, e.g. pinned tensors) selects the unpacked copy."""
+        if into is not None:
+            return self.sampled_unpacked(into)
+        st = self.stats()
+        if int(st.n_sampled) >= 1 << 32:
+            return self.sampled_unpacked()
+        packed, eb = self.sampled_packed()
+        return self.unpack_records(packed, eb, getattr(self, "first", 0), int(st.n_sampled))
 
     def fasta(self, names):
         nb = np.frombuffer(b"".join(names), dtype=np.uint8) if names else np.zeros(0, np.uint8)

@@ -164,21 +164,32 @@ def decode_raw_params(fname: str) -> RawParams:  # parse_raw.go:51-126
     try:
         with open(fname) as f:
             d = json.load(f)
-    except OSError as e:
+    except (OSError, ValueError) as e:  # parse_raw.go:53-60: unreadable file or malformed JSON
         raise ArgError("Error when reading raw parameter file %s: %s" % (fname, e))
+    if not isinstance(d, dict):
+        raise ArgError("Error when reading raw parameter file %s: not a JSON object" % fname)
     for key in ("nr_frags", "nr_cycles", "frag_dist", "gc_eff"):
         if key not in d:
             raise ArgError("The %s key is missing from the raw parameter file!" % key)
     lengths, counts = [], []
     for k, v in d["frag_dist"].items():  # file order (the reference: Go map order)
-        lengths.append(int(k))
-        counts.append(float(v))
+        try:
+            lengths.append(int(k))
+            counts.append(float(v))
+        except (TypeError, ValueError) as e:  # parse_raw.go:93-96
+            raise ArgError("Failed to convert frag_dist key %s: %s" % (k, e))
     total = sum(counts)
     probs = [c / total for c in counts]
     gc = [0.0] * len(d["gc_eff"])
     for k, v in d["gc_eff"].items():
-        gc[int(k)] = float(v)
-    return RawParams(int(d["nr_frags"]), int(d["nr_cycles"]), lengths, probs, gc)
+        try:
+            gc[int(k)] = float(v)
+        except (TypeError, ValueError, IndexError) as e:  # parse_raw.go:118-121
+            raise ArgError("Failed to convert gc_eff key %s: %s" % (k, e))
+    try:
+        return RawParams(int(d["nr_frags"]), int(d["nr_cycles"]), lengths, probs, gc)
+    except (TypeError, ValueError) as e:
+        raise ArgError("Error when reading raw parameter file %s: %s" % (fname, e))
 
 
 _FLAGS = {  # name -> (attribute, kind, default); args.go:98-125

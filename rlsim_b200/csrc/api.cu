@@ -4,101 +4,9 @@
 // Library plumbing used here: cub::DeviceRadixSort / DeviceRunLengthEncode / DeviceScan for the species
 // dedup (transcript.go:156-215), the per-length class view (pool.go:156-189) and the selection sort.
 #include <cub/cub.cuh>
-#include <algorithm>
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <chrono>
-#include <new>
-#include <vector>
-#include "kernels.cuh"
-
-using namespace rl;
+#include "handle.cuh"
 
 namespace {
-
-// Host array in pinned memory with the few std::vector operations the bookkeeping needs: copies from it to the device
-// are real asynchronous DMA (a pageable source would be staged by the driver, with the host waiting for the staging).
-template <typename T>
-struct PinVec {
-    T *p = nullptr;
-    size_t n = 0, cap = 0;
-    PinVec() = default;
-    PinVec(const PinVec &) = delete;
-    PinVec &operator=(const PinVec &) = delete;
-    ~PinVec() { if (p) cudaFreeHost(p); }
-    size_t size() const { return n; }
-    bool empty() const { return n == 0; }
-    T *data() { return p; }
-    const T *data() const { return p; }
-    T &operator[](size_t i) { return p[i]; }
-    const T &operator[](size_t i) const { return p[i]; }
-    T *begin() { return p; }
-    T *end() { return p + n; }
-    const T *begin() const { return p; }
-    const T *end() const { return p + n; }
-    void clear() { n = 0; }
-    void reserve(size_t want) {
-        if (want <= cap) return;
-        size_t c = std::max<size_t>(want + want / 2, 1024);
-        T *q = nullptr;
-        if (cudaHostAlloc((void **)&q, c * sizeof(T), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); throw std::bad_alloc(); }
-        if (n) memcpy(q, p, n * sizeof(T));
-        if (p) cudaFreeHost(p);
-        p = q; cap = c;
-    }
-    void resize(size_t want) { reserve(want); if (want > n) memset(p + n, 0, (want - n) * sizeof(T)); n = want; }
-    void push_back(const T &v) { reserve(n + 1); p[n++] = v; }
-};
-
-template <typename T>
-struct DBuf {
-    T *p = nullptr;
-    size_t n = 0;
-    ~DBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-    cudaError_t ensure(size_t want) {  // contents are NOT preserved; grows with 1/8 slack so sizes that
-        if (p && want <= n) return cudaSuccess;  // fluctuate from run to run do not reallocate every time
-        release();
-        size_t cap = want + want / 8 + 16;
-        cudaError_t e = cudaMalloc(&p, cap * sizeof(T));
-        if (e != cudaSuccess) { cap = std::max<size_t>(want, 1); e = cudaMalloc(&p, cap * sizeof(T)); }
-        if (e == cudaSuccess) n = cap;
-        return e;
-    }
-    // grow to at least `want` elements keeping the first `used` (device-to-device copy on `st`)
-    cudaError_t grow_preserve(size_t want, size_t used, cudaStream_t st) {
-        if (p && want <= n) return cudaSuccess;
-        size_t cap = want + want / 2 + 16;
-        T *q = nullptr;
-        cudaError_t e = cudaMalloc(&q, cap * sizeof(T));
-        if (e != cudaSuccess) { cap = want; e = cudaMalloc(&q, cap * sizeof(T)); }
-        if (e != cudaSuccess) return e;
-        if (p && used) {
-            e = cudaMemcpyAsync(q, p, std::min(used, n) * sizeof(T), cudaMemcpyDeviceToDevice, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        }
-        if (p) cudaFree(p);
-        p = q; n = cap;
-        return e;
-    }
-};
-
-struct Staging {  // reusable device staging of the batch being ingested (kept across rlsim_clear_transcripts)
-    DBuf<uint8_t> bases;
-    DBuf<uint64_t> off;
-};
-
-uint32_t bits_for(uint64_t v) {
-    uint32_t b = 1;
-    while (b < 64 && (v >> b)) b++;
-    return b;
-}
-
-// kernels launched by one cub::DeviceRadixSort call over `bits` key bits (histogram + exclusive sum + onesweep passes)
-uint64_t radix_launches(int bits) { return 2 + (uint64_t)((bits + 7) / 8); }
 
 __global__ void k_iota(uint32_t *p, uint64_t n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -111,153 +19,23 @@ __global__ void k_class_totals(const uint64_t *cls_pre, const uint64_t *bounds, 
 
 }  // namespace
 
-struct PendingTime { int stage; cudaEvent_t a, b; };  // a stage timer whose events have not been resolved yet
-struct rlsim_handle {
-    int device = 0;
-    cudaStream_t st = nullptr;
-    std::string err;
-    rlsim_params p{};
-    bool have_model = false;
-    // target
-    std::vector<uint32_t> raw_len;
-    std::vector<double> raw_prob;
-    std::vector<uint64_t> h_target;  // histogram by length
-    bool have_target = false;
-    uint64_t req_frags = 0;
-    uint64_t low = 0, high = 0;
-    double raw_location = 0.0;
-    uint32_t polya_max = 0;
-    std::vector<double> h_len_eff;  // host-supplied table
-    uint64_t len_eff_low = 0, len_eff_high = 0;
-    // transcripts
-    uint32_t first_index = 0;
-    Staging staging;
-    cudaStream_t st_copy = nullptr;  // H2D of the next chunk overlaps ingest/prefix of the previous one
-    cudaStream_t st_pcr = nullptr;   // eager pipeline: PCR of group g (FP64 issue bound) overlaps the memory-bound stages of group g+1
-    cudaEvent_t ev_sp = nullptr, ev_pcr = nullptr, ev_ingest = nullptr, ev_aux = nullptr;
-    cudaStream_t st_aux = nullptr;   // target-length sampling runs beside the transcript pipeline
-    bool target_pending = false;     // the sampled histogram is still on the device (target_host)
-    uint32_t target_hist_n = 0;
-    bool pcr_in_flight = false;
-    unsigned long long *pin = nullptr;  // pinned scratch for the small device-to-host count reads
-    std::vector<cudaEvent_t> ev_chunk, ev_free;
-    std::vector<PendingTime> pending_times;  // stage timers not yet resolved (drain_timers)
-    std::vector<uint64_t> h_srclen;  // unpadded lengths as added
-    PinVec<uint64_t> h_expr, h_rel;   // pinned: sources of the per-batch metadata copies
-    PinVec<uint64_t> h_off;          // padded offsets [n+1]
-    PinVec<uint32_t> h_len;          // with polyA
-    uint64_t n_mol = 0, total_padded = 0;
-    double sum_expr = 0, sum_expr_len = 0;  // for the fragment-capacity estimate
-    bool mol_off_valid = false;
-    PinVec<uint64_t> h_mol_off;             // exclusive scan of the expression levels [n+1]
-    // eager pipeline: while later chunks are still being copied, earlier chunks are already fragmented and amplified
-    uint32_t eager_upto = 0;                // transcripts [0, eager_upto) are done under the current model
-    bool eager_failed = false;              // a buffer estimate was too small: the monolithic path takes over
-    bool eager_started = false;             // counters / histograms zeroed for this transcript set
-    bool eager_pcr = false;                 // species counts already amplified (consumed by the next rlsim_pcr)
-    bool eager_used = false;                // the current species table came from the eager pipeline (rlsim_stats.flags)
-    uint32_t eager_groups = 0;              // groups started since the last reset (test hook)
-    uint64_t eager_keys = 0, eager_sp = 0;  // running fragment-key / species counts
-    bool len_eff_ready = false;
-    DBuf<uint8_t> d_bases;
-    DBuf<uint32_t> d_packed, d_nmask, d_len;
-    DBuf<uint2> d_gc;  // GC groups: {prefix count, bit mask} per 32 bases
-    // device FASTA reader (rlsim_add_fasta)
-    DBuf<uint8_t> d_fa_text, d_fa_tiles, d_fa_seq, d_fa_seq2, d_fa_valid;
-    DBuf<uint4> d_fa_carry;
-    DBuf<unsigned long long> d_fa_tot;
-    DBuf<uint64_t> d_fa_rec_start, d_fa_hdr_end, d_fa_seq_off, d_fa_level, d_fa_seq_len;
-    DBuf<uint32_t> d_fa_hdr_len, d_fa_name_len;
-    std::vector<uint64_t> fa_start, fa_level, fa_seq_len;
-    std::vector<uint32_t> fa_hdr_len, fa_name_len;
-    std::vector<uint8_t> fa_valid;
-    uint32_t fa_n = 0;
-    DBuf<uint64_t> d_off, d_expr, d_mol_off, d_Cf, d_Cr;  // coarse prefix sums
-    DBuf<uint32_t> d_Ff, d_Fr;                          // fine (in-block) prefix sums
-    uint32_t prefix_upto = 0;  // transcripts [0, prefix_upto) have valid priming prefix sums for the current model
-    bool lut_valid = false;
-    int lut_k = 0; double lut_T = 0; bool lut_sym = false, want_mirror = true;  // cached k-mer table; reverse-complement symmetric after quantisation
-    DBuf<uint32_t> d_dirty;  // per transcript: letters outside ACGT present
-    // model tables
-    DBuf<double> d_gc_raw, d_len_eff, d_raw_prob, d_K;
-    DBuf<uint32_t> d_raw_len, d_wq_f, d_wq_r;
-    DBuf<unsigned long long> d_kmax;
-    // fragmentation
-    DBuf<uint64_t> d_keys, d_keys_sorted, d_uniq;
-    DBuf<unsigned long long> d_counters;  // [0] fragment count, [1] run count
-    DBuf<unsigned long long> d_hist_frag, d_hist_polya, d_hist_target;
-    DBuf<uint2> d_long_list, d_q_b;
-    DBuf<uint4> d_q_a;
-    DBuf<uint32_t> d_long_hi;
-    DBuf<unsigned int> d_long_count, d_work;
-    DBuf<int> d_error;
-    DBuf<unsigned char> d_cub;
-    uint64_t n_frag = 0;
-    bool fragmented = false, amplified = false, sampled = false;
-    std::vector<uint64_t> h_hist_frag, h_hist_polya;
-    // species
-    uint64_t n_sp = 0;
-    DBuf<uint32_t> d_sp_tr, d_sp_start, d_sp_len, d_sp_count0, d_sp_gc;
-    DBuf<uint64_t> d_sp_count;
-    DBuf<double> d_sp_eff;
-    bool keep_debug = true;  // keep per-species eff / gc for rlsim_get_species
-    // classes
-    DBuf<uint32_t> d_iota, d_sorted_len, d_order;
-    DBuf<uint64_t> d_cls_cnt, d_cls_pre, d_bounds, d_totals;
-    uint32_t n_len = 0;
-    std::vector<uint64_t> h_totals;  // local per-length totals
-    uint64_t pool_total = 0;
-    // selection
-    std::vector<uint64_t> h_sampled, h_missing, h_after_sampling, h_after_pcr;
-    DBuf<uint64_t> d_cand_keys, d_cand_keys_sorted, d_fscan, d_taken, d_out_off, d_plan_u64;
-    DBuf<uint32_t> d_cand_idx, d_cand_idx_sorted, d_flags, d_plan_len;
-    DBuf<unsigned long long> d_hits;
-    DBuf<uint8_t> d_mode;
-    DBuf<unsigned long long> d_emit;  // [0..64) counts, [64..128) segment offsets, [128..192) cursors
-    DBuf<uint64_t> d_all_base, d_my_base;
-    DBuf<int> d_short;
-    uint64_t n_out = 0;
-    DBuf<uint32_t> d_o_tr, d_o_start, d_o_end;
-    DBuf<uint8_t> d_o_minus;
-    DBuf<uint64_t> d_o_id, d_tr_out_base;
-    DBuf<uint32_t> d_cand_k32, d_cand_k32_sorted;  // narrow sort keys of the selection candidates
-    // fasta
-    DBuf<uint8_t> d_names, d_fasta;
-    DBuf<uint64_t> d_name_off, d_rec_sizes, d_rec_off;
-    // timings
-    float ms[RLSIM_T_COUNT] = {0};
-    uint64_t launches[RLSIM_T_COUNT] = {0};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-};
-
 static std::string g_create_error;
 
-#define FAIL(h, code, msg) do { (h)->err = (msg); return (code); } while (0)
-#define CK(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__); return RLSIM_E_CUDA; } } while (0)
+namespace rl_api {
 
-namespace {
-
-// Stage timing never blocks the host: event pairs are parked and resolved when the timings are read.
-void drain_timers(rlsim_handle *h);
-struct StageTimer {
-    rlsim_handle *h;
-    int stage;
-    cudaStream_t st;
-    cudaEvent_t a = nullptr, b = nullptr;
-    StageTimer(rlsim_handle *h_, int s, uint64_t nl, cudaStream_t stream = nullptr) : h(h_), stage(s), st(stream ? stream : h_->st) {
-        for (cudaEvent_t *e : {&a, &b}) {
-            if (!h->ev_free.empty()) { *e = h->ev_free.back(); h->ev_free.pop_back(); }
-            else cudaEventCreate(e);
-        }
-        cudaEventRecord(a, st);
-        h->launches[s] += nl;
+StageTimer::StageTimer(rlsim_handle *h_, int s, uint64_t nl, cudaStream_t stream) : h(h_), stage(s), st(stream ? stream : h_->st) {
+    for (cudaEvent_t *e : {&a, &b}) {
+        if (!h->ev_free.empty()) { *e = h->ev_free.back(); h->ev_free.pop_back(); }
+        else cudaEventCreate(e);
     }
-    void stop() {
-        cudaEventRecord(b, st);
-        h->pending_times.push_back(PendingTime{stage, a, b});
-        if (h->pending_times.size() > 512) drain_timers(h);
-    }
-};
+    cudaEventRecord(a, st);
+    h->launches[s] += nl;
+}
+void StageTimer::stop() {
+    cudaEventRecord(b, st);
+    h->pending_times.push_back(PendingTime{stage, a, b});
+    if (h->pending_times.size() > 512) drain_timers(h);
+}
 void drain_timers(rlsim_handle *h) {
     for (auto &p : h->pending_times) {
         float t = 0;
@@ -383,9 +161,44 @@ int launch_prefix_range(rlsim_handle *h, uint32_t t0, uint32_t t1) {
     return 0;
 }
 
+// Device -> caller's host buffer on h->st.  Pinned destinations are written by the copy engine directly (asynchronous:
+// the caller synchronises); pageable ones are staged through the pinned ring and drained by the copy team while the next
+// slot is on the wire (complete on return).
+int d2h_any(rlsim_handle *h, void *dst_, const void *src_, size_t bytes) {
+    if (!bytes || !dst_) return 0;
+    uint8_t *dst = (uint8_t *)dst_;
+    const uint8_t *src = (const uint8_t *)src_;
+    if (bytes < (1u << 20) || getenv("RLSIM_NO_STAGING") || host_pinned(dst)) {
+        CK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->st));
+        return 0;
+    }
+    constexpr size_t SLOT = 8u << 20;
+    constexpr uint32_t RING = 3;
+    if (h->stage_ring_bytes < RING * SLOT) {
+        if (h->stage_ring) cudaFreeHost(h->stage_ring);
+        h->stage_ring = nullptr; h->stage_ring_bytes = 0;
+        CK(h, cudaHostAlloc((void **)&h->stage_ring, RING * SLOT, cudaHostAllocDefault));
+        h->stage_ring_bytes = RING * SLOT;
+    }
+    while (h->ev_slot.size() < RING) { cudaEvent_t e; CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_slot.push_back(e); }
+    if (!h->team) h->team = new CopyTeam(stage_threads());
+    const size_t nch = (bytes + SLOT - 1) / SLOT;
+    auto issue = [&](size_t c) -> cudaError_t {
+        const size_t a = c * SLOT, len = std::min(SLOT, bytes - a);
+        cudaError_t e = cudaMemcpyAsync(h->stage_ring + (c % RING) * SLOT, src + a, len, cudaMemcpyDeviceToHost, h->st);
+        return e != cudaSuccess ? e : cudaEventRecord(h->ev_slot[c % RING], h->st);
+    };
+    for (size_t c = 0; c < std::min<size_t>(nch, RING - 1); c++) CK(h, issue(c));
+    for (size_t c = 0; c < nch; c++) {
+        if (c + RING - 1 < nch) CK(h, issue(c + RING - 1));  // its slot was drained in the previous iteration
+        CK(h, cudaEventSynchronize(h->ev_slot[c % RING]));
+        const size_t a = c * SLOT, len = std::min(SLOT, bytes - a);
+        h->team->copy(dst + a, h->stage_ring + (c % RING) * SLOT, len);
+    }
+    return 0;
+}
+
 #define D2H(dst, src, bytes) do { if (dst) CK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->st)); } while (0)
-int cub_temp(rlsim_handle *h, size_t bytes);
-int check_device_error(rlsim_handle *h);
 
 void eager_reset(rlsim_handle *h) {
     h->eager_upto = 0; h->eager_failed = h->eager_started = h->eager_pcr = false; h->eager_keys = h->eager_sp = 0;
@@ -577,7 +390,8 @@ int upload_tables(rlsim_handle *h) {
 
 int cub_temp(rlsim_handle *h, size_t bytes) { CK(h, h->d_cub.ensure(bytes + 16)); return 0; }
 
-}  // namespace
+}  // namespace rl_api
+using namespace rl_api;
 
 extern "C" {
 
@@ -612,6 +426,7 @@ void rlsim_destroy(rlsim_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     drain_timers(h);
+    comm_destroy(h);
     for (auto e : h->ev_chunk) cudaEventDestroy(e);
     for (auto e : h->ev_free) cudaEventDestroy(e);
     if (h->st_copy) cudaStreamDestroy(h->st_copy);
@@ -622,6 +437,9 @@ void rlsim_destroy(rlsim_handle *h) {
     if (h->ev_pcr) cudaEventDestroy(h->ev_pcr);
     if (h->ev_ingest) cudaEventDestroy(h->ev_ingest);
     if (h->pin) cudaFreeHost(h->pin);
+    delete h->team;
+    if (h->stage_ring) cudaFreeHost(h->stage_ring);
+    for (auto e : h->ev_slot) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->st) cudaStreamDestroy(h->st);
@@ -678,8 +496,9 @@ int rlsim_set_raw_target(rlsim_handle *h, const uint32_t *lengths, const double 
     return upload_tables(h);
 }
 
+}  // extern "C"
 // bring the sampled target histogram to the host (no-op when it is already there)
-static int target_host(rlsim_handle *h) {
+int rl_api::target_host(rlsim_handle *h) {
     if (!h->target_pending) return 0;
     h->target_pending = false;
     h->h_target.assign(h->target_hist_n, 0);
@@ -688,6 +507,7 @@ static int target_host(rlsim_handle *h) {
     return 0;
 }
 
+extern "C" {
 static int sample_target_range(rlsim_handle *h, uint64_t first, uint64_t count, bool whole) {
     if (!h->have_model) FAIL(h, RLSIM_E_ARG, "rlsim_set_model first");
     bool raw = h->p.n_target == 0;
@@ -734,13 +554,22 @@ int rlsim_set_target_hist(rlsim_handle *h, const uint32_t *lengths, const uint64
     for (uint32_t i = 0; i < n; i++) mx = std::max(mx, lengths[i]);
     if (mx >= (1u << 24)) FAIL(h, RLSIM_E_UNSUPPORTED, "maximum fragment length >= 2^24");
     if (h->target_pending) { cudaSetDevice(h->device); CK(h, cudaStreamSynchronize(h->st_aux)); h->target_pending = false; }
-    h->h_target.assign((size_t)mx + 1, 0);
-    h->req_frags = 0;
-    for (uint32_t i = 0; i < n; i++) { h->h_target[lengths[i]] += counts[i]; h->req_frags += counts[i]; }
-    h->have_target = true;
-    if (h->p.n_target == 0) { raw_target_finish(h); h->len_eff_ready = false; if (h->eager_upto) { h->eager_upto = 0; h->eager_failed = true; } }
+    std::vector<uint64_t> hist((size_t)mx + 1, 0);
+    for (uint32_t i = 0; i < n; i++) hist[lengths[i]] += counts[i];
+    set_target_from_hist(h, hist.data(), mx + 1);
     return 0;
 }
+}  // extern "C"
+// impose a complete target histogram indexed by length (the host's own Targeter, or the sum of the ranks' partial draws)
+void rl_api::set_target_from_hist(rlsim_handle *h, const uint64_t *hist, uint32_t n) {
+    h->target_pending = false;
+    h->h_target.assign(hist, hist + n);
+    h->req_frags = 0;
+    for (uint32_t i = 0; i < n; i++) h->req_frags += hist[i];
+    h->have_target = true;
+    if (h->p.n_target == 0) { raw_target_finish(h); h->len_eff_ready = false; if (h->eager_upto) { h->eager_upto = 0; h->eager_failed = true; } }
+}
+extern "C" {
 
 int rlsim_set_first_index(rlsim_handle *h, uint32_t first_index) {
     if (first_index != h->first_index && h->eager_upto) { h->eager_upto = 0; h->eager_failed = true; }  // streams are keyed by it
@@ -856,12 +685,55 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     }
     const uint32_t n_chunks = (uint32_t)cuts.size() - 1;
     while (h->ev_chunk.size() < n_chunks) { cudaEvent_t e; CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_chunk.push_back(e); }
-    for (uint32_t c = 0; c < n_chunks; c++) {  // all copies are queued first: the copy engine never waits for the host
-        const uint32_t t0 = cuts[c], t1 = cuts[c + 1];
-        if (rel[t1] > rel[t0] && !dev_bases)
-            CK(h, cudaMemcpyAsync(h->staging.bases.p + rel[t0], bases + offsets[0] + rel[t0], rel[t1] - rel[t0], cudaMemcpyHostToDevice, h->st_copy));
-        CK(h, cudaEventRecord(h->ev_chunk[c], h->st_copy));
+    // A pageable caller buffer (Go slice, numpy array) cannot be read by the copy engine: its chunks are staged through a
+    // ring of pinned slots by a feeder thread + copy team while the previous slot is on the wire.  Pinned buffers are
+    // copied directly.  `issued` = chunks whose copy and event have been queued (the main thread waits for it before it
+    // touches a chunk's event).
+    const bool stage = !dev_bases && nbytes > 0 && !getenv("RLSIM_NO_STAGING") && !host_pinned(bases + offsets[0]);
+    h->staged_pageable = stage;
+    std::atomic<uint32_t> issued{0};
+    std::atomic<int> feeder_err{0};
+    std::thread feeder;
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{feeder};
+    if (!stage) {
+        for (uint32_t c = 0; c < n_chunks; c++) {  // all copies are queued first: the copy engine never waits for the host
+            const uint32_t t0 = cuts[c], t1 = cuts[c + 1];
+            if (rel[t1] > rel[t0] && !dev_bases)
+                CK(h, cudaMemcpyAsync(h->staging.bases.p + rel[t0], bases + offsets[0] + rel[t0], rel[t1] - rel[t0], cudaMemcpyHostToDevice, h->st_copy));
+            CK(h, cudaEventRecord(h->ev_chunk[c], h->st_copy));
+        }
+        issued.store(n_chunks);
+    } else {
+        constexpr uint32_t RING = 3;
+        size_t slot = 0;
+        for (uint32_t c = 0; c < n_chunks; c++) slot = std::max<size_t>(slot, rel[cuts[c + 1]] - rel[cuts[c]]);
+        slot = (slot + 4095) & ~(size_t)4095;
+        if (h->stage_ring_bytes < RING * slot) {
+            if (h->stage_ring) cudaFreeHost(h->stage_ring);
+            h->stage_ring = nullptr; h->stage_ring_bytes = 0;
+            CK(h, cudaHostAlloc((void **)&h->stage_ring, RING * slot, cudaHostAllocDefault));
+            h->stage_ring_bytes = RING * slot;
+        }
+        if (!h->team) h->team = new CopyTeam(stage_threads());
+        const uint8_t *src_host = bases + offsets[0];
+        feeder = std::thread([&, slot, src_host] {
+            cudaSetDevice(h->device);
+            for (uint32_t c = 0; c < n_chunks; c++) {
+                cudaError_t e = cudaSuccess;
+                if (c >= RING) e = cudaEventSynchronize(h->ev_chunk[c - RING]);  // the slot's previous copy has left it
+                const uint64_t a = rel[cuts[c]], b = rel[cuts[c + 1]];
+                uint8_t *sl = h->stage_ring + (size_t)(c % RING) * slot;
+                if (e == cudaSuccess && b > a) {
+                    h->team->copy(sl, src_host + a, b - a);
+                    e = cudaMemcpyAsync(h->staging.bases.p + a, sl, b - a, cudaMemcpyHostToDevice, h->st_copy);
+                }
+                if (e == cudaSuccess) e = cudaEventRecord(h->ev_chunk[c], h->st_copy);
+                if (e != cudaSuccess) { feeder_err.store((int)e); issued.store(n_chunks, std::memory_order_release); return; }
+                issued.store(c + 1, std::memory_order_release);
+            }
+        });
     }
+    auto wait_issued = [&](uint32_t c) { while (issued.load(std::memory_order_acquire) <= c) std::this_thread::yield(); };
     // Eager groups are self-sizing: once a group is done, every chunk that has arrived meanwhile forms the next one, so
     // the per-group fixed cost (host round trips for counts, small sorts) never makes compute fall behind the copies.
     // The grouping does not influence the result (streams are addressed by global molecule / species identity).
@@ -871,9 +743,11 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     const double t_begin = now_ms();
     for (uint32_t c = 0; c < n_chunks;) {
         uint32_t c_end = c + 1;
+        wait_issued(c);
+        if (feeder_err.load()) break;
         if (eager) {
             CK(h, cudaEventSynchronize(h->ev_chunk[c]));
-            while (c_end < n_chunks && cudaEventQuery(h->ev_chunk[c_end]) == cudaSuccess) c_end++;
+            while (c_end < n_chunks && issued.load(std::memory_order_acquire) > c_end && cudaEventQuery(h->ev_chunk[c_end]) == cudaSuccess) c_end++;
             (void)cudaGetLastError();  // cudaErrorNotReady from the query is not an error
         }
         for (uint32_t cc = c; cc < c_end; cc++) {
@@ -894,6 +768,8 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
         }
         c = c_end;
     }
+    if (feeder.joinable()) feeder.join();
+    if (feeder_err.load()) { h->err = std::string("staged host-to-device copy: ") + cudaGetErrorString((cudaError_t)feeder_err.load()); return RLSIM_E_CUDA; }
     if (h->pcr_in_flight) { CK(h, cudaStreamWaitEvent(h->st, h->ev_pcr, 0)); h->pcr_in_flight = false; }
     CK(h, cudaStreamSynchronize(h->st_copy));  // caller-owned buffers are only read during the call
     if (trace) fprintf(stderr, "[rlsim trace] copies done %.3f ms\n", now_ms() - t_begin);
@@ -1219,14 +1095,14 @@ int rlsim_class_totals(rlsim_handle *h, uint64_t *totals, uint32_t n_len) {
 
 }  // extern "C" (selection helpers follow)
 
-namespace {
+namespace rl_api {
 
 // Size selection core (sampler.go:65-106 + spec 4.6) for the length classes l with l % nparts == part.
 //   records == nullptr : single-rank form - drawn ranks are applied to this rank's species directly (rank_base form)
 //   records != nullptr : drawn / excluded ranks are written as records grouped by owner rank (multi-GPU form)
 int select_core(rlsim_handle *h, const std::vector<uint64_t> &T, const std::vector<uint64_t> &base, uint32_t nparts,
                 uint32_t part, const uint64_t *d_all_base, uint4 *records, uint64_t cap, uint64_t *counts_out,
-                uint64_t *needed_out) {
+                uint64_t *needed_out, bool sync_records) {
     int rc;
     if ((rc = target_host(h))) return rc;
     uint32_t n_len = h->n_len;
@@ -1343,6 +1219,9 @@ int select_core(rlsim_handle *h, const std::vector<uint64_t> &T, const std::vect
                                  h->d_emit.p, h->d_emit.p + 64, h->d_emit.p + 128, records, h->d_short.p);
             tm2.stop();
             CK(h, cudaGetLastError());
+            // h->st is a non-blocking stream: the caller's collective runs on another one, so the records must be
+            // complete in memory when this call returns (include/rlsim_gpu.h documents that)
+            if (sync_records) CK(h, cudaStreamSynchronize(h->st));
         }
         break;
     }
@@ -1354,7 +1233,7 @@ int finish_sample(rlsim_handle *h) {
     int rc;
     uint64_t ns = h->n_sp;
     DevModel m = make_model(h);
-    StageTimer tm(h, RLSIM_T_EXPAND, 5);
+    StageTimer tm(h, RLSIM_T_EXPAND, 6);
     launch_taken(h->st, make_sp(h), h->d_mode.p, h->n_len, h->d_hits.p, h->d_taken.p);
     CK(h, cudaMemsetAsync(h->d_out_off.p, 0, 8, h->st));
     h->n_out = 0;
@@ -1370,6 +1249,13 @@ int finish_sample(rlsim_handle *h) {
     CK(h, h->d_o_minus.ensure(h->n_out)); CK(h, h->d_o_id.ensure(h->n_out));
     DevSampled out{h->d_o_tr.p, h->d_o_start.p, h->d_o_end.p, h->d_o_minus.p, h->d_o_id.p};
     CK(h, h->d_tr_out_base.ensure(h->h_len.size() + 1));
+    if (h->n_out < (1ull << 32)) {  // packed host format (rlsim_get_sampled_packed)
+        if (h->high < 32768) { CK(h, h->d_o_ls16.ensure(h->n_out)); out.ls16 = h->d_o_ls16.p; }
+        else { CK(h, h->d_o_ls32.ensure(h->n_out)); out.ls32 = h->d_o_ls32.p; }
+        CK(h, h->d_o_trcnt.ensure(h->h_len.size() + 1));
+        CK(h, cudaMemsetAsync(h->d_o_trcnt.p, 0, (h->h_len.size() + 1) * 4, h->st));
+        out.tr_counts = h->d_o_trcnt.p;
+    }
     launch_expand(h->st, m, make_sp(h), h->d_out_off.p, h->d_tr_out_base.p, h->n_out, out);
     tm.stop();
     CK(h, cudaGetLastError());
@@ -1378,7 +1264,7 @@ int finish_sample(rlsim_handle *h) {
     return 0;
 }
 
-}  // namespace
+}  // namespace rl_api
 
 extern "C" {
 
@@ -1399,6 +1285,11 @@ int rlsim_sample(rlsim_handle *h, const uint64_t *global_totals, const uint64_t 
 
 int rlsim_select_classes(rlsim_handle *h, const uint64_t *all_totals, uint32_t nparts, uint32_t part, uint32_t n_len_in,
                          void *records_dev, uint64_t cap, uint64_t *counts_out, uint64_t *needed_out) {
+    return select_partitioned(h, all_totals, nparts, part, n_len_in, records_dev, cap, counts_out, needed_out, true);
+}
+}  // extern "C"
+int rl_api::select_partitioned(rlsim_handle *h, const uint64_t *all_totals, uint32_t nparts, uint32_t part, uint32_t n_len_in,
+                               void *records_dev, uint64_t cap, uint64_t *counts_out, uint64_t *needed_out, bool sync_records) {
     if (!h->amplified) FAIL(h, RLSIM_E_ARG, "rlsim_pcr first");
     if (!h->have_target) FAIL(h, RLSIM_E_ARG, "no target histogram");
     if (nparts < 1 || nparts > 64 || part >= nparts) FAIL(h, RLSIM_E_ARG, "invalid rank partition");
@@ -1425,12 +1316,17 @@ int rlsim_select_classes(rlsim_handle *h, const uint64_t *all_totals, uint32_t n
     CK(h, cudaMemsetAsync(h->d_error.p, 0, 4, h->st));
     static uint4 dummy_sentinel;
     uint4 *rec = records_dev ? (uint4 *)records_dev : &dummy_sentinel;  // non-null => record form; cap 0 => sizes only
-    return select_core(h, T, mine, nparts, part, h->d_all_base.p, rec, records_dev ? cap : 0, counts_out, needed_out);
+    return select_core(h, T, mine, nparts, part, h->d_all_base.p, rec, records_dev ? cap : 0, counts_out, needed_out, sync_records);
 }
+extern "C" {
 
 int rlsim_apply_selected(rlsim_handle *h, const void *records_dev, uint64_t n) {
     if (!h->amplified) FAIL(h, RLSIM_E_ARG, "rlsim_pcr first");
     cudaSetDevice(h->device);
+    return apply_records(h, records_dev, n);
+}
+}  // extern "C"
+int rl_api::apply_records(rlsim_handle *h, const void *records_dev, uint64_t n) {
     StageTimer tm(h, RLSIM_T_SELECT, 1);
     launch_apply_records(h->st, (const uint4 *)records_dev, n, h->d_my_base.p, h->d_cls_pre.p, h->d_bounds.p, h->d_order.p,
                          h->d_hits.p, h->d_error.p);
@@ -1442,6 +1338,7 @@ int rlsim_apply_selected(rlsim_handle *h, const void *records_dev, uint64_t n) {
     if (e) FAIL(h, RLSIM_E_ARG, "a selection record was routed to a rank that does not own the copy");
     return 0;
 }
+extern "C" {
 
 int rlsim_finish_sample(rlsim_handle *h) {
     if (!h->amplified) FAIL(h, RLSIM_E_ARG, "rlsim_pcr first");
@@ -1462,7 +1359,8 @@ int rlsim_get_stats(rlsim_handle *h, rlsim_stats *out) {
     out->n_sampled = h->sampled ? h->n_out : 0;
     out->low = h->low; out->high = h->high; out->polya_max = h->polya_max;
     out->flags = (needs_rev(h->p.frag_method) && h->lut_valid && h->lut_sym && h->want_mirror ? RLSIM_F_MIRRORED_REVERSE : 0) |
-                 (h->eager_used ? RLSIM_F_EAGER : 0);
+                 (h->eager_used ? RLSIM_F_EAGER : 0) | (h->staged_pageable ? RLSIM_F_PAGEABLE_STAGED : 0) |
+                 (std::min<uint32_t>(h->eager_groups, 255u) << RLSIM_F_GROUPS_SHIFT);
     return 0;
 }
 
@@ -1477,6 +1375,7 @@ int rlsim_get_hist(rlsim_handle *h, int kind, uint64_t *out, uint32_t n) {
     case RLSIM_H_SAMPLED: src = &h->h_sampled; break;
     case RLSIM_H_MISSING: src = &h->h_missing; break;
     case RLSIM_H_AFTER_SAMPLING: src = &h->h_after_sampling; break;
+    case RLSIM_H_POOL_GLOBAL: src = &h->h_global_totals; break;
     default: FAIL(h, RLSIM_E_ARG, "unknown histogram kind");
     }
     for (uint32_t i = 0; i < n; i++) out[i] = i < src->size() ? (*src)[i] : 0;
@@ -1508,8 +1407,40 @@ int rlsim_get_sampled(rlsim_handle *h, uint32_t *tr, uint32_t *start, uint32_t *
     cudaSetDevice(h->device);
     uint64_t n = h->n_out;
     if (!n) return 0;
-    D2H(tr, h->d_o_tr.p, n * 4); D2H(start, h->d_o_start.p, n * 4); D2H(end, h->d_o_end.p, n * 4);
-    D2H(minus_strand, h->d_o_minus.p, n); D2H(id, h->d_o_id.p, n * 8);
+    int rc;
+    if ((rc = d2h_any(h, tr, h->d_o_tr.p, n * 4)) || (rc = d2h_any(h, start, h->d_o_start.p, n * 4)) ||
+        (rc = d2h_any(h, end, h->d_o_end.p, n * 4)) || (rc = d2h_any(h, minus_strand, h->d_o_minus.p, n)) ||
+        (rc = d2h_any(h, id, h->d_o_id.p, n * 8)))
+        return rc;
+    CK(h, cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int rlsim_get_sampled_packed(rlsim_handle *h, uint32_t *tr_counts, uint32_t *start, void *len_strand, int elem_bytes) {
+    if (!h->sampled) FAIL(h, RLSIM_E_ARG, "rlsim_sample first");
+    if (elem_bytes != 2 && elem_bytes != 4) FAIL(h, RLSIM_E_ARG, "len_strand elements are 2 or 4 bytes wide");
+    if (h->n_out >= (1ull << 32)) FAIL(h, RLSIM_E_UNSUPPORTED, "more than 2^32-1 records: use rlsim_get_sampled");
+    const bool have16 = h->high < 32768;
+    if (elem_bytes == 2 && !have16) FAIL(h, RLSIM_E_ARG, "fragment lengths need 4-byte len_strand elements (high >= 32768)");
+    cudaSetDevice(h->device);
+    const uint64_t n = h->n_out;
+    int rc;
+    const size_t ntr = h->h_len.size();
+    if (tr_counts && !n) memset(tr_counts, 0, ntr * 4);  // nothing was expanded: the device table is stale
+    if (n) {
+        if ((rc = d2h_any(h, tr_counts, h->d_o_trcnt.p, ntr * 4)) || (rc = d2h_any(h, start, h->d_o_start.p, n * 4))) return rc;
+        if (len_strand) {
+            if (elem_bytes == 2) { if ((rc = d2h_any(h, len_strand, h->d_o_ls16.p, n * 2))) return rc; }
+            else if (!have16) { if ((rc = d2h_any(h, len_strand, h->d_o_ls32.p, n * 4))) return rc; }
+            else {  // 4-byte elements requested although the device holds the 2-byte form: widen on the host
+                std::vector<uint16_t> tmp(n);
+                CK(h, cudaMemcpyAsync(tmp.data(), h->d_o_ls16.p, n * 2, cudaMemcpyDeviceToHost, h->st));
+                CK(h, cudaStreamSynchronize(h->st));
+                uint32_t *o = (uint32_t *)len_strand;
+                for (uint64_t i = 0; i < n; i++) o[i] = (tmp[i] & 0x7fffu) | ((uint32_t)(tmp[i] >> 15) << 31);
+            }
+        }
+    }
     CK(h, cudaStreamSynchronize(h->st));
     return 0;
 }
@@ -1545,7 +1476,7 @@ int rlsim_format_fasta(rlsim_handle *h, const uint8_t *names, const uint64_t *na
     launch_fasta_write(h->st, make_tr(h), s, n, h->d_names.p, h->d_name_off.p, h->d_rec_off.p, h->first_index, h->d_fasta.p);
     tm.stop();
     CK(h, cudaGetLastError());
-    CK(h, cudaMemcpyAsync(buf, h->d_fasta.p, total, cudaMemcpyDeviceToHost, h->st));
+    if ((rc = d2h_any(h, buf, h->d_fasta.p, total))) return rc;
     CK(h, cudaStreamSynchronize(h->st));
     return 0;
 }

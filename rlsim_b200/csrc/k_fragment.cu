@@ -303,13 +303,14 @@ k_fragment(const __grid_constant__ DevModel m, DevTranscripts tr, uint64_t g_beg
     for (uint32_t i = threadIdx.x; i < hist_s_n + m.polya_max + 1; i += FRAG_THREADS) hist_s[i] = 0;
     __syncthreads();
     uint64_t g = g_begin + (uint64_t)blockIdx.x * FRAG_THREADS + threadIdx.x;  // global molecule index
+    const unsigned in_range = __ballot_sync(0xffffffffu, g < g_end);  // taken while the warp is still converged
     if (g < g_end) {
         // molecule -> transcript: the warp's first lane searches; a warp rarely spans more than a few transcripts.
         // (measured: a 32-ary search by the whole warp and a tile loop per CTA are both slower here)
         const uint64_t g0 = g - (threadIdx.x & 31);
         uint32_t t = 0;
         if ((threadIdx.x & 31) == 0) t = upper_bound_u64(tr.mol_off, tr.n + 1, g0) - 1;
-        t = __shfl_sync(__activemask(), t, 0);
+        t = __shfl_sync(in_range, t, 0);  // lane 0 holds the smallest g of the warp: it is in range whenever any lane is
         while (tr.mol_off[t + 1] <= g) t++;
         uint64_t mol = g - tr.mol_off[t];
         MolCtx c = make_ctx(m, tr, t);

@@ -249,6 +249,16 @@ __global__ void k_tr_out_base(DevSpecies sp, const uint64_t *__restrict__ out_of
     if (s == 0 || sp.tr[s - 1] != t) tr_out_base[t] = out_off[s];
 }
 
+// records per transcript (the packed host format replaces the per-record transcript index and id by these counts):
+// the last species of a transcript closes its run of output records
+__global__ void k_tr_counts(DevSpecies sp, const uint64_t *__restrict__ out_off, const uint64_t *__restrict__ tr_out_base,
+                            uint32_t *__restrict__ tr_counts) {
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= sp.n) return;
+    const uint32_t t = sp.tr[s];
+    if (s + 1 == sp.n || sp.tr[s + 1] != t) tr_counts[t] = (uint32_t)(out_off[s + 1] - tr_out_base[t]);
+}
+
 __global__ void k_expand(const __grid_constant__ DevModel m, DevSpecies sp, const uint64_t *__restrict__ out_off,
                          const uint64_t *__restrict__ tr_out_base, uint64_t n_out, DevSampled out) {
     uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -269,11 +279,15 @@ __global__ void k_expand(const __grid_constant__ DevModel m, DevSpecies sp, cons
     out.end[o] = end;
     out.minus[o] = minus ? 1 : 0;
     out.id[o] = o - tr_out_base[t];  // per-transcript fragment id (sampler.go:189,204)
+    // packed host format: length with the strand in the top bit, 2 bytes when every length fits 15 bits
+    if (out.ls16) out.ls16[o] = (uint16_t)((end - start) | (minus ? 0x8000u : 0u));
+    else if (out.ls32) out.ls32[o] = (end - start) | (minus ? 0x80000000u : 0u);
 }
 void launch_expand(cudaStream_t st, const DevModel &m, const DevSpecies &sp, const uint64_t *out_off, uint64_t *tr_out_base,
                    uint64_t n_out, DevSampled out) {
     if (!n_out) return;
     k_tr_out_base<<<(unsigned)((sp.n + 255) / 256), 256, 0, st>>>(sp, out_off, tr_out_base);
+    if (out.tr_counts) k_tr_counts<<<(unsigned)((sp.n + 255) / 256), 256, 0, st>>>(sp, out_off, tr_out_base, out.tr_counts);
     k_expand<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(m, sp, out_off, tr_out_base, n_out, out);
 }
 

@@ -175,11 +175,13 @@ __global__ void k_kmer_lut(int k, double T, double *__restrict__ K, unsigned lon
     atomicMax(kmax_bits, (unsigned long long)__double_as_longlong(v));  // positive doubles order like their bit patterns
 }
 
-// spec 4.3: w = min(floor(K * 2^26 / Kmax + 1/2), 2^26 - 1)
+// spec 4.3: w = clamp(floor(K * 2^26 / Kmax + 1/2), 1, 2^26 - 1).  The lower clamp keeps every window's total positive:
+// SampleIndexFloat64 (random.go:369-401) accepts any positive weights, so a low -p or a run of N must not abort the run.
 #define PFX_SCALE 67108864.0
 __device__ __forceinline__ uint32_t quantize(double K, double scale) {
     double x = K * scale + 0.5;
     if (!(x < 67108863.0)) return 67108863u;
+    if (x < 1.0) return 1u;
     return (uint32_t)x;
 }
 

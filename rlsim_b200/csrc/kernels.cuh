@@ -72,7 +72,11 @@ void launch_apply_records(cudaStream_t st, const uint4 *records, uint64_t n, con
                           const uint64_t *bounds, const uint32_t *order, unsigned long long *hits, int *error);
 void launch_taken(cudaStream_t st, const DevSpecies &sp, const uint8_t *mode_by_len, uint32_t n_len,
                   const unsigned long long *hits, uint64_t *taken);
-struct DevSampled { uint32_t *tr, *start, *end; uint8_t *minus; uint64_t *id; };
+struct DevSampled {
+    uint32_t *tr, *start, *end; uint8_t *minus; uint64_t *id;
+    // packed host format (rlsim_get_sampled_packed); any of them may be null
+    uint16_t *ls16 = nullptr; uint32_t *ls32 = nullptr; uint32_t *tr_counts = nullptr;  // tr_counts: zeroed by the caller
+};
 void launch_expand(cudaStream_t st, const DevModel &m, const DevSpecies &sp, const uint64_t *out_off, uint64_t *tr_out_base,
                    uint64_t n_out, DevSampled out);
 

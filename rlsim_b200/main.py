@@ -66,6 +66,10 @@ def run(argv, out=None):
     log.v("Starting up rlsim using maximum %d cores." % args.max_procs)
     if args.init_seed == 0:
         args.init_seed = int(time.time())  # main.go:76-79
+        if world > 1:  # every rank must key its streams with the logged seed: rank 0's clock decides
+            box = [args.init_seed]
+            dist.broadcast_object_list(box, src=0)
+            args.init_seed = int(box[0])
     log.v("Initial random seed: %d" % args.init_seed)
     if args.raw_params_file:
         log.v("Using raw parameter file: %s" % args.raw_params_file)
@@ -116,7 +120,9 @@ def run(argv, out=None):
         log.v("Sampling ratio: %g" % (stats.nr_sampled / float(stats.total_frags) if stats.total_frags else float("nan")))
         log.v("Sampled %d fragments." % stats.nr_sampled)
         log.v("Missing fragments: %d" % (args.req_frags - stats.nr_sampled))
-    except (_native.RlsimError, OverflowError, ImportError) as e:
+    except (_native.RlsimError, OverflowError, ImportError, ValueError, IndexError, KeyError) as e:
+        # the reference's only error policy is a fatal log line and exit 1 (logging.go:67-73): "Illegal fasta record"
+        # (fasta.go:183-185) and malformed raw-parameter files (parse_raw.go) included - json.JSONDecodeError is a ValueError
         log.fatal(str(e))
     if report:  # fragstats.go:120-141
         report.report_map(stats.after_frag, "Length", "Count", "Fragdist after fragmentation", "bar")

@@ -37,6 +37,28 @@ class GpuPool:
         self.rank, self.world, self.dist_device = rank, world, dist_device
         self.names = []
         self.first = 0
+        self.lib_comm = False
+        if world > 1:
+            self._init_lib_comm()
+
+    def _init_lib_comm(self):
+        """Join the ranks' handles with the library's own NCCL communicator (rlsim_comm_init): afterwards the whole
+        multi-GPU selection is one library call on the handle's stream.  The id travels through the process group that
+        launched the ranks; without NCCL / a GPU process group (gloo-only CPU tests) the torch.distributed exchange of
+        shard.RecordExchange remains."""
+        import os
+        try:
+            import torch.distributed as dist
+            if os.environ.get("RLSIM_TORCH_EXCHANGE") or not (dist.is_available() and dist.is_initialized()):
+                return
+            if self.dist_device is None:  # gloo (CPU) group: no GPUs to join
+                return
+            box = [_native.comm_unique_id() if self.rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            self.handle.comm_init(box[0], self.world, self.rank)
+            self.lib_comm = True
+        except _native.RlsimError:
+            self.lib_comm = False
 
     def configure(self, args: CmdArgs):
         """NewFragmentor + NewTechne + NewTarget + NewLenSampler, main.go:88-127."""
@@ -52,8 +74,10 @@ class GpuPool:
             a, b = n * self.rank // self.world, n * (self.rank + 1) // self.world
             h.sample_target_range(a, b - a)  # asynchronous, on the library's own stream
             nb = int(max([c.high for c in args.target_mix] + (args.raw_len_probs.lengths if args.raw_len_probs else [0]))) + 1
-            if args.raw_len_probs is not None:
-                self._sum_target(shard.allreduce_hist(h.hist(_native.H_TARGET, nb), device=self.dist_device))  # shapes the library: now
+            if args.raw_len_probs is not None and self.lib_comm:
+                h.comm_sum_target()  # a raw target shapes the library (range, mean): summed over the ranks now
+            elif args.raw_len_probs is not None:
+                self._sum_target(shard.allreduce_hist(h.hist(_native.H_TARGET, nb), device=self.dist_device))
             else:
                 self._target_nb = nb  # summed later, together with the per-length totals (finish_target / RecordExchange)
         else:
@@ -67,7 +91,10 @@ class GpuPool:
 
     def finish_target(self):
         """Multi-GPU: sum the ranks' partial target histograms if that is still pending (no-op otherwise)."""
-        if getattr(self, "_target_nb", 0):
+        if getattr(self, "_target_nb", 0) and self.lib_comm:
+            self.handle.comm_sum_target()
+            self._target_nb = 0
+        elif getattr(self, "_target_nb", 0):
             self._sum_target(shard.allreduce_hist(self.handle.hist(_native.H_TARGET, self._target_nb), device=self.dist_device))
 
     def reset(self):
@@ -133,7 +160,11 @@ class GpuSampler:
     def sample_fragments(self, pool: GpuPool, stats: FragStats = None):
         """sampler.go:108-154.  -> dict of arrays (tr, start, end, minus, id) for this rank's shard."""
         h = pool.handle
-        if pool.world > 1:  # classes partitioned over the ranks, drawn copy ranks routed to their owners (all-to-all)
+        if pool.world > 1 and pool.lib_comm:  # the whole exchange inside the library (NCCL on the handle's stream)
+            h.sample_distributed()
+            pool._target_nb = 0
+            total = h.hist(_native.H_POOL_GLOBAL, int(h.stats().high) + 1)
+        elif pool.world > 1:  # classes partitioned over the ranks, drawn copy ranks routed to their owners (all-to-all)
             if not hasattr(pool, "_exchange"):
                 pool._exchange = shard.RecordExchange(pool.dist_device)
             all_tot = pool._exchange.run(h, pool.rank, pool.world, int(pool.args.req_frags) // pool.world + 4096, pool=pool)

@@ -151,6 +151,24 @@ def test_product_never_touches_the_oracle():
                 assert "pyoracle" not in txt and "liboracle" not in txt and "oracle/" not in txt.replace("the oracle", ""), f
 
 
+def test_exchange_plan_host_arithmetic():
+    """rlsim_exchange_plan: where each rank's groups start in its send buffer and where each sender's records land
+    (the routing arithmetic of rlsim_sample_distributed; no GPU involved)."""
+    from rlsim_b200 import _native
+    rng = np.random.default_rng(4)
+    for n in (1, 2, 3, 8):
+        c = rng.integers(0, 1000, size=(n, n)).astype(np.uint64)
+        c[0, n - 1] = 0
+        for r in range(n):
+            so, ro = _native.exchange_plan(c, r)
+            assert list(so) == [int(c[r, :d].sum()) for d in range(n + 1)]
+            assert list(ro) == [int(c[:s, r].sum()) for s in range(n + 1)]
+        # what every rank sends to rank r is what rank r expects to receive
+        assert all(int(_native.exchange_plan(c, r)[1][-1]) == int(c[:, r].sum()) for r in range(n))
+    with pytest.raises(_native.RlsimError):
+        _native.exchange_plan(np.zeros((2, 2), np.uint64), 2)
+
+
 def test_contiguous_partition():
     rng = np.random.default_rng(0)
     w = rng.gamma(0.5, 10.0, 1000)
