@@ -89,7 +89,8 @@ typedef struct {
 enum { RLSIM_F_MIRRORED_REVERSE = 1,  /* reverse priming reads the forward prefix sums mirrored (symmetric k-mer table) */
        RLSIM_F_EAGER = 2,             /* the last library was fragmented and amplified while its transcripts were copied */
        RLSIM_F_GROUPS_SHIFT = 8,      /* bits 8..15: number of chunk groups the eager pipeline ran (saturating at 255) */
-       RLSIM_F_PAGEABLE_STAGED = 4 }; /* the last rlsim_add_transcripts staged a pageable caller buffer through pinned memory */
+       RLSIM_F_PAGEABLE_STAGED = 4,   /* the last rlsim_add_transcripts staged a pageable caller buffer through pinned memory */
+       RLSIM_F_FUSED = 16 };          /* fragmentation kept the priming prefix sums in shared memory (fused kernel) */
 
 /* histogram kinds (fragstats.go:45-56); every histogram is indexed by length */
 enum { RLSIM_H_TARGET = 0, RLSIM_H_POLYA = 1, RLSIM_H_AFTER_FRAG = 2, RLSIM_H_AFTER_PCR = 3, RLSIM_H_SAMPLED = 4,

@@ -20,7 +20,7 @@ COMM_ID_BYTES = 128
 
 E_CUDA, E_ARG, E_PRIMING, E_PCR_OVERFLOW, E_POOL_OVERFLOW, E_UNSUPPORTED, E_NOMEM = range(1, 8)  # include/rlsim_gpu.h
 
-F_MIRRORED_REVERSE, F_EAGER, F_PAGEABLE_STAGED, F_GROUPS_SHIFT = 1, 2, 4, 8  # rlsim_stats.flags
+F_MIRRORED_REVERSE, F_EAGER, F_PAGEABLE_STAGED, F_GROUPS_SHIFT, F_FUSED = 1, 2, 4, 8, 16  # rlsim_stats.flags
 
 EXPORTS = [
     "rlsim_create", "rlsim_destroy", "rlsim_last_error", "rlsim_set_model", "rlsim_set_len_eff", "rlsim_set_raw_target",

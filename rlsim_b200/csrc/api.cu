@@ -143,8 +143,7 @@ int grow_prefix(rlsim_handle *h, uint64_t tot, uint32_t n, uint64_t old_tot, uin
 }
 
 // priming affinities -> prefix sums for transcripts [t0, t1) (nnthermo.go:177-201); launches only
-int launch_prefix_range(rlsim_handle *h, uint32_t t0, uint32_t t1) {
-    int method = h->p.frag_method;
+int ensure_lut(rlsim_handle *h) {
     if (!h->lut_valid) {
         uint32_t nk = 1u << (2 * h->p.kmer_len);
         CK(h, h->d_K.ensure(nk)); CK(h, h->d_wq_f.ensure(nk)); CK(h, h->d_wq_r.ensure(nk));
@@ -155,6 +154,12 @@ int launch_prefix_range(rlsim_handle *h, uint32_t t0, uint32_t t1) {
         h->lut_valid = true; h->lut_k = h->p.kmer_len; h->lut_T = h->p.priming_temp;
         h->launches[RLSIM_T_PREFIX] += 3;
     }
+    return 0;
+}
+int launch_prefix_range(rlsim_handle *h, uint32_t t0, uint32_t t1) {
+    int method = h->p.frag_method;
+    int rcl = ensure_lut(h);
+    if (rcl) return rcl;
     launch_prefix(h->st, make_tr(h), t0, t1, h->p.kmer_len, h->p.priming_temp, h->d_wq_f.p, h->d_wq_r.p, h->d_kmax.p,
                   h->d_Ff.p, h->d_Fr.p, h->d_Cf.p, h->d_Cr.p, needs_rev(method) ? 2 : 1, h->d_work.p);
     h->launches[RLSIM_T_PREFIX] += 1;
@@ -201,6 +206,7 @@ int d2h_any(rlsim_handle *h, void *dst_, const void *src_, size_t bytes) {
 #define D2H(dst, src, bytes) do { if (dst) CK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->st)); } while (0)
 
 void eager_reset(rlsim_handle *h) {
+    h->fused_used = false;
     h->eager_upto = 0; h->eager_failed = h->eager_started = h->eager_pcr = false; h->eager_keys = h->eager_sp = 0;
     h->eager_groups = 0;
 }
@@ -244,6 +250,81 @@ bool ns_need(rlsim_handle *h, uint64_t ns) {  // would any per-species array be 
     return ns > h->d_sp_tr.n || ns > h->d_sp_start.n || ns > h->d_sp_len.n || ns > h->d_sp_count.n || ns > h->d_sp_eff.n || ns > h->d_sp_gc.n;
 }
 
+// ---- fused path: prefix sums in shared memory (k_fused).  Eligible: the priming methods whose intervals are searched
+// once per breakpoint pair; every transcript of the range must fit one CTA's shared memory and produce few enough
+// breakpoints for the deferred-molecule kernel.
+bool fused_method(rlsim_handle *h) {
+    const bool disabled = getenv("RLSIM_NO_FUSED") != nullptr;  // diagnostic switch: HBM prefix sums (k_prefix + k_fragment + k_intervals)
+    return !disabled && !h->fused_disabled && (h->p.frag_method == RLSIM_AFTER_PRIM || h->p.frag_method == RLSIM_AFTER_PRIM_DOUBLE);
+}
+bool fused_len_ok(rlsim_handle *h, uint32_t L) {
+    return (((uint64_t)L + 63) & ~63ull) <= FUSED_CAP_LARGE && (double)L / frag_denominator(h) <= (double)FUSED_LONG_BREAKS;
+}
+bool fused_range_ok(rlsim_handle *h, uint32_t t0, uint32_t t1) {
+    if (!fused_method(h)) return false;
+    if (fused_len_ok(h, h->max_len)) return true;
+    for (uint32_t t = t0; t < t1; t++)
+        if (h->h_expr[t] && !fused_len_ok(h, h->h_len[t])) return false;
+    return true;
+}
+
+// Work items for the transcripts [t0, t1): runs of consecutive transcripts whose prefix sums fit the small class together
+// (at most FUSED_MAX molecules each; heavily expressed transcripts are split by molecule range), one transcript per item
+// in the large class.  The kernel sub-batches an item if it turns out not to fit (transcripts with letters outside ACGT
+// carry explicit reverse arrays, which the host does not know).
+int build_fused_items(rlsim_handle *h, uint32_t t0, uint32_t t1) {
+    const bool dbl = h->p.frag_method == RLSIM_AFTER_PRIM_DOUBLE;
+    const bool sym = h->lut_sym && h->want_mirror;
+    const int key = (dbl ? 1 : 0) | (sym ? 2 : 0);
+    if (h->fitems_key == key && h->fitems_t0 == t0 && h->fitems_t1 == t1) return 0;  // still on the device
+    constexpr uint64_t M_MAX = 4096;
+    PinVec<FusedItem> &S = h->h_fitems_s, &Lg = h->h_fitems_l;
+    S.clear(); Lg.clear();
+    const uint64_t *mo = h->h_mol_off.data();
+    uint32_t ts = 0, te = 0, cnt = 0;
+    uint64_t sumE = 0, sumM = 0;
+    auto flush = [&] { if (cnt) S.push_back(FusedItem{ts, te, mo[ts], mo[te]}); cnt = 0; sumE = 0; sumM = 0; };
+    for (uint32_t t = t0; t < t1; t++) {
+        const uint64_t ex = h->h_expr[t];
+        if (!ex) continue;
+        const uint64_t e1 = ((uint64_t)h->h_len[t] + 63) & ~63ull;
+        const bool small = (dbl ? 2 : 1) * e1 <= FUSED_CAP_SMALL;  // fits alone even with explicit reverse arrays
+        const uint64_t est = e1 * (dbl && !sym ? 2 : 1);
+        if (!small || ex > M_MAX) {
+            flush();
+            PinVec<FusedItem> &dst = small ? S : Lg;
+            for (uint64_t g = mo[t]; g < mo[t + 1]; g += M_MAX) dst.push_back(FusedItem{t, t + 1, g, std::min<uint64_t>(g + M_MAX, mo[t + 1])});
+            continue;
+        }
+        if (cnt && (sumE + est > FUSED_CAP_SMALL || sumM + ex > M_MAX || cnt >= 32)) flush();
+        if (!cnt) ts = t;
+        te = t + 1; sumE += est; sumM += ex; cnt++;
+    }
+    flush();
+    CK(h, h->d_fitems_s.ensure(S.size() + 1)); CK(h, h->d_fitems_l.ensure(Lg.size() + 1));
+    if (S.size()) CK(h, cudaMemcpyAsync(h->d_fitems_s.p, S.data(), S.size() * sizeof(FusedItem), cudaMemcpyHostToDevice, h->st));
+    if (Lg.size()) CK(h, cudaMemcpyAsync(h->d_fitems_l.p, Lg.data(), Lg.size() * sizeof(FusedItem), cudaMemcpyHostToDevice, h->st));
+    h->fitems_key = key; h->fitems_t0 = t0; h->fitems_t1 = t1;
+    return 0;
+}
+
+// queue the fused kernels for the transcripts [t0, t1) (launches only; the caller reads the counters)
+int launch_fused_range(rlsim_handle *h, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t t0, uint32_t t1) {
+    int rc;
+    if ((rc = ensure_lut(h))) return rc;
+    DevTranscripts trs = tr;
+    trs.sym = h->lut_sym && h->want_mirror ? 1 : 0;  // ensure_lut may just have established it
+    if ((rc = build_fused_items(h, t0, t1))) return rc;
+    int *fallback = reinterpret_cast<int *>(h->d_work.p + 6);
+    CK(h, cudaMemsetAsync(fallback, 0, 4, h->st));
+    if ((rc = launch_fused(h->st, m, trs, fb, h->d_fitems_s.p, (uint32_t)h->h_fitems_s.size(), FUSED_CAP_SMALL, h->d_work.p + 4, h->d_wq_f.p,
+                           h->d_wq_r.p, h->d_kmax.p, fallback, h->sm_count))) return rc;
+    if ((rc = launch_fused(h->st, m, trs, fb, h->d_fitems_l.p, (uint32_t)h->h_fitems_l.size(), FUSED_CAP_LARGE, h->d_work.p + 5, h->d_wq_f.p,
+                           h->d_wq_r.p, h->d_kmax.p, fallback, h->sm_count))) return rc;
+    h->launches[RLSIM_T_FRAGMENT] += (h->h_fitems_s.size() ? 1 : 0) + (h->h_fitems_l.size() ? 1 : 0);
+    return 0;
+}
+
 // Fragment, dedup and amplify the transcripts [t0, t1) of a chunk whose ingest + prefix sums are already queued on
 // the compute stream.  The host waits on the compute stream only; the copy stream keeps feeding later chunks.
 int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
@@ -276,23 +357,38 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
     DevTranscripts tr = make_tr(h);
     FragBuffers fb{h->d_keys.p, h->d_keys.n, h->d_counters.p, h->d_hist_frag.p, h->d_hist_polya.p, h->d_long_list.p, h->d_long_hi.p,
                    long_cap, h->d_long_count.p, h->d_error.p, h->d_q_a.p, h->d_q_b.p, h->d_q_a.n, h->d_counters.p + 2};
-    if ((rc = launch_fragment(h->st, m, tr, g0, g1, fb))) { h->eager_failed = true; return 0; }
+    const bool fused = fused_range_ok(h, t0, t1);
+    if (fused) { if ((rc = launch_fused_range(h, m, tr, fb, t0, t1))) { h->eager_failed = true; return 0; } }
+    else if ((rc = launch_fragment(h->st, m, tr, g0, g1, fb))) { h->eager_failed = true; return 0; }
     CK(h, cudaMemcpyAsync(h->pin, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
     CK(h, cudaMemcpyAsync(h->pin + 1, h->d_counters.p + 2, 8, cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaMemcpyAsync(h->pin + 7, h->d_work.p + 6, 4, cudaMemcpyDeviceToHost, h->st));
     CK(h, cudaStreamSynchronize(h->st));
     const unsigned int n_long = *reinterpret_cast<unsigned int *>(h->pin);
-    const unsigned long long n_q = h->pin[1];
+    const unsigned long long n_q = fused ? 0ull : h->pin[1];
+    if (fused && *reinterpret_cast<int *>(h->pin + 7)) { h->fused_disabled = true; h->eager_failed = true; return 0; }
     tt1 = now_ms();
     // test hook: pretend the estimate of group number RLSIM_EAGER_TEST_FAIL (0-based) was too small
     const char *fail_at = getenv("RLSIM_EAGER_TEST_FAIL");
     const bool forced = fail_at && (uint32_t)atoi(fail_at) == h->eager_groups;
     h->eager_groups++;
     if (forced || n_long > long_cap || n_q > h->d_q_a.n) { h->eager_failed = true; return 0; }
-    launch_intervals(h->st, m, tr, fb, n_q);
-    launch_fragment_long(h->st, m, tr, fb, n_long);
-    h->launches[RLSIM_T_FRAGMENT] += 1 + (n_long ? 1 : 0); h->launches[RLSIM_T_INTERVALS] += n_q ? 1 : 0;
+    if (fused) {
+        if (n_long) {
+            DevTranscripts trs = tr; trs.sym = h->lut_sym && h->want_mirror ? 1 : 0;
+            launch_fused_long(h->st, m, trs, fb, n_long, FUSED_CAP_LARGE, h->d_wq_f.p, h->d_wq_r.p, h->d_kmax.p, reinterpret_cast<int *>(h->d_work.p + 6));
+            CK(h, cudaMemcpyAsync(h->pin + 7, h->d_work.p + 6, 4, cudaMemcpyDeviceToHost, h->st));
+            h->launches[RLSIM_T_FRAGMENT] += 1;
+        }
+        h->fused_used = true;
+    } else {
+        launch_intervals(h->st, m, tr, fb, n_q);
+        launch_fragment_long(h->st, m, tr, fb, n_long);
+        h->launches[RLSIM_T_FRAGMENT] += 1 + (n_long ? 1 : 0); h->launches[RLSIM_T_INTERVALS] += n_q ? 1 : 0;
+    }
     CK(h, cudaMemcpyAsync(h->pin + 2, h->d_counters.p, 8, cudaMemcpyDeviceToHost, h->st));
     CK(h, cudaStreamSynchronize(h->st));
+    if (fused && *reinterpret_cast<int *>(h->pin + 7)) { h->fused_disabled = true; h->eager_failed = true; return 0; }
     const unsigned long long cnt = h->pin[2];
     tt2 = now_ms();
     CK(h, cudaGetLastError());
@@ -363,7 +459,7 @@ int finalize(rlsim_handle *h) {
         CK(h, cudaStreamSynchronize(h->st));
         h->mol_off_valid = true;
     }
-    if (needs_fwd(h->p.frag_method) && h->prefix_upto < n) {
+    if (needs_fwd(h->p.frag_method) && h->prefix_upto < n && !fused_range_ok(h, 0, n)) {
         int rcg = grow_prefix(h, h->total_padded, n, h->prefix_upto ? h->total_padded : 0, h->prefix_upto);
         if (rcg) return rcg;
         StageTimer tm(h, RLSIM_T_PREFIX, 0);
@@ -412,12 +508,13 @@ int rlsim_create(int device, rlsim_handle **out) {
         (e = cudaHostAlloc((void **)&h->pin, 64, cudaHostAllocDefault)) != cudaSuccess ||
         (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
         (e = h->d_error.ensure(1)) != cudaSuccess || (e = h->d_counters.ensure(4)) != cudaSuccess ||
-        (e = h->d_long_count.ensure(1)) != cudaSuccess || (e = h->d_work.ensure(4)) != cudaSuccess || (e = h->d_kmax.ensure(1)) != cudaSuccess) {
+        (e = h->d_long_count.ensure(1)) != cudaSuccess || (e = h->d_work.ensure(8)) != cudaSuccess || (e = h->d_kmax.ensure(1)) != cudaSuccess) {
         g_create_error = std::string("rlsim_create: ") + cudaGetErrorString(e);
         delete h;
         return RLSIM_E_CUDA;
     }
     cudaMemsetAsync(h->d_error.p, 0, sizeof(int), h->st);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     *out = h;
     return 0;
 }
@@ -464,6 +561,7 @@ int rlsim_set_model(rlsim_handle *h, const rlsim_params *p) {
     if (!h->h_len.empty() && h->polya_max != (uint32_t)mx) FAIL(h, RLSIM_E_ARG, "poly(A) maximum cannot change after transcripts were added");
     h->polya_max = (uint32_t)mx;
     h->prefix_upto = 0;
+    h->fused_disabled = false; h->fitems_key = -1;
     h->lut_valid = h->lut_valid && h->lut_k == p->kmer_len && h->lut_T == p->priming_temp;
     h->want_mirror = getenv("RLSIM_NO_MIRROR") == nullptr;  // diagnostic switch: always build explicit reverse arrays
     h->len_eff_ready = false;
@@ -582,6 +680,7 @@ int rlsim_clear_transcripts(rlsim_handle *h) {
     cudaStreamSynchronize(h->st);
     h->h_srclen.clear(); h->h_expr.clear(); h->h_off.clear(); h->h_len.clear();
     h->prefix_upto = 0; h->fragmented = h->amplified = h->sampled = false;
+    h->fused_disabled = false; h->fitems_key = -1; h->max_len = 0;
     h->n_mol = h->total_padded = h->n_frag = h->n_sp = h->n_out = h->pool_total = 0;
     h->sum_expr = h->sum_expr_len = 0; h->mol_off_valid = false;
     h->h_mol_off.clear();
@@ -619,6 +718,7 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
             rel[i + 1] = r1;
             too_long |= L >> 32;
             srclen[i] = l; ex[i] = expr[i]; len[i] = (uint32_t)L;
+            if (expr[i] && L > h->max_len && !(L >> 32)) h->max_len = (uint32_t)L;
             off[i + 1] = off[i] + ((L + 31) & ~31ull);
             molo[i + 1] = molo[i] + expr[i];
             se += (double)expr[i];
@@ -642,12 +742,14 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     CK(h, h->d_packed.grow_preserve(tot / 16 + 8, old_total / 16, h->st));
     CK(h, h->d_nmask.grow_preserve(tot / 32 + 8, old_total / 32, h->st));
     CK(h, h->d_gc.grow_preserve(tot / 32 + nn + 8, old_total / 32 + n0 + 1, h->st));
-    const bool want_prefix = needs_fwd(h->p.frag_method) && h->prefix_upto == n0;
+    // priming prefix sums: in shared memory inside the fused kernel when every transcript of the batch fits, else in HBM
+    const bool range_fused = fused_range_ok(h, n0, nn);
+    const bool want_prefix = needs_fwd(h->p.frag_method) && !range_fused && h->prefix_upto == n0;
     if (want_prefix) {
         int rcg = grow_prefix(h, tot, nn, old_total, n0);
         if (rcg) return rcg;
     }
-    const bool want_eager = (want_prefix || !needs_fwd(h->p.frag_method)) && eager_possible(h, n0);
+    const bool want_eager = (want_prefix || range_fused || !needs_fwd(h->p.frag_method)) && eager_possible(h, n0);
     CK(h, h->d_off.ensure(nn + 1)); CK(h, h->d_len.ensure(nn)); CK(h, h->d_expr.ensure(nn));
     CK(h, h->d_dirty.grow_preserve(nn + 1, n0, h->st));
     if (want_eager) {
@@ -922,7 +1024,7 @@ int rlsim_fragment(rlsim_handle *h) {
         h->fragmented = true; h->amplified = false; h->sampled = false;
         return 0;
     }
-    h->eager_upto = 0; h->eager_failed = true; h->eager_pcr = false; h->eager_used = false;
+    h->eager_upto = 0; h->eager_failed = true; h->eager_pcr = false; h->eager_used = false; h->fused_used = false;
     // ---- capacity estimate for the fragment keys
     double loc = h->raw_location;
     if (h->p.n_target > 0) {
@@ -956,17 +1058,39 @@ int rlsim_fragment(rlsim_handle *h) {
         CK(h, cudaMemsetAsync(h->d_error.p, 0, 4, h->st));
         FragBuffers fb{h->d_keys.p, cap, h->d_counters.p, h->d_hist_frag.p, h->d_hist_polya.p, h->d_long_list.p, h->d_long_hi.p,
                        long_cap, h->d_long_count.p, h->d_error.p, h->d_q_a.p, h->d_q_b.p, q_cap, h->d_counters.p + 2};
-        StageTimer tm(h, RLSIM_T_FRAGMENT, 1);
-        rc = launch_fragment(h->st, m, tr, 0, h->n_mol, fb);
-        if (rc) FAIL(h, rc, "fragmentation launch configuration unsupported (poly(A) maximum too large)");
+        const bool fused = fused_range_ok(h, 0, n);
+        StageTimer tm(h, RLSIM_T_FRAGMENT, fused ? 0 : 1);
+        if (fused) {
+            if ((rc = launch_fused_range(h, m, tr, fb, 0, n))) { tm.stop(); h->fused_disabled = true; attempt--; if ((rc = finalize(h))) return rc; tr = make_tr(h); continue; }
+        } else {
+            rc = launch_fragment(h->st, m, tr, 0, h->n_mol, fb);
+            if (rc) FAIL(h, rc, "fragmentation launch configuration unsupported (poly(A) maximum too large)");
+        }
         unsigned int n_long = 0;
         unsigned long long n_q = 0;
+        int fell_back = 0;
         CK(h, cudaMemcpyAsync(&n_long, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
         CK(h, cudaMemcpyAsync(&n_q, h->d_counters.p + 2, 8, cudaMemcpyDeviceToHost, h->st));
+        if (fused) CK(h, cudaMemcpyAsync(&fell_back, h->d_work.p + 6, 4, cudaMemcpyDeviceToHost, h->st));
         CK(h, cudaStreamSynchronize(h->st));
         if (n_long > long_cap) { tm.stop(); long_cap = n_long + 1024; continue; }
+        if (fused && n_long && !fell_back) {
+            DevTranscripts trs = tr; trs.sym = h->lut_sym && h->want_mirror ? 1 : 0;
+            h->launches[RLSIM_T_FRAGMENT]++;
+            launch_fused_long(h->st, m, trs, fb, n_long, FUSED_CAP_LARGE, h->d_wq_f.p, h->d_wq_r.p, h->d_kmax.p, reinterpret_cast<int *>(h->d_work.p + 6));
+            CK(h, cudaMemcpyAsync(&fell_back, h->d_work.p + 6, 4, cudaMemcpyDeviceToHost, h->st));
+            CK(h, cudaStreamSynchronize(h->st));
+        }
+        if (fused && fell_back) {  // a transcript's sums do not fit shared memory: HBM prefix sums for this library
+            tm.stop();
+            h->fused_disabled = true;
+            if ((rc = finalize(h))) return rc;
+            tr = make_tr(h);
+            continue;
+        }
+        if (fused) h->fused_used = true;
         if (n_q > q_cap) { tm.stop(); q_cap = n_q + n_q / 8 + 65536; continue; }
-        if (n_long) { h->launches[RLSIM_T_FRAGMENT]++; launch_fragment_long(h->st, m, tr, fb, n_long); }
+        if (!fused && n_long) { h->launches[RLSIM_T_FRAGMENT]++; launch_fragment_long(h->st, m, tr, fb, n_long); }
         tm.stop();
         if (n_q) {
             StageTimer tq(h, RLSIM_T_INTERVALS, 1);
@@ -1360,6 +1484,7 @@ int rlsim_get_stats(rlsim_handle *h, rlsim_stats *out) {
     out->low = h->low; out->high = h->high; out->polya_max = h->polya_max;
     out->flags = (needs_rev(h->p.frag_method) && h->lut_valid && h->lut_sym && h->want_mirror ? RLSIM_F_MIRRORED_REVERSE : 0) |
                  (h->eager_used ? RLSIM_F_EAGER : 0) | (h->staged_pageable ? RLSIM_F_PAGEABLE_STAGED : 0) |
+                 (h->fused_used ? RLSIM_F_FUSED : 0) |
                  (std::min<uint32_t>(h->eager_groups, 255u) << RLSIM_F_GROUPS_SHIFT);
     return 0;
 }
@@ -1497,10 +1622,19 @@ int rlsim_probe_kmer_lut(rlsim_handle *h, double *K_out, uint32_t *w_out, uint32
 }
 
 int rlsim_probe_prefix(rlsim_handle *h, uint32_t tr, int reverse, uint64_t *out, uint32_t n) {
-    if (h->prefix_upto <= tr) FAIL(h, RLSIM_E_ARG, "no priming prefix sums (run rlsim_fragment with a priming method)");
     if (tr >= h->h_len.size()) FAIL(h, RLSIM_E_ARG, "transcript index out of range");
+    if (!needs_fwd(h->p.frag_method)) FAIL(h, RLSIM_E_ARG, "no priming prefix sums for this fragmentation method");
     if (reverse && !needs_rev(h->p.frag_method)) FAIL(h, RLSIM_E_ARG, "no reverse profile for this method");
     cudaSetDevice(h->device);
+    if (h->prefix_upto <= tr) {  // the fused path keeps the sums in shared memory: materialise them in HBM for the probe
+        const uint32_t nt = (uint32_t)h->h_len.size();
+        int rcg = grow_prefix(h, h->total_padded, nt, h->prefix_upto ? h->total_padded : 0, h->prefix_upto);
+        if (rcg) return rcg;
+        if ((rcg = launch_prefix_range(h, h->prefix_upto, nt))) return rcg;
+        CK(h, cudaStreamSynchronize(h->st));
+        CK(h, cudaGetLastError());
+        h->prefix_upto = nt;
+    }
     // rebuild P(0..proflen) from the two levels: P(i) = coarse[i >> 6] + (i & 63 ? fine[i - 1] : 0)
     uint32_t proflen = h->h_len[tr] > (uint32_t)h->p.kmer_len ? h->h_len[tr] - h->p.kmer_len : 0;
     const bool sym = make_tr(h).sym != 0;

@@ -235,7 +235,15 @@ struct rlsim_handle {
     uint32_t fa_n = 0;
     DBuf<uint64_t> d_off, d_expr, d_mol_off, d_Cf, d_Cr;  // coarse prefix sums
     DBuf<uint32_t> d_Ff, d_Fr;                          // fine (in-block) prefix sums
-    uint32_t prefix_upto = 0;  // transcripts [0, prefix_upto) have valid priming prefix sums for the current model
+    uint32_t prefix_upto = 0;  // transcripts [0, prefix_upto) have valid priming prefix sums IN HBM for the current model
+    // fused path (after_prim / after_prim_double): prefix sums in shared memory, work items = runs of transcripts
+    PinVec<FusedItem> h_fitems_s, h_fitems_l;     // small-class / large-class items of the last build
+    DBuf<FusedItem> d_fitems_s, d_fitems_l;
+    uint32_t fitems_t0 = 0, fitems_t1 = 0; int fitems_key = -1;  // what the device item lists cover (transcript range, layout key)
+    bool fused_disabled = false;                  // a transcript did not fit shared memory: this library stays on the HBM path
+    bool fused_used = false;
+    uint32_t max_len = 0;                         // longest transcript (with tail) added so far
+    int sm_count = 148;
     bool lut_valid = false;
     int lut_k = 0; double lut_T = 0; bool lut_sym = false, want_mirror = true;  // cached k-mer table; reverse-complement symmetric after quantisation
     DBuf<uint32_t> d_dirty;  // per transcript: letters outside ACGT present

@@ -12,7 +12,9 @@
 // Molecules whose Poisson draw asks for more than FRAG_LOCAL_BREAKS breakpoints are deferred to k_fragment_long
 // (one CTA per molecule, breakpoints sorted in shared memory).  Every draw is addressed by
 // (transcript, molecule, sub-stream, index), so both kernels produce the same fragments.
+#include <algorithm>
 #include "kernels.cuh"
+#include "prefix.cuh"
 #include "variates.cuh"
 
 namespace rl {
@@ -423,6 +425,296 @@ k_fragment_long(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused path (after_prim / after_prim_double): priming prefix sums live in SHARED memory, never in HBM.
+//
+// A work item is a run of consecutive transcripts (+ a molecule range) whose prefix sums fit one CTA's shared memory.
+// The CTA (persistent, items fetched from a global counter) builds the two-level prefix sums of the item's transcripts
+// from the 2-bit packed bases (0.25 B/nt of HBM reads instead of 4.1 B/nt written and ~0.5 KB per interval read back at
+// random), then fragments the item's molecules with every priming search served from shared memory.  The draws are
+// addressed by (transcript, molecule, sub-stream, index) and the search result is defined by the integers alone, so the
+// fragments are those of k_prefix + k_fragment + k_intervals bit for bit.
+//
+// Shared-memory layout (dynamic): [fine u32 x cap_entries][coarse u64 x (cap_entries/64 + 2*FUSED_MAX_TR)][LUT u32 x 4^k]
+// [histograms u32].  Inside it every profile (transcript, strand) owns a 64-entry aligned run of fine sums and
+// nblk + 1 coarse sums, exactly the per-transcript layout of the HBM arrays (common.cuh), so prime_search is shared.
+constexpr int FUSED_THREADS = 512;
+constexpr int FUSED_WARPS = FUSED_THREADS / 32;
+constexpr int FUSED_MAX_TR = 32;       // transcripts per sub-batch
+constexpr int FUSED_SEG = 1024;        // entries per prefix task (one warp, four sub-tiles)
+
+struct FusedBatch {                    // the sub-batch being processed (shared memory)
+    uint32_t n, t_next;                // transcripts in it; first transcript of the next sub-batch
+    uint32_t nprof, ntask;
+    int fail;
+    uint32_t t[FUSED_MAX_TR];          // transcript index
+    uint32_t L[FUSED_MAX_TR];
+    uint32_t fo[FUSED_MAX_TR], co[FUSED_MAX_TR];   // forward arrays: fine offset (entries), coarse offset (u64 slots)
+    uint32_t ro[FUSED_MAX_TR], rco[FUSED_MAX_TR];  // reverse arrays (0xffffffff: none / mirrored)
+    uint32_t mirror[FUSED_MAX_TR];
+    uint64_t off[FUSED_MAX_TR];
+    uint64_t mol[FUSED_MAX_TR + 1];    // mol_off of the transcripts (mol[n] = end of the last one)
+    // profiles = (transcript slot, strand): prefix tasks are enumerated over them
+    uint32_t p_slot[2 * FUSED_MAX_TR], p_rev[2 * FUSED_MAX_TR], p_ent[2 * FUSED_MAX_TR], p_task0[2 * FUSED_MAX_TR + 1];
+};
+
+__device__ __forceinline__ uint32_t pad64(uint32_t x) { return (x + 63u) & ~63u; }
+
+// thread 0: take transcripts from t_cur while their prefix sums fit `cap` entries
+__device__ void fused_pack(FusedBatch &B, const DevModel &m, const DevTranscripts &tr, uint32_t t_cur, uint32_t t_end,
+                           uint32_t cap, bool dbl) {
+    uint32_t used = 0, cused = 0, n = 0, np = 0, ntask = 0, t = t_cur;
+    B.fail = 0;
+    while (t < t_end && n < FUSED_MAX_TR) {
+        if (tr.expr[t] == 0) { t++; continue; }  // pool.go:104: never fragmented
+        const uint32_t L = tr.len[t], k = (uint32_t)m.k;
+        const bool dirty = tr.dirty[t] != 0;
+        const bool mirror = dbl && tr.sym && !dirty;
+        // forward arrays hold one more window in symmetric mode (the first window of the reverse profile)
+        const uint32_t entF = L >= k + (tr.sym ? 0u : 1u) ? L - k + (tr.sym ? 1u : 0u) : 0u;
+        const uint32_t entR = (dbl && !mirror && L > k) ? L - k : 0u;
+        const uint32_t eF = pad64(entF), eR = pad64(entR);
+        if (used + eF + eR > cap) {
+            if (n == 0) B.fail = 1;  // a single transcript that does not fit: the host reruns on the HBM path
+            break;
+        }
+        B.t[n] = t; B.L[n] = L; B.off[n] = tr.off[t]; B.mol[n] = tr.mol_off[t]; B.mirror[n] = mirror ? 1u : 0u;
+        B.fo[n] = used; B.co[n] = cused;
+        B.p_slot[np] = n; B.p_rev[np] = 0; B.p_ent[np] = entF; B.p_task0[np] = ntask; ntask += (entF + FUSED_SEG - 1) / FUSED_SEG; np++;
+        used += eF; cused += eF / 64 + 1;
+        if (dbl && !mirror) {
+            B.ro[n] = used; B.rco[n] = cused;
+            B.p_slot[np] = n; B.p_rev[np] = 1; B.p_ent[np] = entR; B.p_task0[np] = ntask; ntask += (entR + FUSED_SEG - 1) / FUSED_SEG; np++;
+            used += eR; cused += eR / 64 + 1;
+        } else { B.ro[n] = 0xffffffffu; B.rco[n] = 0xffffffffu; }
+        n++; t++;
+    }
+    if (n) B.mol[n] = tr.mol_off[B.t[n - 1] + 1];
+    B.p_task0[np] = ntask;
+    B.n = n; B.t_next = t; B.nprof = np; B.ntask = ntask;
+}
+
+// pass 1 (all warps): in-block sums of every 1024-entry segment + raw block totals into coarse[b + 1]
+// pass 2 (one warp per profile): coarse[] <- running sums of the block totals.  Both separated by CTA barriers (caller).
+__device__ void fused_prefix_pass1(const FusedBatch &B, const DevModel &m, const DevTranscripts &tr, uint32_t *fine_s,
+                                   uint64_t *coarse_s, const uint32_t *lut_f, const uint32_t *lut_r, double scale,
+                                   uint32_t warp, uint32_t nwarps, uint32_t lane) {
+    const uint32_t kmask = (1u << (2 * m.k)) - 1u, mmask = (1u << m.k) - 1u;
+    for (uint32_t task = warp; task < B.ntask; task += nwarps) {
+        uint32_t p = 0;
+        while (B.p_task0[p + 1] <= task) p++;
+        const uint32_t slot = B.p_slot[p], rev = B.p_rev[p], ent = B.p_ent[p];
+        const uint32_t seg0 = (task - B.p_task0[p]) * FUSED_SEG;
+        uint32_t *F = fine_s + (rev ? B.ro[slot] : B.fo[slot]);
+        uint64_t *C = coarse_s + (rev ? B.rco[slot] : B.co[slot]);
+        const PfxCtx pc{B.off[slot], B.L[slot], ent, m.k, (int)rev, m.T, scale, rev ? lut_r : lut_f, kmask, mmask};
+        const uint32_t seg1 = min(ent, seg0 + FUSED_SEG);
+        PfxWords nxt{0, 0, 0, 0, 0};
+        uint32_t ib = seg0 + lane * PFX_ITEMS;
+        if (ib < ent) nxt = pfx_load(tr, pc.o, pfx_jb(rev, pc.L, m.k, ent, ib));
+        for (uint32_t i0 = seg0; i0 < seg1; i0 += PFX_SUB) {
+            ib = i0 + lane * PFX_ITEMS;
+            const PfxWords w5 = nxt;
+            const uint32_t ibn = ib + PFX_SUB;
+            if (ibn < seg1 && ibn < ent) nxt = pfx_load(tr, pc.o, pfx_jb(rev, pc.L, m.k, ent, ibn));
+            uint32_t x[PFX_ITEMS];
+            const uint32_t run = pfx_lane_sums(tr, pc, ib, w5, x);
+            uint32_t incl = run;
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, d, 8);
+                if ((lane & 7) >= (uint32_t)d) incl += v;
+            }
+            const uint32_t excl = incl - run;
+            if (ib < ent) {  // the fine region is padded to 64 entries: whole 8-entry groups may be stored
+                uint4 *dst = reinterpret_cast<uint4 *>(F + ib);
+                dst[0] = make_uint4(excl + x[0], excl + x[1], excl + x[2], excl + x[3]);
+                dst[1] = make_uint4(excl + x[4], excl + x[5], excl + x[6], excl + x[7]);
+            }
+            if ((lane & 7) == 7 && i0 + (lane >> 3) * PFX_BLOCK < ent) C[(i0 >> PFX_BLOCK_SHIFT) + (lane >> 3) + 1] = incl;  // block total
+        }
+    }
+}
+__device__ void fused_prefix_pass2(const FusedBatch &B, uint64_t *coarse_s, uint32_t warp, uint32_t nwarps, uint32_t lane) {
+    for (uint32_t p = warp; p < B.nprof; p += nwarps) {
+        const uint32_t slot = B.p_slot[p];
+        uint64_t *C = coarse_s + (B.p_rev[p] ? B.rco[slot] : B.co[slot]);
+        const uint32_t nblk = (B.p_ent[p] + PFX_BLOCK - 1) >> PFX_BLOCK_SHIFT;
+        uint64_t carry = 0;
+        if (lane == 0) C[0] = 0;
+        for (uint32_t b0 = 0; b0 < nblk; b0 += 32) {
+            const uint32_t b = b0 + lane;
+            uint64_t v = b < nblk ? C[b + 1] : 0ull, incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint64_t u = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += u;
+            }
+            if (b < nblk) C[b + 1] = carry + incl;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+}
+
+struct FusedArgs {
+    const FusedItem *items; uint32_t n_items; uint32_t cap_entries;
+    unsigned int *work;                       // item counter
+    const uint32_t *wq_f, *wq_r; const unsigned long long *kmax_bits; int lut_in_smem;
+    int *fallback;                            // set when a transcript's sums do not fit: the host reruns on the HBM path
+};
+
+__global__ void __launch_bounds__(FUSED_THREADS, 2)
+k_fused(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, FusedArgs a, uint32_t hist_s_n) {
+    extern __shared__ __align__(16) unsigned char fsm[];
+    __shared__ FusedBatch B;
+    __shared__ uint32_t s_item;
+    uint32_t *fine_s = reinterpret_cast<uint32_t *>(fsm);
+    uint64_t *coarse_s = reinterpret_cast<uint64_t *>(fine_s + a.cap_entries);
+    uint32_t *lut_s = reinterpret_cast<uint32_t *>(coarse_s + (a.cap_entries / 64 + 2 * FUSED_MAX_TR));
+    const uint32_t nlut = a.lut_in_smem ? (1u << (2 * m.k)) : 0u;
+    unsigned int *hist_s = lut_s + 2 * nlut;  // [hist_s_n] after-fragmentation bins from `low`, then [polya_max+1]
+    unsigned int *hist_pa = hist_s + hist_s_n;
+    const bool dbl = m.method == RLSIM_AFTER_PRIM_DOUBLE;
+    const bool need_r_lut = dbl;  // explicit reverse profiles (dirty transcripts / asymmetric table)
+    for (uint32_t i = threadIdx.x; i < nlut; i += FUSED_THREADS) { lut_s[i] = a.wq_f[i]; if (need_r_lut) lut_s[nlut + i] = a.wq_r[i]; }
+    for (uint32_t i = threadIdx.x; i < hist_s_n + m.polya_max + 1; i += FUSED_THREADS) hist_s[i] = 0;
+    const uint32_t *lut_f = nlut ? lut_s : a.wq_f, *lut_r = nlut ? lut_s + nlut : a.wq_r;
+    const double scale = PFX_SCALE / __longlong_as_double((long long)*a.kmax_bits);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(a.work, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= a.n_items) break;
+        const FusedItem it = a.items[item];
+        uint32_t t_cur = it.t0;
+        while (t_cur < it.t1) {
+            if (threadIdx.x == 0) fused_pack(B, m, tr, t_cur, it.t1, a.cap_entries, dbl);
+            __syncthreads();
+            if (B.fail) { if (threadIdx.x == 0) atomicExch(a.fallback, 1); break; }
+            t_cur = B.t_next;
+            if (B.n == 0) break;  // nothing expressed in the rest of the item
+            const uint64_t gs = max(it.g0, B.mol[0]), ge = min(it.g1, B.mol[B.n]);
+            if (gs < ge) {
+                fused_prefix_pass1(B, m, tr, fine_s, coarse_s, lut_f, lut_r, scale, warp, FUSED_WARPS, lane);
+                __syncthreads();
+                fused_prefix_pass2(B, coarse_s, warp, FUSED_WARPS, lane);
+                __syncthreads();
+                for (uint64_t g = gs + threadIdx.x; g < ge; g += FUSED_THREADS) {
+                    uint32_t s = 0;  // transcript slot of molecule g
+                    while (B.mol[s + 1] <= g) s++;
+                    const uint64_t mol = g - B.mol[s];
+                    MolCtx c;
+                    c.t = B.t[s]; c.tg = m.first_index + c.t; c.L = B.L[s];
+                    c.proflen = c.L > (uint32_t)m.k ? c.L - (uint32_t)m.k : 0;
+                    c.off = B.off[s];
+                    c.Pf = Profile{fine_s + B.fo[s], coarse_s + B.co[s]};
+                    c.Pr = B.ro[s] != 0xffffffffu ? Profile{fine_s + B.ro[s], coarse_s + B.rco[s]} : Profile{nullptr, nullptr};
+                    c.mirror = B.mirror[s] != 0;
+                    Header h = mol_header<0>(m, c, mol);
+                    atomicAdd(&hist_pa[h.tail], 1u);
+                    if (h.nb > FRAG_LOCAL_BREAKS) {
+                        unsigned int slot = atomicAdd(o.long_count, 1u);
+                        if (slot < o.long_cap) { o.long_list[slot] = make_uint2(c.t, (uint32_t)(mol & 0xffffffffu)); o.long_hi[slot] = (uint32_t)(mol >> 32); }
+                    } else if (h.nb > 0) {
+                        const uint32_t length = (uint32_t)h.polyAend;
+                        uint32_t br[FRAG_LOCAL_BREAKS + 2];
+                        PxStream bs = mol_stream(m, c.tg, mol, SUB_BREAKS);
+                        br[0] = 0;
+                        int cnt = 1;
+                        for (int32_t j = 0; j < h.nb; j++) {  // insertion sort while drawing (fragmentor.go:125-129)
+                            uint32_t v = (uint32_t)bs.below((uint32_t)j, (uint64_t)length);
+                            int q = cnt++;
+                            while (q > 0 && br[q - 1] > v) { br[q] = br[q - 1]; q--; }
+                            br[q] = v;
+                        }
+                        br[cnt] = length;
+                        PxStream iv = mol_stream(m, c.tg, mol, SUB_INTERVAL);
+                        for (int32_t i = 0; i < h.nb; i++)  // the last interval is never visited (fragmentor.go:132)
+                            after_interval(m, c, iv, (uint32_t)i, br[i], br[i + 1], o, hist_s, hist_s_n);
+                    }
+                }
+            }
+            __syncthreads();  // the arrays are rebuilt for the next sub-batch
+        }
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < hist_s_n; i += FUSED_THREADS)
+        if (hist_s[i]) atomicAdd(&o.hist_frag[m.low + i], (unsigned long long)hist_s[i]);
+    for (uint32_t i = threadIdx.x; i <= m.polya_max; i += FUSED_THREADS)
+        if (hist_pa[i]) atomicAdd(&o.hist_polya[i], (unsigned long long)hist_pa[i]);
+}
+
+// Deferred molecules of the fused path (more breakpoints than a thread sorts locally): one CTA per molecule, its
+// transcript's prefix sums rebuilt in shared memory, breakpoints bitonic-sorted in shared memory.
+constexpr int FLONG_THREADS = 256;
+constexpr uint32_t FLONG_BREAKS = 4096;  // power of two; the host only takes the fused path when far fewer are expected
+__global__ void __launch_bounds__(FLONG_THREADS)
+k_fused_long(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, FusedArgs a, uint32_t n_long) {
+    extern __shared__ __align__(16) unsigned char fsm[];
+    __shared__ FusedBatch B;
+    __shared__ Header hs;
+    uint32_t *fine_s = reinterpret_cast<uint32_t *>(fsm);
+    uint64_t *coarse_s = reinterpret_cast<uint64_t *>(fine_s + a.cap_entries);
+    uint32_t *brs = reinterpret_cast<uint32_t *>(coarse_s + (a.cap_entries / 64 + 2 * FUSED_MAX_TR));
+    const uint32_t slot = blockIdx.x;
+    if (slot >= n_long) return;
+    const uint32_t t = o.long_list[slot].x;
+    const uint64_t mol = (uint64_t)o.long_list[slot].y | ((uint64_t)o.long_hi[slot] << 32);
+    const bool dbl = m.method == RLSIM_AFTER_PRIM_DOUBLE;
+    if (threadIdx.x == 0) fused_pack(B, m, tr, t, t + 1, a.cap_entries, dbl);
+    __syncthreads();
+    if (B.fail || B.n != 1) { if (threadIdx.x == 0) atomicExch(a.fallback, 1); return; }
+    const double scale = PFX_SCALE / __longlong_as_double((long long)*a.kmax_bits);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    fused_prefix_pass1(B, m, tr, fine_s, coarse_s, a.wq_f, a.wq_r, scale, warp, FLONG_THREADS / 32, lane);
+    __syncthreads();
+    fused_prefix_pass2(B, coarse_s, warp, FLONG_THREADS / 32, lane);
+    MolCtx c;
+    c.t = t; c.tg = m.first_index + t; c.L = B.L[0];
+    c.proflen = c.L > (uint32_t)m.k ? c.L - (uint32_t)m.k : 0;
+    c.off = B.off[0];
+    c.Pf = Profile{fine_s + B.fo[0], coarse_s + B.co[0]};
+    c.Pr = B.ro[0] != 0xffffffffu ? Profile{fine_s + B.ro[0], coarse_s + B.rco[0]} : Profile{nullptr, nullptr};
+    c.mirror = B.mirror[0] != 0;
+    if (threadIdx.x == 0) hs = mol_header<0>(m, c, mol);
+    __syncthreads();
+    const Header h = hs;
+    const uint32_t n = (uint32_t)h.nb + 2;
+    uint32_t npow = 1;
+    while (npow < n) npow <<= 1;
+    if (npow > FLONG_BREAKS) { if (threadIdx.x == 0) atomicExch(a.fallback, 1); return; }
+    const uint32_t length = (uint32_t)h.polyAend;
+    PxStream bs = mol_stream(m, c.tg, mol, SUB_BREAKS);
+    for (uint32_t j = threadIdx.x; j < npow; j += FLONG_THREADS) {
+        uint32_t v;
+        if (j < (uint32_t)h.nb) v = (uint32_t)bs.below(j, (uint64_t)length);
+        else if (j == (uint32_t)h.nb) v = 0u;
+        else if (j == (uint32_t)h.nb + 1) v = length;
+        else v = 0xffffffffu;
+        brs[j] = v;
+    }
+    __syncthreads();
+    for (uint32_t k2 = 2; k2 <= npow; k2 <<= 1) {
+        for (uint32_t j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+            for (uint32_t i = threadIdx.x; i < npow; i += FLONG_THREADS) {
+                uint32_t ixj = i ^ j2;
+                if (ixj > i) {
+                    uint32_t x = brs[i], y = brs[ixj];
+                    bool up = ((i & k2) == 0);
+                    if ((x > y) == up) { brs[i] = y; brs[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    PxStream iv = mol_stream(m, c.tg, mol, SUB_INTERVAL);
+    for (uint32_t i = threadIdx.x; i < (uint32_t)h.nb; i += FLONG_THREADS)
+        after_interval(m, c, iv, i, brs[i], brs[i + 1], o, nullptr, 0);
+}
+
 static uint32_t frag_hist_bins(const DevModel &m) {
     uint32_t n = m.high - m.low + 1;
     return n > 8192 ? 0 : n;
@@ -456,6 +748,45 @@ int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &t
     if (blocks > 0x7fffffffull) return RLSIM_E_UNSUPPORTED;
     const uint64_t max_blocks = 148ull * 5 * 6;
     k_intervals<<<(unsigned)std::min(blocks, max_blocks), IV_THREADS, (size_t)hist_s_n * 4, st>>>(m, tr, o, n_q, hist_s_n);
+    return 0;
+}
+
+// ---- fused path launches.  smem_optin = the device's opt-in shared memory per block.
+size_t fused_smem_bytes(const DevModel &m, uint32_t cap_entries, bool lut_in_smem, uint32_t hist_s_n) {
+    return (size_t)cap_entries * 4 + ((size_t)cap_entries / 64 + 2 * FUSED_MAX_TR) * 8 + (lut_in_smem ? ((size_t)8 << (2 * m.k)) : 0) +
+           ((size_t)hist_s_n + m.polya_max + 1) * 4 + 16;
+}
+int launch_fused(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, const FusedItem *items,
+                 uint32_t n_items, uint32_t cap_entries, unsigned int *work, const uint32_t *wq_f, const uint32_t *wq_r,
+                 const unsigned long long *kmax_bits, int *fallback, int sm_count) {
+    if (!n_items) return 0;
+    FragOut o{fb.keys, fb.cap, key_len_bits(m.high), fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, fb.long_cap, fb.long_count,
+              fb.error, fb.q_a, fb.q_b, fb.q_cap, fb.q_count};
+    const bool lut_in_smem = m.k <= 6;
+    uint32_t hist_s_n = frag_hist_bins(m);
+    size_t smem = fused_smem_bytes(m, cap_entries, lut_in_smem, hist_s_n);
+    if (smem > 227 * 1024) { hist_s_n = 0; smem = fused_smem_bytes(m, cap_entries, lut_in_smem, 0); }
+    if (smem > 227 * 1024) return RLSIM_E_UNSUPPORTED;
+    cudaFuncSetAttribute(k_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused, FUSED_THREADS, smem);
+    if (per_sm < 1) per_sm = 1;
+    const uint32_t blocks = std::min<uint32_t>(n_items, (uint32_t)(sm_count * per_sm));
+    cudaMemsetAsync(work, 0, sizeof(unsigned int), st);
+    FusedArgs a{items, n_items, cap_entries, work, wq_f, wq_r, kmax_bits, lut_in_smem ? 1 : 0, fallback};
+    k_fused<<<blocks, FUSED_THREADS, smem, st>>>(m, tr, o, a, hist_s_n);
+    return 0;
+}
+int launch_fused_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t n_long,
+                      uint32_t cap_entries, const uint32_t *wq_f, const uint32_t *wq_r, const unsigned long long *kmax_bits, int *fallback) {
+    if (!n_long) return 0;
+    FragOut o{fb.keys, fb.cap, key_len_bits(m.high), fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, n_long, nullptr,
+              fb.error, fb.q_a, fb.q_b, fb.q_cap, fb.q_count};
+    const size_t smem = (size_t)cap_entries * 4 + ((size_t)cap_entries / 64 + 2 * FUSED_MAX_TR) * 8 + (size_t)FLONG_BREAKS * 4 + 16;
+    if (smem > 227 * 1024) return RLSIM_E_UNSUPPORTED;
+    cudaFuncSetAttribute(k_fused_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    FusedArgs a{nullptr, 0, cap_entries, nullptr, wq_f, wq_r, kmax_bits, 0, fallback};
+    k_fused_long<<<n_long, FLONG_THREADS, smem, st>>>(m, tr, o, a, n_long);
     return 0;
 }
 

@@ -26,6 +26,16 @@ int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr
                     const FragBuffers &fb);
 int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint64_t n_q);
 int launch_fragment_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t n_long);
+// fused prefix + fragmentation (after_prim / after_prim_double): prefix sums in shared memory
+struct FusedItem { uint32_t t0, t1; uint64_t g0, g1; };  // transcripts [t0, t1), global molecules [g0, g1)
+constexpr uint32_t FUSED_CAP_SMALL = 20480;   // prefix entries a CTA holds, two CTAs per SM
+constexpr uint32_t FUSED_CAP_LARGE = 49152;   // ... one CTA per SM (transcripts up to 49 k bases)
+constexpr uint32_t FUSED_LONG_BREAKS = 1024;  // expected breakpoints per molecule the deferred-molecule kernel is trusted with
+int launch_fused(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, const FusedItem *items,
+                 uint32_t n_items, uint32_t cap_entries, unsigned int *work, const uint32_t *wq_f, const uint32_t *wq_r,
+                 const unsigned long long *kmax_bits, int *fallback, int sm_count);
+int launch_fused_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t n_long,
+                      uint32_t cap_entries, const uint32_t *wq_f, const uint32_t *wq_r, const unsigned long long *kmax_bits, int *fallback);
 
 // k_pcr.cu
 struct DevSpecies {

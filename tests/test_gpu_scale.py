@@ -296,3 +296,54 @@ def test_pageable_and_pinned_buffers_agree(gpu, monkeypatch):
     for k in ("tr", "start", "end", "minus", "id"):
         assert np.array_equal(ref[k].astype(np.int64), into[k].numpy().astype(np.int64) & (0xffffffff if k != "id" else -1)), k
     assert staged.fasta(names) == pinned.fasta(names)
+
+
+# ---- fused prefix + fragmentation kernel (prefix sums in shared memory) --------------------------------------------
+def test_fused_path_variants(oracle, gpu, monkeypatch):
+    """after_prim / after_prim_double keep the priming prefix sums in shared memory (k_fused).  Same fragments as the HBM
+    path (RLSIM_NO_FUSED) and as the oracle for: the small class, items split by molecule range (a heavily expressed
+    transcript), the large class with deferred molecules (k_fused_long), explicit reverse arrays of transcripts with
+    letters outside ACGT (sub-batching), and a transcript whose sums do not fit (fallback to the HBM path)."""
+    def both(argv, names, seqs, levels, expect_fused=True, eager=True):
+        h = _compare_records(oracle, gpu, argv, names, seqs, levels)
+        assert bool(int(h.stats().flags) & gpu.F_FUSED) == expect_fused, argv
+        monkeypatch.setenv("RLSIM_NO_FUSED", "1")
+        h2 = util.run_gpu(gpu, util.parse(argv), names, seqs, levels)
+        monkeypatch.delenv("RLSIM_NO_FUSED")
+        assert not (int(h2.stats().flags) & gpu.F_FUSED)
+        for k in ("tr", "start", "end", "count0", "count"):
+            assert np.array_equal(h.species()[k], h2.species()[k]), k
+        for kind in (gpu.H_AFTER_FRAG, gpu.H_POLYA):
+            assert h.hist_dict(kind, 1 << 16) == h2.hist_dict(kind, 1 << 16)
+        if not eager:
+            return
+        monkeypatch.setenv("RLSIM_NO_EAGER", "1")  # the monolithic launch over all items
+        h3 = util.run_gpu(gpu, util.parse(argv), names, seqs, levels)
+        monkeypatch.delenv("RLSIM_NO_EAGER")
+        assert bool(int(h3.stats().flags) & gpu.F_FUSED) == expect_fused and not (int(h3.stats().flags) & gpu.F_EAGER)
+        for k in ("tr", "start", "end", "count0", "count"):
+            assert np.array_equal(h.species()[k], h3.species()[k]), k
+
+    # small class, many transcripts per item, one transcript far beyond 4096 molecules, zero-expression gaps
+    names, seqs, levels = util.synth_transcriptome(300, seed=41, mean_len=1500, hi=9000, total_molecules=60000, non_acgt=0.0005)
+    levels = list(levels)
+    levels[5] = 25000
+    levels[6] = levels[7] = 0
+    both(["-n", "50000", "-c", "4", "-si", "12", "-f", "after_prim_double"], names, seqs, levels)
+    both(["-n", "50000", "-c", "4", "-si", "12", "-f", "after_prim"], names, seqs, levels)
+    # large class (12-40 kb) + deferred molecules: default -d asks for L/378 breakpoints
+    names, seqs, levels = util.synth_transcriptome(24, seed=42, mean_len=22000, sigma=0.4, lo=11000, hi=45000, total_molecules=1500)
+    both(["-n", "30000", "-c", "3", "-si", "13", "-f", "after_prim_double"], names, seqs, levels)
+    both(["-n", "30000", "-c", "3", "-si", "13", "-f", "after_prim_double:150"], names, seqs, levels)
+    # letters outside ACGT in a 20 kb transcript: explicit reverse arrays, still fits the large class
+    seqs = list(seqs)
+    lens = [len(x) for x in seqs]
+    t_mid = int(np.argmin([abs(l - 20000) for l in lens]))
+    b = bytearray(seqs[t_mid]); b[5000:5003] = b"NRN"; seqs[t_mid] = bytes(b)
+    if lens[t_mid] <= 24000:
+        both(["-n", "30000", "-c", "3", "-si", "14", "-f", "after_prim_double"], names, seqs, levels)
+    # ... and in a > 24.5 kb one: forward + reverse arrays exceed shared memory -> the library falls back to the HBM path
+    t_big = int(np.argmax(lens))
+    assert lens[t_big] > 25000
+    b = bytearray(seqs[t_big]); b[100] = ord("N"); seqs[t_big] = bytes(b)
+    both(["-n", "30000", "-c", "3", "-si", "15", "-f", "after_prim_double"], names, seqs, levels, expect_fused=False, eager=False)
