@@ -461,38 +461,64 @@ struct FusedBatch {                    // the sub-batch being processed (shared 
 
 __device__ __forceinline__ uint32_t pad64(uint32_t x) { return (x + 63u) & ~63u; }
 
-// thread 0: take transcripts from t_cur while their prefix sums fit `cap` entries
-__device__ void fused_pack(FusedBatch &B, const DevModel &m, const DevTranscripts &tr, uint32_t t_cur, uint32_t t_end,
-                           uint32_t cap, bool dbl) {
-    uint32_t used = 0, cused = 0, n = 0, np = 0, ntask = 0, t = t_cur;
-    B.fail = 0;
-    while (t < t_end && n < FUSED_MAX_TR) {
-        if (tr.expr[t] == 0) { t++; continue; }  // pool.go:104: never fragmented
-        const uint32_t L = tr.len[t], k = (uint32_t)m.k;
-        const bool dirty = tr.dirty[t] != 0;
-        const bool mirror = dbl && tr.sym && !dirty;
-        // forward arrays hold one more window in symmetric mode (the first window of the reverse profile)
-        const uint32_t entF = L >= k + (tr.sym ? 0u : 1u) ? L - k + (tr.sym ? 1u : 0u) : 0u;
-        const uint32_t entR = (dbl && !mirror && L > k) ? L - k : 0u;
-        const uint32_t eF = pad64(entF), eR = pad64(entR);
-        if (used + eF + eR > cap) {
-            if (n == 0) B.fail = 1;  // a single transcript that does not fit: the host reruns on the HBM path
-            break;
-        }
-        B.t[n] = t; B.L[n] = L; B.off[n] = tr.off[t]; B.mol[n] = tr.mol_off[t]; B.mirror[n] = mirror ? 1u : 0u;
-        B.fo[n] = used; B.co[n] = cused;
-        B.p_slot[np] = n; B.p_rev[np] = 0; B.p_ent[np] = entF; B.p_task0[np] = ntask; ntask += (entF + FUSED_SEG - 1) / FUSED_SEG; np++;
-        used += eF; cused += eF / 64 + 1;
-        if (dbl && !mirror) {
-            B.ro[n] = used; B.rco[n] = cused;
-            B.p_slot[np] = n; B.p_rev[np] = 1; B.p_ent[np] = entR; B.p_task0[np] = ntask; ntask += (entR + FUSED_SEG - 1) / FUSED_SEG; np++;
-            used += eR; cused += eR / 64 + 1;
-        } else { B.ro[n] = 0xffffffffu; B.rco[n] = 0xffffffffu; }
-        n++; t++;
+// Warp 0 takes transcripts from t_cur while their prefix sums fit `cap` entries: lane i looks at transcript t_cur + i, warp
+// scans give every taken transcript its offsets.  (A serial loop here costs more than the prefix sums themselves.)
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t u = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (uint32_t)d) v += u;
     }
-    if (n) B.mol[n] = tr.mol_off[B.t[n - 1] + 1];
-    B.p_task0[np] = ntask;
-    B.n = n; B.t_next = t; B.nprof = np; B.ntask = ntask;
+    return v;
+}
+__device__ void fused_pack(FusedBatch &B, const DevModel &m, const DevTranscripts &tr, uint32_t t_cur, uint32_t t_end,
+                           uint32_t cap, bool dbl, uint32_t lane) {
+    const uint32_t t = t_cur + lane, k = (uint32_t)m.k;
+    const bool in = t < t_end;
+    const bool expressed = in && tr.expr[t] != 0;  // pool.go:104: the others are never fragmented
+    uint32_t L = 0, entF = 0, entR = 0;
+    bool mirror = false;
+    if (expressed) {
+        L = tr.len[t];
+        mirror = dbl && tr.sym && tr.dirty[t] == 0;
+        // forward arrays hold one more window in symmetric mode (the first window of the reverse profile)
+        entF = L >= k + (tr.sym ? 0u : 1u) ? L - k + (tr.sym ? 1u : 0u) : 0u;
+        entR = (dbl && !mirror && L > k) ? L - k : 0u;
+    }
+    const bool has_rev = expressed && dbl && !mirror;
+    const uint32_t eF = pad64(entF), eR = pad64(entR), need = expressed ? eF + eR : 0u;
+    const uint32_t pre = warp_incl_scan(need, lane);
+    // the batch ends before the first expressed transcript whose sums no longer fit
+    const unsigned over = __ballot_sync(0xffffffffu, expressed && pre > cap);
+    const uint32_t cut = over ? (uint32_t)__ffs(over) - 1u : 32u;
+    const bool take = expressed && lane < cut;
+    const unsigned takes = __ballot_sync(0xffffffffu, take);
+    const uint32_t n = __popc(takes), slot = __popc(takes & ((1u << lane) - 1u));
+    const uint32_t cs = take ? eF / 64 + 1 + (has_rev ? eR / 64 + 1 : 0u) : 0u;
+    const uint32_t cpre = warp_incl_scan(cs, lane);
+    const uint32_t np_l = take ? (has_rev ? 2u : 1u) : 0u;
+    const uint32_t ppre = warp_incl_scan(np_l, lane);
+    const uint32_t tf = (entF + FUSED_SEG - 1) / FUSED_SEG, trv = (entR + FUSED_SEG - 1) / FUSED_SEG;
+    const uint32_t nt_l = take ? tf + (has_rev ? trv : 0u) : 0u;
+    const uint32_t tpre = warp_incl_scan(nt_l, lane);
+    if (take) {
+        const uint32_t fo = pre - need, co = cpre - cs, p0 = ppre - np_l, k0 = tpre - nt_l;
+        B.t[slot] = t; B.L[slot] = L; B.off[slot] = tr.off[t]; B.mol[slot] = tr.mol_off[t]; B.mirror[slot] = mirror ? 1u : 0u;
+        B.fo[slot] = fo; B.co[slot] = co;
+        B.p_slot[p0] = slot; B.p_rev[p0] = 0; B.p_ent[p0] = entF; B.p_task0[p0] = k0;
+        if (has_rev) {
+            B.ro[slot] = fo + eF; B.rco[slot] = co + eF / 64 + 1;
+            B.p_slot[p0 + 1] = slot; B.p_rev[p0 + 1] = 1; B.p_ent[p0 + 1] = entR; B.p_task0[p0 + 1] = k0 + tf;
+        } else { B.ro[slot] = 0xffffffffu; B.rco[slot] = 0xffffffffu; }
+        if (slot + 1 == n) B.mol[n] = tr.mol_off[t + 1];
+    }
+    if (lane == 31) { B.nprof = ppre; B.ntask = tpre; B.p_task0[ppre] = tpre; }
+    if (lane == 0) {
+        B.n = n;
+        B.t_next = min(t_end, t_cur + cut);
+        // nothing taken although an expressed transcript is waiting: it does not fit alone - the host reruns on the HBM path
+        B.fail = (n == 0 && over != 0u) ? 1 : 0;
+    }
 }
 
 // pass 1 (all warps): in-block sums of every 1024-entry segment + raw block totals into coarse[b + 1]
@@ -573,13 +599,14 @@ k_fused(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, FusedA
     uint64_t *coarse_s = reinterpret_cast<uint64_t *>(fine_s + a.cap_entries);
     uint32_t *lut_s = reinterpret_cast<uint32_t *>(coarse_s + (a.cap_entries / 64 + 2 * FUSED_MAX_TR));
     const uint32_t nlut = a.lut_in_smem ? (1u << (2 * m.k)) : 0u;
-    unsigned int *hist_s = lut_s + 2 * nlut;  // [hist_s_n] after-fragmentation bins from `low`, then [polya_max+1]
-    unsigned int *hist_pa = hist_s + hist_s_n;
     const bool dbl = m.method == RLSIM_AFTER_PRIM_DOUBLE;
-    const bool need_r_lut = dbl;  // explicit reverse profiles (dirty transcripts / asymmetric table)
-    for (uint32_t i = threadIdx.x; i < nlut; i += FUSED_THREADS) { lut_s[i] = a.wq_f[i]; if (need_r_lut) lut_s[nlut + i] = a.wq_r[i]; }
+    // a symmetric table (w[c] == w[rc(c)]) serves explicit reverse profiles too; otherwise the reverse table sits beside it
+    const bool two_luts = dbl && !tr.sym;
+    unsigned int *hist_s = lut_s + (two_luts ? 2 : 1) * nlut;  // [hist_s_n] after-fragmentation bins from `low`, then [polya_max+1]
+    unsigned int *hist_pa = hist_s + hist_s_n;
+    for (uint32_t i = threadIdx.x; i < nlut; i += FUSED_THREADS) { lut_s[i] = a.wq_f[i]; if (two_luts) lut_s[nlut + i] = a.wq_r[i]; }
     for (uint32_t i = threadIdx.x; i < hist_s_n + m.polya_max + 1; i += FUSED_THREADS) hist_s[i] = 0;
-    const uint32_t *lut_f = nlut ? lut_s : a.wq_f, *lut_r = nlut ? lut_s + nlut : a.wq_r;
+    const uint32_t *lut_f = nlut ? lut_s : a.wq_f, *lut_r = nlut ? (two_luts ? lut_s + nlut : lut_s) : a.wq_r;
     const double scale = PFX_SCALE / __longlong_as_double((long long)*a.kmax_bits);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __syncthreads();
@@ -591,11 +618,12 @@ k_fused(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, FusedA
         const FusedItem it = a.items[item];
         uint32_t t_cur = it.t0;
         while (t_cur < it.t1) {
-            if (threadIdx.x == 0) fused_pack(B, m, tr, t_cur, it.t1, a.cap_entries, dbl);
+            __syncthreads();  // everyone is done with the previous sub-batch: its table and arrays may be rebuilt
+            if (warp == 0) fused_pack(B, m, tr, t_cur, it.t1, a.cap_entries, dbl, lane);
             __syncthreads();
             if (B.fail) { if (threadIdx.x == 0) atomicExch(a.fallback, 1); break; }
             t_cur = B.t_next;
-            if (B.n == 0) break;  // nothing expressed in the rest of the item
+            if (B.n == 0) continue;  // a window of unexpressed transcripts
             const uint64_t gs = max(it.g0, B.mol[0]), ge = min(it.g1, B.mol[B.n]);
             if (gs < ge) {
                 fused_prefix_pass1(B, m, tr, fine_s, coarse_s, lut_f, lut_r, scale, warp, FUSED_WARPS, lane);
@@ -637,7 +665,6 @@ k_fused(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, FusedA
                     }
                 }
             }
-            __syncthreads();  // the arrays are rebuilt for the next sub-batch
         }
         __syncthreads();
     }
@@ -664,7 +691,7 @@ k_fused_long(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, F
     const uint32_t t = o.long_list[slot].x;
     const uint64_t mol = (uint64_t)o.long_list[slot].y | ((uint64_t)o.long_hi[slot] << 32);
     const bool dbl = m.method == RLSIM_AFTER_PRIM_DOUBLE;
-    if (threadIdx.x == 0) fused_pack(B, m, tr, t, t + 1, a.cap_entries, dbl);
+    if (threadIdx.x < 32) fused_pack(B, m, tr, t, t + 1, a.cap_entries, dbl, threadIdx.x);
     __syncthreads();
     if (B.fail || B.n != 1) { if (threadIdx.x == 0) atomicExch(a.fallback, 1); return; }
     const double scale = PFX_SCALE / __longlong_as_double((long long)*a.kmax_bits);
@@ -752,8 +779,8 @@ int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &t
 }
 
 // ---- fused path launches.  smem_optin = the device's opt-in shared memory per block.
-size_t fused_smem_bytes(const DevModel &m, uint32_t cap_entries, bool lut_in_smem, uint32_t hist_s_n) {
-    return (size_t)cap_entries * 4 + ((size_t)cap_entries / 64 + 2 * FUSED_MAX_TR) * 8 + (lut_in_smem ? ((size_t)8 << (2 * m.k)) : 0) +
+size_t fused_smem_bytes(const DevModel &m, uint32_t cap_entries, int lut_tables, uint32_t hist_s_n) {
+    return (size_t)cap_entries * 4 + ((size_t)cap_entries / 64 + 2 * FUSED_MAX_TR) * 8 + (size_t)lut_tables * ((size_t)4 << (2 * m.k)) +
            ((size_t)hist_s_n + m.polya_max + 1) * 4 + 16;
 }
 int launch_fused(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, const FusedItem *items,
@@ -762,10 +789,12 @@ int launch_fused(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, c
     if (!n_items) return 0;
     FragOut o{fb.keys, fb.cap, key_len_bits(m.high), fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, fb.long_cap, fb.long_count,
               fb.error, fb.q_a, fb.q_b, fb.q_cap, fb.q_count};
-    const bool lut_in_smem = m.k <= 6;
+    bool lut_in_smem = m.k <= 6;
+    const int tables = (m.method == RLSIM_AFTER_PRIM_DOUBLE && !tr.sym) ? 2 : 1;
     uint32_t hist_s_n = frag_hist_bins(m);
-    size_t smem = fused_smem_bytes(m, cap_entries, lut_in_smem, hist_s_n);
-    if (smem > 227 * 1024) { hist_s_n = 0; smem = fused_smem_bytes(m, cap_entries, lut_in_smem, 0); }
+    size_t smem = fused_smem_bytes(m, cap_entries, lut_in_smem ? tables : 0, hist_s_n);
+    if (smem > 227 * 1024 && lut_in_smem) { lut_in_smem = false; smem = fused_smem_bytes(m, cap_entries, 0, hist_s_n); }
+    if (smem > 227 * 1024) { hist_s_n = 0; smem = fused_smem_bytes(m, cap_entries, 0, 0); }
     if (smem > 227 * 1024) return RLSIM_E_UNSUPPORTED;
     cudaFuncSetAttribute(k_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 1;
