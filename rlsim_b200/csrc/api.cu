@@ -308,20 +308,79 @@ int build_fused_items(rlsim_handle *h, uint32_t t0, uint32_t t1) {
     return 0;
 }
 
-// queue the fused kernels for the transcripts [t0, t1) (launches only; the caller reads the counters)
-int launch_fused_range(rlsim_handle *h, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t t0, uint32_t t1) {
+// Items of the warp kernel for [t0, t1): one transcript (and at most W_MAX molecules) each, in three lists by the size of
+// the per-warp slice the transcript needs.
+int build_warp_items(rlsim_handle *h, uint32_t t0, uint32_t t1) {
+    const int key = 4 | (h->p.frag_method == RLSIM_AFTER_PRIM_DOUBLE ? 1 : 0);
+    if (h->fitems_key == key && h->fitems_t0 == t0 && h->fitems_t1 == t1) return 0;  // still on the device
+    constexpr uint64_t W_MAX = 512;
+    for (auto &v : h->h_witems) v.clear();
+    const uint64_t *mo = h->h_mol_off.data();
+    size_t total = 0;
+    for (uint32_t t = t0; t < t1; t++) {
+        if (!h->h_expr[t]) continue;
+        const uint64_t e1 = ((uint64_t)h->h_len[t] + 63) & ~63ull;
+        PinVec<FusedItem> &dst = h->h_witems[e1 <= FUSED_WARP_CAP_S ? 0 : e1 <= FUSED_WARP_CAP_M ? 1 : 2];
+        for (uint64_t g = mo[t]; g < mo[t + 1]; g += W_MAX) { dst.push_back(FusedItem{t, t + 1, g, std::min<uint64_t>(g + W_MAX, mo[t + 1])}); total++; }
+    }
+    for (int c = 0; c < 3; c++) {
+        CK(h, h->d_witems[c].ensure(h->h_witems[c].size() + 1));
+        if (h->h_witems[c].size())
+            CK(h, cudaMemcpyAsync(h->d_witems[c].p, h->h_witems[c].data(), h->h_witems[c].size() * sizeof(FusedItem), cudaMemcpyHostToDevice, h->st));
+    }
+    CK(h, h->d_redo.ensure(total + 1));
+    h->fitems_key = key; h->fitems_t0 = t0; h->fitems_t1 = t1;
+    return 0;
+}
+
+// Run the fused kernels over the transcripts [t0, t1) up to (not including) the deferred molecules: on return the host
+// knows how many molecules were deferred (*n_long) and whether a transcript did not fit shared memory (*fell_back: the
+// caller reruns the range on the HBM path).
+int run_fused_range(rlsim_handle *h, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t t0, uint32_t t1,
+                    unsigned int *n_long, int *fell_back) {
     int rc;
     if ((rc = ensure_lut(h))) return rc;
     DevTranscripts trs = tr;
     trs.sym = h->lut_sym && h->want_mirror ? 1 : 0;  // ensure_lut may just have established it
-    if ((rc = build_fused_items(h, t0, t1))) return rc;
     int *fallback = reinterpret_cast<int *>(h->d_work.p + 6);
-    CK(h, cudaMemsetAsync(fallback, 0, 4, h->st));
-    if ((rc = launch_fused(h->st, m, trs, fb, h->d_fitems_s.p, (uint32_t)h->h_fitems_s.size(), FUSED_CAP_SMALL, h->d_work.p + 4, h->d_wq_f.p,
-                           h->d_wq_r.p, h->d_kmax.p, fallback, h->sm_count))) return rc;
-    if ((rc = launch_fused(h->st, m, trs, fb, h->d_fitems_l.p, (uint32_t)h->h_fitems_l.size(), FUSED_CAP_LARGE, h->d_work.p + 5, h->d_wq_f.p,
-                           h->d_wq_r.p, h->d_kmax.p, fallback, h->sm_count))) return rc;
-    h->launches[RLSIM_T_FRAGMENT] += (h->h_fitems_s.size() ? 1 : 0) + (h->h_fitems_l.size() ? 1 : 0);
+    unsigned int *redo_count = h->d_work.p + 7;
+    CK(h, cudaMemsetAsync(h->d_work.p + 6, 0, 8, h->st));
+    const bool warp_kernel = trs.sym && h->p.kmer_len <= 6 && !getenv("RLSIM_FUSED_CTA");
+    unsigned int n_redo = 0;
+    if (warp_kernel) {
+        if ((rc = build_warp_items(h, t0, t1))) return rc;
+        static const uint32_t caps[3] = {FUSED_WARP_CAP_S, FUSED_WARP_CAP_M, FUSED_WARP_CAP_L};
+        static const int warps[3] = {8, 8, 4};
+        for (int c = 0; c < 3; c++) {
+            if (!h->h_witems[c].size()) continue;
+            if ((rc = launch_fused_warp(h->st, m, trs, fb, h->d_witems[c].p, (uint32_t)h->h_witems[c].size(), caps[c], warps[c], h->d_work.p + 3 + c,
+                                        h->d_wq_f.p, h->d_redo.p, redo_count, (uint32_t)h->d_redo.n, h->sm_count))) return rc;
+            h->launches[RLSIM_T_FRAGMENT]++;
+        }
+        CK(h, cudaMemcpyAsync(h->pin, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaMemcpyAsync(h->pin + 7, h->d_work.p + 6, 8, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaStreamSynchronize(h->st));
+        n_redo = reinterpret_cast<unsigned int *>(h->pin + 7)[1];
+        if (n_redo) {  // transcripts with letters outside ACGT: explicit reverse sums, CTA-cooperative kernel
+            if ((rc = launch_fused(h->st, m, trs, fb, h->d_redo.p, n_redo, FUSED_CAP_LARGE, h->d_work.p + 3, h->d_wq_f.p, h->d_wq_r.p,
+                                   h->d_kmax.p, fallback, h->sm_count))) return rc;
+            h->launches[RLSIM_T_FRAGMENT]++;
+        }
+    } else {
+        if ((rc = build_fused_items(h, t0, t1))) return rc;
+        if ((rc = launch_fused(h->st, m, trs, fb, h->d_fitems_s.p, (uint32_t)h->h_fitems_s.size(), FUSED_CAP_SMALL, h->d_work.p + 4, h->d_wq_f.p,
+                               h->d_wq_r.p, h->d_kmax.p, fallback, h->sm_count))) return rc;
+        if ((rc = launch_fused(h->st, m, trs, fb, h->d_fitems_l.p, (uint32_t)h->h_fitems_l.size(), FUSED_CAP_LARGE, h->d_work.p + 5, h->d_wq_f.p,
+                               h->d_wq_r.p, h->d_kmax.p, fallback, h->sm_count))) return rc;
+        h->launches[RLSIM_T_FRAGMENT] += (h->h_fitems_s.size() ? 1 : 0) + (h->h_fitems_l.size() ? 1 : 0);
+    }
+    if (!warp_kernel || n_redo) {
+        CK(h, cudaMemcpyAsync(h->pin, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaMemcpyAsync(h->pin + 7, h->d_work.p + 6, 4, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaStreamSynchronize(h->st));
+    }
+    *n_long = *reinterpret_cast<unsigned int *>(h->pin);
+    *fell_back = *reinterpret_cast<int *>(h->pin + 7);
     return 0;
 }
 
@@ -358,15 +417,19 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
     FragBuffers fb{h->d_keys.p, h->d_keys.n, h->d_counters.p, h->d_hist_frag.p, h->d_hist_polya.p, h->d_long_list.p, h->d_long_hi.p,
                    long_cap, h->d_long_count.p, h->d_error.p, h->d_q_a.p, h->d_q_b.p, h->d_q_a.n, h->d_counters.p + 2};
     const bool fused = fused_range_ok(h, t0, t1);
-    if (fused) { if ((rc = launch_fused_range(h, m, tr, fb, t0, t1))) { h->eager_failed = true; return 0; } }
-    else if ((rc = launch_fragment(h->st, m, tr, g0, g1, fb))) { h->eager_failed = true; return 0; }
-    CK(h, cudaMemcpyAsync(h->pin, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
-    CK(h, cudaMemcpyAsync(h->pin + 1, h->d_counters.p + 2, 8, cudaMemcpyDeviceToHost, h->st));
-    CK(h, cudaMemcpyAsync(h->pin + 7, h->d_work.p + 6, 4, cudaMemcpyDeviceToHost, h->st));
-    CK(h, cudaStreamSynchronize(h->st));
-    const unsigned int n_long = *reinterpret_cast<unsigned int *>(h->pin);
-    const unsigned long long n_q = fused ? 0ull : h->pin[1];
-    if (fused && *reinterpret_cast<int *>(h->pin + 7)) { h->fused_disabled = true; h->eager_failed = true; return 0; }
+    unsigned int n_long = 0;
+    unsigned long long n_q = 0;
+    if (fused) {
+        int fell_back = 0;
+        if ((rc = run_fused_range(h, m, tr, fb, t0, t1, &n_long, &fell_back)) || fell_back) { h->fused_disabled = true; h->eager_failed = true; return 0; }
+    } else {
+        if ((rc = launch_fragment(h->st, m, tr, g0, g1, fb))) { h->eager_failed = true; return 0; }
+        CK(h, cudaMemcpyAsync(h->pin, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaMemcpyAsync(h->pin + 1, h->d_counters.p + 2, 8, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaStreamSynchronize(h->st));
+        n_long = *reinterpret_cast<unsigned int *>(h->pin);
+        n_q = h->pin[1];
+    }
     tt1 = now_ms();
     // test hook: pretend the estimate of group number RLSIM_EAGER_TEST_FAIL (0-based) was too small
     const char *fail_at = getenv("RLSIM_EAGER_TEST_FAIL");
@@ -1060,19 +1123,18 @@ int rlsim_fragment(rlsim_handle *h) {
                        long_cap, h->d_long_count.p, h->d_error.p, h->d_q_a.p, h->d_q_b.p, q_cap, h->d_counters.p + 2};
         const bool fused = fused_range_ok(h, 0, n);
         StageTimer tm(h, RLSIM_T_FRAGMENT, fused ? 0 : 1);
-        if (fused) {
-            if ((rc = launch_fused_range(h, m, tr, fb, 0, n))) { tm.stop(); h->fused_disabled = true; attempt--; if ((rc = finalize(h))) return rc; tr = make_tr(h); continue; }
-        } else {
-            rc = launch_fragment(h->st, m, tr, 0, h->n_mol, fb);
-            if (rc) FAIL(h, rc, "fragmentation launch configuration unsupported (poly(A) maximum too large)");
-        }
         unsigned int n_long = 0;
         unsigned long long n_q = 0;
         int fell_back = 0;
-        CK(h, cudaMemcpyAsync(&n_long, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
-        CK(h, cudaMemcpyAsync(&n_q, h->d_counters.p + 2, 8, cudaMemcpyDeviceToHost, h->st));
-        if (fused) CK(h, cudaMemcpyAsync(&fell_back, h->d_work.p + 6, 4, cudaMemcpyDeviceToHost, h->st));
-        CK(h, cudaStreamSynchronize(h->st));
+        if (fused) {
+            if ((rc = run_fused_range(h, m, tr, fb, 0, n, &n_long, &fell_back))) { tm.stop(); h->fused_disabled = true; attempt--; if ((rc = finalize(h))) return rc; tr = make_tr(h); continue; }
+        } else {
+            rc = launch_fragment(h->st, m, tr, 0, h->n_mol, fb);
+            if (rc) FAIL(h, rc, "fragmentation launch configuration unsupported (poly(A) maximum too large)");
+            CK(h, cudaMemcpyAsync(&n_long, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
+            CK(h, cudaMemcpyAsync(&n_q, h->d_counters.p + 2, 8, cudaMemcpyDeviceToHost, h->st));
+            CK(h, cudaStreamSynchronize(h->st));
+        }
         if (n_long > long_cap) { tm.stop(); long_cap = n_long + 1024; continue; }
         if (fused && n_long && !fell_back) {
             DevTranscripts trs = tr; trs.sym = h->lut_sym && h->want_mirror ? 1 : 0;

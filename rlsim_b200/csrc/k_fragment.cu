@@ -99,7 +99,63 @@ __device__ __forceinline__ uint32_t prime_search(const Profile &pf, uint32_t ple
     return base + q + c;
 }
 
-__device__ __forceinline__ bool priming(const PxStream &iv, uint32_t block, const Profile &pf, uint32_t proflen,
+// ---------------------------------------------------------------------------------------------------------------------
+// Compact profile: what one WARP keeps in shared memory for one transcript (k_fused_warp).  0.625 B per entry instead of
+// the 4.1 B of the two-level arrays, so that 40 warps per SM each hold their own transcript:
+//   codes  : the 2-bit packed bases themselves (16 per word, copied from the transcript store)
+//   gsum   : per group of 16 entries, the sum of the weights from the start of its 64-entry block to the group's end
+//   coarse : per 64-entry block, the sum of everything before it (coarse[nblk] = total)
+// A prefix sum P(i) is coarse + group sum + at most 15 weights recomputed from the codes and the shared-memory LUT; the
+// search walks one group.  Same integers as the materialised sums, hence the same draws.  Transcripts with letters
+// outside ACGT do not take this path (their windows need the byte-level affinity and explicit reverse sums).
+struct CProfile {
+    const uint32_t *codes, *gsum;
+    const uint64_t *coarse;
+    const uint32_t *lut;
+    uint32_t kmask;
+    // weights of the entries [16 grp, 16 grp + n) summed; n <= 16
+    __device__ __forceinline__ uint32_t partial(uint32_t grp, uint32_t n) const {
+        if (!n) return 0;
+        const uint64_t win = (uint64_t)codes[grp] | ((uint64_t)codes[grp + 1] << 32);  // 32 bases from 16 grp: 16 windows of k <= 17
+        uint32_t acc = 0;
+#pragma unroll 4
+        for (uint32_t j = 0; j < n; j++) acc += lut[(uint32_t)(win >> (2 * j)) & kmask];
+        return acc;
+    }
+    __device__ __forceinline__ uint64_t P(uint32_t i) const {
+        const uint32_t grp = i >> 4;
+        uint64_t c = coarse[i >> PFX_BLOCK_SHIFT];
+        if (grp & 3u) c += gsum[grp - 1];
+        return c + partial(grp, i & 15u);
+    }
+};
+
+// smallest i in [start, end) with P(i+1) > tgt, given P(start) <= tgt < P(end)
+__device__ __forceinline__ uint32_t prime_search(const CProfile &pf, uint32_t plen, uint32_t start, uint32_t end, uint64_t tgt) {
+    uint32_t lo = start >> PFX_BLOCK_SHIFT, hi = ((end - 1) >> PFX_BLOCK_SHIFT) + 1;  // coarse[lo] <= tgt < coarse[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (pf.coarse[mid] <= tgt) lo = mid; else hi = mid;
+    }
+    const uint32_t r = (uint32_t)(tgt - pf.coarse[lo]);  // < block sum
+    uint32_t grp = lo << 2, before = 0;
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+        const uint32_t s = pf.gsum[(lo << 2) + g];
+        if (s <= r) { grp = (lo << 2) + g + 1; before = s; }  // group sums are nondecreasing inside the block
+    }
+    const uint32_t rem = r - before;
+    const uint64_t win = (uint64_t)pf.codes[grp] | ((uint64_t)pf.codes[grp + 1] << 32);
+    uint32_t acc = 0, j = 0;
+    for (; j < 15; j++) {
+        acc += pf.lut[(uint32_t)(win >> (2 * j)) & pf.kmask];
+        if (acc > rem) break;
+    }
+    return (grp << 4) + j;
+}
+
+template <class PF>
+__device__ __forceinline__ bool priming(const PxStream &iv, uint32_t block, const PF &pf, uint32_t proflen,
                                         uint32_t start, uint32_t end, uint32_t &res) {
     if (end > proflen) end = proflen;
     if (start >= end) { res = 0; return true; }
@@ -114,12 +170,13 @@ __device__ __forceinline__ bool priming(const PxStream &iv, uint32_t block, cons
 // reverse-complement symmetric: reverse entry j is forward window n - j (n = proflen), so with W = forward prefix sums
 // over the n + 1 windows, P_rev(j) = W(n+1) - W(n+1-j).  "Smallest j in [s, e) with P_rev(j+1) > P_rev(s) + u" becomes
 // "smallest x in [n-e+1, n-s+1) with W(x+1) > W(n-s+1) - u - 1", j = n - x: no reverse arrays are needed.
-__device__ __forceinline__ bool priming_reverse(const PxStream &iv, uint32_t block, const Profile &pfwd, const Profile &prev,
+template <class PF>
+__device__ __forceinline__ bool priming_reverse(const PxStream &iv, uint32_t block, const PF &pfwd, const PF &prev,
                                                 bool mirror, uint32_t proflen, uint32_t start, uint32_t end, uint32_t &res) {
     if (end > proflen) end = proflen;
     if (start >= end) { res = 0; return true; }
     // one search serves both representations (a single inlined copy keeps the register count of k_intervals down)
-    const Profile pf = mirror ? pfwd : prev;
+    const PF pf = mirror ? pfwd : prev;
     const uint32_t plen = mirror ? proflen + 1 : proflen;
     const uint32_t lo = mirror ? proflen - end + 1 : start, hi = mirror ? proflen - start + 1 : end;
     const uint64_t plo = pf.P(lo), phi = pf.P(hi);
@@ -168,15 +225,18 @@ __device__ __forceinline__ void enqueue(const FragOut &o, uint32_t t, uint64_t m
     }
 }
 
-struct MolCtx {
+template <class PF>
+struct MolCtxT {
     uint32_t t, tg, L, proflen;
     uint64_t off;
-    Profile Pf, Pr;
+    PF Pf, Pr;
     bool mirror;  // reverse profile = forward arrays read backwards (symmetric table, no non-ACGT letter)
 };
+using MolCtx = MolCtxT<Profile>;
 
 // One interval of the after_* methods, fragmentor.go:132-175
-__device__ __forceinline__ void after_interval(const DevModel &m, const MolCtx &c, const PxStream &iv, uint32_t i,
+template <class PF>
+__device__ __forceinline__ void after_interval(const DevModel &m, const MolCtxT<PF> &c, const PxStream &iv, uint32_t i,
                                                uint32_t start, uint32_t end, const FragOut &o, unsigned int *hist_s,
                                                uint32_t hist_s_n) {
     if (end - start < m.low) return;
@@ -224,8 +284,8 @@ template <class Cur> __device__ __forceinline__ double target_location(const Dev
 }
 
 // KIND: 0 = after_* methods, 1 = pre_prim, 2 = prim_jump (compile-time specialisations of the molecule kernel), -1 = runtime
-template <int KIND>
-__device__ __forceinline__ Header mol_header(const DevModel &m, const MolCtx &c, uint64_t mol) {
+template <int KIND, class CTX>
+__device__ __forceinline__ Header mol_header(const DevModel &m, const CTX &c, uint64_t mol) {
     const bool is_jump = KIND < 0 ? m.method == RLSIM_PRIM_JUMP : KIND == 2;
     const bool is_pre = KIND < 0 ? m.method == RLSIM_PRE_PRIM : KIND == 1;
     Header h;
@@ -674,6 +734,124 @@ k_fused(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, FusedA
         if (hist_pa[i]) atomicAdd(&o.hist_polya[i], (unsigned long long)hist_pa[i]);
 }
 
+// ---- one WARP per transcript, no CTA barrier in the loop (k_fused_warp).
+// The CTA-cooperative kernel above pays a barrier tail per item; here warps are independent: a warp fetches an item (one
+// transcript + a molecule range), builds the transcript's compact profile in its private slice of shared memory and
+// fragments the item's molecules 32 at a time.  The LUT and the histograms are shared by the CTA's warps.
+// Transcripts that cannot take this path (letters outside ACGT, or longer than the slice) are appended to `redo` and
+// served by k_fused afterwards.
+struct WarpArgs {
+    const FusedItem *items; uint32_t n_items;
+    uint32_t cap_entries;                     // entries per warp slice (multiple of 64)
+    unsigned int *work;
+    const uint32_t *wq_f;
+    FusedItem *redo; unsigned int *redo_count; uint32_t redo_cap;
+};
+__host__ __device__ __forceinline__ uint32_t fw_slice_bytes(uint32_t cap) { return (cap / 16 + 4) * 4 + (cap / 16) * 4 + (cap / 64 + 2) * 8; }
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 5 : 1)
+k_fused_warp(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, WarpArgs a, uint32_t hist_s_n) {
+    extern __shared__ __align__(16) unsigned char fsm[];
+    const uint32_t nlut = 1u << (2 * m.k);
+    uint32_t *lut_s = reinterpret_cast<uint32_t *>(fsm);
+    unsigned int *hist_s = lut_s + nlut;  // [hist_s_n] after-fragmentation bins from `low`, then [polya_max+1]
+    unsigned int *hist_pa = hist_s + hist_s_n;
+    const uint32_t hist_words = (hist_s_n + m.polya_max + 1 + 3u) & ~3u;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *slice = reinterpret_cast<unsigned char *>(hist_s + hist_words) + (size_t)warp * fw_slice_bytes(a.cap_entries);
+    uint64_t *coarse = reinterpret_cast<uint64_t *>(slice);
+    uint32_t *codes = reinterpret_cast<uint32_t *>(coarse + (a.cap_entries / 64 + 2));
+    uint32_t *gsum = codes + (a.cap_entries / 16 + 4);
+    for (uint32_t i = threadIdx.x; i < nlut; i += WARPS * 32) lut_s[i] = a.wq_f[i];
+    for (uint32_t i = threadIdx.x; i < hist_s_n + m.polya_max + 1; i += WARPS * 32) hist_s[i] = 0;
+    __syncthreads();
+    const bool dbl = m.method == RLSIM_AFTER_PRIM_DOUBLE;
+    const uint32_t k = (uint32_t)m.k, kmask = nlut - 1u;
+    const CProfile pf{codes, gsum, coarse, lut_s, kmask};
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(a.work, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= a.n_items) break;
+        const FusedItem it = a.items[item];
+        const uint32_t t = it.t0, L = tr.len[t];
+        const uint32_t ent = L >= k ? L - k + 1 : 0u;  // symmetric mode: the forward sums also hold window L-k
+        if (tr.dirty[t] != 0 || pad64(ent) > a.cap_entries) {  // not for this kernel
+            if (lane == 0) { unsigned int r = atomicAdd(a.redo_count, 1u); if (r < a.redo_cap) a.redo[r] = it; }
+            continue;
+        }
+        const uint64_t off = tr.off[t];
+        // ---- compact profile of transcript t
+        const uint32_t nwords = (L + 15) >> 4;
+        const uint32_t *pk = tr.packed + (off >> 4);
+        for (uint32_t w = lane; w < (pad64(ent) >> 4) + 4; w += 32) codes[w] = w < nwords ? __ldg(pk + w) : 0u;
+        __syncwarp();
+        uint64_t carry = 0;
+        if (lane == 0) coarse[0] = 0;
+        for (uint32_t g0 = 0; (g0 << 4) < ent; g0 += 32) {  // 32 groups = 8 blocks per step
+            const uint32_t g = g0 + lane, e0 = g << 4;
+            const uint32_t nv = e0 < ent ? min(16u, ent - e0) : 0u;
+            uint32_t incl = pf.partial(g, nv);
+#pragma unroll
+            for (int d = 1; d < 4; d <<= 1) {  // inclusive sums inside each block (4 groups)
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, d, 4);
+                if ((lane & 3u) >= (uint32_t)d) incl += v;
+            }
+            if (((g >> 2) << 6) < ent) gsum[g] = incl;  // every group of a block that holds entries (groups past the end repeat the block total)
+            uint64_t bt = (lane & 3u) == 3u ? (uint64_t)incl : 0ull;  // block totals, running over the step's 8 blocks
+#pragma unroll
+            for (int d = 4; d < 32; d <<= 1) {
+                uint64_t v = __shfl_up_sync(0xffffffffu, bt, d);
+                if (lane >= (uint32_t)d) bt += v;
+            }
+            if ((lane & 3u) == 3u && ((g >> 2) << 6) < ent) coarse[(g >> 2) + 1] = carry + bt;
+            carry += __shfl_sync(0xffffffffu, bt, 31);
+        }
+        __syncwarp();
+        // ---- molecules of the item, 32 at a time
+        MolCtxT<CProfile> c;
+        c.t = t; c.tg = m.first_index + t; c.L = L;
+        c.proflen = L > k ? L - k : 0;
+        c.off = off; c.Pf = pf; c.Pr = pf; c.mirror = dbl;
+        for (uint64_t gb = it.g0; gb < it.g1; gb += 32) {
+            const uint64_t g = gb + lane;
+            if (g < it.g1) {
+                const uint64_t mol = g - tr.mol_off[t];
+                Header h = mol_header<0>(m, c, mol);
+                atomicAdd(&hist_pa[h.tail], 1u);
+                if (h.nb > FRAG_LOCAL_BREAKS) {
+                    unsigned int slot = atomicAdd(o.long_count, 1u);
+                    if (slot < o.long_cap) { o.long_list[slot] = make_uint2(t, (uint32_t)(mol & 0xffffffffu)); o.long_hi[slot] = (uint32_t)(mol >> 32); }
+                } else if (h.nb > 0) {
+                    const uint32_t length = (uint32_t)h.polyAend;
+                    uint32_t br[FRAG_LOCAL_BREAKS + 2];
+                    PxStream bs = mol_stream(m, c.tg, mol, SUB_BREAKS);
+                    br[0] = 0;
+                    int cnt = 1;
+                    for (int32_t j = 0; j < h.nb; j++) {  // insertion sort while drawing (fragmentor.go:125-129)
+                        uint32_t v = (uint32_t)bs.below((uint32_t)j, (uint64_t)length);
+                        int q = cnt++;
+                        while (q > 0 && br[q - 1] > v) { br[q] = br[q - 1]; q--; }
+                        br[q] = v;
+                    }
+                    br[cnt] = length;
+                    PxStream iv = mol_stream(m, c.tg, mol, SUB_INTERVAL);
+                    for (int32_t i = 0; i < h.nb; i++)  // the last interval is never visited (fragmentor.go:132)
+                        after_interval(m, c, iv, (uint32_t)i, br[i], br[i + 1], o, hist_s, hist_s_n);
+                }
+            }
+            __syncwarp();
+        }
+        __syncwarp();  // the slice is rebuilt for the next item
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < hist_s_n; i += WARPS * 32)
+        if (hist_s[i]) atomicAdd(&o.hist_frag[m.low + i], (unsigned long long)hist_s[i]);
+    for (uint32_t i = threadIdx.x; i <= m.polya_max; i += WARPS * 32)
+        if (hist_pa[i]) atomicAdd(&o.hist_polya[i], (unsigned long long)hist_pa[i]);
+}
+
 // Deferred molecules of the fused path (more breakpoints than a thread sorts locally): one CTA per molecule, its
 // transcript's prefix sums rebuilt in shared memory, breakpoints bitonic-sorted in shared memory.
 constexpr int FLONG_THREADS = 256;
@@ -806,6 +984,39 @@ int launch_fused(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, c
     k_fused<<<blocks, FUSED_THREADS, smem, st>>>(m, tr, o, a, hist_s_n);
     return 0;
 }
+// per-warp slices of `cap_entries`; warps = 8 (small / medium classes) or 4 (large class)
+int launch_fused_warp(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, const FusedItem *items,
+                      uint32_t n_items, uint32_t cap_entries, int warps, unsigned int *work, const uint32_t *wq_f, FusedItem *redo,
+                      unsigned int *redo_count, uint32_t redo_cap, int sm_count) {
+    if (!n_items) return 0;
+    if (m.k > 6) return RLSIM_E_UNSUPPORTED;  // the LUT must fit shared memory beside the slices
+    FragOut o{fb.keys, fb.cap, key_len_bits(m.high), fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, fb.long_cap, fb.long_count,
+              fb.error, fb.q_a, fb.q_b, fb.q_cap, fb.q_count};
+    uint32_t hist_s_n = frag_hist_bins(m);
+    auto bytes = [&](uint32_t hs) {
+        const size_t hist_words = ((size_t)hs + m.polya_max + 1 + 3) & ~(size_t)3;
+        return ((size_t)4 << (2 * m.k)) + hist_words * 4 + (size_t)warps * fw_slice_bytes(cap_entries) + 16;
+    };
+    size_t smem = bytes(hist_s_n);
+    if (smem > 227 * 1024) { hist_s_n = 0; smem = bytes(0); }
+    if (smem > 227 * 1024) return RLSIM_E_UNSUPPORTED;
+    WarpArgs a{items, n_items, cap_entries, work, wq_f, redo, redo_count, redo_cap};
+    cudaMemsetAsync(work, 0, sizeof(unsigned int), st);
+    int per_sm = 1;
+    if (warps == 8) {
+        cudaFuncSetAttribute(k_fused_warp<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_warp<8>, 256, smem);
+        const uint32_t blocks = std::min<uint32_t>((n_items + 7) / 8, (uint32_t)(sm_count * std::max(per_sm, 1)));
+        k_fused_warp<8><<<blocks, 256, smem, st>>>(m, tr, o, a, hist_s_n);
+    } else {
+        cudaFuncSetAttribute(k_fused_warp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_warp<4>, 128, smem);
+        const uint32_t blocks = std::min<uint32_t>((n_items + 3) / 4, (uint32_t)(sm_count * std::max(per_sm, 1)));
+        k_fused_warp<4><<<blocks, 128, smem, st>>>(m, tr, o, a, hist_s_n);
+    }
+    return 0;
+}
+
 int launch_fused_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t n_long,
                       uint32_t cap_entries, const uint32_t *wq_f, const uint32_t *wq_r, const unsigned long long *kmax_bits, int *fallback) {
     if (!n_long) return 0;

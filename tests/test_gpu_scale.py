@@ -301,10 +301,11 @@ def test_pageable_and_pinned_buffers_agree(gpu, monkeypatch):
 
 # ---- fused prefix + fragmentation kernel (prefix sums in shared memory) --------------------------------------------
 def test_fused_path_variants(oracle, gpu, monkeypatch):
-    """after_prim / after_prim_double keep the priming prefix sums in shared memory (k_fused).  Same fragments as the HBM
-    path (RLSIM_NO_FUSED) and as the oracle for: the small class, items split by molecule range (a heavily expressed
-    transcript), the large class with deferred molecules (k_fused_long), explicit reverse arrays of transcripts with
-    letters outside ACGT (sub-batching), and a transcript whose sums do not fit (fallback to the HBM path)."""
+    """after_prim / after_prim_double keep the priming prefix sums in shared memory: one warp per transcript with a compact
+    profile (k_fused_warp), transcripts with letters outside ACGT through the CTA-cooperative kernel (k_fused, explicit
+    reverse sums, sub-batching), deferred molecules through k_fused_long.  Same fragments as the HBM path (RLSIM_NO_FUSED)
+    and as the oracle for: all three slice sizes, items split by molecule range (a heavily expressed transcript),
+    zero-expression gaps, and a transcript whose sums do not fit (fallback to the HBM path)."""
     def both(argv, names, seqs, levels, expect_fused=True, eager=True):
         h = _compare_records(oracle, gpu, argv, names, seqs, levels)
         assert bool(int(h.stats().flags) & gpu.F_FUSED) == expect_fused, argv
@@ -316,6 +317,14 @@ def test_fused_path_variants(oracle, gpu, monkeypatch):
             assert np.array_equal(h.species()[k], h2.species()[k]), k
         for kind in (gpu.H_AFTER_FRAG, gpu.H_POLYA):
             assert h.hist_dict(kind, 1 << 16) == h2.hist_dict(kind, 1 << 16)
+        monkeypatch.setenv("RLSIM_FUSED_CTA", "1")  # the CTA-cooperative kernel for every transcript (normally: only the redo list)
+        h4 = util.run_gpu(gpu, util.parse(argv), names, seqs, levels)
+        monkeypatch.delenv("RLSIM_FUSED_CTA")
+        assert bool(int(h4.stats().flags) & gpu.F_FUSED) == expect_fused
+        for k in ("tr", "start", "end", "count0", "count"):
+            assert np.array_equal(h.species()[k], h4.species()[k]), k
+        for kind in (gpu.H_AFTER_FRAG, gpu.H_POLYA):
+            assert h.hist_dict(kind, 1 << 16) == h4.hist_dict(kind, 1 << 16)
         if not eager:
             return
         monkeypatch.setenv("RLSIM_NO_EAGER", "1")  # the monolithic launch over all items
