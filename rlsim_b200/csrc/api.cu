@@ -308,31 +308,6 @@ int build_fused_items(rlsim_handle *h, uint32_t t0, uint32_t t1) {
     return 0;
 }
 
-// Items of the warp kernel for [t0, t1): one transcript (and at most W_MAX molecules) each, in three lists by the size of
-// the per-warp slice the transcript needs.
-int build_warp_items(rlsim_handle *h, uint32_t t0, uint32_t t1) {
-    const int key = 4 | (h->p.frag_method == RLSIM_AFTER_PRIM_DOUBLE ? 1 : 0);
-    if (h->fitems_key == key && h->fitems_t0 == t0 && h->fitems_t1 == t1) return 0;  // still on the device
-    constexpr uint64_t W_MAX = 512;
-    for (auto &v : h->h_witems) v.clear();
-    const uint64_t *mo = h->h_mol_off.data();
-    size_t total = 0;
-    for (uint32_t t = t0; t < t1; t++) {
-        if (!h->h_expr[t]) continue;
-        const uint64_t e1 = ((uint64_t)h->h_len[t] + 63) & ~63ull;
-        PinVec<FusedItem> &dst = h->h_witems[e1 <= FUSED_WARP_CAP_S ? 0 : e1 <= FUSED_WARP_CAP_M ? 1 : 2];
-        for (uint64_t g = mo[t]; g < mo[t + 1]; g += W_MAX) { dst.push_back(FusedItem{t, t + 1, g, std::min<uint64_t>(g + W_MAX, mo[t + 1])}); total++; }
-    }
-    for (int c = 0; c < 3; c++) {
-        CK(h, h->d_witems[c].ensure(h->h_witems[c].size() + 1));
-        if (h->h_witems[c].size())
-            CK(h, cudaMemcpyAsync(h->d_witems[c].p, h->h_witems[c].data(), h->h_witems[c].size() * sizeof(FusedItem), cudaMemcpyHostToDevice, h->st));
-    }
-    CK(h, h->d_redo.ensure(total + 1));
-    h->fitems_key = key; h->fitems_t0 = t0; h->fitems_t1 = t1;
-    return 0;
-}
-
 // Run the fused kernels over the transcripts [t0, t1) up to (not including) the deferred molecules: on return the host
 // knows how many molecules were deferred (*n_long) and whether a transcript did not fit shared memory (*fell_back: the
 // caller reruns the range on the HBM path).
@@ -348,13 +323,18 @@ int run_fused_range(rlsim_handle *h, const DevModel &m, const DevTranscripts &tr
     const bool warp_kernel = trs.sym && h->p.kmer_len <= 6 && !getenv("RLSIM_FUSED_CTA");
     unsigned int n_redo = 0;
     if (warp_kernel) {
-        if ((rc = build_warp_items(h, t0, t1))) return rc;
-        static const uint32_t caps[3] = {FUSED_WARP_CAP_S, FUSED_WARP_CAP_M, FUSED_WARP_CAP_L};
+        // no item lists: the molecule range is cut into fixed units, every launch serves one slice-size class
+        const uint64_t g0 = h->h_mol_off[t0], g1 = h->h_mol_off[t1];
+        CK(h, h->d_redo.ensure((size_t)(t1 - t0) + fused_warp_units(g1 - g0) + 1));
+        static const uint32_t caps[4] = {0, FUSED_WARP_CAP_S, FUSED_WARP_CAP_M, FUSED_WARP_CAP_L};
         static const int warps[3] = {8, 8, 4};
+        uint32_t longest = 0;
+        if (t1 - t0 == (uint32_t)h->h_len.size()) longest = h->max_len;
+        else for (uint32_t t = t0; t < t1; t++) if (h->h_expr[t]) longest = std::max(longest, h->h_len[t]);
         for (int c = 0; c < 3; c++) {
-            if (!h->h_witems[c].size()) continue;
-            if ((rc = launch_fused_warp(h->st, m, trs, fb, h->d_witems[c].p, (uint32_t)h->h_witems[c].size(), caps[c], warps[c], h->d_work.p + 3 + c,
-                                        h->d_wq_f.p, h->d_redo.p, redo_count, (uint32_t)h->d_redo.n, h->sm_count))) return rc;
+            if (c > 0 && (((uint64_t)longest + 63) & ~63ull) <= caps[c]) break;  // no transcript of this size class or a larger one
+            if ((rc = launch_fused_warp(h->st, m, trs, fb, g0, g1, caps[c], caps[c + 1], warps[c], h->d_work.p + 3 + c, h->d_wq_f.p, h->d_redo.p,
+                                        redo_count, (uint32_t)h->d_redo.n, h->sm_count))) return rc;
             h->launches[RLSIM_T_FRAGMENT]++;
         }
         CK(h, cudaMemcpyAsync(h->pin, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
@@ -624,7 +604,7 @@ int rlsim_set_model(rlsim_handle *h, const rlsim_params *p) {
     if (!h->h_len.empty() && h->polya_max != (uint32_t)mx) FAIL(h, RLSIM_E_ARG, "poly(A) maximum cannot change after transcripts were added");
     h->polya_max = (uint32_t)mx;
     h->prefix_upto = 0;
-    h->fused_disabled = false; h->fitems_key = -1;
+    h->fused_disabled = false;
     h->lut_valid = h->lut_valid && h->lut_k == p->kmer_len && h->lut_T == p->priming_temp;
     h->want_mirror = getenv("RLSIM_NO_MIRROR") == nullptr;  // diagnostic switch: always build explicit reverse arrays
     h->len_eff_ready = false;

@@ -239,8 +239,7 @@ struct rlsim_handle {
     // fused path (after_prim / after_prim_double): prefix sums in shared memory, work items = runs of transcripts
     PinVec<FusedItem> h_fitems_s, h_fitems_l;     // small-class / large-class items of the last build (CTA-cooperative kernel)
     DBuf<FusedItem> d_fitems_s, d_fitems_l;
-    PinVec<FusedItem> h_witems[3];                // warp kernel: one transcript per item, by slice size (S / M / L)
-    DBuf<FusedItem> d_witems[3], d_redo;          // d_redo: items the warp kernel passed on to the CTA-cooperative one
+    DBuf<FusedItem> d_redo;                       // what the warp kernel passed on to the CTA-cooperative one
     uint32_t fitems_t0 = 0, fitems_t1 = 0; int fitems_key = -1;  // what the device item lists cover (transcript range, layout key)
     bool fused_disabled = false;                  // a transcript did not fit shared memory: this library stays on the HBM path
     bool fused_used = false;

@@ -741,12 +741,13 @@ k_fused(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, FusedA
 // Transcripts that cannot take this path (letters outside ACGT, or longer than the slice) are appended to `redo` and
 // served by k_fused afterwards.
 struct WarpArgs {
-    const FusedItem *items; uint32_t n_items;
-    uint32_t cap_entries;                     // entries per warp slice (multiple of 64)
-    unsigned int *work;
+    uint64_t g_begin, g_end;                  // global molecule range of this launch, cut into units of FW_UNIT molecules
+    uint32_t cap_lo, cap_entries;             // this launch serves transcripts with cap_lo < pad64(entries) <= cap_entries
+    unsigned int *work;                       // unit counter
     const uint32_t *wq_f;
     FusedItem *redo; unsigned int *redo_count; uint32_t redo_cap;
 };
+constexpr uint32_t FW_UNIT = 256;             // molecules per unit of work (a transcript with more is shared by several warps)
 __host__ __device__ __forceinline__ uint32_t fw_slice_bytes(uint32_t cap) { return (cap / 16 + 4) * 4 + (cap / 16) * 4 + (cap / 64 + 2) * 8; }
 
 template <int WARPS>
@@ -770,17 +771,27 @@ k_fused_warp(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, W
     const uint32_t k = (uint32_t)m.k, kmask = nlut - 1u;
     const CProfile pf{codes, gsum, coarse, lut_s, kmask};
     for (;;) {
-        uint32_t item = 0;
-        if (lane == 0) item = atomicAdd(a.work, 1u);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= a.n_items) break;
-        const FusedItem it = a.items[item];
-        const uint32_t t = it.t0, L = tr.len[t];
+        uint32_t unit = 0;
+        if (lane == 0) unit = atomicAdd(a.work, 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        uint64_t gs = a.g_begin + (uint64_t)unit * FW_UNIT;
+        if (gs >= a.g_end) break;
+        const uint64_t ge = min(a.g_end, gs + FW_UNIT);
+        uint32_t t = upper_bound_u64(tr.mol_off, tr.n + 1, gs) - 1;  // the transcript that owns molecule gs
+      while (gs < ge) {
+        while (tr.mol_off[t + 1] <= gs) t++;
+        const uint64_t me = min(ge, tr.mol_off[t + 1]);  // this unit's molecules of transcript t: [gs, me)
+        const FusedItem it{t, t + 1, gs, me};
+        gs = me;
+        const uint32_t L = tr.len[t];
         const uint32_t ent = L >= k ? L - k + 1 : 0u;  // symmetric mode: the forward sums also hold window L-k
-        if (tr.dirty[t] != 0 || pad64(ent) > a.cap_entries) {  // not for this kernel
-            if (lane == 0) { unsigned int r = atomicAdd(a.redo_count, 1u); if (r < a.redo_cap) a.redo[r] = it; }
+        const uint32_t e1 = pad64(ent);
+        if (tr.dirty[t] != 0) {  // letters outside ACGT: explicit reverse sums, k_fused (the first size class reports them)
+            if (a.cap_lo == 0 && lane == 0) { unsigned int r = atomicAdd(a.redo_count, 1u); if (r < a.redo_cap) a.redo[r] = it; }
             continue;
         }
+        if (e1 <= a.cap_lo && !(a.cap_lo == 0)) continue;  // another launch's size class
+        if (e1 > a.cap_entries) continue;
         const uint64_t off = tr.off[t];
         // ---- compact profile of transcript t
         const uint32_t nwords = (L + 15) >> 4;
@@ -843,7 +854,8 @@ k_fused_warp(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, W
             }
             __syncwarp();
         }
-        __syncwarp();  // the slice is rebuilt for the next item
+        __syncwarp();  // the slice is rebuilt for the next transcript
+      }
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < hist_s_n; i += WARPS * 32)
@@ -985,10 +997,10 @@ int launch_fused(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, c
     return 0;
 }
 // per-warp slices of `cap_entries`; warps = 8 (small / medium classes) or 4 (large class)
-int launch_fused_warp(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, const FusedItem *items,
-                      uint32_t n_items, uint32_t cap_entries, int warps, unsigned int *work, const uint32_t *wq_f, FusedItem *redo,
+int launch_fused_warp(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint64_t g_begin, uint64_t g_end,
+                      uint32_t cap_lo, uint32_t cap_entries, int warps, unsigned int *work, const uint32_t *wq_f, FusedItem *redo,
                       unsigned int *redo_count, uint32_t redo_cap, int sm_count) {
-    if (!n_items) return 0;
+    if (g_end <= g_begin) return 0;
     if (m.k > 6) return RLSIM_E_UNSUPPORTED;  // the LUT must fit shared memory beside the slices
     FragOut o{fb.keys, fb.cap, key_len_bits(m.high), fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, fb.long_cap, fb.long_count,
               fb.error, fb.q_a, fb.q_b, fb.q_cap, fb.q_count};
@@ -1000,22 +1012,24 @@ int launch_fused_warp(cudaStream_t st, const DevModel &m, const DevTranscripts &
     size_t smem = bytes(hist_s_n);
     if (smem > 227 * 1024) { hist_s_n = 0; smem = bytes(0); }
     if (smem > 227 * 1024) return RLSIM_E_UNSUPPORTED;
-    WarpArgs a{items, n_items, cap_entries, work, wq_f, redo, redo_count, redo_cap};
+    WarpArgs a{g_begin, g_end, cap_lo, cap_entries, work, wq_f, redo, redo_count, redo_cap};
     cudaMemsetAsync(work, 0, sizeof(unsigned int), st);
+    const uint64_t units = (g_end - g_begin + FW_UNIT - 1) / FW_UNIT;
     int per_sm = 1;
     if (warps == 8) {
         cudaFuncSetAttribute(k_fused_warp<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_warp<8>, 256, smem);
-        const uint32_t blocks = std::min<uint32_t>((n_items + 7) / 8, (uint32_t)(sm_count * std::max(per_sm, 1)));
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>((units + 7) / 8, (uint64_t)(sm_count * std::max(per_sm, 1)));
         k_fused_warp<8><<<blocks, 256, smem, st>>>(m, tr, o, a, hist_s_n);
     } else {
         cudaFuncSetAttribute(k_fused_warp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_warp<4>, 128, smem);
-        const uint32_t blocks = std::min<uint32_t>((n_items + 3) / 4, (uint32_t)(sm_count * std::max(per_sm, 1)));
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>((units + 3) / 4, (uint64_t)(sm_count * std::max(per_sm, 1)));
         k_fused_warp<4><<<blocks, 128, smem, st>>>(m, tr, o, a, hist_s_n);
     }
     return 0;
 }
+uint64_t fused_warp_units(uint64_t n_mol) { return (n_mol + FW_UNIT - 1) / FW_UNIT; }
 
 int launch_fused_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t n_long,
                       uint32_t cap_entries, const uint32_t *wq_f, const uint32_t *wq_r, const unsigned long long *kmax_bits, int *fallback) {

@@ -36,9 +36,10 @@ int launch_fused(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, c
                  const unsigned long long *kmax_bits, int *fallback, int sm_count);
 // warp-per-transcript variant with the compact shared-memory profile; unfit transcripts go to `redo` (served by launch_fused)
 constexpr uint32_t FUSED_WARP_CAP_S = 4096, FUSED_WARP_CAP_M = 16384, FUSED_WARP_CAP_L = 49152;
-int launch_fused_warp(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, const FusedItem *items,
-                      uint32_t n_items, uint32_t cap_entries, int warps, unsigned int *work, const uint32_t *wq_f, FusedItem *redo,
+int launch_fused_warp(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint64_t g_begin, uint64_t g_end,
+                      uint32_t cap_lo, uint32_t cap_entries, int warps, unsigned int *work, const uint32_t *wq_f, FusedItem *redo,
                       unsigned int *redo_count, uint32_t redo_cap, int sm_count);
+uint64_t fused_warp_units(uint64_t n_mol);
 int launch_fused_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t n_long,
                       uint32_t cap_entries, const uint32_t *wq_f, const uint32_t *wq_r, const unsigned long long *kmax_bits, int *fallback);
 
