@@ -254,7 +254,8 @@ bool ns_need(rlsim_handle *h, uint64_t ns) {  // would any per-species array be 
 // once per breakpoint pair; every transcript of the range must fit one CTA's shared memory and produce few enough
 // breakpoints for the deferred-molecule kernel.
 bool fused_method(rlsim_handle *h) {
-    const bool disabled = getenv("RLSIM_NO_FUSED") != nullptr;  // diagnostic switch: HBM prefix sums (k_prefix + k_fragment + k_intervals)
+    // opt-in (measured, profiles/r2_experiments.md: at C3 the three HBM-path kernels are faster than either fused variant)
+    const bool disabled = getenv("RLSIM_NO_FUSED") != nullptr || getenv("RLSIM_FUSED") == nullptr;
     return !disabled && !h->fused_disabled && (h->p.frag_method == RLSIM_AFTER_PRIM || h->p.frag_method == RLSIM_AFTER_PRIM_DOUBLE);
 }
 bool fused_len_ok(rlsim_handle *h, uint32_t L) {

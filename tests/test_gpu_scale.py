@@ -306,6 +306,8 @@ def test_fused_path_variants(oracle, gpu, monkeypatch):
     reverse sums, sub-batching), deferred molecules through k_fused_long.  Same fragments as the HBM path (RLSIM_NO_FUSED)
     and as the oracle for: all three slice sizes, items split by molecule range (a heavily expressed transcript),
     zero-expression gaps, and a transcript whose sums do not fit (fallback to the HBM path)."""
+    monkeypatch.setenv("RLSIM_FUSED", "1")  # the fused kernels are opt-in
+
     def both(argv, names, seqs, levels, expect_fused=True, eager=True):
         h = _compare_records(oracle, gpu, argv, names, seqs, levels)
         assert bool(int(h.stats().flags) & gpu.F_FUSED) == expect_fused, argv
