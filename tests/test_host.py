@@ -151,6 +151,47 @@ def test_product_never_touches_the_oracle():
                 assert "pyoracle" not in txt and "liboracle" not in txt and "oracle/" not in txt.replace("the oracle", ""), f
 
 
+def _go_methods(src, receiver):
+    """{method: (params, returns)} of the methods go/gpu_pool.go declares on `receiver` (value or pointer)."""
+    out = {}
+    for m in re.finditer(r"^func \(\w+ \*?%s\) (\w+)\((.*?)\)\s*(.*?)\s*\{" % receiver, src, re.M):
+        out[m.group(1)] = (m.group(2).strip(), m.group(3).strip())
+    return out
+
+
+def test_go_shim_implements_the_reference_interfaces():
+    """go/gpu_pool.go: GpuPool has all 11 Pooler methods (pool.go:36-48) and GpuSampler both Sampler methods
+    (sampler.go:39-42), with the reference's parameter lists and result types.  No Go toolchain here: the file is also
+    checked for balanced delimiters, that every C symbol it calls is declared in include/rlsim_gpu.h, and that the
+    committed method lists are still what the reference declares (when /root/reference is mounted)."""
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "go_interfaces.json")))
+    assert len(want["Pooler"]) == 11 and len(want["Sampler"]) == 2
+    if os.path.isdir("/root/reference/src"):
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import make_go_interfaces
+        assert make_go_interfaces.extract() == want
+    src = open(os.path.join(ROOT, "go", "gpu_pool.go")).read()
+    norm = lambda x: re.sub(r"\s+", " ", x.strip())
+    for iface, typ in (("Pooler", "GpuPool"), ("Sampler", "GpuSampler")):
+        have = _go_methods(src, typ)
+        for name, sig in want[iface].items():
+            assert name in have, "%s.%s is missing" % (typ, name)
+            types = lambda plist: [norm(x).split(" ", 1)[1] for x in plist.split(",") if x.strip()]  # parameter names are free
+            assert types(have[name][0]) == types(sig["params"]), (name, have[name][0], sig["params"])
+            assert norm(have[name][1]) == norm(sig["returns"]), (name, have[name][1], sig["returns"])
+    assert "var _ Pooler = (*GpuPool)(nil)" in src and "var _ Sampler = GpuSampler{}" in src
+    code = re.sub(r"//[^\n]*", "", src)                      # comments ...
+    code = re.sub(r'"(\\.|[^"\\])*"', '""', code)            # ... and string literals out of the way
+    for a, b in ("()", "{}", "[]"):
+        assert code.count(a) == code.count(b), "unbalanced %s%s" % (a, b)
+    hdr = open(os.path.join(ROOT, "include", "rlsim_gpu.h")).read()
+    for sym in set(re.findall(r"C\.(rlsim_\w+|RLSIM_\w+)", src)):
+        assert re.search(r"\b%s\b" % sym, hdr), "C.%s is not declared in include/rlsim_gpu.h" % sym
+    # the report bookkeeping the reference does in SampleFragments / SampleTranscripts (sampler.go:95-101,149-153)
+    for call in ("st.UpdateSampled(", "st.UpdateMissing(", "st.UpdateAfterSampling(", "st.LogSamplingRatio(", "st.UpdateNrSampled("):
+        assert call in src, call
+
+
 def test_exchange_plan_host_arithmetic():
     """rlsim_exchange_plan: where each rank's groups start in its send buffer and where each sender's records land
     (the routing arithmetic of rlsim_sample_distributed; no GPU involved)."""
