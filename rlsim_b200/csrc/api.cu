@@ -105,6 +105,11 @@ DevTranscripts make_tr(rlsim_handle *h) {
     t.Cr = needs_rev(h->p.frag_method) ? h->d_Cr.p : nullptr;
     t.gc = h->d_gc.p;
     t.dirty = h->d_dirty.p;
+    // record layout of the forward sums: needs the mirrored reverse draw (symmetric table) and a LUT that fits shared memory
+    h->rec_layout = needs_fwd(h->p.frag_method) && h->lut_valid && h->lut_sym && h->want_mirror && h->p.kmer_len <= 6 &&
+                    getenv("RLSIM_NO_RECORDS") == nullptr;
+    t.Rf = h->rec_layout ? h->d_Rf.p : nullptr;
+    t.lut = h->d_wq_f.p;
     t.sym = h->lut_sym && h->want_mirror ? 1 : 0;
     return t;
 }
@@ -133,6 +138,7 @@ int raw_target_finish(rlsim_handle *h) {  // raw_target.go:54,59-90
 
 // capacity of the two-level prefix-sum arrays for `tot` padded bases in `n` transcripts, keeping the first old_tot / old_n
 int grow_prefix(rlsim_handle *h, uint64_t tot, uint32_t n, uint64_t old_tot, uint32_t old_n) {
+    CK(h, h->d_Rf.grow_preserve(tot / 64 + 2ull * n + 8, old_n ? old_tot / 64 + 2ull * old_n + 2 : 0, h->st));
     CK(h, h->d_Ff.grow_preserve(tot + 64, old_tot, h->st));
     CK(h, h->d_Cf.grow_preserve(tot / 32 + 2ull * n + 8, old_n ? old_tot / 32 + 2ull * old_n + 2 : 0, h->st));
     if (needs_rev(h->p.frag_method)) {
@@ -160,8 +166,9 @@ int launch_prefix_range(rlsim_handle *h, uint32_t t0, uint32_t t1) {
     int method = h->p.frag_method;
     int rcl = ensure_lut(h);
     if (rcl) return rcl;
-    launch_prefix(h->st, make_tr(h), t0, t1, h->p.kmer_len, h->p.priming_temp, h->d_wq_f.p, h->d_wq_r.p, h->d_kmax.p,
-                  h->d_Ff.p, h->d_Fr.p, h->d_Cf.p, h->d_Cr.p, needs_rev(method) ? 2 : 1, h->d_work.p);
+    const DevTranscripts trp = make_tr(h);
+    launch_prefix(h->st, trp, t0, t1, h->p.kmer_len, h->p.priming_temp, h->d_wq_f.p, h->d_wq_r.p, h->d_kmax.p,
+                  h->d_Ff.p, h->d_Fr.p, h->d_Cf.p, h->d_Cr.p, const_cast<Rec32 *>(trp.Rf), needs_rev(method) ? 2 : 1, h->d_work.p);
     h->launches[RLSIM_T_PREFIX] += 1;
     return 0;
 }
@@ -391,7 +398,7 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
     CK(h, h->d_q_a.ensure(est)); CK(h, h->d_q_b.ensure(est));
     const uint32_t long_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((g1 - g0) / 16, 4096), 1u << 24);
     CK(h, h->d_long_list.ensure(long_cap)); CK(h, h->d_long_hi.ensure(long_cap));
-    CK(h, cudaMemsetAsync(h->d_counters.p + 2, 0, 8, h->st));
+    CK(h, cudaMemsetAsync(h->d_counters.p + 2, 0, 16, h->st));
     CK(h, cudaMemsetAsync(h->d_long_count.p, 0, 4, h->st));
     DevModel m = make_model(h);
     DevTranscripts tr = make_tr(h);
@@ -399,7 +406,7 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
                    long_cap, h->d_long_count.p, h->d_error.p, h->d_q_a.p, h->d_q_b.p, h->d_q_a.n, h->d_counters.p + 2};
     const bool fused = fused_range_ok(h, t0, t1);
     unsigned int n_long = 0;
-    unsigned long long n_q = 0;
+    unsigned long long n_q = 0, n_q_dirty = 0;
     if (fused) {
         int fell_back = 0;
         if ((rc = run_fused_range(h, m, tr, fb, t0, t1, &n_long, &fell_back)) || fell_back) { h->fused_disabled = true; h->eager_failed = true; return 0; }
@@ -407,9 +414,11 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
         if ((rc = launch_fragment(h->st, m, tr, g0, g1, fb))) { h->eager_failed = true; return 0; }
         CK(h, cudaMemcpyAsync(h->pin, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
         CK(h, cudaMemcpyAsync(h->pin + 1, h->d_counters.p + 2, 8, cudaMemcpyDeviceToHost, h->st));
+        CK(h, cudaMemcpyAsync(h->pin + 3, h->d_counters.p + 3, 8, cudaMemcpyDeviceToHost, h->st));
         CK(h, cudaStreamSynchronize(h->st));
         n_long = *reinterpret_cast<unsigned int *>(h->pin);
         n_q = h->pin[1];
+        n_q_dirty = h->pin[3];
     }
     tt1 = now_ms();
     // test hook: pretend the estimate of group number RLSIM_EAGER_TEST_FAIL (0-based) was too small
@@ -426,7 +435,7 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
         }
         h->fused_used = true;
     } else {
-        launch_intervals(h->st, m, tr, fb, n_q);
+        launch_intervals(h->st, m, tr, fb, n_q, n_q_dirty);
         launch_fragment_long(h->st, m, tr, fb, n_long);
         h->launches[RLSIM_T_FRAGMENT] += 1 + (n_long ? 1 : 0); h->launches[RLSIM_T_INTERVALS] += n_q ? 1 : 0;
     }
@@ -1105,7 +1114,7 @@ int rlsim_fragment(rlsim_handle *h) {
         const bool fused = fused_range_ok(h, 0, n);
         StageTimer tm(h, RLSIM_T_FRAGMENT, fused ? 0 : 1);
         unsigned int n_long = 0;
-        unsigned long long n_q = 0;
+        unsigned long long n_q = 0, n_q_dirty = 0;
         int fell_back = 0;
         if (fused) {
             if ((rc = run_fused_range(h, m, tr, fb, 0, n, &n_long, &fell_back))) { tm.stop(); h->fused_disabled = true; attempt--; if ((rc = finalize(h))) return rc; tr = make_tr(h); continue; }
@@ -1114,6 +1123,7 @@ int rlsim_fragment(rlsim_handle *h) {
             if (rc) FAIL(h, rc, "fragmentation launch configuration unsupported (poly(A) maximum too large)");
             CK(h, cudaMemcpyAsync(&n_long, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
             CK(h, cudaMemcpyAsync(&n_q, h->d_counters.p + 2, 8, cudaMemcpyDeviceToHost, h->st));
+            CK(h, cudaMemcpyAsync(&n_q_dirty, h->d_counters.p + 3, 8, cudaMemcpyDeviceToHost, h->st));
             CK(h, cudaStreamSynchronize(h->st));
         }
         if (n_long > long_cap) { tm.stop(); long_cap = n_long + 1024; continue; }
@@ -1137,7 +1147,7 @@ int rlsim_fragment(rlsim_handle *h) {
         tm.stop();
         if (n_q) {
             StageTimer tq(h, RLSIM_T_INTERVALS, 1);
-            launch_intervals(h->st, m, tr, fb, n_q);
+            launch_intervals(h->st, m, tr, fb, n_q, n_q_dirty);
             tq.stop();
         }
         CK(h, cudaGetLastError());
@@ -1678,28 +1688,13 @@ int rlsim_probe_prefix(rlsim_handle *h, uint32_t tr, int reverse, uint64_t *out,
         CK(h, cudaGetLastError());
         h->prefix_upto = nt;
     }
-    // rebuild P(0..proflen) from the two levels: P(i) = coarse[i >> 6] + (i & 63 ? fine[i - 1] : 0)
-    uint32_t proflen = h->h_len[tr] > (uint32_t)h->p.kmer_len ? h->h_len[tr] - h->p.kmer_len : 0;
-    const bool sym = make_tr(h).sym != 0;
-    bool mirror = false;
-    if (sym && reverse) {
-        uint32_t dirty = 0;
-        CK(h, cudaMemcpyAsync(&dirty, h->d_dirty.p + tr, 4, cudaMemcpyDeviceToHost, h->st));
-        CK(h, cudaStreamSynchronize(h->st));
-        mirror = dirty == 0;
-    }
-    const bool use_rev = reverse && !mirror;
-    const uint32_t entries = proflen + ((sym && !use_rev && h->h_len[tr] >= (uint32_t)h->p.kmer_len) ? 1 : 0);  // windows held
-    const uint32_t nblk = (entries + 63) / 64;
-    std::vector<uint32_t> fine(std::max<uint32_t>(entries, 1));
-    std::vector<uint64_t> coarse(nblk + 1);
-    if (entries) CK(h, cudaMemcpyAsync(fine.data(), (use_rev ? h->d_Fr.p : h->d_Ff.p) + h->h_off[tr], (size_t)entries * 4, cudaMemcpyDeviceToHost, h->st));
-    CK(h, cudaMemcpyAsync(coarse.data(), (use_rev ? h->d_Cr.p : h->d_Cf.p) + coarse_base(h->h_off[tr], tr), (size_t)(nblk + 1) * 8, cudaMemcpyDeviceToHost, h->st));
+    // P(0..proflen) evaluated on the device by the profile the searches use (record layout, two-level arrays, mirrored)
+    DBuf<uint64_t> d_out;
+    CK(h, d_out.ensure(std::max<uint32_t>(n, 1)));
+    launch_probe_prefix(h->st, make_model(h), make_tr(h), tr, reverse, d_out.p, n);
+    CK(h, cudaGetLastError());
+    CK(h, cudaMemcpyAsync(out, d_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->st));
     CK(h, cudaStreamSynchronize(h->st));
-    auto P = [&](uint32_t i) { return coarse[i >> 6] + ((i & 63) ? fine[i - 1] : 0); };
-    const uint32_t have = proflen + 1;
-    for (uint32_t i = 0; i < std::min(n, have); i++)
-        out[i] = mirror ? P(proflen + 1) - P(proflen + 1 - i) : P(i);  // mirrored: P_rev(i) = W(n+1) - W(n+1-i)
     return 0;
 }
 

@@ -37,6 +37,10 @@ struct DevModel {
     const double *raw_prob;    // raw target probabilities (file order)
 };
 
+// one 32-byte record per 64-entry block of forward prefix sums (layout described below, at RProfile)
+struct __align__(16) Rec32 { uint64_t coarse; uint32_t half; uint32_t codes[5]; };
+__host__ __device__ __forceinline__ uint64_t rec_base(uint64_t off, uint32_t t) { return (off >> 6) + 2ull * t; }
+
 // Transcript store, SoA in HBM.
 struct DevTranscripts {
     uint32_t n;
@@ -54,6 +58,8 @@ struct DevTranscripts {
     const uint32_t *dirty;    // per transcript: non-zero when a letter outside ACGT occurs (incl. the poly(A) tail: never)
     int sym;                  // quantised k-mer table is reverse-complement symmetric: clean transcripts carry no reverse
                               // arrays, their forward arrays hold one more entry (window len-k) and are read mirrored
+    const Rec32 *Rf;          // record layout of the forward sums (transcripts with dirty[t] == 0), or null: two-level arrays for all
+    const uint32_t *lut;      // quantised k-mer weights in global memory (the record layout recomputes weights from the codes)
     const uint2 *gc;          // per 32-base group {#GC before the group, GC bit mask of the group}; transcript t has
                               // padded_len/32 + 1 entries starting at off[t]/32 + t (see gc_before)
 };
@@ -71,6 +77,41 @@ struct Profile {  // one strand of one transcript
     __device__ __forceinline__ uint64_t P(uint32_t i) const {
         uint64_t c = C[i >> PFX_BLOCK_SHIFT];
         return (i & (PFX_BLOCK - 1)) ? c + F[i - 1] : c;
+    }
+};
+
+// ---- Record layout of the forward prefix sums (transcripts without letters outside ACGT, symmetric k-mer table, k <= 6).
+// One 32-byte record per 64-entry block - exactly one DRAM sector - holds everything a search needs from that block:
+//   coarse : sum of the weights of all entries before the block
+//   half   : sum of the block's first 32 entries
+//   codes  : the 2-bit codes of the 80 bases from the block's first window on (64 windows of k <= 17 bases)
+// P(i) = coarse + (i & 32 ? half : 0) + at most 31 weights recomputed from the codes and the k-mer LUT: 0.5 B per entry
+// in HBM instead of 4.1, one sector per P() instead of two, and the block that holds the answer needs no further read.
+// Record nblk (coarse only) closes a transcript; transcript t's records start at rec_base(off[t], t).
+
+struct RProfile {
+    const Rec32 *R;
+    const uint32_t *lut;   // quantised weights by 2-bit code (shared memory in k_intervals, global elsewhere)
+    uint32_t kmask;
+    // sum of the weights of the entries [j0, j0 + n) of a block, j0 in {0, 32}, n <= 32; w0..w2 = the 48 bases from j0
+    __device__ __forceinline__ uint32_t run(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t n) const {
+        const uint64_t a = (uint64_t)w0 | ((uint64_t)w1 << 32), b = (uint64_t)w1 | ((uint64_t)w2 << 32);
+        uint32_t acc = 0;
+        const uint32_t na = n < 16u ? n : 16u;
+        for (uint32_t j = 0; j < na; j++) acc += lut[(uint32_t)(a >> (2 * j)) & kmask];
+        for (uint32_t j = 16; j < n; j++) acc += lut[(uint32_t)(b >> (2 * (j - 16))) & kmask];
+        return acc;
+    }
+    __device__ __forceinline__ uint64_t P(uint32_t i) const {
+        const uint4 *q = reinterpret_cast<const uint4 *>(R + (i >> PFX_BLOCK_SHIFT));
+        const uint4 u = q[0];
+        uint64_t c = (uint64_t)u.x | ((uint64_t)u.y << 32);
+        const uint32_t r = i & (PFX_BLOCK - 1);
+        if (r == 0) return c;
+        const uint4 v = q[1];  // codes[1..4]
+        const bool hi = r >= 32;
+        if (hi) c += u.z;
+        return c + run(hi ? v.y : u.w, hi ? v.z : v.x, hi ? v.w : v.y, r & 31u);
     }
 };
 

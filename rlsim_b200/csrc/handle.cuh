@@ -235,6 +235,8 @@ struct rlsim_handle {
     uint32_t fa_n = 0;
     DBuf<uint64_t> d_off, d_expr, d_mol_off, d_Cf, d_Cr;  // coarse prefix sums
     DBuf<uint32_t> d_Ff, d_Fr;                          // fine (in-block) prefix sums
+    DBuf<Rec32> d_Rf;                                   // record layout of the forward sums (clean transcripts; common.cuh)
+    bool rec_layout = false;                            // records in use for the current model (symmetric table, k <= 6)
     uint32_t prefix_upto = 0;  // transcripts [0, prefix_upto) have valid priming prefix sums IN HBM for the current model
     // fused path (after_prim / after_prim_double): prefix sums in shared memory, work items = runs of transcripts
     PinVec<FusedItem> h_fitems_s, h_fitems_l;     // small-class / large-class items of the last build (CTA-cooperative kernel)

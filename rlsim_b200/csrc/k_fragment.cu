@@ -99,6 +99,44 @@ __device__ __forceinline__ uint32_t prime_search(const Profile &pf, uint32_t ple
     return base + q + c;
 }
 
+// The same search on the record layout (common.cuh): interpolate over the records' coarse sums, then walk the half of the
+// block that holds the target, recomputing weights from the record's own codes - no read beyond the block's record.
+__device__ __forceinline__ uint32_t prime_search(const RProfile &pf, uint32_t plen, uint32_t start, uint32_t end, uint64_t tgt) {
+    uint32_t lo = start >> PFX_BLOCK_SHIFT, hi = ((end - 1) >> PFX_BLOCK_SHIFT) + 1;  // coarse[lo] <= tgt < coarse[hi]
+    if (hi - lo > 1) {
+        uint64_t clo = pf.R[lo].coarse, chi = pf.R[hi].coarse;
+#pragma unroll 1
+        for (int it = 0; it < PRIME_INTERP_STEPS && hi - lo > 1; it++) {
+            double f = (double)(tgt - clo) / (double)(chi - clo);
+            uint32_t g = lo + (uint32_t)(f * (double)(hi - lo));
+            if (g >= hi) g = hi - 1;
+            uint64_t a = pf.R[g].coarse, b = pf.R[g + 1].coarse;
+            if (tgt < a) { hi = g; chi = a; }
+            else if (tgt >= b) { lo = g + 1; clo = b; }
+            else { lo = g; hi = g + 1; clo = a; chi = b; }
+        }
+        while (hi - lo > 1) {
+            uint32_t mid = lo + ((hi - lo) >> 1);
+            uint64_t c = pf.R[mid].coarse;
+            if (c <= tgt) { lo = mid; clo = c; } else { hi = mid; chi = c; }
+        }
+    }
+    const uint4 *q = reinterpret_cast<const uint4 *>(pf.R + lo);
+    const uint4 u = q[0], v = q[1];
+    uint32_t r = (uint32_t)(tgt - ((uint64_t)u.x | ((uint64_t)u.y << 32)));  // < block sum
+    const bool up = r >= u.z;  // the target lies in the block's second half
+    if (up) r -= u.z;
+    const uint32_t w0 = up ? v.y : u.w, w1 = up ? v.z : v.x, w2 = up ? v.w : v.y;
+    const uint64_t a = (uint64_t)w0 | ((uint64_t)w1 << 32), b = (uint64_t)w1 | ((uint64_t)w2 << 32);
+    uint32_t acc = 0, j = 0;
+    for (; j < 31; j++) {
+        const uint64_t win = j < 16 ? a >> (2 * j) : b >> (2 * (j - 16));
+        acc += pf.lut[(uint32_t)win & pf.kmask];
+        if (acc > r) break;
+    }
+    return (lo << PFX_BLOCK_SHIFT) + (up ? 32u : 0u) + j;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Compact profile: what one WARP keeps in shared memory for one transcript (k_fused_warp).  0.625 B per entry instead of
 // the 4.1 B of the two-level arrays, so that 40 warps per SM each hold their own transcript:
@@ -225,6 +263,7 @@ __device__ __forceinline__ void enqueue(const FragOut &o, uint32_t t, uint64_t m
     }
 }
 
+
 template <class PF>
 struct MolCtxT {
     uint32_t t, tg, L, proflen;
@@ -315,7 +354,8 @@ __device__ __forceinline__ Header mol_header(const DevModel &m, const CTX &c, ui
     return h;
 }
 
-__device__ void prim_jump(const DevModel &m, const MolCtx &c, uint64_t mol, int polyAend, const FragOut &o,
+template <class PF>
+__device__ void prim_jump(const DevModel &m, const MolCtxT<PF> &c, uint64_t mol, int polyAend, const FragOut &o,
                           unsigned int *hist_s, uint32_t hist_s_n) {  // fragmentor.go:303-351
     int ltmp = (int)c.L - (int)c.proflen;
     if (polyAend < ltmp) return;
@@ -356,6 +396,20 @@ __device__ __forceinline__ MolCtx make_ctx(const DevModel &m, const DevTranscrip
     c.mirror = tr.sym && tr.Fr && tr.dirty[t] == 0;
     return c;
 }
+// the record layout serves the transcripts without letters outside ACGT (forward sums; the reverse draw reads them mirrored)
+__device__ __forceinline__ bool uses_records(const DevTranscripts &tr, uint32_t t) { return tr.Rf != nullptr && tr.dirty[t] == 0; }
+__device__ __forceinline__ MolCtxT<RProfile> make_ctx_rec(const DevModel &m, const DevTranscripts &tr, uint32_t t, const uint32_t *lut) {
+    MolCtxT<RProfile> c;
+    c.t = t;
+    c.tg = m.first_index + t;
+    c.L = tr.len[t];
+    c.proflen = c.L > (uint32_t)m.k ? c.L - (uint32_t)m.k : 0;
+    c.off = tr.off[t];
+    c.Pf = RProfile{tr.Rf + rec_base(c.off, t), lut, (1u << (2 * m.k)) - 1u};
+    c.Pr = c.Pf;
+    c.mirror = true;  // records exist only with a symmetric table
+    return c;
+}
 
 template <int KIND>
 __global__ void __launch_bounds__(FRAG_THREADS, 10)
@@ -379,7 +433,8 @@ k_fragment(const __grid_constant__ DevModel m, DevTranscripts tr, uint64_t g_beg
         Header h = mol_header<KIND>(m, c, mol);
         atomicAdd(&hist_pa[h.tail], 1u);
         if (KIND == 2) {
-            prim_jump(m, c, mol, h.polyAend, o, hist_s, hist_s_n);
+            if (uses_records(tr, t)) prim_jump(m, make_ctx_rec(m, tr, t, tr.lut), mol, h.polyAend, o, hist_s, hist_s_n);
+            else prim_jump(m, c, mol, h.polyAend, o, hist_s, hist_s_n);
         } else if (h.nb > FRAG_LOCAL_BREAKS) {
             unsigned int slot = atomicAdd(o.long_count, 1u);
             if (slot < o.long_cap) { o.long_list[slot] = make_uint2(t, (uint32_t)(mol & 0xffffffffu)); o.long_hi[slot] = (uint32_t)(mol >> 32); }
@@ -400,10 +455,12 @@ k_fragment(const __grid_constant__ DevModel m, DevTranscripts tr, uint64_t g_beg
             }
             br[cnt] = length;  // length is >= every draw, so it sorts last
             PxStream iv = mol_stream(m, c.tg, mol, SUB_INTERVAL);
+            uint32_t n_queued = 0;
             for (int32_t i = 0; i < h.nb; i++) {  // the last interval is never visited (fragmentor.go:132)
                 if (KIND == 1) plain_interval(m, c, iv, (uint32_t)i, br[i], br[i + 1], o, hist_s, hist_s_n);
-                else if (br[i + 1] - br[i] >= m.low) enqueue(o, t, mol, (uint32_t)i, br[i], br[i + 1]);
+                else if (br[i + 1] - br[i] >= m.low) { enqueue(o, t, mol, (uint32_t)i, br[i], br[i + 1]); n_queued++; }
             }
+            if (n_queued && tr.Rf != nullptr && tr.dirty[t] != 0) atomicAdd(o.q_count + 1, (unsigned long long)n_queued);
         }
     }
     __syncthreads();
@@ -416,18 +473,24 @@ k_fragment(const __grid_constant__ DevModel m, DevTranscripts tr, uint64_t g_beg
 // One thread per queued interval: the two dependent priming searches (nnthermo.go:203-217) + filters + emit.
 // Kept separate from k_fragment so that this latency-bound part runs lean (few registers, full occupancy).
 constexpr int IV_THREADS = 256;
+// REC = 1: intervals of transcripts on the record layout (k-mer LUT staged in shared memory); REC = 0: the two-level arrays
+// (all transcripts when there are no records, else only those with letters outside ACGT).
+template <int REC>
 __global__ void __launch_bounds__(IV_THREADS, 5)
 k_intervals(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, uint64_t n_q, uint32_t hist_s_n) {
     extern __shared__ unsigned int hist_s[];
     for (uint32_t i = threadIdx.x; i < hist_s_n; i += IV_THREADS) hist_s[i] = 0;
+    uint32_t *lut_s = hist_s + hist_s_n;
+    if (REC) for (uint32_t i = threadIdx.x; i < (1u << (2 * m.k)); i += IV_THREADS) lut_s[i] = tr.lut[i];
     __syncthreads();
     for (uint64_t g = (uint64_t)blockIdx.x * IV_THREADS + threadIdx.x; g < n_q; g += (uint64_t)gridDim.x * IV_THREADS) {
         uint4 a = o.q_a[g];
+        if (tr.Rf != nullptr && (tr.dirty[a.x] == 0) != (REC != 0)) continue;  // the other launch's interval
         uint2 b = o.q_b[g];
         uint64_t mol = (uint64_t)a.y | ((uint64_t)b.y << 32);
-        MolCtx c = make_ctx(m, tr, a.x);
-        PxStream iv = mol_stream(m, c.tg, mol, SUB_INTERVAL);
-        after_interval(m, c, iv, a.z, a.w, b.x, o, hist_s, hist_s_n);
+        PxStream iv = mol_stream(m, m.first_index + a.x, mol, SUB_INTERVAL);
+        if (REC) after_interval(m, make_ctx_rec(m, tr, a.x, lut_s), iv, a.z, a.w, b.x, o, hist_s, hist_s_n);
+        else after_interval(m, make_ctx(m, tr, a.x), iv, a.z, a.w, b.x, o, hist_s, hist_s_n);
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < hist_s_n; i += IV_THREADS)
@@ -479,8 +542,11 @@ k_fragment_long(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o
         }
     }
     PxStream iv = mol_stream(m, c.tg, mol, SUB_INTERVAL);
+    const bool rec = uses_records(tr, t);
+    const MolCtxT<RProfile> cr = rec ? make_ctx_rec(m, tr, t, tr.lut) : MolCtxT<RProfile>{};
     for (uint32_t i = threadIdx.x; i < (uint32_t)h.nb; i += LONG_THREADS) {
         if (m.method == RLSIM_PRE_PRIM) plain_interval(m, c, iv, i, brs[i], brs[i + 1], o, nullptr, 0);
+        else if (rec) after_interval(m, cr, iv, i, brs[i], brs[i + 1], o, nullptr, 0);
         else after_interval(m, c, iv, i, brs[i], brs[i + 1], o, nullptr, 0);
     }
 }
@@ -956,7 +1022,8 @@ int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr
     return 0;
 }
 
-int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint64_t n_q) {
+// n_q_dirty: queued intervals of transcripts that stay on the two-level arrays although records exist (q_count[1])
+int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint64_t n_q, uint64_t n_q_dirty) {
     if (n_q == 0) return 0;
     FragOut o{fb.keys, fb.cap, key_len_bits(m.high), fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, fb.long_cap, fb.long_count,
               fb.error, fb.q_a, fb.q_b, fb.q_cap, fb.q_count};
@@ -964,8 +1031,32 @@ int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &t
     uint64_t blocks = (n_q + IV_THREADS - 1) / IV_THREADS;
     if (blocks > 0x7fffffffull) return RLSIM_E_UNSUPPORTED;
     const uint64_t max_blocks = 148ull * 5 * 6;
-    k_intervals<<<(unsigned)std::min(blocks, max_blocks), IV_THREADS, (size_t)hist_s_n * 4, st>>>(m, tr, o, n_q, hist_s_n);
+    if (tr.Rf != nullptr) {
+        const size_t smem = (size_t)hist_s_n * 4 + ((size_t)4 << (2 * m.k));
+        k_intervals<1><<<(unsigned)std::min(blocks, max_blocks), IV_THREADS, smem, st>>>(m, tr, o, n_q, hist_s_n);
+        if (n_q_dirty == 0) return 0;
+    }
+    k_intervals<0><<<(unsigned)std::min(blocks, max_blocks), IV_THREADS, (size_t)hist_s_n * 4, st>>>(m, tr, o, n_q, hist_s_n);
     return 0;
+}
+
+// P(0..n) of one profile, whichever layout holds it (parity probe)
+__global__ void k_probe_prefix(const __grid_constant__ DevModel m, DevTranscripts tr, uint32_t t, int reverse, uint64_t *out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t L = tr.len[t], proflen = L > (uint32_t)m.k ? L - (uint32_t)m.k : 0;
+    if (i > proflen) { out[i] = 0; return; }
+    if (uses_records(tr, t)) {
+        const MolCtxT<RProfile> c = make_ctx_rec(m, tr, t, tr.lut);
+        out[i] = reverse ? c.Pf.P(proflen + 1) - c.Pf.P(proflen + 1 - i) : c.Pf.P(i);  // mirrored: P_rev(i) = W(n+1) - W(n+1-i)
+    } else {
+        const MolCtx c = make_ctx(m, tr, t);
+        if (!reverse) out[i] = c.Pf.P(i);
+        else out[i] = c.mirror ? c.Pf.P(proflen + 1) - c.Pf.P(proflen + 1 - i) : c.Pr.P(i);
+    }
+}
+void launch_probe_prefix(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint32_t t, int reverse, uint64_t *out, uint32_t n) {
+    if (n) k_probe_prefix<<<(n + 127) / 128, 128, 0, st>>>(m, tr, t, reverse, out, n);
 }
 
 // ---- fused path launches.  smem_optin = the device's opt-in shared memory per block.

@@ -202,7 +202,7 @@ constexpr int PFX_TILE_U32 = 32 * PFX_ROW_U32;
 __global__ void __launch_bounds__(PFX_THREADS, 4)
 k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, const uint32_t *__restrict__ wq_f,
          const uint32_t *__restrict__ wq_r, const unsigned long long *__restrict__ kmax_bits, uint32_t *__restrict__ Ff,
-         uint32_t *__restrict__ Fr, uint64_t *__restrict__ Cf, uint64_t *__restrict__ Cr, int lut_in_smem,
+         uint32_t *__restrict__ Fr, uint64_t *__restrict__ Cf, uint64_t *__restrict__ Cr, Rec32 *__restrict__ Rf, int lut_in_smem,
          unsigned int *__restrict__ work) {
     extern __shared__ __align__(16) unsigned char pfx_smem[];
     uint32_t *tile_s = reinterpret_cast<uint32_t *>(pfx_smem);                 // 8 warps x PFX_TILE_U32
@@ -232,7 +232,10 @@ k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, c
         uint32_t *F = (reverse ? Fr : Ff) + o;
         uint64_t *C = (reverse ? Cr : Cf) + coarse_base(o, t);
         if (tr.sym && reverse && tr.dirty[t] == 0) continue;  // read mirrored from the forward arrays (priming_mirror)
-        if (lane == 0) C[0] = 0;
+        // record layout (common.cuh): clean transcripts write one 32-byte record per block instead of 4 B per entry
+        const bool use_rec = Rf != nullptr && tr.dirty[t] == 0;
+        Rec32 *R = use_rec ? Rf + rec_base(o, t) : nullptr;
+        if (lane == 0) { if (use_rec) R[0].coarse = 0; else C[0] = 0; }
         if (L < (uint32_t)k + (tr.sym && !reverse ? 0u : 1u)) continue;
         // symmetric mode: the forward arrays also hold window len-k, the first window of the reverse profile
         const uint32_t proflen = L - (uint32_t)k + (tr.sym && !reverse ? 1u : 0u);
@@ -260,6 +263,25 @@ k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, c
             // block totals of the 4 blocks of this sub-tile -> coarse sums
             const uint32_t g0 = __shfl_sync(0xffffffffu, incl, 7), g1 = __shfl_sync(0xffffffffu, incl, 15),
                            g2 = __shfl_sync(0xffffffffu, incl, 23), g3 = __shfl_sync(0xffffffffu, incl, 31);
+            if (use_rec) {
+                // first-half sums of the four blocks sit in lanes 3, 11, 19, 27 of the 8-lane scans
+                const uint32_t h0 = __shfl_sync(0xffffffffu, incl, 3), h1 = __shfl_sync(0xffffffffu, incl, 11),
+                               h2 = __shfl_sync(0xffffffffu, incl, 19), h3 = __shfl_sync(0xffffffffu, incl, 27);
+                if (lane < 4 && i0 + lane * PFX_BLOCK < proflen) {
+                    uint64_t before = carry;
+                    if (lane >= 1) before += g0;
+                    if (lane >= 2) before += g1;
+                    if (lane >= 3) before += g2;
+                    const uint32_t half = lane == 0 ? h0 : lane == 1 ? h1 : lane == 2 ? h2 : h3;
+                    const uint32_t blk = (i0 >> PFX_BLOCK_SHIFT) + lane;
+                    const uint32_t *pk = tr.packed + (o >> 4) + 4 * blk;  // 16 bases per word: the block's 80 bases are 5 words
+                    uint4 *dst = reinterpret_cast<uint4 *>(R + blk);
+                    dst[0] = make_uint4((uint32_t)before, (uint32_t)(before >> 32), half, __ldg(pk));
+                    dst[1] = make_uint4(__ldg(pk + 1), __ldg(pk + 2), __ldg(pk + 3), __ldg(pk + 4));
+                }
+                carry += (uint64_t)g0 + g1 + g2 + g3;
+                continue;
+            }
             if (lane < 4) {  // coarse[(i0 >> 6) + lane + 1] = sum of everything before block lane+1 of this sub-tile
                 uint64_t cs = carry + g0;
                 if (lane >= 1) cs += g1;
@@ -286,12 +308,13 @@ k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, c
             }
             __syncwarp();
         }
+        if (use_rec && lane == 0) R[(proflen + PFX_BLOCK - 1) >> PFX_BLOCK_SHIFT].coarse = carry;  // closing record: the total
     }
 }
 
 void launch_prefix(cudaStream_t st, const DevTranscripts &tr, uint32_t t_begin, uint32_t t_end, int k, double T,
                    const uint32_t *wq_f, const uint32_t *wq_r, const unsigned long long *kmax_bits, uint32_t *Ff, uint32_t *Fr,
-                   uint64_t *Cf, uint64_t *Cr, int strands, unsigned int *work) {
+                   uint64_t *Cf, uint64_t *Cr, Rec32 *Rf, int strands, unsigned int *work) {
     if (t_end <= t_begin) return;
     int lut_in_smem = (k <= 6);
     size_t smem = (size_t)(PFX_THREADS / 32) * PFX_TILE_U32 * 4 + (lut_in_smem ? ((size_t)4 << (2 * k)) : 16);
@@ -299,7 +322,7 @@ void launch_prefix(cudaStream_t st, const DevTranscripts &tr, uint32_t t_begin, 
     uint32_t blocks = std::min<uint32_t>((warps_needed + 7) / 8, 148u * 6u);
     cudaMemsetAsync(work, 0, 2 * sizeof(unsigned int), st);
     dim3 grid(blocks, strands);
-    k_prefix<<<grid, PFX_THREADS, smem, st>>>(tr, t_begin, t_end, k, T, wq_f, wq_r, kmax_bits, Ff, Fr, Cf, Cr, lut_in_smem, work);
+    k_prefix<<<grid, PFX_THREADS, smem, st>>>(tr, t_begin, t_end, k, T, wq_f, wq_r, kmax_bits, Ff, Fr, Cf, Cr, Rf, lut_in_smem, work);
 }
 
 }  // namespace rl

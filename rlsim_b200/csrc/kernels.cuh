@@ -11,8 +11,9 @@ void launch_ingest(cudaStream_t st, const uint8_t *src, const uint64_t *src_off,
 void launch_kmer_lut(cudaStream_t st, int k, double T, double *K, unsigned long long *kmax_bits, uint32_t *wq_f,
                      uint32_t *wq_r, unsigned int *asym);
 void launch_prefix(cudaStream_t st, const DevTranscripts &tr, uint32_t t_begin, uint32_t t_end, int k, double T, const uint32_t *wq_f, const uint32_t *wq_r,
-                   const unsigned long long *kmax_bits, uint32_t *Ff, uint32_t *Fr, uint64_t *Cf, uint64_t *Cr, int strands,
+                   const unsigned long long *kmax_bits, uint32_t *Ff, uint32_t *Fr, uint64_t *Cf, uint64_t *Cr, Rec32 *Rf, int strands,
                    unsigned int *work);
+void launch_probe_prefix(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint32_t t, int reverse, uint64_t *out, uint32_t n);
 
 // k_fragment.cu
 struct FragBuffers {
@@ -24,7 +25,7 @@ struct FragBuffers {
 };
 int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint64_t g_begin, uint64_t g_end,
                     const FragBuffers &fb);
-int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint64_t n_q);
+int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint64_t n_q, uint64_t n_q_dirty);
 int launch_fragment_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t n_long);
 // fused prefix + fragmentation (after_prim / after_prim_double): prefix sums in shared memory
 struct FusedItem { uint32_t t0, t1; uint64_t g0, g1; };  // transcripts [t0, t1), global molecules [g0, g1)
