@@ -107,7 +107,7 @@ DevTranscripts make_tr(rlsim_handle *h) {
     t.dirty = h->d_dirty.p;
     // record layout of the forward sums: needs the mirrored reverse draw (symmetric table) and a LUT that fits shared memory
     h->rec_layout = needs_fwd(h->p.frag_method) && h->lut_valid && h->lut_sym && h->want_mirror && h->p.kmer_len <= 6 &&
-                    getenv("RLSIM_NO_RECORDS") == nullptr;
+                    getenv("RLSIM_RECORDS") != nullptr;  // opt-in: measured slower than the two-level arrays (profiles/r2_experiments.md)
     t.Rf = h->rec_layout ? h->d_Rf.p : nullptr;
     t.lut = h->d_wq_f.p;
     t.sym = h->lut_sym && h->want_mirror ? 1 : 0;
@@ -255,6 +255,18 @@ bool eager_possible(rlsim_handle *h, uint32_t n0) {
 
 bool ns_need(rlsim_handle *h, uint64_t ns) {  // would any per-species array be reallocated for ns species?
     return ns > h->d_sp_tr.n || ns > h->d_sp_start.n || ns > h->d_sp_len.n || ns > h->d_sp_count.n || ns > h->d_sp_eff.n || ns > h->d_sp_gc.n;
+}
+
+// table of the first transcript of every warp of k_fragment over the molecules [g0, g1): depends on the expression levels
+// only, so the resident steps of one transcript set build it once
+int ensure_warp_table(rlsim_handle *h, const DevTranscripts &tr, uint64_t g0, uint64_t g1) {
+    const uint32_t n = (uint32_t)h->h_len.size();
+    if (h->warp_t_n == n && h->warp_t_g0 == g0 && h->warp_t_g1 == g1) return 0;
+    CK(h, h->d_warp_t.ensure((g1 - g0 + 31) / 32 + 1));
+    launch_warp_transcripts(h->st, tr, g0, g1, h->d_warp_t.p);
+    h->launches[RLSIM_T_FRAGMENT]++;
+    h->warp_t_n = n; h->warp_t_g0 = g0; h->warp_t_g1 = g1;
+    return 0;
 }
 
 // ---- fused path: prefix sums in shared memory (k_fused).  Eligible: the priming methods whose intervals are searched
@@ -411,7 +423,8 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
         int fell_back = 0;
         if ((rc = run_fused_range(h, m, tr, fb, t0, t1, &n_long, &fell_back)) || fell_back) { h->fused_disabled = true; h->eager_failed = true; return 0; }
     } else {
-        if ((rc = launch_fragment(h->st, m, tr, g0, g1, fb))) { h->eager_failed = true; return 0; }
+        if ((rc = ensure_warp_table(h, tr, g0, g1))) return rc;
+        if ((rc = launch_fragment(h->st, m, tr, g0, g1, fb, h->d_warp_t.p))) { h->eager_failed = true; return 0; }
         CK(h, cudaMemcpyAsync(h->pin, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
         CK(h, cudaMemcpyAsync(h->pin + 1, h->d_counters.p + 2, 8, cudaMemcpyDeviceToHost, h->st));
         CK(h, cudaMemcpyAsync(h->pin + 3, h->d_counters.p + 3, 8, cudaMemcpyDeviceToHost, h->st));
@@ -733,7 +746,7 @@ int rlsim_clear_transcripts(rlsim_handle *h) {
     cudaStreamSynchronize(h->st);
     h->h_srclen.clear(); h->h_expr.clear(); h->h_off.clear(); h->h_len.clear();
     h->prefix_upto = 0; h->fragmented = h->amplified = h->sampled = false;
-    h->fused_disabled = false; h->fitems_key = -1; h->max_len = 0;
+    h->fused_disabled = false; h->fitems_key = -1; h->max_len = 0; h->warp_t_n = 0;
     h->n_mol = h->total_padded = h->n_frag = h->n_sp = h->n_out = h->pool_total = 0;
     h->sum_expr = h->sum_expr_len = 0; h->mol_off_valid = false;
     h->h_mol_off.clear();
@@ -831,10 +844,16 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     // ---- pipeline: H2D of chunk c+1 on the copy stream overlaps ingest (+ prefix sums) of chunk c
     const uint64_t chunk_bytes = getenv("RLSIM_CHUNK_BYTES") ? std::max(1ll, atoll(getenv("RLSIM_CHUNK_BYTES")))  // test knob
                                : (uint64_t)(getenv("RLSIM_CHUNK_MB") ? std::max(1, atoi(getenv("RLSIM_CHUNK_MB"))) : 32) << 20;
+    // The last chunks taper (1/2, 1/4, 1/8, 1/8 of a chunk): what remains to be computed after the last byte has arrived is
+    // the work of the last group, so it should be small.
     std::vector<uint32_t> cuts{0};
     for (uint32_t t0 = 0; t0 < n;) {
+        const uint64_t left = nbytes - rel[t0];
+        uint64_t want = chunk_bytes;
+        if (left <= chunk_bytes + chunk_bytes / 2) want = left > chunk_bytes / 4 ? left / 2 : left;
+        want = std::max<uint64_t>(want, std::min<uint64_t>(chunk_bytes, 1u << 20));
         uint32_t t1 = t0;
-        while (t1 < n && rel[t1] - rel[t0] < chunk_bytes) t1++;
+        while (t1 < n && rel[t1] - rel[t0] < want) t1++;
         cuts.push_back(t1);
         t0 = t1;
     }
@@ -1119,7 +1138,8 @@ int rlsim_fragment(rlsim_handle *h) {
         if (fused) {
             if ((rc = run_fused_range(h, m, tr, fb, 0, n, &n_long, &fell_back))) { tm.stop(); h->fused_disabled = true; attempt--; if ((rc = finalize(h))) return rc; tr = make_tr(h); continue; }
         } else {
-            rc = launch_fragment(h->st, m, tr, 0, h->n_mol, fb);
+            if ((rc = ensure_warp_table(h, tr, 0, h->n_mol))) return rc;
+            rc = launch_fragment(h->st, m, tr, 0, h->n_mol, fb, h->d_warp_t.p);
             if (rc) FAIL(h, rc, "fragmentation launch configuration unsupported (poly(A) maximum too large)");
             CK(h, cudaMemcpyAsync(&n_long, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
             CK(h, cudaMemcpyAsync(&n_q, h->d_counters.p + 2, 8, cudaMemcpyDeviceToHost, h->st));

@@ -235,6 +235,8 @@ struct rlsim_handle {
     uint32_t fa_n = 0;
     DBuf<uint64_t> d_off, d_expr, d_mol_off, d_Cf, d_Cr;  // coarse prefix sums
     DBuf<uint32_t> d_Ff, d_Fr;                          // fine (in-block) prefix sums
+    DBuf<uint32_t> d_warp_t;                            // first transcript of every warp of k_fragment (k_warp_transcripts)
+    uint64_t warp_t_g0 = 0, warp_t_g1 = 0; uint32_t warp_t_n = 0;  // what the table covers (molecule range, transcripts)
     DBuf<Rec32> d_Rf;                                   // record layout of the forward sums (clean transcripts; common.cuh)
     bool rec_layout = false;                            // records in use for the current model (symmetric table, k <= 6)
     uint32_t prefix_upto = 0;  // transcripts [0, prefix_upto) have valid priming prefix sums IN HBM for the current model

@@ -221,19 +221,32 @@ k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, c
     const uint32_t lane = threadIdx.x & 31;
     uint32_t *tile = tile_s + (threadIdx.x >> 5) * PFX_TILE_U32;
 
-    for (;;) {
-        uint32_t t = 0;
-        if (lane == 0) t = t_begin + atomicAdd(&work[reverse], 1u);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= t_end) break;
-        if (tr.expr[t] == 0) continue;  // pool.go:104: never fragmented
-        const uint32_t L = tr.len[t];
-        const uint64_t o = tr.off[t];
+    // Transcripts are short (~9 sub-tiles): the chain work counter -> transcript metadata -> first words is three dependent
+    // round trips per transcript, as long as the sums themselves.  The loop is software-pipelined two deep: the counter
+    // for the transcript after next and the metadata of the next one are in flight while the current one is summed.
+    auto fetch = [&]() -> uint32_t { return lane == 0 ? t_begin + atomicAdd(&work[reverse], 1u) : 0u; };  // result pending on lane 0
+    struct Meta { uint32_t t, L, expressed, dirty; uint64_t o; };
+    auto load_meta = [&](uint32_t t) {
+        Meta mt{t, 0u, 0u, 0u, 0ull};
+        if (t < t_end) { mt.L = tr.len[t]; mt.o = tr.off[t]; mt.expressed = tr.expr[t] != 0; mt.dirty = tr.dirty[t]; }
+        return mt;
+    };
+    Meta cur = load_meta(__shfl_sync(0xffffffffu, fetch(), 0));
+    uint32_t pending = fetch();
+    for (;; ) {
+        if (cur.t >= t_end) break;
+        const Meta mt = cur;
+        cur = load_meta(__shfl_sync(0xffffffffu, pending, 0));  // the next transcript's metadata: in flight from here on
+        pending = fetch();
+        const uint32_t t = mt.t;
+        if (!mt.expressed) continue;  // pool.go:104: never fragmented
+        const uint32_t L = mt.L;
+        const uint64_t o = mt.o;
         uint32_t *F = (reverse ? Fr : Ff) + o;
         uint64_t *C = (reverse ? Cr : Cf) + coarse_base(o, t);
-        if (tr.sym && reverse && tr.dirty[t] == 0) continue;  // read mirrored from the forward arrays (priming_mirror)
+        if (tr.sym && reverse && mt.dirty == 0) continue;  // read mirrored from the forward arrays (priming_mirror)
         // record layout (common.cuh): clean transcripts write one 32-byte record per block instead of 4 B per entry
-        const bool use_rec = Rf != nullptr && tr.dirty[t] == 0;
+        const bool use_rec = Rf != nullptr && mt.dirty == 0;
         Rec32 *R = use_rec ? Rf + rec_base(o, t) : nullptr;
         if (lane == 0) { if (use_rec) R[0].coarse = 0; else C[0] = 0; }
         if (L < (uint32_t)k + (tr.sym && !reverse ? 0u : 1u)) continue;

@@ -23,8 +23,10 @@ struct FragBuffers {
     int *error;
     uint4 *q_a; uint2 *q_b; uint64_t q_cap; unsigned long long *q_count;               // interval work queue
 };
+// warp_t: optional table from launch_warp_transcripts over the same molecule range (FRAG_THREADS is a multiple of 32)
 int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint64_t g_begin, uint64_t g_end,
-                    const FragBuffers &fb);
+                    const FragBuffers &fb, const uint32_t *warp_t = nullptr);
+void launch_warp_transcripts(cudaStream_t st, const DevTranscripts &tr, uint64_t g_begin, uint64_t g_end, uint32_t *warp_t);
 int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint64_t n_q, uint64_t n_q_dirty);
 int launch_fragment_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t n_long);
 // fused prefix + fragmentation (after_prim / after_prim_double): prefix sums in shared memory

@@ -359,3 +359,38 @@ def test_fused_path_variants(oracle, gpu, monkeypatch):
     assert lens[t_big] > 25000
     b = bytearray(seqs[t_big]); b[100] = ord("N"); seqs[t_big] = bytes(b)
     both(["-n", "30000", "-c", "3", "-si", "15", "-f", "after_prim_double"], names, seqs, levels, expect_fused=False, eager=False)
+
+
+def test_record_layout_opt_in(oracle, gpu, monkeypatch):
+    """RLSIM_RECORDS=1: the forward prefix sums of transcripts without letters outside ACGT are kept as one 32-byte record per
+    64-entry block (coarse sum, half sum, codes) and the searches recompute weights from the record.  Same prefix sums (probe),
+    same fragments as the two-level arrays and as the oracle - dirty transcripts (two-level arrays, second k_intervals launch),
+    prim_jump, deferred long molecules and k = 1 included."""
+    names, seqs, levels = util.synth_transcriptome(80, seed=51, mean_len=1600, hi=9000, total_molecules=30000, non_acgt=0.0)
+    seqs = list(seqs)
+    for t in (3, 40):
+        b = bytearray(seqs[t]); b[50] = ord("N"); b[200:204] = b"RYKM"; seqs[t] = bytes(b)
+    seqs[10] = seqs[10][:6]
+    seqs[11] = seqs[11][:70]
+    for argv in (["-n", "30000", "-c", "4", "-si", "3", "-f", "after_prim_double"], ["-n", "20000", "-c", "4", "-si", "3", "-f", "after_prim"],
+                 ["-n", "5000", "-c", "4", "-si", "3", "-f", "prim_jump:300"], ["-n", "5000", "-c", "3", "-si", "4", "-k", "1"]):
+        args = util.parse(argv)
+        plain = util.run_gpu(gpu, args, names, seqs, levels)
+        monkeypatch.setenv("RLSIM_RECORDS", "1")
+        rec = _compare_records(oracle, gpu, argv, names, seqs, levels)
+        for k in ("tr", "start", "end", "count0", "count"):
+            assert np.array_equal(plain.species()[k], rec.species()[k]), (argv, k)
+        pa = int(rec.stats().polya_max)
+        for t in (0, 3, 10, 11, 40, 79):
+            n = len(seqs[t]) + pa + 1
+            for reverse in ((0, 1) if "after_prim_double" in argv else (0,)):
+                got = rec.probe_prefix(t, reverse, n)
+                monkeypatch.delenv("RLSIM_RECORDS")
+                want = plain.probe_prefix(t, reverse, n)
+                monkeypatch.setenv("RLSIM_RECORDS", "1")
+                assert np.array_equal(got, want), (argv, t, reverse)
+        monkeypatch.delenv("RLSIM_RECORDS")
+    # deferred long molecules on the record layout
+    names, seqs, levels = util.synth_transcriptome(6, seed=8, mean_len=60000, sigma=0.05, lo=50000, hi=70000, total_molecules=600)
+    monkeypatch.setenv("RLSIM_RECORDS", "1")
+    _compare_records(oracle, gpu, ["-n", "20000", "-c", "5", "-si", "9"], names, seqs, levels)
