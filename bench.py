@@ -346,7 +346,9 @@ def main():
         n_v = step_e2e(VS)
         d_eager = result_digest(wl.out, n_v)
         eager_flag = bool(int(h.stats().flags) & _native.F_EAGER)
+        os.environ["RLSIM_NO_GROUPS"] = "1"  # one monolithic launch per stage: the path that shares least with the eager one
         n_m = step_resident(VS)
+        del os.environ["RLSIM_NO_GROUPS"]
         mono_flag = bool(int(h.stats().flags) & _native.F_EAGER)
         packed_m, _ = h.sampled_packed(elem_bytes=2)
         d_mono = result_digest(packed_m, n_m)

@@ -386,8 +386,15 @@ int run_fused_range(rlsim_handle *h, const DevModel &m, const DevTranscripts &tr
 
 // Fragment, dedup and amplify the transcripts [t0, t1) of a chunk whose ingest + prefix sums are already queued on
 // the compute stream.  The host waits on the compute stream only; the copy stream keeps feeding later chunks.
-int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
+// timed: record stage timers (only when no chunk copies are in flight: see the note on timing events in add_core)
+int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1, bool timed = false) {
     int rc;
+    struct OptTimer {  // a StageTimer that exists only when `timed`
+        StageTimer *t = nullptr;
+        OptTimer(bool on, rlsim_handle *h, int stage, cudaStream_t st = nullptr) { if (on) t = new StageTimer(h, stage, 0, st); }
+        void stop() { if (t) { t->stop(); delete t; t = nullptr; } }
+        ~OptTimer() { stop(); }
+    };
     const bool trace = getenv("RLSIM_TRACE") != nullptr;
     auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tt0 = now_ms();
@@ -424,7 +431,9 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
         if ((rc = run_fused_range(h, m, tr, fb, t0, t1, &n_long, &fell_back)) || fell_back) { h->fused_disabled = true; h->eager_failed = true; return 0; }
     } else {
         if ((rc = ensure_warp_table(h, tr, g0, g1))) return rc;
+        OptTimer tf(timed, h, RLSIM_T_FRAGMENT);
         if ((rc = launch_fragment(h->st, m, tr, g0, g1, fb, h->d_warp_t.p))) { h->eager_failed = true; return 0; }
+        tf.stop();
         CK(h, cudaMemcpyAsync(h->pin, h->d_long_count.p, 4, cudaMemcpyDeviceToHost, h->st));
         CK(h, cudaMemcpyAsync(h->pin + 1, h->d_counters.p + 2, 8, cudaMemcpyDeviceToHost, h->st));
         CK(h, cudaMemcpyAsync(h->pin + 3, h->d_counters.p + 3, 8, cudaMemcpyDeviceToHost, h->st));
@@ -448,8 +457,10 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
         }
         h->fused_used = true;
     } else {
+        OptTimer ti(timed, h, RLSIM_T_INTERVALS);
         launch_intervals(h->st, m, tr, fb, n_q, n_q_dirty);
         launch_fragment_long(h->st, m, tr, fb, n_long);
+        ti.stop();
         h->launches[RLSIM_T_FRAGMENT] += 1 + (n_long ? 1 : 0); h->launches[RLSIM_T_INTERVALS] += n_q ? 1 : 0;
     }
     CK(h, cudaMemcpyAsync(h->pin + 2, h->d_counters.p, 8, cudaMemcpyDeviceToHost, h->st));
@@ -470,6 +481,7 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
         CK(h, h->d_sp_count0.grow_preserve(need, h->eager_sp, h->st));
         int end_bit = (int)std::min<uint32_t>(64, key_len_bits((uint32_t)h->high) + bits_for(h->total_padded));
         size_t tb = 0;
+        OptTimer td(timed, h, RLSIM_T_DEDUP);
         CK(h, cub::DeviceRadixSort::SortKeys(nullptr, tb, h->d_keys.p + h->eager_keys, h->d_keys_sorted.p, (int)nf, 0, end_bit, h->st));
         if ((rc = cub_temp(h, tb))) return rc;
         CK(h, cub::DeviceRadixSort::SortKeys(h->d_cub.p, tb, h->d_keys.p + h->eager_keys, h->d_keys_sorted.p, (int)nf, 0, end_bit, h->st));
@@ -497,11 +509,14 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
         sp.count0 = h->d_sp_count0.p + h->eager_sp; sp.count = h->d_sp_count.p + h->eager_sp;
         sp.eff = h->keep_debug ? h->d_sp_eff.p + h->eager_sp : nullptr; sp.gc = h->keep_debug ? h->d_sp_gc.p + h->eager_sp : nullptr;
         launch_decode_species(h->st, tr, h->d_uniq.p, sp, (uint32_t)h->high);
+        td.stop();
         if ((rc = ensure_len_eff(h))) return rc;
         m = make_model(h);  // picks up the length-efficiency table pointer
         CK(h, cudaEventRecord(h->ev_sp, h->st));
         CK(h, cudaStreamWaitEvent(h->st_pcr, h->ev_sp, 0));
+        OptTimer tp(timed, h, RLSIM_T_PCR, h->st_pcr);
         launch_pcr(h->st_pcr, m, tr, sp, h->d_error.p);  // thermocycler.go:106-147 for this group's species
+        tp.stop();
         CK(h, cudaEventRecord(h->ev_pcr, h->st_pcr));
         h->pcr_in_flight = true;
         h->launches[RLSIM_T_PCR] += 1;
@@ -515,7 +530,7 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1) {
 }
 
 // everything that needs the complete transcript set: molecule offsets, remaining prefix sums
-int finalize(rlsim_handle *h) {
+int finalize(rlsim_handle *h, bool with_prefix = true) {
     uint32_t n = (uint32_t)h->h_len.size();
     if (!h->mol_off_valid) {
         if (h->h_mol_off.empty()) h->h_mol_off.push_back(0);
@@ -525,7 +540,7 @@ int finalize(rlsim_handle *h) {
         CK(h, cudaStreamSynchronize(h->st));
         h->mol_off_valid = true;
     }
-    if (needs_fwd(h->p.frag_method) && h->prefix_upto < n && !fused_range_ok(h, 0, n)) {
+    if (with_prefix && needs_fwd(h->p.frag_method) && h->prefix_upto < n && !fused_range_ok(h, 0, n)) {
         int rcg = grow_prefix(h, h->total_padded, n, h->prefix_upto ? h->total_padded : 0, h->prefix_upto);
         if (rcg) return rcg;
         StageTimer tm(h, RLSIM_T_PREFIX, 0);
@@ -1074,11 +1089,39 @@ int rlsim_fragment(rlsim_handle *h) {
     if (!h->have_model) FAIL(h, RLSIM_E_ARG, "rlsim_set_model first");
     if (h->p.n_target == 0 && !h->have_target) FAIL(h, RLSIM_E_ARG, "a raw target needs its sampled histogram before fragmentation");
     cudaSetDevice(h->device);
-    int rc = finalize(h);
+    int rc = finalize(h, false);  // molecule offsets; the prefix sums follow once the path is chosen
     if (rc) return rc;
     if (h->low == 0) FAIL(h, RLSIM_E_ARG, "Serious trouble: fragment length is zero!");  // transcript.go:194-196
     uint32_t n = (uint32_t)h->h_len.size();
     int method = h->p.frag_method;
+    // Resident transcripts, nothing computed yet: run them through the same grouped pipeline rlsim_add_transcripts uses while
+    // copying, so that the PCR of one group (FP64 issue bound, own stream) overlaps the memory-bound kernels of the next.
+    // Groups hold equal numbers of molecules; any grouping gives the same result (global stream addressing).
+    if (n && h->eager_upto == 0 && !h->eager_failed && !h->eager_started && h->n_mol >= (1u << 20) && eager_possible(h, 0) &&
+        !getenv("RLSIM_NO_GROUPS")) {
+        const uint32_t G = getenv("RLSIM_GROUPS") ? (uint32_t)std::max(1, atoi(getenv("RLSIM_GROUPS"))) : 4u;
+        uint32_t t0 = 0;
+        for (uint32_t g = 1; g <= G && t0 < n && !h->eager_failed; g++) {
+            uint32_t t1 = n;
+            if (g < G) {
+                const uint64_t want = h->n_mol / G * g;
+                t1 = (uint32_t)(std::lower_bound(h->h_mol_off.begin(), h->h_mol_off.begin() + n + 1, want) - h->h_mol_off.begin());
+                t1 = std::min(std::max(t1, t0), n);
+            }
+            if (t1 == t0) continue;
+            if (needs_fwd(method) && !fused_range_ok(h, t0, t1) && h->prefix_upto < t1) {
+                if ((rc = grow_prefix(h, h->total_padded, n, h->prefix_upto ? h->total_padded : 0, h->prefix_upto))) return rc;
+                StageTimer tm(h, RLSIM_T_PREFIX, 0);
+                if ((rc = launch_prefix_range(h, std::max(t0, h->prefix_upto), t1))) return rc;
+                tm.stop();
+            }
+            if ((rc = eager_chunk(h, t0, t1, true))) return rc;
+            t0 = t1;
+        }
+        if (h->pcr_in_flight) { CK(h, cudaStreamWaitEvent(h->st, h->ev_pcr, 0)); h->pcr_in_flight = false; }
+        if (!h->eager_failed && needs_fwd(method) && !fused_range_ok(h, 0, n)) h->prefix_upto = n;
+    }
+    if (!(n && h->eager_upto == n && !h->eager_failed) && (rc = finalize(h))) return rc;  // monolithic path: all prefix sums now
     if (n && h->eager_upto == n && !h->eager_failed) {
         // every chunk was fragmented, deduplicated and amplified while the transcripts were still arriving
         if ((rc = check_device_error(h))) return rc;

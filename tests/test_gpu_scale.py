@@ -30,7 +30,7 @@ def _species_equal(so, sg):
     assert np.array_equal(so["eff"].view(np.uint64), sg["eff"].view(np.uint64)), "per-species efficiency"
 
 
-def test_c3_shaped_multichunk_eager_bit_exact(oracle, gpu):
+def test_c3_shaped_multichunk_eager_bit_exact(oracle, gpu, monkeypatch):
     """What bench.py times: 30 000 C3-shaped transcripts (67 MB of bases: three 32 MB chunks, at least two eager groups),
     1.5 M molecules, C3 flags, through add_transcripts_raw - against the oracle."""
     from rlsim_b200 import synth
@@ -82,6 +82,28 @@ def test_c3_shaped_multichunk_eager_bit_exact(oracle, gpu):
     f2 = h2.sampled()
     for k in ("tr", "start", "end", "minus", "id"):
         assert np.array_equal(fo[k], f2[k]), k
+
+    # resident transcripts through the grouped pipeline (what bench.py's device-resident step runs): PCR of one group of
+    # transcripts overlaps the fragmentation of the next
+    h3 = gpu.Handle(0)
+    h3.set_model(args.to_params())
+    h3.sample_target(args.req_frags)
+    h3.set_first_index(0)
+    monkeypatch.setenv("RLSIM_NO_EAGER", "1")
+    h3.add_transcripts_raw(pb, po, pl, n_tr)
+    monkeypatch.delenv("RLSIM_NO_EAGER")
+    monkeypatch.setenv("RLSIM_GROUPS", "3")
+    h3.build_library()
+    monkeypatch.delenv("RLSIM_GROUPS")
+    f3 = int(h3.stats().flags)
+    assert f3 & gpu.F_EAGER and (f3 >> gpu.F_GROUPS_SHIFT) & 0xff == 3
+    h3.sample()
+    _species_equal(so, h3.species())
+    r3 = h3.sampled()
+    for k in ("tr", "start", "end", "minus", "id"):
+        assert np.array_equal(fo[k], r3[k]), k
+    for kind in range(7):
+        assert h3.hist_dict(kind, 1 << 16) == o.hist_dict(kind), "histogram %d" % kind
 
 
 def test_c5_stated_shape_bit_exact(oracle, gpu):
