@@ -780,100 +780,14 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     if (n == 0) return 0;
     cudaSetDevice(h->device);
     const uint32_t n0 = (uint32_t)h->h_len.size();
-    const uint64_t nbytes = offsets[n] - offsets[0], o0 = offsets[0];
-    // ---- A. The transfer starts before anything else: the host bookkeeping below (a pass over all transcripts, device array
-    // growth, metadata copies) takes about a millisecond at C3 and runs while the first chunks are on the wire.
-    if (!dev_bases) CK(h, h->staging.bases.ensure(nbytes + 64));  // k_ingest reads whole aligned words
-    // (measured) a timing event recorded on the compute stream while the chunk copies are queued completes only after
-    // all of them, and holds back the first ingest: the stage timer starts before the copies are queued
-    StageTimer tm(h, RLSIM_T_LAYOUT, 0);
-    CK(h, cudaEventRecord(h->ev_ingest, h->st));  // the previous batch's ingest kernels read the staging buffer
-    CK(h, cudaStreamWaitEvent(h->st_copy, h->ev_ingest, 0));
-    const uint8_t *src = dev_bases ? dev_bases + o0 : h->staging.bases.p;
-    // ---- pipeline: H2D of chunk c+1 on the copy stream overlaps ingest (+ prefix sums) of chunk c
-    const uint64_t chunk_bytes = getenv("RLSIM_CHUNK_BYTES") ? std::max(1ll, atoll(getenv("RLSIM_CHUNK_BYTES")))  // test knob
-                               : (uint64_t)(getenv("RLSIM_CHUNK_MB") ? std::max(1, atoi(getenv("RLSIM_CHUNK_MB"))) : 32) << 20;
-    // The last chunks taper (1/2, 1/4, 1/8, 1/8 of a chunk): what remains to be computed after the last byte has arrived is
-    // the work of the last group, so it should be small.
-    std::vector<uint32_t> cuts{0};
-    for (uint32_t t0 = 0; t0 < n;) {
-        const uint64_t left = nbytes - (offsets[t0] - o0);
-        uint64_t want = chunk_bytes;
-        if (left <= chunk_bytes + chunk_bytes / 2) want = left > chunk_bytes / 4 ? left / 2 : left;
-        want = std::max<uint64_t>(want, std::min<uint64_t>(chunk_bytes, 1u << 20));
-        // first t1 in (t0, n] whose transcripts [t0, t1) hold at least `want` bytes
-        const uint32_t t1 = (uint32_t)(std::lower_bound(offsets + t0, offsets + n, offsets[t0] + want) - offsets);
-        cuts.push_back(t1);
-        t0 = t1;
-    }
-    const uint32_t n_chunks = (uint32_t)cuts.size() - 1;
-    while (h->ev_chunk.size() < n_chunks) { cudaEvent_t e; CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_chunk.push_back(e); }
-    auto chunk_a = [&](uint32_t c) { return offsets[cuts[c]] - o0; };      // byte range of chunk c in the batch
-    auto chunk_b = [&](uint32_t c) { return offsets[cuts[c + 1]] - o0; };
-    // A pageable caller buffer (Go slice, numpy array) cannot be read by the copy engine: its chunks are staged through a
-    // ring of pinned slots by a feeder thread + copy team while the previous slot is on the wire.  Pinned buffers are
-    // copied directly.  `issued` = chunks whose copy and event have been queued (the main thread waits for it before it
-    // touches a chunk's event).
-    const bool stage = !dev_bases && nbytes > 0 && !getenv("RLSIM_NO_STAGING") && !host_pinned(bases + o0);
-    h->staged_pageable = stage;
-    std::atomic<uint32_t> issued{0};
-    std::atomic<int> feeder_err{0};
-    std::thread feeder;
-    // on every way out: the feeder is joined and the queued copies have finished reading the caller's buffer
-    struct Joiner { std::thread &t; cudaStream_t sc; ~Joiner() { if (t.joinable()) t.join(); cudaStreamSynchronize(sc); } } joiner{feeder, h->st_copy};
-    auto issue_direct = [&](uint32_t c_from, uint32_t c_to) -> int {  // pinned / device source: plain asynchronous copies
-        for (uint32_t c = c_from; c < c_to; c++) {
-            if (chunk_b(c) > chunk_a(c) && !dev_bases)
-                CK(h, cudaMemcpyAsync(h->staging.bases.p + chunk_a(c), bases + o0 + chunk_a(c), chunk_b(c) - chunk_a(c), cudaMemcpyHostToDevice, h->st_copy));
-            CK(h, cudaEventRecord(h->ev_chunk[c], h->st_copy));
-        }
-        issued.store(c_to);
-        return 0;
-    };
-    // The copy engine serves requests in the order they reach it: the small metadata copies queued by the bookkeeping below
-    // land behind the chunks already queued, so only the first HEAD chunks go out now and the rest after the metadata.
-    const uint32_t HEAD = std::min<uint32_t>(n_chunks, 2);
-    if (!stage) {
-        int rci = issue_direct(0, HEAD);
-        if (rci) return rci;
-    } else {
-        constexpr uint32_t RING = 3;
-        size_t slot = 0;
-        for (uint32_t c = 0; c < n_chunks; c++) slot = std::max<size_t>(slot, chunk_b(c) - chunk_a(c));
-        slot = (slot + 4095) & ~(size_t)4095;
-        if (h->stage_ring_bytes < RING * slot) {
-            if (h->stage_ring) cudaFreeHost(h->stage_ring);
-            h->stage_ring = nullptr; h->stage_ring_bytes = 0;
-            CK(h, cudaHostAlloc((void **)&h->stage_ring, RING * slot, cudaHostAllocDefault));
-            h->stage_ring_bytes = RING * slot;
-        }
-        if (!h->team) h->team = new CopyTeam(stage_threads());
-        const uint8_t *src_host = bases + o0;
-        feeder = std::thread([&, slot, src_host] {
-            cudaSetDevice(h->device);
-            for (uint32_t c = 0; c < n_chunks; c++) {
-                cudaError_t e = cudaSuccess;
-                if (c >= RING) e = cudaEventSynchronize(h->ev_chunk[c - RING]);  // the slot's previous copy has left it
-                const uint64_t a = chunk_a(c), b = chunk_b(c);
-                uint8_t *sl = h->stage_ring + (size_t)(c % RING) * slot;
-                if (e == cudaSuccess && b > a) {
-                    h->team->copy(sl, src_host + a, b - a);
-                    e = cudaMemcpyAsync(h->staging.bases.p + a, sl, b - a, cudaMemcpyHostToDevice, h->st_copy);
-                }
-                if (e == cudaSuccess) e = cudaEventRecord(h->ev_chunk[c], h->st_copy);
-                if (e != cudaSuccess) { feeder_err.store((int)e); issued.store(n_chunks, std::memory_order_release); return; }
-                issued.store(c + 1, std::memory_order_release);
-            }
-        });
-    }
-    // ---- B. bookkeeping
+    const uint64_t nbytes = offsets[n] - offsets[0];
     if (h->h_off.empty()) h->h_off.push_back(0);
     PinVec<uint64_t> &rel = h->h_rel;
     rel.resize(n + 1);
     if (h->h_mol_off.empty()) h->h_mol_off.push_back(0);
     h->h_srclen.resize(n0 + n); h->h_expr.resize(n0 + n); h->h_len.resize(n0 + n); h->h_off.resize(n0 + n + 1); h->h_mol_off.resize(n0 + n + 1);
     {
-        const uint64_t pa = h->polya_max;
+        const uint64_t o0 = offsets[0], pa = h->polya_max;
         uint64_t *srclen = h->h_srclen.data() + n0, *ex = h->h_expr.data() + n0, *off = h->h_off.data() + n0;
         uint32_t *len = h->h_len.data() + n0;
         uint64_t *molo = h->h_mol_off.data() + n0;
@@ -931,10 +845,83 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     CK(h, cudaMemsetAsync(h->d_nmask.p + tot / 32, 0, 8 * 4, h->st));
     CK(h, h->staging.off.ensure(n + 1));
     CK(h, cudaMemcpyAsync(h->staging.off.p, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, h->st));
-    // ---- C. the remaining chunk copies, behind the metadata
+    // ---- The copy engine serves requests in the order they reach it, and requests of a stream may be held back until the
+    // stream's next operation: the chunk copies wait for an event behind the small metadata copies, or those could land
+    // behind all the chunks and stall the first ingest for the whole transfer.  The same event orders the chunk copies
+    // after the previous batch's ingest kernels, which read the staging buffer.
+    if (!dev_bases) CK(h, h->staging.bases.ensure(nbytes + 64));  // k_ingest reads whole aligned words
+    // (measured) a timing event recorded on the compute stream while the chunk copies are queued completes only after
+    // all of them, and holds back the first ingest: the stage timer starts before the copies are queued
+    StageTimer tm(h, RLSIM_T_LAYOUT, 0);
+    CK(h, cudaEventRecord(h->ev_ingest, h->st));
+    CK(h, cudaStreamWaitEvent(h->st_copy, h->ev_ingest, 0));
+    const uint8_t *src = dev_bases ? dev_bases + offsets[0] : h->staging.bases.p;
+    // ---- pipeline: H2D of chunk c+1 on the copy stream overlaps ingest (+ prefix sums) of chunk c
+    const uint64_t chunk_bytes = getenv("RLSIM_CHUNK_BYTES") ? std::max(1ll, atoll(getenv("RLSIM_CHUNK_BYTES")))  // test knob
+                               : (uint64_t)(getenv("RLSIM_CHUNK_MB") ? std::max(1, atoi(getenv("RLSIM_CHUNK_MB"))) : 32) << 20;
+    // The last chunks taper (1/2, 1/4, 1/8, 1/8 of a chunk): what remains to be computed after the last byte has arrived is
+    // the work of the last group, so it should be small.
+    std::vector<uint32_t> cuts{0};
+    for (uint32_t t0 = 0; t0 < n;) {
+        const uint64_t left = nbytes - rel[t0];
+        uint64_t want = chunk_bytes;
+        if (left <= chunk_bytes + chunk_bytes / 2) want = left > chunk_bytes / 4 ? left / 2 : left;
+        want = std::max<uint64_t>(want, std::min<uint64_t>(chunk_bytes, 1u << 20));
+        uint32_t t1 = t0;
+        while (t1 < n && rel[t1] - rel[t0] < want) t1++;
+        cuts.push_back(t1);
+        t0 = t1;
+    }
+    const uint32_t n_chunks = (uint32_t)cuts.size() - 1;
+    while (h->ev_chunk.size() < n_chunks) { cudaEvent_t e; CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_chunk.push_back(e); }
+    // A pageable caller buffer (Go slice, numpy array) cannot be read by the copy engine: its chunks are staged through a
+    // ring of pinned slots by a feeder thread + copy team while the previous slot is on the wire.  Pinned buffers are
+    // copied directly.  `issued` = chunks whose copy and event have been queued (the main thread waits for it before it
+    // touches a chunk's event).
+    const bool stage = !dev_bases && nbytes > 0 && !getenv("RLSIM_NO_STAGING") && !host_pinned(bases + offsets[0]);
+    h->staged_pageable = stage;
+    std::atomic<uint32_t> issued{0};
+    std::atomic<int> feeder_err{0};
+    std::thread feeder;
+    // on every way out: the feeder is joined and the queued copies have finished reading the caller's buffer
+    struct Joiner { std::thread &t; cudaStream_t sc; ~Joiner() { if (t.joinable()) t.join(); cudaStreamSynchronize(sc); } } joiner{feeder, h->st_copy};
     if (!stage) {
-        int rci = issue_direct(HEAD, n_chunks);
-        if (rci) return rci;
+        for (uint32_t c = 0; c < n_chunks; c++) {  // all copies are queued first: the copy engine never waits for the host
+            const uint32_t t0 = cuts[c], t1 = cuts[c + 1];
+            if (rel[t1] > rel[t0] && !dev_bases)
+                CK(h, cudaMemcpyAsync(h->staging.bases.p + rel[t0], bases + offsets[0] + rel[t0], rel[t1] - rel[t0], cudaMemcpyHostToDevice, h->st_copy));
+            CK(h, cudaEventRecord(h->ev_chunk[c], h->st_copy));
+        }
+        issued.store(n_chunks);
+    } else {
+        constexpr uint32_t RING = 3;
+        size_t slot = 0;
+        for (uint32_t c = 0; c < n_chunks; c++) slot = std::max<size_t>(slot, rel[cuts[c + 1]] - rel[cuts[c]]);
+        slot = (slot + 4095) & ~(size_t)4095;
+        if (h->stage_ring_bytes < RING * slot) {
+            if (h->stage_ring) cudaFreeHost(h->stage_ring);
+            h->stage_ring = nullptr; h->stage_ring_bytes = 0;
+            CK(h, cudaHostAlloc((void **)&h->stage_ring, RING * slot, cudaHostAllocDefault));
+            h->stage_ring_bytes = RING * slot;
+        }
+        if (!h->team) h->team = new CopyTeam(stage_threads());
+        const uint8_t *src_host = bases + offsets[0];
+        feeder = std::thread([&, slot, src_host] {
+            cudaSetDevice(h->device);
+            for (uint32_t c = 0; c < n_chunks; c++) {
+                cudaError_t e = cudaSuccess;
+                if (c >= RING) e = cudaEventSynchronize(h->ev_chunk[c - RING]);  // the slot's previous copy has left it
+                const uint64_t a = rel[cuts[c]], b = rel[cuts[c + 1]];
+                uint8_t *sl = h->stage_ring + (size_t)(c % RING) * slot;
+                if (e == cudaSuccess && b > a) {
+                    h->team->copy(sl, src_host + a, b - a);
+                    e = cudaMemcpyAsync(h->staging.bases.p + a, sl, b - a, cudaMemcpyHostToDevice, h->st_copy);
+                }
+                if (e == cudaSuccess) e = cudaEventRecord(h->ev_chunk[c], h->st_copy);
+                if (e != cudaSuccess) { feeder_err.store((int)e); issued.store(n_chunks, std::memory_order_release); return; }
+                issued.store(c + 1, std::memory_order_release);
+            }
+        });
     }
     auto wait_issued = [&](uint32_t c) { while (issued.load(std::memory_order_acquire) <= c) std::this_thread::yield(); };
     // Eager groups are self-sizing: once a group is done, every chunk that has arrived meanwhile forms the next one, so
