@@ -783,9 +783,11 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     const uint64_t nbytes = offsets[n] - offsets[0];
     if (h->h_off.empty()) h->h_off.push_back(0);
     PinVec<uint64_t> &rel = h->h_rel;
-    rel.resize(n + 1);
+    const double t_entry = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    rel.resize_uninit(n + 1);
     if (h->h_mol_off.empty()) h->h_mol_off.push_back(0);
-    h->h_srclen.resize(n0 + n); h->h_expr.resize(n0 + n); h->h_len.resize(n0 + n); h->h_off.resize(n0 + n + 1); h->h_mol_off.resize(n0 + n + 1);
+    h->h_srclen.resize(n0 + n); h->h_expr.resize_uninit(n0 + n); h->h_len.resize_uninit(n0 + n); h->h_off.resize_uninit(n0 + n + 1);
+    h->h_mol_off.resize_uninit(n0 + n + 1);
     {
         const uint64_t o0 = offsets[0], pa = h->polya_max;
         uint64_t *srclen = h->h_srclen.data() + n0, *ex = h->h_expr.data() + n0, *off = h->h_off.data() + n0;
@@ -931,6 +933,7 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     const bool trace = getenv("RLSIM_TRACE") != nullptr;
     auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now_ms();
+    if (trace) fprintf(stderr, "[rlsim trace] host prologue %.3f ms (%u chunks)\n", t_begin - t_entry, n_chunks);
     for (uint32_t c = 0; c < n_chunks;) {
         uint32_t c_end = c + 1;
         wait_issued(c);
@@ -1457,7 +1460,7 @@ int select_core(rlsim_handle *h, const std::vector<uint64_t> &T, const std::vect
             CK(h, cudaMemcpyAsync(h->d_emit.p + 64, seg, nparts * 8, cudaMemcpyHostToDevice, h->st));
             StageTimer tm2(h, RLSIM_T_SELECT, 1);
             launch_emit_selected(h->st, plan_d, n_cand, h->d_cand_keys.p, h->d_flags.p, h->d_fscan.p, d_all_base, nparts, n_len, 1,
-                                 h->d_emit.p, h->d_emit.p + 64, h->d_emit.p + 128, records, h->d_short.p);
+                                 h->d_emit.p, h->d_emit.p + 64, h->d_emit.p + 128, records, h->d_short.p, h->rec8 ? 1 : 0);
             tm2.stop();
             CK(h, cudaGetLastError());
             // h->st is a non-blocking stream: the caller's collective runs on another one, so the records must be
@@ -1570,7 +1573,7 @@ int rlsim_apply_selected(rlsim_handle *h, const void *records_dev, uint64_t n) {
 int rl_api::apply_records(rlsim_handle *h, const void *records_dev, uint64_t n) {
     StageTimer tm(h, RLSIM_T_SELECT, 1);
     launch_apply_records(h->st, (const uint4 *)records_dev, n, h->d_my_base.p, h->d_cls_pre.p, h->d_bounds.p, h->d_order.p,
-                         h->d_hits.p, h->d_error.p);
+                         h->d_hits.p, h->d_error.p, h->rec8 ? 1 : 0);
     tm.stop();
     CK(h, cudaGetLastError());
     int e = 0;
@@ -1590,9 +1593,7 @@ int rlsim_finish_sample(rlsim_handle *h) {
 int rlsim_get_stats(rlsim_handle *h, rlsim_stats *out) {
     memset(out, 0, sizeof *out);
     out->n_transcripts = h->h_srclen.size();
-    uint64_t nm = 0;
-    for (uint64_t e : h->h_expr) nm += e;
-    out->n_molecules = nm;
+    out->n_molecules = h->h_mol_off.empty() ? 0 : h->h_mol_off[h->h_mol_off.size() - 1];  // running sum of the expression levels
     out->n_fragments = h->n_frag;
     out->n_species = h->n_sp;
     out->pool_total = h->pool_total;

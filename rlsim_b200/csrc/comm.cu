@@ -182,6 +182,12 @@ int rlsim_sample_distributed(rlsim_handle *h) {
             for (uint32_t l = 0; l < hn; l++) sum[l] += h->x_pin[(size_t)r * row + n_len + l];
         set_target_from_hist(h, sum.data(), hn);
     }
+    // 8-byte records (length << 40 | copy rank) whenever every class total fits 40 bits; 16-byte ones otherwise
+    bool rec8 = n_len <= (1u << 24);
+    for (uint32_t l = 0; l < n_len && rec8; l++) rec8 = h->h_global_totals[l] < (1ull << 40);
+    h->rec8 = rec8;
+    const size_t u64_per_rec = rec8 ? 1 : 2;
+    struct Rec8Off { rlsim_handle *h; ~Rec8Off() { h->rec8 = false; } } rec8_off{h};  // the C-ABI record form stays 16 bytes
     // ---- 2. draw this rank's classes; records grouped by owner rank in the send buffer
     uint64_t counts[64] = {0}, needed = 0;
     uint64_t cap = std::max<uint64_t>(h->d_rec_send.n, h->req_frags / N + h->req_frags / (8 * N) + 4096);
@@ -205,18 +211,19 @@ int rlsim_sample_distributed(rlsim_handle *h) {
     for (uint32_t r = 0; r < N; r++) from[r] = h->x_pin[(size_t)r * N + me];
     const uint64_t total_recv = recv_off[N];
     CK(h, h->d_rec_recv.ensure(total_recv + 1));
-    // ---- 4. one grouped exchange over NVLink on the handle's stream (16-byte records as pairs of u64)
+    // ---- 4. one grouped exchange over NVLink on the handle's stream
     {
         StageTimer tm(h, RLSIM_T_EXCHANGE, 1);
+        uint64_t *sendp = reinterpret_cast<uint64_t *>(h->d_rec_send.p), *recvp = reinterpret_cast<uint64_t *>(h->d_rec_recv.p);
         NK(h, A->GroupStart());
         for (uint32_t r = 0; r < N; r++) {
             if (r == me) continue;
-            if (counts[r]) NK(h, A->Send(h->d_rec_send.p + send_off[r], (size_t)counts[r] * 2, ncclUint64, (int)r, h->comm, h->st));
-            if (from[r]) NK(h, A->Recv(h->d_rec_recv.p + recv_off[r], (size_t)from[r] * 2, ncclUint64, (int)r, h->comm, h->st));
+            if (counts[r]) NK(h, A->Send(sendp + send_off[r] * u64_per_rec, (size_t)counts[r] * u64_per_rec, ncclUint64, (int)r, h->comm, h->st));
+            if (from[r]) NK(h, A->Recv(recvp + recv_off[r] * u64_per_rec, (size_t)from[r] * u64_per_rec, ncclUint64, (int)r, h->comm, h->st));
         }
         NK(h, A->GroupEnd());
         if (counts[me])
-            CK(h, cudaMemcpyAsync(h->d_rec_recv.p + recv_off[me], h->d_rec_send.p + send_off[me], (size_t)counts[me] * 16,
+            CK(h, cudaMemcpyAsync(recvp + recv_off[me] * u64_per_rec, sendp + send_off[me] * u64_per_rec, (size_t)counts[me] * 8 * u64_per_rec,
                                   cudaMemcpyDeviceToDevice, h->st));
         tm.stop();
     }

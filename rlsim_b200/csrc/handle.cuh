@@ -52,6 +52,7 @@ struct PinVec {
         p = q; cap = c;
     }
     void resize(size_t want) { reserve(want); if (want > n) memset(p + n, 0, (want - n) * sizeof(T)); n = want; }
+    void resize_uninit(size_t want) { reserve(want); n = want; }  // the caller overwrites every new element
     void push_back(const T &v) { reserve(n + 1); p[n++] = v; }
 };
 
@@ -302,6 +303,7 @@ struct rlsim_handle {
     DBuf<uint8_t> d_names, d_fasta;
     DBuf<uint64_t> d_name_off, d_rec_sizes, d_rec_off;
     // multi-GPU exchange inside the library (comm.cu): NCCL communicator bound at run time, buffers of the exchange
+    bool rec8 = false;                   // the exchange in flight uses 8-byte records (length << 40 | rank; all class totals < 2^40)
     ncclComm *comm = nullptr;
     int comm_rank = 0, comm_n = 1;
     DBuf<uint64_t> d_x_send, d_x_recv;   // [totals | partial target] rows, count rows

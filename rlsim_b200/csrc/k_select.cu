@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(EMIT_THREADS)
 k_emit_selected(DevClassPlan plan, uint64_t n_cand, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ flags,
                 const uint64_t *__restrict__ fscan, const uint64_t *__restrict__ all_base, uint32_t nparts, uint32_t n_len,
                 int pass, unsigned long long *__restrict__ counts, const unsigned long long *__restrict__ seg_off,
-                unsigned long long *__restrict__ cursor, uint4 *__restrict__ records, int *short_flag) {
+                unsigned long long *__restrict__ cursor, uint4 *__restrict__ records, int *short_flag, int compact) {
     __shared__ unsigned int cnt_s[EMIT_MAX_PARTS];
     __shared__ unsigned long long base_s[EMIT_MAX_PARTS];
     if (threadIdx.x < EMIT_MAX_PARTS) cnt_s[threadIdx.x] = 0;
@@ -189,26 +189,31 @@ k_emit_selected(DevClassPlan plan, uint64_t n_cand, const uint64_t *__restrict__
     }
     if (pass == 0) return;
     __syncthreads();
-    if (sel) records[base_s[owner] + local] = make_uint4(l, 0u, (uint32_t)(x & 0xffffffffu), (uint32_t)(x >> 32));
+    if (sel) {
+        // compact form (the library's own exchange): 8 bytes, length in the top 24 bits - every class total is below 2^40
+        if (compact) reinterpret_cast<uint64_t *>(records)[base_s[owner] + local] = ((uint64_t)l << 40) | x;
+        else records[base_s[owner] + local] = make_uint4(l, 0u, (uint32_t)(x & 0xffffffffu), (uint32_t)(x >> 32));
+    }
 }
 void launch_emit_selected(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, const uint64_t *keys, const uint32_t *flags,
                           const uint64_t *fscan, const uint64_t *all_base, uint32_t nparts, uint32_t n_len, int pass,
                           unsigned long long *counts, const unsigned long long *seg_off, unsigned long long *cursor,
-                          uint4 *records, int *short_flag) {
+                          uint4 *records, int *short_flag, int compact) {
     if (n_cand)
         k_emit_selected<<<(unsigned)((n_cand + EMIT_THREADS - 1) / EMIT_THREADS), EMIT_THREADS, 0, st>>>(
-            plan, n_cand, keys, flags, fscan, all_base, nparts, n_len, pass, counts, seg_off, cursor, records, short_flag);
+            plan, n_cand, keys, flags, fscan, all_base, nparts, n_len, pass, counts, seg_off, cursor, records, short_flag, compact);
 }
 
 // records received from the drawing ranks -> hits on this rank's species
 __global__ void k_apply_records(const uint4 *__restrict__ records, uint64_t n, const uint64_t *__restrict__ my_base,
                                 const uint64_t *__restrict__ cls_pre, const uint64_t *__restrict__ bounds,
-                                const uint32_t *__restrict__ order, unsigned long long *__restrict__ hits, int *error) {
+                                const uint32_t *__restrict__ order, unsigned long long *__restrict__ hits, int *error, int compact) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint4 r = records[i];
-    uint32_t l = r.x;
-    uint64_t x = (uint64_t)r.z | ((uint64_t)r.w << 32);
+    uint32_t l;
+    uint64_t x;
+    if (compact) { const uint64_t r = reinterpret_cast<const uint64_t *>(records)[i]; l = (uint32_t)(r >> 40); x = r & ((1ull << 40) - 1ull); }
+    else { const uint4 r = records[i]; l = r.x; x = (uint64_t)r.z | ((uint64_t)r.w << 32); }
     uint64_t b = bounds[l], e = bounds[l + 1];
     uint64_t t_local = cls_pre[e] - cls_pre[b];
     if (x < my_base[l] || x - my_base[l] >= t_local) { atomicExch(error, RLSIM_E_ARG); return; }  // mis-routed record
@@ -221,8 +226,8 @@ __global__ void k_apply_records(const uint4 *__restrict__ records, uint64_t n, c
     atomicAdd(&hits[order[lo]], 1ull);
 }
 void launch_apply_records(cudaStream_t st, const uint4 *records, uint64_t n, const uint64_t *my_base, const uint64_t *cls_pre,
-                          const uint64_t *bounds, const uint32_t *order, unsigned long long *hits, int *error) {
-    if (n) k_apply_records<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(records, n, my_base, cls_pre, bounds, order, hits, error);
+                          const uint64_t *bounds, const uint32_t *order, unsigned long long *hits, int *error, int compact) {
+    if (n) k_apply_records<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(records, n, my_base, cls_pre, bounds, order, hits, error, compact);
 }
 
 // mode per length: 0 = nothing drawn, 1 = whole class drawn, 2 = hits are the drawn copies, 3 = hits are the excluded copies
