@@ -91,7 +91,7 @@ __device__ __forceinline__ uint64_t amplify(const PxStream &stream, uint64_t c, 
     const double lq = live ? det_log(q) : 0.0;
     int cyc = live ? 0 : cycles;
     uint32_t blk = 0;
-    bool pending = false, have_setup = false, inv_mode = false, have_bound = false;
+    bool pending = false, have_setup = false, inv_mode = false;
     double nd = 0, b = 0, a = 0, cc = 0, vr = 0, alpha = 0, mm = 0, qn = 0, bound = 0;
     double us = 0, v = 0, k = 0;
     for (;;) {
@@ -103,10 +103,8 @@ __device__ __forceinline__ uint64_t amplify(const PxStream &stream, uint64_t c, 
                 inv_mode = nd * p < PCR_BINV_MAX;
                 if (inv_mode) {
                     qn = det_exp(nd * lq);
-                    // spec: restart when x > bound = min(nd, nd p + 10 sqrt(nd p q + 1)).  bound >= min(nd, 10), so the square
-                    // root is only needed by the rare walk that gets past that (same decisions, fewer FP64 operations)
-                    bound = nd < 10.0 ? nd : 10.0;
-                    have_bound = false;
+                    bound = nd * p + 10.0 * sqrt(nd * p * q + 1.0);
+                    if (bound > nd) bound = nd;
                 } else {
                     double spq = sqrt(nd * p * q);
                     b = 1.15 + 2.53 * spq;
@@ -127,14 +125,7 @@ __device__ __forceinline__ uint64_t amplify(const PxStream &stream, uint64_t c, 
                 bool restart = false;
                 while (u > px) {
                     x = x + 1.0;
-                    if (x > bound) {
-                        if (!have_bound) {
-                            bound = nd * p + 10.0 * sqrt(nd * p * q + 1.0);
-                            if (bound > nd) bound = nd;
-                            have_bound = true;
-                        }
-                        if (x > bound) { restart = true; break; }
-                    }
+                    if (x > bound) { restart = true; break; }
                     u = u - px;
                     px = (((nd - x + 1.0) * r) * px) * RCP_TABLE[(int)x];
                 }
