@@ -192,6 +192,35 @@ def test_go_shim_implements_the_reference_interfaces():
         assert call in src, call
 
 
+def test_go_spec_files_restate_the_oracle():
+    """go/philox.go and go/detmath.go carry the same constants as the plain-C text of the spec (oracle/philox.h,
+    oracle/detmath.h): Philox multipliers / Weyl constants / key-derivation words / tags, and every floating-point literal
+    of the det_* functions.  (They cannot be compiled here; this guards against transcription slips.)"""
+    def floats(text):
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        text = re.sub(r"//[^\n]*", "", text)
+        out = set()
+        for tok in re.findall(r"(?<![\w.])-?\d+\.\d*(?:[eE][-+]?\d+)?|(?<![\w.])-?\d+[eE][-+]?\d+", text):
+            out.add(float(tok))
+        return out
+    go_px = open(os.path.join(ROOT, "go", "philox.go")).read()
+    c_px = open(os.path.join(ROOT, "oracle", "philox.h")).read()
+    for const in ("0xD2511F53", "0xCD9E8D57", "0x9E3779B9", "0xBB67AE85", "0x524c5349", "0x4d423230"):
+        assert const.lower() in go_px.lower() and const.lower() in c_px.lower(), const
+    for tag, val in (("PxTagTarget", 1), ("PxTagFrag", 2), ("PxTagPcr", 3), ("PxTagSelect", 4), ("PxTagStrand", 5)):
+        assert re.search(r"%s\s*=\s*%d\b" % (tag, val), go_px), tag
+    assert "1.1102230246251565404e-16" in go_px and "2.2204460492503130808e-16" in go_px
+    assert "bits.Mul64" in go_px
+    go_dm = floats(open(os.path.join(ROOT, "go", "detmath.go")).read())
+    c_dm = floats(open(os.path.join(ROOT, "oracle", "detmath.h")).read())
+    missing = sorted(x for x in c_dm if x not in go_dm and -x not in go_dm)
+    assert not missing, missing
+    for src in (go_px, open(os.path.join(ROOT, "go", "detmath.go")).read()):
+        code = re.sub(r"//[^\n]*", "", src)
+        for a, b in ("()", "{}", "[]"):
+            assert code.count(a) == code.count(b)
+
+
 def test_exchange_plan_host_arithmetic():
     """rlsim_exchange_plan: where each rank's groups start in its send buffer and where each sender's records land
     (the routing arithmetic of rlsim_sample_distributed; no GPU involved)."""
