@@ -775,89 +775,71 @@ int rlsim_clear_transcripts(rlsim_handle *h) {
 }  // extern "C"
 
 // bases: host memory (copied in pipelined chunks), or -- dev_bases -- sequences already in device memory
+// Per-transcript metadata of a chunk, written by the host into pinned arrays (device-accessible under unified addressing)
+// while the chunk is on the wire, and pulled into device memory by this kernel on the compute stream.  A cudaMemcpyAsync
+// would queue behind the chunk copies already handed to the copy engine (measured twice: the first ingest then waits for the
+// whole transfer); a kernel reading host memory does not.
+__global__ void k_copy_meta(const uint64_t *__restrict__ h_off, const uint32_t *__restrict__ h_len, const uint64_t *__restrict__ h_expr,
+                            const uint64_t *__restrict__ h_mol_off, const uint64_t *__restrict__ h_rel, uint64_t *__restrict__ d_off,
+                            uint32_t *__restrict__ d_len, uint64_t *__restrict__ d_expr, uint64_t *__restrict__ d_mol_off,
+                            uint64_t *__restrict__ d_rel, uint32_t n) {  // all pointers at the chunk's first transcript
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    d_off[i] = h_off[i];           // n + 1 boundary values
+    d_rel[i] = h_rel[i];
+    if (d_mol_off) d_mol_off[i] = h_mol_off[i];
+    if (i < n) { d_len[i] = h_len[i]; d_expr[i] = h_expr[i]; }
+}
+
+// bases: host memory (copied in pipelined chunks), or -- dev_bases -- sequences already in device memory
 static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_bases, const uint64_t *offsets, const uint64_t *expr, uint32_t n) {
     if (!h->have_model) FAIL(h, RLSIM_E_ARG, "rlsim_set_model must precede rlsim_add_transcripts (the poly(A) maximum shapes the layout)");
     if (n == 0) return 0;
     cudaSetDevice(h->device);
-    const uint32_t n0 = (uint32_t)h->h_len.size();
-    const uint64_t nbytes = offsets[n] - offsets[0];
+    const bool trace = getenv("RLSIM_TRACE") != nullptr;
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_entry = now_ms();
+    const uint32_t n0 = (uint32_t)h->h_len.size(), nn = n0 + n;
+    const uint64_t o0 = offsets[0], nbytes = offsets[n] - o0, pa = h->polya_max;
+    // ---- sizes.  The padded layout of the batch is only known after a pass over its transcripts; that pass runs chunk by
+    // chunk while the chunks are on the wire, so the device arrays are sized from an upper bound (every transcript grows by
+    // the poly(A) maximum and at most 31 bases of padding).
+    const uint64_t old_total = h->total_padded;
+    const uint64_t tot_ub = old_total + nbytes + (uint64_t)n * (pa + 31);
+    if (tot_ub >= (1ull << 40)) FAIL(h, RLSIM_E_UNSUPPORTED, "more than 2^40 bases on one GPU");
     if (h->h_off.empty()) h->h_off.push_back(0);
-    PinVec<uint64_t> &rel = h->h_rel;
-    const double t_entry = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
-    rel.resize_uninit(n + 1);
     if (h->h_mol_off.empty()) h->h_mol_off.push_back(0);
-    h->h_srclen.resize(n0 + n); h->h_expr.resize_uninit(n0 + n); h->h_len.resize_uninit(n0 + n); h->h_off.resize_uninit(n0 + n + 1);
-    h->h_mol_off.resize_uninit(n0 + n + 1);
-    {
-        const uint64_t o0 = offsets[0], pa = h->polya_max;
-        uint64_t *srclen = h->h_srclen.data() + n0, *ex = h->h_expr.data() + n0, *off = h->h_off.data() + n0;
-        uint32_t *len = h->h_len.data() + n0;
-        uint64_t *molo = h->h_mol_off.data() + n0;
-        double se = 0, sel = 0;
-        uint64_t too_long = 0;
-        rel[0] = 0;
-        for (uint32_t i = 0; i < n; i++) {
-            const uint64_t r1 = offsets[i + 1] - o0, l = r1 - rel[i], L = l + pa;
-            rel[i + 1] = r1;
-            too_long |= L >> 32;
-            srclen[i] = l; ex[i] = expr[i]; len[i] = (uint32_t)L;
-            if (expr[i] && L > h->max_len && !(L >> 32)) h->max_len = (uint32_t)L;
-            off[i + 1] = off[i] + ((L + 31) & ~31ull);
-            molo[i + 1] = molo[i] + expr[i];
-            se += (double)expr[i];
-            sel += (double)expr[i] * (double)L;
-        }
-        if (too_long) {
-            h->h_srclen.resize(n0); h->h_expr.resize(n0); h->h_len.resize(n0); h->h_off.resize(n0 + 1); h->h_mol_off.resize(n0 + 1);
-            FAIL(h, RLSIM_E_UNSUPPORTED, "transcript longer than 2^32-1 bases");
-        }
-        h->sum_expr += se; h->sum_expr_len += sel;
-    }
-    const uint32_t nn = n0 + n;
-    const uint64_t old_total = h->total_padded, tot = h->h_off[nn];
-    if (tot >= (1ull << 40)) FAIL(h, RLSIM_E_UNSUPPORTED, "more than 2^40 bases on one GPU");
-    h->total_padded = tot;
+    PinVec<uint64_t> &rel = h->h_rel;
+    rel.resize_uninit(n + 1);
+    h->h_srclen.resize(nn); h->h_expr.resize_uninit(nn); h->h_len.resize_uninit(nn); h->h_off.resize_uninit(nn + 1);
+    h->h_mol_off.resize_uninit(nn + 1);
     h->mol_off_valid = false;
     h->eager_pcr = false;
     h->fragmented = h->amplified = h->sampled = false;
     // ---- device arrays: grow keeping what earlier batches wrote
-    CK(h, h->d_bases.grow_preserve(tot + 64, old_total, h->st));
-    CK(h, h->d_packed.grow_preserve(tot / 16 + 8, old_total / 16, h->st));
-    CK(h, h->d_nmask.grow_preserve(tot / 32 + 8, old_total / 32, h->st));
-    CK(h, h->d_gc.grow_preserve(tot / 32 + nn + 8, old_total / 32 + n0 + 1, h->st));
-    // priming prefix sums: in shared memory inside the fused kernel when every transcript of the batch fits, else in HBM
-    const bool range_fused = fused_range_ok(h, n0, nn);
-    const bool want_prefix = needs_fwd(h->p.frag_method) && !range_fused && h->prefix_upto == n0;
-    if (want_prefix) {
-        int rcg = grow_prefix(h, tot, nn, old_total, n0);
+    CK(h, h->d_bases.grow_preserve(tot_ub + 64, old_total, h->st));
+    CK(h, h->d_packed.grow_preserve(tot_ub / 16 + 8, old_total / 16, h->st));
+    CK(h, h->d_nmask.grow_preserve(tot_ub / 32 + 8, old_total / 32, h->st));
+    CK(h, h->d_gc.grow_preserve(tot_ub / 32 + nn + 8, old_total / 32 + n0 + 1, h->st));
+    // priming prefix sums: in shared memory inside the fused kernel (opt-in) when every transcript of the batch fits, else in HBM
+    const bool fused_batch = fused_method(h);  // decided per batch below, once the lengths are known
+    const bool want_prefix_any = needs_fwd(h->p.frag_method) && h->prefix_upto == n0;
+    if (want_prefix_any) {
+        int rcg = grow_prefix(h, tot_ub, nn, old_total, n0);
         if (rcg) return rcg;
     }
-    const bool want_eager = (want_prefix || range_fused || !needs_fwd(h->p.frag_method)) && eager_possible(h, n0);
-    CK(h, h->d_off.ensure(nn + 1)); CK(h, h->d_len.ensure(nn)); CK(h, h->d_expr.ensure(nn));
+    CK(h, h->d_off.grow_preserve(nn + 1, n0 + 1, h->st)); CK(h, h->d_len.grow_preserve(nn, n0, h->st)); CK(h, h->d_expr.grow_preserve(nn, n0, h->st));
+    CK(h, h->d_mol_off.grow_preserve(nn + 1, n0 + 1, h->st));
     CK(h, h->d_dirty.grow_preserve(nn + 1, n0, h->st));
-    if (want_eager) {
-        CK(h, h->d_mol_off.ensure(nn + 1));
-        CK(h, cudaMemcpyAsync(h->d_mol_off.p, h->h_mol_off.data(), (size_t)(nn + 1) * 8, cudaMemcpyHostToDevice, h->st));
-        h->n_mol = h->h_mol_off[nn];
-    }
-    CK(h, cudaMemcpyAsync(h->d_off.p, h->h_off.data(), (size_t)(nn + 1) * 8, cudaMemcpyHostToDevice, h->st));
-    CK(h, cudaMemcpyAsync(h->d_len.p, h->h_len.data(), (size_t)nn * 4, cudaMemcpyHostToDevice, h->st));
-    CK(h, cudaMemcpyAsync(h->d_expr.p, h->h_expr.data(), (size_t)nn * 8, cudaMemcpyHostToDevice, h->st));
-    CK(h, cudaMemsetAsync(h->d_packed.p + tot / 16, 0, 8 * 4, h->st));
-    CK(h, cudaMemsetAsync(h->d_nmask.p + tot / 32, 0, 8 * 4, h->st));
     CK(h, h->staging.off.ensure(n + 1));
-    CK(h, cudaMemcpyAsync(h->staging.off.p, rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, h->st));
-    // ---- The copy engine serves requests in the order they reach it, and requests of a stream may be held back until the
-    // stream's next operation: the chunk copies wait for an event behind the small metadata copies, or those could land
-    // behind all the chunks and stall the first ingest for the whole transfer.  The same event orders the chunk copies
-    // after the previous batch's ingest kernels, which read the staging buffer.
     if (!dev_bases) CK(h, h->staging.bases.ensure(nbytes + 64));  // k_ingest reads whole aligned words
+    // ---- the chunks
     // (measured) a timing event recorded on the compute stream while the chunk copies are queued completes only after
     // all of them, and holds back the first ingest: the stage timer starts before the copies are queued
     StageTimer tm(h, RLSIM_T_LAYOUT, 0);
-    CK(h, cudaEventRecord(h->ev_ingest, h->st));
+    CK(h, cudaEventRecord(h->ev_ingest, h->st));  // the previous batch's ingest kernels read the staging buffer
     CK(h, cudaStreamWaitEvent(h->st_copy, h->ev_ingest, 0));
-    const uint8_t *src = dev_bases ? dev_bases + offsets[0] : h->staging.bases.p;
+    const uint8_t *src = dev_bases ? dev_bases + o0 : h->staging.bases.p;
     // ---- pipeline: H2D of chunk c+1 on the copy stream overlaps ingest (+ prefix sums) of chunk c
     const uint64_t chunk_bytes = getenv("RLSIM_CHUNK_BYTES") ? std::max(1ll, atoll(getenv("RLSIM_CHUNK_BYTES")))  // test knob
                                : (uint64_t)(getenv("RLSIM_CHUNK_MB") ? std::max(1, atoi(getenv("RLSIM_CHUNK_MB"))) : 32) << 20;
@@ -865,22 +847,24 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     // the work of the last group, so it should be small.
     std::vector<uint32_t> cuts{0};
     for (uint32_t t0 = 0; t0 < n;) {
-        const uint64_t left = nbytes - rel[t0];
+        const uint64_t left = nbytes - (offsets[t0] - o0);
         uint64_t want = chunk_bytes;
         if (left <= chunk_bytes + chunk_bytes / 2) want = left > chunk_bytes / 4 ? left / 2 : left;
         want = std::max<uint64_t>(want, std::min<uint64_t>(chunk_bytes, 1u << 20));
-        uint32_t t1 = t0;
-        while (t1 < n && rel[t1] - rel[t0] < want) t1++;
-        cuts.push_back(t1);
-        t0 = t1;
+        // first t1 in (t0, n] whose transcripts [t0, t1) hold at least `want` bytes
+        const uint32_t t1 = (uint32_t)(std::lower_bound(offsets + t0, offsets + n, offsets[t0] + want) - offsets);
+        cuts.push_back(std::max(t1, t0 + 1));
+        t0 = cuts.back();
     }
     const uint32_t n_chunks = (uint32_t)cuts.size() - 1;
     while (h->ev_chunk.size() < n_chunks) { cudaEvent_t e; CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_chunk.push_back(e); }
+    auto chunk_a = [&](uint32_t c) { return offsets[cuts[c]] - o0; };      // byte range of chunk c in the batch
+    auto chunk_b = [&](uint32_t c) { return offsets[cuts[c + 1]] - o0; };
     // A pageable caller buffer (Go slice, numpy array) cannot be read by the copy engine: its chunks are staged through a
     // ring of pinned slots by a feeder thread + copy team while the previous slot is on the wire.  Pinned buffers are
     // copied directly.  `issued` = chunks whose copy and event have been queued (the main thread waits for it before it
     // touches a chunk's event).
-    const bool stage = !dev_bases && nbytes > 0 && !getenv("RLSIM_NO_STAGING") && !host_pinned(bases + offsets[0]);
+    const bool stage = !dev_bases && nbytes > 0 && !getenv("RLSIM_NO_STAGING") && !host_pinned(bases + o0);
     h->staged_pageable = stage;
     std::atomic<uint32_t> issued{0};
     std::atomic<int> feeder_err{0};
@@ -889,16 +873,15 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     struct Joiner { std::thread &t; cudaStream_t sc; ~Joiner() { if (t.joinable()) t.join(); cudaStreamSynchronize(sc); } } joiner{feeder, h->st_copy};
     if (!stage) {
         for (uint32_t c = 0; c < n_chunks; c++) {  // all copies are queued first: the copy engine never waits for the host
-            const uint32_t t0 = cuts[c], t1 = cuts[c + 1];
-            if (rel[t1] > rel[t0] && !dev_bases)
-                CK(h, cudaMemcpyAsync(h->staging.bases.p + rel[t0], bases + offsets[0] + rel[t0], rel[t1] - rel[t0], cudaMemcpyHostToDevice, h->st_copy));
+            if (chunk_b(c) > chunk_a(c) && !dev_bases)
+                CK(h, cudaMemcpyAsync(h->staging.bases.p + chunk_a(c), bases + o0 + chunk_a(c), chunk_b(c) - chunk_a(c), cudaMemcpyHostToDevice, h->st_copy));
             CK(h, cudaEventRecord(h->ev_chunk[c], h->st_copy));
         }
         issued.store(n_chunks);
     } else {
         constexpr uint32_t RING = 3;
         size_t slot = 0;
-        for (uint32_t c = 0; c < n_chunks; c++) slot = std::max<size_t>(slot, rel[cuts[c + 1]] - rel[cuts[c]]);
+        for (uint32_t c = 0; c < n_chunks; c++) slot = std::max<size_t>(slot, chunk_b(c) - chunk_a(c));
         slot = (slot + 4095) & ~(size_t)4095;
         if (h->stage_ring_bytes < RING * slot) {
             if (h->stage_ring) cudaFreeHost(h->stage_ring);
@@ -907,13 +890,13 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
             h->stage_ring_bytes = RING * slot;
         }
         if (!h->team) h->team = new CopyTeam(stage_threads());
-        const uint8_t *src_host = bases + offsets[0];
+        const uint8_t *src_host = bases + o0;
         feeder = std::thread([&, slot, src_host] {
             cudaSetDevice(h->device);
             for (uint32_t c = 0; c < n_chunks; c++) {
                 cudaError_t e = cudaSuccess;
                 if (c >= RING) e = cudaEventSynchronize(h->ev_chunk[c - RING]);  // the slot's previous copy has left it
-                const uint64_t a = rel[cuts[c]], b = rel[cuts[c + 1]];
+                const uint64_t a = chunk_a(c), b = chunk_b(c);
                 uint8_t *sl = h->stage_ring + (size_t)(c % RING) * slot;
                 if (e == cudaSuccess && b > a) {
                     h->team->copy(sl, src_host + a, b - a);
@@ -926,21 +909,74 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
         });
     }
     auto wait_issued = [&](uint32_t c) { while (issued.load(std::memory_order_acquire) <= c) std::this_thread::yield(); };
+    // ---- bookkeeping of the transcripts [t0, t1) of the batch (host arrays; the device copies follow through k_copy_meta)
+    rel[0] = 0;
+    auto host_meta = [&](uint32_t t0, uint32_t t1) -> int {
+        uint64_t *srclen = h->h_srclen.data() + n0, *ex = h->h_expr.data() + n0, *off = h->h_off.data() + n0, *molo = h->h_mol_off.data() + n0;
+        uint32_t *len = h->h_len.data() + n0;
+        double se = 0, sel = 0;
+        uint64_t too_long = 0;
+        for (uint32_t i = t0; i < t1; i++) {
+            const uint64_t r1 = offsets[i + 1] - o0, l = r1 - rel[i], L = l + pa;
+            rel[i + 1] = r1;
+            too_long |= L >> 32;
+            srclen[i] = l; ex[i] = expr[i]; len[i] = (uint32_t)L;
+            if (expr[i] && L > h->max_len && !(L >> 32)) h->max_len = (uint32_t)L;
+            off[i + 1] = off[i] + ((L + 31) & ~31ull);
+            molo[i + 1] = molo[i] + expr[i];
+            se += (double)expr[i];
+            sel += (double)expr[i] * (double)L;
+        }
+        if (too_long) return RLSIM_E_UNSUPPORTED;
+        h->sum_expr += se; h->sum_expr_len += sel;
+        h->total_padded = off[t1];
+        return 0;
+    };
+    auto meta_to_device = [&](uint32_t t0, uint32_t t1) {
+        const uint32_t m = t1 - t0;
+        k_copy_meta<<<(m + 1 + 255) / 256, 256, 0, h->st>>>(h->h_off.data() + n0 + t0, h->h_len.data() + n0 + t0, h->h_expr.data() + n0 + t0,
+                                                         h->h_mol_off.data() + n0 + t0, rel.data() + t0, h->d_off.p + n0 + t0, h->d_len.p + n0 + t0,
+                                                         h->d_expr.p + n0 + t0, h->d_mol_off.p + n0 + t0, h->staging.off.p + t0, m);
+    };
+    auto fail_batch = [&](int code, const char *msg) {  // forget the batch: the handle stays usable with what it held before
+        h->h_srclen.resize(n0); h->h_expr.resize(n0); h->h_len.resize(n0); h->h_off.resize(n0 + 1); h->h_mol_off.resize(n0 + 1);
+        h->total_padded = old_total;
+        cudaStreamSynchronize(h->st);
+        h->err = msg;
+        return code;
+    };
+    // With the fused (opt-in) kernels the per-batch decisions need every length first: the whole pass runs up front.
+    const bool lazy_meta = !fused_batch;
+    if (!lazy_meta) {
+        if (host_meta(0, n)) return fail_batch(RLSIM_E_UNSUPPORTED, "transcript longer than 2^32-1 bases");
+        meta_to_device(0, n);
+    }
+    const bool range_fused = !lazy_meta && fused_range_ok(h, n0, nn);
+    const bool want_prefix = want_prefix_any && !range_fused;
+    const bool want_eager = (want_prefix || range_fused || !needs_fwd(h->p.frag_method)) && eager_possible(h, n0);
     // Eager groups are self-sizing: once a group is done, every chunk that has arrived meanwhile forms the next one, so
     // the per-group fixed cost (host round trips for counts, small sorts) never makes compute fall behind the copies.
     // The grouping does not influence the result (streams are addressed by global molecule / species identity).
     bool eager = want_eager;
-    const bool trace = getenv("RLSIM_TRACE") != nullptr;
-    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now_ms();
     if (trace) fprintf(stderr, "[rlsim trace] host prologue %.3f ms (%u chunks)\n", t_begin - t_entry, n_chunks);
     for (uint32_t c = 0; c < n_chunks;) {
         uint32_t c_end = c + 1;
+        if (lazy_meta) {  // while chunk c is on the wire
+            if (host_meta(cuts[c], cuts[c + 1])) return fail_batch(RLSIM_E_UNSUPPORTED, "transcript longer than 2^32-1 bases");
+            meta_to_device(cuts[c], cuts[c + 1]);
+        }
         wait_issued(c);
         if (feeder_err.load()) break;
         if (eager) {
             CK(h, cudaEventSynchronize(h->ev_chunk[c]));
-            while (c_end < n_chunks && issued.load(std::memory_order_acquire) > c_end && cudaEventQuery(h->ev_chunk[c_end]) == cudaSuccess) c_end++;
+            while (c_end < n_chunks && issued.load(std::memory_order_acquire) > c_end && cudaEventQuery(h->ev_chunk[c_end]) == cudaSuccess) {
+                if (lazy_meta) {
+                    if (host_meta(cuts[c_end], cuts[c_end + 1])) return fail_batch(RLSIM_E_UNSUPPORTED, "transcript longer than 2^32-1 bases");
+                    meta_to_device(cuts[c_end], cuts[c_end + 1]);
+                }
+                c_end++;
+            }
             (void)cudaGetLastError();  // cudaErrorNotReady from the query is not an error
         }
         for (uint32_t cc = c; cc < c_end; cc++) {
@@ -948,7 +984,7 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
             CK(h, cudaStreamWaitEvent(h->st, h->ev_chunk[cc], 0));
             launch_ingest(h->st, src, h->staging.off.p + t0, t1 - t0, n0 + t0, (h->h_off[n0 + t1] - h->h_off[n0 + t0]) >> 5,
                           h->polya_max, h->d_off.p + n0 + t0, h->d_bases.p, h->d_packed.p, h->d_nmask.p, h->d_gc.p, h->d_dirty.p);
-            h->launches[RLSIM_T_LAYOUT] += 2;
+            h->launches[RLSIM_T_LAYOUT] += 3;
             if (want_prefix) { int rc = launch_prefix_range(h, n0 + t0, n0 + t1); if (rc) return rc; }
         }
         if (eager) {
@@ -963,8 +999,17 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     }
     if (feeder.joinable()) feeder.join();
     if (feeder_err.load()) { h->err = std::string("staged host-to-device copy: ") + cudaGetErrorString((cudaError_t)feeder_err.load()); return RLSIM_E_CUDA; }
+    h->n_mol = h->h_mol_off[nn];
+    CK(h, cudaEventRecord(h->ev_ingest, h->st));  // behind the last k_copy_meta (see below)
+    {   // zero words behind the last transcript (k_prefix reads whole words past a transcript's end)
+        const uint64_t tot = h->total_padded;
+        CK(h, cudaMemsetAsync(h->d_packed.p + tot / 16, 0, 8 * 4, h->st));
+        CK(h, cudaMemsetAsync(h->d_nmask.p + tot / 32, 0, 8 * 4, h->st));
+    }
     if (h->pcr_in_flight) { CK(h, cudaStreamWaitEvent(h->st, h->ev_pcr, 0)); h->pcr_in_flight = false; }
     CK(h, cudaStreamSynchronize(h->st_copy));  // caller-owned buffers are only read during the call
+    // k_copy_meta reads the pinned host arrays, which the next call may move when it grows them: all reads are done here
+    CK(h, cudaEventSynchronize(h->ev_ingest));
     if (trace) fprintf(stderr, "[rlsim trace] copies done %.3f ms\n", now_ms() - t_begin);
     tm.stop();
     CK(h, cudaGetLastError());
