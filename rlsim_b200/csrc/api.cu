@@ -260,7 +260,7 @@ bool ns_need(rlsim_handle *h, uint64_t ns) {  // would any per-species array be 
 // table of the first transcript of every warp of k_fragment over the molecules [g0, g1): depends on the expression levels
 // only, so the resident steps of one transcript set build it once
 int ensure_warp_table(rlsim_handle *h, const DevTranscripts &tr, uint64_t g0, uint64_t g1) {
-    const uint32_t n = (uint32_t)h->h_len.size();
+    const uint32_t n = tr.n;
     if (h->warp_t_n == n && h->warp_t_g0 == g0 && h->warp_t_g1 == g1) return 0;
     CK(h, h->d_warp_t.ensure((g1 - g0 + 31) / 32 + 1));
     launch_warp_transcripts(h->st, tr, g0, g1, h->d_warp_t.p);
@@ -421,6 +421,7 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1, bool timed = false) {
     CK(h, cudaMemsetAsync(h->d_long_count.p, 0, 4, h->st));
     DevModel m = make_model(h);
     DevTranscripts tr = make_tr(h);
+    tr.n = t1;  // the metadata of later transcripts reaches the device chunk by chunk: searches over off / mol_off stop here
     FragBuffers fb{h->d_keys.p, h->d_keys.n, h->d_counters.p, h->d_hist_frag.p, h->d_hist_polya.p, h->d_long_list.p, h->d_long_hi.p,
                    long_cap, h->d_long_count.p, h->d_error.p, h->d_q_a.p, h->d_q_b.p, h->d_q_a.n, h->d_counters.p + 2};
     const bool fused = fused_range_ok(h, t0, t1);
