@@ -264,36 +264,58 @@ __global__ void k_tr_counts(DevSpecies sp, const uint64_t *__restrict__ out_off,
     if (s + 1 == sp.n || sp.tr[s + 1] != t) tr_counts[t] = (uint32_t)(out_off[s + 1] - tr_out_base[t]);
 }
 
-__global__ void k_expand(const __grid_constant__ DevModel m, DevSpecies sp, const uint64_t *__restrict__ out_off,
-                         const uint64_t *__restrict__ tr_out_base, uint64_t n_out, DevSampled out) {
-    uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= n_out) return;
-    // species s with out_off[s] <= o < out_off[s+1]
-    uint64_t lo = 0, hi = sp.n;
-    while (lo < hi) {
-        uint64_t mid = lo + ((hi - lo) >> 1);
-        if (!(out_off[mid + 1] > o)) lo = mid + 1; else hi = mid;
+// One warp per 32 consecutive species: their output records are consecutive (out_off is the running sum of the copies
+// taken), so the warp writes them 32 at a time, coalesced, and finds the species of a record by a 5-step search over the
+// lanes' own offsets with shuffles - no 22-step bisection of out_off in memory per record.
+__global__ void __launch_bounds__(256)
+k_expand(const __grid_constant__ DevModel m, DevSpecies sp, const uint64_t *__restrict__ out_off,
+         const uint64_t *__restrict__ tr_out_base, uint64_t n_out, DevSampled out) {
+    const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t s0 = w * 32;
+    if (s0 >= sp.n) return;
+    const uint64_t s = s0 + lane;
+    const uint64_t my_off = out_off[min(s, sp.n)], my_end = out_off[min(s + 1, sp.n)];
+    uint32_t t = 0, start = 0, len = 0;
+    uint64_t trb = 0;
+    if (s < sp.n && my_end > my_off) { t = sp.tr[s]; start = sp.start[s]; len = sp.len[s]; trb = tr_out_base[t]; }
+    const uint64_t base = __shfl_sync(0xffffffffu, my_off, 0);
+    const uint64_t total = __shfl_sync(0xffffffffu, my_end, 31) - base;
+    for (uint64_t r0 = 0; r0 < total; r0 += 32) {
+        const uint64_t o = base + r0 + lane;
+        const bool active = r0 + lane < total;
+        // owner = the last lane whose first record is at or before o (lanes of species with no record share an offset)
+        uint32_t lo = 0, hi = 31;
+#pragma unroll
+        for (int it = 0; it < 5; it++) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            const uint64_t v = __shfl_sync(0xffffffffu, my_off, mid);
+            if (v <= o) lo = mid; else hi = mid - 1;
+        }
+        const uint64_t ooff = __shfl_sync(0xffffffffu, my_off, lo);
+        const uint32_t ot = __shfl_sync(0xffffffffu, t, lo), ostart = __shfl_sync(0xffffffffu, start, lo), olen = __shfl_sync(0xffffffffu, len, lo);
+        const uint64_t otrb = __shfl_sync(0xffffffffu, trb, lo);
+        if (!active) continue;
+        const uint64_t j = o - ooff;
+        const uint32_t end = ostart + olen;
+        PxStream str{m.key_strand, m.first_index + ot, ostart, end};
+        const bool minus = px_u01(px_draw64(str, j)) < m.strand_bias;  // sampler.go:219-227
+        out.tr[o] = m.first_index + ot;  // global transcript index
+        out.start[o] = ostart;
+        out.end[o] = end;
+        out.minus[o] = minus ? 1 : 0;
+        out.id[o] = o - otrb;  // per-transcript fragment id (sampler.go:189,204)
+        // packed host format: length with the strand in the top bit, 2 bytes when every length fits 15 bits
+        if (out.ls16) out.ls16[o] = (uint16_t)(olen | (minus ? 0x8000u : 0u));
+        else if (out.ls32) out.ls32[o] = olen | (minus ? 0x80000000u : 0u);
     }
-    uint64_t s = lo;
-    uint64_t j = o - out_off[s];
-    uint32_t t = sp.tr[s], start = sp.start[s], end = start + sp.len[s];
-    PxStream str{m.key_strand, m.first_index + t, start, end};
-    bool minus = px_u01(px_draw64(str, j)) < m.strand_bias;  // sampler.go:219-227
-    out.tr[o] = m.first_index + t;  // global transcript index
-    out.start[o] = start;
-    out.end[o] = end;
-    out.minus[o] = minus ? 1 : 0;
-    out.id[o] = o - tr_out_base[t];  // per-transcript fragment id (sampler.go:189,204)
-    // packed host format: length with the strand in the top bit, 2 bytes when every length fits 15 bits
-    if (out.ls16) out.ls16[o] = (uint16_t)((end - start) | (minus ? 0x8000u : 0u));
-    else if (out.ls32) out.ls32[o] = (end - start) | (minus ? 0x80000000u : 0u);
 }
 void launch_expand(cudaStream_t st, const DevModel &m, const DevSpecies &sp, const uint64_t *out_off, uint64_t *tr_out_base,
                    uint64_t n_out, DevSampled out) {
     if (!n_out) return;
     k_tr_out_base<<<(unsigned)((sp.n + 255) / 256), 256, 0, st>>>(sp, out_off, tr_out_base);
     if (out.tr_counts) k_tr_counts<<<(unsigned)((sp.n + 255) / 256), 256, 0, st>>>(sp, out_off, tr_out_base, out.tr_counts);
-    k_expand<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(m, sp, out_off, tr_out_base, n_out, out);
+    k_expand<<<(unsigned)((sp.n + 255) / 256), 256, 0, st>>>(m, sp, out_off, tr_out_base, n_out, out);  // a thread per species slot
 }
 
 }  // namespace rl
