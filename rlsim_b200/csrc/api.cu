@@ -1462,17 +1462,20 @@ int select_core(rlsim_handle *h, const std::vector<uint64_t> &T, const std::vect
         if (narrow) { CK(h, h->d_cand_k32.ensure(n_cand)); CK(h, h->d_cand_k32_sorted.ensure(n_cand)); }
         launch_candidates(h->st, m, plan_d, n_cand, h->d_cand_keys.p, narrow ? h->d_cand_k32.p : nullptr, h->d_cand_idx.p);
         size_t tb = 0;
+        // the sort only groups equal keys: when there are at most two candidates per 2^24 values it stops after three radix
+        // passes and the few candidates that share their low 24 bits are compared directly (k_first_flags)
         int eb = (int)bits_for(G);
+        if (eb > 24 && n_cand <= (1ull << 25) && !getenv("RLSIM_FULL_SORT")) eb = 24;
         if (narrow) {
             CK(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, h->d_cand_k32.p, h->d_cand_k32_sorted.p, h->d_cand_idx.p, h->d_cand_idx_sorted.p, (int)n_cand, 0, eb, h->st));
             if ((rc = cub_temp(h, tb))) return rc;
             CK(h, cub::DeviceRadixSort::SortPairs(h->d_cub.p, tb, h->d_cand_k32.p, h->d_cand_k32_sorted.p, h->d_cand_idx.p, h->d_cand_idx_sorted.p, (int)n_cand, 0, eb, h->st));
-            launch_first_flags32(h->st, h->d_cand_k32_sorted.p, h->d_cand_idx_sorted.p, n_cand, h->d_flags.p);
+            launch_first_flags32(h->st, h->d_cand_k32_sorted.p, h->d_cand_idx_sorted.p, n_cand, h->d_flags.p, eb);
         } else {
             CK(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, h->d_cand_keys.p, h->d_cand_keys_sorted.p, h->d_cand_idx.p, h->d_cand_idx_sorted.p, (int)n_cand, 0, eb, h->st));
             if ((rc = cub_temp(h, tb))) return rc;
             CK(h, cub::DeviceRadixSort::SortPairs(h->d_cub.p, tb, h->d_cand_keys.p, h->d_cand_keys_sorted.p, h->d_cand_idx.p, h->d_cand_idx_sorted.p, (int)n_cand, 0, eb, h->st));
-            launch_first_flags(h->st, h->d_cand_keys_sorted.p, h->d_cand_idx_sorted.p, n_cand, h->d_flags.p);
+            launch_first_flags(h->st, h->d_cand_keys_sorted.p, h->d_cand_idx_sorted.p, n_cand, h->d_flags.p, eb);
         }
         CK(h, cudaMemsetAsync(h->d_fscan.p, 0, 8, h->st));
         tb = 0;
@@ -1481,8 +1484,8 @@ int select_core(rlsim_handle *h, const std::vector<uint64_t> &T, const std::vect
         CK(h, cub::DeviceScan::InclusiveSum(h->d_cub.p, tb, h->d_flags.p, h->d_fscan.p + 1, (int)n_cand, h->st));
         unsigned long long h_counts[64] = {0};
         if (!records) {
-            launch_apply_picks(h->st, plan_d, n_cand, h->d_cand_keys.p, h->d_flags.p, h->d_fscan.p, h->d_cls_pre.p, h->d_bounds.p,
-                               h->d_order.p, h->d_hits.p, h->d_short.p);
+            launch_apply_picks_sorted(h->st, plan_d, n_cand, narrow ? nullptr : h->d_cand_keys_sorted.p, narrow ? h->d_cand_k32_sorted.p : nullptr,
+                                      h->d_cand_idx_sorted.p, h->d_fscan.p, h->d_cls_pre.p, h->d_bounds.p, h->d_order.p, h->d_hits.p, h->d_short.p, eb);
         } else {  // count per owner, then scatter into the owner groups
             CK(h, cudaMemsetAsync(h->d_emit.p, 0, 3 * 64 * 8, h->st));
             launch_emit_selected(h->st, plan_d, n_cand, h->d_cand_keys.p, h->d_flags.p, h->d_fscan.p, d_all_base, nparts, n_len, 0,

@@ -10,6 +10,7 @@
 //                     -> rank-to-species binary search in the per-class prefix sums of the amplified counts.
 //   k_expand        : sampler.go:187-227 + frag.go - one record per drawn copy, strand ~ Bernoulli(bias),
 //                     per-transcript ids, output ordered by (transcript, start, end).
+#include <algorithm>
 #include "kernels.cuh"
 #include "variates.cuh"
 
@@ -91,18 +92,33 @@ void launch_candidates(cudaStream_t st, const DevModel &m, DevClassPlan plan, ui
 }
 
 // after the stable sort by key: the first entry of each run of equal keys is the earliest draw of that rank
+// The sort only has to bring equal keys together in draw order, so it may stop at the low `sort_bits` bits (one radix
+// pass fewer): a run of candidates that agree in those bits is short (about one candidate per 2^sort_bits values) and keeps
+// the draw order (stable sort), and a candidate is a first occurrence iff no earlier member of its run has the same key.
+template <typename K>
+__device__ __forceinline__ bool first_in_run(const K *__restrict__ sk, uint64_t p, K mask) {
+    const K key = sk[p], low = key & mask;
+    for (uint64_t q = p; q > 0; q--) {
+        const K prev = sk[q - 1];
+        if ((prev & mask) != low) break;
+        if (prev == key) return false;
+    }
+    return true;
+}
 template <typename K>
 __global__ void k_first_flags(const K *__restrict__ sk, const uint32_t *__restrict__ si, uint64_t n,
-                              uint32_t *__restrict__ flags) {
+                              uint32_t *__restrict__ flags, K mask) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    flags[si[p]] = (p == 0 || sk[p] != sk[p - 1]) ? 1u : 0u;
+    flags[si[p]] = first_in_run(sk, p, mask) ? 1u : 0u;
 }
-void launch_first_flags(cudaStream_t st, const uint64_t *sk, const uint32_t *si, uint64_t n, uint32_t *flags) {
-    if (n) k_first_flags<uint64_t><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sk, si, n, flags);
+void launch_first_flags(cudaStream_t st, const uint64_t *sk, const uint32_t *si, uint64_t n, uint32_t *flags, int sort_bits) {
+    const uint64_t mask = sort_bits >= 64 ? ~0ull : ((1ull << sort_bits) - 1ull);
+    if (n) k_first_flags<uint64_t><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sk, si, n, flags, mask);
 }
-void launch_first_flags32(cudaStream_t st, const uint32_t *sk, const uint32_t *si, uint64_t n, uint32_t *flags) {
-    if (n) k_first_flags<uint32_t><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sk, si, n, flags);
+void launch_first_flags32(cudaStream_t st, const uint32_t *sk, const uint32_t *si, uint64_t n, uint32_t *flags, int sort_bits) {
+    const uint32_t mask = sort_bits >= 32 ? ~0u : ((1u << sort_bits) - 1u);
+    if (n) k_first_flags<uint32_t><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sk, si, n, flags, mask);
 }
 
 __global__ void k_apply_picks(DevClassPlan plan, uint64_t n_cand, const uint64_t *__restrict__ keys,
@@ -132,6 +148,50 @@ __global__ void k_apply_picks(DevClassPlan plan, uint64_t n_cand, const uint64_t
     }
     atomicAdd(&hits[order[lo]], 1ull);
 }
+// The same in SORTED candidate order (single-rank form): neighbouring threads hold neighbouring copy ranks, so their
+// bisections of cls_pre walk the same cache lines and end in adjacent species - the per-candidate cost becomes one random
+// 8-byte read (the candidate's position among the first occurrences in draw order) instead of an 11-step random search.
+// A candidate is a first occurrence iff its sorted neighbour on the left has another key (the sort is stable).
+template <typename K>
+__global__ void k_apply_picks_sorted(DevClassPlan plan, uint64_t n_cand, const K *__restrict__ sk, const uint32_t *__restrict__ sidx,
+                                     const uint64_t *__restrict__ fscan, const uint64_t *__restrict__ cls_pre,
+                                     const uint64_t *__restrict__ bounds, const uint32_t *__restrict__ order,
+                                     unsigned long long *__restrict__ hits, int *short_flag, K mask) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_cand) return;
+    if (p < plan.n_classes) {  // enough distinct candidates in class p?
+        const uint64_t c0 = plan.cand_off[p];
+        if (fscan[plan.cand_off[p + 1]] - fscan[c0] < plan.pick[p]) short_flag[p] = 1;
+    }
+    const uint64_t key = (uint64_t)sk[p];
+    if (!first_in_run(sk, p, mask)) return;  // a later draw of the same copy rank
+    const uint32_t c = upper_bound_u64(plan.G, plan.n_classes, key) - 1;  // keys of class c lie in [G[c], G[c] + T[c])
+    const uint32_t g = sidx[p];
+    if (fscan[g] - fscan[plan.cand_off[c]] >= plan.pick[c]) return;  // beyond the first `pick` distinct values
+    const uint64_t x = key - plan.G[c];
+    const uint32_t l = plan.len[c];
+    const uint64_t b = bounds[l], e = bounds[l + 1];
+    const uint64_t t_local = cls_pre[e] - cls_pre[b];
+    if (x < plan.base[c] || x - plan.base[c] >= t_local) return;  // another rank's copy
+    const uint64_t tgt = cls_pre[b] + (x - plan.base[c]);
+    uint64_t lo = b, hi = e;
+    while (lo < hi) {
+        uint64_t mid = lo + ((hi - lo) >> 1);
+        if (!(cls_pre[mid + 1] > tgt)) lo = mid + 1; else hi = mid;
+    }
+    atomicAdd(&hits[order[lo]], 1ull);
+}
+void launch_apply_picks_sorted(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, const uint64_t *sk64, const uint32_t *sk32,
+                               const uint32_t *sidx, const uint64_t *fscan, const uint64_t *cls_pre, const uint64_t *bounds,
+                               const uint32_t *order, unsigned long long *hits, int *short_flag, int sort_bits) {
+    if (!n_cand) return;
+    const unsigned blocks = (unsigned)((std::max<uint64_t>(n_cand, plan.n_classes) + 255) / 256);
+    if (sk32) k_apply_picks_sorted<uint32_t><<<blocks, 256, 0, st>>>(plan, n_cand, sk32, sidx, fscan, cls_pre, bounds, order, hits, short_flag,
+                                                                     sort_bits >= 32 ? ~0u : ((1u << sort_bits) - 1u));
+    else k_apply_picks_sorted<uint64_t><<<blocks, 256, 0, st>>>(plan, n_cand, sk64, sidx, fscan, cls_pre, bounds, order, hits, short_flag,
+                                                                sort_bits >= 64 ? ~0ull : ((1ull << sort_bits) - 1ull));
+}
+
 void launch_apply_picks(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, const uint64_t *keys, const uint32_t *flags,
                         const uint64_t *fscan, const uint64_t *cls_pre, const uint64_t *bounds, const uint32_t *order,
                         unsigned long long *hits, int *short_flag) {

@@ -78,11 +78,15 @@ struct DevClassPlan {          // per requested length class (host-built, device
 };
 void launch_candidates(cudaStream_t st, const DevModel &m, DevClassPlan plan, uint64_t n_cand, uint64_t *keys, uint32_t *keys32,
                        uint32_t *idx);
-void launch_first_flags(cudaStream_t st, const uint64_t *sorted_keys, const uint32_t *sorted_idx, uint64_t n, uint32_t *flags);
-void launch_first_flags32(cudaStream_t st, const uint32_t *sorted_keys, const uint32_t *sorted_idx, uint64_t n, uint32_t *flags);
+// sort_bits: the low key bits the stable sort covered (runs that agree in them are scanned for equal keys)
+void launch_first_flags(cudaStream_t st, const uint64_t *sorted_keys, const uint32_t *sorted_idx, uint64_t n, uint32_t *flags, int sort_bits);
+void launch_first_flags32(cudaStream_t st, const uint32_t *sorted_keys, const uint32_t *sorted_idx, uint64_t n, uint32_t *flags, int sort_bits);
 void launch_apply_picks(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, const uint64_t *keys_by_idx,
                         const uint32_t *flags, const uint64_t *flag_scan, const uint64_t *cls_pre,
                         const uint64_t *bounds, const uint32_t *order, unsigned long long *hits, int *short_flag);
+void launch_apply_picks_sorted(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, const uint64_t *sk64, const uint32_t *sk32,
+                               const uint32_t *sidx, const uint64_t *fscan, const uint64_t *cls_pre, const uint64_t *bounds,
+                               const uint32_t *order, unsigned long long *hits, int *short_flag, int sort_bits);
 void launch_emit_selected(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, const uint64_t *keys, const uint32_t *flags,
                           const uint64_t *fscan, const uint64_t *all_base, uint32_t nparts, uint32_t n_len, int pass,
                           unsigned long long *counts, const unsigned long long *seg_off, unsigned long long *cursor,
