@@ -1447,7 +1447,7 @@ int select_core(rlsim_handle *h, const std::vector<uint64_t> &T, const std::vect
         plan.insert(plan.end(), c_G.begin(), c_G.end());
         plan.insert(plan.end(), cand_off.begin(), cand_off.end());
         plan.insert(plan.end(), c_pick.begin(), c_pick.end());
-        CK(h, h->d_plan_u64.ensure(plan.size())); CK(h, h->d_plan_len.ensure(nc)); CK(h, h->d_short.ensure(nc));
+        CK(h, h->d_plan_u64.ensure(plan.size())); CK(h, h->d_plan_len.ensure(nc)); CK(h, h->d_short.ensure(nc)); CK(h, h->d_plan_cut.ensure(nc));
         CK(h, cudaMemcpyAsync(h->d_plan_u64.p, plan.data(), plan.size() * 8, cudaMemcpyHostToDevice, h->st));
         CK(h, cudaMemcpyAsync(h->d_plan_len.p, c_len.data(), nc * 4, cudaMemcpyHostToDevice, h->st));
         CK(h, cudaMemsetAsync(h->d_short.p, 0, nc * 4, h->st));
@@ -1485,7 +1485,8 @@ int select_core(rlsim_handle *h, const std::vector<uint64_t> &T, const std::vect
         unsigned long long h_counts[64] = {0};
         if (!records) {
             launch_apply_picks_sorted(h->st, plan_d, n_cand, narrow ? nullptr : h->d_cand_keys_sorted.p, narrow ? h->d_cand_k32_sorted.p : nullptr,
-                                      h->d_cand_idx_sorted.p, h->d_fscan.p, h->d_cls_pre.p, h->d_bounds.p, h->d_order.p, h->d_hits.p, h->d_short.p, eb);
+                                      h->d_cand_idx_sorted.p, h->d_fscan.p, h->d_plan_cut.p, h->d_cls_pre.p, h->d_bounds.p, h->d_order.p, h->d_hits.p,
+                                      h->d_short.p, eb);
         } else {  // count per owner, then scatter into the owner groups
             CK(h, cudaMemsetAsync(h->d_emit.p, 0, 3 * 64 * 8, h->st));
             launch_emit_selected(h->st, plan_d, n_cand, h->d_cand_keys.p, h->d_flags.p, h->d_fscan.p, d_all_base, nparts, n_len, 0,

@@ -285,7 +285,7 @@ struct rlsim_handle {
     uint64_t pool_total = 0;
     // selection
     std::vector<uint64_t> h_sampled, h_missing, h_after_sampling, h_after_pcr;
-    DBuf<uint64_t> d_cand_keys, d_cand_keys_sorted, d_fscan, d_taken, d_out_off, d_plan_u64;
+    DBuf<uint64_t> d_cand_keys, d_cand_keys_sorted, d_fscan, d_taken, d_out_off, d_plan_u64, d_plan_cut;
     DBuf<uint32_t> d_cand_idx, d_cand_idx_sorted, d_flags, d_plan_len;
     DBuf<unsigned long long> d_hits;
     DBuf<uint8_t> d_mode;

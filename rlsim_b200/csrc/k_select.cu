@@ -152,22 +152,33 @@ __global__ void k_apply_picks(DevClassPlan plan, uint64_t n_cand, const uint64_t
 // bisections of cls_pre walk the same cache lines and end in adjacent species - the per-candidate cost becomes one random
 // 8-byte read (the candidate's position among the first occurrences in draw order) instead of an 11-step random search.
 // A candidate is a first occurrence iff its sorted neighbour on the left has another key (the sort is stable).
+// cut[c] = the first candidate index of class c that lies beyond the class's first `pick` distinct values: the number of
+// first occurrences before a candidate (fscan) does not decrease along the draws, so "among the first pick distinct values"
+// is "first occurrence and index below cut[c]" - one bisection per class instead of a random read per candidate.
+__global__ void k_cut_index(DevClassPlan plan, const uint64_t *__restrict__ fscan, uint64_t *__restrict__ cut, int *short_flag) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= plan.n_classes) return;
+    const uint64_t c0 = plan.cand_off[c], c1 = plan.cand_off[c + 1], tgt = fscan[c0] + plan.pick[c];
+    if (fscan[c1] < tgt) short_flag[c] = 1;  // not enough distinct candidates: the host draws more and repeats
+    uint64_t lo = c0, hi = c1;  // first g with fscan[g] >= tgt
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if (fscan[mid] < tgt) lo = mid + 1; else hi = mid;
+    }
+    cut[c] = lo;
+}
+
 template <typename K>
 __global__ void k_apply_picks_sorted(DevClassPlan plan, uint64_t n_cand, const K *__restrict__ sk, const uint32_t *__restrict__ sidx,
-                                     const uint64_t *__restrict__ fscan, const uint64_t *__restrict__ cls_pre,
+                                     const uint64_t *__restrict__ cut, const uint64_t *__restrict__ cls_pre,
                                      const uint64_t *__restrict__ bounds, const uint32_t *__restrict__ order,
-                                     unsigned long long *__restrict__ hits, int *short_flag, K mask) {
+                                     unsigned long long *__restrict__ hits, K mask) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_cand) return;
-    if (p < plan.n_classes) {  // enough distinct candidates in class p?
-        const uint64_t c0 = plan.cand_off[p];
-        if (fscan[plan.cand_off[p + 1]] - fscan[c0] < plan.pick[p]) short_flag[p] = 1;
-    }
     const uint64_t key = (uint64_t)sk[p];
-    if (!first_in_run(sk, p, mask)) return;  // a later draw of the same copy rank
     const uint32_t c = upper_bound_u64(plan.G, plan.n_classes, key) - 1;  // keys of class c lie in [G[c], G[c] + T[c])
-    const uint32_t g = sidx[p];
-    if (fscan[g] - fscan[plan.cand_off[c]] >= plan.pick[c]) return;  // beyond the first `pick` distinct values
+    if ((uint64_t)sidx[p] >= cut[c]) return;  // beyond the first `pick` distinct values
+    if (!first_in_run(sk, p, mask)) return;   // a later draw of the same copy rank
     const uint64_t x = key - plan.G[c];
     const uint32_t l = plan.len[c];
     const uint64_t b = bounds[l], e = bounds[l + 1];
@@ -182,13 +193,14 @@ __global__ void k_apply_picks_sorted(DevClassPlan plan, uint64_t n_cand, const K
     atomicAdd(&hits[order[lo]], 1ull);
 }
 void launch_apply_picks_sorted(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, const uint64_t *sk64, const uint32_t *sk32,
-                               const uint32_t *sidx, const uint64_t *fscan, const uint64_t *cls_pre, const uint64_t *bounds,
+                               const uint32_t *sidx, const uint64_t *fscan, uint64_t *cut, const uint64_t *cls_pre, const uint64_t *bounds,
                                const uint32_t *order, unsigned long long *hits, int *short_flag, int sort_bits) {
     if (!n_cand) return;
-    const unsigned blocks = (unsigned)((std::max<uint64_t>(n_cand, plan.n_classes) + 255) / 256);
-    if (sk32) k_apply_picks_sorted<uint32_t><<<blocks, 256, 0, st>>>(plan, n_cand, sk32, sidx, fscan, cls_pre, bounds, order, hits, short_flag,
+    k_cut_index<<<(plan.n_classes + 127) / 128, 128, 0, st>>>(plan, fscan, cut, short_flag);
+    const unsigned blocks = (unsigned)((n_cand + 255) / 256);
+    if (sk32) k_apply_picks_sorted<uint32_t><<<blocks, 256, 0, st>>>(plan, n_cand, sk32, sidx, cut, cls_pre, bounds, order, hits,
                                                                      sort_bits >= 32 ? ~0u : ((1u << sort_bits) - 1u));
-    else k_apply_picks_sorted<uint64_t><<<blocks, 256, 0, st>>>(plan, n_cand, sk64, sidx, fscan, cls_pre, bounds, order, hits, short_flag,
+    else k_apply_picks_sorted<uint64_t><<<blocks, 256, 0, st>>>(plan, n_cand, sk64, sidx, cut, cls_pre, bounds, order, hits,
                                                                 sort_bits >= 64 ? ~0ull : ((1ull << sort_bits) - 1ull));
 }
 

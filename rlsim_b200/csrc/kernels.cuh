@@ -85,7 +85,7 @@ void launch_apply_picks(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, con
                         const uint32_t *flags, const uint64_t *flag_scan, const uint64_t *cls_pre,
                         const uint64_t *bounds, const uint32_t *order, unsigned long long *hits, int *short_flag);
 void launch_apply_picks_sorted(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, const uint64_t *sk64, const uint32_t *sk32,
-                               const uint32_t *sidx, const uint64_t *fscan, const uint64_t *cls_pre, const uint64_t *bounds,
+                               const uint32_t *sidx, const uint64_t *fscan, uint64_t *cut, const uint64_t *cls_pre, const uint64_t *bounds,
                                const uint32_t *order, unsigned long long *hits, int *short_flag, int sort_bits);
 void launch_emit_selected(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, const uint64_t *keys, const uint32_t *flags,
                           const uint64_t *fscan, const uint64_t *all_base, uint32_t nparts, uint32_t n_len, int pass,
