@@ -1392,10 +1392,11 @@ namespace rl_api {
 //   records != nullptr : drawn / excluded ranks are written as records grouped by owner rank (multi-GPU form)
 int select_core(rlsim_handle *h, const std::vector<uint64_t> &T, const std::vector<uint64_t> &base, uint32_t nparts,
                 uint32_t part, const uint64_t *d_all_base, uint4 *records, uint64_t cap, uint64_t *counts_out,
-                uint64_t *needed_out, bool sync_records) {
+                uint64_t *needed_out, bool sync_records, const uint64_t *all_tot, uint64_t *seg_out) {
     int rc;
     if ((rc = target_host(h))) return rc;
     uint32_t n_len = h->n_len;
+    std::vector<double> expect(nparts, 0.0);  // expected records per owner rank (one-sweep emit)
     // ---- sampler.go:65-106 bookkeeping per requested length (global view, identical on every rank)
     size_t nt = std::max<size_t>(h->h_target.size(), n_len);
     h->h_sampled.assign(nt, 0); h->h_missing.assign(nt, 0);
@@ -1420,6 +1421,8 @@ int select_core(rlsim_handle *h, const std::vector<uint64_t> &T, const std::vect
         if (l % nparts != part) continue;  // another rank draws this class
         c_len.push_back((uint32_t)l); c_T.push_back(tot); c_base.push_back(base[l]); c_G.push_back(G); c_pick.push_back(pick);
         G += tot;
+        if (all_tot)  // a uniform draw without replacement splits over the owners in proportion to their copies
+            for (uint32_t r = 0; r < nparts; r++) expect[r] += (double)pick * (double)all_tot[(size_t)r * n_len + l] / (double)tot;
         // expected draws until `pick` distinct values out of tot: tot * ln(tot / (tot - pick))
         double e = (double)tot * std::log((double)tot / (double)(tot - pick));
         c_cand.push_back((uint64_t)(e * slack + 6.0 * std::sqrt((double)pick) + 64.0));
@@ -1428,7 +1431,7 @@ int select_core(rlsim_handle *h, const std::vector<uint64_t> &T, const std::vect
     DevModel m = make_model(h);
     CK(h, h->d_hits.ensure(ns)); CK(h, h->d_taken.ensure(ns)); CK(h, h->d_out_off.ensure(ns + 1)); CK(h, h->d_mode.ensure(n_len + 1));
     CK(h, cudaMemcpyAsync(h->d_mode.p, mode.data(), n_len + 1, cudaMemcpyHostToDevice, h->st));
-    CK(h, h->d_emit.ensure(3 * 64));
+    CK(h, h->d_emit.ensure(3 * 64 + 2));
     uint32_t nc = (uint32_t)c_len.size();
     if (counts_out) for (uint32_t r = 0; r < nparts; r++) counts_out[r] = 0;
     if (needed_out) *needed_out = 0;
@@ -1487,6 +1490,44 @@ int select_core(rlsim_handle *h, const std::vector<uint64_t> &T, const std::vect
             launch_apply_picks_sorted(h->st, plan_d, n_cand, narrow ? nullptr : h->d_cand_keys_sorted.p, narrow ? h->d_cand_k32_sorted.p : nullptr,
                                       h->d_cand_idx_sorted.p, h->d_fscan.p, h->d_plan_cut.p, h->d_cls_pre.p, h->d_bounds.p, h->d_order.p, h->d_hits.p,
                                       h->d_short.p, eb);
+        } else if (seg_out && cap) {
+            // one sweep: owner groups sized from the expected split (+ 6 sigma); an overflow falls back to count + scatter
+            unsigned long long seg[128] = {0}, at = 0;
+            for (uint32_t r = 0; r < nparts; r++) {
+                seg[r] = at;
+                seg[64 + r] = (unsigned long long)(expect[r] + 6.0 * std::sqrt(expect[r] + 1.0) + 256.0);
+                at += seg[64 + r];
+            }
+            if (at <= cap) {
+                int *overflow = reinterpret_cast<int *>(h->d_emit.p + 3 * 64);
+                CK(h, cudaMemsetAsync(h->d_emit.p, 0, (3 * 64 + 1) * 8, h->st));
+                CK(h, cudaMemcpyAsync(h->d_emit.p + 64, seg, 128 * 8, cudaMemcpyHostToDevice, h->st));  // [64,128) offsets, [128,192) capacities
+                // cursors live in [0, 64): the kernel reads seg_off[r] and seg_off[64 + r]
+                launch_emit_selected(h->st, plan_d, n_cand, h->d_cand_keys.p, h->d_flags.p, h->d_fscan.p, d_all_base, nparts, n_len, 2,
+                                     nullptr, h->d_emit.p + 64, h->d_emit.p, records, h->d_short.p, h->rec8 ? 1 : 0, overflow);
+                tm.stop();
+                CK(h, cudaGetLastError());
+                std::vector<int> shortf(nc, 0);
+                int ovf = 0;
+                CK(h, cudaMemcpyAsync(shortf.data(), h->d_short.p, nc * 4, cudaMemcpyDeviceToHost, h->st));
+                CK(h, cudaMemcpyAsync(h_counts, h->d_emit.p, nparts * 8, cudaMemcpyDeviceToHost, h->st));
+                CK(h, cudaMemcpyAsync(&ovf, overflow, 4, cudaMemcpyDeviceToHost, h->st));
+                CK(h, cudaStreamSynchronize(h->st));
+                bool again = false;
+                for (uint32_t c = 0; c < nc; c++)
+                    if (shortf[c]) { c_cand[c] = c_cand[c] * 2 + 1024; again = true; }
+                if (again) continue;
+                if (!ovf) {
+                    unsigned long long total = 0;
+                    for (uint32_t r = 0; r < nparts; r++) { counts_out[r] = h_counts[r]; seg_out[r] = seg[r]; total += h_counts[r]; }
+                    *needed_out = total;
+                    break;
+                }
+                // overflow: the split was unusually skewed - redo this attempt with the exact counts (below)
+                for (uint32_t r = 0; r < nparts; r++) h_counts[r] = 0;
+            }
+            seg_out = nullptr;  // this call continues in the two-pass form; the caller sees contiguous groups (seg_out untouched => prefix of counts)
+            continue;
         } else {  // count per owner, then scatter into the owner groups
             CK(h, cudaMemsetAsync(h->d_emit.p, 0, 3 * 64 * 8, h->st));
             launch_emit_selected(h->st, plan_d, n_cand, h->d_cand_keys.p, h->d_flags.p, h->d_fscan.p, d_all_base, nparts, n_len, 0,
@@ -1583,7 +1624,8 @@ int rlsim_select_classes(rlsim_handle *h, const uint64_t *all_totals, uint32_t n
 }
 }  // extern "C"
 int rl_api::select_partitioned(rlsim_handle *h, const uint64_t *all_totals, uint32_t nparts, uint32_t part, uint32_t n_len_in,
-                               void *records_dev, uint64_t cap, uint64_t *counts_out, uint64_t *needed_out, bool sync_records) {
+                               void *records_dev, uint64_t cap, uint64_t *counts_out, uint64_t *needed_out, bool sync_records,
+                               uint64_t *seg_out) {
     if (!h->amplified) FAIL(h, RLSIM_E_ARG, "rlsim_pcr first");
     if (!h->have_target) FAIL(h, RLSIM_E_ARG, "no target histogram");
     if (nparts < 1 || nparts > 64 || part >= nparts) FAIL(h, RLSIM_E_ARG, "invalid rank partition");
@@ -1610,7 +1652,15 @@ int rl_api::select_partitioned(rlsim_handle *h, const uint64_t *all_totals, uint
     CK(h, cudaMemsetAsync(h->d_error.p, 0, 4, h->st));
     static uint4 dummy_sentinel;
     uint4 *rec = records_dev ? (uint4 *)records_dev : &dummy_sentinel;  // non-null => record form; cap 0 => sizes only
-    return select_core(h, T, mine, nparts, part, h->d_all_base.p, rec, records_dev ? cap : 0, counts_out, needed_out, sync_records);
+    std::vector<uint64_t> tot_mat;
+    if (seg_out) {  // the expected split needs every rank's totals on this handle's length grid
+        tot_mat.assign((size_t)nparts * n_len, 0);
+        for (uint32_t r = 0; r < nparts; r++)
+            for (uint32_t l = 0; l < n_len && l < n_len_in; l++) tot_mat[(size_t)r * n_len + l] = all_totals[(size_t)r * n_len_in + l];
+        for (uint32_t r = 0; r < nparts; r++) seg_out[r] = ~0ull;  // stays so when the call ends in the two-pass form
+    }
+    return select_core(h, T, mine, nparts, part, h->d_all_base.p, rec, records_dev ? cap : 0, counts_out, needed_out, sync_records,
+                       seg_out ? tot_mat.data() : nullptr, seg_out);
 }
 extern "C" {
 

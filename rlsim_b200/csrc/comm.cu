@@ -189,12 +189,12 @@ int rlsim_sample_distributed(rlsim_handle *h) {
     const size_t u64_per_rec = rec8 ? 1 : 2;
     struct Rec8Off { rlsim_handle *h; ~Rec8Off() { h->rec8 = false; } } rec8_off{h};  // the C-ABI record form stays 16 bytes
     // ---- 2. draw this rank's classes; records grouped by owner rank in the send buffer
-    uint64_t counts[64] = {0}, needed = 0;
+    uint64_t counts[64] = {0}, seg[64], needed = 0;
     uint64_t cap = std::max<uint64_t>(h->d_rec_send.n, h->req_frags / N + h->req_frags / (8 * N) + 4096);
     for (int attempt = 0;; attempt++) {
         if (attempt > 3) FAIL(h, RLSIM_E_NOMEM, "selection record buffer kept overflowing");
         CK(h, h->d_rec_send.ensure(cap));
-        if ((rc = select_partitioned(h, all_tot.data(), N, me, n_len, h->d_rec_send.p, h->d_rec_send.n, counts, &needed, false))) return rc;
+        if ((rc = select_partitioned(h, all_tot.data(), N, me, n_len, h->d_rec_send.p, h->d_rec_send.n, counts, &needed, false, seg))) return rc;
         if (needed <= h->d_rec_send.n) break;
         cap = needed + needed / 8 + 4096;
     }
@@ -207,6 +207,8 @@ int rlsim_sample_distributed(rlsim_handle *h) {
     if ((rc = gather_rows(h, h->d_x_send.p, N))) return rc;
     std::vector<uint64_t> send_off(N + 1), recv_off(N + 1);
     rlsim_exchange_plan(h->x_pin, N, me, send_off.data(), recv_off.data());
+    if (seg[0] != ~0ull)  // one-sweep emit: the owner groups sit at their pre-sized offsets, not back to back
+        for (uint32_t r = 0; r < N; r++) send_off[r] = seg[r];
     std::vector<uint64_t> from(N);
     for (uint32_t r = 0; r < N; r++) from[r] = h->x_pin[(size_t)r * N + me];
     const uint64_t total_recv = recv_off[N];

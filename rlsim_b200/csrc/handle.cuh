@@ -334,11 +334,14 @@ int cub_temp(rlsim_handle *h, size_t bytes);
 int target_host(rlsim_handle *h);
 int d2h_any(rlsim_handle *h, void *dst, const void *src, size_t bytes);
 void set_target_from_hist(rlsim_handle *h, const uint64_t *hist, uint32_t n);
+// seg_out != null (the library's own exchange): one sweep into owner groups whose capacities come from the expected split
+// (all_tot = every rank's per-length totals, [nparts][n_len]); seg_out[r] = where rank r's group starts in `records`
 int select_core(rlsim_handle *h, const std::vector<uint64_t> &T, const std::vector<uint64_t> &base, uint32_t nparts,
                 uint32_t part, const uint64_t *d_all_base, uint4 *records, uint64_t cap, uint64_t *counts_out,
-                uint64_t *needed_out, bool sync_records = true);
+                uint64_t *needed_out, bool sync_records = true, const uint64_t *all_tot = nullptr, uint64_t *seg_out = nullptr);
 int select_partitioned(rlsim_handle *h, const uint64_t *all_totals, uint32_t nparts, uint32_t part, uint32_t n_len_in,
-                       void *records_dev, uint64_t cap, uint64_t *counts_out, uint64_t *needed_out, bool sync_records);
+                       void *records_dev, uint64_t cap, uint64_t *counts_out, uint64_t *needed_out, bool sync_records,
+                       uint64_t *seg_out = nullptr);
 int finish_sample(rlsim_handle *h);
 int apply_records(rlsim_handle *h, const void *records_dev, uint64_t n);
 void comm_destroy(rlsim_handle *h);  // comm.cu

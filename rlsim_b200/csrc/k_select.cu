@@ -226,12 +226,14 @@ __device__ __forceinline__ uint32_t owner_of(const uint64_t *all_base, uint32_t 
 }
 constexpr int EMIT_THREADS = 256;
 constexpr int EMIT_MAX_PARTS = 64;
-// pass 0: per-owner counts (+ per-class "not enough distinct candidates" flags); pass 1: scatter into the owner groups
+// pass 0: per-owner counts (+ per-class "not enough distinct candidates" flags); pass 1: scatter into the owner groups;
+// pass 2: both in one sweep - the owner groups have capacities sized by the host from the expected split (seg_off[64 + r]),
+// a record that does not fit raises *overflow and the host falls back to passes 0 + 1
 __global__ void __launch_bounds__(EMIT_THREADS)
 k_emit_selected(DevClassPlan plan, uint64_t n_cand, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ flags,
                 const uint64_t *__restrict__ fscan, const uint64_t *__restrict__ all_base, uint32_t nparts, uint32_t n_len,
                 int pass, unsigned long long *__restrict__ counts, const unsigned long long *__restrict__ seg_off,
-                unsigned long long *__restrict__ cursor, uint4 *__restrict__ records, int *short_flag, int compact) {
+                unsigned long long *__restrict__ cursor, uint4 *__restrict__ records, int *short_flag, int compact, int *overflow) {
     __shared__ unsigned int cnt_s[EMIT_MAX_PARTS];
     __shared__ unsigned long long base_s[EMIT_MAX_PARTS];
     if (threadIdx.x < EMIT_MAX_PARTS) cnt_s[threadIdx.x] = 0;
@@ -242,7 +244,7 @@ k_emit_selected(DevClassPlan plan, uint64_t n_cand, const uint64_t *__restrict__
     uint64_t x = 0;
     if (g < n_cand) {
         uint32_t c = class_of(plan, g);
-        if (pass == 0 && g == plan.cand_off[c]) {
+        if (pass != 1 && g == plan.cand_off[c]) {
             uint64_t distinct = fscan[plan.cand_off[c + 1]] - fscan[plan.cand_off[c]];
             if (distinct < plan.pick[c]) short_flag[c] = 1;
         }
@@ -262,18 +264,20 @@ k_emit_selected(DevClassPlan plan, uint64_t n_cand, const uint64_t *__restrict__
     if (pass == 0) return;
     __syncthreads();
     if (sel) {
+        const unsigned long long pos = base_s[owner] + local;
+        if (pass == 2 && pos - seg_off[owner] >= seg_off[EMIT_MAX_PARTS + owner]) { atomicExch(overflow, 1); return; }
         // compact form (the library's own exchange): 8 bytes, length in the top 24 bits - every class total is below 2^40
-        if (compact) reinterpret_cast<uint64_t *>(records)[base_s[owner] + local] = ((uint64_t)l << 40) | x;
-        else records[base_s[owner] + local] = make_uint4(l, 0u, (uint32_t)(x & 0xffffffffu), (uint32_t)(x >> 32));
+        if (compact) reinterpret_cast<uint64_t *>(records)[pos] = ((uint64_t)l << 40) | x;
+        else records[pos] = make_uint4(l, 0u, (uint32_t)(x & 0xffffffffu), (uint32_t)(x >> 32));
     }
 }
 void launch_emit_selected(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, const uint64_t *keys, const uint32_t *flags,
                           const uint64_t *fscan, const uint64_t *all_base, uint32_t nparts, uint32_t n_len, int pass,
                           unsigned long long *counts, const unsigned long long *seg_off, unsigned long long *cursor,
-                          uint4 *records, int *short_flag, int compact) {
+                          uint4 *records, int *short_flag, int compact, int *overflow) {
     if (n_cand)
         k_emit_selected<<<(unsigned)((n_cand + EMIT_THREADS - 1) / EMIT_THREADS), EMIT_THREADS, 0, st>>>(
-            plan, n_cand, keys, flags, fscan, all_base, nparts, n_len, pass, counts, seg_off, cursor, records, short_flag, compact);
+            plan, n_cand, keys, flags, fscan, all_base, nparts, n_len, pass, counts, seg_off, cursor, records, short_flag, compact, overflow);
 }
 
 // records received from the drawing ranks -> hits on this rank's species

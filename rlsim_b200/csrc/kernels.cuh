@@ -90,7 +90,7 @@ void launch_apply_picks_sorted(cudaStream_t st, DevClassPlan plan, uint64_t n_ca
 void launch_emit_selected(cudaStream_t st, DevClassPlan plan, uint64_t n_cand, const uint64_t *keys, const uint32_t *flags,
                           const uint64_t *fscan, const uint64_t *all_base, uint32_t nparts, uint32_t n_len, int pass,
                           unsigned long long *counts, const unsigned long long *seg_off, unsigned long long *cursor,
-                          uint4 *records, int *short_flag, int compact = 0);
+                          uint4 *records, int *short_flag, int compact = 0, int *overflow = nullptr);
 void launch_apply_records(cudaStream_t st, const uint4 *records, uint64_t n, const uint64_t *my_base, const uint64_t *cls_pre,
                           const uint64_t *bounds, const uint32_t *order, unsigned long long *hits, int *error, int compact = 0);
 void launch_taken(cudaStream_t st, const DevSpecies &sp, const uint8_t *mode_by_len, uint32_t n_len,
