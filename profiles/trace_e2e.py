@@ -35,3 +35,24 @@ for step in range(4):
     packed, _ = h.sampled_packed()
     t.append(time.perf_counter())
     print("step %d: configure %.3f add %.3f build %.3f sample %.3f d2h %.3f ms" % ((step,) + tuple(1000 * (y - x) for x, y in zip(t[:-1], t[1:]))), file=sys.stderr)
+
+# ---- how long do the same bytes take as bare chunked copies, and as add_transcripts without the eager groups?
+os.environ.pop("RLSIM_TRACE", None)
+dst = torch.empty(pb.numel(), dtype=torch.uint8, device="cuda:0")
+CH = 32 << 20
+for rep in range(3):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for a in range(0, pb.numel(), CH):
+        dst[a:a + CH].copy_(pb[a:a + CH], non_blocking=True)
+    torch.cuda.synchronize()
+    print("bare chunked H2D of %d MB: %.3f ms" % (pb.numel() >> 20, 1000 * (time.perf_counter() - t0)), file=sys.stderr)
+os.environ["RLSIM_NO_EAGER"] = "1"
+for rep in range(3):
+    torch.cuda.synchronize()
+    pool.reset().configure(bench.make_args(int(bench.C3_FRAGS * scale), 50 + rep))
+    h.set_first_index(0)
+    t0 = time.perf_counter()
+    h.add_transcripts_raw(pb, po, pl, n_tr)
+    torch.cuda.synchronize()
+    print("add_transcripts without eager groups (copy + ingest + prefix only): %.3f ms" % (1000 * (time.perf_counter() - t0)), file=sys.stderr)
