@@ -14,6 +14,7 @@ species dedup -> PCR -> per-length pools -> without-replacement draw -> fragment
                    device copy of the transcripts and device -> pinned-host read of the sampled fragment records (packed
                    form, 6 B per record) inside the timed region, every step
     e2e_pageable : e2e with plain (unpinned) numpy buffers on both sides - what a cgo caller hands over
+    e2e_packed_in: e2e from a host that keeps the transcriptome as 2-bit codes + N mask (rlsim_add_transcripts_packed)
     e2e_dropin   : FASTA text in -> FASTA text out (rlsim_add_fasta ... rlsim_format_fasta): what the reference's CLI does
     verified     : outside the timed regions - the eager end-to-end result, the pageable one and the monolithic
                    device-resident one give the same digest for one seed
@@ -256,14 +257,17 @@ def main():
         else:
             h.sample()
 
-    def step_e2e(step, timed=False, pageable=None):
-        """public API, host buffers in, host records out.  pageable = (bases, off, levels, out) plain numpy buffers."""
+    def step_e2e(step, timed=False, pageable=None, packed=None):
+        """public API, host buffers in, host records out.  pageable = (bases, off, levels, out) plain numpy buffers;
+        packed = (codes, nmask) pinned arrays of rlsim_add_transcripts_packed."""
         t = [time.perf_counter()]
         pool.reset().configure(make_args(wl.n_frags_global, step + 1))
         t.append(time.perf_counter())
         h.set_first_index(wl.first)
         if pageable:
             h.add_transcripts_raw(pageable[0], pageable[1], pageable[2], wl.n_tr)
+        elif packed:
+            h.add_transcripts_packed(packed[0], packed[1], wl.off, wl.levels, wl.n_tr)
         else:
             h.add_transcripts_raw(wl.bases, wl.off, wl.levels, wl.n_tr)
         t.append(time.perf_counter())
@@ -371,6 +375,22 @@ def main():
                             "staged_by_library": staged, "stage_threads": int(os.environ.get("RLSIM_STAGE_THREADS", "0")) or min(6, max(1, (os.cpu_count() or 2) - 1)),
                             "note": "same step with plain numpy buffers on both sides (what a cgo caller hands over): chunks staged through "
                                     "a ring of pinned slots by the library's copy threads"}
+    # ---- e2e from a host that keeps its transcriptome packed (2-bit codes + N mask; 0.375 B per base on the host link)
+    e2e_packed_in = None
+    if world == 1 and not opts.no_extras:
+        codes_np, nmask_np = _native.pack_bases(wl.bases_np)  # once, outside the timed region: the host's own resident format
+        pk = (pin(codes_np), pin(nmask_np) if nmask_np is not None else None)
+        n_k = step_e2e(VS, packed=pk)
+        d_pk = result_digest(wl.out, n_k)
+        verified = verified and d_pk == d_eager
+        verify_note["packed_in_e2e_digest"] = d_pk[:16]
+        ksteps = max(1, min(10, opts.steps))
+        step_e2e(VS + 2, packed=pk)
+        n_kk, t_kk = timed_loop(step_e2e, ksteps, 600, packed=pk)
+        e2e_packed_in = {"value": n_kk / t_kk, "unit": "fragments/s", "steps": ksteps, "ms_per_step": 1000.0 * t_kk / ksteps,
+                         "h2d_bytes_per_step": int(pk[0].numel() + (pk[1].numel() if pk[1] is not None else 0) + wl.off.numel() * 8 + wl.levels.numel() * 8),
+                         "note": "same step through rlsim_add_transcripts_packed: the host holds 2-bit codes (+ a mask for letters outside "
+                                 "ACGT) instead of ASCII; packing is the host's one-off cost and is not timed"}
     # ---- FASTA text in / out (SURVEY 8f rows 1 + 3): the reference CLI's own boundary
     e2e_text_in = e2e_dropin = None
     if world == 1 and not opts.no_extras:
@@ -544,6 +564,7 @@ def main():
                 "copy_ceiling_ms": ceiling_ms,
                 "frac_of_copy_ceiling": (ceiling_ms / e2e_ms) if ceiling_ms else None},
         "e2e_pageable": e2e_pageable,
+        "e2e_packed_in": e2e_packed_in,
         "e2e_text_in": e2e_text_in,
         "e2e_dropin": e2e_dropin,
         "strong": strong,

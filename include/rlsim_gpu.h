@@ -136,6 +136,17 @@ int rlsim_set_target_hist(rlsim_handle *h, const uint32_t *lengths, const uint64
  * finishes the per-length view (rlsim_stats.flags & RLSIM_F_EAGER).  The result does not depend on that. */
 int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t *offsets, const uint64_t *expr,
                           uint32_t n);
+/* The same batch from a host that keeps its transcriptome packed (0.375 B per base on the host link instead of 1):
+ * codes = 2 bits per base, base i of the concatenation in bits 2*(i&3) of byte i>>2 (A C G T = 0 1 2 3); nmask = 1 bit per
+ * base, bit i&7 of byte i>>3, set where the letter is outside ACGT (its code is ignored), or NULL when there is none.
+ * offsets[n+1] and expr[n] as for rlsim_add_transcripts (offsets count bases, offsets[0] need not be 0 or a multiple of 4).
+ * The library built from it is the one rlsim_add_transcripts builds from the same sequences with every letter outside
+ * ACGT written as 'N': exact for inputs whose only such letter is N.  (The reference itself tells other letters apart
+ * from N in one place only, the palindrome test of KmerAffinity, nnthermo.go:154-161: their doublets miss the energy
+ * maps alike, nnthermo.go:138-142, and none counts as G/C, thermocycler.go:161-166.)  FASTA output shows 'N' for them.
+ * Pinned caller arrays are copied directly; pageable ones go through the driver's staging. */
+int rlsim_add_transcripts_packed(rlsim_handle *h, const uint8_t *codes, const uint8_t *nmask, const uint64_t *offsets,
+                                 const uint64_t *expr, uint32_t n);
 /* Device-side FASTA reader (next row 8f-3; fasta.go:113-212 ReadFasta/FastaToSeq, input.go:82-124 ParseSeqName and the
  * -m multiplier): `text` = the raw bytes of the input files, concatenated as io.MultiReader would (fasta.go:98-104).
  * Record splitting, despacing, upper-casing and `name$level` parsing run on the GPU; records with malformed names are

@@ -24,7 +24,7 @@ F_MIRRORED_REVERSE, F_EAGER, F_PAGEABLE_STAGED, F_GROUPS_SHIFT, F_FUSED = 1, 2, 
 
 EXPORTS = [
     "rlsim_create", "rlsim_destroy", "rlsim_last_error", "rlsim_set_model", "rlsim_set_len_eff", "rlsim_set_raw_target",
-    "rlsim_sample_target", "rlsim_sample_target_range", "rlsim_set_target_hist", "rlsim_add_transcripts", "rlsim_add_fasta", "rlsim_get_fasta_index", "rlsim_set_first_index", "rlsim_clear_transcripts",
+    "rlsim_sample_target", "rlsim_sample_target_range", "rlsim_set_target_hist", "rlsim_add_transcripts", "rlsim_add_transcripts_packed", "rlsim_add_fasta", "rlsim_get_fasta_index", "rlsim_set_first_index", "rlsim_clear_transcripts",
     "rlsim_build_library", "rlsim_fragment", "rlsim_pcr", "rlsim_class_totals", "rlsim_sample", "rlsim_select_classes", "rlsim_apply_selected", "rlsim_finish_sample", "rlsim_get_stats",
     "rlsim_get_hist", "rlsim_get_species", "rlsim_get_sampled", "rlsim_get_sampled_packed", "rlsim_format_fasta", "rlsim_probe_kmer_lut",
     "rlsim_probe_prefix", "rlsim_probe_gc_prefix", "rlsim_probe_math", "rlsim_probe_philox", "rlsim_probe_amplify",
@@ -71,6 +71,7 @@ def load():
         "rlsim_sample_target_range": (i32, [vp, u64, u64]),
         "rlsim_set_target_hist": (i32, [vp, vp, vp, u32]),
         "rlsim_add_transcripts": (i32, [vp, vp, vp, vp, u32]),
+        "rlsim_add_transcripts_packed": (i32, [vp, vp, vp, vp, vp, u32]),
         "rlsim_add_fasta": (i32, [vp, vp, u64, C.c_double, C.POINTER(u32), C.POINTER(u32)]),
         "rlsim_get_fasta_index": (i32, [vp] + [vp] * 6),
         "rlsim_set_first_index": (i32, [vp, u32]),
@@ -107,6 +108,23 @@ def load():
         f.restype, f.argtypes = res, args
     _lib = L
     return L
+
+
+def pack_bases(bases):
+    """ASCII bases (uint8 array, upper case) -> (codes, nmask) in the layout of rlsim_add_transcripts_packed: 2 bits per base
+    (A C G T = 0 1 2 3, base i in bits 2*(i&3) of byte i>>2) and 1 bit per base for letters outside ACGT (bit i&7 of byte
+    i>>3), or nmask = None when every letter is one of ACGT.  What a host that keeps its transcriptome packed does once."""
+    b = np.ascontiguousarray(bases, dtype=np.uint8)
+    lut = np.full(256, 4, np.uint8)
+    lut[[65, 67, 71, 84]] = [0, 1, 2, 3]
+    c = lut[b]
+    bad = c == 4
+    c[bad] = 0
+    pad = (-len(c)) % 4
+    c4 = np.concatenate([c, np.zeros(pad, np.uint8)]).reshape(-1, 4)
+    codes = (c4[:, 0] | (c4[:, 1] << 2) | (c4[:, 2] << 4) | (c4[:, 3] << 6)).astype(np.uint8)
+    nmask = np.packbits(bad, bitorder="little") if bad.any() else None
+    return codes, nmask
 
 
 def comm_unique_id():
@@ -204,6 +222,11 @@ class Handle:
     def add_transcripts_raw(self, bases, offsets, expr, n):
         """bases/offsets/expr: host numpy arrays or (pinned) torch tensors."""
         self._chk(self.L.rlsim_add_transcripts(self.h, _addr(bases), _addr(offsets), _addr(expr), int(n)))
+
+    def add_transcripts_packed(self, codes, nmask, offsets, expr, n):
+        """codes / nmask as pack_bases() returns them (nmask may be None); offsets count bases."""
+        self._chk(self.L.rlsim_add_transcripts_packed(self.h, _addr(codes), _addr(nmask) if nmask is not None else None,
+                                                      _addr(offsets), _addr(expr), int(n)))
 
     def add_transcripts(self, seqs, expr):
         bases = np.frombuffer(b"".join(seqs), dtype=np.uint8) if seqs else np.zeros(0, np.uint8)

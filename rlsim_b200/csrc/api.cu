@@ -792,8 +792,11 @@ __global__ void k_copy_meta(const uint64_t *__restrict__ h_off, const uint32_t *
     if (i < n) { d_len[i] = h_len[i]; d_expr[i] = h_expr[i]; }
 }
 
-// bases: host memory (copied in pipelined chunks), or -- dev_bases -- sequences already in device memory
-static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_bases, const uint64_t *offsets, const uint64_t *expr, uint32_t n) {
+// bases: host memory (copied in pipelined chunks), or -- dev_bases -- sequences already in device memory.
+// packed: `bases` holds 2-bit codes (4 bases per byte) and `pk_mask` (may be null) 1 bit per base, both indexed by the
+// same base offsets as an ASCII batch (rlsim_add_transcripts_packed); 0.375 B per base cross the host link.
+static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_bases, const uint64_t *offsets, const uint64_t *expr, uint32_t n,
+                    bool packed = false, const uint8_t *pk_mask = nullptr) {
     if (!h->have_model) FAIL(h, RLSIM_E_ARG, "rlsim_set_model must precede rlsim_add_transcripts (the poly(A) maximum shapes the layout)");
     if (n == 0) return 0;
     cudaSetDevice(h->device);
@@ -833,7 +836,9 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     CK(h, h->d_mol_off.grow_preserve(nn + 1, n0 + 1, h->st));
     CK(h, h->d_dirty.grow_preserve(nn + 1, n0, h->st));
     CK(h, h->staging.off.ensure(n + 1));
-    if (!dev_bases) CK(h, h->staging.bases.ensure(nbytes + 64));  // k_ingest reads whole aligned words
+    // packed source: codes from byte (o0 >> 2) of the caller's array at staging byte 0, the mask from byte (o0 >> 3) at pk_m0
+    const uint64_t pk_m0 = ((nbytes >> 2) + 64 + 15) & ~15ull;
+    if (!dev_bases) CK(h, h->staging.bases.ensure(std::max(nbytes + 64, pk_m0 + (nbytes >> 3) + 80)));  // the ingest kernels read whole aligned words
     // ---- the chunks
     // (measured) a timing event recorded on the compute stream while the chunk copies are queued completes only after
     // all of them, and holds back the first ingest: the stage timer starts before the copies are queued
@@ -865,7 +870,9 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     // ring of pinned slots by a feeder thread + copy team while the previous slot is on the wire.  Pinned buffers are
     // copied directly.  `issued` = chunks whose copy and event have been queued (the main thread waits for it before it
     // touches a chunk's event).
-    const bool stage = !dev_bases && nbytes > 0 && !getenv("RLSIM_NO_STAGING") && !host_pinned(bases + o0);
+    // (a pageable packed batch is left to the driver's own staging: a third of the bytes, and hosts that keep a packed
+    // transcriptome can keep it pinned)
+    const bool stage = !dev_bases && !packed && nbytes > 0 && !getenv("RLSIM_NO_STAGING") && !host_pinned(bases + o0);
     h->staged_pageable = stage;
     std::atomic<uint32_t> issued{0};
     std::atomic<int> feeder_err{0};
@@ -874,7 +881,12 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     struct Joiner { std::thread &t; cudaStream_t sc; ~Joiner() { if (t.joinable()) t.join(); cudaStreamSynchronize(sc); } } joiner{feeder, h->st_copy};
     if (!stage) {
         for (uint32_t c = 0; c < n_chunks; c++) {  // all copies are queued first: the copy engine never waits for the host
-            if (chunk_b(c) > chunk_a(c) && !dev_bases)
+            if (chunk_b(c) > chunk_a(c) && packed) {
+                const uint64_t A = o0 + chunk_a(c), B = o0 + chunk_b(c);  // base range of the chunk in the caller's arrays
+                CK(h, cudaMemcpyAsync(h->staging.bases.p + ((A >> 2) - (o0 >> 2)), bases + (A >> 2), ((B + 3) >> 2) - (A >> 2), cudaMemcpyHostToDevice, h->st_copy));
+                if (pk_mask)
+                    CK(h, cudaMemcpyAsync(h->staging.bases.p + pk_m0 + ((A >> 3) - (o0 >> 3)), pk_mask + (A >> 3), ((B + 7) >> 3) - (A >> 3), cudaMemcpyHostToDevice, h->st_copy));
+            } else if (chunk_b(c) > chunk_a(c) && !dev_bases)
                 CK(h, cudaMemcpyAsync(h->staging.bases.p + chunk_a(c), bases + o0 + chunk_a(c), chunk_b(c) - chunk_a(c), cudaMemcpyHostToDevice, h->st_copy));
             CK(h, cudaEventRecord(h->ev_chunk[c], h->st_copy));
         }
@@ -983,8 +995,14 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
         for (uint32_t cc = c; cc < c_end; cc++) {
             const uint32_t t0 = cuts[cc], t1 = cuts[cc + 1];
             CK(h, cudaStreamWaitEvent(h->st, h->ev_chunk[cc], 0));
-            launch_ingest(h->st, src, h->staging.off.p + t0, t1 - t0, n0 + t0, (h->h_off[n0 + t1] - h->h_off[n0 + t0]) >> 5,
-                          h->polya_max, h->d_off.p + n0 + t0, h->d_bases.p, h->d_packed.p, h->d_nmask.p, h->d_gc.p, h->d_dirty.p);
+            if (packed)
+                launch_ingest_packed(h->st, reinterpret_cast<const uint32_t *>(h->staging.bases.p),
+                                     pk_mask ? reinterpret_cast<const uint32_t *>(h->staging.bases.p + pk_m0) : nullptr, (uint32_t)(o0 & 3), (uint32_t)(o0 & 7),
+                                     h->staging.off.p + t0, t1 - t0, n0 + t0, (h->h_off[n0 + t1] - h->h_off[n0 + t0]) >> 5, h->polya_max,
+                                     h->d_off.p + n0 + t0, h->d_bases.p, h->d_packed.p, h->d_nmask.p, h->d_gc.p, h->d_dirty.p);
+            else
+                launch_ingest(h->st, src, h->staging.off.p + t0, t1 - t0, n0 + t0, (h->h_off[n0 + t1] - h->h_off[n0 + t0]) >> 5,
+                              h->polya_max, h->d_off.p + n0 + t0, h->d_bases.p, h->d_packed.p, h->d_nmask.p, h->d_gc.p, h->d_dirty.p);
             h->launches[RLSIM_T_LAYOUT] += 3;
             if (want_prefix) { int rc = launch_prefix_range(h, n0 + t0, n0 + t1); if (rc) return rc; }
         }
@@ -1030,6 +1048,16 @@ int rlsim_add_transcripts(rlsim_handle *h, const uint8_t *bases, const uint64_t 
 }
 
 // Device-side FASTA reader (k_fasta_in.cu): fasta.go:113-212 + input.go:82-124 in four kernels, then the usual ingest
+int rlsim_add_transcripts_packed(rlsim_handle *h, const uint8_t *codes, const uint8_t *nmask, const uint64_t *offsets, const uint64_t *expr,
+                                 uint32_t n) {
+    if (!codes && n && offsets[n] > offsets[0]) FAIL(h, RLSIM_E_ARG, "rlsim_add_transcripts_packed: codes is NULL");
+    try {
+        return add_core(h, codes, nullptr, offsets, expr, n, true, nmask);
+    } catch (const std::bad_alloc &) {
+        FAIL(h, RLSIM_E_NOMEM, "out of host memory while adding transcripts");
+    }
+}
+
 int rlsim_add_fasta(rlsim_handle *h, const uint8_t *text, uint64_t n_bytes, double expr_mul, uint32_t *n_records, uint32_t *n_added) {
     if (n_records) *n_records = 0;
     if (n_added) *n_added = 0;

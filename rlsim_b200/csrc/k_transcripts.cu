@@ -27,16 +27,9 @@ __device__ __forceinline__ uint32_t gather_bit0(uint32_t z) {  // bit 0 of each 
     return (z | (z >> 7) | (z >> 14) | (z >> 21)) & 0xfu;
 }
 
-__global__ void __launch_bounds__(INGEST_THREADS)
-k_ingest(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, uint32_t n, uint32_t t_index0, uint32_t polya_max,
-         const uint64_t *__restrict__ off, uint8_t *__restrict__ bases, uint32_t *__restrict__ packed,
-         uint32_t *__restrict__ nmask, uint2 *__restrict__ gc, uint32_t *__restrict__ dirty) {
-    const uint64_t P0 = off[0], n_groups = (off[n] - P0) >> 5;
-    const uint64_t g = (uint64_t)blockIdx.x * INGEST_THREADS + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    // transcript of the warp's first group: 32-ary search, every lane probes one split point per round
-    const uint64_t gw = min(g - lane, n_groups ? n_groups - 1 : 0);
-    const uint64_t Pw = P0 + (gw << 5);
+// Transcript of the warp's first 32-base group (padded position Pw): 32-ary search, every lane probes one split point per
+// round.  Returns lo with off[lo] <= Pw < off[hi]; must be called by all 32 lanes.
+__device__ __forceinline__ uint32_t warp_first_transcript(const uint64_t *__restrict__ off, uint32_t n, uint64_t Pw, int lane) {
     uint32_t lo = 0, hi = n;  // invariant: off[lo] <= Pw < off[hi]
     while (hi - lo > 1) {
         uint32_t span = hi - lo;
@@ -52,6 +45,18 @@ k_ingest(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, 
             hi = lo + 1;
         } else { lo = new_lo; hi = new_hi; }
     }
+    return lo;
+}
+
+__global__ void __launch_bounds__(INGEST_THREADS)
+k_ingest(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off, uint32_t n, uint32_t t_index0, uint32_t polya_max,
+         const uint64_t *__restrict__ off, uint8_t *__restrict__ bases, uint32_t *__restrict__ packed,
+         uint32_t *__restrict__ nmask, uint2 *__restrict__ gc, uint32_t *__restrict__ dirty) {
+    const uint64_t P0 = off[0], n_groups = (off[n] - P0) >> 5;
+    const uint64_t g = (uint64_t)blockIdx.x * INGEST_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const uint64_t gw = min(g - lane, n_groups ? n_groups - 1 : 0);
+    const uint32_t lo = warp_first_transcript(off, n, P0 + (gw << 5), lane);
     if (g >= n_groups) return;
     const uint64_t P = P0 + (g << 5);
     uint32_t t = lo;
@@ -134,6 +139,102 @@ void launch_ingest(cudaStream_t st, const uint8_t *src, const uint64_t *src_off,
     if (n_groups)
         k_ingest<<<(unsigned)((n_groups + INGEST_THREADS - 1) / INGEST_THREADS), INGEST_THREADS, 0, st>>>(
             src, src_off, n, t_index0, polya_max, off, bases, packed, nmask, gc, dirty);
+    k_gc_scan<<<(n + INGEST_THREADS / 32 - 1) / (INGEST_THREADS / 32), INGEST_THREADS, 0, st>>>(n, t_index0, off, gc);
+}
+
+// ---------------------------------------------------------------- ingest of a packed batch (rlsim_add_transcripts_packed)
+// The same outputs as k_ingest from a source that is already 2-bit packed: `codes` = 4 bases per byte (base i of the batch
+// at bits 2*(i&3) of byte i>>2; A C G T = 0 1 2 3), `mask` = 1 bit per base (bit i&7 of byte i>>3: a letter outside ACGT,
+// carried as 'N') or null.  Both device copies start at a 4-byte boundary of the source arrays: c_shift / m_shift = bases
+// between that boundary and the first base of the batch.  0.375 B per base on the host link instead of 1.
+__device__ __forceinline__ uint32_t even_bits(uint64_t x) {  // bits 0, 2, 4 ... 62 -> a 32-bit word
+    x &= 0x5555555555555555ull;
+    x = (x | (x >> 1)) & 0x3333333333333333ull;
+    x = (x | (x >> 2)) & 0x0f0f0f0f0f0f0f0full;
+    x = (x | (x >> 4)) & 0x00ff00ff00ff00ffull;
+    x = (x | (x >> 8)) & 0x0000ffff0000ffffull;
+    x = (x | (x >> 16)) & 0x00000000ffffffffull;
+    return (uint32_t)x;
+}
+__device__ __forceinline__ uint64_t spread_bits(uint32_t m) {  // bit i -> bits 2i and 2i+1
+    uint64_t x = m;
+    x = (x | (x << 16)) & 0x0000ffff0000ffffull;
+    x = (x | (x << 8)) & 0x00ff00ff00ff00ffull;
+    x = (x | (x << 4)) & 0x0f0f0f0f0f0f0f0full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;
+    x = (x | (x << 1)) & 0x5555555555555555ull;
+    return x | (x << 1);
+}
+
+__global__ void __launch_bounds__(INGEST_THREADS)
+k_ingest_packed(const uint32_t *__restrict__ codes, const uint32_t *__restrict__ mask, uint32_t c_shift, uint32_t m_shift,
+                const uint64_t *__restrict__ src_off, uint32_t n, uint32_t t_index0, uint32_t polya_max,
+                const uint64_t *__restrict__ off, uint8_t *__restrict__ bases, uint32_t *__restrict__ packed,
+                uint32_t *__restrict__ nmask, uint2 *__restrict__ gc, uint32_t *__restrict__ dirty) {
+    const uint64_t P0 = off[0], n_groups = (off[n] - P0) >> 5;
+    const uint64_t g = (uint64_t)blockIdx.x * INGEST_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const uint64_t gw = min(g - lane, n_groups ? n_groups - 1 : 0);
+    uint32_t t = warp_first_transcript(off, n, P0 + (gw << 5), lane);
+    if (g >= n_groups) return;
+    const uint64_t P = P0 + (g << 5);
+    while (off[t + 1] <= P) t++;  // later lanes may sit in later transcripts (zero-length ones are skipped)
+    const uint64_t so = src_off[t];
+    const uint32_t l = (uint32_t)(src_off[t + 1] - so);
+    const uint32_t L = l + polya_max;
+    const uint32_t p0 = (uint32_t)(P - off[t]);
+    uint64_t pk = 0;
+    uint32_t mk = 0;
+    if (p0 < l) {
+        const uint32_t nsrc = min(l - p0, 32u);
+        const uint64_t real2 = nsrc >= 32 ? ~0ull : ((1ull << (2 * nsrc)) - 1ull);
+        const uint32_t real1 = nsrc >= 32 ? 0xffffffffu : ((1u << nsrc) - 1u);
+        const uint64_t qc = so + p0 + c_shift;  // base position in the device copy of the codes
+        const uint32_t *cw = codes + (qc >> 4);
+        const uint32_t sh = (uint32_t)(qc & 15) * 2;
+        const uint32_t w0 = __ldg(cw), w1 = __ldg(cw + 1), w2 = sh ? __ldg(cw + 2) : 0u;
+        pk = ((uint64_t)__funnelshift_r(w1, w2, sh) << 32 | __funnelshift_r(w0, w1, sh)) & real2;
+        if (mask) {
+            const uint64_t qm = so + p0 + m_shift;
+            const uint32_t *mw = mask + (qm >> 5);
+            const uint32_t ms = (uint32_t)(qm & 31);
+            mk = __funnelshift_r(__ldg(mw), ms ? __ldg(mw + 1) : 0u, ms) & real1;
+            pk &= ~spread_bits(mk);  // masked letters carry code 0, as k_ingest writes them
+        }
+    }
+    const uint32_t gm = even_bits(pk ^ (pk >> 1));  // G or C: exactly one of the two code bits
+    uint32_t out[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t c8 = (uint32_t)(pk >> (8 * j)) & 0xffu;
+        const uint32_t sel = (c8 & 3u) | ((c8 & 0xcu) << 2) | ((c8 & 0x30u) << 4) | ((c8 & 0xc0u) << 6);
+        uint32_t x = __byte_perm(0x54474341u, 0u, sel);  // "ACGT"[code] in each byte
+        const uint32_t m4 = (mk >> (4 * j)) & 0xfu;
+        const uint32_t mb = ((m4 & 1u) | ((m4 & 2u) << 7) | ((m4 & 4u) << 14) | ((m4 & 8u) << 21)) * 0xffu;
+        x = (x & ~mb) | (0x4e4e4e4eu & mb);
+        const int64_t q = (int64_t)p0 + 4 * j;
+        out[j] = x & byte_mask((int64_t)L - q);  // source letters, then the poly(A) tail (code 0 = 'A'), then zero padding
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(bases + P);
+    dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+    dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+    *reinterpret_cast<uint2 *>(packed + (P >> 4)) = make_uint2((uint32_t)pk, (uint32_t)(pk >> 32));
+    // beyond L the ASCII path marks the zero padding as "not ACGT" in nmask (mask bit of a zero byte): keep that
+    const uint32_t nreal = L > p0 ? min(L - p0, 32u) : 0u;
+    const uint32_t real = nreal >= 32 ? 0xffffffffu : ((1u << nreal) - 1u);
+    nmask[P >> 5] = mk | ~real;
+    if (mk & real) atomicOr(&dirty[t_index0 + t], 1u);
+    gc[(P >> 5) + t_index0 + t] = make_uint2(__popc(gm), gm);
+}
+
+void launch_ingest_packed(cudaStream_t st, const uint32_t *codes, const uint32_t *mask, uint32_t c_shift, uint32_t m_shift,
+                          const uint64_t *src_off, uint32_t n, uint32_t t_index0, uint64_t n_groups, uint32_t polya_max,
+                          const uint64_t *off, uint8_t *bases, uint32_t *packed, uint32_t *nmask, uint2 *gc, uint32_t *dirty) {
+    if (!n) return;
+    cudaMemsetAsync(dirty + t_index0, 0, (size_t)n * 4, st);
+    if (n_groups)
+        k_ingest_packed<<<(unsigned)((n_groups + INGEST_THREADS - 1) / INGEST_THREADS), INGEST_THREADS, 0, st>>>(
+            codes, mask, c_shift, m_shift, src_off, n, t_index0, polya_max, off, bases, packed, nmask, gc, dirty);
     k_gc_scan<<<(n + INGEST_THREADS / 32 - 1) / (INGEST_THREADS / 32), INGEST_THREADS, 0, st>>>(n, t_index0, off, gc);
 }
 

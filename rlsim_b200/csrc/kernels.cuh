@@ -8,6 +8,9 @@ namespace rl {
 void launch_ingest(cudaStream_t st, const uint8_t *src, const uint64_t *src_off, uint32_t n, uint32_t t_index0, uint64_t n_groups,
                    uint32_t polya_max, const uint64_t *off, uint8_t *bases, uint32_t *packed, uint32_t *nmask, uint2 *gc,
                    uint32_t *dirty);
+void launch_ingest_packed(cudaStream_t st, const uint32_t *codes, const uint32_t *mask, uint32_t c_shift, uint32_t m_shift,
+                          const uint64_t *src_off, uint32_t n, uint32_t t_index0, uint64_t n_groups, uint32_t polya_max,
+                          const uint64_t *off, uint8_t *bases, uint32_t *packed, uint32_t *nmask, uint2 *gc, uint32_t *dirty);
 void launch_kmer_lut(cudaStream_t st, int k, double T, double *K, unsigned long long *kmax_bits, uint32_t *wq_f,
                      uint32_t *wq_r, unsigned int *asym);
 void launch_prefix(cudaStream_t st, const DevTranscripts &tr, uint32_t t_begin, uint32_t t_end, int k, double T, const uint32_t *wq_f, const uint32_t *wq_r,

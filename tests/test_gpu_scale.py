@@ -321,6 +321,91 @@ def test_pageable_and_pinned_buffers_agree(gpu, monkeypatch):
     assert staged.fasta(names) == pinned.fasta(names)
 
 
+def test_packed_input_equals_ascii_input(oracle, gpu, monkeypatch):
+    """rlsim_add_transcripts_packed (2-bit codes + N mask, 0.375 B per base on the host link) builds the library
+    rlsim_add_transcripts builds from the same sequences: species, records and FASTA text, with runs of N, transcripts of
+    every length mod 32 (empty ones included), a batch that starts in the middle of a code byte, two batches on one handle,
+    pinned and pageable arrays, many small chunks; and the oracle agrees with both."""
+    import torch
+    rng = np.random.default_rng(77)
+    names, seqs, levels = util.synth_transcriptome(150, seed=31, mean_len=900, hi=3000, total_molecules=40000)
+    seqs, levels = list(seqs), list(levels)
+    for t in range(0, 150, 7):  # N runs and single Ns
+        b = bytearray(seqs[t])
+        a = int(rng.integers(0, max(1, len(b) - 60)))
+        r = int(rng.integers(1, 50))
+        b[a:a + r] = b"N" * len(b[a:a + r])
+        seqs[t] = bytes(b)
+    for t in range(40):  # every length mod 32, very short ones, an empty one
+        seqs[100 + t] = seqs[100 + t][:t]
+    argv = ["-n", "30000", "-c", "6", "-si", "12"]
+    args = util.parse(argv)
+    lead = 5  # the batch starts at base 5 of the caller's arrays: inside a code byte and a mask byte
+    bases = np.frombuffer(b"ACGTN" + b"".join(seqs), dtype=np.uint8)
+    off = np.zeros(len(seqs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(x) for x in seqs])
+    off += lead
+    lv = np.asarray(levels, dtype=np.uint64)
+    codes, nmask = gpu.pack_bases(bases)
+    assert nmask is not None and len(codes) == (len(bases) + 3) // 4
+
+    def run(add, split=None):
+        h = gpu.Handle(0)
+        h.set_model(args.to_params())
+        h.sample_target(args.req_frags)
+        n = len(seqs)
+        if split is None:
+            add(h, off, lv, n)
+        else:  # two batches
+            add(h, off[:split + 1].copy(), lv[:split].copy(), split)
+            add(h, off[split:].copy(), lv[split:].copy(), n - split)
+        h.build_library()
+        h.sample()
+        return h
+
+    ascii_h = run(lambda h, o, l, n: h.add_transcripts_raw(bases, o, l, n))
+    ref_sp, ref = ascii_h.species(), ascii_h.sampled()
+    assert int(ascii_h.stats().n_sampled) > 5000
+    pin = lambda x: torch.from_numpy(x).pin_memory()
+    variants = {
+        "pageable": lambda: run(lambda h, o, l, n: h.add_transcripts_packed(codes, nmask, o, l, n)),
+        "pinned": lambda: run(lambda h, o, l, n: h.add_transcripts_packed(pin(codes), pin(nmask), o, l, n)),
+        "two_batches": lambda: run(lambda h, o, l, n: h.add_transcripts_packed(codes, nmask, o, l, n), split=61),
+    }
+    monkeypatch.setenv("RLSIM_CHUNK_BYTES", "7001")
+    variants["small_chunks"] = lambda: run(lambda h, o, l, n: h.add_transcripts_packed(pin(codes), pin(nmask), o, l, n))
+    for name, make in variants.items():
+        if name == "small_chunks":
+            monkeypatch.setenv("RLSIM_CHUNK_BYTES", "7001")
+        else:
+            monkeypatch.delenv("RLSIM_CHUNK_BYTES", raising=False)
+        h = make()
+        sp, got = h.species(), h.sampled()
+        for k in ("tr", "start", "end", "count0", "count"):
+            assert np.array_equal(ref_sp[k], sp[k]), (name, k)
+        for k in ("tr", "start", "end", "minus", "id"):
+            assert np.array_equal(ref[k], got[k]), (name, k)
+        assert h.fasta(names) == ascii_h.fasta(names), name
+        assert int(h.stats().flags) & gpu.F_EAGER, name
+    monkeypatch.delenv("RLSIM_CHUNK_BYTES", raising=False)
+    # no mask at all: a clean set
+    clean = [bytes(x).replace(b"N", b"A") for x in seqs]
+    cb = np.frombuffer(b"".join(clean), dtype=np.uint8)
+    o0 = off - lead
+    cc, cm = gpu.pack_bases(cb)
+    assert cm is None
+    a = run(lambda h, o, l, n: h.add_transcripts_raw(cb, o0, l, n))
+    b = run(lambda h, o, l, n: h.add_transcripts_packed(cc, None, o0, l, n))
+    for k in ("tr", "start", "end", "minus", "id"):
+        assert np.array_equal(a.sampled()[k], b.sampled()[k]), k
+    assert a.fasta(names) == b.fasta(names)
+    # and the oracle on the N-carrying set
+    o = util.run_oracle(oracle, args, names, seqs, levels, oracle.MODE_PHILOX)
+    fo = o.sampled()
+    for k in ("tr", "start", "end", "minus", "id"):
+        assert np.array_equal(fo[k], ref[k]), k
+
+
 # ---- fused prefix + fragmentation kernel (prefix sums in shared memory) --------------------------------------------
 def test_fused_path_variants(oracle, gpu, monkeypatch):
     """after_prim / after_prim_double keep the priming prefix sums in shared memory: one warp per transcript with a compact

@@ -366,3 +366,21 @@ def test_bench_own_arm_fails_loudly_without_gpu():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0", "--scale", "0.01"],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
     assert p.returncode != 0 and b"no CPU fallback" in p.stderr and p.stdout.strip() == b""
+
+
+def test_pack_bases_layout():
+    """The packed host format of rlsim_add_transcripts_packed (include/rlsim_gpu.h): 2 bits per base, low bits first; the
+    mask marks every letter outside ACGT and is None for a clean sequence."""
+    from rlsim_b200 import _native
+    rng = np.random.default_rng(3)
+    b = rng.choice(np.frombuffer(b"ACGTNRY", dtype=np.uint8), size=1003)
+    codes, nmask = _native.pack_bases(b)
+    assert codes.dtype == np.uint8 and len(codes) == 251 and len(nmask) == 126
+    i = np.arange(len(b))
+    c = (codes[i >> 2] >> (2 * (i & 3))) & 3
+    m = (nmask[i >> 3] >> (i & 7)) & 1
+    clean = np.isin(b, np.frombuffer(b"ACGT", dtype=np.uint8))
+    assert np.array_equal(m.astype(bool), ~clean)
+    assert np.array_equal(np.frombuffer(b"ACGT", dtype=np.uint8)[c][clean], b[clean]) and not c[~clean].any()
+    assert _native.pack_bases(np.frombuffer(b"ACGTTGCA", dtype=np.uint8))[1] is None
+    assert _native.pack_bases(np.frombuffer(b"CA", dtype=np.uint8))[0].tolist() == [1]
