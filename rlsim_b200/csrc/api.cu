@@ -140,6 +140,7 @@ int raw_target_finish(rlsim_handle *h) {  // raw_target.go:54,59-90
 int grow_prefix(rlsim_handle *h, uint64_t tot, uint32_t n, uint64_t old_tot, uint32_t old_n) {
     CK(h, h->d_Rf.grow_preserve(tot / 64 + 2ull * n + 8, old_n ? old_tot / 64 + 2ull * old_n + 2 : 0, h->st));
     CK(h, h->d_Ff.grow_preserve(tot + 64, old_tot, h->st));
+    CK(h, h->d_pfx_long.ensure(2ull * n + 2));  // k_prefix's list of long transcripts, per strand
     CK(h, h->d_Cf.grow_preserve(tot / 32 + 2ull * n + 8, old_n ? old_tot / 32 + 2ull * old_n + 2 : 0, h->st));
     if (needs_rev(h->p.frag_method)) {
         CK(h, h->d_Fr.grow_preserve(tot + 64, old_tot, h->st));
@@ -162,14 +163,18 @@ int ensure_lut(rlsim_handle *h) {
     }
     return 0;
 }
-int launch_prefix_range(rlsim_handle *h, uint32_t t0, uint32_t t1) {
+int launch_prefix_range(rlsim_handle *h, uint32_t t0, uint32_t t1, cudaStream_t st = nullptr) {
     int method = h->p.frag_method;
-    int rcl = ensure_lut(h);
+    int rcl = ensure_lut(h);  // (on h->st; a caller with its own stream has made it wait for that)
     if (rcl) return rcl;
     const DevTranscripts trp = make_tr(h);
-    launch_prefix(h->st, trp, t0, t1, h->p.kmer_len, h->p.priming_temp, h->d_wq_f.p, h->d_wq_r.p, h->d_kmax.p,
-                  h->d_Ff.p, h->d_Fr.p, h->d_Cf.p, h->d_Cr.p, const_cast<Rec32 *>(trp.Rf), needs_rev(method) ? 2 : 1, h->d_work.p);
-    h->launches[RLSIM_T_PREFIX] += 1;
+    launch_prefix(st ? st : h->st, trp, t0, t1, h->p.kmer_len, h->p.priming_temp, h->d_wq_f.p, h->d_wq_r.p, h->d_kmax.p,
+                  h->d_Ff.p, h->d_Fr.p, h->d_Cf.p, h->d_Cr.p, const_cast<Rec32 *>(trp.Rf), needs_rev(method) ? 2 : 1, h->d_work.p + 8,
+                  // opt-in (RLSIM_PREFIX_LONG=1): long transcripts summed by whole CTAs (k_prefix_long).  Measured without
+                  // effect on the chunk pipeline (the one-warp tail of a launch overlaps the other streams' kernels) and
+                  // 0.06 ms slower over a whole transcriptome, where enough warps are in flight to hide it.
+                  getenv("RLSIM_PREFIX_LONG") ? h->d_pfx_long.p : nullptr, (uint32_t)(h->d_pfx_long.n / 2));
+    h->launches[RLSIM_T_PREFIX] += 2;
     return 0;
 }
 
@@ -216,6 +221,7 @@ void eager_reset(rlsim_handle *h) {
     h->fused_used = false;
     h->eager_upto = 0; h->eager_failed = h->eager_started = h->eager_pcr = false; h->eager_keys = h->eager_sp = 0;
     h->eager_groups = 0;
+    h->ecs_used = 0; h->eager_sp_ub = 0; h->eager_async = false;
 }
 
 double frag_denominator(rlsim_handle *h) {  // expected fragments per molecule <= L / denominator + 1
@@ -530,6 +536,194 @@ int eager_chunk(rlsim_handle *h, uint32_t t0, uint32_t t1, bool timed = false) {
     return 0;
 }
 
+// ---- asynchronous form of the chunk pipeline ------------------------------------------------------------------------
+// eager_chunk above reads three counts back per group (queued intervals, fragment keys, species) and the GPU idles while
+// the host turns each of them into the next launch: measured, half of the time of a batch.  Here a chunk is split into a
+// FRONT half (fragmentation: k_fragment, k_intervals on h->st, fed by device-side counts) and a BACK half (dedup + PCR:
+// sort, run-length pass, species decode on h->st_back, k_pcr on h->st_pcr).  The only number the host needs is the
+// chunk's fragment count (cub takes its item count by value); it is copied to pinned memory behind the front half and
+// read one chunk later, after the next chunk's front half has been queued - so the GPU always has work while the host
+// waits.  Where the species of a chunk land in the species table is decided on the device (k_species_begin).
+// Fragment keys rotate through EAGER_BUFS buffers, so a slow sort (small, latency-bound) does not hold back the front half.  Any bound that proves too small raises a flag and the monolithic path
+// recomputes the library, as with eager_chunk.
+uint64_t eager_chunk_bound(rlsim_handle *h, double sum_expr_len, double sum_expr) {
+    return (uint64_t)((sum_expr_len / frag_denominator(h) + sum_expr) * 1.25) + 2048;
+}
+
+// Sizes the buffers of the front half for `n_chunks` more chunks (largest fragment bound: `largest`, most molecules in
+// one chunk: `max_mol`): nothing of it is reallocated while chunks are in flight.
+int eager_async_reserve(rlsim_handle *h, uint32_t n_chunks, uint64_t largest, uint64_t max_mol) {
+    // The short stages that gate the others run at high stream priority: their blocks are placed before the pending blocks
+    // of the long k_fragment / k_pcr grids (measured: the radix sort of a chunk - decoupled look-back between its blocks -
+    // took 0.5-0.9 ms beside those grids at equal priority, more than the whole chunk takes otherwise).
+    int prio_lo = 0, prio_hi = 0;
+    CK(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    if (getenv("RLSIM_NO_PRIORITY")) prio_hi = prio_lo;
+    if (!h->st_back) CK(h, cudaStreamCreateWithPriority(&h->st_back, cudaStreamNonBlocking, prio_hi));
+    if (!h->st_in) CK(h, cudaStreamCreateWithPriority(&h->st_in, cudaStreamNonBlocking, prio_hi));
+    while (h->ev_in.size() < n_chunks) { cudaEvent_t e; CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_in.push_back(e); }
+    const uint32_t slots = h->ecs_used + n_chunks;
+    if (slots > h->d_ecs.n) {  // the records move: everything that reads them must be done
+        CK(h, cudaStreamSynchronize(h->st_back));
+        CK(h, cudaStreamSynchronize(h->st_pcr));
+        h->pcr_in_flight = false;
+    }
+    if (!h->eager_started) {  // first chunk of this transcript set: histograms, counters
+        h->eager_started = true;
+        h->eager_async = true;
+        uint32_t hist_frag_n = (uint32_t)h->high + 1, hist_pa_n = h->polya_max + 1;
+        CK(h, h->d_hist_frag.ensure(hist_frag_n)); CK(h, h->d_hist_polya.ensure(hist_pa_n));
+        CK(h, h->d_eglobal.ensure(1));
+        CK(h, cudaMemsetAsync(h->d_hist_frag.p, 0, (size_t)hist_frag_n * 8, h->st));
+        CK(h, cudaMemsetAsync(h->d_hist_polya.p, 0, (size_t)hist_pa_n * 8, h->st));
+        CK(h, cudaMemsetAsync(h->d_counters.p, 0, 4 * 8, h->st));
+        CK(h, cudaMemsetAsync(h->d_eglobal.p, 0, sizeof(rl::EagerGlobal), h->st));
+        CK(h, cudaMemsetAsync(h->d_error.p, 0, 4, h->st));
+    }
+    CK(h, h->d_ecs.grow_preserve(slots, h->ecs_used, h->st));
+    CK(h, cudaMemsetAsync(h->d_ecs.p + h->ecs_used, 0, (size_t)n_chunks * sizeof(rl::EagerChunk), h->st));
+    h->ecs_pin.resize(slots);
+    while (h->ev_cnt.size() < slots) {
+        cudaEvent_t e1, e2;
+        CK(h, cudaEventCreateWithFlags(&e1, cudaEventDisableTiming)); h->ev_cnt.push_back(e1);
+        CK(h, cudaEventCreateWithFlags(&e2, cudaEventDisableTiming)); h->ev_sorted.push_back(e2);
+    }
+    if (largest > h->d_ekeys[0].n) CK(h, cudaStreamSynchronize(h->st_back));  // a sort may still read them
+    for (uint32_t i = 0; i < EAGER_BUFS; i++) CK(h, h->d_ekeys[i].ensure(largest));
+    CK(h, h->d_q_a.ensure(largest)); CK(h, h->d_q_b.ensure(largest));
+    const uint32_t long_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(max_mol / 16, 4096), 1u << 24);
+    for (uint32_t i = 0; i < EAGER_BUFS; i++) { CK(h, h->d_elong_list[i].ensure(long_cap)); CK(h, h->d_elong_hi[i].ensure(long_cap)); }
+    CK(h, h->d_warp_t.ensure(max_mol / 32 + 2));
+    return ensure_len_eff(h);
+}
+
+// Front half of the transcripts [t0, t1) (ingest + prefix sums already queued on h->st).  Returns the chunk's slot, or -1.
+int eager_front(rlsim_handle *h, uint32_t t0, uint32_t t1, uint64_t bound, int *slot_out) {
+    int rc;
+    *slot_out = -1;
+    const uint64_t g0 = h->h_mol_off[t0], g1 = h->h_mol_off[t1];
+    const char *fail_at = getenv("RLSIM_EAGER_TEST_FAIL");  // test hook: pretend the bound of chunk number N was too small
+    const bool forced = fail_at && (uint32_t)atoi(fail_at) == h->eager_groups;
+    if (g1 == g0) { h->eager_upto = t1; return 0; }
+    h->eager_groups++;
+    if (forced || bound >= (1ull << 31) || bound > h->d_ekeys[0].n || h->ecs_used >= h->d_ecs.n) { h->eager_failed = true; return 0; }
+    const uint32_t slot = h->ecs_used++;
+    rl::EagerChunk *cs = h->d_ecs.p + slot;
+    uint64_t *keys = h->d_ekeys[slot % EAGER_BUFS].p;
+    if (slot >= EAGER_BUFS) CK(h, cudaStreamWaitEvent(h->st, h->ev_sorted[slot - EAGER_BUFS], 0));  // that chunk's sort has read this buffer
+    const uint32_t long_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((g1 - g0) / 16, 4096), h->d_elong_list[slot % EAGER_BUFS].n);
+    DevModel m = make_model(h);
+    DevTranscripts tr = make_tr(h);
+    tr.n = t1;  // the metadata of later transcripts reaches the device chunk by chunk: searches over off / mol_off stop here
+    const uint64_t q_cap = std::min<uint64_t>(bound, std::min(h->d_q_a.n, h->d_q_b.n));
+    // molecules with more breakpoints than a thread sorts locally are listed (per key buffer: the back half serves them)
+    FragBuffers fb{keys, bound, &cs->key_count, h->d_hist_frag.p, h->d_hist_polya.p, h->d_elong_list[slot % EAGER_BUFS].p, h->d_elong_hi[slot % EAGER_BUFS].p,
+                   long_cap, &cs->long_count, h->d_error.p, h->d_q_a.p, h->d_q_b.p, q_cap, &cs->q_count};
+    const bool tm = getenv("RLSIM_TRACE") && atoi(getenv("RLSIM_TRACE")) >= 2;
+    if (tm) h->mark("front start", (int)slot, h->st);
+    if ((rc = ensure_warp_table(h, tr, g0, g1))) return rc;
+    if ((rc = launch_fragment(h->st, m, tr, g0, g1, fb, h->d_warp_t.p))) { h->eager_failed = true; return 0; }
+    if (tm) h->mark("fragment end", (int)slot, h->st);
+    launch_intervals(h->st, m, tr, fb, q_cap, 1, &cs->q_count);
+    if (tm) h->mark("intervals end", (int)slot, h->st);
+    h->launches[RLSIM_T_FRAGMENT] += 1; h->launches[RLSIM_T_INTERVALS] += 1;
+    h->ecs_bound.resize(std::max<size_t>(h->ecs_bound.size(), slot + 1));  // host-side notes for the back half
+    h->ecs_bound[slot] = {bound, q_cap, long_cap, t1};
+    CK(h, cudaMemcpyAsync(&h->ecs_pin[slot], cs, sizeof(rl::EagerChunk), cudaMemcpyDeviceToHost, h->st));
+    CK(h, cudaEventRecord(h->ev_cnt[slot], h->st));
+    CK(h, cudaGetLastError());
+    h->eager_upto = t1;
+    *slot_out = (int)slot;
+    return 0;
+}
+
+// Back half of a chunk: sort + run-length encode its keys (transcript.go:156-215), place and decode its species, amplify.
+int eager_back(rlsim_handle *h, int slot) {
+    int rc;
+    if (slot < 0 || h->eager_failed) return 0;
+    CK(h, cudaEventSynchronize(h->ev_cnt[slot]));  // the one host wait per chunk; the next chunk's front half is queued behind it
+    rl::EagerChunk c = h->ecs_pin[slot];
+    const auto &b = h->ecs_bound[slot];
+    if (c.key_count > b.bound || c.q_count > b.q_cap || c.long_count > b.long_cap || c.key_count >= (1ull << 31)) { h->eager_failed = true; return 0; }
+    rl::EagerChunk *cs = h->d_ecs.p + slot;
+    CK(h, cudaStreamWaitEvent(h->st_back, h->ev_cnt[slot], 0));
+    if (c.long_count) {  // rare: deferred molecules add keys, so the count is read again
+        DevModel ml = make_model(h);
+        DevTranscripts trl = make_tr(h);
+        trl.n = b.t1;
+        FragBuffers fb{h->d_ekeys[slot % EAGER_BUFS].p, b.bound, &cs->key_count, h->d_hist_frag.p, h->d_hist_polya.p, h->d_elong_list[slot % EAGER_BUFS].p,
+                       h->d_elong_hi[slot % EAGER_BUFS].p, b.long_cap, &cs->long_count, h->d_error.p, h->d_q_a.p, h->d_q_b.p, b.q_cap, &cs->q_count};
+        launch_fragment_long(h->st_back, ml, trl, fb, c.long_count);
+        CK(h, cudaMemcpyAsync(&h->ecs_pin[slot], cs, sizeof(rl::EagerChunk), cudaMemcpyDeviceToHost, h->st_back));
+        CK(h, cudaStreamSynchronize(h->st_back));
+        c = h->ecs_pin[slot];
+        h->launches[RLSIM_T_FRAGMENT] += 1;
+        if (c.key_count > b.bound || c.key_count >= (1ull << 31)) { h->eager_failed = true; return 0; }
+    }
+    const uint64_t nf = c.key_count;
+    if (nf == 0) { CK(h, cudaEventRecord(h->ev_sorted[slot], h->st_back)); return 0; }
+    const uint64_t need = h->eager_sp_ub + nf;
+    if (ns_need(h, need) || need > h->d_sp_count0.n || nf > h->d_keys_sorted.n || nf > h->d_uniq.n || nf > h->d_rle_cnt.n) {
+        CK(h, cudaStreamSynchronize(h->st_back));   // the arrays move: whatever reads them must be done
+        CK(h, cudaStreamSynchronize(h->st_pcr));
+        const uint64_t used = h->eager_sp_ub;
+        CK(h, h->d_sp_count0.grow_preserve(need, used, h->st_back));
+        CK(h, h->d_sp_tr.grow_preserve(need, used, h->st_back)); CK(h, h->d_sp_start.grow_preserve(need, used, h->st_back));
+        CK(h, h->d_sp_len.grow_preserve(need, used, h->st_back)); CK(h, h->d_sp_count.grow_preserve(need, used, h->st_back));
+        CK(h, h->d_sp_eff.grow_preserve(need, used, h->st_back)); CK(h, h->d_sp_gc.grow_preserve(need, used, h->st_back));
+        CK(h, h->d_keys_sorted.ensure(nf)); CK(h, h->d_uniq.ensure(nf)); CK(h, h->d_rle_cnt.ensure(nf));
+    }
+    h->eager_sp_ub = need;
+    DevModel m = make_model(h);
+    DevTranscripts tr = make_tr(h);
+    tr.n = b.t1;
+    const uint64_t *keys = h->d_ekeys[slot % EAGER_BUFS].p;
+    const int end_bit = (int)std::min<uint32_t>(64, key_len_bits((uint32_t)h->high) + bits_for(h->h_off[b.t1]));
+    size_t tb = 0, tb2 = 0;
+    CK(h, cub::DeviceRadixSort::SortKeys(nullptr, tb, keys, h->d_keys_sorted.p, (int)nf, 0, end_bit, h->st_back));
+    CK(h, cub::DeviceRunLengthEncode::Encode(nullptr, tb2, h->d_keys_sorted.p, h->d_uniq.p, h->d_rle_cnt.p, &cs->runs, (int)nf, h->st_back));
+    if (std::max(tb, tb2) + 16 > h->d_cub.n) { CK(h, cudaStreamSynchronize(h->st_back)); if ((rc = cub_temp(h, std::max(tb, tb2) * 2))) return rc; }
+    tb = h->d_cub.n;
+    const bool tm = getenv("RLSIM_TRACE") && atoi(getenv("RLSIM_TRACE")) >= 2;
+    if (tm) h->mark("back start", slot, h->st_back);
+    CK(h, cub::DeviceRadixSort::SortKeys(h->d_cub.p, tb, keys, h->d_keys_sorted.p, (int)nf, 0, end_bit, h->st_back));
+    CK(h, cudaEventRecord(h->ev_sorted[slot], h->st_back));
+    if (tm) h->mark("sort end", slot, h->st_back);
+    tb = h->d_cub.n;
+    CK(h, cub::DeviceRunLengthEncode::Encode(h->d_cub.p, tb, h->d_keys_sorted.p, h->d_uniq.p, h->d_rle_cnt.p, &cs->runs, (int)nf, h->st_back));
+    launch_species_begin(h->st_back, cs, h->d_eglobal.p, h->d_uniq.p, b.bound, b.q_cap, b.long_cap, h->d_sp_tr.n);
+    DevSpecies sp{};
+    sp.n = nf;
+    sp.tr = h->d_sp_tr.p; sp.start = h->d_sp_start.p; sp.len = h->d_sp_len.p; sp.count0 = h->d_sp_count0.p; sp.count = h->d_sp_count.p;
+    sp.eff = h->keep_debug ? h->d_sp_eff.p : nullptr; sp.gc = h->keep_debug ? h->d_sp_gc.p : nullptr;
+    launch_decode_species_dyn(h->st_back, tr, h->d_uniq.p, h->d_rle_cnt.p, sp, (uint32_t)h->high, cs, nf);
+    if (tm) h->mark("back end", slot, h->st_back);
+    h->launches[RLSIM_T_DEDUP] += 4 + radix_launches(end_bit);
+    CK(h, cudaEventRecord(h->ev_sp, h->st_back));
+    CK(h, cudaStreamWaitEvent(h->st_pcr, h->ev_sp, 0));
+    if (tm) h->mark("pcr start", slot, h->st_pcr);
+    launch_pcr_dyn(h->st_pcr, m, tr, sp, h->d_error.p, cs, nf);  // thermocycler.go:106-147 for this chunk's species
+    if (tm) h->mark("pcr end", slot, h->st_pcr);
+    CK(h, cudaEventRecord(h->ev_pcr, h->st_pcr));
+    h->pcr_in_flight = true;
+    h->launches[RLSIM_T_PCR] += 1;
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+// End of a batch: totals and overflow flags (PCR of the last chunks may still be running; h->st waits for the back half).
+int eager_async_finish(rlsim_handle *h) {
+    if (!h->eager_async || !h->eager_started || !h->st_back) return 0;
+    CK(h, cudaMemcpyAsync(h->pin, h->d_eglobal.p, sizeof(rl::EagerGlobal), cudaMemcpyDeviceToHost, h->st_back));
+    CK(h, cudaStreamSynchronize(h->st_back));
+    const rl::EagerGlobal g = *reinterpret_cast<const rl::EagerGlobal *>(h->pin);
+    if (g.fail) { h->eager_failed = true; return 0; }
+    if (h->eager_failed) return 0;
+    h->eager_keys = g.frag_total;
+    h->eager_sp = g.sp_cursor;
+    return 0;
+}
+
 // everything that needs the complete transcript set: molecule offsets, remaining prefix sums
 int finalize(rlsim_handle *h, bool with_prefix = true) {
     uint32_t n = (uint32_t)h->h_len.size();
@@ -590,7 +784,7 @@ int rlsim_create(int device, rlsim_handle **out) {
         (e = cudaHostAlloc((void **)&h->pin, 64, cudaHostAllocDefault)) != cudaSuccess ||
         (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
         (e = h->d_error.ensure(1)) != cudaSuccess || (e = h->d_counters.ensure(4)) != cudaSuccess ||
-        (e = h->d_long_count.ensure(1)) != cudaSuccess || (e = h->d_work.ensure(8)) != cudaSuccess || (e = h->d_kmax.ensure(1)) != cudaSuccess) {
+        (e = h->d_long_count.ensure(1)) != cudaSuccess || (e = h->d_work.ensure(16)) != cudaSuccess || (e = h->d_kmax.ensure(1)) != cudaSuccess) {
         g_create_error = std::string("rlsim_create: ") + cudaGetErrorString(e);
         delete h;
         return RLSIM_E_CUDA;
@@ -610,6 +804,11 @@ void rlsim_destroy(rlsim_handle *h) {
     for (auto e : h->ev_free) cudaEventDestroy(e);
     if (h->st_copy) cudaStreamDestroy(h->st_copy);
     if (h->st_pcr) cudaStreamDestroy(h->st_pcr);
+    if (h->st_back) cudaStreamDestroy(h->st_back);
+    if (h->st_in) cudaStreamDestroy(h->st_in);
+    for (auto e : h->ev_in) cudaEventDestroy(e);
+    for (auto e : h->ev_cnt) cudaEventDestroy(e);
+    for (auto e : h->ev_sorted) cudaEventDestroy(e);
     if (h->st_aux) cudaStreamDestroy(h->st_aux);
     if (h->ev_aux) cudaEventDestroy(h->ev_aux);
     if (h->ev_sp) cudaEventDestroy(h->ev_sp);
@@ -848,7 +1047,9 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     const uint8_t *src = dev_bases ? dev_bases + o0 : h->staging.bases.p;
     // ---- pipeline: H2D of chunk c+1 on the copy stream overlaps ingest (+ prefix sums) of chunk c
     const uint64_t chunk_bytes = getenv("RLSIM_CHUNK_BYTES") ? std::max(1ll, atoll(getenv("RLSIM_CHUNK_BYTES")))  // test knob
-                               : (uint64_t)(getenv("RLSIM_CHUNK_MB") ? std::max(1, atoi(getenv("RLSIM_CHUNK_MB"))) : 32) << 20;
+                               : (uint64_t)(getenv("RLSIM_CHUNK_MB") ? std::max(1, atoi(getenv("RLSIM_CHUNK_MB"))) : (packed ? 128 : 32)) << 20;
+    // (bases per chunk.  A packed batch crosses the link in 3/8 of the time, so its pipeline is bound by the kernels, which
+    // run more efficiently over larger chunks: measured 7.6 / 6.9 / 6.6 ms per C3 batch at 32 / 64 / 128 M bases per chunk)
     // The last chunks taper (1/2, 1/4, 1/8, 1/8 of a chunk): what remains to be computed after the last byte has arrived is
     // the work of the last group, so it should be small.
     std::vector<uint32_t> cuts{0};
@@ -945,9 +1146,10 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
         h->total_padded = off[t1];
         return 0;
     };
+    bool async_meta = false;  // asynchronous pipeline: the metadata follow the ingest stream
     auto meta_to_device = [&](uint32_t t0, uint32_t t1) {
         const uint32_t m = t1 - t0;
-        k_copy_meta<<<(m + 1 + 255) / 256, 256, 0, h->st>>>(h->h_off.data() + n0 + t0, h->h_len.data() + n0 + t0, h->h_expr.data() + n0 + t0,
+        k_copy_meta<<<(m + 1 + 255) / 256, 256, 0, async_meta ? h->st_in : h->st>>>(h->h_off.data() + n0 + t0, h->h_len.data() + n0 + t0, h->h_expr.data() + n0 + t0,
                                                          h->h_mol_off.data() + n0 + t0, rel.data() + t0, h->d_off.p + n0 + t0, h->d_len.p + n0 + t0,
                                                          h->d_expr.p + n0 + t0, h->d_mol_off.p + n0 + t0, h->staging.off.p + t0, m);
     };
@@ -971,6 +1173,33 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     // the per-group fixed cost (host round trips for counts, small sorts) never makes compute fall behind the copies.
     // The grouping does not influence the result (streams are addressed by global molecule / species identity).
     bool eager = want_eager;
+    // asynchronous form (default): no host round trip inside the batch; RLSIM_EAGER_SYNC=1 keeps the grouped form above
+    const bool async = want_eager && lazy_meta && !getenv("RLSIM_EAGER_SYNC") && (h->eager_async || !h->eager_started);
+    std::vector<uint64_t> bound;
+    int pending_slot = -1;
+    if (async) {  // the chunks' fragment bounds from one pass over lengths and expression levels
+        bound.resize(n_chunks);
+        uint64_t largest = 1, max_mol = 0;
+        for (uint32_t c = 0; c < n_chunks; c++) {
+            double se = 0, sel = 0;
+            uint64_t mol = 0;
+            for (uint32_t i = cuts[c]; i < cuts[c + 1]; i++) {
+                se += (double)expr[i];
+                sel += (double)expr[i] * (double)(offsets[i + 1] - offsets[i] + pa);
+                mol += expr[i];
+            }
+            bound[c] = mol ? eager_chunk_bound(h, sel, se) : 0;
+            largest = std::max(largest, bound[c]); max_mol = std::max(max_mol, mol);
+        }
+        int rc = eager_async_reserve(h, n_chunks, largest, max_mol);
+        if (rc) return rc;
+        // ingest + prefix sums of a chunk run on their own stream, beside the fragmentation of the chunk before
+        if (want_prefix && (rc = ensure_lut(h))) return rc;
+        CK(h, cudaEventRecord(h->ev_aux, h->st));
+        CK(h, cudaStreamWaitEvent(h->st_in, h->ev_aux, 0));
+    }
+    cudaStream_t sa = async ? h->st_in : h->st;
+    async_meta = async;
     const double t_begin = now_ms();
     if (trace) fprintf(stderr, "[rlsim trace] host prologue %.3f ms (%u chunks)\n", t_begin - t_entry, n_chunks);
     for (uint32_t c = 0; c < n_chunks;) {
@@ -981,7 +1210,7 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
         }
         wait_issued(c);
         if (feeder_err.load()) break;
-        if (eager) {
+        if (eager && !async) {
             CK(h, cudaEventSynchronize(h->ev_chunk[c]));
             while (c_end < n_chunks && issued.load(std::memory_order_acquire) > c_end && cudaEventQuery(h->ev_chunk[c_end]) == cudaSuccess) {
                 if (lazy_meta) {
@@ -994,19 +1223,34 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
         }
         for (uint32_t cc = c; cc < c_end; cc++) {
             const uint32_t t0 = cuts[cc], t1 = cuts[cc + 1];
-            CK(h, cudaStreamWaitEvent(h->st, h->ev_chunk[cc], 0));
+            CK(h, cudaStreamWaitEvent(sa, h->ev_chunk[cc], 0));
+            const bool tm = async && trace && atoi(getenv("RLSIM_TRACE")) >= 2;
+            if (tm) h->mark("arrived", (int)cc, sa);
             if (packed)
-                launch_ingest_packed(h->st, reinterpret_cast<const uint32_t *>(h->staging.bases.p),
+                launch_ingest_packed(sa, reinterpret_cast<const uint32_t *>(h->staging.bases.p),
                                      pk_mask ? reinterpret_cast<const uint32_t *>(h->staging.bases.p + pk_m0) : nullptr, (uint32_t)(o0 & 3), (uint32_t)(o0 & 7),
                                      h->staging.off.p + t0, t1 - t0, n0 + t0, (h->h_off[n0 + t1] - h->h_off[n0 + t0]) >> 5, h->polya_max,
                                      h->d_off.p + n0 + t0, h->d_bases.p, h->d_packed.p, h->d_nmask.p, h->d_gc.p, h->d_dirty.p);
             else
-                launch_ingest(h->st, src, h->staging.off.p + t0, t1 - t0, n0 + t0, (h->h_off[n0 + t1] - h->h_off[n0 + t0]) >> 5,
+                launch_ingest(sa, src, h->staging.off.p + t0, t1 - t0, n0 + t0, (h->h_off[n0 + t1] - h->h_off[n0 + t0]) >> 5,
                               h->polya_max, h->d_off.p + n0 + t0, h->d_bases.p, h->d_packed.p, h->d_nmask.p, h->d_gc.p, h->d_dirty.p);
             h->launches[RLSIM_T_LAYOUT] += 3;
-            if (want_prefix) { int rc = launch_prefix_range(h, n0 + t0, n0 + t1); if (rc) return rc; }
+            if (tm) h->mark("ingest end", (int)cc, sa);
+            if (want_prefix) { int rc = launch_prefix_range(h, n0 + t0, n0 + t1, sa); if (rc) return rc; }
+            if (tm) h->mark("prefix end", (int)cc, sa);
         }
-        if (eager) {
+        if (async) {  // the fragmentation of this chunk (h->st) follows its ingest + prefix sums (h->st_in)
+            CK(h, cudaEventRecord(h->ev_in[c], h->st_in));
+            CK(h, cudaStreamWaitEvent(h->st, h->ev_in[c], 0));
+        }
+        if (eager && async) {
+            int slot = -1, rc = eager_front(h, n0 + cuts[c], n0 + cuts[c_end], bound[c], &slot);
+            if (rc) return rc;
+            if ((rc = eager_back(h, pending_slot))) return rc;  // the chunk before: its count has had a whole front half to arrive
+            pending_slot = slot;
+            eager = !h->eager_failed;
+            if (trace) fprintf(stderr, "[rlsim trace] chunk %u front queued at %.3f ms\n", c, now_ms() - t_begin);
+        } else if (eager) {
             if (trace) { const double t_l = now_ms(); cudaStreamSynchronize(h->st); fprintf(stderr, "[rlsim trace]   prev pcr + ingest + prefix %.3f ms\n", now_ms() - t_l); }
             const double t_a = now_ms();
             int rc = eager_chunk(h, n0 + cuts[c], n0 + cuts[c_end]);
@@ -1019,6 +1263,25 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     if (feeder.joinable()) feeder.join();
     if (feeder_err.load()) { h->err = std::string("staged host-to-device copy: ") + cudaGetErrorString((cudaError_t)feeder_err.load()); return RLSIM_E_CUDA; }
     h->n_mol = h->h_mol_off[nn];
+    if (async) {
+        CK(h, cudaEventRecord(h->ev_aux, h->st_in));  // chunks past a failed bound were only ingested: h->st follows them too
+        CK(h, cudaStreamWaitEvent(h->st, h->ev_aux, 0));
+        int rc = eager_back(h, pending_slot);
+        if (rc) return rc;
+        if ((rc = eager_async_finish(h))) return rc;
+        if (trace) fprintf(stderr, "[rlsim trace] last chunk deduplicated %.3f ms\n", now_ms() - t_begin);
+        if (!h->trace_marks.empty()) {  // RLSIM_TRACE=2: the device's own timeline, relative to the first mark
+            cudaStreamSynchronize(h->st_pcr); cudaStreamSynchronize(h->st_in); cudaStreamSynchronize(h->st);
+            for (auto &mk : h->trace_marks) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, h->trace_marks[0].ev, mk.ev);
+                fprintf(stderr, "[rlsim timeline] %8.3f ms  chunk %2d  %s\n", ms, mk.chunk, mk.what);
+                if (&mk != &h->trace_marks[0]) cudaEventDestroy(mk.ev);
+            }
+            cudaEventDestroy(h->trace_marks[0].ev);
+            h->trace_marks.clear();
+        }
+    }
     CK(h, cudaEventRecord(h->ev_ingest, h->st));  // behind the last k_copy_meta (see below)
     {   // zero words behind the last transcript (k_prefix reads whole words past a transcript's end)
         const uint64_t tot = h->total_padded;

@@ -220,6 +220,28 @@ struct rlsim_handle {
     uint32_t eager_groups = 0;              // groups started since the last reset (test hook)
     bool staged_pageable = false;           // the last add call staged a pageable caller buffer through pinned memory
     uint64_t eager_keys = 0, eager_sp = 0;  // running fragment-key / species counts
+    // asynchronous form of the pipeline (default): per-chunk counts stay on the device, the host never waits inside a batch
+    DBuf<rl::EagerChunk> d_ecs;             // one per chunk handed to the pipeline since the last reset
+    DBuf<rl::EagerGlobal> d_eglobal;        // species cursor, fragment total, overflow flags
+    DBuf<uint32_t> d_rle_cnt;               // run lengths of the chunk being deduplicated
+    uint32_t ecs_used = 0;                  // chunks handed out
+    uint64_t eager_sp_ub = 0;               // upper bound of the species placed so far (sum of the chunks' fragment counts)
+    bool eager_async = false;               // this transcript set runs through the asynchronous form
+    cudaStream_t st_back = nullptr;         // back half of a chunk (sort, run-length pass, species decode)
+    cudaStream_t st_in = nullptr;           // ingest + prefix sums of a chunk, beside the fragmentation of the chunk before
+    std::vector<cudaEvent_t> ev_in;         // per chunk of a batch: ingest + prefix sums queued
+    std::vector<cudaEvent_t> ev_cnt, ev_sorted;  // per chunk: front half done (counts on their way) / key buffer read
+    PinVec<rl::EagerChunk> ecs_pin;         // landing zone of the chunks' records
+    struct ChunkBound { uint64_t bound, q_cap; uint32_t long_cap, t1; };
+    std::vector<ChunkBound> ecs_bound;
+    DBuf<uint64_t> d_ekeys[rl::EAGER_BUFS];     // fragment keys of the chunks between their front half and the end of their sort
+    struct TraceMark { const char *what; int chunk; cudaEvent_t ev; };
+    std::vector<TraceMark> trace_marks;     // RLSIM_TRACE=2: device-side timeline of the chunk pipeline (timing events)
+    void mark(const char *what, int chunk, cudaStream_t s) {
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); trace_marks.push_back({what, chunk, e});
+    }
+    DBuf<uint2> d_elong_list[rl::EAGER_BUFS];   // deferred (long) molecules of those chunks
+    DBuf<uint32_t> d_elong_hi[rl::EAGER_BUFS];
     bool len_eff_ready = false;
     DBuf<uint8_t> d_bases;
     DBuf<uint32_t> d_packed, d_nmask, d_len;
@@ -264,7 +286,8 @@ struct rlsim_handle {
     DBuf<uint2> d_long_list, d_q_b;
     DBuf<uint4> d_q_a;
     DBuf<uint32_t> d_long_hi;
-    DBuf<unsigned int> d_long_count, d_work;
+    DBuf<unsigned int> d_long_count, d_work;  // d_work: [0..7] fused-path counters and flags, [8..11] k_prefix work counters
+    DBuf<uint32_t> d_pfx_long;               // transcripts k_prefix leaves to k_prefix_long (2 strands)
     DBuf<int> d_error;
     DBuf<unsigned char> d_cub;
     uint64_t n_frag = 0;

@@ -494,8 +494,13 @@ constexpr int IV_THREADS = 256;
 // (all transcripts when there are no records, else only those with letters outside ACGT).
 template <int REC>
 __global__ void __launch_bounds__(IV_THREADS, 5)
-k_intervals(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, uint64_t n_q, uint32_t hist_s_n) {
+k_intervals(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, uint64_t n_q, uint32_t hist_s_n,
+            const unsigned long long *__restrict__ n_q_dev) {
     extern __shared__ unsigned int hist_s[];
+    if (n_q_dev) {  // asynchronous chunk pipeline: the queue length never visited the host
+        n_q = min((uint64_t)*n_q_dev, o.q_cap);
+        if ((uint64_t)blockIdx.x * IV_THREADS >= n_q) return;
+    }
     for (uint32_t i = threadIdx.x; i < hist_s_n; i += IV_THREADS) hist_s[i] = 0;
     uint32_t *lut_s = hist_s + hist_s_n;
     if (REC) for (uint32_t i = threadIdx.x; i < (1u << (2 * m.k)); i += IV_THREADS) lut_s[i] = tr.lut[i];
@@ -517,11 +522,13 @@ k_intervals(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, ui
 // One CTA per deferred molecule: breakpoints drawn in parallel, bitonic-sorted in shared memory, intervals in parallel.
 constexpr int LONG_THREADS = 256;
 __global__ void __launch_bounds__(LONG_THREADS)
-k_fragment_long(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, uint32_t n_long, uint32_t smem_cap) {
+k_fragment_long(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o, uint32_t n_long, uint32_t smem_cap,
+                const unsigned int *__restrict__ n_long_dev) {
     extern __shared__ uint32_t brs[];  // smem_cap entries (power of two)
     __shared__ Header hs;
-    uint32_t slot = blockIdx.x;
-    if (slot >= n_long) return;
+    if (n_long_dev) n_long = min(*n_long_dev, n_long);  // asynchronous chunk pipeline: the count never visited the host
+  for (uint32_t slot = blockIdx.x; slot < n_long; slot += gridDim.x) {
+    __syncthreads();  // the previous molecule of this CTA is done with hs / brs
     uint32_t t = o.long_list[slot].x;
     uint64_t mol = (uint64_t)o.long_list[slot].y | ((uint64_t)o.long_hi[slot] << 32);
     MolCtx c = make_ctx(m, tr, t);
@@ -531,7 +538,7 @@ k_fragment_long(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o
     uint32_t n = (uint32_t)h.nb + 2;
     uint32_t npow = 1;
     while (npow < n) npow <<= 1;
-    if (npow > smem_cap) { if (threadIdx.x == 0) atomicExch(o.error, RLSIM_E_UNSUPPORTED); return; }
+    if (npow > smem_cap) { if (threadIdx.x == 0) atomicExch(o.error, RLSIM_E_UNSUPPORTED); continue; }
     uint32_t length = (uint32_t)h.polyAend;
     uint32_t first = m.method == RLSIM_PRE_PRIM ? h.elong : 0u;
     uint64_t span = (uint64_t)length - first;
@@ -566,6 +573,7 @@ k_fragment_long(const __grid_constant__ DevModel m, DevTranscripts tr, FragOut o
         else if (rec) after_interval(m, cr, iv, i, brs[i], brs[i + 1], o, nullptr, 0);
         else after_interval(m, c, iv, i, brs[i], brs[i + 1], o, nullptr, 0);
     }
+  }
 }
 
 
@@ -1040,7 +1048,8 @@ int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr
 }
 
 // n_q_dirty: queued intervals of transcripts that stay on the two-level arrays although records exist (q_count[1])
-int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint64_t n_q, uint64_t n_q_dirty) {
+int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint64_t n_q, uint64_t n_q_dirty,
+                     const unsigned long long *n_q_dev) {
     if (n_q == 0) return 0;
     FragOut o{fb.keys, fb.cap, key_len_bits(m.high), fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, fb.long_cap, fb.long_count,
               fb.error, fb.q_a, fb.q_b, fb.q_cap, fb.q_count};
@@ -1050,10 +1059,10 @@ int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &t
     const uint64_t max_blocks = 148ull * 5 * 6;
     if (tr.Rf != nullptr) {
         const size_t smem = (size_t)hist_s_n * 4 + ((size_t)4 << (2 * m.k));
-        k_intervals<1><<<(unsigned)std::min(blocks, max_blocks), IV_THREADS, smem, st>>>(m, tr, o, n_q, hist_s_n);
+        k_intervals<1><<<(unsigned)std::min(blocks, max_blocks), IV_THREADS, smem, st>>>(m, tr, o, n_q, hist_s_n, n_q_dev);
         if (n_q_dirty == 0) return 0;
     }
-    k_intervals<0><<<(unsigned)std::min(blocks, max_blocks), IV_THREADS, (size_t)hist_s_n * 4, st>>>(m, tr, o, n_q, hist_s_n);
+    k_intervals<0><<<(unsigned)std::min(blocks, max_blocks), IV_THREADS, (size_t)hist_s_n * 4, st>>>(m, tr, o, n_q, hist_s_n, n_q_dev);
     return 0;
 }
 
@@ -1152,13 +1161,15 @@ int launch_fused_long(cudaStream_t st, const DevModel &m, const DevTranscripts &
     return 0;
 }
 
-int launch_fragment_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t n_long) {
+int launch_fragment_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t n_long,
+                         const unsigned int *n_long_dev) {
     if (n_long == 0) return 0;
     FragOut o{fb.keys, fb.cap, key_len_bits(m.high), fb.count, fb.hist_frag, fb.hist_polya, fb.long_list, fb.long_hi, n_long, nullptr,
               fb.error, fb.q_a, fb.q_b, fb.q_cap, fb.q_count};
     const uint32_t smem_cap = 32768;  // breakpoints per molecule (128 KB of shared memory)
     cudaFuncSetAttribute(k_fragment_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_cap * 4));
-    k_fragment_long<<<n_long, LONG_THREADS, smem_cap * 4, st>>>(m, tr, o, n_long, smem_cap);
+    // device-side count: a fixed grid strides over however many molecules were deferred (normally none)
+    k_fragment_long<<<n_long_dev ? std::min(n_long, 296u) : n_long, LONG_THREADS, smem_cap * 4, st>>>(m, tr, o, n_long, smem_cap, n_long_dev);
     return 0;
 }
 

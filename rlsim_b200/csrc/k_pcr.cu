@@ -23,6 +23,41 @@ void launch_decode_species(cudaStream_t st, const DevTranscripts &tr, const uint
     if (sp.n) k_decode_species<<<(unsigned)((sp.n + 255) / 256), 256, 0, st>>>(tr, keys, sp, key_len_bits(high));
 }
 
+// ---- asynchronous chunk pipeline: a chunk's species land behind those of the chunks before it, without a host round trip
+// Runs after the run-length pass of a chunk (one thread): where the chunk's species go, and whether anything overflowed.
+__global__ void k_species_begin(EagerChunk *cs, EagerGlobal *g, const uint64_t *__restrict__ uniq, uint64_t key_cap, uint64_t q_cap,
+                                uint32_t long_cap, uint64_t sp_cap) {
+    unsigned long long n = cs->runs;
+    if (cs->key_count > key_cap || cs->q_count > q_cap || cs->long_count > long_cap) { g->fail |= 1ull; n = 0; }
+    if (g->sp_cursor + n > sp_cap) { g->fail |= 2ull; n = 0; }
+    cs->sp_base = g->sp_cursor;
+    cs->sp_n = n;
+    g->sp_cursor += n;
+    g->frag_total += cs->key_count;
+}
+void launch_species_begin(cudaStream_t st, EagerChunk *cs, EagerGlobal *g, const uint64_t *uniq, uint64_t key_cap, uint64_t q_cap,
+                          uint32_t long_cap, uint64_t sp_cap) {
+    k_species_begin<<<1, 1, 0, st>>>(cs, g, uniq, key_cap, q_cap, long_cap, sp_cap);
+}
+
+__global__ void k_decode_species_dyn(DevTranscripts tr, const uint64_t *__restrict__ uniq, const uint32_t *__restrict__ run_len, DevSpecies sp,
+                                     uint32_t len_bits, const EagerChunk *__restrict__ cs) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cs->sp_n) return;
+    const uint64_t j = cs->sp_base + i;
+    const uint64_t key = uniq[i];
+    const uint64_t gstart = key >> len_bits;
+    const uint32_t t = upper_bound_u64(tr.off, tr.n + 1, gstart) - 1;
+    sp.tr[j] = t;
+    sp.start[j] = (uint32_t)(gstart - tr.off[t]);
+    sp.len[j] = (uint32_t)(key & ((1ull << len_bits) - 1ull));
+    sp.count0[j] = run_len[i];
+}
+void launch_decode_species_dyn(cudaStream_t st, const DevTranscripts &tr, const uint64_t *uniq, const uint32_t *run_len, DevSpecies sp,
+                               uint32_t high, const EagerChunk *cs, uint64_t n_bound) {
+    if (n_bound) k_decode_species_dyn<<<(unsigned)((n_bound + 255) / 256), 256, 0, st>>>(tr, uniq, run_len, sp, key_len_bits(high), cs);
+}
+
 // CalcLenScalers + CalcLengthEff, thermocycler.go:83-92,149-156, with the library's restatement of Go's math.Pow
 __global__ void k_len_eff(const __grid_constant__ DevModel m, double *__restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,10 +223,18 @@ __device__ __forceinline__ uint64_t amplify(const PxStream &stream, uint64_t c, 
 }
 
 constexpr int PCR_THREADS = 128;
+template <bool DYN>
 __global__ void __launch_bounds__(PCR_THREADS, 9)
-k_pcr(const __grid_constant__ DevModel m, DevTranscripts tr, DevSpecies sp, int *error) {
+k_pcr(const __grid_constant__ DevModel m, DevTranscripts tr, DevSpecies sp, int *error, const EagerChunk *__restrict__ cs) {
     uint64_t i = (uint64_t)blockIdx.x * PCR_THREADS + threadIdx.x;
-    const bool live = i < sp.n;
+    uint64_t n = sp.n;
+    if (DYN) {  // asynchronous chunk pipeline: this launch covers the chunk's species, wherever they landed
+        n = cs->sp_n;
+        if ((uint64_t)blockIdx.x * PCR_THREADS >= n) return;
+        n += cs->sp_base;
+        i += cs->sp_base;
+    }
+    const bool live = i < n;
     uint32_t t = 0, start = 0, len = 1, gcc = 0;
     uint64_t c0 = 0;
     double e = m.fixed_eff;
@@ -215,7 +258,10 @@ k_pcr(const __grid_constant__ DevModel m, DevTranscripts tr, DevSpecies sp, int 
     if (sp.gc) sp.gc[i] = gcc;
 }
 void launch_pcr(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, DevSpecies sp, int *error) {
-    if (sp.n) k_pcr<<<(unsigned)((sp.n + PCR_THREADS - 1) / PCR_THREADS), PCR_THREADS, 0, st>>>(m, tr, sp, error);
+    if (sp.n) k_pcr<false><<<(unsigned)((sp.n + PCR_THREADS - 1) / PCR_THREADS), PCR_THREADS, 0, st>>>(m, tr, sp, error, nullptr);
+}
+void launch_pcr_dyn(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, DevSpecies sp, int *error, const EagerChunk *cs, uint64_t n_bound) {
+    if (n_bound) k_pcr<true><<<(unsigned)((n_bound + PCR_THREADS - 1) / PCR_THREADS), PCR_THREADS, 0, st>>>(m, tr, sp, error, cs);
 }
 
 // ---- probes (parity tests of the building blocks) ----

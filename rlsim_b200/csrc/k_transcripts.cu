@@ -286,6 +286,7 @@ void launch_kmer_lut(cudaStream_t st, int k, double T, double *K, unsigned long 
 
 // ---------------------------------------------------------------- priming prefix sums
 constexpr int PFX_THREADS = 256;                 // 8 independent warps per CTA
+constexpr uint32_t PFX_LONG = 8192;              // profile entries from which a transcript is summed by a whole CTA (k_prefix_long)
 constexpr int PFX_ROW_U32 = PFX_ITEMS + 4;       // padded row of one lane in the transpose tile (48 B: 16 B accesses stay conflict-free)
 constexpr int PFX_TILE_U32 = 32 * PFX_ROW_U32;
 
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(PFX_THREADS, 4)
 k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, const uint32_t *__restrict__ wq_f,
          const uint32_t *__restrict__ wq_r, const unsigned long long *__restrict__ kmax_bits, uint32_t *__restrict__ Ff,
          uint32_t *__restrict__ Fr, uint64_t *__restrict__ Cf, uint64_t *__restrict__ Cr, Rec32 *__restrict__ Rf, int lut_in_smem,
-         unsigned int *__restrict__ work) {
+         unsigned int *__restrict__ work, uint32_t *__restrict__ long_list, uint32_t long_cap) {
     extern __shared__ __align__(16) unsigned char pfx_smem[];
     uint32_t *tile_s = reinterpret_cast<uint32_t *>(pfx_smem);                 // 8 warps x PFX_TILE_U32
     uint32_t *lut_s = tile_s + (PFX_THREADS / 32) * PFX_TILE_U32;
@@ -353,6 +354,10 @@ k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, c
         if (L < (uint32_t)k + (tr.sym && !reverse ? 0u : 1u)) continue;
         // symmetric mode: the forward arrays also hold window len-k, the first window of the reverse profile
         const uint32_t proflen = L - (uint32_t)k + (tr.sym && !reverse ? 1u : 0u);
+        if (long_list != nullptr && proflen > PFX_LONG && !use_rec) {  // a whole CTA sums it (k_prefix_long): no one-warp tail
+            if (lane == 0) { const uint32_t slot = atomicAdd(&work[2 + reverse], 1u); if (slot < long_cap) long_list[(size_t)reverse * long_cap + slot] = t; }
+            continue;
+        }
         uint64_t carry = 0;  // sum of all weights before this sub-tile
         const PfxCtx pc{o, L, proflen, k, reverse, T, scale, lut, kmask, mmask};
 
@@ -426,17 +431,122 @@ k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, c
     }
 }
 
+// Long transcripts (more than PFX_LONG profile entries; k_prefix lists them): one CTA per transcript, its 8 warps sum 8
+// consecutive sub-tiles per step.  The in-block sums need nothing from outside their block; the coarse sums need the total
+// of everything before, which the warps exchange through shared memory once per step (double-buffered: one barrier).
+// A 30 000-base transcript is 15 steps here instead of 117 dependent iterations of one warp - which, chunk by chunk, was
+// the floor of every k_prefix launch of the chunk pipeline.
+__global__ void __launch_bounds__(PFX_THREADS, 4)
+k_prefix_long(DevTranscripts tr, int k, double T, const uint32_t *__restrict__ wq_f, const uint32_t *__restrict__ wq_r,
+              const unsigned long long *__restrict__ kmax_bits, uint32_t *__restrict__ Ff, uint32_t *__restrict__ Fr,
+              uint64_t *__restrict__ Cf, uint64_t *__restrict__ Cr, int lut_in_smem, const unsigned int *__restrict__ work,
+              const uint32_t *__restrict__ long_list, uint32_t long_cap) {
+    extern __shared__ __align__(16) unsigned char pfx_smem[];
+    __shared__ unsigned long long totals[2][PFX_THREADS / 32];
+    uint32_t *tile_s = reinterpret_cast<uint32_t *>(pfx_smem);
+    uint32_t *lut_s = tile_s + (PFX_THREADS / 32) * PFX_TILE_U32;
+    const int reverse = blockIdx.y;
+    const uint32_t n_long = min(work[2 + reverse], long_cap);
+    if (blockIdx.x >= n_long) return;
+    const uint32_t *lut = reverse ? wq_r : wq_f;
+    if (lut_in_smem) {
+        uint32_t n = 1u << (2 * k);
+        for (uint32_t i = threadIdx.x; i < n; i += PFX_THREADS) lut_s[i] = lut[i];
+        lut = lut_s;
+    }
+    __syncthreads();
+    const double scale = PFX_SCALE / __longlong_as_double((long long)*kmax_bits);
+    const uint32_t kmask = (1u << (2 * k)) - 1u;
+    const uint32_t mmask = (1u << k) - 1u;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *tile = tile_s + warp * PFX_TILE_U32;
+    int buf = 0;
+    for (uint32_t item = blockIdx.x; item < n_long; item += gridDim.x) {
+        const uint32_t t = long_list[(size_t)reverse * long_cap + item];
+        const uint32_t L = tr.len[t];
+        const uint64_t o = tr.off[t];
+        uint32_t *F = (reverse ? Fr : Ff) + o;
+        uint64_t *C = (reverse ? Cr : Cf) + coarse_base(o, t);
+        const uint32_t proflen = L - (uint32_t)k + (tr.sym && !reverse ? 1u : 0u);
+        const PfxCtx pc{o, L, proflen, k, reverse, T, scale, lut, kmask, mmask};
+        uint64_t carry = 0;  // sum of all weights before this step
+        for (uint32_t s0 = 0; s0 < proflen; s0 += (PFX_THREADS / 32) * PFX_SUB) {
+            const uint32_t i0 = s0 + warp * PFX_SUB;
+            const bool active = i0 < proflen;
+            uint32_t x[PFX_ITEMS];
+            uint32_t excl = 0, g0 = 0, g1 = 0, g2 = 0, g3 = 0;
+            if (active) {
+                const uint32_t ib = i0 + lane * PFX_ITEMS;
+                PfxWords w5{0, 0, 0, 0, 0};
+                if (ib < proflen) w5 = pfx_load(tr, o, pfx_jb(reverse, L, k, proflen, ib));
+                const uint32_t run = pfx_lane_sums(tr, pc, ib, w5, x);
+                uint32_t incl = run;
+#pragma unroll
+                for (int d = 1; d < 8; d <<= 1) {
+                    uint32_t v = __shfl_up_sync(0xffffffffu, incl, d, 8);
+                    if ((lane & 7) >= (uint32_t)d) incl += v;
+                }
+                excl = incl - run;
+                g0 = __shfl_sync(0xffffffffu, incl, 7); g1 = __shfl_sync(0xffffffffu, incl, 15);
+                g2 = __shfl_sync(0xffffffffu, incl, 23); g3 = __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) totals[buf][warp] = (unsigned long long)g0 + g1 + g2 + g3;
+            __syncthreads();
+            uint64_t before = carry, all = 0;
+#pragma unroll
+            for (int w = 0; w < PFX_THREADS / 32; w++) {
+                const uint64_t v = totals[buf][w];
+                if ((uint32_t)w < warp) before += v;
+                all += v;
+            }
+            carry += all;
+            buf ^= 1;
+            if (!active) continue;
+            if (lane < 4) {  // coarse[(i0 >> 6) + lane + 1] = sum of everything before block lane+1 of this sub-tile
+                uint64_t cs = before + g0;
+                if (lane >= 1) cs += g1;
+                if (lane >= 2) cs += g2;
+                if (lane >= 3) cs += g3;
+                if (i0 + lane * PFX_BLOCK < proflen) C[(i0 >> PFX_BLOCK_SHIFT) + lane + 1] = cs;
+            }
+            {
+                uint4 *row = reinterpret_cast<uint4 *>(tile + lane * PFX_ROW_U32);
+                row[0] = make_uint4(excl + x[0], excl + x[1], excl + x[2], excl + x[3]);
+                row[1] = make_uint4(excl + x[4], excl + x[5], excl + x[6], excl + x[7]);
+            }
+            __syncwarp();
+            const uint32_t nsub = min((uint32_t)PFX_SUB, proflen - i0);
+            uint32_t *dst = F + i0;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const uint32_t e = 4 * (q * 32 + lane);
+                const uint32_t *src = tile + (e >> 3) * PFX_ROW_U32 + (e & 7);
+                if (e + 3 < nsub) *reinterpret_cast<uint4 *>(dst + e) = *reinterpret_cast<const uint4 *>(src);
+                else for (uint32_t z = 0; z < 4 && e + z < nsub; z++) dst[e + z] = src[z];
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// work: 4 counters (next transcript per strand, listed long transcripts per strand); long_list: 2 x long_cap entries or null
 void launch_prefix(cudaStream_t st, const DevTranscripts &tr, uint32_t t_begin, uint32_t t_end, int k, double T,
                    const uint32_t *wq_f, const uint32_t *wq_r, const unsigned long long *kmax_bits, uint32_t *Ff, uint32_t *Fr,
-                   uint64_t *Cf, uint64_t *Cr, Rec32 *Rf, int strands, unsigned int *work) {
+                   uint64_t *Cf, uint64_t *Cr, Rec32 *Rf, int strands, unsigned int *work, uint32_t *long_list, uint32_t long_cap) {
     if (t_end <= t_begin) return;
     int lut_in_smem = (k <= 6);
     size_t smem = (size_t)(PFX_THREADS / 32) * PFX_TILE_U32 * 4 + (lut_in_smem ? ((size_t)4 << (2 * k)) : 16);
     uint32_t warps_needed = t_end - t_begin;
     uint32_t blocks = std::min<uint32_t>((warps_needed + 7) / 8, 148u * 6u);
-    cudaMemsetAsync(work, 0, 2 * sizeof(unsigned int), st);
+    cudaMemsetAsync(work, 0, 4 * sizeof(unsigned int), st);
     dim3 grid(blocks, strands);
-    k_prefix<<<grid, PFX_THREADS, smem, st>>>(tr, t_begin, t_end, k, T, wq_f, wq_r, kmax_bits, Ff, Fr, Cf, Cr, Rf, lut_in_smem, work);
+    if (Rf != nullptr) long_list = nullptr;  // record layout (opt-in): every transcript stays with its warp
+    k_prefix<<<grid, PFX_THREADS, smem, st>>>(tr, t_begin, t_end, k, T, wq_f, wq_r, kmax_bits, Ff, Fr, Cf, Cr, Rf, lut_in_smem, work,
+                                              long_list, long_cap);
+    if (long_list != nullptr) {
+        dim3 lgrid(std::min<uint32_t>(std::max<uint32_t>(long_cap, 1u), 148u * 4u), strands);
+        k_prefix_long<<<lgrid, PFX_THREADS, smem, st>>>(tr, k, T, wq_f, wq_r, kmax_bits, Ff, Fr, Cf, Cr, lut_in_smem, work, long_list, long_cap);
+    }
 }
 
 }  // namespace rl

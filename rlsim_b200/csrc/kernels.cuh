@@ -15,7 +15,7 @@ void launch_kmer_lut(cudaStream_t st, int k, double T, double *K, unsigned long 
                      uint32_t *wq_r, unsigned int *asym);
 void launch_prefix(cudaStream_t st, const DevTranscripts &tr, uint32_t t_begin, uint32_t t_end, int k, double T, const uint32_t *wq_f, const uint32_t *wq_r,
                    const unsigned long long *kmax_bits, uint32_t *Ff, uint32_t *Fr, uint64_t *Cf, uint64_t *Cr, Rec32 *Rf, int strands,
-                   unsigned int *work);
+                   unsigned int *work, uint32_t *long_list = nullptr, uint32_t long_cap = 0);
 void launch_probe_prefix(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint32_t t, int reverse, uint64_t *out, uint32_t n);
 
 // k_fragment.cu
@@ -30,8 +30,11 @@ struct FragBuffers {
 int launch_fragment(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint64_t g_begin, uint64_t g_end,
                     const FragBuffers &fb, const uint32_t *warp_t = nullptr);
 void launch_warp_transcripts(cudaStream_t st, const DevTranscripts &tr, uint64_t g_begin, uint64_t g_end, uint32_t *warp_t);
-int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint64_t n_q, uint64_t n_q_dirty);
-int launch_fragment_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t n_long);
+// n_q_dev / n_long_dev: the counts stay on the device (asynchronous chunk pipeline); n_q / n_long then only bound the grid
+int launch_intervals(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint64_t n_q, uint64_t n_q_dirty,
+                     const unsigned long long *n_q_dev = nullptr);
+int launch_fragment_long(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, const FragBuffers &fb, uint32_t n_long,
+                         const unsigned int *n_long_dev = nullptr);
 // fused prefix + fragmentation (after_prim / after_prim_double): prefix sums in shared memory
 struct FusedItem { uint32_t t0, t1; uint64_t g0, g1; };  // transcripts [t0, t1), global molecules [g0, g1)
 constexpr uint32_t FUSED_CAP_SMALL = 20480;   // prefix entries a CTA holds, two CTAs per SM
@@ -59,6 +62,22 @@ struct DevSpecies {
     uint32_t *gc;                 // optional (tests): GC count
 };
 void launch_decode_species(cudaStream_t st, const DevTranscripts &tr, const uint64_t *keys, DevSpecies sp, uint32_t high);
+// Asynchronous chunk pipeline (api.cu: eager_front / eager_back): only a chunk's fragment count visits the host.
+struct EagerChunk {            // one per chunk, device memory, zeroed before use
+    unsigned long long key_count;   // fragment keys written into the chunk's key buffer (may exceed its capacity: overflow)
+    unsigned long long runs;        // run count of the run-length pass = species of the chunk
+    unsigned long long q_count, q_dirty;  // interval work queue
+    unsigned long long sp_base, sp_n;     // the chunk's species: [sp_base, sp_base + sp_n) of the species table
+    unsigned int long_count, pad;
+};
+struct EagerGlobal { unsigned long long sp_cursor, frag_total, fail, pad; };
+constexpr uint32_t EAGER_BUFS = 4;        // key buffers the chunks rotate through
+void launch_species_begin(cudaStream_t st, EagerChunk *cs, EagerGlobal *g, const uint64_t *uniq, uint64_t key_cap, uint64_t q_cap,
+                          uint32_t long_cap, uint64_t sp_cap);
+// sp: whole-table base pointers; the chunk's rows are cs->sp_base ...; n_bound threads are launched
+void launch_decode_species_dyn(cudaStream_t st, const DevTranscripts &tr, const uint64_t *uniq, const uint32_t *run_len, DevSpecies sp,
+                               uint32_t high, const EagerChunk *cs, uint64_t n_bound);
+void launch_pcr_dyn(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, DevSpecies sp, int *error, const EagerChunk *cs, uint64_t n_bound);
 void launch_len_eff(cudaStream_t st, const DevModel &m, double *len_eff);
 void launch_pcr(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, DevSpecies sp, int *error);
 void launch_amplify_probe(cudaStream_t st, PxKey key, const uint32_t *tse, const uint64_t *n0, const double *p, int cycles,

@@ -161,11 +161,24 @@ def test_non_acgt_and_edge_transcripts(oracle, gpu):
     _compare(oracle, gpu, ["-n", "3000", "-f", "prim_jump:200"], seqs_override=(names, seqs, levels))
 
 
-def test_long_molecule_path(oracle, gpu):
-    """A 60 kb transcript with the default -d asks for ~150 breakpoints: exercises k_fragment_long."""
+@pytest.mark.parametrize("prefix_long", [False, True])
+def test_long_molecule_path(oracle, gpu, monkeypatch, prefix_long):
+    """A 60 kb transcript with the default -d asks for ~150 breakpoints: exercises k_fragment_long; with RLSIM_PREFIX_LONG
+    (opt-in) the prefix sums of such transcripts are built by whole CTAs (k_prefix_long) instead of one warp."""
+    if prefix_long:
+        monkeypatch.setenv("RLSIM_PREFIX_LONG", "1")
     names, seqs, levels = util.synth_transcriptome(6, seed=8, mean_len=60000, sigma=0.05, lo=50000, hi=70000, total_molecules=600)
-    _compare(oracle, gpu, ["-n", "20000", "-c", "5"], seqs_override=(names, seqs, levels))
+    o, h = _compare(oracle, gpu, ["-n", "20000", "-c", "5"], seqs_override=(names, seqs, levels))
+    assert int(h.stats().flags) & gpu.F_EAGER  # chunk pipeline: the deferred molecules are served in the chunk's back half
     _compare(oracle, gpu, ["-n", "2000", "-f", "pre_prim:20000", "-d", "1:n:(150,20,50,400)"], seqs_override=(names, seqs, levels))
+    # letters outside ACGT in long transcripts: their reverse profiles are explicit arrays, summed by whole CTAs as well
+    dirty = list(seqs)
+    for t in (1, 4):
+        s_ = bytearray(dirty[t])
+        s_[20000:20040] = b"N" * 40
+        s_[333] = ord("R")
+        dirty[t] = bytes(s_)
+    _compare(oracle, gpu, ["-n", "20000", "-c", "5", "-f", "after_prim"], seqs_override=(names, dirty, levels))
 
 
 def test_pool_exhaustion_and_complement(oracle, gpu):
@@ -326,6 +339,15 @@ def test_eager_chunk_pipeline_equals_monolithic(gpu, monkeypatch, flags):
     monkeypatch.setenv("RLSIM_CHUNK_BYTES", "30000")
     variants.append(run(first_builds=2))                                   # second build recomputes from resident data
     variants.append(run(batches=((0, 1), (1, 150), (150, 151), (151, 400))))  # eager across several add calls
+    # the grouped form of the pipeline (host round trips per group; what the asynchronous default replaced)
+    monkeypatch.setenv("RLSIM_EAGER_SYNC", "1")
+    variants.append(run())
+    variants.append(run(batches=((0, 150), (150, 400))))
+    monkeypatch.delenv("RLSIM_EAGER_SYNC")
+    # the asynchronous form without stream priorities
+    monkeypatch.setenv("RLSIM_NO_PRIORITY", "1")
+    variants.append(run())
+    monkeypatch.delenv("RLSIM_NO_PRIORITY")
     # a buffer estimate that turns out too small in the first group, or in a later one (two add calls make at least two
     # groups whatever the copy timing): the monolithic path takes over and recomputes from the resident transcripts
     for fail_at, batches in (("0", ((0, 400),)), ("1", ((0, 200), (200, 400)))):
