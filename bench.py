@@ -554,7 +554,8 @@ def main():
                    "cpu_binding_rank0": (sorted(cpus)[0], sorted(cpus)[-1], len(cpus)) if cpus else None,
                    "l2": "inputs (0.45 GB bases + %.1f GB prefix sums per GPU) exceed the 126 MB L2; no explicit flush" % ((1 if mirrored else 2) * 4.125 * nt_total / 1e9),
                    "reverse_profile": "mirrored forward sums" if mirrored else "explicit arrays",
-                   "e2e_path": ("eager chunk pipeline (fragment+dedup+PCR per arrived group of 32 MB chunks; %d groups in the last step)" % e2e_groups) if e2e_eager else "monolithic",
+                   "e2e_path": ("chunk pipeline: every 32 MB chunk is ingested, fragmented, deduplicated and amplified on four streams while later "
+                                "chunks are copied, one lagged host read per chunk (%d chunks in the last step)" % e2e_groups) if e2e_eager else "monolithic",
                    "species_per_gpu": weak_stats["n_species"], "fragments_after_fragmentation_per_gpu": weak_stats["n_fragments"],
                    "pool_total_rank0": weak_stats["pool_total"]},
         "e2e": {"value": n_e2e / t_e2e, "unit": "fragments/s", "h2d_bytes_per_step": int(weak.h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),

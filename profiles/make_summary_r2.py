@@ -137,7 +137,9 @@ out.append("Device-resident step %.2f ms = %.3g %s; end to end through the C-ABI
            "%.1f %s of %.0f (%s), frac %.4f, ncu traffic %s." % (
                d["ms_per_step"], d["value"], d["unit"], e.get("ms_per_step", float("nan")), e["value"], rf.get("kernel", "k_pcr"),
                rf["achieved"], rf["unit"], rf["peak"], rf.get("peak_source", ""), rf["frac"], rf.get("traffic")))
-for k in ("e2e_pageable", "e2e_text_in", "e2e_fasta", "e2e_dropin"):
+out.append("- copy ceiling of this box for the same bytes (pinned H2D + D2H, nothing else): %.2f ms; e2e = %.2f of it" % (
+    e.get("copy_ceiling_ms", float("nan")), e.get("copy_ceiling_ms", float("nan")) / e["ms_per_step"]))
+for k in ("e2e_pageable", "e2e_packed_in", "e2e_text_in", "e2e_fasta", "e2e_dropin"):
     if isinstance(d.get(k), dict) and "ms_per_step" in d[k]:
         out.append("- `%s`: %.2f ms per step" % (k, d[k]["ms_per_step"]))
 if os.path.exists(P("r2_final_bench_reference.json")):
