@@ -15,8 +15,12 @@ from rlsim_b200.pool import GpuPool  # noqa: E402
 n_tr = bench.C3_TRANSCRIPTS
 b, o, l = synth.transcriptome(n_tr, seed=bench.SEED, total_molecules=bench.C3_MOLECULES)
 print("cpus", os.cpu_count(), "affinity", len(os.sched_getaffinity(0)), file=sys.stderr)
-for threads in ("2", "4", "6", "8", "12", "16"):
+for threads, nt in (("4", 1), ("6", 1), ("8", 1), ("12", 1), ("4", 0), ("6", 0), ("8", 0), ("12", 0)):
     os.environ["RLSIM_STAGE_THREADS"] = threads
+    if nt:
+        os.environ.pop("RLSIM_NO_STREAM_COPY", None)
+    else:
+        os.environ["RLSIM_NO_STREAM_COPY"] = "1"
     pool = GpuPool(0, 0, 1, None)
     h = pool.handle
     ts = []
@@ -28,7 +32,7 @@ for threads in ("2", "4", "6", "8", "12", "16"):
         h.add_transcripts_raw(b, o, l, n_tr)
         ts.append(1000 * (time.perf_counter() - t0))
         h.build_library()
-    print("stage threads %2s: add %.2f ms (staged=%d)" % (threads, min(ts[1:]), bool(int(h.stats().flags) & _native.F_PAGEABLE_STAGED)), file=sys.stderr)
+    print("stage threads %2s, %s: add %.2f ms (staged=%d)" % (threads, "non-temporal stores" if nt else "memcpy", min(ts[1:]), bool(int(h.stats().flags) & _native.F_PAGEABLE_STAGED)), file=sys.stderr)
     h.close()
 # plain memcpy rate of one thread, for scale
 src = b

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librlsim_gpu.so")
-SOURCES = ["api.cu", "k_transcripts.cu", "k_fragment.cu", "k_pcr.cu", "k_select.cu", "k_fasta.cu", "k_fasta_in.cu", "comm.cu"]
+SOURCES = ["api.cu", "k_transcripts.cu", "k_fragment.cu", "k_pcr.cu", "k_select.cu", "k_fasta.cu", "k_fasta_in.cu", "comm.cu", "hostcopy.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared", "-ldl"]
 

@@ -98,6 +98,7 @@ struct Staging {  // reusable device staging of the batch being ingested (kept a
 // (a Go slice, a numpy array): DMA needs pinned pages, and the driver's own staging of a pageable cudaMemcpyAsync is
 // single-threaded and synchronous.  The library stages through a ring of pinned slots instead, filled (or drained) by this
 // team at several times the single-thread memcpy rate while the previous slot is on the wire.
+extern "C" void rl_stream_copy(void *dst, const void *src, size_t n);  // hostcopy.cpp: memcpy with non-temporal stores
 class CopyTeam {
 public:
     explicit CopyTeam(int threads) : T(std::max(1, threads)) {
@@ -110,7 +111,7 @@ public:
     }
     int size() const { return T; }
     void copy(void *dst_, const void *src_, size_t n_) {  // returns when all n bytes are in place
-        if (T == 1 || n_ < (256u << 10)) { memcpy(dst_, src_, n_); return; }
+        if (T == 1 || n_ < (256u << 10)) { rl_stream_copy(dst_, src_, n_); return; }
         { std::lock_guard<std::mutex> lk(m); dst = (uint8_t *)dst_; src = (const uint8_t *)src_; n = n_; pending = T - 1; gen++; }
         cv.notify_all();
         slice(0, (uint8_t *)dst_, (const uint8_t *)src_, n_);
@@ -120,7 +121,7 @@ public:
 private:
     void slice(int j, uint8_t *d, const uint8_t *s, size_t nn) const {
         size_t per = ((nn + T - 1) / T + 4095) & ~(size_t)4095, a = std::min(nn, per * j), b = std::min(nn, a + per);
-        if (b > a) memcpy(d + a, s + a, b - a);
+        if (b > a) rl_stream_copy(d + a, s + a, b - a);
     }
     void worker(int j) {
         uint64_t seen = 0;
