@@ -691,7 +691,7 @@ int eager_back(rlsim_handle *h, int slot) {
     if (tm) h->mark("sort end", slot, h->st_back);
     tb = h->d_cub.n;
     CK(h, cub::DeviceRunLengthEncode::Encode(h->d_cub.p, tb, h->d_keys_sorted.p, h->d_uniq.p, h->d_rle_cnt.p, &cs->runs, (int)nf, h->st_back));
-    launch_species_begin(h->st_back, cs, h->d_eglobal.p, h->d_uniq.p, b.bound, b.q_cap, b.long_cap, h->d_sp_tr.n);
+    launch_species_begin(h->st_back, cs, h->d_eglobal.p, b.bound, b.q_cap, b.long_cap, h->d_sp_tr.n);
     DevSpecies sp{};
     sp.n = nf;
     sp.tr = h->d_sp_tr.p; sp.start = h->d_sp_start.p; sp.len = h->d_sp_len.p; sp.count0 = h->d_sp_count0.p; sp.count = h->d_sp_count.p;

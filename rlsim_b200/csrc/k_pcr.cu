@@ -25,7 +25,7 @@ void launch_decode_species(cudaStream_t st, const DevTranscripts &tr, const uint
 
 // ---- asynchronous chunk pipeline: a chunk's species land behind those of the chunks before it, without a host round trip
 // Runs after the run-length pass of a chunk (one thread): where the chunk's species go, and whether anything overflowed.
-__global__ void k_species_begin(EagerChunk *cs, EagerGlobal *g, const uint64_t *__restrict__ uniq, uint64_t key_cap, uint64_t q_cap,
+__global__ void k_species_begin(EagerChunk *cs, EagerGlobal *g, uint64_t key_cap, uint64_t q_cap,
                                 uint32_t long_cap, uint64_t sp_cap) {
     unsigned long long n = cs->runs;
     if (cs->key_count > key_cap || cs->q_count > q_cap || cs->long_count > long_cap) { g->fail |= 1ull; n = 0; }
@@ -35,9 +35,9 @@ __global__ void k_species_begin(EagerChunk *cs, EagerGlobal *g, const uint64_t *
     g->sp_cursor += n;
     g->frag_total += cs->key_count;
 }
-void launch_species_begin(cudaStream_t st, EagerChunk *cs, EagerGlobal *g, const uint64_t *uniq, uint64_t key_cap, uint64_t q_cap,
+void launch_species_begin(cudaStream_t st, EagerChunk *cs, EagerGlobal *g, uint64_t key_cap, uint64_t q_cap,
                           uint32_t long_cap, uint64_t sp_cap) {
-    k_species_begin<<<1, 1, 0, st>>>(cs, g, uniq, key_cap, q_cap, long_cap, sp_cap);
+    k_species_begin<<<1, 1, 0, st>>>(cs, g, key_cap, q_cap, long_cap, sp_cap);
 }
 
 __global__ void k_decode_species_dyn(DevTranscripts tr, const uint64_t *__restrict__ uniq, const uint32_t *__restrict__ run_len, DevSpecies sp,
@@ -106,6 +106,16 @@ __constant__ double RCP_TABLE[128] = {     0.0, 1.0 / 1, 1.0 / 2, 1.0 / 3, 1.0 /
 // (lanes without a species pass live = false).  The draws of a species depend only on its own block counter, so the
 // schedule does not change the result: it is the sequence the oracle produces cycle by cycle.
 constexpr int PCR_SLOW_BATCH = 10;
+// log(k!) - Stirling, for the FP32 pre-decision of the acceptance test (the spec's FP64 det_logfact_tail decides close calls)
+__constant__ float LFT_F[10] = {0.08106146679532726f, 0.04134069595540929f, 0.02767792568499834f, 0.02079067210376509f,
+                                0.01664469118982119f, 0.01387612882307075f, 0.01189670994589177f, 0.01041126526197209f,
+                                0.009255462182712733f, 0.008330563433362871f};
+__device__ __forceinline__ float logfact_tail_f(double k) {
+    if (k <= 9.0) return LFT_F[(int)k];
+    const float inv = 1.0f / (float)(k + 1.0);
+    const float inv2 = inv * inv;
+    return inv * (0.083333333f - inv2 * (0.0027777778f - inv2 * 0.00079365079f));
+}
 #ifndef PCR_BINV_MAX
 #define PCR_BINV_MAX 10.0
 #endif
@@ -132,6 +142,8 @@ __device__ __forceinline__ uint64_t amplify(const PxStream &stream, uint64_t c, 
     for (;;) {
         const bool runnable = cyc < cycles && !pending;
         if (!__any_sync(0xffffffffu, cyc < cycles)) break;
+        bool done = false;   // this round's attempt produced the cycle's variate (committed once, at the end of the round)
+        uint64_t res = 0;
         if (runnable) {
             if (!have_setup) {
                 nd = (double)c;
@@ -153,8 +165,6 @@ __device__ __forceinline__ uint64_t amplify(const PxStream &stream, uint64_t c, 
                 have_setup = true;
             }
             const PxBlock B = stream.block(blk++);
-            bool done = false;
-            uint64_t res = 0;
             if (inv_mode) {  // BINV: walk the pmf from 0
                 double x = 0.0, px = qn, u = px_u01(px_lo64(B));
                 bool restart = false;
@@ -173,14 +183,9 @@ __device__ __forceinline__ uint64_t amplify(const PxStream &stream, uint64_t c, 
                 if (us >= 0.07 && v <= vr) { res = (uint64_t)k; done = true; }
                 else if (!(k < 0.0 || k > nd)) pending = true;
             }
-            if (done) {
-                uint64_t nc = c + (flip ? c - res : res);
-                if (nc < c) { overflow = true; cyc = cycles; }
-                else { c = nc; cyc++; have_setup = false; }
-            }
         }
         const unsigned pend = __ballot_sync(0xffffffffu, pending);
-        const unsigned run = __ballot_sync(0xffffffffu, cyc < cycles && !pending);
+        const unsigned run = __ballot_sync(0xffffffffu, !pending && (done ? cyc + 1 < cycles : cyc < cycles));
         if (pend != 0u && (__popc(pend) >= PCR_SLOW_BATCH || run == 0u)) {
             if (pending) {
                 // Acceptance test  log(v * alpha / (a/us^2 + b))  <=  ub(k).  Decision first in FP32: every logarithm of ub
@@ -192,14 +197,17 @@ __device__ __forceinline__ uint64_t amplify(const PxStream &stream, uint64_t c, 
                 const float d2 = (float)(k - mm) / (float)t2;                  // (n-m+1)/(n-k+1) - 1
                 const float d3 = (float)(r * t2 - t3) / (float)t3;             // r(n-k+1)/(k+1) - 1
                 const float f1 = (float)(mm + 0.5) * log1pf(d1), f2 = (float)(nd + 1.0) * log1pf(d2), f3 = (float)(k + 0.5) * log1pf(d3);
-                const float ft = (float)(det_logfact_tail(mm) + det_logfact_tail(nd - mm)) - (float)(det_logfact_tail(k) + det_logfact_tail(nd - k));
-                const float lvf = logf((float)(v * alpha) / (float)(a / (us * us) + b));
+                const float ft = (logfact_tail_f(mm) + logfact_tail_f(nd - mm)) - (logfact_tail_f(k) + logfact_tail_f(nd - k));
+                const float usf = (float)us;
+                const float lvf = logf((float)(v * alpha) / ((float)a / (usf * usf) + (float)b));
                 const float gap = lvf - (f1 + f2 + f3 + ft);
                 // 2e-6 * magnitudes: FP32 evaluation error (<= ~5e-7 of them); 2e-15 * coefficients: the spec's own FP64 quotient
                 // rounding (1.1e-16 per argument) amplified by the coefficients, which matters once counts pass ~1e9
+                // (the four tails, each below 0.084, and the quotient under the logarithm are evaluated in FP32 as well: a few
+                // 1e-7 absolute, inside the constant term of the margin)
                 const float margin = 2e-6f * (fabsf(f1) + fabsf(f2) + fabsf(f3) + fabsf(lvf) + 1.0f) + (float)(2e-15 * (mm + nd + k));
                 bool accept;
-                if (fabsf(gap) > margin) {
+                if (fabsf(gap) > margin && fabsf(gap) < 3.0e38f) {
                     accept = gap < 0.0f;
                 } else {  // exact acceptance test of the spec
                     double lv = det_log(v * alpha / (a / (us * us) + b));
@@ -209,14 +217,14 @@ __device__ __forceinline__ uint64_t amplify(const PxStream &stream, uint64_t c, 
                                 det_logfact_tail(nd - mm) - det_logfact_tail(k) - det_logfact_tail(nd - k);
                     accept = lv <= ub;
                 }
-                if (accept) {
-                    uint64_t res = (uint64_t)k;
-                    uint64_t nc = c + (flip ? c - res : res);
-                    if (nc < c) { overflow = true; cyc = cycles; }
-                    else { c = nc; cyc++; have_setup = false; }
-                }
+                if (accept) { res = (uint64_t)k; done = true; }
                 pending = false;
             }
+        }
+        if (done) {
+            const uint64_t nc = c + (flip ? c - res : res);
+            if (nc < c) { overflow = true; cyc = cycles; }
+            else { c = nc; cyc++; have_setup = false; }
         }
     }
     return c;

@@ -72,7 +72,7 @@ struct EagerChunk {            // one per chunk, device memory, zeroed before us
 };
 struct EagerGlobal { unsigned long long sp_cursor, frag_total, fail, pad; };
 constexpr uint32_t EAGER_BUFS = 4;        // key buffers the chunks rotate through
-void launch_species_begin(cudaStream_t st, EagerChunk *cs, EagerGlobal *g, const uint64_t *uniq, uint64_t key_cap, uint64_t q_cap,
+void launch_species_begin(cudaStream_t st, EagerChunk *cs, EagerGlobal *g, uint64_t key_cap, uint64_t q_cap,
                           uint32_t long_cap, uint64_t sp_cap);
 // sp: whole-table base pointers; the chunk's rows are cs->sp_base ...; n_bound threads are launched
 void launch_decode_species_dyn(cudaStream_t st, const DevTranscripts &tr, const uint64_t *uniq, const uint32_t *run_len, DevSpecies sp,
