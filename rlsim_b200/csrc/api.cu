@@ -173,7 +173,8 @@ int launch_prefix_range(rlsim_handle *h, uint32_t t0, uint32_t t1, cudaStream_t 
                   // opt-in (RLSIM_PREFIX_LONG=1): long transcripts summed by whole CTAs (k_prefix_long).  Measured without
                   // effect on the chunk pipeline (the one-warp tail of a launch overlaps the other streams' kernels) and
                   // 0.06 ms slower over a whole transcriptome, where enough warps are in flight to hide it.
-                  getenv("RLSIM_PREFIX_LONG") ? h->d_pfx_long.p : nullptr, (uint32_t)(h->d_pfx_long.n / 2));
+                  getenv("RLSIM_PREFIX_LONG") ? h->d_pfx_long.p : nullptr, (uint32_t)(h->d_pfx_long.n / 2),
+                  getenv("RLSIM_PREFIX_BULK") != nullptr);
     h->launches[RLSIM_T_PREFIX] += 2;
     return 0;
 }

@@ -301,14 +301,20 @@ constexpr int PFX_TILE_U32 = 32 * PFX_ROW_U32;
 // the weights from the shared-memory LUT; an 8-lane segmented shuffle scan gives the in-block sums, four shuffles the
 // block totals.  The words of the next sub-tile are requested before the current one is processed; the sums go
 // through a per-warp shared-memory tile so that every store instruction covers 512 contiguous bytes.
+// BULK: the 1 KB of fine sums a warp produces per sub-tile leaves shared memory as ONE bulk asynchronous copy
+// (cp.async.bulk.global.shared::cta, the TMA engine; SASS UBLKCP) issued by lane 0, double-buffered, instead of two 16-byte
+// stores per lane behind a transposing read of the tile.
+constexpr int PFX_BULK_TILE_U32 = 2 * PFX_SUB;   // two contiguous 256-entry buffers per warp
+template <bool BULK>
 __global__ void __launch_bounds__(PFX_THREADS, 4)
 k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, const uint32_t *__restrict__ wq_f,
          const uint32_t *__restrict__ wq_r, const unsigned long long *__restrict__ kmax_bits, uint32_t *__restrict__ Ff,
          uint32_t *__restrict__ Fr, uint64_t *__restrict__ Cf, uint64_t *__restrict__ Cr, Rec32 *__restrict__ Rf, int lut_in_smem,
          unsigned int *__restrict__ work, uint32_t *__restrict__ long_list, uint32_t long_cap) {
     extern __shared__ __align__(16) unsigned char pfx_smem[];
-    uint32_t *tile_s = reinterpret_cast<uint32_t *>(pfx_smem);                 // 8 warps x PFX_TILE_U32
-    uint32_t *lut_s = tile_s + (PFX_THREADS / 32) * PFX_TILE_U32;
+    constexpr int TILE_U32 = BULK ? PFX_BULK_TILE_U32 : PFX_TILE_U32;
+    uint32_t *tile_s = reinterpret_cast<uint32_t *>(pfx_smem);                 // 8 warps x TILE_U32
+    uint32_t *lut_s = tile_s + (PFX_THREADS / 32) * TILE_U32;
     const int reverse = blockIdx.y;
     const uint32_t *lut = reverse ? wq_r : wq_f;
     if (lut_in_smem) {
@@ -321,7 +327,8 @@ k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, c
     const uint32_t kmask = (1u << (2 * k)) - 1u;
     const uint32_t mmask = (1u << k) - 1u;
     const uint32_t lane = threadIdx.x & 31;
-    uint32_t *tile = tile_s + (threadIdx.x >> 5) * PFX_TILE_U32;
+    uint32_t *tile = tile_s + (threadIdx.x >> 5) * TILE_U32;
+    uint32_t bulk_buf = 0;  // BULK: which of the warp's two buffers the next sub-tile uses
 
     // Transcripts are short (~9 sub-tiles): the chain work counter -> transcript metadata -> first words is three dependent
     // round trips per transcript, as long as the sums themselves.  The loop is software-pipelined two deep: the counter
@@ -409,6 +416,26 @@ k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, c
                 if (i0 + lane * PFX_BLOCK < proflen) C[(i0 >> PFX_BLOCK_SHIFT) + lane + 1] = cs;
             }
             carry += (uint64_t)g0 + g1 + g2 + g3;
+            if (BULK) {
+                uint32_t *tb = tile + bulk_buf * PFX_SUB;
+                bulk_buf ^= 1u;
+                // the copy issued two sub-tiles ago has read this buffer (at most the last one may still be pending)
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                uint4 *row = reinterpret_cast<uint4 *>(tb + lane * PFX_ITEMS);
+                row[0] = make_uint4(excl + x[0], excl + x[1], excl + x[2], excl + x[3]);
+                row[1] = make_uint4(excl + x[4], excl + x[5], excl + x[6], excl + x[7]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the copy engine
+                __syncwarp();
+                if (lane == 0) {
+                    const uint32_t nsub = min((uint32_t)PFX_SUB, proflen - i0);
+                    const uint32_t bytes = ((nsub + 3u) & ~3u) * 4u;  // whole 16-byte units: up to 3 entries of the transcript's padding
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(F + i0), "r"((uint32_t)__cvta_generic_to_shared(tb)), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                continue;
+            }
             // transpose through this warp's shared-memory tile so that every store instruction covers 512 contiguous bytes
             {
                 uint4 *row = reinterpret_cast<uint4 *>(tile + lane * PFX_ROW_U32);
@@ -429,6 +456,7 @@ k_prefix(DevTranscripts tr, uint32_t t_begin, uint32_t t_end, int k, double T, c
         }
         if (use_rec && lane == 0) R[(proflen + PFX_BLOCK - 1) >> PFX_BLOCK_SHIFT].coarse = carry;  // closing record: the total
     }
+    if (BULK && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory outlives the copies
 }
 
 // Long transcripts (more than PFX_LONG profile entries; k_prefix lists them): one CTA per transcript, its 8 warps sum 8
@@ -532,7 +560,8 @@ k_prefix_long(DevTranscripts tr, int k, double T, const uint32_t *__restrict__ w
 // work: 4 counters (next transcript per strand, listed long transcripts per strand); long_list: 2 x long_cap entries or null
 void launch_prefix(cudaStream_t st, const DevTranscripts &tr, uint32_t t_begin, uint32_t t_end, int k, double T,
                    const uint32_t *wq_f, const uint32_t *wq_r, const unsigned long long *kmax_bits, uint32_t *Ff, uint32_t *Fr,
-                   uint64_t *Cf, uint64_t *Cr, Rec32 *Rf, int strands, unsigned int *work, uint32_t *long_list, uint32_t long_cap) {
+                   uint64_t *Cf, uint64_t *Cr, Rec32 *Rf, int strands, unsigned int *work, uint32_t *long_list, uint32_t long_cap,
+                   bool bulk_stores) {
     if (t_end <= t_begin) return;
     int lut_in_smem = (k <= 6);
     size_t smem = (size_t)(PFX_THREADS / 32) * PFX_TILE_U32 * 4 + (lut_in_smem ? ((size_t)4 << (2 * k)) : 16);
@@ -541,8 +570,13 @@ void launch_prefix(cudaStream_t st, const DevTranscripts &tr, uint32_t t_begin, 
     cudaMemsetAsync(work, 0, 4 * sizeof(unsigned int), st);
     dim3 grid(blocks, strands);
     if (Rf != nullptr) long_list = nullptr;  // record layout (opt-in): every transcript stays with its warp
-    k_prefix<<<grid, PFX_THREADS, smem, st>>>(tr, t_begin, t_end, k, T, wq_f, wq_r, kmax_bits, Ff, Fr, Cf, Cr, Rf, lut_in_smem, work,
-                                              long_list, long_cap);
+    if (bulk_stores && Rf == nullptr) {
+        const size_t smem_b = (size_t)(PFX_THREADS / 32) * PFX_BULK_TILE_U32 * 4 + (lut_in_smem ? ((size_t)4 << (2 * k)) : 16);
+        k_prefix<true><<<grid, PFX_THREADS, smem_b, st>>>(tr, t_begin, t_end, k, T, wq_f, wq_r, kmax_bits, Ff, Fr, Cf, Cr, Rf, lut_in_smem, work,
+                                                          long_list, long_cap);
+    } else
+    k_prefix<false><<<grid, PFX_THREADS, smem, st>>>(tr, t_begin, t_end, k, T, wq_f, wq_r, kmax_bits, Ff, Fr, Cf, Cr, Rf, lut_in_smem, work,
+                                                     long_list, long_cap);
     if (long_list != nullptr) {
         dim3 lgrid(std::min<uint32_t>(std::max<uint32_t>(long_cap, 1u), 148u * 4u), strands);
         k_prefix_long<<<lgrid, PFX_THREADS, smem, st>>>(tr, k, T, wq_f, wq_r, kmax_bits, Ff, Fr, Cf, Cr, lut_in_smem, work, long_list, long_cap);

@@ -15,7 +15,7 @@ void launch_kmer_lut(cudaStream_t st, int k, double T, double *K, unsigned long 
                      uint32_t *wq_r, unsigned int *asym);
 void launch_prefix(cudaStream_t st, const DevTranscripts &tr, uint32_t t_begin, uint32_t t_end, int k, double T, const uint32_t *wq_f, const uint32_t *wq_r,
                    const unsigned long long *kmax_bits, uint32_t *Ff, uint32_t *Fr, uint64_t *Cf, uint64_t *Cr, Rec32 *Rf, int strands,
-                   unsigned int *work, uint32_t *long_list = nullptr, uint32_t long_cap = 0);
+                   unsigned int *work, uint32_t *long_list = nullptr, uint32_t long_cap = 0, bool bulk_stores = false);
 void launch_probe_prefix(cudaStream_t st, const DevModel &m, const DevTranscripts &tr, uint32_t t, int reverse, uint64_t *out, uint32_t n);
 
 // k_fragment.cu

@@ -175,10 +175,16 @@ def test_probe_kmer_lut_vs_oracle(oracle, gpu, k, T):
         assert (want_w == 1).any(), "the low-temperature table should reach the lower clamp"
 
 
-def test_probe_prefix_and_gc_vs_oracle(oracle, gpu):
+@pytest.mark.parametrize("variant", ["default", "bulk_stores", "long_by_cta"])
+def test_probe_prefix_and_gc_vs_oracle(oracle, gpu, monkeypatch, variant):
     """a3 + a12: the priming prefix sums the searches read (forward, explicit reverse, mirrored reverse) against the
     cumulative sums of the oracle's quantised weights - windows with letters outside ACGT included - and the GC prefix
-    counts against a byte scan."""
+    counts against a byte scan.  Variants: the fine sums leaving shared memory as bulk asynchronous copies
+    (RLSIM_PREFIX_BULK), long transcripts summed by whole CTAs (RLSIM_PREFIX_LONG)."""
+    if variant == "bulk_stores":
+        monkeypatch.setenv("RLSIM_PREFIX_BULK", "1")
+    if variant == "long_by_cta":
+        monkeypatch.setenv("RLSIM_PREFIX_LONG", "1")
     args = util.parse(["-n", "3000", "-c", "3", "-si", "9", "-f", "after_prim_double"])
     names, seqs, levels = util.synth_transcriptome(12, seed=77, mean_len=900, hi=3000, total_molecules=3000)
     rng = np.random.default_rng(5)
@@ -190,6 +196,8 @@ def test_probe_prefix_and_gc_vs_oracle(oracle, gpu):
         b[10:18] = b"NNNNNNNN"  # a run longer than k: windows with no valid doublet at all
         seqs[t] = bytes(b)
     seqs[7] = seqs[7][:6]
+    seqs[5] = (seqs[5] * 40)[:256 * 3 + 6 + 1]      # profile of exactly three sub-tiles + 1 entry (poly(A) adds to it below)
+    seqs[11] = (seqs[11] * 40)[:9000]               # above the threshold of k_prefix_long
     h = util.run_gpu(gpu, args, names, seqs, levels, stages="fragment")
     pa = int(h.stats().polya_max)
     k, T = 6, 5.0
