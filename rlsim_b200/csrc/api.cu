@@ -174,7 +174,7 @@ int launch_prefix_range(rlsim_handle *h, uint32_t t0, uint32_t t1, cudaStream_t 
                   // effect on the chunk pipeline (the one-warp tail of a launch overlaps the other streams' kernels) and
                   // 0.06 ms slower over a whole transcriptome, where enough warps are in flight to hide it.
                   getenv("RLSIM_PREFIX_LONG") ? h->d_pfx_long.p : nullptr, (uint32_t)(h->d_pfx_long.n / 2),
-                  getenv("RLSIM_PREFIX_BULK") != nullptr);
+                  getenv("RLSIM_NO_PREFIX_BULK") == nullptr);  // fine sums leave shared memory as bulk asynchronous copies
     h->launches[RLSIM_T_PREFIX] += 2;
     return 0;
 }

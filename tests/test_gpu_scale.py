@@ -175,14 +175,14 @@ def test_probe_kmer_lut_vs_oracle(oracle, gpu, k, T):
         assert (want_w == 1).any(), "the low-temperature table should reach the lower clamp"
 
 
-@pytest.mark.parametrize("variant", ["default", "bulk_stores", "long_by_cta"])
+@pytest.mark.parametrize("variant", ["default", "lane_stores", "long_by_cta"])
 def test_probe_prefix_and_gc_vs_oracle(oracle, gpu, monkeypatch, variant):
     """a3 + a12: the priming prefix sums the searches read (forward, explicit reverse, mirrored reverse) against the
     cumulative sums of the oracle's quantised weights - windows with letters outside ACGT included - and the GC prefix
-    counts against a byte scan.  Variants: the fine sums leaving shared memory as bulk asynchronous copies
-    (RLSIM_PREFIX_BULK), long transcripts summed by whole CTAs (RLSIM_PREFIX_LONG)."""
-    if variant == "bulk_stores":
-        monkeypatch.setenv("RLSIM_PREFIX_BULK", "1")
+    counts against a byte scan.  Variants: the fine sums stored by the lanes instead of leaving shared memory as bulk
+    asynchronous copies (RLSIM_NO_PREFIX_BULK), long transcripts summed by whole CTAs (RLSIM_PREFIX_LONG)."""
+    if variant == "lane_stores":
+        monkeypatch.setenv("RLSIM_NO_PREFIX_BULK", "1")
     if variant == "long_by_cta":
         monkeypatch.setenv("RLSIM_PREFIX_LONG", "1")
     args = util.parse(["-n", "3000", "-c", "3", "-si", "9", "-f", "after_prim_double"])

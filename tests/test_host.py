@@ -384,3 +384,19 @@ def test_pack_bases_layout():
     assert np.array_equal(np.frombuffer(b"ACGT", dtype=np.uint8)[c][clean], b[clean]) and not c[~clean].any()
     assert _native.pack_bases(np.frombuffer(b"ACGTTGCA", dtype=np.uint8))[1] is None
     assert _native.pack_bases(np.frombuffer(b"CA", dtype=np.uint8))[0].tolist() == [1]
+
+
+def test_prefix_kernel_uses_bulk_async_copies():
+    """The fine prefix sums leave shared memory through the TMA engine (cp.async.bulk.global.shared::cta): the sm_100a SASS of
+    the built library carries UBLKCP (profiling guide: the mnemonic that proves bulk asynchronous copies)."""
+    import shutil
+    import subprocess
+    from rlsim_b200 import build
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([tool, "-sass", "-fun", "_ZN2rl8k_prefixILb1EEEvNS_14DevTranscriptsEjjidPKjS3_PKyPjS6_PmS7_PNS_5Rec32EiS6_S6_j", build.LIB],
+                          capture_output=True, text=True).stdout
+    if "UBLKCP" not in sass:  # symbol name drift: look at the whole library
+        sass = subprocess.run([tool, "-sass", build.LIB], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass
