@@ -553,7 +553,7 @@ uint64_t eager_chunk_bound(rlsim_handle *h, double sum_expr_len, double sum_expr
 
 // Sizes the buffers of the front half for `n_chunks` more chunks (largest fragment bound: `largest`, most molecules in
 // one chunk: `max_mol`): nothing of it is reallocated while chunks are in flight.
-int eager_async_reserve(rlsim_handle *h, uint32_t n_chunks, uint64_t largest, uint64_t max_mol) {
+int eager_async_reserve(rlsim_handle *h, uint32_t n_chunks, uint64_t largest, uint64_t max_mol, uint64_t total_bound) {
     // The short stages that gate the others run at high stream priority: their blocks are placed before the pending blocks
     // of the long k_fragment / k_pcr grids (measured: the radix sort of a chunk - decoupled look-back between its blocks -
     // took 0.5-0.9 ms beside those grids at equal priority, more than the whole chunk takes otherwise).
@@ -595,6 +595,22 @@ int eager_async_reserve(rlsim_handle *h, uint32_t n_chunks, uint64_t largest, ui
     const uint32_t long_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(max_mol / 16, 4096), 1u << 24);
     for (uint32_t i = 0; i < EAGER_BUFS; i++) { CK(h, h->d_elong_list[i].ensure(long_cap)); CK(h, h->d_elong_hi[i].ensure(long_cap)); }
     CK(h, h->d_warp_t.ensure(max_mol / 32 + 2));
+    {   // Back half: the species table and the dedup scratch grow on demand (eager_back), which stalls the pipeline each time.
+        // A first library is spared most of that by starting from a quarter of the bound (the bound itself is ~10x the
+        // fragments a typical model keeps); later libraries find the buffers at the size the last one needed.
+        const uint64_t need = h->eager_sp_ub + total_bound / 4, scratch = largest / 4 + 1;
+        if (ns_need(h, need) || need > h->d_sp_count0.n || scratch > h->d_keys_sorted.n || scratch > h->d_uniq.n || scratch > h->d_rle_cnt.n) {
+            CK(h, cudaStreamSynchronize(h->st_back));
+            CK(h, cudaStreamSynchronize(h->st_pcr));
+            h->pcr_in_flight = false;
+            const uint64_t used = h->eager_sp_ub;
+            CK(h, h->d_sp_count0.grow_preserve(need, used, h->st_back));
+            CK(h, h->d_sp_tr.grow_preserve(need, used, h->st_back)); CK(h, h->d_sp_start.grow_preserve(need, used, h->st_back));
+            CK(h, h->d_sp_len.grow_preserve(need, used, h->st_back)); CK(h, h->d_sp_count.grow_preserve(need, used, h->st_back));
+            CK(h, h->d_sp_eff.grow_preserve(need, used, h->st_back)); CK(h, h->d_sp_gc.grow_preserve(need, used, h->st_back));
+            CK(h, h->d_keys_sorted.ensure(scratch)); CK(h, h->d_uniq.ensure(scratch)); CK(h, h->d_rle_cnt.ensure(scratch));
+        }
+    }
     return ensure_len_eff(h);
 }
 
@@ -1180,7 +1196,7 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
     int pending_slot = -1;
     if (async) {  // the chunks' fragment bounds from one pass over lengths and expression levels
         bound.resize(n_chunks);
-        uint64_t largest = 1, max_mol = 0;
+        uint64_t largest = 1, max_mol = 0, total_bound = 0;
         for (uint32_t c = 0; c < n_chunks; c++) {
             double se = 0, sel = 0;
             uint64_t mol = 0;
@@ -1190,9 +1206,9 @@ static int add_core(rlsim_handle *h, const uint8_t *bases, const uint8_t *dev_ba
                 mol += expr[i];
             }
             bound[c] = mol ? eager_chunk_bound(h, sel, se) : 0;
-            largest = std::max(largest, bound[c]); max_mol = std::max(max_mol, mol);
+            largest = std::max(largest, bound[c]); max_mol = std::max(max_mol, mol); total_bound += bound[c];
         }
-        int rc = eager_async_reserve(h, n_chunks, largest, max_mol);
+        int rc = eager_async_reserve(h, n_chunks, largest, max_mol, total_bound);
         if (rc) return rc;
         // ingest + prefix sums of a chunk run on their own stream, beside the fragmentation of the chunk before
         if (want_prefix && (rc = ensure_lut(h))) return rc;
