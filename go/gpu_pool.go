@@ -41,6 +41,41 @@ type GpuPool struct {
 	names  []string // transcript names in input order (Frag.String needs them)
 	nrTr   int      // transcripts with a non-zero expression level (pool.go:104-106)
 	rng    string   // "philox": target lengths are drawn on the device; otherwise the host Targeter's draw is imposed
+	Packed bool     // hand the transcripts over as 2-bit codes + a mask of the letters outside ACGT (0.375 B per base on the link)
+}
+
+// packCode maps a letter to its 2-bit code; ok is false for every letter outside ACGT (it travels as a mask bit).
+func packCode(b byte) (code byte, ok bool) {
+	switch b {
+	case 'A':
+		return 0, true
+	case 'C':
+		return 1, true
+	case 'G':
+		return 2, true
+	case 'T':
+		return 3, true
+	}
+	return 0, false
+}
+
+// appendPacked appends seq at base position n to the packed arrays of rlsim_add_transcripts_packed (include/rlsim_gpu.h):
+// codes hold 4 bases per byte, low bits first; mask one bit per base, bit i&7 of byte i>>3.
+func appendPacked(codes, mask []byte, n int, seq string) ([]byte, []byte) {
+	for i := 0; i < len(seq); i, n = i+1, n+1 {
+		if n&3 == 0 {
+			codes = append(codes, 0)
+		}
+		if n&7 == 0 {
+			mask = append(mask, 0)
+		}
+		c, ok := packCode(seq[i])
+		codes[n>>2] |= c << (2 * uint(n&3))
+		if !ok {
+			mask[n>>3] |= 1 << uint(n&7)
+		}
+	}
+	return codes, mask
 }
 
 // GpuSampler implements Sampler.
@@ -228,19 +263,29 @@ func (p *GpuPool) InitTranscripts(input Inputer, tg Targeter, fg Fragmentor, tc 
 	}
 	L.PrintfV("Fragmenting transcripts and amplifying fragments:\n")
 	const batchBases = 256 << 20
-	var bases []byte
+	var bases, codes, mask []byte
+	nBases := 0
 	offs := []uint64{0}
 	var expr []uint64
 	flush := func() {
 		if len(expr) == 0 {
 			return
 		}
-		var bp *C.uint8_t
-		if len(bases) > 0 {
-			bp = (*C.uint8_t)(unsafe.Pointer(&bases[0]))
+		op, ep := (*C.uint64_t)(unsafe.Pointer(&offs[0])), (*C.uint64_t)(unsafe.Pointer(&expr[0]))
+		if p.Packed {
+			var cp, mp *C.uint8_t
+			if len(codes) > 0 {
+				cp, mp = (*C.uint8_t)(unsafe.Pointer(&codes[0])), (*C.uint8_t)(unsafe.Pointer(&mask[0]))
+			}
+			gpuFatal(p.h, C.rlsim_add_transcripts_packed(p.h, cp, mp, op, ep, C.uint32_t(len(expr))))
+		} else {
+			var bp *C.uint8_t
+			if len(bases) > 0 {
+				bp = (*C.uint8_t)(unsafe.Pointer(&bases[0]))
+			}
+			gpuFatal(p.h, C.rlsim_add_transcripts(p.h, bp, op, ep, C.uint32_t(len(expr))))
 		}
-		gpuFatal(p.h, C.rlsim_add_transcripts(p.h, bp, (*C.uint64_t)(unsafe.Pointer(&offs[0])), (*C.uint64_t)(unsafe.Pointer(&expr[0])), C.uint32_t(len(expr))))
-		bases, offs, expr = bases[:0], offs[:1], expr[:0]
+		bases, codes, mask, nBases, offs, expr = bases[:0], codes[:0], mask[:0], 0, offs[:1], expr[:0]
 	}
 	in := input.(Input)
 	for seq := input.NextSeq(); seq != nil; seq = input.NextSeq() { // input.go:106-122 without NewTranscript
@@ -255,10 +300,15 @@ func (p *GpuPool) InitTranscripts(input Inputer, tg Targeter, fg Fragmentor, tc 
 			p.nrTr++
 		}
 		p.names = append(p.names, name)
-		bases = append(bases, seq.Seq...)
-		offs = append(offs, uint64(len(bases)))
+		if p.Packed {
+			codes, mask = appendPacked(codes, mask, nBases, seq.Seq)
+		} else {
+			bases = append(bases, seq.Seq...)
+		}
+		nBases += len(seq.Seq)
+		offs = append(offs, uint64(nBases))
 		expr = append(expr, level)
-		if len(bases) >= batchBases {
+		if nBases >= batchBases {
 			flush()
 		}
 	}
