@@ -400,3 +400,25 @@ def test_prefix_kernel_uses_bulk_async_copies():
     if "UBLKCP" not in sass:  # symbol name drift: look at the whole library
         sass = subprocess.run([tool, "-sass", build.LIB], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass
+
+
+def test_streaming_host_copy_is_a_memcpy(tmp_path):
+    """csrc/hostcopy.cpp (staging of pageable caller buffers with non-temporal stores): every byte arrives, nothing beside
+    the destination is touched, for all alignments of source and destination and sizes around the vector width."""
+    import shutil
+    import subprocess
+    if not shutil.which("g++"):
+        pytest.skip("g++ not available")
+    so = str(tmp_path / "hostcopy.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", os.path.join(ROOT, "rlsim_b200", "csrc", "hostcopy.cpp"), "-o", so])
+    lib = ctypes.CDLL(so)
+    lib.rl_stream_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    rng = np.random.default_rng(1)
+    for n in (0, 1, 31, 127, 128, 4095, 4096, 4097, 4096 + 127, 100003, 1_000_001):
+        for off_s in (0, 1, 7, 31):
+            for off_d in (0, 3, 17, 32):
+                src = rng.integers(0, 256, n + 96, dtype=np.uint8)
+                dst = np.zeros(n + 96, np.uint8)
+                lib.rl_stream_copy(dst.ctypes.data + off_d, src.ctypes.data + off_s, n)
+                assert np.array_equal(dst[off_d:off_d + n], src[off_s:off_s + n]), (n, off_s, off_d)
+                assert not dst[:off_d].any() and not dst[off_d + n:].any(), (n, off_s, off_d)
