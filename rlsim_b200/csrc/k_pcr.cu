@@ -102,10 +102,15 @@ __constant__ double RCP_TABLE[128] = {     0.0, 1.0 / 1, 1.0 / 2, 1.0 / 3, 1.0 /
 // Philox block, (setup), inversion walk or BTRS squeeze test - so that code runs with (nearly) all lanes.  An attempt
 // that needs the exact BTRS acceptance test (four logarithms, ~14% of the attempts) only marks its lane PENDING; the
 // test runs when at least PCR_SLOW_BATCH lanes are pending (or nothing else can run), for all of them together.
+// (Round 1 found 10 the best batch for the FP64 test; since the test is decided in FP32 with FP32 Stirling tails the
+// waiting costs more than the lanes it gathers, and the best batch is 1: the test runs at the end of the same round.)
 // Per-species constants (p, q, p/q, log q) are hoisted out of the cycle loop.  Must be called by all 32 lanes
 // (lanes without a species pass live = false).  The draws of a species depend only on its own block counter, so the
 // schedule does not change the result: it is the sequence the oracle produces cycle by cycle.
-constexpr int PCR_SLOW_BATCH = 10;
+#ifndef PCR_SLOW_BATCH_N
+#define PCR_SLOW_BATCH_N 1   // measured 1.667 / 1.689 / 1.694 / 1.706 / 1.723 / 1.750 ms for 1 / 4 / 6 / 8 / 10 / 12 (C3)
+#endif
+constexpr int PCR_SLOW_BATCH = PCR_SLOW_BATCH_N;
 // log(k!) - Stirling, for the FP32 pre-decision of the acceptance test (the spec's FP64 det_logfact_tail decides close calls)
 __constant__ float LFT_F[10] = {0.08106146679532726f, 0.04134069595540929f, 0.02767792568499834f, 0.02079067210376509f,
                                 0.01664469118982119f, 0.01387612882307075f, 0.01189670994589177f, 0.01041126526197209f,
